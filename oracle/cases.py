@@ -1,0 +1,43 @@
+"""Parity cases shared by oracle/make_golden.py and tests/ (test infrastructure)."""
+import numpy as np
+
+# A deliberately small ViT-Res (image 224, patch 14 are fixed by the reference, so N = 257/65/17 as in
+# the real nets) that still exercises: conv stem, head dims 32/48/64, a skippable block, a BypassBlock
+# (exists=0), both SR blocks, and keep counts that are not multiples of 8.
+SMALL_DEF = ((4, 64),
+             (1, (64, 2, 32), (64, 128), 1), (1, (64, 2, 32), (64, 128), 1),
+             (3, 64, 128),
+             (1, (128, 2, 48), (128, 256), 1), (1, (128, 2, 48), (128, 256), 0), (1, (128, 2, 48), (128, 256), 1),
+             (3, 128, 256),
+             (1, (256, 4, 64), (256, 512), 1), (1, (256, 4, 64), (256, 512), 1),
+             (2, 256, 1000))
+
+
+def _blk(attn, mlp, layer=None):
+    return {'attn': np.array(attn), 'mlp': np.array(mlp), 'layer': None if layer is None else np.array(layer)}
+
+
+SMALL_SPACE = [np.array([64, 56, 44, 40]),
+               _blk([64, 32], [128, 96, 64]), _blk([64, 32], [128, 96, 64], [64, 64, 0, 0]),
+               np.array([128, 112, 100, 80]),
+               _blk([96, 48], [256, 192, 128]), _blk([96, 48], [256, 192, 128]), _blk([96, 48], [256, 192, 128], [128, 128, 0, 0]),
+               np.array([256, 224, 200, 160]),
+               _blk([256, 192, 128], [512, 384, 256]), _blk([256, 192, 128], [512, 384, 256], [256, 0]),
+               None]
+
+VIT_RES_TINY = ((4, 192),) + ((1, (192, 3, 64), (192, 768), 1),) * 4 + ((3, 192, 384),) + \
+    ((1, (384, 6, 64), (384, 1536), 1),) * 4 + ((3, 384, 768),) + \
+    ((1, (768, 12, 64), (768, 3072), 1),) * 4 + ((2, 768, 1000),)
+
+CASES = {
+    # name: net, supernet?, batch, example_per_arch, warm-up epochs, epoch, RNG seed before forward
+    'small_multi':   dict(net='small', supernet=True, batch=8, epa=2, warmup=0, epoch=0, seed=11),
+    'small_multi2':  dict(net='small', supernet=True, batch=8, epa=4, warmup=0, epoch=0, seed=12, xseed=77),
+    'small_single':  dict(net='small', supernet=True, batch=8, epa=2, warmup=0, epoch=3, seed=30007, single=True),
+    'small_hybrid':  dict(net='small', supernet=True, batch=8, epa=2, warmup=0, epoch=1, seed=10002, hybrid=True),
+    'small_warmup':  dict(net='small', supernet=True, batch=8, epa=2, warmup=5, epoch=2, seed=13),
+    'small_eval':    dict(net='small', supernet=True, batch=4, epa=2, warmup=0, epoch=0, seed=14, train=False),
+    'small_dense':   dict(net='small', supernet=False, batch=4, epa=None, warmup=0, epoch=0, seed=15),
+    # BASELINE.json configs[0]: ViT-Res-Tiny reference net, forward + loss on CPU, batch 2
+    'vit_res_tiny_b2': dict(net='vit_res_tiny', supernet=False, batch=2, epa=None, warmup=0, epoch=0, seed=16),
+}
