@@ -1,0 +1,115 @@
+/*
+ * vsx.h -- C ABI of libvsx.so: the sm_100a kernels behind the ViT-Res super-network training hot path.
+ *
+ * The reference (yilunliao/vit-search) is pure Python on PyTorch and has NO operator/FFI layer of its own:
+ * every device op is an ATen / cuBLAS / cuDNN call made from nets/*.py.  This header is therefore the
+ * boundary a maintainer would bind (ctypes stub in INTEGRATION.md); each entry point names the reference
+ * call site it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative VSX_ERR_* code; vsx_last_error() gives the text
+ *     (thread-local).  Nothing throws, allocates device memory, or synchronises the device.
+ *   - all pointers are DEVICE pointers unless named *_host; `stream` is a cudaStream_t passed as void*.
+ *   - activation storage type `dtype`: VSX_BF16 (training path) or VSX_F32 (high-precision parity path);
+ *     parameters, the residual stream, statistics, gradients of parameters and logits are always fp32.
+ *   - a call covers one SEGMENT: a run of consecutive samples that share one sub-architecture, i.e. the same
+ *     prefix keep-counts (every mask the reference can draw is a prefix mask, nets/channel_drop.py:153-157).
+ *     Callers loop over segments; pointers are pre-offset to the segment's first row.
+ *   - `ld*` are row pitches in ELEMENTS.
+ */
+#ifndef VSX_H_
+#define VSX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSX_OK 0
+#define VSX_ERR_ARG (-1)     /* invalid argument / unsupported shape */
+#define VSX_ERR_CUDA (-2)    /* CUDA runtime / driver error at launch */
+#define VSX_ERR_NO_GPU (-3)  /* no sm_100 device */
+
+#define VSX_BF16 0
+#define VSX_F32 1
+
+#define VSX_ABI_VERSION 1
+
+const char* vsx_last_error(void);
+int vsx_abi_version(void);
+/* 0 if device `dev` is an sm_100 part, VSX_ERR_NO_GPU otherwise. */
+int vsx_device_ok(int dev);
+
+/* ----------------------------------------------------------------------------------------------------
+ * Masked LayerNorm -- replaces MaskedLayerNormFunc.forward/backward + the `x * mask` re-mask
+ * (nets/masked_layer_norm.py:23-50, :55-88, :113-125) and F.layer_norm for keep == C (:121).
+ * Statistics over the first `keep` channels only; y[:, keep:] = 0.
+ * Row remap (final norm feeding cls_head / patch_head, nets/vit_sr_supernet.py:420-424): when
+ * rows_per_sample > 0, input row r = b*rows_per_sample + t is written to `y` row b*split_tokens + t when
+ * t < split_tokens, else to `y2` row b*(rows_per_sample-split_tokens) + (t-split_tokens).  Pass 0 / NULL
+ * for the plain row-to-row mapping.  mean/rstd are indexed by the input row.
+ * -------------------------------------------------------------------------------------------------- */
+int vsx_masked_ln_fwd(const float* x, long ldx, const float* gamma, const float* beta, void* y, void* y2, int dtype,
+                      long ldy, float* mean, float* rstd, int rows, int C, int keep, float eps, int rows_per_sample,
+                      int split_tokens, void* stream);
+/* g_out = (g_in ? g_in : 0) + dx on channels < keep; channels >= keep copy g_in (or 0).
+ * dgamma/dbeta (fp32 [C]) are ACCUMULATED into (atomic adds); zero them once per step. */
+int vsx_masked_ln_bwd(const void* dy, const void* dy2, int dtype, long lddy, const float* x, long ldx,
+                      const float* mean, const float* rstd, const float* gamma, const float* g_in, float* g_out,
+                      long ldg, float* dgamma, float* dbeta, int rows, int C, int keep, int rows_per_sample,
+                      int split_tokens, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------
+ * Tensor-core GEMM (tcgen05 / TMEM / TMA) -- replaces every nn.Linear on the path and its autograd:
+ * Attention.qkv / .proj (nets/supernet_blocks.py:102,118), Mlp.fc1 / .fc2 (:38,:50), the SR conv as an
+ * implicit GEMM and token Linear (nets/vit_sr_supernet.py:142,150), conv_proj (nets/patch_conv.py:72),
+ * cls_head / patch_head (nets/vit_sr_supernet.py:440,446), plus the fused elementwise tails around them
+ * (bias, GELU :39, drop-path nets/drop.py:11-26, branch mask and residual add :238-253).
+ *
+ *   D[M,N] = epilogue( sum_{t<terms} A_t[M,K] * B_t[N,K]^T )      bf16 operands, fp32 accumulate
+ *
+ * terms == 3 is the split-bf16 ("bf16x3") high-precision mode: A = A_hi + A_lo, B = B_hi + B_lo and the three
+ * products hi*hi, lo*hi, hi*lo accumulate into the same TMEM tile.
+ * Layout of an operand: VSX_KMAJOR  -- stored [M or N rows, K contiguous]      (forward: x and W)
+ *                       VSX_MNMAJOR -- stored [K rows, M or N contiguous]      (dgrad: W; wgrad: dY and x)
+ * -------------------------------------------------------------------------------------------------- */
+#define VSX_KMAJOR 0
+#define VSX_MNMAJOR 1
+
+#define VSX_EPI_STORE 0     /* out = acc + bias                                   (out: bf16|f32)            */
+#define VSX_EPI_GELU 1      /* out = acc + bias (pre-activation), out2 = gelu(out) (bf16|f32)                */
+#define VSX_EPI_RESIDUAL 2  /* out = aux + [n < n_keep] * row_scale[sample] * (acc + bias)   (f32, aux f32)  */
+#define VSX_EPI_GELUGRAD 3  /* out = acc * gelu'(aux)                             (out, aux: bf16|f32)       */
+#define VSX_EPI_ATOMIC 4    /* out += acc (fp32 atomics; weight gradients, split-K over the reduction)      */
+
+typedef struct vsx_gemm_desc {
+  const void* a[3]; /* bf16 A operand per term */
+  const void* b[3]; /* bf16 B operand per term */
+  int terms;        /* 1 or 3 */
+  long lda, ldb;
+  int a_layout, b_layout;
+  int M, N, K;      /* N, K are the COMPUTED extents (kept prefix); reads beyond them are zero-filled by TMA */
+  int epilogue;
+  int out_dtype;    /* VSX_BF16 | VSX_F32 */
+  void* out;
+  long ldo;
+  void* out2;
+  long ldo2;
+  int n_out;        /* columns written, N <= n_out <= ldo: [N, n_out) is zero-filled (RESIDUAL: copied from aux) */
+  const float* bias; /* [>= N] or NULL */
+  const void* aux;
+  long ld_aux;
+  const float* row_scale; /* RESIDUAL: per-sample scale (drop-path keep / keep_prob x layer mask) or NULL (= 1) */
+  int rows_per_sample;    /* RESIDUAL: rows of one sample (tokens)                                           */
+  int n_keep;             /* RESIDUAL: columns < n_keep receive the branch                                    */
+  int split_k;            /* ATOMIC: number of reduction splits (>= 1)                                        */
+} vsx_gemm_desc;
+
+int vsx_gemm(const vsx_gemm_desc* d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSX_H_ */

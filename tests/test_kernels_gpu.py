@@ -1,0 +1,188 @@
+"""GPU parity of the individual kernels (through the C ABI) against the CPU oracle / fp64 torch math."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit_res_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope='module')
+def ops():
+    from vit_search_b200 import _lib, ops
+    _lib.check(_lib.lib().vsx_device_ok(0))
+    return ops
+
+
+# ---------------------------------------------------------------------------------------------- masked LN
+@pytest.mark.parametrize('C,keep', [(64, 64), (64, 44), (256, 160), (320, 220), (1024, 704), (1280, 1280)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_masked_ln(ops, C, keep, dtype):
+    g = torch.Generator().manual_seed(C + keep)
+    B, N = 3, 37
+    rows = B * N
+    x = torch.randn(B, N, C, generator=g) * O.prefix_mask([keep] * B, C, torch.float32) + 0.3
+    x = x * O.prefix_mask([keep] * B, C, torch.float32)
+    w = 1 + 0.1 * torch.randn(C, generator=g)
+    b = 0.1 * torch.randn(C, generator=g)
+    go = torch.randn(B, N, C, generator=g)
+    gin = torch.randn(B, N, C, generator=g)
+    y_ref = O.masked_layer_norm(x.double(), w.double(), b.double(), [keep] * B)
+    m = O.prefix_mask([keep] * B, C, torch.float64)
+    go_q = go.to(dtype).double()
+    gx_ref, gw_ref, gb_ref = O.masked_layer_norm_backward(go_q * m, x.double(), w.double(), [keep] * B)
+    gx_ref = gx_ref * m + gin.double()        # masked channels carry only the incoming gradient
+
+    xd, wd, bd = x.cuda().view(rows, C), w.cuda(), b.cuda()
+    y = torch.full((rows, C), float('nan'), device='cuda', dtype=dtype)
+    mean = torch.empty(rows, device='cuda')
+    rstd = torch.empty(rows, device='cuda')
+    ops.masked_ln_fwd(xd, C, wd, bd, y, C, mean, rstd, rows, C, keep, 1e-6)
+    tol = 1e-5 if dtype == torch.float32 else 6e-3
+    assert rel(y.view(B, N, C), y_ref) < tol
+    assert torch.all(y[:, keep:] == 0)
+
+    gout = torch.full((rows, C), float('nan'), device='cuda')
+    dgam = torch.zeros(C, device='cuda')
+    dbet = torch.zeros(C, device='cuda')
+    ops.masked_ln_bwd(go.to(dtype).cuda().view(rows, C), C, xd, C, mean, rstd, wd, gin.cuda().view(rows, C), gout, C,
+                      dgam, dbet, rows, C, keep)
+    assert rel(gout.view(B, N, C), gx_ref) < 2e-5
+    assert rel(dgam, gw_ref) < 2e-5
+    assert rel(dbet, gb_ref) < 2e-5
+
+
+def test_masked_ln_golden(ops):
+    """The reference's own outputs (tests/golden/functions.npz) with per-sample keeps -> one segment per sample."""
+    import os
+    G = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'functions.npz'))
+    keep = G['ln_keep'].tolist()
+    B, N, C = 6, 5, 48
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, N, C, generator=g) * O.prefix_mask(keep, C, torch.float32)
+    wt = 1 + 0.1 * torch.randn(C, generator=g)
+    bs = 0.1 * torch.randn(C, generator=g)
+    go = torch.randn(B, N, C, generator=g)
+    xd = x.cuda().view(B * N, C)
+    y = torch.empty(B * N, C, device='cuda')
+    mean = torch.empty(B * N, device='cuda')
+    rstd = torch.empty(B * N, device='cuda')
+    gout = torch.empty(B * N, C, device='cuda')
+    dg = torch.zeros(C, device='cuda')
+    db = torch.zeros(C, device='cuda')
+    god = go.cuda().view(B * N, C)
+    for s in range(B):
+        ops.masked_ln_fwd(xd, C, wt.cuda(), bs.cuda(), y, C, mean, rstd, N, C, keep[s], 1e-6,
+                          x_off=s * N * C, y_off=s * N * C, stat_off=s * N)
+        ops.masked_ln_bwd(god, C, xd, C, mean, rstd, wt.cuda(), None, gout, C, dg, db, N, C, keep[s],
+                          dy_off=s * N * C, x_off=s * N * C, stat_off=s * N, g_off=s * N * C)
+    m = O.prefix_mask(keep, C, torch.float32)
+    assert rel(y.view(B, N, C), torch.from_numpy(G['ln_y'])) < 1e-5
+    assert rel(gout.view(B, N, C).cpu() * m, torch.from_numpy(G['ln_gx']) * m) < 2e-5   # masked lanes are dead gradients
+    assert rel(dg, torch.from_numpy(G['ln_gw'])) < 2e-5
+    assert rel(db, torch.from_numpy(G['ln_gb'])) < 2e-5
+
+
+# ---------------------------------------------------------------------------------------------- GEMM
+def _split(t):
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
+def _mk(M, N, K, seed):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(M, K, generator=g), torch.randn(N, K, generator=g) * 0.05
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 64), (256, 128, 128), (300, 200, 96), (1028, 576, 256), (514, 768, 160),
+                                   (130, 1000, 1024), (64, 44, 220)])
+def test_gemm_store_kmajor(ops, M, N, K):
+    Kp = (K + 7) // 8 * 8 + 8            # pitch > K: junk beyond K must be clipped by the TMA descriptor
+    A, W = _mk(M, N, Kp, M + N + K)
+    bias = torch.randn(N)
+    Ab, Wb = A.to(torch.bfloat16), W.to(torch.bfloat16)
+    ref = Ab[:, :K].double() @ Wb[:, :K].double().t() + bias.double()
+    n_out = (N + 7) // 8 * 8
+    for odt, tol in ((torch.float32, 1e-5), (torch.bfloat16, 5e-3)):
+        out = torch.full((M, n_out), float('nan'), device='cuda', dtype=odt)
+        ops.gemm(Ab.cuda(), Wb.cuda(), Kp, Kp, M, N, K, ops.EPI_STORE, out, n_out, n_out=n_out, bias=bias.cuda())
+        torch.cuda.synchronize()
+        assert rel(out[:, :N], ref) < tol, (M, N, K, odt)
+        assert torch.all(out[:, N:] == 0)
+
+
+def test_gemm_split3_precision(ops):
+    """bf16x3 split mode must recover ~fp32 accuracy (the high-precision parity path)."""
+    M, N, K = 384, 256, 512
+    A, W = _mk(M, N, K, 5)
+    ref = A.double() @ W.double().t()
+    (ah, al), (wh, wl) = _split(A), _split(W)
+    out = torch.empty(M, N, device='cuda')
+    ops.gemm((ah.cuda(), al.cuda()), (wh.cuda(), wl.cuda()), K, K, M, N, K, ops.EPI_STORE, out, N)
+    assert rel(out, ref) < 3e-5
+    out1 = torch.empty(M, N, device='cuda')
+    ops.gemm(ah.cuda(), wh.cuda(), K, K, M, N, K, ops.EPI_STORE, out1, N)
+    assert 1e-4 < rel(out1, ref) < 1e-2      # plain bf16 is visibly worse: the 3 terms really are accumulated
+
+
+@pytest.mark.parametrize('M,N,K', [(256, 128, 128), (300, 136, 200), (1028, 256, 576)])
+def test_gemm_dgrad_layout(ops, M, N, K):
+    """dX[M,N] = dY[M,K] @ W[K,N]: A K-major, B MN-major (W stored [K rows, N contiguous])."""
+    g = torch.Generator().manual_seed(M)
+    dY = torch.randn(M, K, generator=g).to(torch.bfloat16)
+    W = (torch.randn(K, N, generator=g) * 0.05).to(torch.bfloat16)
+    ref = dY.double() @ W.double()
+    out = torch.empty(M, N, device='cuda')
+    ops.gemm(dY.cuda(), W.cuda(), K, N, M, N, K, ops.EPI_STORE, out, N, b_layout=ops.MNMAJOR)
+    assert rel(out, ref) < 1e-5
+
+
+@pytest.mark.parametrize('R,Nw,Kw,split', [(256, 128, 128, 1), (1000, 200, 136, 3), (4112, 576, 256, 8), (771, 44, 60, 2)])
+def test_gemm_wgrad_layout(ops, R, Nw, Kw, split):
+    """dW[Nw,Kw] += dY[R,Nw]^T @ X[R,Kw]: both operands MN-major, split-K atomics."""
+    g = torch.Generator().manual_seed(R)
+    dY = torch.randn(R, Nw + 8, generator=g).to(torch.bfloat16)      # pitch > extent: exercises TMA OOB clipping
+    X = torch.randn(R, Kw + 16, generator=g).to(torch.bfloat16)
+    ref = dY[:, :Nw].double().t() @ X[:, :Kw].double()
+    out = torch.ones(Nw, Kw, device='cuda')
+    ops.gemm(dY.cuda(), X.cuda(), Nw + 8, Kw + 16, Nw, Kw, R, ops.EPI_ATOMIC, out, Kw, a_layout=ops.MNMAJOR,
+             b_layout=ops.MNMAJOR, split_k=split)
+    assert rel(out - 1, ref) < 2e-5
+
+
+def test_gemm_epilogues(ops):
+    M, N, K, C = 514, 200, 128, 256      # 2 samples x 257 rows
+    A, W = _mk(M, N, K, 9)
+    Ab, Wb = A.to(torch.bfloat16), W.to(torch.bfloat16)
+    bias = torch.randn(N) * 0.1
+    acc = Ab.double() @ Wb.double().t() + bias.double()
+    # GELU: out = pre-activation, out2 = gelu, zero fill up to n_out
+    pre = torch.full((M, 256), float('nan'), device='cuda', dtype=torch.bfloat16)
+    act = torch.full((M, 256), float('nan'), device='cuda', dtype=torch.bfloat16)
+    ops.gemm(Ab.cuda(), Wb.cuda(), K, K, M, N, K, ops.EPI_GELU, pre, 256, n_out=256, out2=act, ldo2=256, bias=bias.cuda())
+    assert rel(pre[:, :N], acc) < 5e-3 and rel(act[:, :N], torch.nn.functional.gelu(acc)) < 6e-3
+    assert torch.all(pre[:, N:] == 0) and torch.all(act[:, N:] == 0)
+    # GELUGRAD: out = acc * gelu'(aux)
+    u = torch.randn(M, 256)
+    out = torch.full((M, 256), float('nan'), device='cuda')
+    ops.gemm(Ab.cuda(), Wb.cuda(), K, K, M, N, K, ops.EPI_GELUGRAD, out, 256, n_out=256, aux=u.cuda(), ld_aux=256)
+    ud = u[:, :N].double().requires_grad_(True)
+    torch.nn.functional.gelu(ud).sum().backward()
+    assert rel(out[:, :N], (acc - bias.double()) * ud.grad) < 1e-5 and torch.all(out[:, N:] == 0)
+    # RESIDUAL: out = res + [n < keep] * scale[sample] * (acc + bias); columns >= N copy the residual
+    res = torch.randn(M, C)
+    scale = torch.tensor([1.25, 0.0])
+    keep = 160
+    out = torch.full((M, C), float('nan'), device='cuda')
+    ops.gemm(Ab.cuda(), Wb.cuda(), K, K, M, N, K, ops.EPI_RESIDUAL, out, C, n_out=C, bias=bias.cuda(), aux=res.cuda(),
+             ld_aux=C, row_scale=scale.cuda(), rows_per_sample=257, n_keep=keep)
+    ref = res.double().clone()
+    ref[:, :keep] += scale.double().repeat_interleave(257).view(-1, 1) * acc[:, :keep]
+    assert rel(out, ref) < 1e-5

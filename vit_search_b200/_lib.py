@@ -1,0 +1,66 @@
+"""ctypes binding of libvsx.so (the C ABI declared in include/vsx.h).
+
+The library is the product: there is NO fallback.  If it is missing, stale against the header, or the device is
+not an sm_100 part, loading / calling fails loudly.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libvsx.so')
+ABI_VERSION = 1
+
+BF16, F32 = 0, 1
+KMAJOR, MNMAJOR = 0, 1
+EPI_STORE, EPI_GELU, EPI_RESIDUAL, EPI_GELUGRAD, EPI_ATOMIC = 0, 1, 2, 3, 4
+
+_p, _i, _l, _f = C.c_void_p, C.c_int, C.c_long, C.c_float
+
+
+class GemmDesc(C.Structure):
+    _fields_ = [('a', _p * 3), ('b', _p * 3), ('terms', _i), ('lda', _l), ('ldb', _l), ('a_layout', _i), ('b_layout', _i),
+                ('M', _i), ('N', _i), ('K', _i), ('epilogue', _i), ('out_dtype', _i), ('out', _p), ('ldo', _l),
+                ('out2', _p), ('ldo2', _l), ('n_out', _i), ('bias', _p), ('aux', _p), ('ld_aux', _l),
+                ('row_scale', _p), ('rows_per_sample', _i), ('n_keep', _i), ('split_k', _i)]
+
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/vsx.h one to one
+SIGNATURES = {
+    'vsx_last_error': [],
+    'vsx_abi_version': [],
+    'vsx_device_ok': [_i],
+    'vsx_masked_ln_fwd': [_p, _l, _p, _p, _p, _p, _i, _l, _p, _p, _i, _i, _i, _f, _i, _i, _p],
+    'vsx_masked_ln_bwd': [_p, _p, _i, _l, _p, _l, _p, _p, _p, _p, _p, _l, _p, _p, _i, _i, _i, _i, _i, _p],
+    'vsx_gemm': [C.POINTER(GemmDesc), _p],
+}
+_RESTYPES = {'vsx_last_error': C.c_char_p}
+
+_lib = None
+
+
+class VsxError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libvsx.so once.  Raises if it has not been built (python -m vit_search_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VsxError('libvsx.so not found at %s -- build it with `python -m vit_search_b200.build`; '
+                           'there is no CPU or PyTorch fallback for the hot path' % LIB_PATH)
+        h = C.CDLL(LIB_PATH)
+        for name, argtypes in SIGNATURES.items():
+            fn = getattr(h, name)          # AttributeError if the library lacks a declared symbol
+            fn.argtypes = argtypes
+            fn.restype = _RESTYPES.get(name, _i)
+        if h.vsx_abi_version() != ABI_VERSION:
+            raise VsxError('libvsx.so ABI version %d does not match the Python binding (%d); rebuild'
+                           % (h.vsx_abi_version(), ABI_VERSION))
+        _lib = h
+    return _lib
+
+
+def check(rc):
+    if rc != 0:
+        raise VsxError('libvsx error %d: %s' % (rc, lib().vsx_last_error().decode()))

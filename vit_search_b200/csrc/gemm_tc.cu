@@ -1,0 +1,350 @@
+// tcgen05 / TMEM / TMA GEMM with fused epilogues for the ViT-Res super-network hot path (sm_100a).
+//
+//   D[M,N] = epilogue( sum_t A_t[M,K] * B_t[N,K]^T ),  bf16 operands, fp32 accumulation in tensor memory.
+//
+// One CTA computes one 128x128 output tile.  Warp roles (192 threads):
+//   warp 0      TMA producer : cp.async.bulk.tensor loads of 128x64 A / B boxes (128B swizzle) into a
+//                              STAGES-deep shared-memory ring, completion on "full" mbarriers
+//   warp 1      MMA issuer   : one elected thread issues tcgen05.mma (128x128x16, cta_group::1); tcgen05.commit
+//                              releases ring slots ("empty" mbarriers) and finally signals the epilogue
+//   warps 2..5  epilogue     : tcgen05.ld of the fp32 accumulator (one TMEM lane = one output row per thread),
+//                              fused bias / GELU / drop-path scale / prefix mask / residual / GELU' / atomic add
+// Two CTAs fit per SM (96 KB shared memory, 128 TMEM columns each), so one tile's epilogue overlaps the other's
+// main loop.  Both operand layouts are supported through the shared-memory descriptors (K-major for the forward
+// pass, MN-major for dgrad / wgrad), so no transposed copies of activations or weights are ever made.
+//
+// Replaces: nn.Linear forward/backward at nets/supernet_blocks.py:38,50,102,118 and the elementwise tails at
+// :39 (GELU), :238-253 (mask, residual), nets/drop.py:11-26 (drop-path scale); see include/vsx.h.
+#include "common.cuh"
+
+namespace vsx {
+
+namespace {
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 3;
+constexpr int STAGE_A = BM * BK * 2;
+constexpr int STAGE_B = BN * BK * 2;
+constexpr int TMEM_COLS = 128;
+constexpr int GEMM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * (STAGE_A + STAGE_B) + 1024 /*align*/ + 128 /*barriers*/;
+
+struct TmapPack {
+  CUtensorMap a[3];
+  CUtensorMap b[3];
+};
+
+struct GemmArgs {
+  int M, N, K, num_kb, terms, a_mn, b_mn, n_out, split_k;
+  void* out;
+  long ldo;
+  void* out2;
+  long ldo2;
+  const float* bias;
+  const void* aux;
+  long ld_aux;
+  const float* row_scale;
+  int rows_per_sample, n_keep;
+};
+
+// Shared-memory matrix descriptor (tcgen05), 128B swizzle.  K-major: rows of 128 B, 8-row groups 1024 B apart (SBO).
+// MN-major: 64-element (128 B) MN atoms, k-rows 128 B apart, 8-row groups SBO = 1024 B, MN atoms LBO = BK*128 B apart.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, bool mn_major) {
+  const uint64_t lbo = mn_major ? (uint64_t)((BK * 128) >> 4) : 0ull;
+  const uint64_t sbo = 1024 >> 4;
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// Instruction descriptor, kind::f16: D=f32, A=B=bf16, M=128, N=128.
+__device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+template <typename OutT>
+__device__ __forceinline__ void store32(OutT* dst, const float (&v)[32], int n, int n_out);
+template <>
+__device__ __forceinline__ void store32<float>(float* dst, const float (&v)[32], int n, int n_out) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (n + 4 * i < n_out) st4(dst + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+}
+template <>
+__device__ __forceinline__ void store32<bf16>(bf16* dst, const float (&v)[32], int n, int n_out) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (n + 8 * i < n_out) {
+      uint4 r;
+      r.x = pack_bf16(v[8 * i], v[8 * i + 1]);
+      r.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+      r.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+      r.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+      *reinterpret_cast<uint4*>(dst + 8 * i) = r;
+    }
+}
+template <typename T>
+__device__ __forceinline__ void load32(const T* src, float (&v)[32], int n, int n_lim) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n + 4 * i < n_lim) t = ld4(src + 4 * i);
+    v[4 * i] = t.x, v[4 * i + 1] = t.y, v[4 * i + 2] = t.z, v[4 * i + 3] = t.w;
+  }
+}
+
+// One output row `m`, 32 consecutive columns starting at `n`.
+template <int EPI, typename OutT>
+__device__ __forceinline__ void epilogue_row(const GemmArgs& g, int m, int n, float (&v)[32]) {
+  if (EPI == VSX_EPI_ATOMIC) {
+    float* dst = reinterpret_cast<float*>(g.out) + (long)m * g.ldo + n;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = n + 4 * i;
+      if (c + 3 < g.N) {
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * i), "f"(v[4 * i]), "f"(v[4 * i + 1]),
+                     "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
+                     : "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c + j < g.N) atomicAdd(dst + 4 * i + j, v[4 * i + j]);
+      }
+    }
+    return;
+  }
+  if (g.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n + j < g.N) v[j] += __ldg(g.bias + n + j);
+  }
+  if (EPI == VSX_EPI_STORE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n + j >= g.N) v[j] = 0.f;
+    store32<OutT>(reinterpret_cast<OutT*>(g.out) + (long)m * g.ldo + n, v, n, g.n_out);
+  } else if (EPI == VSX_EPI_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n + j >= g.N) v[j] = 0.f;
+    store32<OutT>(reinterpret_cast<OutT*>(g.out) + (long)m * g.ldo + n, v, n, g.n_out);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);   // gelu(0) = 0 keeps the zero fill
+    store32<OutT>(reinterpret_cast<OutT*>(g.out2) + (long)m * g.ldo2 + n, v, n, g.n_out);
+  } else if (EPI == VSX_EPI_RESIDUAL) {
+    const float s = g.row_scale != nullptr ? __ldg(g.row_scale + m / g.rows_per_sample) : 1.0f;
+    float r[32];
+    load32<float>(reinterpret_cast<const float*>(g.aux) + (long)m * g.ld_aux + n, r, n, g.n_out);
+    const int lim = g.n_keep < g.N ? g.n_keep : g.N;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) r[j] += (n + j < lim) ? s * v[j] : 0.f;
+    store32<float>(reinterpret_cast<float*>(g.out) + (long)m * g.ldo + n, r, n, g.n_out);
+  } else if (EPI == VSX_EPI_GELUGRAD) {
+    float u[32];
+    load32<OutT>(reinterpret_cast<const OutT*>(g.aux) + (long)m * g.ld_aux + n, u, n, g.n_out);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = (n + j < g.N) ? v[j] * gelu_grad_f(u[j]) : 0.f;
+    store32<OutT>(reinterpret_cast<OutT*>(g.out) + (long)m * g.ldo + n, v, n, g.n_out);
+  }
+}
+
+template <int EPI, typename OutT>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_constant__ TmapPack maps, const GemmArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;   // 128B-swizzle atoms need 1024-byte alignment
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t sA = base, sB = base + STAGES * STAGE_A;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (STAGE_A + STAGE_B));
+  const uint32_t bar0 = base + STAGES * (STAGE_A + STAGE_B);
+  // bars: [0,S) full, [S,2S) empty, [2S] accumulator ready; then the TMEM base address slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
+  const uint32_t acc_bar = bar0 + 8u * (2 * STAGES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+
+  int kb_begin = 0, kb_end = g.num_kb;
+  if (EPI == VSX_EPI_ATOMIC) {
+    const int per = (g.num_kb + g.split_k - 1) / g.split_k;
+    kb_begin = blockIdx.z * per;
+    kb_end = min(g.num_kb, kb_begin + per);
+    if (kb_begin >= kb_end) return;   // uniform for the whole CTA
+  }
+  const int nkb = kb_end - kb_begin;
+  const int iters = nkb * g.terms;
+  const bool has_mma = (n0 < g.N) && iters > 0;
+
+  if (warp == 0 && lane == 0) {
+    for (int t = 0; t < g.terms; ++t) {
+      tma_prefetch_desc(&maps.a[t]);
+      tma_prefetch_desc(&maps.b[t]);
+    }
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < STAGES; ++s) {
+        mbar_init(full_bar(s), 1);
+        mbar_init(empty_bar(s), 1);
+      }
+      mbar_init(acc_bar, 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (has_mma && warp == 0 && lane == 0) {
+    // ---------------- TMA producer ----------------
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(empty_bar(s), ph ^ 1u);
+      const int term = it / nkb, k0 = (kb_begin + it % nkb) * BK;
+      const uint32_t dA = sA + s * STAGE_A, dB = sB + s * STAGE_B, fb = full_bar(s);
+      mbar_expect_tx(fb, STAGE_A + STAGE_B);
+      if (!g.a_mn) {
+        tma_load_2d(dA, &maps.a[term], fb, k0, m0);
+      } else {
+        tma_load_2d(dA, &maps.a[term], fb, m0, k0);
+        tma_load_2d(dA + BK * 128, &maps.a[term], fb, m0 + 64, k0);
+      }
+      if (!g.b_mn) {
+        tma_load_2d(dB, &maps.b[term], fb, k0, n0);
+      } else {
+        tma_load_2d(dB, &maps.b[term], fb, n0, k0);
+        tma_load_2d(dB + BK * 128, &maps.b[term], fb, n0 + 64, k0);
+      }
+    }
+  } else if (has_mma && warp == 1 && lane == 0) {
+    // ---------------- MMA issuer ----------------
+    const uint32_t idesc = make_idesc(g.a_mn != 0, g.b_mn != 0);
+    const uint32_t a_step = g.a_mn ? (UMMA_K * 128) : (UMMA_K * 2);   // bytes per 16-wide k step
+    const uint32_t b_step = g.b_mn ? (UMMA_K * 128) : (UMMA_K * 2);
+    for (int it = 0; it < iters; ++it) {
+      const int s = it % STAGES;
+      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+      mbar_wait(full_bar(s), ph);
+      tc_fence_after();
+      const uint32_t aA = sA + s * STAGE_A, aB = sB + s * STAGE_B;
+#pragma unroll
+      for (int k = 0; k < BK / UMMA_K; ++k) {
+        umma_bf16(tmem_base, make_smem_desc(aA + k * a_step, g.a_mn != 0), make_smem_desc(aB + k * b_step, g.b_mn != 0),
+                  idesc, (it | k) != 0 ? 1u : 0u);
+      }
+      umma_commit(empty_bar(s));   // slot reusable once these MMAs have read it
+    }
+    umma_commit(acc_bar);          // accumulator complete
+  } else if (warp >= 2) {
+    // ---------------- epilogue ----------------
+    const int q = warp & 3;        // TMEM lane quarter this warp may access
+    const int m = m0 + q * 32 + lane;
+    if (has_mma) {
+      mbar_wait(acc_bar, 0);
+      tc_fence_after();
+    }
+    for (int c = 0; c < BN; c += 32) {
+      if (n0 + c >= g.n_out) break;
+      float v[32];
+      if (has_mma) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+      }
+      if (m < g.M) epilogue_row<EPI, OutT>(g, m, n0 + c, v);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int EPI, typename OutT>
+int launch(const TmapPack& maps, const GemmArgs& g, dim3 grid, cudaStream_t st) {
+  static bool configured = false;   // benign race: attribute set is idempotent
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    if (e != cudaSuccess) {
+      set_error("vsx_gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      return VSX_ERR_CUDA;
+    }
+    configured = true;
+  }
+  gemm_tc_kernel<EPI, OutT><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(maps, g);
+  return check_launch("vsx_gemm");
+}
+
+}  // namespace
+}  // namespace vsx
+
+using namespace vsx;
+
+extern "C" int vsx_gemm(const vsx_gemm_desc* d, void* stream) {
+  VSX_REQUIRE(d != nullptr, "vsx_gemm: null descriptor");
+  VSX_REQUIRE(d->terms == 1 || d->terms == 3, "vsx_gemm: terms must be 1 or 3 (got %d)", d->terms);
+  VSX_REQUIRE(d->M > 0 && d->N >= 0 && d->K >= 0, "vsx_gemm: bad extents M=%d N=%d K=%d", d->M, d->N, d->K);
+  VSX_REQUIRE(d->lda % 8 == 0 && d->ldb % 8 == 0, "vsx_gemm: operand pitches must be multiples of 8 elements (lda=%ld ldb=%ld)", d->lda, d->ldb);
+  VSX_REQUIRE(d->out != nullptr && d->n_out >= d->N && d->n_out <= d->ldo, "vsx_gemm: need N <= n_out <= ldo (N=%d n_out=%d ldo=%ld)", d->N, d->n_out, d->ldo);
+  const bool f32 = d->out_dtype == VSX_F32;
+  VSX_REQUIRE(d->out_dtype == VSX_F32 || d->out_dtype == VSX_BF16, "vsx_gemm: bad out_dtype %d", d->out_dtype);
+  if (d->epilogue != VSX_EPI_ATOMIC)
+    VSX_REQUIRE(d->n_out % (f32 ? 4 : 8) == 0 && d->ldo % (f32 ? 4 : 8) == 0, "vsx_gemm: n_out/ldo must be multiples of %d (n_out=%d ldo=%ld)", f32 ? 4 : 8, d->n_out, d->ldo);
+  if (d->n_out == 0) return VSX_OK;
+
+  GemmArgs g;
+  g.M = d->M, g.N = d->N, g.K = d->K, g.num_kb = ceil_div(d->K, BK), g.terms = d->terms;
+  g.a_mn = d->a_layout == VSX_MNMAJOR, g.b_mn = d->b_layout == VSX_MNMAJOR;
+  g.n_out = d->n_out, g.split_k = d->split_k < 1 ? 1 : d->split_k;
+  g.out = d->out, g.ldo = d->ldo, g.out2 = d->out2, g.ldo2 = d->ldo2, g.bias = d->bias, g.aux = d->aux, g.ld_aux = d->ld_aux;
+  g.row_scale = d->row_scale, g.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1, g.n_keep = d->n_keep;
+
+  TmapPack maps;
+  if (d->N > 0 && d->K > 0) {
+    for (int t = 0; t < d->terms; ++t) {
+      VSX_REQUIRE(d->a[t] != nullptr && d->b[t] != nullptr, "vsx_gemm: null operand for term %d", t);
+      int rc;
+      if (!g.a_mn) rc = make_tmap_2d(&maps.a[t], d->a[t], (uint64_t)d->K, (uint64_t)d->M, (uint64_t)d->lda, BK, BM);
+      else         rc = make_tmap_2d(&maps.a[t], d->a[t], (uint64_t)d->M, (uint64_t)d->K, (uint64_t)d->lda, 64, BK);
+      if (rc) return rc;
+      if (!g.b_mn) rc = make_tmap_2d(&maps.b[t], d->b[t], (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldb, BK, BN);
+      else         rc = make_tmap_2d(&maps.b[t], d->b[t], (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->ldb, 64, BK);
+      if (rc) return rc;
+    }
+  } else {
+    g.N = 0;   // nothing to contract: epilogue-only tiles
+    memset(&maps, 0, sizeof(maps));
+  }
+  dim3 grid(ceil_div(d->M, BM), ceil_div(d->n_out, BN), 1);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  switch (d->epilogue) {
+    case VSX_EPI_STORE:
+      return f32 ? launch<VSX_EPI_STORE, float>(maps, g, grid, st) : launch<VSX_EPI_STORE, bf16>(maps, g, grid, st);
+    case VSX_EPI_GELU:
+      VSX_REQUIRE(d->out2 != nullptr && d->ldo2 >= d->n_out, "vsx_gemm: GELU epilogue needs out2");
+      return f32 ? launch<VSX_EPI_GELU, float>(maps, g, grid, st) : launch<VSX_EPI_GELU, bf16>(maps, g, grid, st);
+    case VSX_EPI_RESIDUAL:
+      VSX_REQUIRE(f32 && d->aux != nullptr, "vsx_gemm: RESIDUAL epilogue is fp32 and needs aux");
+      return launch<VSX_EPI_RESIDUAL, float>(maps, g, grid, st);
+    case VSX_EPI_GELUGRAD:
+      VSX_REQUIRE(d->aux != nullptr, "vsx_gemm: GELUGRAD epilogue needs aux (pre-activation)");
+      return f32 ? launch<VSX_EPI_GELUGRAD, float>(maps, g, grid, st) : launch<VSX_EPI_GELUGRAD, bf16>(maps, g, grid, st);
+    case VSX_EPI_ATOMIC:
+      VSX_REQUIRE(f32, "vsx_gemm: ATOMIC epilogue accumulates into fp32");
+      if (g.N == 0) return VSX_OK;
+      grid.y = ceil_div(d->N, BN);
+      grid.z = g.split_k = (g.split_k > g.num_kb ? (g.num_kb > 0 ? g.num_kb : 1) : g.split_k);
+      g.n_out = d->N;
+      return launch<VSX_EPI_ATOMIC, float>(maps, g, grid, st);
+    default:
+      set_error("vsx_gemm: unknown epilogue %d", d->epilogue);
+      return VSX_ERR_ARG;
+  }
+}

@@ -1,0 +1,259 @@
+// Masked LayerNorm forward / backward (HBM-bound; one warp per row, 16-byte loads, shuffle reductions).
+//
+// Restates MaskedLayerNormFunc (nets/masked_layer_norm.py:23-50 forward, :55-88 backward) plus the `x * mask`
+// at :124 for PREFIX masks: statistics use the first `keep` channels only (mean = sum/keep, var = E[x^2]-mean^2,
+// eps inside the sqrt), output channels >= keep are zero.  keep == C is torch's F.layer_norm (:121).
+// The reference spends ~15 ATen passes over [B,N,C] per direction; here each direction is one pass:
+//   forward : read x fp32 (4 B/ch), write y bf16 (2 B/ch) + 8 B/row of statistics
+//   backward: read dy (2 B) + x (4 B) + g_in (4 B), write g_out (4 B); dgamma/dbeta via per-CTA partials + atomics
+#include "common.cuh"
+
+namespace vsx {
+namespace {
+
+constexpr int LN_WARPS = 8;
+
+// Row remap for the final norm (see vsx.h): returns the output row and selects y vs y2.
+__device__ __forceinline__ long remap_row(long r, int rps, int split, bool& second) {
+  second = false;
+  if (rps <= 0) return r;
+  const long b = r / rps;
+  const int t = (int)(r - b * rps);
+  if (t < split) return b * split + t;
+  second = true;
+  return b * (rps - split) + (t - split);
+}
+
+// NV = number of float4 chunks per lane: lane owns columns (i*32 + lane)*4 .. +3 for i < NV.
+template <int NV, typename T>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, T* __restrict__ y, T* __restrict__ y2,
+                                                                long ldy, float* __restrict__ mean, float* __restrict__ rstd,
+                                                                int rows, int C, int keep, float eps, int rps, int split) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float inv_keep = 1.0f / (float)keep;
+  for (long r = (long)blockIdx.x * LN_WARPS + warp; r < rows; r += (long)gridDim.x * LN_WARPS) {
+    const float* xr = x + r * ldx;
+    float4 v[NV];
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < keep) {
+        v[i] = ld4(xr + c);
+        if (c + 1 >= keep) v[i].y = 0.f;
+        if (c + 2 >= keep) v[i].z = 0.f;
+        if (c + 3 >= keep) v[i].w = 0.f;
+      }
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      ss += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    const float mu = s * inv_keep;
+    const float var = ss * inv_keep - mu * mu;
+    const float rs = 1.0f / sqrtf(var + eps);
+    if (lane == 0) {
+      mean[r] = mu;
+      rstd[r] = rs;
+    }
+    bool second;
+    const long orow = remap_row(r, rps, split, second);
+    T* yr = (second ? y2 : y) + orow * ldy;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < C) {
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < keep) {
+          const float4 gm = ld4(gamma + c), bt = ld4(beta + c);
+          o.x = gm.x * ((v[i].x - mu) * rs) + bt.x;
+          o.y = (c + 1 < keep) ? gm.y * ((v[i].y - mu) * rs) + bt.y : 0.f;
+          o.z = (c + 2 < keep) ? gm.z * ((v[i].z - mu) * rs) + bt.z : 0.f;
+          o.w = (c + 3 < keep) ? gm.w * ((v[i].w - mu) * rs) + bt.w : 0.f;
+        }
+        st4(yr + c, o);
+      }
+    }
+  }
+}
+
+template <int NV, typename T>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ dy2, long lddy,
+                                                                const float* __restrict__ x, long ldx, const float* __restrict__ mean,
+                                                                const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                                const float* __restrict__ g_in, float* __restrict__ g_out, long ldg,
+                                                                float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int C,
+                                                                int keep, int rps, int split) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float inv_keep = 1.0f / (float)keep;
+  float4 gm[NV], ag[NV], ab[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = (i * 32 + lane) * 4;
+    gm[i] = (c < keep) ? ld4(gamma + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (long r = (long)blockIdx.x * LN_WARPS + warp; r < rows; r += (long)gridDim.x * LN_WARPS) {
+    bool second;
+    const long irow = remap_row(r, rps, split, second);
+    const T* dyr = (second ? dy2 : dy) + irow * lddy;
+    const float* xr = x + r * ldx;
+    const float mu = mean[r], rs = rstd[r];
+    float4 d[NV], z[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      d[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < keep) {
+        d[i] = ld4(dyr + c);
+        const float4 xv = ld4(xr + c);
+        z[i] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        if (c + 1 >= keep) d[i].y = 0.f, z[i].y = 0.f;
+        if (c + 2 >= keep) d[i].z = 0.f, z[i].z = 0.f;
+        if (c + 3 >= keep) d[i].w = 0.f, z[i].w = 0.f;
+        // parameter gradients: g_gamma = sum dy*z, g_beta = sum dy   (masked_layer_norm.py:78-86)
+        ag[i].x += d[i].x * z[i].x, ag[i].y += d[i].y * z[i].y, ag[i].z += d[i].z * z[i].z, ag[i].w += d[i].w * z[i].w;
+        ab[i].x += d[i].x, ab[i].y += d[i].y, ab[i].z += d[i].z, ab[i].w += d[i].w;
+        // dz = dy * gamma
+        d[i].x *= gm[i].x, d[i].y *= gm[i].y, d[i].z *= gm[i].z, d[i].w *= gm[i].w;
+      }
+      s1 += (d[i].x + d[i].y) + (d[i].z + d[i].w);
+      s2 += (d[i].x * z[i].x + d[i].y * z[i].y) + (d[i].z * z[i].z + d[i].w * z[i].w);
+    }
+    s1 = warp_sum(s1) * inv_keep;   // mean(dz)/p
+    s2 = warp_sum(s2) * inv_keep;   // mean(z*dz)/p
+    float* go = g_out + r * ldg;
+    const float* gi = g_in != nullptr ? g_in + r * ldg : nullptr;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < C) {
+        float4 o = gi != nullptr ? ld4(gi + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < keep) {
+          o.x += (d[i].x - s1 - z[i].x * s2) * rs;
+          if (c + 1 < keep) o.y += (d[i].y - s1 - z[i].y * s2) * rs;
+          if (c + 2 < keep) o.z += (d[i].z - s1 - z[i].z * s2) * rs;
+          if (c + 3 < keep) o.w += (d[i].w - s1 - z[i].w * s2) * rs;
+        }
+        st4(go + c, o);
+      }
+    }
+  }
+  // cross-warp reduction of the per-lane column partials, then one atomic per column per CTA
+  __shared__ float4 red[LN_WARPS][32];
+  for (int pass = 0; pass < 2; ++pass) {
+    float* dst = pass == 0 ? dgamma : dbeta;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      red[warp][lane] = pass == 0 ? ag[i] : ab[i];
+      __syncthreads();
+      if (warp == 0) {
+        float4 t = red[0][lane];
+#pragma unroll
+        for (int w = 1; w < LN_WARPS; ++w) {
+          const float4 u = red[w][lane];
+          t.x += u.x, t.y += u.y, t.z += u.z, t.w += u.w;
+        }
+        const int c = (i * 32 + lane) * 4;
+        if (c < keep) atomicAdd(dst + c, t.x);
+        if (c + 1 < keep) atomicAdd(dst + c + 1, t.y);
+        if (c + 2 < keep) atomicAdd(dst + c + 2, t.z);
+        if (c + 3 < keep) atomicAdd(dst + c + 3, t.w);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+int ln_grid(int rows, int per_sm) {
+  const int need = ceil_div(rows, LN_WARPS);
+  const int cap = num_sms() * per_sm;
+  return need < cap ? need : cap;
+}
+
+template <typename T>
+int ln_fwd_dispatch(const float* x, long ldx, const float* gamma, const float* beta, void* y, void* y2, long ldy, float* mean,
+                    float* rstd, int rows, int C, int keep, float eps, int rps, int split, cudaStream_t st) {
+  const int nv = ceil_div(C, 128);
+  const int grid = ln_grid(rows, 8);
+#define VSX_LN_F(NV)                                                                                                        \
+  case NV:                                                                                                                  \
+    ln_fwd_kernel<NV, T><<<grid, LN_WARPS * 32, 0, st>>>(x, ldx, gamma, beta, (T*)y, (T*)y2, ldy, mean, rstd, rows, C, keep, \
+                                                          eps, rps, split);                                                  \
+    break;
+  switch (nv) {
+    VSX_LN_F(1) VSX_LN_F(2) VSX_LN_F(3) VSX_LN_F(4) VSX_LN_F(5) VSX_LN_F(6) VSX_LN_F(7) VSX_LN_F(8) VSX_LN_F(9) VSX_LN_F(10)
+    default:
+      set_error("vsx_masked_ln_fwd: C=%d exceeds the supported 1280 channels", C);
+      return VSX_ERR_ARG;
+  }
+#undef VSX_LN_F
+  return check_launch("vsx_masked_ln_fwd");
+}
+
+template <typename T>
+int ln_bwd_dispatch(const void* dy, const void* dy2, long lddy, const float* x, long ldx, const float* mean, const float* rstd,
+                    const float* gamma, const float* g_in, float* g_out, long ldg, float* dgamma, float* dbeta, int rows, int C,
+                    int keep, int rps, int split, cudaStream_t st) {
+  const int nv = ceil_div(C, 128);
+  const int grid = ln_grid(rows, 4);
+#define VSX_LN_B(NV)                                                                                                      \
+  case NV:                                                                                                                \
+    ln_bwd_kernel<NV, T><<<grid, LN_WARPS * 32, 0, st>>>((const T*)dy, (const T*)dy2, lddy, x, ldx, mean, rstd, gamma, g_in, \
+                                                          g_out, ldg, dgamma, dbeta, rows, C, keep, rps, split);          \
+    break;
+  switch (nv) {
+    VSX_LN_B(1) VSX_LN_B(2) VSX_LN_B(3) VSX_LN_B(4) VSX_LN_B(5) VSX_LN_B(6) VSX_LN_B(7) VSX_LN_B(8) VSX_LN_B(9) VSX_LN_B(10)
+    default:
+      set_error("vsx_masked_ln_bwd: C=%d exceeds the supported 1280 channels", C);
+      return VSX_ERR_ARG;
+  }
+#undef VSX_LN_B
+  return check_launch("vsx_masked_ln_bwd");
+}
+
+}  // namespace
+}  // namespace vsx
+
+using namespace vsx;
+
+extern "C" int vsx_masked_ln_fwd(const float* x, long ldx, const float* gamma, const float* beta, void* y, void* y2, int dtype,
+                                 long ldy, float* mean, float* rstd, int rows, int C, int keep, float eps, int rows_per_sample,
+                                 int split_tokens, void* stream) {
+  VSX_REQUIRE(rows >= 0 && C > 0 && keep > 0 && keep <= C, "vsx_masked_ln_fwd: need 0 < keep <= C (keep=%d C=%d)", keep, C);
+  VSX_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "vsx_masked_ln_fwd: C and pitches must be multiples of 4");
+  VSX_REQUIRE(rows_per_sample <= 0 || (y2 != nullptr && split_tokens > 0 && split_tokens < rows_per_sample),
+              "vsx_masked_ln_fwd: row remap needs y2 and 0 < split_tokens < rows_per_sample");
+  if (rows == 0) return VSX_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == VSX_BF16)
+    return ln_fwd_dispatch<bf16>(x, ldx, gamma, beta, y, y2, ldy, mean, rstd, rows, C, keep, eps, rows_per_sample, split_tokens, st);
+  if (dtype == VSX_F32)
+    return ln_fwd_dispatch<float>(x, ldx, gamma, beta, y, y2, ldy, mean, rstd, rows, C, keep, eps, rows_per_sample, split_tokens, st);
+  set_error("vsx_masked_ln_fwd: bad dtype %d", dtype);
+  return VSX_ERR_ARG;
+}
+
+extern "C" int vsx_masked_ln_bwd(const void* dy, const void* dy2, int dtype, long lddy, const float* x, long ldx, const float* mean,
+                                 const float* rstd, const float* gamma, const float* g_in, float* g_out, long ldg, float* dgamma,
+                                 float* dbeta, int rows, int C, int keep, int rows_per_sample, int split_tokens, void* stream) {
+  VSX_REQUIRE(rows >= 0 && C > 0 && keep > 0 && keep <= C, "vsx_masked_ln_bwd: need 0 < keep <= C (keep=%d C=%d)", keep, C);
+  VSX_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0 && ldg % 4 == 0, "vsx_masked_ln_bwd: C and pitches must be multiples of 4");
+  VSX_REQUIRE(rows_per_sample <= 0 || (dy2 != nullptr && split_tokens > 0 && split_tokens < rows_per_sample),
+              "vsx_masked_ln_bwd: row remap needs dy2 and 0 < split_tokens < rows_per_sample");
+  if (rows == 0) return VSX_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == VSX_BF16)
+    return ln_bwd_dispatch<bf16>(dy, dy2, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, dgamma, dbeta, rows, C, keep,
+                                 rows_per_sample, split_tokens, st);
+  if (dtype == VSX_F32)
+    return ln_bwd_dispatch<float>(dy, dy2, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, dgamma, dbeta, rows, C, keep,
+                                  rows_per_sample, split_tokens, st);
+  set_error("vsx_masked_ln_bwd: bad dtype %d", dtype);
+  return VSX_ERR_ARG;
+}

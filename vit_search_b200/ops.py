@@ -1,0 +1,74 @@
+"""Tensor-level wrappers over the C ABI (include/vsx.h).  PyTorch is used for device memory and streams only.
+
+Every function takes CUDA tensors, computes raw pointers (+ element offsets for segment / column windows) and
+calls into libvsx.so on the current stream.  No arithmetic happens here.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, KMAJOR, MNMAJOR, EPI_STORE, EPI_GELU, EPI_RESIDUAL, EPI_GELUGRAD, EPI_ATOMIC  # noqa: F401
+
+_DT = {torch.bfloat16: BF16, torch.float32: F32}
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t, offset=0):
+    """Device pointer of element `offset` of tensor t (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda, 'libvsx operates on CUDA tensors only (no CPU fallback)'
+    return t.data_ptr() + offset * t.element_size()
+
+
+def dt(t):
+    return _DT[t.dtype]
+
+
+# ------------------------------------------------------------------------------------------------ layer norm
+def masked_ln_fwd(x, ldx, gamma, beta, y, ldy, mean, rstd, rows, C_, keep, eps, x_off=0, y_off=0, stat_off=0,
+                  y2=None, rows_per_sample=0, split_tokens=0):
+    _lib.check(_lib.lib().vsx_masked_ln_fwd(
+        _ptr(x, x_off), ldx, _ptr(gamma), _ptr(beta), _ptr(y, y_off), _ptr(y2), dt(y), ldy,
+        _ptr(mean, stat_off), _ptr(rstd, stat_off), rows, C_, keep, eps, rows_per_sample, split_tokens, _stream()))
+
+
+def masked_ln_bwd(dy, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, dgamma, dbeta, rows, C_, keep,
+                  dy_off=0, x_off=0, stat_off=0, g_off=0, dy2=None, rows_per_sample=0, split_tokens=0):
+    _lib.check(_lib.lib().vsx_masked_ln_bwd(
+        _ptr(dy, dy_off), _ptr(dy2), dt(dy), lddy, _ptr(x, x_off), ldx, _ptr(mean, stat_off), _ptr(rstd, stat_off),
+        _ptr(gamma), _ptr(g_in, g_off), _ptr(g_out, g_off), ldg, _ptr(dgamma), _ptr(dbeta), rows, C_, keep,
+        rows_per_sample, split_tokens, _stream()))
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+def gemm(a, b, lda, ldb, M, N, K, epilogue, out, ldo, *, a_off=0, b_off=0, out_off=0, a_layout=KMAJOR,
+         b_layout=KMAJOR, n_out=None, out2=None, ldo2=0, out2_off=0, bias=None, bias_off=0, aux=None, ld_aux=0,
+         aux_off=0, row_scale=None, row_scale_off=0, rows_per_sample=1, n_keep=0, split_k=1):
+    """a, b: a bf16 tensor, or a tuple (hi, lo) of bf16 tensors for the split-bf16 (3-term) high-precision mode."""
+    d = _lib.GemmDesc()
+    if isinstance(a, (tuple, list)):
+        (ah, al), (bh, bl) = a, b
+        terms = [(ah, bh), (al, bh), (ah, bl)]
+    else:
+        terms = [(a, b)]
+    for t, (ta, tb) in enumerate(terms):
+        assert ta.dtype == torch.bfloat16 and tb.dtype == torch.bfloat16
+        d.a[t] = _ptr(ta, a_off)
+        d.b[t] = _ptr(tb, b_off)
+    d.terms = len(terms)
+    d.lda, d.ldb, d.a_layout, d.b_layout = lda, ldb, a_layout, b_layout
+    d.M, d.N, d.K = M, N, K
+    d.epilogue, d.out_dtype = epilogue, dt(out)
+    d.out, d.ldo = _ptr(out, out_off), ldo
+    d.out2, d.ldo2 = _ptr(out2, out2_off), ldo2
+    d.n_out = N if n_out is None else n_out
+    d.bias = _ptr(bias, bias_off)
+    d.aux, d.ld_aux = _ptr(aux, aux_off), ld_aux
+    d.row_scale = _ptr(row_scale, row_scale_off)
+    d.rows_per_sample, d.n_keep, d.split_k = rows_per_sample, n_keep, split_k
+    _lib.check(_lib.lib().vsx_gemm(C.byref(d), _stream()))
