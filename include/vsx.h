@@ -109,6 +109,35 @@ typedef struct vsx_gemm_desc {
 
 int vsx_gemm(const vsx_gemm_desc* d, void* stream);
 
+/* ----------------------------------------------------------------------------------------------------
+ * Attention core -- replaces q@k^T*scale, softmax, attn@v, the head transpose/reshape and the head ChannelDrop
+ * (nets/supernet_blocks.py:103-112) and their autograd.  qkv: [batch*tokens, 3*heads*head_dim] with features
+ * ordered (3, heads, head_dim) (:102); o: [batch*tokens, heads*head_dim]; lse: fp32 [batch, heads, tokens]
+ * (log-sum-exp of the scaled scores, saved for the backward).  Heads >= heads_keep are not computed: their o /
+ * dqkv slices are written as zeros.  impl: VSX_ATTN_IMPL_AUTO picks the tensor-core kernel when the shape is
+ * supported; VSX_ATTN_IMPL_FP32 forces the fp32-math kernel (always used for dtype VSX_F32).
+ * -------------------------------------------------------------------------------------------------- */
+#define VSX_ATTN_IMPL_AUTO 0
+#define VSX_ATTN_IMPL_FP32 1
+int vsx_attn_fwd(const void* qkv, void* o, float* lse, int dtype, int batch, int tokens, int heads, int head_dim,
+                 int heads_keep, float scale, int impl, void* stream);
+int vsx_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int dtype, int batch,
+                 int tokens, int heads, int head_dim, int heads_keep, float scale, int impl, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------
+ * Elementwise helpers around the GEMMs.
+ * vsx_split_bf16     : hi = bf16(src), lo = bf16(src - hi) (lo may be NULL: plain cast).  Operand preparation for
+ *                      vsx_gemm (weights every step; activations only in the fp32 parity mode).
+ * vsx_scale_mask_cast: out[m,n] = n < n_keep ? g[m,n] * row_scale[m / rows_per_sample] : 0 -- the gradient of
+ *                      `x + mask * drop_path(f)` w.r.t. f (nets/supernet_blocks.py:243-253, nets/drop.py:25);
+ *                      also the forward of a stand-alone ChannelDrop (nets/channel_drop.py:80-81).
+ * vsx_colsum         : out[c] += sum_r x[r,c]  (bias gradients of every nn.Linear).
+ * -------------------------------------------------------------------------------------------------- */
+int vsx_split_bf16(const float* src, long lds, void* hi, void* lo, long ldd, int rows, int cols, void* stream);
+int vsx_scale_mask_cast(const float* g, long ldg, const float* row_scale, int rows_per_sample, int n_keep, void* out,
+                        int dtype, long ldo, int rows, int cols, void* stream);
+int vsx_colsum(const void* x, int dtype, long ldx, int rows, int cols, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,74 @@
+"""GPU parity of one transformer Block (both halves, forward + backward) against the CPU oracle."""
+import pytest
+import torch
+
+from oracle import vit_res_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+CASES = [
+    # C, H, D, F, N, per-sample keeps: embed, attn, layer, mlp, drop-path scales (attn, mlp)
+    dict(C=64, H=2, D=32, F=128, N=257, embed=[64, 64, 44, 44], attn=[64, 64, 32, 32], layer=None, mlp=[128, 128, 96, 64]),
+    dict(C=128, H=2, D=48, F=256, N=65, embed=[128, 112, 100, 80], attn=[96, 48, 96, 48], layer=[128, 0, 128, 128],
+         mlp=[256, 192, 128, 256], layer_in=[128, 128, 0, 128], dp=([1.25, 0., 1.25, 1.25], [0., 1.25, 1.25, 1.25])),
+    dict(C=256, H=4, D=64, F=512, N=17, embed=None, attn=None, layer=None, mlp=None),
+    dict(C=256, H=4, D=64, F=512, N=17, embed=[256, 200, 160, 160, 224, 224], attn=[256, 192, 128, 128, 64, 64], layer=None,
+         mlp=[512, 384, 256, 256, 512, 512]),
+]
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+@pytest.mark.parametrize('ci', range(len(CASES)))
+def test_block_parity(ci, prec):
+    from vit_search_b200 import core
+    from vit_search_b200.nets import Block
+    c = CASES[ci]
+    C, H, D, F, N = c['C'], c['H'], c['D'], c['F'], c['N']
+    B = len(c['embed']) if c['embed'] is not None else 3
+    shapes = {'norm1.weight': (C,), 'norm1.bias': (C,), 'attn.qkv.weight': (3 * H * D, C), 'attn.qkv.bias': (3 * H * D,),
+              'attn.proj.weight': (C, H * D), 'attn.proj.bias': (C,), 'norm2.weight': (C,), 'norm2.bias': (C,),
+              'mlp.fc1.weight': (F, C), 'mlp.fc1.bias': (F,), 'mlp.fc2.weight': (C, F), 'mlp.fc2.bias': (C,)}
+    w = O.keyed_fill(shapes, seed=ci)
+    for k in w:                                   # larger weights than init so the branches matter
+        if k.endswith('weight') and w[k].ndim == 2:
+            w[k] = w[k] * 3
+    g = torch.Generator().manual_seed(100 + ci)
+    x = torch.randn(B, N, C, generator=g)
+    if c['embed'] is not None:
+        x = x * O.prefix_mask(c['embed'], C, torch.float32)
+    gout = torch.randn(B, N, C, generator=g)
+    keeps = {k: c[k] for k in ('attn', 'layer', 'mlp') if c.get(k) is not None}
+    dp = c.get('dp')
+
+    # oracle in fp64
+    p = {'b.' + k: v.double().requires_grad_(True) for k, v in w.items()}
+    xo = x.double().requires_grad_(True)
+    dpk = None
+    if dp is not None:
+        dpk = ([1.0 if v > 0 else 0.0 for v in dp[0]], [1.0 if v > 0 else 0.0 for v in dp[1]])
+    yo, _, cur_o = O.block(xo, p, 'b.', H, D, c['embed'], c.get('layer_in'), keeps, dpk, 0.2 if dp is not None else 0.0)
+    yo.backward(gout.double())
+
+    blk = Block(C, H, D, F).cuda()
+    blk.load_state_dict(w)
+    xd = x.cuda().requires_grad_(True)
+    dpt = None if dp is None else torch.tensor(dp, dtype=torch.float32).cuda().contiguous()
+    with core.precision(prec):
+        y, cur = blk.forward_keeps(xd, c['embed'], c.get('layer_in'), keeps, dpt, 0)
+        y.backward(gout.cuda())
+    torch.cuda.synchronize()
+    assert cur == cur_o
+    tol = 2e-5 if prec == 'fp32' else 2e-2
+    errs = {'y': rel(y, yo)}
+    m = O.prefix_mask(c['embed'], C, torch.float64) if c['embed'] is not None else 1.0
+    errs['gx'] = rel(xd.grad.double().cpu() * m, xo.grad * m)       # gradients on masked input lanes are dead
+    for k, prm in blk.named_parameters():
+        errs[k] = rel(prm.grad, p['b.' + k].grad)
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, (prec, bad, errs)

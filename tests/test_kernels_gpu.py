@@ -148,11 +148,12 @@ def test_gemm_dgrad_layout(ops, M, N, K):
 def test_gemm_wgrad_layout(ops, R, Nw, Kw, split):
     """dW[Nw,Kw] += dY[R,Nw]^T @ X[R,Kw]: both operands MN-major, split-K atomics."""
     g = torch.Generator().manual_seed(R)
-    dY = torch.randn(R, Nw + 8, generator=g).to(torch.bfloat16)      # pitch > extent: exercises TMA OOB clipping
-    X = torch.randn(R, Kw + 16, generator=g).to(torch.bfloat16)
+    lda, ldb = (Nw + 7) // 8 * 8 + 8, (Kw + 7) // 8 * 8 + 16     # pitch > extent: exercises TMA OOB clipping
+    dY = torch.randn(R, lda, generator=g).to(torch.bfloat16)
+    X = torch.randn(R, ldb, generator=g).to(torch.bfloat16)
     ref = dY[:, :Nw].double().t() @ X[:, :Kw].double()
     out = torch.ones(Nw, Kw, device='cuda')
-    ops.gemm(dY.cuda(), X.cuda(), Nw + 8, Kw + 16, Nw, Kw, R, ops.EPI_ATOMIC, out, Kw, a_layout=ops.MNMAJOR,
+    ops.gemm(dY.cuda(), X.cuda(), lda, ldb, Nw, Kw, R, ops.EPI_ATOMIC, out, Kw, a_layout=ops.MNMAJOR,
              b_layout=ops.MNMAJOR, split_k=split)
     assert rel(out - 1, ref) < 2e-5
 

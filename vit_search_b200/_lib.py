@@ -32,6 +32,11 @@ SIGNATURES = {
     'vsx_masked_ln_fwd': [_p, _l, _p, _p, _p, _p, _i, _l, _p, _p, _i, _i, _i, _f, _i, _i, _p],
     'vsx_masked_ln_bwd': [_p, _p, _i, _l, _p, _l, _p, _p, _p, _p, _p, _l, _p, _p, _i, _i, _i, _i, _i, _p],
     'vsx_gemm': [C.POINTER(GemmDesc), _p],
+    'vsx_attn_fwd': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p],
+    'vsx_attn_bwd': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p],
+    'vsx_split_bf16': [_p, _l, _p, _p, _l, _i, _i, _p],
+    'vsx_scale_mask_cast': [_p, _l, _p, _i, _i, _p, _i, _l, _i, _i, _p],
+    'vsx_colsum': [_p, _i, _l, _i, _i, _p, _p],
 }
 _RESTYPES = {'vsx_last_error': C.c_char_p}
 

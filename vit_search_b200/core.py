@@ -1,0 +1,402 @@
+"""Host-side orchestration of the kernels: precision modes, weight operand cache, segments, and the fused
+half-block forward/backward routines (attention half, MLP half) used by nets/supernet_blocks.py.
+
+All arithmetic happens in libvsx.so (see ops.py).  torch is used for allocation, streams and autograd wiring.
+"""
+import math
+from contextlib import contextmanager
+
+import torch
+
+from . import ops
+
+# ------------------------------------------------------------------------------------------------ precision
+# 'bf16' : activations stored in bf16, single-term bf16 tensor-core GEMMs (the training path; bench.py).
+# 'fp32' : activations stored in fp32, every GEMM operand split into bf16 hi+lo and contracted as three
+#          tensor-core terms (hi*hi + lo*hi + hi*lo), attention in fp32 math.  Same kernels, ~1e-5 relative
+#          accuracy -- the path that proves parity with the fp32 reference to the north-star's 1e-3.
+_precision = 'bf16'
+
+
+def set_precision(p):
+    global _precision
+    assert p in ('bf16', 'fp32')
+    _precision = p
+
+
+def get_precision():
+    return _precision
+
+
+@contextmanager
+def precision(p):
+    old = get_precision()
+    set_precision(p)
+    try:
+        yield
+    finally:
+        set_precision(old)
+
+
+def act_dtype():
+    return torch.bfloat16 if _precision == 'bf16' else torch.float32
+
+
+def require_cuda(t, what):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError('%s: vit_search_b200 runs on a B200 through libvsx.so only -- got a %s tensor; there is no CPU '
+                           'fallback (the CPU restatement lives in oracle/ and is test-only)' % (what, getattr(t, 'device', type(t))))
+
+
+# ------------------------------------------------------------------------------------------------ operand preparation
+class _WeightCache:
+    """bf16 (hi[, lo]) copies of fp32 parameters, keyed on storage pointer + version counter, so a weight is cast
+    once per optimizer step and never after `rewiring` re-allocates it (nets/supernet_blocks.py:55-71,123-161)."""
+
+    def __init__(self):
+        self.entries = {}
+
+    def get(self, w, layout=None):
+        key = (id(w), layout)
+        tag = (w.data_ptr(), w._version, _precision, tuple(w.shape))
+        e = self.entries.get(key)
+        if e is not None and e[0] == tag:
+            return e[1]
+        src = w.detach()
+        if layout == 'ohwi':                       # conv weight [O, I, kh, kw] -> [O, kh*kw*I]
+            src = src.permute(0, 2, 3, 1)
+        src = src.reshape(src.shape[0], -1).contiguous()
+        rows, cols = src.shape
+        colsp = (cols + 7) // 8 * 8                # TMA needs 16-byte row pitch
+        hi = torch.zeros(rows, colsp, device=w.device, dtype=torch.bfloat16) if colsp != cols else \
+            torch.empty(rows, cols, device=w.device, dtype=torch.bfloat16)
+        lo = torch.zeros_like(hi) if _precision == 'fp32' else None
+        ops.split_bf16(src, cols, hi, lo, colsp, rows, cols) if cols % 4 == 0 else _split_slow(src, hi, lo)
+        val = (hi, lo) if lo is not None else hi
+        self.entries[key] = (tag, val)
+        return val
+
+    def clear(self):
+        self.entries.clear()
+
+
+def _split_slow(src, hi, lo):
+    cols = src.shape[1]
+    hi[:, :cols] = src.to(torch.bfloat16)
+    if lo is not None:
+        lo[:, :cols] = (src - hi[:, :cols].float()).to(torch.bfloat16)
+
+
+weights = _WeightCache()
+
+
+def ld_of(op):
+    return (op[0] if isinstance(op, tuple) else op).shape[-1]
+
+
+class _ActOperands:
+    """Per-call cache of activation GEMM operands.  bf16 mode: the tensor itself.  fp32 mode: hi/lo bf16 buffers of the
+    same [rows, ld] shape, filled segment by segment right before use."""
+
+    def __init__(self):
+        self.buf = {}
+
+    def get(self, t, ld, row0, rows, cols):
+        if t.dtype == torch.bfloat16:
+            return t
+        key = id(t)
+        if key not in self.buf:
+            self.buf[key] = (torch.empty(t.shape, device=t.device, dtype=torch.bfloat16),
+                             torch.empty(t.shape, device=t.device, dtype=torch.bfloat16), set())
+        hi, lo, done = self.buf[key]
+        c4 = (cols + 3) // 4 * 4
+        if (row0, rows, c4) not in done:
+            ops.split_bf16(t, ld, hi, lo, ld, rows, min(c4, ld), src_off=row0 * ld, dst_off=row0 * ld)
+            done.add((row0, rows, c4))
+        return (hi, lo)
+
+    def invalidate(self, t):
+        self.buf.pop(id(t), None)
+
+
+def split_k_for(m_rows, n_cols, red_rows):
+    tiles = math.ceil(m_rows / 128) * math.ceil(n_cols / 128)
+    kb = max(1, math.ceil(red_rows / 64))
+    return max(1, min(kb, (2 * 148) // max(tiles, 1)))
+
+
+def up8(n):
+    return (n + 7) // 8 * 8
+
+
+# ------------------------------------------------------------------------------------------------ segments
+class Seg:
+    """A run of consecutive samples sharing one sub-architecture in this layer."""
+    __slots__ = ('b0', 'b1', 'ek', 'ik', 'ck', 'active')
+
+    def __init__(self, b0, b1, ek, ik, ck, active=True):
+        self.b0, self.b1 = b0, b1
+        self.ek = ek          # embedding channels kept (input width of the branch)
+        self.ik = ik          # inner width kept: heads*head_dim for attention, hidden channels for the MLP
+        self.ck = ck          # channels of the branch output that reach the residual (layer & embed mask)
+        self.active = active  # False: the whole block is dropped for these samples
+
+    def key(self):
+        return (self.ek, self.ik, self.ck, self.active)
+
+
+def make_segments(batch, width, embed_keep, inner_keep, inner_full, cur_keep):
+    """Per-sample keep lists (or None) -> list of Seg with maximal runs of identical keeps."""
+    segs = []
+    for b in range(batch):
+        ek = width if embed_keep is None else int(embed_keep[b])
+        ik = inner_full if inner_keep is None else int(inner_keep[b])
+        ck = width if cur_keep is None else int(cur_keep[b])
+        act = ck > 0 and ik > 0 and ek > 0
+        if segs and segs[-1].key() == (ek, ik, ck, act):
+            segs[-1].b1 = b + 1
+        else:
+            segs.append(Seg(b, b + 1, ek, ik, ck, act))
+    return segs
+
+
+class HalfMeta:
+    """Static description of one half-block call."""
+
+    def __init__(self, kind, segs, tokens, width, heads=0, head_dim=0, hidden=0, row_scale=None, scale_off=0,
+                 pre_norm=True, residual=True, eps=1e-6):
+        self.kind, self.segs, self.N, self.C = kind, segs, tokens, width
+        self.H, self.D, self.F = heads, head_dim, hidden
+        self.row_scale, self.scale_off = row_scale, scale_off
+        self.pre_norm, self.residual, self.eps = pre_norm, residual, eps
+
+
+# ------------------------------------------------------------------------------------------------ attention half
+def _pre(meta, x2, g, b, xn, mean, rstd, s, r0, rows):
+    C = meta.C
+    if meta.pre_norm:
+        ops.masked_ln_fwd(x2, C, g, b, xn, C, mean, rstd, rows, C, s.ek, meta.eps, x_off=r0 * C, y_off=r0 * C, stat_off=r0)
+    else:
+        ops.scale_mask_cast(x2, C, None, 1, s.ek, xn, C, rows, C, g_off=r0 * C, out_off=r0 * C)
+
+
+def attn_half_forward(meta, x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b):
+    B, N, C = x.shape
+    M, H, D = B * N, meta.H, meta.D
+    HD = H * D
+    T = act_dtype()
+    dev = x.device
+    x2 = x.view(M, C)
+    xn = torch.empty(M, C, device=dev, dtype=T)
+    mean = torch.empty(M, device=dev)
+    rstd = torch.empty(M, device=dev)
+    qkv = torch.empty(M, 3 * HD, device=dev, dtype=T)
+    o = torch.empty(M, HD, device=dev, dtype=T)
+    lse = torch.empty(B, H, N, device=dev)
+    out = torch.empty_like(x)
+    out2 = out.view(M, C)
+    wq, wp = weights.get(qkv_w), weights.get(proj_w)
+    acts = _ActOperands()
+    scale = D ** -0.5
+    for s in meta.segs:
+        r0, rows, nb = s.b0 * N, (s.b1 - s.b0) * N, s.b1 - s.b0
+        if not s.active:
+            if meta.residual:
+                out[s.b0:s.b1].copy_(x[s.b0:s.b1])
+            else:
+                out[s.b0:s.b1].zero_()
+            continue
+        hk = s.ik // D
+        _pre(meta, x2, ln_w, ln_b, xn, mean, rstd, s, r0, rows)
+        a = acts.get(xn, C, r0, rows, s.ek)
+        if hk == H:
+            ops.gemm(a, wq, C, C, rows, 3 * HD, s.ek, ops.EPI_STORE, qkv, 3 * HD, a_off=r0 * C, out_off=r0 * 3 * HD, bias=qkv_b)
+        else:
+            for j in range(3):   # q / k / v row blocks of the kept heads only  (features ordered (3,H,D))
+                ops.gemm(a, wq, C, C, rows, hk * D, s.ek, ops.EPI_STORE, qkv, 3 * HD, a_off=r0 * C, b_off=j * HD * C,
+                         out_off=r0 * 3 * HD + j * HD, bias=qkv_b, bias_off=j * HD)
+        ops.attn_fwd(qkv, o, lse, nb, N, H, D, hk, scale, qkv_off=r0 * 3 * HD, o_off=r0 * HD, lse_off=s.b0 * H * N)
+        ao = acts.get(o, HD, r0, rows, hk * D)
+        if meta.residual:
+            ops.gemm(ao, wp, HD, HD, rows, s.ck, hk * D, ops.EPI_RESIDUAL, out2, C, a_off=r0 * HD, out_off=r0 * C, n_out=C,
+                     bias=proj_b, aux=x2, ld_aux=C, aux_off=r0 * C, row_scale=meta.row_scale,
+                     row_scale_off=meta.scale_off + s.b0, rows_per_sample=N, n_keep=s.ck)
+        else:
+            ops.gemm(ao, wp, HD, HD, rows, C, hk * D, ops.EPI_STORE, out2, C, a_off=r0 * HD, out_off=r0 * C, n_out=C, bias=proj_b)
+    return out, (xn, mean, rstd, qkv, o, lse)
+
+
+def attn_half_backward(meta, g_out, saved, x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b):
+    xn, mean, rstd, qkv, o, lse = saved
+    B, N, C = x.shape
+    M, H, D = B * N, meta.H, meta.D
+    HD = H * D
+    T = act_dtype()
+    dev = x.device
+    x2, g2 = x.view(M, C), g_out.view(M, C)
+    g_in = torch.empty_like(x)
+    gi2 = g_in.view(M, C)
+    df = torch.empty(M, C, device=dev, dtype=T)
+    d_o = torch.empty(M, HD, device=dev, dtype=T)
+    dqkv = torch.empty(M, 3 * HD, device=dev, dtype=T)
+    dxn = torch.empty(M, C, device=dev, dtype=T) if meta.pre_norm else None
+    d_lnw, d_lnb = torch.zeros_like(ln_w), torch.zeros_like(ln_b)
+    d_qw, d_qb = torch.zeros_like(qkv_w), torch.zeros_like(qkv_b)
+    d_pw, d_pb = torch.zeros_like(proj_w), torch.zeros_like(proj_b)
+    wq, wp = weights.get(qkv_w), weights.get(proj_w)
+    acts = _ActOperands()
+    scale = D ** -0.5
+    for s in meta.segs:
+        r0, rows, nb = s.b0 * N, (s.b1 - s.b0) * N, s.b1 - s.b0
+        if not s.active:
+            if meta.residual:
+                g_in[s.b0:s.b1].copy_(g_out[s.b0:s.b1])
+            else:
+                g_in[s.b0:s.b1].zero_()
+            continue
+        hk = s.ik // D
+        hkd = hk * D
+        ck = s.ck if meta.residual else C
+        ops.scale_mask_cast(g2, C, meta.row_scale if meta.residual else None, N, ck, df, C, rows, C, g_off=r0 * C, out_off=r0 * C,
+                            scale_off=meta.scale_off + s.b0)
+        ops.colsum(df, C, rows, ck, d_pb, x_off=r0 * C)
+        a_df = acts.get(df, C, r0, rows, ck)
+        a_o = acts.get(o, HD, r0, rows, hkd)
+        # dWproj[ck, hkd] += df^T o
+        ops.gemm(a_df, a_o, C, HD, ck, hkd, rows, ops.EPI_ATOMIC, d_pw, HD, a_off=r0 * C, b_off=r0 * HD, a_layout=ops.MNMAJOR,
+                 b_layout=ops.MNMAJOR, split_k=split_k_for(ck, hkd, rows))
+        # d_o[rows, hkd] = df[rows, ck] Wproj[ck, hkd]
+        ops.gemm(a_df, wp, C, HD, rows, hkd, ck, ops.EPI_STORE, d_o, HD, a_off=r0 * C, out_off=r0 * HD, b_layout=ops.MNMAJOR)
+        ops.attn_bwd(qkv, o, d_o, lse, dqkv, nb, N, H, D, hk, scale, qkv_off=r0 * 3 * HD, o_off=r0 * HD, lse_off=s.b0 * H * N)
+        ops.colsum(dqkv, 3 * HD, rows, 3 * HD, d_qb, x_off=r0 * 3 * HD)
+        a_dq = acts.get(dqkv, 3 * HD, r0, rows, 3 * HD)
+        a_xn = acts.get(xn, C, r0, rows, s.ek)
+        for j in (range(3) if hk < H else range(1)):
+            nrow = hkd if hk < H else 3 * HD
+            ops.gemm(a_dq, a_xn, 3 * HD, C, nrow, s.ek, rows, ops.EPI_ATOMIC, d_qw, C, a_off=r0 * 3 * HD + j * HD, b_off=r0 * C,
+                     out_off=j * HD * C, a_layout=ops.MNMAJOR, b_layout=ops.MNMAJOR, split_k=split_k_for(nrow, s.ek, rows))
+        # dxn[rows, ek] = dqkv[rows, 3HD] Wqkv[3HD, ek]   (masked heads are zero columns of dqkv)
+        if meta.pre_norm:
+            ops.gemm(a_dq, wq, 3 * HD, C, rows, s.ek, 3 * HD, ops.EPI_STORE, dxn, C, a_off=r0 * 3 * HD, out_off=r0 * C,
+                     n_out=up8(s.ek), b_layout=ops.MNMAJOR)
+            ops.masked_ln_bwd(dxn, C, x2, C, mean, rstd, ln_w, g2 if meta.residual else None, gi2, C, d_lnw, d_lnb, rows, C, s.ek,
+                              dy_off=r0 * C, x_off=r0 * C, stat_off=r0, g_off=r0 * C)
+        else:
+            ops.gemm(a_dq, wq, 3 * HD, C, rows, s.ek, 3 * HD, ops.EPI_STORE, gi2, C, a_off=r0 * 3 * HD, out_off=r0 * C, n_out=C,
+                     b_layout=ops.MNMAJOR)
+    return g_in, (d_lnw, d_lnb, d_qw, d_qb, d_pw, d_pb)
+
+
+# ------------------------------------------------------------------------------------------------ MLP half
+def mlp_half_forward(meta, x, ln_w, ln_b, fc1_w, fc1_b, fc2_w, fc2_b):
+    B, N, C = x.shape
+    M, F = B * N, meta.F
+    T = act_dtype()
+    dev = x.device
+    x2 = x.view(M, C)
+    xn = torch.empty(M, C, device=dev, dtype=T)
+    mean = torch.empty(M, device=dev)
+    rstd = torch.empty(M, device=dev)
+    u = torch.empty(M, F, device=dev, dtype=T)
+    h = torch.empty(M, F, device=dev, dtype=T)
+    out = torch.empty_like(x)
+    out2 = out.view(M, C)
+    w1, w2 = weights.get(fc1_w), weights.get(fc2_w)
+    acts = _ActOperands()
+    for s in meta.segs:
+        r0, rows = s.b0 * N, (s.b1 - s.b0) * N
+        if not s.active:
+            if meta.residual:
+                out[s.b0:s.b1].copy_(x[s.b0:s.b1])
+            else:
+                out[s.b0:s.b1].zero_()
+            continue
+        _pre(meta, x2, ln_w, ln_b, xn, mean, rstd, s, r0, rows)
+        a = acts.get(xn, C, r0, rows, s.ek)
+        ops.gemm(a, w1, C, C, rows, s.ik, s.ek, ops.EPI_GELU, u, F, a_off=r0 * C, out_off=r0 * F, n_out=up8(s.ik), out2=h,
+                 ldo2=F, out2_off=r0 * F, bias=fc1_b)
+        ah = acts.get(h, F, r0, rows, s.ik)
+        if meta.residual:
+            ops.gemm(ah, w2, F, F, rows, s.ck, s.ik, ops.EPI_RESIDUAL, out2, C, a_off=r0 * F, out_off=r0 * C, n_out=C, bias=fc2_b,
+                     aux=x2, ld_aux=C, aux_off=r0 * C, row_scale=meta.row_scale, row_scale_off=meta.scale_off + s.b0,
+                     rows_per_sample=N, n_keep=s.ck)
+        else:
+            ops.gemm(ah, w2, F, F, rows, C, s.ik, ops.EPI_STORE, out2, C, a_off=r0 * F, out_off=r0 * C, n_out=C, bias=fc2_b)
+    return out, (xn, mean, rstd, u, h)
+
+
+def mlp_half_backward(meta, g_out, saved, x, ln_w, ln_b, fc1_w, fc1_b, fc2_w, fc2_b):
+    xn, mean, rstd, u, h = saved
+    B, N, C = x.shape
+    M, F = B * N, meta.F
+    T = act_dtype()
+    dev = x.device
+    x2, g2 = x.view(M, C), g_out.view(M, C)
+    g_in = torch.empty_like(x)
+    gi2 = g_in.view(M, C)
+    df = torch.empty(M, C, device=dev, dtype=T)
+    du = torch.empty(M, F, device=dev, dtype=T)
+    dxn = torch.empty(M, C, device=dev, dtype=T) if meta.pre_norm else None
+    d_lnw, d_lnb = torch.zeros_like(ln_w), torch.zeros_like(ln_b)
+    d_w1, d_b1 = torch.zeros_like(fc1_w), torch.zeros_like(fc1_b)
+    d_w2, d_b2 = torch.zeros_like(fc2_w), torch.zeros_like(fc2_b)
+    w1, w2 = weights.get(fc1_w), weights.get(fc2_w)
+    acts = _ActOperands()
+    for s in meta.segs:
+        r0, rows = s.b0 * N, (s.b1 - s.b0) * N
+        if not s.active:
+            if meta.residual:
+                g_in[s.b0:s.b1].copy_(g_out[s.b0:s.b1])
+            else:
+                g_in[s.b0:s.b1].zero_()
+            continue
+        ck = s.ck if meta.residual else C
+        ops.scale_mask_cast(g2, C, meta.row_scale if meta.residual else None, N, ck, df, C, rows, C, g_off=r0 * C, out_off=r0 * C,
+                            scale_off=meta.scale_off + s.b0)
+        ops.colsum(df, C, rows, ck, d_b2, x_off=r0 * C)
+        a_df = acts.get(df, C, r0, rows, ck)
+        a_h = acts.get(h, F, r0, rows, s.ik)
+        # dW2[ck, ik] += df^T h
+        ops.gemm(a_df, a_h, C, F, ck, s.ik, rows, ops.EPI_ATOMIC, d_w2, F, a_off=r0 * C, b_off=r0 * F, a_layout=ops.MNMAJOR,
+                 b_layout=ops.MNMAJOR, split_k=split_k_for(ck, s.ik, rows))
+        # du[rows, ik] = (df[rows, ck] W2[ck, ik]) * gelu'(u)
+        ops.gemm(a_df, w2, C, F, rows, s.ik, ck, ops.EPI_GELUGRAD, du, F, a_off=r0 * C, out_off=r0 * F, n_out=up8(s.ik), aux=u,
+                 ld_aux=F, aux_off=r0 * F, b_layout=ops.MNMAJOR)
+        ops.colsum(du, F, rows, s.ik, d_b1, x_off=r0 * F)
+        a_du = acts.get(du, F, r0, rows, s.ik)
+        a_xn = acts.get(xn, C, r0, rows, s.ek)
+        # dW1[ik, ek] += du^T xn
+        ops.gemm(a_du, a_xn, F, C, s.ik, s.ek, rows, ops.EPI_ATOMIC, d_w1, C, a_off=r0 * F, b_off=r0 * C, a_layout=ops.MNMAJOR,
+                 b_layout=ops.MNMAJOR, split_k=split_k_for(s.ik, s.ek, rows))
+        # dxn[rows, ek] = du[rows, ik] W1[ik, ek]
+        if meta.pre_norm:
+            ops.gemm(a_du, w1, F, C, rows, s.ek, s.ik, ops.EPI_STORE, dxn, C, a_off=r0 * F, out_off=r0 * C, n_out=up8(s.ek),
+                     b_layout=ops.MNMAJOR)
+            ops.masked_ln_bwd(dxn, C, x2, C, mean, rstd, ln_w, g2 if meta.residual else None, gi2, C, d_lnw, d_lnb, rows, C, s.ek,
+                              dy_off=r0 * C, x_off=r0 * C, stat_off=r0, g_off=r0 * C)
+        else:
+            ops.gemm(a_du, w1, F, C, rows, s.ek, s.ik, ops.EPI_STORE, gi2, C, a_off=r0 * F, out_off=r0 * C, n_out=C,
+                     b_layout=ops.MNMAJOR)
+    return g_in, (d_lnw, d_lnb, d_w1, d_b1, d_w2, d_b2)
+
+
+class HalfBlockFn(torch.autograd.Function):
+    """x_out = x + mask * drop_path(branch(LN(x)))  for one half of a Block (nets/supernet_blocks.py:213-253)."""
+
+    @staticmethod
+    def forward(ctx, meta, x, *params):
+        require_cuda(x, 'Block')
+        x = x.contiguous()
+        fwd = attn_half_forward if meta.kind == 'attn' else mlp_half_forward
+        out, saved = fwd(meta, x, *params)
+        ctx.meta, ctx.saved = meta, saved
+        ctx.save_for_backward(x, *params)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, *params = ctx.saved_tensors
+        bwd = attn_half_backward if ctx.meta.kind == 'attn' else mlp_half_backward
+        g_in, pg = bwd(ctx.meta, g.contiguous(), ctx.saved, x, *params)
+        ctx.saved = None
+        return (None, g_in) + tuple(pg)

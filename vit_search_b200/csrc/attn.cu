@@ -1,0 +1,54 @@
+// C-ABI entry points of the attention core (dispatch between the tensor-core and the fp32 kernels).
+#include "common.cuh"
+
+namespace vsx {
+template <typename T>
+int attn_fwd_ref(const void* qkv, void* o, float* lse, int B, int N, int H, int D, int Hk, float scale, cudaStream_t st);
+template <typename T>
+int attn_bwd_ref(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int N, int H, int D, int Hk,
+                 float scale, cudaStream_t st);
+int attn_fwd_mma(const void* qkv, void* o, float* lse, int B, int N, int H, int D, int Hk, float scale, cudaStream_t st);
+int attn_bwd_mma(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int N, int H, int D, int Hk,
+                 float scale, cudaStream_t st);
+bool attn_mma_supported(int N, int D);
+}  // namespace vsx
+
+using namespace vsx;
+
+static int check_shape(const char* what, int B, int N, int H, int D, int Hk) {
+  VSX_REQUIRE(B >= 0 && N > 0 && H > 0 && Hk >= 0 && Hk <= H, "%s: bad shape batch=%d tokens=%d heads=%d heads_keep=%d", what, B, N, H, Hk);
+  VSX_REQUIRE(D % 4 == 0 && D > 0 && D <= 64, "%s: head_dim must be a multiple of 4 and <= 64 (got %d)", what, D);
+  return VSX_OK;
+}
+
+extern "C" int vsx_attn_fwd(const void* qkv, void* o, float* lse, int dtype, int batch, int tokens, int heads, int head_dim,
+                            int heads_keep, float scale, int impl, void* stream) {
+  int rc = check_shape("vsx_attn_fwd", batch, tokens, heads, head_dim, heads_keep);
+  if (rc) return rc;
+  if (batch == 0) return VSX_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == VSX_F32) return attn_fwd_ref<float>(qkv, o, lse, batch, tokens, heads, head_dim, heads_keep, scale, st);
+  if (dtype == VSX_BF16) {
+    if (impl != VSX_ATTN_IMPL_FP32 && attn_mma_supported(tokens, head_dim))
+      return attn_fwd_mma(qkv, o, lse, batch, tokens, heads, head_dim, heads_keep, scale, st);
+    return attn_fwd_ref<bf16>(qkv, o, lse, batch, tokens, heads, head_dim, heads_keep, scale, st);
+  }
+  set_error("vsx_attn_fwd: bad dtype %d", dtype);
+  return VSX_ERR_ARG;
+}
+
+extern "C" int vsx_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int dtype, int batch,
+                            int tokens, int heads, int head_dim, int heads_keep, float scale, int impl, void* stream) {
+  int rc = check_shape("vsx_attn_bwd", batch, tokens, heads, head_dim, heads_keep);
+  if (rc) return rc;
+  if (batch == 0) return VSX_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (dtype == VSX_F32) return attn_bwd_ref<float>(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, heads_keep, scale, st);
+  if (dtype == VSX_BF16) {
+    if (impl != VSX_ATTN_IMPL_FP32 && attn_mma_supported(tokens, head_dim))
+      return attn_bwd_mma(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, heads_keep, scale, st);
+    return attn_bwd_ref<bf16>(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, heads_keep, scale, st);
+  }
+  set_error("vsx_attn_bwd: bad dtype %d", dtype);
+  return VSX_ERR_ARG;
+}

@@ -1,0 +1,130 @@
+// Small HBM-bound helper kernels around the GEMMs: operand casts / bf16 hi-lo splits, the masked + drop-path-scaled
+// gradient cast that opens each branch's backward, and bias-gradient column sums.
+#include "common.cuh"
+
+namespace vsx {
+namespace {
+
+// hi = bf16(src); lo = bf16(src - hi) (optional).  4 elements per thread.
+__global__ void split_kernel(const float* __restrict__ src, long lds, bf16* __restrict__ hi, bf16* __restrict__ lo, long ldd, int rows,
+                             int cols4) {
+  const long total = (long)rows * cols4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / cols4;
+    const int c = (int)(i - r * cols4) * 4;
+    const float4 v = ld4(src + r * lds + c);
+    const bf16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
+    bf16* hp = hi + r * ldd + c;
+    hp[0] = h0, hp[1] = h1, hp[2] = h2, hp[3] = h3;
+    if (lo != nullptr) {
+      st4(lo + r * ldd + c, make_float4(v.x - __bfloat162float(h0), v.y - __bfloat162float(h1), v.z - __bfloat162float(h2),
+                                        v.w - __bfloat162float(h3)));
+    }
+  }
+}
+
+// out[m, n] = n < n_keep ? g[m, n] * row_scale[m / rows_per_sample] : 0     (Block backward, nets/supernet_blocks.py:243,251
+// together with nets/drop.py:25: the branch output was scaled by drop-path and masked before the residual add)
+template <typename T>
+__global__ void scale_mask_cast_kernel(const float* __restrict__ g, long ldg, const float* __restrict__ row_scale, int rps, int n_keep,
+                                       T* __restrict__ out, long ldo, int rows, int cols4) {
+  const long total = (long)rows * cols4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long r = i / cols4;
+    const int c = (int)(i - r * cols4) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < n_keep) {
+      const float s = row_scale != nullptr ? __ldg(row_scale + r / rps) : 1.0f;
+      v = ld4(g + r * ldg + c);
+      v.x *= s;
+      v.y = (c + 1 < n_keep) ? v.y * s : 0.f;
+      v.z = (c + 2 < n_keep) ? v.z * s : 0.f;
+      v.w = (c + 3 < n_keep) ? v.w * s : 0.f;
+    }
+    st4(out + r * ldo + c, v);
+  }
+}
+
+// out[c] += sum_r x[r, c].  CTA = 256 threads = 32 column-quads x 8 row lanes, covers 128 columns x ROWS_PER_CTA rows.
+constexpr int CS_ROWS = 512;
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long ldx, int rows, int cols, float* __restrict__ out) {
+  const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int c = blockIdx.x * 128 + cq * 4;
+  const long r0 = (long)blockIdx.y * CS_ROWS;
+  const long r1 = r0 + CS_ROWS < rows ? r0 + CS_ROWS : rows;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c < cols) {
+    for (long r = r0 + rl; r < r1; r += 8) {
+      const float4 v = ld4(x + r * ldx + c);
+      acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+    }
+  }
+  __shared__ float4 red[8][32];
+  red[rl][cq] = acc;
+  __syncthreads();
+  if (rl == 0 && c < cols) {
+    for (int k = 1; k < 8; ++k) {
+      const float4 u = red[k][cq];
+      acc.x += u.x, acc.y += u.y, acc.z += u.z, acc.w += u.w;
+    }
+    atomicAdd(out + c, acc.x);
+    if (c + 1 < cols) atomicAdd(out + c + 1, acc.y);
+    if (c + 2 < cols) atomicAdd(out + c + 2, acc.z);
+    if (c + 3 < cols) atomicAdd(out + c + 3, acc.w);
+  }
+}
+
+int ew_grid(long work_items) {
+  long g = ceil_div_l(work_items, 256);
+  const long cap = (long)num_sms() * 16;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+}  // namespace vsx
+
+using namespace vsx;
+
+extern "C" int vsx_split_bf16(const float* src, long lds, void* hi, void* lo, long ldd, int rows, int cols, void* stream) {
+  VSX_REQUIRE(cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "vsx_split_bf16: cols and pitches must be multiples of 4");
+  if (rows <= 0 || cols <= 0) return VSX_OK;
+  split_kernel<<<ew_grid((long)rows * cols / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, lds, (bf16*)hi, (bf16*)lo, ldd,
+                                                                                                 rows, cols / 4);
+  return check_launch("vsx_split_bf16");
+}
+
+extern "C" int vsx_scale_mask_cast(const float* g, long ldg, const float* row_scale, int rows_per_sample, int n_keep, void* out,
+                                   int dtype, long ldo, int rows, int cols, void* stream) {
+  VSX_REQUIRE(cols % 4 == 0 && ldg % 4 == 0 && ldo % 4 == 0, "vsx_scale_mask_cast: cols and pitches must be multiples of 4");
+  if (rows <= 0 || cols <= 0) return VSX_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int rps = rows_per_sample > 0 ? rows_per_sample : 1;
+  const int grid = ew_grid((long)rows * cols / 4);
+  if (dtype == VSX_BF16)
+    scale_mask_cast_kernel<bf16><<<grid, 256, 0, st>>>(g, ldg, row_scale, rps, n_keep, (bf16*)out, ldo, rows, cols / 4);
+  else if (dtype == VSX_F32)
+    scale_mask_cast_kernel<float><<<grid, 256, 0, st>>>(g, ldg, row_scale, rps, n_keep, (float*)out, ldo, rows, cols / 4);
+  else {
+    set_error("vsx_scale_mask_cast: bad dtype %d", dtype);
+    return VSX_ERR_ARG;
+  }
+  return check_launch("vsx_scale_mask_cast");
+}
+
+extern "C" int vsx_colsum(const void* x, int dtype, long ldx, int rows, int cols, float* out, void* stream) {
+  VSX_REQUIRE(ldx % 4 == 0, "vsx_colsum: pitch must be a multiple of 4");
+  if (rows <= 0 || cols <= 0) return VSX_OK;
+  VSX_REQUIRE(cols % 4 == 0 || cols <= ldx, "vsx_colsum: bad cols");
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  dim3 grid(ceil_div(cols, 128), ceil_div(rows, CS_ROWS));
+  if (dtype == VSX_BF16)
+    colsum_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, ldx, rows, cols, out);
+  else if (dtype == VSX_F32)
+    colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ldx, rows, cols, out);
+  else {
+    set_error("vsx_colsum: bad dtype %d", dtype);
+    return VSX_ERR_ARG;
+  }
+  return check_launch("vsx_colsum");
+}

@@ -72,3 +72,33 @@ def gemm(a, b, lda, ldb, M, N, K, epilogue, out, ldo, *, a_off=0, b_off=0, out_o
     d.row_scale = _ptr(row_scale, row_scale_off)
     d.rows_per_sample, d.n_keep, d.split_k = rows_per_sample, n_keep, split_k
     _lib.check(_lib.lib().vsx_gemm(C.byref(d), _stream()))
+
+
+# ------------------------------------------------------------------------------------------------ attention core
+ATTN_AUTO, ATTN_FP32 = 0, 1
+
+
+def attn_fwd(qkv, o, lse, batch, tokens, heads, head_dim, heads_keep, scale, *, qkv_off=0, o_off=0, lse_off=0, impl=ATTN_AUTO):
+    _lib.check(_lib.lib().vsx_attn_fwd(_ptr(qkv, qkv_off), _ptr(o, o_off), _ptr(lse, lse_off), dt(qkv), batch, tokens, heads,
+                                       head_dim, heads_keep, scale, impl, _stream()))
+
+
+def attn_bwd(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, heads_keep, scale, *, qkv_off=0, o_off=0, lse_off=0,
+             impl=ATTN_AUTO):
+    _lib.check(_lib.lib().vsx_attn_bwd(_ptr(qkv, qkv_off), _ptr(o, o_off), _ptr(d_o, o_off), _ptr(lse, lse_off),
+                                       _ptr(dqkv, qkv_off), dt(qkv), batch, tokens, heads, head_dim, heads_keep, scale, impl,
+                                       _stream()))
+
+
+# ------------------------------------------------------------------------------------------------ elementwise
+def split_bf16(src, lds, hi, lo, ldd, rows, cols, src_off=0, dst_off=0):
+    _lib.check(_lib.lib().vsx_split_bf16(_ptr(src, src_off), lds, _ptr(hi, dst_off), _ptr(lo, dst_off), ldd, rows, cols, _stream()))
+
+
+def scale_mask_cast(g, ldg, row_scale, rows_per_sample, n_keep, out, ldo, rows, cols, g_off=0, out_off=0, scale_off=0):
+    _lib.check(_lib.lib().vsx_scale_mask_cast(_ptr(g, g_off), ldg, _ptr(row_scale, scale_off), rows_per_sample, n_keep,
+                                              _ptr(out, out_off), dt(out), ldo, rows, cols, _stream()))
+
+
+def colsum(x, ldx, rows, cols, out, x_off=0, out_off=0):
+    _lib.check(_lib.lib().vsx_colsum(_ptr(x, x_off), dt(x), ldx, rows, cols, _ptr(out, out_off), _stream()))
