@@ -138,6 +138,76 @@ int vsx_scale_mask_cast(const float* g, long ldg, const float* row_scale, int ro
                         int dtype, long ldo, int rows, int cols, void* stream);
 int vsx_colsum(const void* x, int dtype, long ldx, int rows, int cols, float* out, void* stream);
 
+/* ----------------------------------------------------------------------------------------------------
+ * Convolutions as GEMMs -- replaces the cuDNN convs of PatchConvEmbed (nets/patch_conv.py:23-36, :63-74) and the
+ * SR block's patch_reduce (nets/vit_sr_supernet.py:139-143).  Feature maps are channels-last [B,H,W,C]
+ * (`pix_pitch` elements between pixels, `batch_pitch` between samples, so token tensors [B,1+g*g,C] are read in
+ * place).  vsx_im2col gathers k x k taps (tap-major, channel-minor columns: weights are used as [O, kh, kw, I]) and
+ * fuses the producer's BatchNorm-apply + ReLU (scale/shift per channel, NULL = identity) and an optional second,
+ * added input (the stem's residual, patch_conv.py:69-71).  nchw != 0: in1 is the fp32 image [B,C,H,W].
+ * vsx_col2im is the transposed gather for the data gradient (optionally adding `add`).
+ * -------------------------------------------------------------------------------------------------- */
+int vsx_im2col(const void* in1, const float* scale1, const float* shift1, const void* in2, const float* scale2,
+               const float* shift2, int in_dtype, int nchw, long batch_pitch, long pix_pitch, int B, int H, int W, int C,
+               int k, int stride, int pad, void* out, int out_dtype, long ldo, void* stream);
+int vsx_col2im(const void* dcol, long ldc, const void* add, int dtype, int B, int H, int W, int C, int k, int stride,
+               int pad, void* din, long batch_pitch, long pix_pitch, void* stream);
+
+/* BatchNorm2d in training mode over a channels-last map y[P,C] (C <= 32) -- nn.BatchNorm2d at nets/patch_conv.py:28.
+ * stats: sums[0..C) += sum y, sums[C..2C) += sum y^2 (fp64, zero them first).  finalize: biased batch variance for
+ * the normalisation (scale = gamma*rstd, shift = beta - mean*scale), running stats move with `momentum` towards
+ * (mean, unbiased var), num_batches_tracked += 1 (pointers may be NULL).  Backward through relu(bn(y)):
+ * bwd_stats: sums = (sum dz, sum dz*zhat) with dz = da*[bn(y) > 0]; bwd_apply: dy, and dgamma/dbeta += sums. */
+int vsx_bn_stats(const void* y, int dtype, long P, int C, double* sums, void* stream);
+int vsx_bn_finalize(const double* sums, long P, int C, const float* gamma, const float* beta, float eps, float momentum,
+                    float* scale, float* shift, float* mean, float* rstd, float* running_mean, float* running_var,
+                    long long* num_batches_tracked, void* stream);
+int vsx_bn_bwd_stats(const void* da, const void* y, int dtype, long P, int C, const float* gamma, const float* beta,
+                     const float* mean, const float* rstd, double* sums, void* stream);
+int vsx_bn_bwd_apply(const void* da, const void* y, int dtype, long P, int C, const float* gamma, const float* beta,
+                     const float* mean, const float* rstd, const double* sums, void* dy, float* dgamma, float* dbeta,
+                     void* stream);
+
+/* Token assembly: x0[b,t,:] = mask * ((t == 0 ? tokens : patches[b,t-1]) + pos_embed[t])  -- replaces cat / expand /
+ * add / embed ChannelDrop at nets/vit_sr_supernet.py:399-407; backward gives dpatches (activation dtype), and
+ * ACCUMULATES dpos_embed [N,C] and dtokens [C]. */
+int vsx_embed_assemble(const float* patches, const float* tokens, const float* pos, float* x0, int batch,
+                       int tokens_per_sample, int C, int keep, void* stream);
+int vsx_embed_assemble_bwd(const float* g, void* dpatches, int dtype, float* dpos, float* dtokens, int batch,
+                           int tokens_per_sample, int C, int keep, void* stream);
+
+/* SR block combine (nets/vit_sr_supernet.py:131-166): y = mask2 * (cat(tok, conv + pos) + zero-pad(cat(x[:,0], avgpool2x2(x[:,1:])))).
+ * Backward: dconv / dtok (activation dtype), dpos ACCUMULATED, and the residual-path gradient gres [B,1+g*g,C1]. */
+int vsx_sr_combine(const float* conv, const float* tok, const float* pos, const float* x, float* y, int batch, int grid_in,
+                   int C1, int C2, int keep2, void* stream);
+int vsx_sr_combine_bwd(const float* gy, void* dconv, void* dtok, int dtype, float* dpos, float* gres, int batch, int grid_in,
+                       int C1, int C2, int keep2, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------
+ * Loss and optimizer ends of the step (engine.py:152-157, :175-177).
+ * vsx_soft_ce: *loss_sum += loss_scale * sum_rows(-sum_c t*log_softmax(x)); dlogits = grad_scale*(softmax*sum(t) - t)
+ *              (timm SoftTargetCrossEntropy, main.py:392-394; dlogits may be NULL).
+ * vsx_adamw  : one launch over all parameters (torch.optim.AdamW semantics: decoupled decay, bias correction); each
+ *              chunk i of vsx_adamw_chunk_elems() elements belongs to tensor chunk_tensor[i] at chunk_index[i].
+ *              shadow_hi / shadow_lo (bf16, may be NULL) receive the refreshed GEMM operand copies of the weight.
+ * -------------------------------------------------------------------------------------------------- */
+typedef struct vsx_adamw_tensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  void* shadow_hi;
+  void* shadow_lo;
+  long numel;
+  float weight_decay;
+} vsx_adamw_tensor;
+int vsx_soft_ce(const float* logits, long ld, const float* target, long ldt, int rows, int cols, float loss_scale,
+                float grad_scale, float* loss_sum, float* dlogits, long ldd, void* stream);
+int vsx_scale_by_scalar(float* x, long n, const float* scalar_dev, void* stream);
+int vsx_adamw_chunk_elems(void);
+int vsx_adamw(const vsx_adamw_tensor* tensors_dev, const int* chunk_tensor_dev, const int* chunk_index_dev, int num_chunks,
+              float lr, float beta1, float beta2, float eps, int step, const float* grad_scale_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,8 +37,29 @@ SIGNATURES = {
     'vsx_split_bf16': [_p, _l, _p, _p, _l, _i, _i, _p],
     'vsx_scale_mask_cast': [_p, _l, _p, _i, _i, _p, _i, _l, _i, _i, _p],
     'vsx_colsum': [_p, _i, _l, _i, _i, _p, _p],
+    'vsx_im2col': [_p, _p, _p, _p, _p, _p, _i, _i, _l, _l, _i, _i, _i, _i, _i, _i, _i, _p, _i, _l, _p],
+    'vsx_col2im': [_p, _l, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _l, _l, _p],
+    'vsx_bn_stats': [_p, _i, _l, _i, _p, _p],
+    'vsx_bn_finalize': [_p, _l, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p],
+    'vsx_bn_bwd_stats': [_p, _p, _i, _l, _i, _p, _p, _p, _p, _p, _p],
+    'vsx_bn_bwd_apply': [_p, _p, _i, _l, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    'vsx_embed_assemble': [_p, _p, _p, _p, _i, _i, _i, _i, _p],
+    'vsx_embed_assemble_bwd': [_p, _p, _i, _p, _p, _i, _i, _i, _i, _p],
+    'vsx_sr_combine': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    'vsx_sr_combine_bwd': [_p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p],
+    'vsx_soft_ce': [_p, _l, _p, _l, _i, _i, _f, _f, _p, _p, _l, _p],
+    'vsx_scale_by_scalar': [_p, _l, _p, _p],
+    'vsx_adamw_chunk_elems': [],
+    'vsx_adamw': [_p, _p, _p, _i, _f, _f, _f, _f, _i, _p, _p],
 }
 _RESTYPES = {'vsx_last_error': C.c_char_p}
+
+
+
+class AdamWTensor(C.Structure):
+    _fields_ = [('param', _p), ('grad', _p), ('exp_avg', _p), ('exp_avg_sq', _p), ('shadow_hi', _p), ('shadow_lo', _p),
+                ('numel', _l), ('weight_decay', _f)]
+
 
 _lib = None
 

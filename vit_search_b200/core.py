@@ -55,10 +55,11 @@ class _WeightCache:
 
     def __init__(self):
         self.entries = {}
+        self.generation = 0          # bumped by optimizers that update parameters through raw pointers
 
     def get(self, w, layout=None):
         key = (id(w), layout)
-        tag = (w.data_ptr(), w._version, _precision, tuple(w.shape))
+        tag = (w.data_ptr(), w._version, self.generation, _precision, tuple(w.shape))
         e = self.entries.get(key)
         if e is not None and e[0] == tag:
             return e[1]

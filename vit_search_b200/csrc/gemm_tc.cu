@@ -101,7 +101,7 @@ __device__ __forceinline__ void epilogue_row(const GemmArgs& g, int m, int n, fl
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = n + 4 * i;
-      if (c + 3 < g.N) {
+      if (c + 3 < g.N && (g.ldo & 3) == 0) {
         asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * i), "f"(v[4 * i]), "f"(v[4 * i + 1]),
                      "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
                      : "memory");

@@ -1,0 +1,167 @@
+"""The train step of the ViT-Res super-network -- the body of the reference's engine.train_one_epoch loop
+(engine.py:101-185) re-built around the libvsx kernels: RNG bracket for architecture sampling (:119-131, :164-165),
+forward, the two soft-target cross-entropies (:152-157), backward, data-parallel gradient all-reduce (DDP at
+main.py:366-368), fused AdamW (:175-177).  Compared with the reference there is no host sync between forward and
+backward (`loss.item()` at :168 becomes a device-side scalar read once per logging interval) and the optimizer is one
+kernel launch instead of a per-tensor loop.
+"""
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib, core, ops
+
+_SAMPLE_EPOCH_OFFSET = 10000   # engine.py:98
+
+
+# ------------------------------------------------------------------------------------------------ loss
+class _SoftCEFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target):
+        core.require_cuda(logits, 'SoftTargetCrossEntropy')
+        K = logits.shape[-1]
+        x = logits.contiguous().view(-1, K).float()
+        t = target.contiguous().view(-1, K).float()
+        rows = x.shape[0]
+        loss = torch.zeros((), device=x.device)
+        need_grad = logits.requires_grad
+        dl = torch.empty_like(x) if need_grad else None
+        ops.call('soft_ce', x, K, t, K, rows, K, 1.0 / rows, 1.0 / rows, loss, dl, K)
+        ctx.dl, ctx.shape = dl, logits.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        dl = ctx.dl
+        ctx.dl = None
+        ops.call('scale_by_scalar', dl, dl.numel(), g.contiguous().float())
+        return dl.view(ctx.shape), None
+
+
+class SoftTargetCrossEntropy(nn.Module):
+    """timm's SoftTargetCrossEntropy (main.py:392-394): mean over rows of sum(-target * log_softmax(x))."""
+
+    def forward(self, x, target):
+        return _SoftCEFn.apply(x, target)
+
+
+# ------------------------------------------------------------------------------------------------ optimizer
+class FusedAdamW:
+    """torch.optim.AdamW semantics with timm's parameter grouping (no decay for biases, 1-D tensors and the names in
+    model.no_weight_decay(); main.py:385, :434), executed as ONE kernel launch over all parameters, which also refreshes
+    the bf16 GEMM-operand copies of the weights held by core.weights."""
+
+    def __init__(self, model, lr=5e-4, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8):
+        self.model = model
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.step_count = 0
+        skip = model.no_weight_decay() if hasattr(model, 'no_weight_decay') else set()
+        self.entries = []
+        for name, p in model.named_parameters():
+            if not p.requires_grad:
+                continue
+            no_decay = p.ndim <= 1 or name.endswith('.bias') or name in skip
+            self.entries.append((name, p, 0.0 if no_decay else weight_decay))
+        self.state = {}
+        self._table_key = None
+        self.param_groups = [{'lr': lr}]
+        self.chunk = _lib.lib().vsx_adamw_chunk_elems()
+
+    def zero_grad(self, set_to_none=True):
+        for _, p, _ in self.entries:
+            p.grad = None
+
+    def _build_table(self):
+        dev = self.entries[0][1].device
+        arr = (_lib.AdamWTensor * len(self.entries))()
+        ct, ci = [], []
+        for i, (name, p, wd) in enumerate(self.entries):
+            if p.grad is None:
+                p.grad = torch.zeros_like(p)
+            st = self.state.get(name)
+            if st is None or st[0].shape != p.shape:
+                st = (torch.zeros_like(p), torch.zeros_like(p))
+                self.state[name] = st
+            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+            arr[i].param, arr[i].grad = p.data_ptr(), g.data_ptr()
+            arr[i].exp_avg, arr[i].exp_avg_sq = st[0].data_ptr(), st[1].data_ptr()
+            arr[i].shadow_hi = arr[i].shadow_lo = None
+            arr[i].numel, arr[i].weight_decay = p.numel(), wd
+            n = math.ceil(p.numel() / self.chunk)
+            ct += [i] * n
+            ci += list(range(n))
+        raw = bytes(arr)
+        self._tab = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        self._ct = torch.tensor(ct, dtype=torch.int32, device=dev)
+        self._ci = torch.tensor(ci, dtype=torch.int32, device=dev)
+        self._nchunks = len(ct)
+
+    def step(self):
+        # gradient tensors are re-allocated by every backward, parameters by `rewiring`: re-derive the pointer table when
+        # any pointer changed (a host-side comparison of ~250 integers)
+        key = tuple((p.data_ptr(), 0 if p.grad is None else p.grad.data_ptr()) for _, p, _ in self.entries)
+        if key != self._table_key:
+            self._build_table()
+            self._table_key = tuple((p.data_ptr(), p.grad.data_ptr()) for _, p, _ in self.entries)
+        self.step_count += 1
+        self.lr = self.param_groups[0]['lr']
+        ops.call('adamw', self._tab, self._ct, self._ci, self._nchunks, float(self.lr), float(self.betas[0]), float(self.betas[1]),
+                 float(self.eps), self.step_count, None)
+        core.weights.generation += 1      # parameters were written through raw pointers: operand copies are stale
+
+
+# ------------------------------------------------------------------------------------------------ train step
+class TrainStep:
+    """One data-parallel training step, the drop-in for the body of engine.train_one_epoch."""
+
+    def __init__(self, model, optimizer=None, criterion=None, arch_sample='multi', world_size=1, ddp_model=None):
+        self.model = model
+        self.net = ddp_model if ddp_model is not None else model
+        self.optimizer = optimizer if optimizer is not None else FusedAdamW(model)
+        self.criterion = criterion if criterion is not None else SoftTargetCrossEntropy()
+        self.arch_sample = arch_sample
+        self.world_size = world_size
+        self.train_iter = 0
+
+    def __call__(self, samples, targets, patch_targets, epoch=0):
+        """samples [B,3,224,224], targets [B,K], patch_targets [B,16,K] on the GPU.  Returns the loss as a device scalar
+        (no host sync)."""
+        rng = None
+        if self.arch_sample is not None:                         # engine.py:119-131
+            rng = torch.random.get_rng_state()
+            if self.arch_sample in ('single', 'hybrid'):
+                torch.manual_seed(epoch * _SAMPLE_EPOCH_OFFSET + self.train_iter)
+            elif self.arch_sample != 'multi':
+                raise ValueError('arch_sample has invalid value {}.'.format(self.arch_sample))
+        cls_pred, patch_pred = self.net(samples, patch_output_type='seq')
+        loss = self.criterion(cls_pred, targets) + self.criterion(patch_pred, patch_targets)     # engine.py:153-157
+        if rng is not None:
+            torch.random.set_rng_state(rng)                      # engine.py:164-165
+        self.train_iter += 1
+        self.optimizer.zero_grad()
+        loss.backward()
+        if self.world_size > 1 and self.net is self.model:
+            allreduce_gradients(self.model, self.world_size)
+        self.optimizer.step()
+        return loss.detach()
+
+
+def allreduce_gradients(model, world_size):
+    """Gradient all-reduce (SUM / world) over NCCL when the model is not wrapped in DistributedDataParallel: one flat
+    fp32 bucket per ~64 MB, reduced in place."""
+    import torch.distributed as dist
+    grads = [p.grad for p in model.parameters() if p.grad is not None]
+    bucket, size = [], 0
+    for g in grads + [None]:
+        if g is not None:
+            bucket.append(g)
+            size += g.numel()
+        if bucket and (g is None or size >= 16 * 1024 * 1024):
+            flat = torch._utils._flatten_dense_tensors(bucket)
+            dist.all_reduce(flat)
+            flat.div_(world_size)
+            for b, f in zip(bucket, torch._utils._unflatten_dense_tensors(flat, bucket)):
+                b.copy_(f)
+            bucket, size = [], 0

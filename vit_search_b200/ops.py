@@ -102,3 +102,18 @@ def scale_mask_cast(g, ldg, row_scale, rows_per_sample, n_keep, out, ldo, rows, 
 
 def colsum(x, ldx, rows, cols, out, x_off=0, out_off=0):
     _lib.check(_lib.lib().vsx_colsum(_ptr(x, x_off), dt(x), ldx, rows, cols, _ptr(out, out_off), _stream()))
+
+
+# ------------------------------------------------------------------------------------------------ generic caller
+def call(name, *args):
+    """Call `vsx_<name>` with tensors converted to device pointers ((tensor, element_offset) tuples allowed, None -> NULL);
+    the current CUDA stream is appended as the last argument."""
+    conv = []
+    for a in args:
+        if isinstance(a, torch.Tensor):
+            conv.append(_ptr(a))
+        elif isinstance(a, tuple):
+            conv.append(_ptr(a[0], a[1]))
+        else:
+            conv.append(a)
+    _lib.check(getattr(_lib.lib(), 'vsx_' + name)(*conv, _stream()))
