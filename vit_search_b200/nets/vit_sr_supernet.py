@@ -290,8 +290,8 @@ class _HeadFn(torch.autograd.Function):
         gcls = gcls.contiguous()
         dc = torch.empty(B, K, device=dev, dtype=T)
         ops.scale_mask_cast(gcls, K, None, 1, K, dc, K, B, K)
-        d_cw, d_cb = torch.zeros_like(cw), torch.zeros_like(cb)
-        d_pw, d_pb = torch.zeros_like(pw), torch.zeros_like(pb)
+        d_cw, d_cb = torch.zeros_like(cw), torch.zeros(K, device=dev)
+        d_pw, d_pb = torch.zeros_like(pw), torch.zeros(K, device=dev)
         d_lnw, d_lnb = torch.zeros_like(ln_w), torch.zeros_like(ln_w)
         ops.colsum(dc, K, B, K, d_cb)
         dtokf = torch.empty(B, C, device=dev, dtype=T)

@@ -12,6 +12,15 @@ from ._lib import BF16, F32, KMAJOR, MNMAJOR, EPI_STORE, EPI_GELU, EPI_RESIDUAL,
 
 _DT = {torch.bfloat16: BF16, torch.float32: F32}
 
+LAUNCHES = 0      # kernels launched through the C ABI (every entry point launches exactly one kernel)
+PROFILE = None    # when a list: (start_event, end_event, algorithmic_flops) per tensor-core GEMM launch (bench.py roofline)
+
+
+def _ck(rc):
+    global LAUNCHES
+    LAUNCHES += 1
+    _lib.check(rc)
+
 
 def _stream():
     return torch.cuda.current_stream().cuda_stream
@@ -32,14 +41,14 @@ def dt(t):
 # ------------------------------------------------------------------------------------------------ layer norm
 def masked_ln_fwd(x, ldx, gamma, beta, y, ldy, mean, rstd, rows, C_, keep, eps, x_off=0, y_off=0, stat_off=0,
                   y2=None, rows_per_sample=0, split_tokens=0):
-    _lib.check(_lib.lib().vsx_masked_ln_fwd(
+    _ck(_lib.lib().vsx_masked_ln_fwd(
         _ptr(x, x_off), ldx, _ptr(gamma), _ptr(beta), _ptr(y, y_off), _ptr(y2), dt(y), ldy,
         _ptr(mean, stat_off), _ptr(rstd, stat_off), rows, C_, keep, eps, rows_per_sample, split_tokens, _stream()))
 
 
 def masked_ln_bwd(dy, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, dgamma, dbeta, rows, C_, keep,
                   dy_off=0, x_off=0, stat_off=0, g_off=0, dy2=None, rows_per_sample=0, split_tokens=0):
-    _lib.check(_lib.lib().vsx_masked_ln_bwd(
+    _ck(_lib.lib().vsx_masked_ln_bwd(
         _ptr(dy, dy_off), _ptr(dy2), dt(dy), lddy, _ptr(x, x_off), ldx, _ptr(mean, stat_off), _ptr(rstd, stat_off),
         _ptr(gamma), _ptr(g_in, g_off), _ptr(g_out, g_off), ldg, _ptr(dgamma), _ptr(dbeta), rows, C_, keep,
         rows_per_sample, split_tokens, _stream()))
@@ -71,7 +80,14 @@ def gemm(a, b, lda, ldb, M, N, K, epilogue, out, ldo, *, a_off=0, b_off=0, out_o
     d.aux, d.ld_aux = _ptr(aux, aux_off), ld_aux
     d.row_scale = _ptr(row_scale, row_scale_off)
     d.rows_per_sample, d.n_keep, d.split_k = rows_per_sample, n_keep, split_k
-    _lib.check(_lib.lib().vsx_gemm(C.byref(d), _stream()))
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _ck(_lib.lib().vsx_gemm(C.byref(d), _stream()))
+        e1.record()
+        PROFILE.append((e0, e1, 2.0 * M * N * K))
+        return
+    _ck(_lib.lib().vsx_gemm(C.byref(d), _stream()))
 
 
 # ------------------------------------------------------------------------------------------------ attention core
@@ -79,29 +95,29 @@ ATTN_AUTO, ATTN_FP32 = 0, 1
 
 
 def attn_fwd(qkv, o, lse, batch, tokens, heads, head_dim, heads_keep, scale, *, qkv_off=0, o_off=0, lse_off=0, impl=ATTN_AUTO):
-    _lib.check(_lib.lib().vsx_attn_fwd(_ptr(qkv, qkv_off), _ptr(o, o_off), _ptr(lse, lse_off), dt(qkv), batch, tokens, heads,
+    _ck(_lib.lib().vsx_attn_fwd(_ptr(qkv, qkv_off), _ptr(o, o_off), _ptr(lse, lse_off), dt(qkv), batch, tokens, heads,
                                        head_dim, heads_keep, scale, impl, _stream()))
 
 
 def attn_bwd(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, heads_keep, scale, *, qkv_off=0, o_off=0, lse_off=0,
              impl=ATTN_AUTO):
-    _lib.check(_lib.lib().vsx_attn_bwd(_ptr(qkv, qkv_off), _ptr(o, o_off), _ptr(d_o, o_off), _ptr(lse, lse_off),
+    _ck(_lib.lib().vsx_attn_bwd(_ptr(qkv, qkv_off), _ptr(o, o_off), _ptr(d_o, o_off), _ptr(lse, lse_off),
                                        _ptr(dqkv, qkv_off), dt(qkv), batch, tokens, heads, head_dim, heads_keep, scale, impl,
                                        _stream()))
 
 
 # ------------------------------------------------------------------------------------------------ elementwise
 def split_bf16(src, lds, hi, lo, ldd, rows, cols, src_off=0, dst_off=0):
-    _lib.check(_lib.lib().vsx_split_bf16(_ptr(src, src_off), lds, _ptr(hi, dst_off), _ptr(lo, dst_off), ldd, rows, cols, _stream()))
+    _ck(_lib.lib().vsx_split_bf16(_ptr(src, src_off), lds, _ptr(hi, dst_off), _ptr(lo, dst_off), ldd, rows, cols, _stream()))
 
 
 def scale_mask_cast(g, ldg, row_scale, rows_per_sample, n_keep, out, ldo, rows, cols, g_off=0, out_off=0, scale_off=0):
-    _lib.check(_lib.lib().vsx_scale_mask_cast(_ptr(g, g_off), ldg, _ptr(row_scale, scale_off), rows_per_sample, n_keep,
+    _ck(_lib.lib().vsx_scale_mask_cast(_ptr(g, g_off), ldg, _ptr(row_scale, scale_off), rows_per_sample, n_keep,
                                               _ptr(out, out_off), dt(out), ldo, rows, cols, _stream()))
 
 
 def colsum(x, ldx, rows, cols, out, x_off=0, out_off=0):
-    _lib.check(_lib.lib().vsx_colsum(_ptr(x, x_off), dt(x), ldx, rows, cols, _ptr(out, out_off), _stream()))
+    _ck(_lib.lib().vsx_colsum(_ptr(x, x_off), dt(x), ldx, rows, cols, _ptr(out, out_off), _stream()))
 
 
 # ------------------------------------------------------------------------------------------------ generic caller
@@ -116,4 +132,4 @@ def call(name, *args):
             conv.append(_ptr(a[0], a[1]))
         else:
             conv.append(a)
-    _lib.check(getattr(_lib.lib(), 'vsx_' + name)(*conv, _stream()))
+    _ck(getattr(_lib.lib(), 'vsx_' + name)(*conv, _stream()))
