@@ -35,7 +35,7 @@ extern "C" {
 #define VSX_BF16 0
 #define VSX_F32 1
 
-#define VSX_ABI_VERSION 1
+#define VSX_ABI_VERSION 2
 
 const char* vsx_last_error(void);
 int vsx_abi_version(void);
@@ -70,8 +70,10 @@ int vsx_masked_ln_bwd(const void* dy, const void* dy2, int dtype, long lddy, con
  *
  *   D[M,N] = epilogue( sum_{t<terms} A_t[M,K] * B_t[N,K]^T )      bf16 operands, fp32 accumulate
  *
- * terms == 3 is the split-bf16 ("bf16x3") high-precision mode: A = A_hi + A_lo, B = B_hi + B_lo and the three
- * products hi*hi, lo*hi, hi*lo accumulate into the same TMEM tile.
+ * terms > 1 is the split-bf16 high-precision mode: every fp32 operand is written as a sum of bf16 parts
+ * (x = x1 + x2 [+ x3], vsx_split_bf16) and the significant cross products accumulate into the same TMEM tile:
+ * 3 terms (x1y1, x2y1, x1y2; ~2^-16 relative) or 6 terms (+ x2y2, x3y1, x1y3; ~2^-24, i.e. fp32-exact).  The caller
+ * lists the operand pair of each term.
  * Layout of an operand: VSX_KMAJOR  -- stored [M or N rows, K contiguous]      (forward: x and W)
  *                       VSX_MNMAJOR -- stored [K rows, M or N contiguous]      (dgrad: W; wgrad: dY and x)
  * -------------------------------------------------------------------------------------------------- */
@@ -85,9 +87,9 @@ int vsx_masked_ln_bwd(const void* dy, const void* dy2, int dtype, long lddy, con
 #define VSX_EPI_ATOMIC 4    /* out += acc (fp32 atomics; weight gradients, split-K over the reduction)      */
 
 typedef struct vsx_gemm_desc {
-  const void* a[3]; /* bf16 A operand per term */
-  const void* b[3]; /* bf16 B operand per term */
-  int terms;        /* 1 or 3 */
+  const void* a[6]; /* bf16 A operand per term */
+  const void* b[6]; /* bf16 B operand per term */
+  int terms;        /* 1 .. 6 */
   long lda, ldb;
   int a_layout, b_layout;
   int M, N, K;      /* N, K are the COMPUTED extents (kept prefix); reads beyond them are zero-filled by TMA */
@@ -126,14 +128,15 @@ int vsx_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* l
 
 /* ----------------------------------------------------------------------------------------------------
  * Elementwise helpers around the GEMMs.
- * vsx_split_bf16     : hi = bf16(src), lo = bf16(src - hi) (lo may be NULL: plain cast).  Operand preparation for
- *                      vsx_gemm (weights every step; activations only in the fp32 parity mode).
+ * vsx_split_bf16     : hi = bf16(src), lo = bf16(src - hi), lo2 = bf16(src - hi - lo) (lo / lo2 may be NULL: plain
+ *                      cast / 2-way split).  Operand preparation for vsx_gemm (weights every step; activations only
+ *                      in the fp32 parity mode).
  * vsx_scale_mask_cast: out[m,n] = n < n_keep ? g[m,n] * row_scale[m / rows_per_sample] : 0 -- the gradient of
  *                      `x + mask * drop_path(f)` w.r.t. f (nets/supernet_blocks.py:243-253, nets/drop.py:25);
  *                      also the forward of a stand-alone ChannelDrop (nets/channel_drop.py:80-81).
  * vsx_colsum         : out[c] += sum_r x[r,c]  (bias gradients of every nn.Linear).
  * -------------------------------------------------------------------------------------------------- */
-int vsx_split_bf16(const float* src, long lds, void* hi, void* lo, long ldd, int rows, int cols, void* stream);
+int vsx_split_bf16(const float* src, long lds, void* hi, void* lo, void* lo2, long ldd, int rows, int cols, void* stream);
 int vsx_scale_mask_cast(const float* g, long ldg, const float* row_scale, int rows_per_sample, int n_keep, void* out,
                         int dtype, long ldo, int rows, int cols, void* stream);
 int vsx_colsum(const void* x, int dtype, long ldx, int rows, int cols, float* out, void* stream);

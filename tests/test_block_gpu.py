@@ -64,7 +64,7 @@ def test_block_parity(ci, prec):
         y.backward(gout.cuda())
     torch.cuda.synchronize()
     assert cur == cur_o
-    tol = 2e-5 if prec == 'fp32' else 2e-2
+    tol = 2e-5 if prec == 'fp32' else 2e-2      # fp32 parity path / bf16 training path, rel-L2 vs the fp64 oracle
     errs = {'y': rel(y, yo)}
     m = O.prefix_mask(c['embed'], C, torch.float64) if c['embed'] is not None else 1.0
     errs['gx'] = rel(xd.grad.double().cpu() * m, xo.grad * m)       # gradients on masked input lanes are dead

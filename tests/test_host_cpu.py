@@ -1,0 +1,158 @@
+"""CPU: host-side logic of the product (no kernels run): sampling protocol, module surface, registry, MAC counter,
+C-ABI export table, and the loud failure when asked to compute without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit_res_oracle as O
+from oracle.cases import CASES, SMALL_DEF, SMALL_SPACE, VIT_RES_TINY
+from vit_search_b200 import _lib, core, macs
+from vit_search_b200 import supernet_config as sc
+from vit_search_b200.nets import (Block, ChannelDrop, FlexibleDistillVisionTransformerSR, MaskedLayerNorm, create_model,
+                                  list_models)
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _small(**kw):
+    return create_model('flexible_vit_sr_patch14_224_patch_output_supernet', network_def=SMALL_DEF, num_classes=1000, drop_rate=0.,
+                        drop_path_rate=0., drop_block_rate=None, num_channels_to_keep=SMALL_SPACE, **kw)
+
+
+def test_abi_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, 'include', 'vsx.h')).read()
+    declared = set(re.findall(r'\b(vsx_[a-z0-9_]+)\s*\(', hdr))
+    declared -= {'vsx_gemm_desc', 'vsx_adamw_tensor'}
+    lib = _lib.lib()                      # loads without a GPU
+    for name in declared:
+        assert hasattr(lib, name), 'libvsx.so does not export %s' % name
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    assert lib.vsx_abi_version() == _lib.ABI_VERSION
+
+
+def test_no_cpu_fallback():
+    blk = Block(64, 2, 32, 128)
+    with pytest.raises(RuntimeError, match='no CPU'):
+        blk(torch.randn(2, 5, 64))
+    with pytest.raises(RuntimeError, match='no CPU'):
+        MaskedLayerNorm(64)(torch.randn(2, 5, 64))
+    m = _small(example_per_arch=2, num_warmup_epochs=0)
+    m.set_epoch(0)
+    with pytest.raises(RuntimeError, match='no CPU'):
+        m(torch.randn(8, 3, 224, 224))
+
+
+def test_state_dict_surface_matches_reference_layout():
+    for nd, sup in ((SMALL_DEF, True), (VIT_RES_TINY, False), (sc.network_def('sr_tiny_mh'), True)):
+        if sup:
+            space = SMALL_SPACE if nd is SMALL_DEF else sc.num_channels_to_keep('sr_tiny_mh')
+            m = create_model('flexible_vit_sr_patch14_224_patch_output_supernet', network_def=nd, num_channels_to_keep=space,
+                             example_per_arch=2, num_warmup_epochs=0)
+        else:
+            m = create_model('flexible_vit_sr_patch14_224_patch_output', network_def=nd)
+        sd, sh = m.state_dict(), O.param_shapes(nd)          # O.param_shapes is asserted against the reference in make_golden
+        assert list(sd) == list(sh)
+        assert all(tuple(sd[k].shape) == tuple(sh[k]) for k in sd)
+    assert len(sd) == 258                                    # SURVEY.md §8b probe for sr_tiny_mh
+    assert m.no_weight_decay() == {'tokens'}
+    assert len(list_models()) == 9
+
+
+@pytest.mark.parametrize('name', [n for n, c in CASES.items() if c['supernet'] and c.get('train', True)])
+def test_sampling_protocol_matches_reference(name):
+    """Same CPU-RNG seed => same sub-architectures as the reference (keeps recorded in the golden files)."""
+    case = CASES[name]
+    m = _small(example_per_arch=case['epa'], num_warmup_epochs=case['warmup'], single_arch=case.get('single', False),
+               hybrid_arch=case.get('hybrid', False))
+    m.set_epoch(case['epoch'])
+    m.train()
+    torch.manual_seed(case['seed'])
+    keeps = m.sample_keeps(case['batch'])
+    flat = [k[n] for k in keeps for n in ('embed', 'attn', 'layer', 'mlp') if n in k]
+    assert flat == np.load(os.path.join(GOLD, name + '.npz'))['keeps'].tolist()
+    perm = m._group_permutation(keeps, case['batch'])
+    if perm is not None:
+        assert sorted(perm) == list(range(case['batch']))
+        sig = [tuple(v[b] for k in keeps for v in k.values()) for b in perm]
+        seen, last = set(), None
+        for s in sig:                                        # groups are contiguous after the permutation
+            assert s == last or s not in seen
+            seen.add(s)
+            last = s
+    m.eval()
+    full = m.sample_keeps(3)
+    assert full[0]['embed'] == [SMALL_DEF[0][1]] * 3         # eval: all-true masks (nets/channel_drop.py:84-88)
+
+
+def test_channel_drop_tables_and_epoch_reset():
+    G = np.load(os.path.join(GOLD, 'functions.npz'))
+    i = 0
+    for epoch in (0, 2, 5, 9):
+        for single in (False, True):
+            cd = ChannelDrop(np.array([96, 64, 128, 32, 80]), num_warmup_epochs=5, example_per_arch=2, single_arch=single)
+            cd.set_epoch(epoch)
+            cd.train()
+            torch.manual_seed(100 + epoch)
+            assert cd.draw(12, 128) == G['cd_draws'][i].tolist()
+            assert cd.keep_table == O.keep_table([96, 64, 128, 32, 80], 12, 2, single, epoch, 5)
+            cd.set_epoch(epoch + 1)
+            assert cd.keep_table is None
+            i += 1
+    cd = ChannelDrop(np.array([64, 32]), num_warmup_epochs=0, example_per_arch=4)
+    cd.set_epoch(0)
+    with pytest.raises(AssertionError):
+        cd.draw(6, 64)                                       # batch not divisible by example_per_arch (reference :123)
+
+
+def test_segments_and_keep_algebra():
+    segs = core.make_segments(6, 64, [64, 64, 44, 44, 44, 64], [32, 32, 32, 64, 64, 64], 64, [64, 64, 0, 0, 44, 64])
+    assert [(s.b0, s.b1, s.ek, s.ik, s.ck, s.active) for s in segs] == [
+        (0, 2, 64, 32, 64, True), (2, 3, 44, 32, 0, False), (3, 4, 44, 64, 0, False), (4, 5, 44, 64, 44, True), (5, 6, 64, 64, 64, True)]
+    from vit_search_b200.nets._masks import and_keep
+    assert and_keep([4, 8], None) == [4, 8] and and_keep([4, 8], [6, 2]) == [4, 2] and and_keep(None, None) is None
+
+
+def test_rewiring_sorts_by_l1_like_reference():
+    torch.manual_seed(0)
+    blk = Block(32, 4, 8, 64)
+    sd0 = {k: v.clone() for k, v in blk.state_dict().items()}
+    blk.rewiring()
+    w1, b1, w2 = sd0['mlp.fc1.weight'], sd0['mlp.fc1.bias'], sd0['mlp.fc2.weight']
+    score = w2.abs().sum(0) + w1.abs().sum(1) + b1.abs()
+    idx = torch.sort(score, descending=True)[1]
+    assert torch.equal(blk.mlp.fc1.weight.data, w1[idx]) and torch.equal(blk.mlp.fc2.weight.data, w2[:, idx])
+    q = sd0['attn.qkv.weight']
+    hs = q.abs().sum(1).reshape(3, 4, 8).sum((0, 2)) + sd0['attn.qkv.bias'].abs().reshape(3, 4, 8).sum((0, 2)) + \
+        sd0['attn.proj.weight'].abs().sum(0).reshape(4, 8).sum(1)
+    hidx = torch.sort(hs, descending=True)[1]
+    assert torch.equal(blk.attn.qkv.weight.data, q.reshape(3, 4, 8, -1)[:, hidx].reshape(96, -1))
+    assert torch.equal(blk.attn.proj.weight.data, sd0['attn.proj.weight'].reshape(-1, 4, 8)[:, hidx].reshape(-1, 32))
+
+
+def test_mac_counter_known_answers():
+    G = np.load(os.path.join(GOLD, 'functions.npz'))
+    assert macs.network_macs(VIT_RES_TINY) == int(G['mac_vit_res_tiny']) == 1794378240     # compute_flop_mac.py __main__, tiny.sh:19
+    assert macs.network_macs(SMALL_DEF) == int(G['mac_small_def'])
+    assert macs.network_macs(sc.network_def('sr_tiny_mh')) == 3497553920
+    assert macs.network_macs(sc.network_def('sr_tiny')) == 3650185728
+    m = _small(example_per_arch=2, num_warmup_epochs=0)
+    m.set_epoch(0)
+    m.train()
+    torch.manual_seed(3)
+    keeps = m.sample_keeps(8)
+    eff = [macs.network_macs(macs.effective_network_def(SMALL_DEF, keeps, b)) for b in range(8)]
+    assert max(eff) <= macs.network_macs(SMALL_DEF) and min(eff) > 0
+
+
+def test_fused_adamw_grouping_matches_timm_rules():
+    from vit_search_b200.engine import FusedAdamW
+    m = _small(example_per_arch=2, num_warmup_epochs=0)
+    opt = FusedAdamW(m, lr=1e-3, weight_decay=0.05)
+    wd = {n: w for n, _, w in opt.entries}
+    assert wd['tokens'] == 0.0 and wd['pos_embed'] == 0.05 and wd['blocks.0.attn.qkv.weight'] == 0.05
+    assert wd['blocks.0.attn.qkv.bias'] == 0.0 and wd['blocks.0.norm1.weight'] == 0.0 and wd['patch_embed.conv1.bn.weight'] == 0.0
+    assert wd['blocks.2.pos_embed'] == 0.05

@@ -130,6 +130,18 @@ def test_gemm_split3_precision(ops):
     out1 = torch.empty(M, N, device='cuda')
     ops.gemm(ah.cuda(), wh.cuda(), K, K, M, N, K, ops.EPI_STORE, out1, N)
     assert 1e-4 < rel(out1, ref) < 1e-2      # plain bf16 is visibly worse: the 3 terms really are accumulated
+    # three bf16 parts per operand, six product terms: fp32-exact (the 'fp32' parity mode of core.py)
+    a3 = (ah, al, (A - ah.float() - al.float()).to(torch.bfloat16))
+    w3 = (wh, wl, (W - wh.float() - wl.float()).to(torch.bfloat16))
+    out6 = torch.empty(M, N, device='cuda')
+    ops.gemm(tuple(t.cuda() for t in a3), tuple(t.cuda() for t in w3), K, K, M, N, K, ops.EPI_STORE, out6, N)
+    e6 = rel(out6, ref)
+    assert e6 < 1e-5 and e6 < 0.7 * rel(out, ref)     # floor = fp32 accumulation inside the tensor core, not the operand split
+    # and the device-side splitter agrees with the host split
+    src = A.cuda()
+    parts = [torch.empty(M, K, device='cuda', dtype=torch.bfloat16) for _ in range(3)]
+    ops.split_bf16(src, K, parts[0], parts[1], K, M, K, lo2=parts[2])
+    assert all(torch.equal(p.cpu(), q) for p, q in zip(parts, a3))
 
 
 @pytest.mark.parametrize('M,N,K', [(256, 128, 128), (300, 136, 200), (1028, 256, 576)])
@@ -187,3 +199,39 @@ def test_gemm_epilogues(ops):
     ref = res.double().clone()
     ref[:, :keep] += scale.double().repeat_interleave(257).view(-1, 1) * acc[:, :keep]
     assert rel(out, ref) < 1e-5
+
+
+# ---------------------------------------------------------------------------------------------- attention core
+@pytest.mark.parametrize('N,H,D,Hk', [(257, 3, 64, 3), (257, 6, 32, 5), (65, 4, 48, 2), (17, 4, 64, 3), (50, 2, 32, 2), (197, 2, 64, 1)])
+@pytest.mark.parametrize('mode', ['bf16_mma', 'bf16_fp32math', 'fp32'])
+def test_attention_core(ops, N, H, D, Hk, mode):
+    B = 3
+    g = torch.Generator().manual_seed(N + H + D)
+    dt_ = torch.float32 if mode == 'fp32' else torch.bfloat16
+    qkv = (torch.randn(B, N, 3, H, D, generator=g) * 1.5).to(dt_)
+    do = torch.randn(B, N, H, D, generator=g).to(dt_)
+    q, k, v = [qkv[:, :, i].double().permute(0, 2, 1, 3).requires_grad_(True) for i in range(3)]   # [B,H,N,D]
+    s = (q @ k.transpose(-1, -2)) * D ** -0.5
+    p = s.softmax(-1)
+    o_ref = (p @ v).permute(0, 2, 1, 3)                                       # [B,N,H,D]
+    keep = torch.zeros(H, dtype=torch.float64)
+    keep[:Hk] = 1
+    (o_ref * do.double() * keep.view(1, 1, H, 1)).sum().backward()
+    dqkv_ref = torch.stack([t.grad.permute(0, 2, 1, 3) for t in (q, k, v)], dim=2)   # [B,N,3,H,D]
+    o_ref = o_ref.detach() * keep.view(1, 1, H, 1)
+    lse_ref = torch.logsumexp(s.detach(), -1)                                 # [B,H,N]
+
+    impl = ops.ATTN_FP32 if mode == 'bf16_fp32math' else ops.ATTN_AUTO
+    qd = qkv.cuda().view(B * N, 3 * H * D)
+    o = torch.full((B * N, H * D), float('nan'), device='cuda', dtype=dt_)
+    lse = torch.zeros(B, H, N, device='cuda')
+    ops.attn_fwd(qd, o, lse, B, N, H, D, Hk, D ** -0.5, impl=impl)
+    tol = 1e-5 if mode == 'fp32' else 8e-3
+    assert rel(o.view(B, N, H, D), o_ref) < tol
+    assert rel(lse[:, :Hk], lse_ref[:, :Hk]) < (1e-6 if mode == 'fp32' else 2e-3)
+    dq = torch.full((B * N, 3 * H * D), float('nan'), device='cuda', dtype=dt_)
+    ops.attn_bwd(qd, o, do.cuda().view(B * N, H * D), lse, dq, B, N, H, D, Hk, D ** -0.5, impl=impl)
+    dq = dq.view(B, N, 3, H, D)
+    assert torch.all(dq[:, :, :, Hk:] == 0) and torch.all(o.view(B, N, H, D)[:, :, Hk:] == 0)
+    for i, nm in enumerate('qkv'):
+        assert rel(dq[:, :, i], dqkv_ref[:, :, i]) < (2e-5 if mode == 'fp32' else 1.5e-2), nm

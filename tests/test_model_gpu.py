@@ -1,10 +1,15 @@
 """Whole-model GPU parity: the CUDA modules against the REFERENCE's own outputs (tests/golden, written by
 oracle/make_golden.py from /root/reference) and against the CPU oracle, forward + backward + one optimizer step.
 
-Tolerances (stated per SURVEY.md §8c / BASELINE.json north star):
-  fp32 parity path (bf16x3 tensor-core GEMMs, fp32 storage): logits rel-L2 <= 1e-3 (north star); we assert 2e-4,
-      parameter-gradient rel-L2 <= 1e-3.
-  bf16 training path: logits rel-L2 <= 3e-2, loss abs <= 3e-2 (the reference's own bf16 autocast is 8.4e-3 from fp64).
+Tolerances (stated per SURVEY.md §8c / BASELINE.json north star "logits within 1e-3 rel"):
+  fp32 parity path (fp32 storage, 6-term split-bf16 tensor-core GEMMs): logits rel-L2 <= 2e-4 asserted (5e-6 observed);
+      parameter gradients rel-L2 <= 2e-4 (2e-5 observed), except the conv-stem conv/BN parameters: 5e-3.
+  bf16 training path: logits rel-L2 <= 3e-2, loss abs <= 3e-2 (the reference's own bf16 autocast sits 8.4e-3 from fp64),
+      parameter gradients <= 8e-2, stem conv/BN parameters <= 0.3.
+Why the stem is looser: its gradients pass through three BatchNorm+ReLU layers whose batch reductions cancel almost
+completely (|sum dz| ~ sqrt(P) |dz| over P = B*112*112 pixels), so ONE ReLU unit flipping sign because a pre-activation moved
+by 1e-7 relative changes d(beta) by ~1/sqrt(P) ~ 3e-3.  The reference's own fp32 run differs from its fp64 run by that much
+on these tensors; with fp32-exact GEMMs our stem gradients match the fp64 oracle to 2e-5 (test_model_full_gradients_vs_oracle).
 """
 import os
 
@@ -56,7 +61,7 @@ def test_model_vs_reference_golden(name, prec):
     train = case.get('train', True)
     m.train(train)
     crit = SoftTargetCrossEntropy()
-    tol_logit, tol_grad = (2e-4, 1e-3) if prec == 'fp32' else (3e-2, 8e-2)
+    tol_logit, tol_grad, tol_stem = (2e-4, 2e-4, 5e-3) if prec == 'fp32' else (3e-2, 8e-2, 0.3)
     with core.precision(prec):
         torch.manual_seed(case['seed'])
         if not train:
@@ -82,7 +87,8 @@ def test_model_vs_reference_golden(name, prec):
             gerr[k] = rel(p.grad, ref) if gn > 0 else p.grad.norm().item()
         else:
             gerr[k] = abs(p.grad.double().norm().item() - gn) / max(gn, 1e-30) if gn > 0 else p.grad.norm().item()
-    bad = {k: v for k, v in gerr.items() if not v < tol_grad}
+    stem = lambda k: k.startswith('patch_embed.conv') and 'conv_proj' not in k    # noqa: E731
+    bad = {k: v for k, v in gerr.items() if not v < (tol_stem if stem(k) else tol_grad)}
     assert not bad, (prec, bad)
     if prec == 'fp32':
         for k, v in m.state_dict().items():
@@ -112,7 +118,7 @@ def test_model_full_gradients_vs_oracle():
     bad = {}
     for k, prm in m.named_parameters():
         e = rel(prm.grad, p[k].grad)
-        if not e < 5e-4:
+        if not e < 1e-4:
             bad[k] = e
     assert not bad, bad
 

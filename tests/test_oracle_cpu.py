@@ -1,0 +1,103 @@
+"""CPU: the oracle restatement against the REFERENCE's outputs (tests/golden/*.npz, written by oracle/make_golden.py
+from the unmodified /root/reference modules).  This is what pins the oracle; it runs without /root/reference."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit_res_oracle as O
+from oracle.cases import CASES, SMALL_DEF, SMALL_SPACE, VIT_RES_TINY
+
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+TOL = 2e-5
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(np.asarray(a)).double(), torch.as_tensor(np.asarray(b)).double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_oracle_matches_reference_golden(name):
+    case = CASES[name]
+    G = np.load(os.path.join(GOLD, name + '.npz'))
+    nd = VIT_RES_TINY if case['net'] == 'vit_res_tiny' else SMALL_DEF
+    w = O.keyed_fill(O.param_shapes(nd), seed=case.get('wseed', 0))
+    p = {k: v.clone().requires_grad_(v.is_floating_point() and 'running' not in k) for k, v in w.items()}
+    B = case['batch']
+    x, t, pt = O.synthetic_batch(B, seed=case.get('xseed', 1234))
+    if not case.get('train', True):
+        with torch.no_grad():
+            cls = O.forward(p, nd, x, None, training=False, eval_full_mask=case['supernet'])
+        assert rel(cls.numpy(), G['cls']) < TOL
+        return
+    keeps = None
+    if case['supernet']:
+        smp = O.Sampler(nd, SMALL_SPACE, case['epa'], case['warmup'], case.get('single', False), case.get('hybrid', False))
+        smp.set_epoch(case['epoch'])
+        torch.manual_seed(case['seed'])
+        keeps = smp.sample(B)
+        flat = [k[n] for k in keeps for n in ('embed', 'attn', 'layer', 'mlp') if n in k]
+        assert flat == G['keeps'].tolist()
+    stats = {}
+    loss, cls, patch = O.train_loss(p, nd, x, t, pt, keeps, new_stats=stats)
+    loss.backward()
+    assert rel(cls.detach().numpy(), G['cls']) < TOL and rel(patch.detach().numpy(), G['patch']) < TOL
+    assert abs(loss.item() - float(G['loss'])) < 1e-5
+    for k in G.files:
+        if k.startswith('g:'):
+            g = p[k[2:]].grad
+            ref = G[k]
+            assert (rel(g.numpy(), ref) < TOL) if np.linalg.norm(ref) > 0 else (g.norm().item() < 1e-12), k
+        elif k.startswith('gn:'):
+            gn = float(G[k])
+            n = p[k[3:]].grad.double().norm().item()
+            assert abs(n - gn) <= TOL * max(gn, 1e-12) + 1e-12, k
+        elif k.startswith('s:'):
+            assert rel(stats[k[2:]].float().numpy(), G[k].astype(np.float32)) < TOL, k
+
+
+def test_function_level_vectors():
+    G = np.load(os.path.join(GOLD, 'functions.npz'))
+    g = torch.Generator().manual_seed(7)
+    B, N, C = 6, 5, 48
+    keep = G['ln_keep'].tolist()
+    x = torch.randn(B, N, C, generator=g) * O.prefix_mask(keep, C, torch.float32)
+    wt = 1 + 0.1 * torch.randn(C, generator=g)
+    bs = 0.1 * torch.randn(C, generator=g)
+    go = torch.randn(B, N, C, generator=g)
+    assert rel(O.masked_layer_norm(x, wt, bs, keep).numpy(), G['ln_y']) < TOL
+    gx, gw, gb = O.masked_layer_norm_backward(go * O.prefix_mask(keep, C, torch.float32), x, wt, keep)
+    assert rel(gx.numpy(), G['ln_gx']) < TOL and rel(gw.numpy(), G['ln_gw']) < TOL and rel(gb.numpy(), G['ln_gb']) < TOL
+    # masked LN == plain LN on the kept slice
+    y = O.masked_layer_norm(x, wt, bs, keep)
+    for b, k in enumerate(keep):
+        ref = torch.nn.functional.layer_norm(x[b, :, :k], (k,), wt[:k], bs[:k], 1e-6)
+        assert rel(y[b, :, :k].numpy(), ref.numpy()) < 1e-5 and float(y[b, :, k:].abs().max() if k < C else 0) == 0
+    # ChannelDrop tables / draws across warm-up epochs
+    i = 0
+    for epoch in (0, 2, 5, 9):
+        for single in (False, True):
+            table = O.keep_table([96, 64, 128, 32, 80], 12, 2, single, epoch, 5)
+            torch.manual_seed(100 + epoch)
+            assert O.draw_keep(table, 12, 2, single) == G['cd_draws'][i].tolist()
+            i += 1
+    f = torch.randn(8, 3, 4, generator=g)
+    assert rel(O.drop_path_scale(f, G['dp_keep'].tolist(), 0.25).numpy(), G['dp_y']) < 1e-6
+
+
+def test_oracle_fp64_noise_floor():
+    """fp32 oracle vs its own fp64 evaluation: the noise floor the GPU tolerances sit above."""
+    case = CASES['small_multi']
+    w32 = O.keyed_fill(O.param_shapes(SMALL_DEF))
+    w64 = {k: (v.double() if v.is_floating_point() else v) for k, v in w32.items()}
+    x, t, pt = O.synthetic_batch(4)
+    smp = O.Sampler(SMALL_DEF, SMALL_SPACE, 2, 0)
+    smp.set_epoch(0)
+    torch.manual_seed(1)
+    keeps = smp.sample(4)
+    with torch.no_grad():
+        a = O.forward(w32, SMALL_DEF, x, keeps)[0]
+        b = O.forward(w64, SMALL_DEF, x.double(), keeps)[0]
+    assert rel(a.numpy(), b.numpy()) < 1e-5

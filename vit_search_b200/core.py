@@ -12,9 +12,9 @@ from . import ops
 
 # ------------------------------------------------------------------------------------------------ precision
 # 'bf16' : activations stored in bf16, single-term bf16 tensor-core GEMMs (the training path; bench.py).
-# 'fp32' : activations stored in fp32, every GEMM operand split into bf16 hi+lo and contracted as three
-#          tensor-core terms (hi*hi + lo*hi + hi*lo), attention in fp32 math.  Same kernels, ~1e-5 relative
-#          accuracy -- the path that proves parity with the fp32 reference to the north-star's 1e-3.
+# 'fp32' : activations stored in fp32, every GEMM operand split into three bf16 parts (x = x1+x2+x3, 24 mantissa bits)
+#          and contracted as six tensor-core terms (all cross products down to 2^-24), attention in fp32 math.  Same
+#          kernels, fp32-level accuracy -- the path that proves parity with the fp32 reference to the north-star's 1e-3.
 _precision = 'bf16'
 
 
@@ -72,8 +72,9 @@ class _WeightCache:
         hi = torch.zeros(rows, colsp, device=w.device, dtype=torch.bfloat16) if colsp != cols else \
             torch.empty(rows, cols, device=w.device, dtype=torch.bfloat16)
         lo = torch.zeros_like(hi) if _precision == 'fp32' else None
-        ops.split_bf16(src, cols, hi, lo, colsp, rows, cols) if cols % 4 == 0 else _split_slow(src, hi, lo)
-        val = (hi, lo) if lo is not None else hi
+        lo2 = torch.zeros_like(hi) if _precision == 'fp32' else None
+        ops.split_bf16(src, cols, hi, lo, colsp, rows, cols, lo2=lo2) if cols % 4 == 0 else _split_slow(src, hi, lo, lo2)
+        val = (hi, lo, lo2) if lo is not None else hi
         self.entries[key] = (tag, val)
         return val
 
@@ -81,11 +82,14 @@ class _WeightCache:
         self.entries.clear()
 
 
-def _split_slow(src, hi, lo):
+def _split_slow(src, hi, lo, lo2):
+    """Widths that are not a multiple of 4 (only conv1's [mid, 27] weight): same split with torch ops, once per step."""
     cols = src.shape[1]
     hi[:, :cols] = src.to(torch.bfloat16)
     if lo is not None:
-        lo[:, :cols] = (src - hi[:, :cols].float()).to(torch.bfloat16)
+        r = src - hi[:, :cols].float()
+        lo[:, :cols] = r.to(torch.bfloat16)
+        lo2[:, :cols] = (r - lo[:, :cols].float()).to(torch.bfloat16)
 
 
 weights = _WeightCache()
@@ -107,14 +111,13 @@ class _ActOperands:
             return t
         key = id(t)
         if key not in self.buf:
-            self.buf[key] = (torch.empty(t.shape, device=t.device, dtype=torch.bfloat16),
-                             torch.empty(t.shape, device=t.device, dtype=torch.bfloat16), set())
-        hi, lo, done = self.buf[key]
+            self.buf[key] = tuple(torch.empty(t.shape, device=t.device, dtype=torch.bfloat16) for _ in range(3)) + (set(),)
+        hi, lo, lo2, done = self.buf[key]
         c4 = (cols + 3) // 4 * 4
         if (row0, rows, c4) not in done:
-            ops.split_bf16(t, ld, hi, lo, ld, rows, min(c4, ld), src_off=row0 * ld, dst_off=row0 * ld)
+            ops.split_bf16(t, ld, hi, lo, ld, rows, min(c4, ld), src_off=row0 * ld, dst_off=row0 * ld, lo2=lo2)
             done.add((row0, rows, c4))
-        return (hi, lo)
+        return (hi, lo, lo2)
 
     def invalidate(self, t):
         self.buf.pop(id(t), None)

@@ -5,21 +5,25 @@
 namespace vsx {
 namespace {
 
-// hi = bf16(src); lo = bf16(src - hi) (optional).  4 elements per thread.
-__global__ void split_kernel(const float* __restrict__ src, long lds, bf16* __restrict__ hi, bf16* __restrict__ lo, long ldd, int rows,
-                             int cols4) {
+// hi = bf16(src); lo = bf16(src - hi) (optional); lo2 = bf16(src - hi - lo) (optional).  4 elements per thread.
+__global__ void split_kernel(const float* __restrict__ src, long lds, bf16* __restrict__ hi, bf16* __restrict__ lo, bf16* __restrict__ lo2,
+                             long ldd, int rows, int cols4) {
   const long total = (long)rows * cols4;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long r = i / cols4;
     const int c = (int)(i - r * cols4) * 4;
-    const float4 v = ld4(src + r * lds + c);
-    const bf16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z), h3 = __float2bfloat16_rn(v.w);
-    bf16* hp = hi + r * ldd + c;
-    hp[0] = h0, hp[1] = h1, hp[2] = h2, hp[3] = h3;
-    if (lo != nullptr) {
-      st4(lo + r * ldd + c, make_float4(v.x - __bfloat162float(h0), v.y - __bfloat162float(h1), v.z - __bfloat162float(h2),
-                                        v.w - __bfloat162float(h3)));
+    const float4 v4 = ld4(src + r * lds + c);
+    const float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    float h[4], l[4] = {0.f, 0.f, 0.f, 0.f}, l2[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      h[j] = __bfloat162float(__float2bfloat16_rn(v[j]));
+      if (lo != nullptr) l[j] = __bfloat162float(__float2bfloat16_rn(v[j] - h[j]));
+      l2[j] = (v[j] - h[j]) - l[j];
     }
+    st4(hi + r * ldd + c, make_float4(h[0], h[1], h[2], h[3]));
+    if (lo != nullptr) st4(lo + r * ldd + c, make_float4(l[0], l[1], l[2], l[3]));
+    if (lo2 != nullptr) st4(lo2 + r * ldd + c, make_float4(l2[0], l2[1], l2[2], l2[3]));
   }
 }
 
@@ -86,11 +90,11 @@ int ew_grid(long work_items) {
 
 using namespace vsx;
 
-extern "C" int vsx_split_bf16(const float* src, long lds, void* hi, void* lo, long ldd, int rows, int cols, void* stream) {
+extern "C" int vsx_split_bf16(const float* src, long lds, void* hi, void* lo, void* lo2, long ldd, int rows, int cols, void* stream) {
   VSX_REQUIRE(cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "vsx_split_bf16: cols and pitches must be multiples of 4");
   if (rows <= 0 || cols <= 0) return VSX_OK;
-  split_kernel<<<ew_grid((long)rows * cols / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, lds, (bf16*)hi, (bf16*)lo, ldd,
-                                                                                                 rows, cols / 4);
+  split_kernel<<<ew_grid((long)rows * cols / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, lds, (bf16*)hi, (bf16*)lo, (bf16*)lo2,
+                                                                                                 ldd, rows, cols / 4);
   return check_launch("vsx_split_bf16");
 }
 

@@ -30,9 +30,10 @@ constexpr int TMEM_COLS = 128;
 constexpr int GEMM_THREADS = 192;
 constexpr int SMEM_BYTES = STAGES * (STAGE_A + STAGE_B) + 1024 /*align*/ + 128 /*barriers*/;
 
+constexpr int MAX_TERMS = 6;
 struct TmapPack {
-  CUtensorMap a[3];
-  CUtensorMap b[3];
+  CUtensorMap a[MAX_TERMS];
+  CUtensorMap b[MAX_TERMS];
 };
 
 struct GemmArgs {
@@ -289,7 +290,7 @@ using namespace vsx;
 
 extern "C" int vsx_gemm(const vsx_gemm_desc* d, void* stream) {
   VSX_REQUIRE(d != nullptr, "vsx_gemm: null descriptor");
-  VSX_REQUIRE(d->terms == 1 || d->terms == 3, "vsx_gemm: terms must be 1 or 3 (got %d)", d->terms);
+  VSX_REQUIRE(d->terms >= 1 && d->terms <= MAX_TERMS, "vsx_gemm: terms must be 1..6 (got %d)", d->terms);
   VSX_REQUIRE(d->M > 0 && d->N >= 0 && d->K >= 0, "vsx_gemm: bad extents M=%d N=%d K=%d", d->M, d->N, d->K);
   VSX_REQUIRE(d->lda % 8 == 0 && d->ldb % 8 == 0, "vsx_gemm: operand pitches must be multiples of 8 elements (lda=%ld ldb=%ld)", d->lda, d->ldb);
   VSX_REQUIRE(d->out != nullptr && d->n_out >= d->N && d->n_out <= d->ldo, "vsx_gemm: need N <= n_out <= ldo (N=%d n_out=%d ldo=%ld)", d->N, d->n_out, d->ldo);

@@ -58,11 +58,13 @@ def masked_ln_bwd(dy, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, dgamma,
 def gemm(a, b, lda, ldb, M, N, K, epilogue, out, ldo, *, a_off=0, b_off=0, out_off=0, a_layout=KMAJOR,
          b_layout=KMAJOR, n_out=None, out2=None, ldo2=0, out2_off=0, bias=None, bias_off=0, aux=None, ld_aux=0,
          aux_off=0, row_scale=None, row_scale_off=0, rows_per_sample=1, n_keep=0, split_k=1):
-    """a, b: a bf16 tensor, or a tuple (hi, lo) of bf16 tensors for the split-bf16 (3-term) high-precision mode."""
+    """a, b: a bf16 tensor, or tuples of 2 (3 product terms, ~2^-16) or 3 (6 terms, fp32-exact) bf16 parts whose sum is
+    the fp32 operand (split-bf16 high-precision mode)."""
     d = _lib.GemmDesc()
     if isinstance(a, (tuple, list)):
-        (ah, al), (bh, bl) = a, b
-        terms = [(ah, bh), (al, bh), (ah, bl)]
+        n = min(len(a), len(b))
+        pairs = [(0, 0), (1, 0), (0, 1)] if n == 2 else [(0, 0), (1, 0), (0, 1), (1, 1), (2, 0), (0, 2)]
+        terms = [(a[i], b[j]) for i, j in pairs]
     else:
         terms = [(a, b)]
     for t, (ta, tb) in enumerate(terms):
@@ -107,8 +109,9 @@ def attn_bwd(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, heads_keep,
 
 
 # ------------------------------------------------------------------------------------------------ elementwise
-def split_bf16(src, lds, hi, lo, ldd, rows, cols, src_off=0, dst_off=0):
-    _ck(_lib.lib().vsx_split_bf16(_ptr(src, src_off), lds, _ptr(hi, dst_off), _ptr(lo, dst_off), ldd, rows, cols, _stream()))
+def split_bf16(src, lds, hi, lo, ldd, rows, cols, src_off=0, dst_off=0, lo2=None):
+    _ck(_lib.lib().vsx_split_bf16(_ptr(src, src_off), lds, _ptr(hi, dst_off), _ptr(lo, dst_off), _ptr(lo2, dst_off), ldd, rows, cols,
+                                  _stream()))
 
 
 def scale_mask_cast(g, ldg, row_scale, rows_per_sample, n_keep, out, ldo, rows, cols, g_off=0, out_off=0, scale_off=0):
