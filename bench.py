@@ -238,8 +238,8 @@ def run_ours(args):
     for _ in range(2):
         dev_step()
     torch.cuda.synchronize()
-    gemm_ms = sum(a.elapsed_time(b) for a, b, _ in ops.PROFILE)
-    gemm_flops = sum(f for _, _, f in ops.PROFILE)
+    gemm_ms = sum(r[0].elapsed_time(r[1]) for r in ops.PROFILE)
+    gemm_flops = sum(r[2] for r in ops.PROFILE)
     n_gemm = len(ops.PROFILE)
     ops.PROFILE = None
     keeps = model.last_keeps

@@ -87,7 +87,7 @@ def gemm(a, b, lda, ldb, M, N, K, epilogue, out, ldo, *, a_off=0, b_off=0, out_o
         e0.record()
         _ck(_lib.lib().vsx_gemm(C.byref(d), _stream()))
         e1.record()
-        PROFILE.append((e0, e1, 2.0 * M * N * K))
+        PROFILE.append((e0, e1, 2.0 * M * N * K, (M, N, K, epilogue, a_layout, b_layout, d.n_out, split_k, len(terms))))
         return
     _ck(_lib.lib().vsx_gemm(C.byref(d), _stream()))
 
