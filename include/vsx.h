@@ -171,6 +171,20 @@ int vsx_bn_bwd_apply(const void* da, const void* y, int dtype, long P, int C, co
                      const float* mean, const float* rstd, const double* sums, void* dy, float* dgamma, float* dbeta,
                      void* stream);
 
+/* Direct 3x3 convolution, stride 1, pad 1, C_in = C_out = C (multiple of 8, <= 32) on channels-last bf16 maps -- the
+ * 24->24 ConvBnAct layers of the stem (nets/patch_conv.py:53-54) without an im2col matrix.
+ *   out[p][n] = (add ? add[p][n] : 0) + sum_{tap,k} act(in[p+tap-1][k]) * wt[tap][n][k],  wt: bf16 [9][32][32] zero padded,
+ *   act = relu(x*in_scale[k] + in_shift[k]) when in_scale != NULL (the producing layer's BatchNorm + ReLU), else identity.
+ * stats_mode 1: sums[0..C) += sum(out), sums[C..2C) += sum(out^2)  (this layer's BatchNorm batch statistics);
+ * stats_mode 2: sums += (sum dz, sum dz*zhat), dz = out*[gamma*zhat+beta > 0], zhat = (y_prev-mean)*rstd  (out is a gradient
+ * w.r.t. relu(bn(y_prev)): the reductions vsx_bn_bwd_apply needs).  The data gradient of the conv is this same call with
+ * wt[tap'][ci][co] = W[co][ci][2-ky][2-kx].   vsx_conv3x3_wgrad: dw[co][tap][ci] (fp32) += sum_p dy[p][co]*act(in[p+tap-1][ci]). */
+int vsx_conv3x3(const void* in, const float* in_scale, const float* in_shift, const void* wt, const void* add, void* out, int B,
+                int H, int W, int C, int stats_mode, const void* y_prev, const float* gamma, const float* beta,
+                const float* mean, const float* rstd, double* sums, void* stream);
+int vsx_conv3x3_wgrad(const void* dy, const void* in, const float* in_scale, const float* in_shift, float* dw, int B, int H,
+                      int W, int C, void* stream);
+
 /* Token assembly: x0[b,t,:] = mask * ((t == 0 ? tokens : patches[b,t-1]) + pos_embed[t])  -- replaces cat / expand /
  * add / embed ChannelDrop at nets/vit_sr_supernet.py:399-407; backward gives dpatches (activation dtype), and
  * ACCUMULATES dpos_embed [N,C] and dtokens [C]. */

@@ -235,3 +235,48 @@ def test_attention_core(ops, N, H, D, Hk, mode):
     assert torch.all(dq[:, :, :, Hk:] == 0) and torch.all(o.view(B, N, H, D)[:, :, Hk:] == 0)
     for i, nm in enumerate('qkv'):
         assert rel(dq[:, :, i], dqkv_ref[:, :, i]) < (2e-5 if mode == 'fp32' else 1.5e-2), nm
+
+
+# ---------------------------------------------------------------------------------------------- direct 3x3 conv (stem)
+@pytest.mark.parametrize('C', [24, 32])
+def test_conv3x3_direct(ops, C):
+    """Tensor-core direct conv (forward with fused BN+ReLU input and batch statistics, data gradient with the BN-backward
+    reductions, weight gradient) against torch fp64 math on the same bf16-rounded operands."""
+    import torch.nn.functional as F
+    from vit_search_b200 import core
+    B, H, W = 2, 16, 32
+    g = torch.Generator().manual_seed(C)
+    y_in = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16)
+    sc, sh = 1 + 0.2 * torch.randn(C, generator=g), 0.3 * torch.randn(C, generator=g)
+    wgt = (torch.randn(C, C, 3, 3, generator=g) * 0.1)
+    wq = wgt.to(torch.bfloat16).double()
+    a = F.relu(y_in.double() * sc.double() + sh.double()).to(torch.bfloat16).double()      # the kernel rounds the activated halo to bf16
+    ref = F.conv2d(a.permute(0, 3, 1, 2), wq, padding=1).permute(0, 2, 3, 1)               # [B,H,W,C]
+    wparam = torch.nn.Parameter(wgt.cuda())
+    out = torch.full((B, H, W, C), float('nan'), device='cuda', dtype=torch.bfloat16)
+    sums = torch.zeros(2 * C, device='cuda', dtype=torch.float64)
+    ops.call('conv3x3', y_in.cuda(), sc.cuda(), sh.cuda(), core.weights.get(wparam, 'conv3x3_fwd'), None, out, B, H, W, C, 1, None, None,
+             None, None, None, sums)
+    assert rel(out, ref) < 6e-3
+    o64 = out.double().cpu()
+    assert rel(sums[:C], o64.sum((0, 1, 2))) < 1e-5 and rel(sums[C:], (o64 * o64).sum((0, 1, 2))) < 1e-5
+    # data gradient: dy -> d_a = conv_transpose(dy, W) + add, with (sum dz, sum dz*zhat) of the previous BN
+    dy = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16)
+    add = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16)
+    gam, bet = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    mean, rstd = 0.1 * torch.randn(C, generator=g), 1 + 0.1 * torch.rand(C, generator=g)
+    ref_da = F.conv_transpose2d(dy.double().permute(0, 3, 1, 2), wq, padding=1).permute(0, 2, 3, 1) + add.double()
+    d_a = torch.empty(B, H, W, C, device='cuda', dtype=torch.bfloat16)
+    sums2 = torch.zeros(2 * C, device='cuda', dtype=torch.float64)
+    ops.call('conv3x3', dy.cuda(), None, None, core.weights.get(wparam, 'conv3x3_bwd'), add.cuda(), d_a, B, H, W, C, 2, y_in.cuda(),
+             gam.cuda(), bet.cuda(), mean.cuda(), rstd.cuda(), sums2)
+    assert rel(d_a, ref_da) < 6e-3
+    zh = (y_in.float() - mean) * rstd
+    dz = d_a.float().cpu() * (gam * zh + bet > 0)
+    assert rel(sums2[:C], dz.double().sum((0, 1, 2))) < 1e-4 and rel(sums2[C:], (dz * zh).double().sum((0, 1, 2))) < 1e-4
+    # weight gradient: dW[co][ci][ky][kx] = sum dy[p][co] * a[p + tap - 1][ci]
+    wref = wq.clone().requires_grad_(True)
+    (F.conv2d(a.permute(0, 3, 1, 2), wref, padding=1) * dy.double().permute(0, 3, 1, 2)).sum().backward()
+    dw = torch.zeros(C, 9 * C, device='cuda')
+    ops.call('conv3x3_wgrad', dy.cuda(), y_in.cuda(), sc.cuda(), sh.cuda(), dw, B, H, W, C)
+    assert rel(dw.view(C, 3, 3, C).permute(0, 3, 1, 2), wref.grad) < 2e-3

@@ -64,6 +64,15 @@ class _WeightCache:
         if e is not None and e[0] == tag:
             return e[1]
         src = w.detach()
+        if layout in ('conv3x3_fwd', 'conv3x3_bwd'):
+            # direct-conv operand [9 taps][32 n][32 k] bf16, zero padded (csrc/conv3x3.cu).  fwd: n = out ch, k = in ch;
+            # bwd (data gradient): taps flipped, n = in ch, k = out ch
+            o, i = src.shape[0], src.shape[1]
+            t9 = src.permute(2, 3, 0, 1).reshape(9, o, i) if layout == 'conv3x3_fwd' else src.flip(2, 3).permute(2, 3, 1, 0).reshape(9, i, o)
+            val = torch.zeros(9, 32, 32, device=w.device, dtype=torch.bfloat16)
+            val[:, :t9.shape[1], :t9.shape[2]] = t9.to(torch.bfloat16)
+            self.entries[key] = (tag, val)
+            return val
         if layout == 'ohwi':                       # conv weight [O, I, kh, kw] -> [O, kh*kw*I]
             src = src.permute(0, 2, 3, 1)
         src = src.reshape(src.shape[0], -1).contiguous()

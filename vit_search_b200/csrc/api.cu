@@ -51,22 +51,23 @@ static EncodeTiledFn encode_fn() {
 }
 
 int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
-                 uint32_t box_rows) {
+                 uint32_t box_rows, int dtype) {
+  const uint64_t es = dtype == VSX_F32 ? 4 : 2;
   EncodeTiledFn fn = encode_fn();
   if (fn == nullptr) {
     set_error("cuTensorMapEncodeTiled is not available from the driver");
     return VSX_ERR_CUDA;
   }
-  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld_elems * 2) % 16 != 0 || cols == 0 || rows == 0) {
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld_elems * es) % 16 != 0 || cols == 0 || rows == 0) {
     set_error("make_tmap_2d: operand must be 16-byte aligned with a 16-byte-multiple pitch (base=%p ld=%llu cols=%llu rows=%llu)",
               base, (unsigned long long)ld_elems, (unsigned long long)cols, (unsigned long long)rows);
     return VSX_ERR_ARG;
   }
   cuuint64_t dims[2] = {cols, rows};
-  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint64_t strides[1] = {ld_elems * es};
   cuuint32_t box[2] = {box_cols, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = fn(m, dtype == VSX_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

@@ -7,8 +7,10 @@
 //                              STAGES-deep shared-memory ring, completion on "full" mbarriers
 //   warp 1      MMA issuer   : one elected thread issues tcgen05.mma (128x128x16, cta_group::1); tcgen05.commit
 //                              releases ring slots ("empty" mbarriers) and finally signals the epilogue
-//   warps 2..5  epilogue     : tcgen05.ld of the fp32 accumulator (one TMEM lane = one output row per thread),
-//                              fused bias / GELU / drop-path scale / prefix mask / residual / GELU' / atomic add
+//   warps 2..5  epilogue     : tcgen05.ld of the fp32 accumulator (one TMEM lane = one output row per thread), fused
+//                              bias / GELU / drop-path scale / prefix mask / residual / GELU'; the tile is staged in the
+//                              idle operand ring (128B-swizzled) and leaves by TMA store, or TMA reduce-add for the
+//                              split-K weight gradients; residual / pre-activation tiles arrive by TMA load
 // Two CTAs fit per SM (96 KB shared memory, 128 TMEM columns each), so one tile's epilogue overlaps the other's
 // main loop.  Both operand layouts are supported through the shared-memory descriptors (K-major for the forward
 // pass, MN-major for dgrad / wgrad), so no transposed copies of activations or weights are ever made.
@@ -28,23 +30,18 @@ constexpr int STAGE_A = BM * BK * 2;
 constexpr int STAGE_B = BN * BK * 2;
 constexpr int TMEM_COLS = 128;
 constexpr int GEMM_THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * (STAGE_A + STAGE_B) + 1024 /*align*/ + 128 /*barriers*/;
+constexpr int SMEM_BYTES = STAGES * (STAGE_A + STAGE_B) + 1024 /*align*/ + 128 /*barriers, tmem slot*/ + 512 /*bias tile*/;
 
 constexpr int MAX_TERMS = 6;
 struct TmapPack {
   CUtensorMap a[MAX_TERMS];
   CUtensorMap b[MAX_TERMS];
+  CUtensorMap out, out2, aux;   // epilogue tiles (128B-swizzled boxes of 128 rows x 128 bytes)
 };
 
 struct GemmArgs {
   int M, N, K, num_kb, terms, a_mn, b_mn, n_out, split_k;
-  void* out;
-  long ldo;
-  void* out2;
-  long ldo2;
   const float* bias;
-  const void* aux;
-  long ld_aux;
   const float* row_scale;
   int rows_per_sample, n_keep;
 };
@@ -63,89 +60,61 @@ __device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn) {
          ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- epilogue staging (shared memory, TMA layout)
+// A staged tile is a row of 16 KB boxes: [128 rows][128 bytes], 16-byte chunks XOR-swizzled with (row & 7) -- the
+// SWIZZLE_128B layout the output / aux tensor maps use.  bf16: 64 columns per box, fp32: 32 columns per box.
+// Thread = tile row; a 512-byte warp access to one chunk column touches each bank group 4 times = the 4-wavefront minimum.
+constexpr int BOX_BYTES = 128 * 128;
+
+__device__ __forceinline__ uint32_t box_off(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+// 32 consecutive columns starting at tile column c (multiple of 32) of row `row`
 template <typename OutT>
-__device__ __forceinline__ void store32(OutT* dst, const float (&v)[32], int n, int n_out);
+__device__ __forceinline__ void stage_write32(uint8_t* tile, int row, int c, const float (&v)[32]);
 template <>
-__device__ __forceinline__ void store32<float>(float* dst, const float (&v)[32], int n, int n_out) {
+__device__ __forceinline__ void stage_write32<float>(uint8_t* tile, int row, int c, const float (&v)[32]) {
+  uint8_t* box = tile + (c / 32) * BOX_BYTES;
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (n + 4 * i < n_out) st4(dst + 4 * i, make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]));
+  for (int i = 0; i < 8; ++i) *reinterpret_cast<float4*>(box + box_off(row, i)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
 }
 template <>
-__device__ __forceinline__ void store32<bf16>(bf16* dst, const float (&v)[32], int n, int n_out) {
+__device__ __forceinline__ void stage_write32<bf16>(uint8_t* tile, int row, int c, const float (&v)[32]) {
+  uint8_t* box = tile + (c / 64) * BOX_BYTES;
+  const int ch0 = (c % 64) / 8;
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
-    if (n + 8 * i < n_out) {
-      uint4 r;
-      r.x = pack_bf16(v[8 * i], v[8 * i + 1]);
-      r.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
-      r.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
-      r.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
-      *reinterpret_cast<uint4*>(dst + 8 * i) = r;
-    }
+  for (int i = 0; i < 4; ++i) {
+    uint4 r;
+    r.x = pack_bf16(v[8 * i], v[8 * i + 1]);
+    r.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+    r.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+    r.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+    *reinterpret_cast<uint4*>(box + box_off(row, ch0 + i)) = r;
+  }
 }
-template <typename T>
-__device__ __forceinline__ void load32(const T* src, float (&v)[32], int n, int n_lim) {
+template <typename OutT>
+__device__ __forceinline__ void stage_read32(const uint8_t* tile, int row, int c, float (&v)[32]);
+template <>
+__device__ __forceinline__ void stage_read32<float>(const uint8_t* tile, int row, int c, float (&v)[32]) {
+  const uint8_t* box = tile + (c / 32) * BOX_BYTES;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (n + 4 * i < n_lim) t = ld4(src + 4 * i);
+    const float4 t = *reinterpret_cast<const float4*>(box + box_off(row, i));
     v[4 * i] = t.x, v[4 * i + 1] = t.y, v[4 * i + 2] = t.z, v[4 * i + 3] = t.w;
   }
 }
-
-// One output row `m`, 32 consecutive columns starting at `n`.
-template <int EPI, typename OutT>
-__device__ __forceinline__ void epilogue_row(const GemmArgs& g, int m, int n, float (&v)[32]) {
-  if (EPI == VSX_EPI_ATOMIC) {
-    float* dst = reinterpret_cast<float*>(g.out) + (long)m * g.ldo + n;
+template <>
+__device__ __forceinline__ void stage_read32<bf16>(const uint8_t* tile, int row, int c, float (&v)[32]) {
+  const uint8_t* box = tile + (c / 64) * BOX_BYTES;
+  const int ch0 = (c % 64) / 8;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = n + 4 * i;
-      if (c + 3 < g.N && (g.ldo & 3) == 0) {
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * i), "f"(v[4 * i]), "f"(v[4 * i + 1]),
-                     "f"(v[4 * i + 2]), "f"(v[4 * i + 3])
-                     : "memory");
-      } else {
+  for (int i = 0; i < 4; ++i) {
+    const uint4 r = *reinterpret_cast<const uint4*>(box + box_off(row, ch0 + i));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (c + j < g.N) atomicAdd(dst + 4 * i + j, v[4 * i + j]);
-      }
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+      v[8 * i + 2 * j] = f.x, v[8 * i + 2 * j + 1] = f.y;
     }
-    return;
-  }
-  if (g.bias != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (n + j < g.N) v[j] += __ldg(g.bias + n + j);
-  }
-  if (EPI == VSX_EPI_STORE) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (n + j >= g.N) v[j] = 0.f;
-    store32<OutT>(reinterpret_cast<OutT*>(g.out) + (long)m * g.ldo + n, v, n, g.n_out);
-  } else if (EPI == VSX_EPI_GELU) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (n + j >= g.N) v[j] = 0.f;
-    store32<OutT>(reinterpret_cast<OutT*>(g.out) + (long)m * g.ldo + n, v, n, g.n_out);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);   // gelu(0) = 0 keeps the zero fill
-    store32<OutT>(reinterpret_cast<OutT*>(g.out2) + (long)m * g.ldo2 + n, v, n, g.n_out);
-  } else if (EPI == VSX_EPI_RESIDUAL) {
-    const float s = g.row_scale != nullptr ? __ldg(g.row_scale + m / g.rows_per_sample) : 1.0f;
-    float r[32];
-    load32<float>(reinterpret_cast<const float*>(g.aux) + (long)m * g.ld_aux + n, r, n, g.n_out);
-    const int lim = g.n_keep < g.N ? g.n_keep : g.N;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) r[j] += (n + j < lim) ? s * v[j] : 0.f;
-    store32<float>(reinterpret_cast<float*>(g.out) + (long)m * g.ldo + n, r, n, g.n_out);
-  } else if (EPI == VSX_EPI_GELUGRAD) {
-    float u[32];
-    load32<OutT>(reinterpret_cast<const OutT*>(g.aux) + (long)m * g.ld_aux + n, u, n, g.n_out);
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = (n + j < g.N) ? v[j] * gelu_grad_f(u[j]) : 0.f;
-    store32<OutT>(reinterpret_cast<OutT*>(g.out) + (long)m * g.ldo + n, v, n, g.n_out);
   }
 }
 
@@ -158,11 +127,13 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
   const uint32_t sA = base, sB = base + STAGES * STAGE_A;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (STAGE_A + STAGE_B));
   const uint32_t bar0 = base + STAGES * (STAGE_A + STAGE_B);
-  // bars: [0,S) full, [S,2S) empty, [2S] accumulator ready; then the TMEM base address slot
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  // bars: [0,S) full, [S,2S) empty, [2S] accumulator ready, [2S+1] aux tile landed; then the TMEM base slot and the bias tile
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * STAGES + 4);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
   const uint32_t acc_bar = bar0 + 8u * (2 * STAGES);
+  const uint32_t aux_bar = bar0 + 8u * (2 * STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -183,6 +154,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
       tma_prefetch_desc(&maps.a[t]);
       tma_prefetch_desc(&maps.b[t]);
     }
+    tma_prefetch_desc(&maps.out);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -191,6 +163,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
         mbar_init(empty_bar(s), 1);
       }
       mbar_init(acc_bar, 1);
+      mbar_init(aux_bar, 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -243,24 +216,93 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
     }
     umma_commit(acc_bar);          // accumulator complete
   } else if (warp >= 2) {
-    // ---------------- epilogue ----------------
-    const int q = warp & 3;        // TMEM lane quarter this warp may access
-    const int m = m0 + q * 32 + lane;
+    // ---------------- epilogue: TMEM -> registers -> fused math -> swizzled smem tile -> TMA store / reduce-add ----------------
+    constexpr int BOXC = 128 / (int)sizeof(OutT);     // columns per 128-byte box row
+    const int q = warp & 3;                           // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;                    // tile row == TMEM lane
+    const int et = (int)threadIdx.x - 64;             // 0..127 among the epilogue threads
+    const int m = m0 + row;
+    const int ncols = min(BN, g.n_out - n0);          // columns of this tile that exist in the output
+    bias_s[et] = (g.bias != nullptr && n0 + et < g.N) ? __ldg(g.bias + n0 + et) : 0.f;
     if (has_mma) {
-      mbar_wait(acc_bar, 0);
+      mbar_wait(acc_bar, 0);                          // all MMAs done => the operand ring is free: reuse it as the staging tile
       tc_fence_after();
     }
-    for (int c = 0; c < BN; c += 32) {
-      if (n0 + c >= g.n_out) break;
-      float v[32];
-      if (has_mma) {
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-        tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = 0.f;
+    uint8_t* tile = smem;                             // generic view of the (now idle) stage memory
+    // GELU writes two tiles (pre-activation and activation): side by side for bf16 (2 x 32 KB); for fp32 (2 x 64 KB > ring)
+    // the activation tile is produced in a second pass over the accumulator after the first tile has left.
+    constexpr bool TWO_PASS = (EPI == VSX_EPI_GELU) && sizeof(OutT) == 4;
+    uint8_t* tile2 = TWO_PASS ? smem : smem + (BN / BOXC) * BOX_BYTES;
+    const int nbox = (ncols + BOXC - 1) / BOXC;
+    if (EPI == VSX_EPI_RESIDUAL || EPI == VSX_EPI_GELUGRAD) {
+      if (et == 0) {                                  // aux tile (residual stream / pre-activation) by TMA, OOB zero-filled
+        mbar_expect_tx(aux_bar, (uint32_t)nbox * BOX_BYTES);
+        for (int bx = 0; bx < nbox; ++bx) tma_load_2d(base + bx * BOX_BYTES, &maps.aux, aux_bar, n0 + bx * BOXC, m0);
       }
-      if (m < g.M) epilogue_row<EPI, OutT>(g, m, n0 + c, v);
+    }
+    named_bar_sync(1, 128);                           // bias tile visible
+    if (EPI == VSX_EPI_RESIDUAL || EPI == VSX_EPI_GELUGRAD) mbar_wait(aux_bar, 0);
+    float scale = 1.0f;
+    if (EPI == VSX_EPI_RESIDUAL && g.row_scale != nullptr && m < g.M) scale = __ldg(g.row_scale + m / g.rows_per_sample);
+    const int lim = g.n_keep < g.N ? g.n_keep : g.N;
+    for (int pass = 0; pass < (TWO_PASS ? 2 : 1); ++pass) {
+      for (int c = 0; c < BN; c += 32) {
+        if (c >= ncols) break;
+        float v[32];
+        if (has_mma) {
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        const int n = n0 + c;
+        if (EPI == VSX_EPI_ATOMIC) {
+          stage_write32<float>(tile, row, c, v);
+        } else if (EPI == VSX_EPI_STORE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (n + j < g.N) ? v[j] + bias_s[c + j] : 0.f;
+          stage_write32<OutT>(tile, row, c, v);
+        } else if (EPI == VSX_EPI_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (n + j < g.N) ? v[j] + bias_s[c + j] : 0.f;
+          if (!TWO_PASS || pass == 0) stage_write32<OutT>(tile, row, c, v);
+          if (!TWO_PASS || pass == 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);   // gelu(0) = 0 keeps the zero fill
+            stage_write32<OutT>(tile2, row, c, v);
+          }
+        } else if (EPI == VSX_EPI_RESIDUAL) {
+          float r[32];
+          stage_read32<float>(tile, row, c, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] += (n + j < lim) ? scale * (v[j] + bias_s[c + j]) : 0.f;
+          stage_write32<float>(tile, row, c, r);
+        } else if (EPI == VSX_EPI_GELUGRAD) {
+          float u[32];
+          stage_read32<OutT>(tile, row, c, u);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = (n + j < g.N) ? v[j] * gelu_grad_f(u[j]) : 0.f;
+          stage_write32<OutT>(tile, row, c, v);
+        }
+      }
+      fence_proxy_async();                            // generic-proxy smem writes -> visible to the TMA (async proxy)
+      named_bar_sync(1, 128);
+      if (et == 0) {
+        for (int bx = 0; bx < nbox; ++bx) {
+          if (EPI == VSX_EPI_ATOMIC) {
+            tma_reduce_add_2d(&maps.out, base + bx * BOX_BYTES, n0 + bx * BOXC, m0);
+          } else if (EPI == VSX_EPI_GELU) {
+            if (!TWO_PASS || pass == 0) tma_store_2d(&maps.out, base + bx * BOX_BYTES, n0 + bx * BOXC, m0);
+            if (!TWO_PASS) tma_store_2d(&maps.out2, base + (BN / BOXC + bx) * BOX_BYTES, n0 + bx * BOXC, m0);
+            if (TWO_PASS && pass == 1) tma_store_2d(&maps.out2, base + bx * BOX_BYTES, n0 + bx * BOXC, m0);
+          } else {
+            tma_store_2d(&maps.out, base + bx * BOX_BYTES, n0 + bx * BOXC, m0);
+          }
+        }
+        tma_store_commit_wait();                      // shared memory must stay valid until the TMA has read it
+      }
+      if (TWO_PASS) named_bar_sync(1, 128);           // the staging tile may be overwritten by the second pass
     }
   }
   tc_fence_before();
@@ -296,15 +338,14 @@ extern "C" int vsx_gemm(const vsx_gemm_desc* d, void* stream) {
   VSX_REQUIRE(d->out != nullptr && d->n_out >= d->N && d->n_out <= d->ldo, "vsx_gemm: need N <= n_out <= ldo (N=%d n_out=%d ldo=%ld)", d->N, d->n_out, d->ldo);
   const bool f32 = d->out_dtype == VSX_F32;
   VSX_REQUIRE(d->out_dtype == VSX_F32 || d->out_dtype == VSX_BF16, "vsx_gemm: bad out_dtype %d", d->out_dtype);
-  if (d->epilogue != VSX_EPI_ATOMIC)
-    VSX_REQUIRE(d->n_out % (f32 ? 4 : 8) == 0 && d->ldo % (f32 ? 4 : 8) == 0, "vsx_gemm: n_out/ldo must be multiples of %d (n_out=%d ldo=%ld)", f32 ? 4 : 8, d->n_out, d->ldo);
+  VSX_REQUIRE(d->ldo % (f32 ? 4 : 8) == 0, "vsx_gemm: ldo must be a multiple of %d elements (16 bytes) for the TMA store (ldo=%ld)", f32 ? 4 : 8, d->ldo);
   if (d->n_out == 0) return VSX_OK;
 
   GemmArgs g;
   g.M = d->M, g.N = d->N, g.K = d->K, g.num_kb = ceil_div(d->K, BK), g.terms = d->terms;
   g.a_mn = d->a_layout == VSX_MNMAJOR, g.b_mn = d->b_layout == VSX_MNMAJOR;
   g.n_out = d->n_out, g.split_k = d->split_k < 1 ? 1 : d->split_k;
-  g.out = d->out, g.ldo = d->ldo, g.out2 = d->out2, g.ldo2 = d->ldo2, g.bias = d->bias, g.aux = d->aux, g.ld_aux = d->ld_aux;
+  g.bias = d->bias;
   g.row_scale = d->row_scale, g.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1, g.n_keep = d->n_keep;
 
   TmapPack maps;
@@ -325,11 +366,30 @@ extern "C" int vsx_gemm(const vsx_gemm_desc* d, void* stream) {
   }
   dim3 grid(ceil_div(d->M, BM), ceil_div(d->n_out, BN), 1);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  {  // epilogue tensor maps: [M rows, n_out columns], boxes of 128 rows x 128 bytes
+    const int odt = f32 ? VSX_F32 : VSX_BF16;
+    const uint32_t boxc = f32 ? 32 : 64;
+    const uint64_t ocols = d->epilogue == VSX_EPI_ATOMIC ? (uint64_t)d->N : (uint64_t)d->n_out;
+    if (ocols == 0) return VSX_OK;
+    int rc = make_tmap_2d(&maps.out, d->out, ocols, (uint64_t)d->M, (uint64_t)d->ldo, boxc, BM, odt);
+    if (rc) return rc;
+    maps.out2 = maps.out;
+    maps.aux = maps.out;
+    if (d->epilogue == VSX_EPI_GELU) {
+      VSX_REQUIRE(d->out2 != nullptr && d->ldo2 >= d->n_out && d->ldo2 % (f32 ? 4 : 8) == 0, "vsx_gemm: GELU epilogue needs out2 with a 16-byte-multiple pitch");
+      rc = make_tmap_2d(&maps.out2, d->out2, ocols, (uint64_t)d->M, (uint64_t)d->ldo2, boxc, BM, odt);
+      if (rc) return rc;
+    }
+    if (d->epilogue == VSX_EPI_RESIDUAL || d->epilogue == VSX_EPI_GELUGRAD) {
+      VSX_REQUIRE(d->aux != nullptr && d->ld_aux % (f32 ? 4 : 8) == 0, "vsx_gemm: this epilogue needs aux with a 16-byte-multiple pitch");
+      rc = make_tmap_2d(&maps.aux, d->aux, ocols, (uint64_t)d->M, (uint64_t)d->ld_aux, boxc, BM, odt);
+      if (rc) return rc;
+    }
+  }
   switch (d->epilogue) {
     case VSX_EPI_STORE:
       return f32 ? launch<VSX_EPI_STORE, float>(maps, g, grid, st) : launch<VSX_EPI_STORE, bf16>(maps, g, grid, st);
     case VSX_EPI_GELU:
-      VSX_REQUIRE(d->out2 != nullptr && d->ldo2 >= d->n_out, "vsx_gemm: GELU epilogue needs out2");
       return f32 ? launch<VSX_EPI_GELU, float>(maps, g, grid, st) : launch<VSX_EPI_GELU, bf16>(maps, g, grid, st);
     case VSX_EPI_RESIDUAL:
       VSX_REQUIRE(f32 && d->aux != nullptr, "vsx_gemm: RESIDUAL epilogue is fp32 and needs aux");

@@ -30,9 +30,13 @@ class ConvBnAct(nn.Module):
 
 
 def _bn_train(y, P, C, bn, dt):
-    dev = y.device
-    sums = torch.zeros(2 * C, device=dev, dtype=torch.float64)
+    sums = torch.zeros(2 * C, device=y.device, dtype=torch.float64)
     ops.call('bn_stats', y, dt, P, C, sums)
+    return _bn_finalize(sums, P, C, bn)
+
+
+def _bn_finalize(sums, P, C, bn):
+    dev = sums.device
     scale, shift, mean, rstd = (torch.empty(C, device=dev) for _ in range(4))
     track = bn.track_running_stats and bn.running_mean is not None
     ops.call('bn_finalize', sums, P, C, bn.weight, bn.bias, float(bn.eps), BN_MOMENTUM if bn.momentum is None else float(bn.momentum),
@@ -77,16 +81,32 @@ class _StemFn(torch.autograd.Function):
         y1 = torch.empty(P, Cm, device=dev, dtype=T)
         conv(A1, k1, w1, y1)
         s1 = _bn_train(y1, P, Cm, bns[0], dt) if train else _bn_eval(bns[0])
-        A2 = torch.empty(P, 9 * Cm, device=dev, dtype=T)
-        ops.call('im2col', y1, s1[0], s1[1], None, None, None, dt, 0, H1 * W1 * Cm, Cm, B, H1, W1, Cm, 3, 1, 1, A2, dt, 9 * Cm)
+        direct = T == torch.bfloat16 and Cm % 8 == 0 and H1 % 8 == 0 and W1 % 16 == 0     # tensor-core direct conv (csrc/conv3x3.cu)
+        A2 = A3 = None
         y2 = torch.empty(P, Cm, device=dev, dtype=T)
-        conv(A2, 9 * Cm, w2, y2)
-        s2 = _bn_train(y2, P, Cm, bns[1], dt) if train else _bn_eval(bns[1])
-        A3 = torch.empty(P, 9 * Cm, device=dev, dtype=T)
-        ops.call('im2col', y2, s2[0], s2[1], None, None, None, dt, 0, H1 * W1 * Cm, Cm, B, H1, W1, Cm, 3, 1, 1, A3, dt, 9 * Cm)
         y3 = torch.empty(P, Cm, device=dev, dtype=T)
-        conv(A3, 9 * Cm, w3, y3)
-        s3 = _bn_train(y3, P, Cm, bns[2], dt) if train else _bn_eval(bns[2])
+
+        def conv3(y_in, s_in, w, y_out, bn):
+            """3x3 conv of relu(bn(y_in)) with this layer's batch statistics fused into the epilogue."""
+            sums = torch.zeros(2 * Cm, device=dev, dtype=torch.float64) if train else None
+            ops.call('conv3x3', y_in, s_in[0], s_in[1], weights.get(w, 'conv3x3_fwd'), None, y_out, B, H1, W1, Cm, 1 if train else 0,
+                     None, None, None, None, None, sums)
+            if not train:
+                return _bn_eval(bn)
+            return _bn_finalize(sums, P, Cm, bn)
+
+        if direct:
+            s2 = conv3(y1, s1, w2, y2, bns[1])
+            s3 = conv3(y2, s2, w3, y3, bns[2])
+        else:
+            A2 = torch.empty(P, 9 * Cm, device=dev, dtype=T)
+            ops.call('im2col', y1, s1[0], s1[1], None, None, None, dt, 0, H1 * W1 * Cm, Cm, B, H1, W1, Cm, 3, 1, 1, A2, dt, 9 * Cm)
+            conv(A2, 9 * Cm, w2, y2)
+            s2 = _bn_train(y2, P, Cm, bns[1], dt) if train else _bn_eval(bns[1])
+            A3 = torch.empty(P, 9 * Cm, device=dev, dtype=T)
+            ops.call('im2col', y2, s2[0], s2[1], None, None, None, dt, 0, H1 * W1 * Cm, Cm, B, H1, W1, Cm, 3, 1, 1, A3, dt, 9 * Cm)
+            conv(A3, 9 * Cm, w3, y3)
+            s3 = _bn_train(y3, P, Cm, bns[2], dt) if train else _bn_eval(bns[2])
         kp = k * k * Cm
         A4 = torch.empty(B * Hp * Wp, core.up8(kp), device=dev, dtype=T)
         ops.call('im2col', y3, s3[0], s3[1], y1, s1[0], s1[1], dt, 0, H1 * W1 * Cm, Cm, B, H1, W1, Cm, k, k, 0, A4, dt, A4.shape[1])
@@ -119,13 +139,14 @@ class _StemFn(torch.autograd.Function):
         def wgrad(dy, a_col, kdim, like):
             """dW (ohwi layout [O, kdim]) = dy^T a_col, then back to the parameter's [O, I, kh, kw] layout."""
             O = dy.shape[1]
-            dw = torch.zeros(O, kdim, device=dev)
+            ldw = (kdim + 3) // 4 * 4                  # 16-byte row pitch for the TMA reduce-add
+            dw = torch.zeros(O, ldw, device=dev)
             a = acts.get(dy, O, 0, dy.shape[0], O)
             bcol = acts.get(a_col, a_col.shape[1], 0, a_col.shape[0], kdim)
-            ops.gemm(a, bcol, O, a_col.shape[1], O, kdim, dy.shape[0], ops.EPI_ATOMIC, dw, kdim, a_layout=ops.MNMAJOR,
+            ops.gemm(a, bcol, O, a_col.shape[1], O, kdim, dy.shape[0], ops.EPI_ATOMIC, dw, ldw, a_layout=ops.MNMAJOR,
                      b_layout=ops.MNMAJOR, split_k=split_k_for(O, kdim, dy.shape[0]))
             kh = like.shape[-1]
-            return dw.view(O, kh, kh, like.shape[1]).permute(0, 3, 1, 2).contiguous()
+            return dw[:, :kdim].reshape(O, kh, kh, like.shape[1]).permute(0, 3, 1, 2).contiguous()
 
         def dgrad(dy, w, kdim, out):
             wc = weights.get(w, 'ohwi')
@@ -147,18 +168,38 @@ class _StemFn(torch.autograd.Function):
         d_out = torch.empty(P, Cm, device=dev, dtype=T)      # gradient of (a3 + a1)
         ops.call('col2im', dA4, A4.shape[1], None, dt, B, H1, W1, Cm, k, k, 0, d_out, H1 * W1 * Cm, Cm)
         dy3, d_g3, d_b3 = bn_bwd(d_out, y3, g3, b3, s3)
-        d_w3 = wgrad(dy3, A3, 9 * Cm, w3)
-        dA = torch.empty(P, 9 * Cm, device=dev, dtype=T)
-        dgrad(dy3, w3, 9 * Cm, dA)
         d_a2 = torch.empty(P, Cm, device=dev, dtype=T)
-        ops.call('col2im', dA, 9 * Cm, None, dt, B, H1, W1, Cm, 3, 1, 1, d_a2, H1 * W1 * Cm, Cm)
-        dy2, d_g2, d_b2 = bn_bwd(d_a2, y2, g2, b2, s2)
-        d_w2 = wgrad(dy2, A2, 9 * Cm, w2)
-        acts.invalidate(dA)
-        dgrad(dy2, w2, 9 * Cm, dA)
         d_a1 = torch.empty(P, Cm, device=dev, dtype=T)
-        ops.call('col2im', dA, 9 * Cm, d_out, dt, B, H1, W1, Cm, 3, 1, 1, d_a1, H1 * W1 * Cm, Cm)
-        dy1, d_g1, d_b1 = bn_bwd(d_a1, y1, g1, b1, s1)
+        if A3 is None:     # direct tensor-core convs: weight gradient, and data gradient with the BN-backward reductions fused
+            def wgrad3(dy, y_in, s_in, like):
+                dw = torch.zeros(Cm, 9 * Cm, device=dev)
+                ops.call('conv3x3_wgrad', dy, y_in, s_in[0], s_in[1], dw, B, H1, W1, Cm)
+                return dw.view(Cm, 3, 3, like.shape[1]).permute(0, 3, 1, 2).contiguous()
+
+            def dgrad3(dy, w, add, d_a, y_prev, gam, bet, st):
+                sums = torch.zeros(2 * Cm, device=dev, dtype=torch.float64)
+                ops.call('conv3x3', dy, None, None, weights.get(w, 'conv3x3_bwd'), add, d_a, B, H1, W1, Cm, 2, y_prev, gam, bet, st[2],
+                         st[3], sums)
+                dyp = torch.empty(P, Cm, device=dev, dtype=T)
+                dgam, dbet = torch.zeros(Cm, device=dev), torch.zeros(Cm, device=dev)
+                ops.call('bn_bwd_apply', d_a, y_prev, dt, P, Cm, gam, bet, st[2], st[3], sums, dyp, dgam, dbet)
+                return dyp, dgam, dbet
+
+            d_w3 = wgrad3(dy3, y2, s2, w3)
+            dy2, d_g2, d_b2 = dgrad3(dy3, w3, None, d_a2, y2, g2, b2, s2)
+            d_w2 = wgrad3(dy2, y1, s1, w2)
+            dy1, d_g1, d_b1 = dgrad3(dy2, w2, d_out, d_a1, y1, g1, b1, s1)
+        else:
+            d_w3 = wgrad(dy3, A3, 9 * Cm, w3)
+            dA = torch.empty(P, 9 * Cm, device=dev, dtype=T)
+            dgrad(dy3, w3, 9 * Cm, dA)
+            ops.call('col2im', dA, 9 * Cm, None, dt, B, H1, W1, Cm, 3, 1, 1, d_a2, H1 * W1 * Cm, Cm)
+            dy2, d_g2, d_b2 = bn_bwd(d_a2, y2, g2, b2, s2)
+            d_w2 = wgrad(dy2, A2, 9 * Cm, w2)
+            acts.invalidate(dA)
+            dgrad(dy2, w2, 9 * Cm, dA)
+            ops.call('col2im', dA, 9 * Cm, d_out, dt, B, H1, W1, Cm, 3, 1, 1, d_a1, H1 * W1 * Cm, Cm)
+            dy1, d_g1, d_b1 = bn_bwd(d_a1, y1, g1, b1, s1)
         d_w1 = wgrad(dy1, A1, k1, w1)
         return (None, None, d_w1, d_g1, d_b1, d_w2, d_g2, d_b2, d_w3, d_g3, d_b3, d_wp, d_bp)
 
@@ -220,11 +261,12 @@ class _PatchProjFn(torch.autograd.Function):
         ops.scale_mask_cast(g.contiguous().view(R, C), C, None, 1, C, dtok, C, R, C)
         db = torch.zeros(C, device=g.device)
         ops.colsum(dtok, C, R, C, db)
-        dw = torch.zeros(C, kd, device=g.device)
-        ops.gemm(acts.get(dtok, C, 0, R, C), acts.get(A, A.shape[1], 0, R, kd), C, A.shape[1], C, kd, R, ops.EPI_ATOMIC, dw, kd,
+        ldw = (kd + 3) // 4 * 4
+        dw = torch.zeros(C, ldw, device=g.device)
+        ops.gemm(acts.get(dtok, C, 0, R, C), acts.get(A, A.shape[1], 0, R, kd), C, A.shape[1], C, kd, R, ops.EPI_ATOMIC, dw, ldw,
                  a_layout=ops.MNMAJOR, b_layout=ops.MNMAJOR, split_k=split_k_for(C, kd, R))
         k = w.shape[-1]
-        return None, dw.view(C, k, k, w.shape[1]).permute(0, 3, 1, 2).contiguous(), db
+        return None, dw[:, :kd].reshape(C, k, k, w.shape[1]).permute(0, 3, 1, 2).contiguous(), db
 
 
 class PatchEmbed(nn.Module):
