@@ -35,7 +35,7 @@ extern "C" {
 #define VSX_BF16 0
 #define VSX_F32 1
 
-#define VSX_ABI_VERSION 2
+#define VSX_ABI_VERSION 3
 
 const char* vsx_last_error(void);
 int vsx_abi_version(void);
@@ -107,6 +107,7 @@ typedef struct vsx_gemm_desc {
   int rows_per_sample;    /* RESIDUAL: rows of one sample (tokens)                                           */
   int n_keep;             /* RESIDUAL: columns < n_keep receive the branch                                    */
   int split_k;            /* ATOMIC: number of reduction splits (>= 1)                                        */
+  float* colsum;          /* GELUGRAD (or STORE without bias): colsum[n] += sum_m out[m,n] (bias gradient), or NULL  */
 } vsx_gemm_desc;
 
 int vsx_gemm(const vsx_gemm_desc* d, void* stream);
@@ -124,7 +125,8 @@ int vsx_gemm(const vsx_gemm_desc* d, void* stream);
 int vsx_attn_fwd(const void* qkv, void* o, float* lse, int dtype, int batch, int tokens, int heads, int head_dim,
                  int heads_keep, float scale, int impl, void* stream);
 int vsx_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int dtype, int batch,
-                 int tokens, int heads, int head_dim, int heads_keep, float scale, int impl, void* stream);
+                 int tokens, int heads, int head_dim, int heads_keep, float scale, int impl,
+                 float* dbias /* NULL, or [3*heads*head_dim]: += column sums of dqkv (the qkv bias gradient) */, void* stream);
 
 /* ----------------------------------------------------------------------------------------------------
  * Elementwise helpers around the GEMMs.
@@ -138,7 +140,8 @@ int vsx_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* l
  * -------------------------------------------------------------------------------------------------- */
 int vsx_split_bf16(const float* src, long lds, void* hi, void* lo, void* lo2, long ldd, int rows, int cols, void* stream);
 int vsx_scale_mask_cast(const float* g, long ldg, const float* row_scale, int rows_per_sample, int n_keep, void* out,
-                        int dtype, long ldo, int rows, int cols, void* stream);
+                        int dtype, long ldo, int rows, int cols, float* colsum /* NULL, or [>= n_keep]: += column sums of out */,
+                        void* stream);
 int vsx_colsum(const void* x, int dtype, long ldx, int rows, int cols, float* out, void* stream);
 
 /* ----------------------------------------------------------------------------------------------------

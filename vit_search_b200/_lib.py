@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libvsx.so')
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 BF16, F32 = 0, 1
 KMAJOR, MNMAJOR = 0, 1
@@ -21,7 +21,7 @@ class GemmDesc(C.Structure):
     _fields_ = [('a', _p * 6), ('b', _p * 6), ('terms', _i), ('lda', _l), ('ldb', _l), ('a_layout', _i), ('b_layout', _i),
                 ('M', _i), ('N', _i), ('K', _i), ('epilogue', _i), ('out_dtype', _i), ('out', _p), ('ldo', _l),
                 ('out2', _p), ('ldo2', _l), ('n_out', _i), ('bias', _p), ('aux', _p), ('ld_aux', _l),
-                ('row_scale', _p), ('rows_per_sample', _i), ('n_keep', _i), ('split_k', _i)]
+                ('row_scale', _p), ('rows_per_sample', _i), ('n_keep', _i), ('split_k', _i), ('colsum', _p)]
 
 
 # name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/vsx.h one to one
@@ -33,9 +33,9 @@ SIGNATURES = {
     'vsx_masked_ln_bwd': [_p, _p, _i, _l, _p, _l, _p, _p, _p, _p, _p, _l, _p, _p, _i, _i, _i, _i, _i, _p],
     'vsx_gemm': [C.POINTER(GemmDesc), _p],
     'vsx_attn_fwd': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p],
-    'vsx_attn_bwd': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p],
+    'vsx_attn_bwd': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p],
     'vsx_split_bf16': [_p, _l, _p, _p, _p, _l, _i, _i, _p],
-    'vsx_scale_mask_cast': [_p, _l, _p, _i, _i, _p, _i, _l, _i, _i, _p],
+    'vsx_scale_mask_cast': [_p, _l, _p, _i, _i, _p, _i, _l, _i, _i, _p, _p],
     'vsx_colsum': [_p, _i, _l, _i, _i, _p, _p],
     'vsx_im2col': [_p, _p, _p, _p, _p, _p, _i, _i, _l, _l, _i, _i, _i, _i, _i, _i, _i, _p, _i, _l, _p],
     'vsx_col2im': [_p, _l, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _l, _l, _p],

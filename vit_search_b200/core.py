@@ -271,8 +271,7 @@ def attn_half_backward(meta, g_out, saved, x, ln_w, ln_b, qkv_w, qkv_b, proj_w, 
         hkd = hk * D
         ck = s.ck if meta.residual else C
         ops.scale_mask_cast(g2, C, meta.row_scale if meta.residual else None, N, ck, df, C, rows, C, g_off=r0 * C, out_off=r0 * C,
-                            scale_off=meta.scale_off + s.b0)
-        ops.colsum(df, C, rows, ck, d_pb, x_off=r0 * C)
+                            scale_off=meta.scale_off + s.b0, colsum=d_pb)
         a_df = acts.get(df, C, r0, rows, ck)
         a_o = acts.get(o, HD, r0, rows, hkd)
         # dWproj[ck, hkd] += df^T o
@@ -280,8 +279,7 @@ def attn_half_backward(meta, g_out, saved, x, ln_w, ln_b, qkv_w, qkv_b, proj_w, 
                  b_layout=ops.MNMAJOR, split_k=split_k_for(ck, hkd, rows))
         # d_o[rows, hkd] = df[rows, ck] Wproj[ck, hkd]
         ops.gemm(a_df, wp, C, HD, rows, hkd, ck, ops.EPI_STORE, d_o, HD, a_off=r0 * C, out_off=r0 * HD, b_layout=ops.MNMAJOR)
-        ops.attn_bwd(qkv, o, d_o, lse, dqkv, nb, N, H, D, hk, scale, qkv_off=r0 * 3 * HD, o_off=r0 * HD, lse_off=s.b0 * H * N)
-        ops.colsum(dqkv, 3 * HD, rows, 3 * HD, d_qb, x_off=r0 * 3 * HD)
+        ops.attn_bwd(qkv, o, d_o, lse, dqkv, nb, N, H, D, hk, scale, qkv_off=r0 * 3 * HD, o_off=r0 * HD, lse_off=s.b0 * H * N, dbias=d_qb)
         a_dq = acts.get(dqkv, 3 * HD, r0, rows, 3 * HD)
         a_xn = acts.get(xn, C, r0, rows, s.ek)
         for j in (range(3) if hk < H else range(1)):
@@ -365,8 +363,7 @@ def mlp_half_backward(meta, g_out, saved, x, ln_w, ln_b, fc1_w, fc1_b, fc2_w, fc
             continue
         ck = s.ck if meta.residual else C
         ops.scale_mask_cast(g2, C, meta.row_scale if meta.residual else None, N, ck, df, C, rows, C, g_off=r0 * C, out_off=r0 * C,
-                            scale_off=meta.scale_off + s.b0)
-        ops.colsum(df, C, rows, ck, d_b2, x_off=r0 * C)
+                            scale_off=meta.scale_off + s.b0, colsum=d_b2)
         a_df = acts.get(df, C, r0, rows, ck)
         a_h = acts.get(h, F, r0, rows, s.ik)
         # dW2[ck, ik] += df^T h
@@ -374,8 +371,7 @@ def mlp_half_backward(meta, g_out, saved, x, ln_w, ln_b, fc1_w, fc1_b, fc2_w, fc
                  b_layout=ops.MNMAJOR, split_k=split_k_for(ck, s.ik, rows))
         # du[rows, ik] = (df[rows, ck] W2[ck, ik]) * gelu'(u)
         ops.gemm(a_df, w2, C, F, rows, s.ik, ck, ops.EPI_GELUGRAD, du, F, a_off=r0 * C, out_off=r0 * F, n_out=up8(s.ik), aux=u,
-                 ld_aux=F, aux_off=r0 * F, b_layout=ops.MNMAJOR)
-        ops.colsum(du, F, rows, s.ik, d_b1, x_off=r0 * F)
+                 ld_aux=F, aux_off=r0 * F, b_layout=ops.MNMAJOR, colsum=d_b1)
         a_du = acts.get(du, F, r0, rows, s.ik)
         a_xn = acts.get(xn, C, r0, rows, s.ek)
         # dW1[ik, ek] += du^T xn

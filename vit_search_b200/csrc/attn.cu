@@ -9,7 +9,7 @@ int attn_bwd_ref(const void* qkv, const void* o, const void* d_o, const float* l
                  float scale, cudaStream_t st);
 int attn_fwd_mma(const void* qkv, void* o, float* lse, int B, int N, int H, int D, int Hk, float scale, cudaStream_t st);
 int attn_bwd_mma(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int N, int H, int D, int Hk,
-                 float scale, cudaStream_t st);
+                 float scale, float* dbias, cudaStream_t st);
 bool attn_mma_supported(int N, int D);
 }  // namespace vsx
 
@@ -37,17 +37,26 @@ extern "C" int vsx_attn_fwd(const void* qkv, void* o, float* lse, int dtype, int
   return VSX_ERR_ARG;
 }
 
+extern "C" int vsx_colsum(const void* x, int dtype, long ldx, int rows, int cols, float* out, void* stream);
+
 extern "C" int vsx_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int dtype, int batch,
-                            int tokens, int heads, int head_dim, int heads_keep, float scale, int impl, void* stream) {
+                            int tokens, int heads, int head_dim, int heads_keep, float scale, int impl, float* dbias, void* stream) {
   int rc = check_shape("vsx_attn_bwd", batch, tokens, heads, head_dim, heads_keep);
   if (rc) return rc;
   if (batch == 0) return VSX_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (dtype == VSX_F32) return attn_bwd_ref<float>(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, heads_keep, scale, st);
+  const long ld = 3L * heads * head_dim;
+  if (dtype == VSX_F32) {
+    rc = attn_bwd_ref<float>(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, heads_keep, scale, st);
+    if (rc == VSX_OK && dbias != nullptr) rc = vsx_colsum(dqkv, dtype, ld, batch * tokens, (int)ld, dbias, stream);   // fused only in the tensor-core kernel
+    return rc;
+  }
   if (dtype == VSX_BF16) {
     if (impl != VSX_ATTN_IMPL_FP32 && attn_mma_supported(tokens, head_dim))
-      return attn_bwd_mma(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, heads_keep, scale, st);
-    return attn_bwd_ref<bf16>(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, heads_keep, scale, st);
+      return attn_bwd_mma(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, heads_keep, scale, dbias, st);
+    rc = attn_bwd_ref<bf16>(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, heads_keep, scale, st);
+    if (rc == VSX_OK && dbias != nullptr) rc = vsx_colsum(dqkv, dtype, ld, batch * tokens, (int)ld, dbias, stream);
+    return rc;
   }
   set_error("vsx_attn_bwd: bad dtype %d", dtype);
   return VSX_ERR_ARG;

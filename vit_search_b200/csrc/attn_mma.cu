@@ -1,6 +1,7 @@
 // Tensor-core attention for the ViT-Res shapes (N = 257 / 65 / 17 tokens, head_dim 32 / 48 / 64), bf16 in / fp32 softmax.
 //
-// One CTA per (sample, head); Q, K, V (and dO in the backward) of the head are staged once in shared memory (<= 148 KB),
+// One CTA per (sample, head); the two "column" operands of the head (K,V -- or Q,dO in the key-owner phase of the backward)
+// are staged in shared memory (<= 81 KB, two CTAs per SM), the row-owner operands come straight from global memory,
 // every warp owns 16-row blocks and streams over the other dimension in 32/64-column chunks with mma.sync m16n8k16
 // (ldmatrix operand loads, online softmax in the forward, recomputation from the saved log-sum-exp in the backward).
 // Nothing of size N x N is written to HBM -- the reference materialises [B,H,N,N] scores three times
@@ -68,6 +69,23 @@ __device__ __forceinline__ void stage_tile(uint8_t* smem, const Tile<D>& t, cons
   }
 }
 
+// A-operand fragments (16 rows x D) of the rows [row0, row0+16) straight from global memory (rows >= N read as zero):
+// the row-owner operands are touched once per row block, so they do not need a shared-memory copy.
+template <int D>
+__device__ __forceinline__ void load_a_global(uint32_t (&f)[D / 16][4], const bf16* __restrict__ src, long ld, int row0, int N, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const bool v0 = row0 + g < N, v1 = row0 + g + 8 < N;
+  const bf16* p0 = src + (long)(row0 + g) * ld + 2 * t;
+  const bf16* p1 = p0 + 8 * ld;
+#pragma unroll
+  for (int ks = 0; ks < D / 16; ++ks) {
+    f[ks][0] = v0 ? *reinterpret_cast<const uint32_t*>(p0 + ks * 16) : 0u;
+    f[ks][1] = v1 ? *reinterpret_cast<const uint32_t*>(p1 + ks * 16) : 0u;
+    f[ks][2] = v0 ? *reinterpret_cast<const uint32_t*>(p0 + ks * 16 + 8) : 0u;
+    f[ks][3] = v1 ? *reinterpret_cast<const uint32_t*>(p1 + ks * 16 + 8) : 0u;
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ void zero_slice(T* dst, long ld, int N, int D) {
   for (int idx = threadIdx.x; idx < N * (D / 8); idx += blockDim.x) {
@@ -91,9 +109,8 @@ __global__ void __launch_bounds__(288) attn_fwd_mma_kernel(const bf16* __restric
   const int Np = (N + 15) / 16 * 16;
   const uint32_t sbase = smem_u32(smem);
   constexpr int TB = (D + 8) * 2;   // bytes per tile row
-  Tile<D> Qs{sbase}, Ks{sbase + (uint32_t)Np * TB}, Vs{sbase + 2u * Np * TB};
+  Tile<D> Ks{sbase}, Vs{sbase + (uint32_t)Np * TB};
   const bf16* base = qkv + (long)b * N * ldq + h * D;
-  stage_tile<D>(smem, Qs, base, ldq, N, Np, sbase);
   stage_tile<D>(smem, Ks, base + (long)H * D, ldq, N, Np, sbase);
   stage_tile<D>(smem, Vs, base + 2L * H * D, ldq, N, Np, sbase);
   __syncthreads();
@@ -104,8 +121,7 @@ __global__ void __launch_bounds__(288) attn_fwd_mma_kernel(const bf16* __restric
   for (int rb = warp; rb * 16 < N; rb += nwarps) {
     const int row0 = rb * 16;
     uint32_t qf[D / 16][4];
-#pragma unroll
-    for (int ks = 0; ks < D / 16; ++ks) Qs.load_a(qf[ks], row0, ks * 16, lane);
+    load_a_global<D>(qf, base, ldq, row0, N, lane);
     float oacc[D / 8][4];
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
@@ -192,21 +208,16 @@ __global__ void __launch_bounds__(288) attn_fwd_mma_kernel(const bf16* __restric
 
 // ------------------------------------------------------------------------------------------------ backward
 // One 16-row block of the "owner" operand against all columns of the other, producing two accumulators:
+//   (xf, yf are the owner rows' A-operand fragments, loaded from global memory by the caller)
 //   TRANSPOSED = true  (phase A): owner rows = keys.    X = K, Y = V (A operands);  cols = queries: Bs = Q (for S^T), Bd = dO (for dP^T)
 //        acc1 = dV += P^T dO, acc2 = dK += dS^T Q;     per-COLUMN statistics lse2[q], delta[q]
 //   TRANSPOSED = false (phase B): owner rows = queries. X = Q, Y = dO;  cols = keys: Bs = K, Bd = V
 //        acc2 = dQ += dS K (acc1 unused);               per-ROW statistics
 template <int D, bool TRANSPOSED>
-__device__ __forceinline__ void bwd_block(const Tile<D>& X, const Tile<D>& Y, const Tile<D>& Bs, const Tile<D>& Bd,
+__device__ __forceinline__ void bwd_block(const uint32_t (&xf)[D / 16][4], const uint32_t (&yf)[D / 16][4], const Tile<D>& Bs, const Tile<D>& Bd,
                                           const float* __restrict__ lse2_s, const float* __restrict__ delta_s, int row0, int ntiles,
                                           float c, int lane, float (&acc1)[D / 8][4], float (&acc2)[D / 8][4]) {
   const int g = lane >> 2, t = lane & 3;
-  uint32_t xf[D / 16][4], yf[D / 16][4];
-#pragma unroll
-  for (int ks = 0; ks < D / 16; ++ks) {
-    X.load_a(xf[ks], row0, ks * 16, lane);
-    Y.load_a(yf[ks], row0, ks * 16, lane);
-  }
   float rl0 = 0.f, rl1 = 0.f, rd0 = 0.f, rd1 = 0.f;
   if (!TRANSPOSED) {
     rl0 = lse2_s[row0 + g], rl1 = lse2_s[row0 + g + 8];
@@ -285,10 +296,32 @@ __device__ __forceinline__ void store_block(bf16* dst, long ld, int row0, int N,
   }
 }
 
+// Column sums of a row block's gradient (rows < N only) into per-CTA shared accumulators: the qkv bias gradient.
+template <int D>
+__device__ __forceinline__ void colsum_block(float* cs, int row0, int N, int lane, const float (&acc)[D / 8][4], float mul) {
+  const int g = lane >> 2, t = lane & 3;
+  const bool v0 = row0 + g < N, v1 = row0 + g + 8 < N;
+#pragma unroll
+  for (int i = 0; i < D / 8; ++i) {
+    float a = (v0 ? acc[i][0] : 0.f) + (v1 ? acc[i][2] : 0.f), b = (v0 ? acc[i][1] : 0.f) + (v1 ? acc[i][3] : 0.f);
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      a += __shfl_xor_sync(0xffffffffu, a, o);
+      b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    if (g == 0) {
+      atomicAdd(cs + i * 8 + 2 * t, a * mul);
+      atomicAdd(cs + i * 8 + 2 * t + 1, b * mul);
+    }
+  }
+}
+
 template <int D>
 __global__ void __launch_bounds__(288) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ d_o,
-                                    const float* __restrict__ lse, bf16* __restrict__ dqkv, int N, int H, int Hk, float scale) {
+                                    const float* __restrict__ lse, bf16* __restrict__ dqkv, int N, int H, int Hk, float scale,
+                                    float* __restrict__ dbias) {
   extern __shared__ __align__(16) uint8_t smem[];
+  __shared__ float cs[3 * D];
   const int h = blockIdx.x, b = blockIdx.y;
   const long ldq = 3L * H * D, ldo = (long)H * D;
   bf16* dbase = dqkv + (long)b * N * ldq + h * D;
@@ -301,16 +334,15 @@ __global__ void __launch_bounds__(288) attn_bwd_mma_kernel(const bf16* __restric
   const int Np = (N + 15) / 16 * 16;
   const uint32_t sbase = smem_u32(smem);
   constexpr int TB = (D + 8) * 2;
-  Tile<D> Qs{sbase}, Ks{sbase + (uint32_t)Np * TB}, Vs{sbase + 2u * Np * TB}, Os{sbase + 3u * Np * TB};
-  float* lse2_s = reinterpret_cast<float*>(smem + 4 * (size_t)Np * TB);
+  Tile<D> T0{sbase}, T1{sbase + (uint32_t)Np * TB};     // phase A: Q, dO     phase B: K, V   (two CTAs fit per SM)
+  float* lse2_s = reinterpret_cast<float*>(smem + 2 * (size_t)Np * TB);
   float* delta_s = lse2_s + Np + STAT_PAD;
   const bf16* base = qkv + (long)b * N * ldq + h * D;
   const bf16* ob = o + (long)b * N * ldo + h * D;
   const bf16* dob = d_o + (long)b * N * ldo + h * D;
-  stage_tile<D>(smem, Qs, base, ldq, N, Np, sbase);
-  stage_tile<D>(smem, Ks, base + (long)H * D, ldq, N, Np, sbase);
-  stage_tile<D>(smem, Vs, base + 2L * H * D, ldq, N, Np, sbase);
-  stage_tile<D>(smem, Os, dob, ldo, N, Np, sbase);
+  stage_tile<D>(smem, T0, base, ldq, N, Np, sbase);
+  stage_tile<D>(smem, T1, dob, ldo, N, Np, sbase);
+  for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) cs[i] = 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   // delta_i = dO_i . O_i, lse in log2 units; padded rows get finite zeros
   for (int i = warp; i < Np + STAT_PAD; i += nwarps) {   // the padding keeps the 32-column chunk loads in bounds
@@ -326,54 +358,75 @@ __global__ void __launch_bounds__(288) attn_bwd_mma_kernel(const bf16* __restric
   __syncthreads();
   const float c = scale * LOG2E;
   const int ntiles = Np / 8;
-  // ---- phase A: dK, dV (owner rows = keys)
+  uint32_t xf[D / 16][4], yf[D / 16][4];
+  // ---- phase A: dK, dV (owner rows = keys; K, V fragments from global, Q and dO in shared memory)
   for (int rb = warp; rb * 16 < N; rb += nwarps) {
     float dv[D / 8][4], dk[D / 8][4];
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
-    bwd_block<D, true>(Ks, Vs, Qs, Os, lse2_s, delta_s, rb * 16, ntiles, c, lane, dv, dk);
+    load_a_global<D>(xf, base + (long)H * D, ldq, rb * 16, N, lane);
+    load_a_global<D>(yf, base + 2L * H * D, ldq, rb * 16, N, lane);
+    bwd_block<D, true>(xf, yf, T0, T1, lse2_s, delta_s, rb * 16, ntiles, c, lane, dv, dk);
     store_block<D>(dbase + (long)H * D, ldq, rb * 16, N, lane, dk, scale);
     store_block<D>(dbase + 2L * H * D, ldq, rb * 16, N, lane, dv, 1.0f);
+    if (dbias != nullptr) {
+      colsum_block<D>(cs + D, rb * 16, N, lane, dk, scale);
+      colsum_block<D>(cs + 2 * D, rb * 16, N, lane, dv, 1.0f);
+    }
   }
-  // ---- phase B: dQ (owner rows = queries)
+  __syncthreads();
+  stage_tile<D>(smem, T0, base + (long)H * D, ldq, N, Np, sbase);
+  stage_tile<D>(smem, T1, base + 2L * H * D, ldq, N, Np, sbase);
+  __syncthreads();
+  // ---- phase B: dQ (owner rows = queries; Q, dO fragments from global, K and V in shared memory)
   for (int rb = warp; rb * 16 < N; rb += nwarps) {
     float unused[D / 8][4], dq[D / 8][4];
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
-    bwd_block<D, false>(Qs, Os, Ks, Vs, lse2_s, delta_s, rb * 16, ntiles, c, lane, unused, dq);
+    load_a_global<D>(xf, base, ldq, rb * 16, N, lane);
+    load_a_global<D>(yf, dob, ldo, rb * 16, N, lane);
+    bwd_block<D, false>(xf, yf, T0, T1, lse2_s, delta_s, rb * 16, ntiles, c, lane, unused, dq);
     store_block<D>(dbase, ldq, rb * 16, N, lane, dq, scale);
+    if (dbias != nullptr) colsum_block<D>(cs, rb * 16, N, lane, dq, scale);
+  }
+  if (dbias != nullptr) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) atomicAdd(dbias + (long)(i / D) * H * D + h * D + (i % D), cs[i]);
   }
 }
 
-int warps_for(int N) {
+// Warps per CTA.  257 tokens = 17 row blocks; the register file (168 regs/thread in the backward, 139 in the forward at
+// head_dim 64) allows two co-resident CTAs of 6 (backward) / 7 (forward) warps -- 3 rounds of row blocks each.
+int warps_for(int N, bool bwd) {
   const int rb = (N + 15) / 16;
-  return rb >= 17 ? 9 : (rb > 8 ? 8 : rb);   // 257 tokens = 17 row blocks -> 9 warps x 2 rounds
+  if (rb >= 12) return bwd ? 6 : 7;
+  return rb > 8 ? 8 : rb;
 }
 
 template <int D>
 int launch_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int Hk, float scale, cudaStream_t st) {
   const int Np = (N + 15) / 16 * 16;
-  const size_t smem = 3 * (size_t)Np * (D + 8) * 2;
+  const size_t smem = 2 * (size_t)Np * (D + 8) * 2;
   cudaError_t e = cudaFuncSetAttribute(attn_fwd_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("vsx_attn_fwd: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
     return VSX_ERR_CUDA;
   }
-  attn_fwd_mma_kernel<D><<<dim3(H, B), warps_for(N) * 32, smem, st>>>((const bf16*)qkv, (bf16*)o, lse, N, H, Hk, scale);
+  attn_fwd_mma_kernel<D><<<dim3(H, B), warps_for(N, false) * 32, smem, st>>>((const bf16*)qkv, (bf16*)o, lse, N, H, Hk, scale);
   return check_launch("vsx_attn_fwd");
 }
 template <int D>
 int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int N, int H, int Hk, float scale,
-               cudaStream_t st) {
+               float* dbias, cudaStream_t st) {
   const int Np = (N + 15) / 16 * 16;
-  const size_t smem = 4 * (size_t)Np * (D + 8) * 2 + 2 * (size_t)(Np + STAT_PAD) * sizeof(float);
+  const size_t smem = 2 * (size_t)Np * (D + 8) * 2 + 2 * (size_t)(Np + STAT_PAD) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(attn_bwd_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("vsx_attn_bwd: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
     return VSX_ERR_CUDA;
   }
-  attn_bwd_mma_kernel<D><<<dim3(H, B), warps_for(N) * 32, smem, st>>>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse, (bf16*)dqkv, N,
-                                                                    H, Hk, scale);
+  attn_bwd_mma_kernel<D><<<dim3(H, B), warps_for(N, true) * 32, smem, st>>>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse, (bf16*)dqkv, N,
+                                                                    H, Hk, scale, dbias);
   return check_launch("vsx_attn_bwd");
 }
 
@@ -382,7 +435,7 @@ int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse
 bool attn_mma_supported(int N, int D) {
   if (!(D == 32 || D == 48 || D == 64)) return false;
   const int Np = (N + 15) / 16 * 16;
-  return 4 * (size_t)Np * (D + 8) * 2 + 2 * (size_t)(Np + STAT_PAD) * sizeof(float) <= 227 * 1024;
+  return 2 * (size_t)Np * (D + 8) * 2 + 2 * (size_t)(Np + STAT_PAD) * sizeof(float) <= 227 * 1024;
 }
 
 int attn_fwd_mma(const void* qkv, void* o, float* lse, int B, int N, int H, int D, int Hk, float scale, cudaStream_t st) {
@@ -396,11 +449,11 @@ int attn_fwd_mma(const void* qkv, void* o, float* lse, int B, int N, int H, int 
 }
 
 int attn_bwd_mma(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int N, int H, int D, int Hk,
-                 float scale, cudaStream_t st) {
+                 float scale, float* dbias, cudaStream_t st) {
   switch (D) {
-    case 32: return launch_bwd<32>(qkv, o, d_o, lse, dqkv, B, N, H, Hk, scale, st);
-    case 48: return launch_bwd<48>(qkv, o, d_o, lse, dqkv, B, N, H, Hk, scale, st);
-    case 64: return launch_bwd<64>(qkv, o, d_o, lse, dqkv, B, N, H, Hk, scale, st);
+    case 32: return launch_bwd<32>(qkv, o, d_o, lse, dqkv, B, N, H, Hk, scale, dbias, st);
+    case 48: return launch_bwd<48>(qkv, o, d_o, lse, dqkv, B, N, H, Hk, scale, dbias, st);
+    case 64: return launch_bwd<64>(qkv, o, d_o, lse, dqkv, B, N, H, Hk, scale, dbias, st);
   }
   set_error("attn_bwd_mma: unsupported head_dim %d", D);
   return VSX_ERR_ARG;

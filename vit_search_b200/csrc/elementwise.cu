@@ -28,24 +28,57 @@ __global__ void split_kernel(const float* __restrict__ src, long lds, bf16* __re
 }
 
 // out[m, n] = n < n_keep ? g[m, n] * row_scale[m / rows_per_sample] : 0     (Block backward, nets/supernet_blocks.py:243,251
-// together with nets/drop.py:25: the branch output was scaled by drop-path and masked before the residual add)
-template <typename T>
-__global__ void scale_mask_cast_kernel(const float* __restrict__ g, long ldg, const float* __restrict__ row_scale, int rps, int n_keep,
-                                       T* __restrict__ out, long ldo, int rows, int cols4) {
-  const long total = (long)rows * cols4;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const long r = i / cols4;
-    const int c = (int)(i - r * cols4) * 4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c < n_keep) {
-      const float s = row_scale != nullptr ? __ldg(row_scale + r / rps) : 1.0f;
-      v = ld4(g + r * ldg + c);
-      v.x *= s;
-      v.y = (c + 1 < n_keep) ? v.y * s : 0.f;
-      v.z = (c + 2 < n_keep) ? v.z * s : 0.f;
-      v.w = (c + 3 < n_keep) ? v.w * s : 0.f;
+// together with nets/drop.py:25: the branch output was scaled by drop-path and masked before the residual add).
+// Optionally colsum[n] += sum_m out[m, n] -- the bias gradient of the Linear that produced the branch output -- from the same pass.
+// One warp per row, lane owns columns (i*32 + lane)*4..+3, i < NV (like the LayerNorm kernels).
+constexpr int SMC_WARPS = 8;
+template <int NV, typename T>
+__global__ void __launch_bounds__(SMC_WARPS * 32) scale_mask_cast_kernel(const float* __restrict__ g, long ldg, const float* __restrict__ row_scale,
+                                                                        int rps, int n_keep, T* __restrict__ out, long ldo, int rows, int cols,
+                                                                        float* __restrict__ colsum) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long r = (long)blockIdx.x * SMC_WARPS + warp; r < rows; r += (long)gridDim.x * SMC_WARPS) {
+    const float s = row_scale != nullptr ? __ldg(row_scale + r / rps) : 1.0f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < cols) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < n_keep) {
+          v = ld4(g + r * ldg + c);
+          v.x *= s;
+          v.y = (c + 1 < n_keep) ? v.y * s : 0.f;
+          v.z = (c + 2 < n_keep) ? v.z * s : 0.f;
+          v.w = (c + 3 < n_keep) ? v.w * s : 0.f;
+        }
+        st4(out + r * ldo + c, v);
+        acc[i].x += v.x, acc[i].y += v.y, acc[i].z += v.z, acc[i].w += v.w;
+      }
     }
-    st4(out + r * ldo + c, v);
+  }
+  if (colsum == nullptr) return;
+  __shared__ float4 red[SMC_WARPS][32];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    red[warp][lane] = acc[i];
+    __syncthreads();
+    if (warp == 0) {
+      float4 t = red[0][lane];
+#pragma unroll
+      for (int w = 1; w < SMC_WARPS; ++w) {
+        const float4 u = red[w][lane];
+        t.x += u.x, t.y += u.y, t.z += u.z, t.w += u.w;
+      }
+      const int c = (i * 32 + lane) * 4;
+      if (c < n_keep) atomicAdd(colsum + c, t.x);
+      if (c + 1 < n_keep) atomicAdd(colsum + c + 1, t.y);
+      if (c + 2 < n_keep) atomicAdd(colsum + c + 2, t.z);
+      if (c + 3 < n_keep) atomicAdd(colsum + c + 3, t.w);
+    }
+    __syncthreads();
   }
 }
 
@@ -98,22 +131,36 @@ extern "C" int vsx_split_bf16(const float* src, long lds, void* hi, void* lo, vo
   return check_launch("vsx_split_bf16");
 }
 
+template <typename T>
+static int smc_dispatch(const float* g, long ldg, const float* row_scale, int rps, int n_keep, void* out, long ldo, int rows, int cols,
+                        float* colsum, cudaStream_t st) {
+  const int nv = ceil_div(cols, 128);
+  const int need = ceil_div(rows, SMC_WARPS), cap = num_sms() * 8;
+  const int grid = need < cap ? need : cap;
+#define VSX_SMC(NV)                                                                                                                 \
+  case NV:                                                                                                                          \
+    scale_mask_cast_kernel<NV, T><<<grid, SMC_WARPS * 32, 0, st>>>(g, ldg, row_scale, rps, n_keep, (T*)out, ldo, rows, cols, colsum); \
+    break;
+  switch (nv) {
+    VSX_SMC(1) VSX_SMC(2) VSX_SMC(3) VSX_SMC(4) VSX_SMC(5) VSX_SMC(6) VSX_SMC(7) VSX_SMC(8) VSX_SMC(9) VSX_SMC(10)
+    default:
+      set_error("vsx_scale_mask_cast: cols=%d exceeds the supported 1280", cols);
+      return VSX_ERR_ARG;
+  }
+#undef VSX_SMC
+  return check_launch("vsx_scale_mask_cast");
+}
+
 extern "C" int vsx_scale_mask_cast(const float* g, long ldg, const float* row_scale, int rows_per_sample, int n_keep, void* out,
-                                   int dtype, long ldo, int rows, int cols, void* stream) {
+                                   int dtype, long ldo, int rows, int cols, float* colsum, void* stream) {
   VSX_REQUIRE(cols % 4 == 0 && ldg % 4 == 0 && ldo % 4 == 0, "vsx_scale_mask_cast: cols and pitches must be multiples of 4");
   if (rows <= 0 || cols <= 0) return VSX_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int rps = rows_per_sample > 0 ? rows_per_sample : 1;
-  const int grid = ew_grid((long)rows * cols / 4);
-  if (dtype == VSX_BF16)
-    scale_mask_cast_kernel<bf16><<<grid, 256, 0, st>>>(g, ldg, row_scale, rps, n_keep, (bf16*)out, ldo, rows, cols / 4);
-  else if (dtype == VSX_F32)
-    scale_mask_cast_kernel<float><<<grid, 256, 0, st>>>(g, ldg, row_scale, rps, n_keep, (float*)out, ldo, rows, cols / 4);
-  else {
-    set_error("vsx_scale_mask_cast: bad dtype %d", dtype);
-    return VSX_ERR_ARG;
-  }
-  return check_launch("vsx_scale_mask_cast");
+  if (dtype == VSX_BF16) return smc_dispatch<bf16>(g, ldg, row_scale, rps, n_keep, out, ldo, rows, cols, colsum, st);
+  if (dtype == VSX_F32) return smc_dispatch<float>(g, ldg, row_scale, rps, n_keep, out, ldo, rows, cols, colsum, st);
+  set_error("vsx_scale_mask_cast: bad dtype %d", dtype);
+  return VSX_ERR_ARG;
 }
 
 extern "C" int vsx_colsum(const void* x, int dtype, long ldx, int rows, int cols, float* out, void* stream) {

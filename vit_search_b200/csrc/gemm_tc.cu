@@ -25,11 +25,12 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 3;
+constexpr int STAGES = 2;              // x 3 co-resident CTAs per SM = 6 operand stages in flight per SM
 constexpr int STAGE_A = BM * BK * 2;
 constexpr int STAGE_B = BN * BK * 2;
 constexpr int TMEM_COLS = 128;
-constexpr int GEMM_THREADS = 192;
+constexpr int EPI_WARPS = 8;            // two warps per TMEM lane quarter, each owning half of the tile's columns
+constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
 constexpr int SMEM_BYTES = STAGES * (STAGE_A + STAGE_B) + 1024 /*align*/ + 128 /*barriers, tmem slot*/ + 512 /*bias tile*/;
 
 constexpr int MAX_TERMS = 6;
@@ -43,6 +44,7 @@ struct GemmArgs {
   int M, N, K, num_kb, terms, a_mn, b_mn, n_out, split_k;
   const float* bias;
   const float* row_scale;
+  float* colsum;
   int rows_per_sample, n_keep;
 };
 
@@ -119,7 +121,7 @@ __device__ __forceinline__ void stage_read32<bf16>(const uint8_t* tile, int row,
 }
 
 template <int EPI, typename OutT>
-__global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_constant__ TmapPack maps, const GemmArgs g) {
+__global__ void __launch_bounds__(GEMM_THREADS, 3) gemm_tc_kernel(const __grid_constant__ TmapPack maps, const GemmArgs g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;   // 128B-swizzle atoms need 1024-byte alignment
@@ -220,10 +222,11 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
     constexpr int BOXC = 128 / (int)sizeof(OutT);     // columns per 128-byte box row
     const int q = warp & 3;                           // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;                    // tile row == TMEM lane
-    const int et = (int)threadIdx.x - 64;             // 0..127 among the epilogue threads
+    const int et = (int)threadIdx.x - 64;             // 0..255 among the epilogue threads
+    const int chalf = (warp - 2) >> 2;                // which 64-column half of the tile this warp handles
     const int m = m0 + row;
     const int ncols = min(BN, g.n_out - n0);          // columns of this tile that exist in the output
-    bias_s[et] = (g.bias != nullptr && n0 + et < g.N) ? __ldg(g.bias + n0 + et) : 0.f;
+    if (et < BN) bias_s[et] = (g.bias != nullptr && n0 + et < g.N) ? __ldg(g.bias + n0 + et) : 0.f;
     if (has_mma) {
       mbar_wait(acc_bar, 0);                          // all MMAs done => the operand ring is free: reuse it as the staging tile
       tc_fence_after();
@@ -240,13 +243,13 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
         for (int bx = 0; bx < nbox; ++bx) tma_load_2d(base + bx * BOX_BYTES, &maps.aux, aux_bar, n0 + bx * BOXC, m0);
       }
     }
-    named_bar_sync(1, 128);                           // bias tile visible
+    named_bar_sync(1, EPI_WARPS * 32);                           // bias tile visible
     if (EPI == VSX_EPI_RESIDUAL || EPI == VSX_EPI_GELUGRAD) mbar_wait(aux_bar, 0);
     float scale = 1.0f;
     if (EPI == VSX_EPI_RESIDUAL && g.row_scale != nullptr && m < g.M) scale = __ldg(g.row_scale + m / g.rows_per_sample);
     const int lim = g.n_keep < g.N ? g.n_keep : g.N;
     for (int pass = 0; pass < (TWO_PASS ? 2 : 1); ++pass) {
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
         if (c >= ncols) break;
         float v[32];
         if (has_mma) {
@@ -287,7 +290,16 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
         }
       }
       fence_proxy_async();                            // generic-proxy smem writes -> visible to the TMA (async proxy)
-      named_bar_sync(1, 128);
+      named_bar_sync(1, EPI_WARPS * 32);
+      if ((EPI == VSX_EPI_GELUGRAD || EPI == VSX_EPI_STORE) && g.colsum != nullptr && et >= 128 && n0 + (et - 128) < g.N) {
+        // bias gradient fused into the dgrad epilogue: column sums of the staged (already rounded) tile over its valid rows
+        const int cc = et - 128, rmax = min(BM, g.M - m0);
+        const uint8_t* colp = tile + (cc / BOXC) * BOX_BYTES + (cc % (16 / (int)sizeof(OutT))) * (int)sizeof(OutT);
+        const int chunk = (cc % BOXC) / (16 / (int)sizeof(OutT));
+        float acc = 0.f;
+        for (int r = 0; r < rmax; ++r) acc += Store<OutT>::ld(reinterpret_cast<const OutT*>(colp + box_off(r, chunk)));
+        atomicAdd(g.colsum + n0 + cc, acc);
+      }
       if (et == 0) {
         for (int bx = 0; bx < nbox; ++bx) {
           if (EPI == VSX_EPI_ATOMIC) {
@@ -302,7 +314,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_tc_kernel(const __grid_cons
         }
         tma_store_commit_wait();                      // shared memory must stay valid until the TMA has read it
       }
-      if (TWO_PASS) named_bar_sync(1, 128);           // the staging tile may be overwritten by the second pass
+      if (TWO_PASS) named_bar_sync(1, EPI_WARPS * 32);           // the staging tile may be overwritten by the second pass
     }
   }
   tc_fence_before();
@@ -346,6 +358,7 @@ extern "C" int vsx_gemm(const vsx_gemm_desc* d, void* stream) {
   g.a_mn = d->a_layout == VSX_MNMAJOR, g.b_mn = d->b_layout == VSX_MNMAJOR;
   g.n_out = d->n_out, g.split_k = d->split_k < 1 ? 1 : d->split_k;
   g.bias = d->bias;
+  g.colsum = d->colsum;
   g.row_scale = d->row_scale, g.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1, g.n_keep = d->n_keep;
 
   TmapPack maps;
@@ -388,6 +401,7 @@ extern "C" int vsx_gemm(const vsx_gemm_desc* d, void* stream) {
   }
   switch (d->epilogue) {
     case VSX_EPI_STORE:
+      VSX_REQUIRE(d->colsum == nullptr || d->bias == nullptr, "vsx_gemm: STORE with colsum must not add a bias");
       return f32 ? launch<VSX_EPI_STORE, float>(maps, g, grid, st) : launch<VSX_EPI_STORE, bf16>(maps, g, grid, st);
     case VSX_EPI_GELU:
       return f32 ? launch<VSX_EPI_GELU, float>(maps, g, grid, st) : launch<VSX_EPI_GELU, bf16>(maps, g, grid, st);

@@ -57,7 +57,7 @@ def masked_ln_bwd(dy, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, dgamma,
 # ------------------------------------------------------------------------------------------------ GEMM
 def gemm(a, b, lda, ldb, M, N, K, epilogue, out, ldo, *, a_off=0, b_off=0, out_off=0, a_layout=KMAJOR,
          b_layout=KMAJOR, n_out=None, out2=None, ldo2=0, out2_off=0, bias=None, bias_off=0, aux=None, ld_aux=0,
-         aux_off=0, row_scale=None, row_scale_off=0, rows_per_sample=1, n_keep=0, split_k=1):
+         aux_off=0, row_scale=None, row_scale_off=0, rows_per_sample=1, n_keep=0, split_k=1, colsum=None, colsum_off=0):
     """a, b: a bf16 tensor, or tuples of 2 (3 product terms, ~2^-16) or 3 (6 terms, fp32-exact) bf16 parts whose sum is
     the fp32 operand (split-bf16 high-precision mode)."""
     d = _lib.GemmDesc()
@@ -82,6 +82,7 @@ def gemm(a, b, lda, ldb, M, N, K, epilogue, out, ldo, *, a_off=0, b_off=0, out_o
     d.aux, d.ld_aux = _ptr(aux, aux_off), ld_aux
     d.row_scale = _ptr(row_scale, row_scale_off)
     d.rows_per_sample, d.n_keep, d.split_k = rows_per_sample, n_keep, split_k
+    d.colsum = _ptr(colsum, colsum_off)
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -102,10 +103,10 @@ def attn_fwd(qkv, o, lse, batch, tokens, heads, head_dim, heads_keep, scale, *, 
 
 
 def attn_bwd(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, heads_keep, scale, *, qkv_off=0, o_off=0, lse_off=0,
-             impl=ATTN_AUTO):
+             impl=ATTN_AUTO, dbias=None):
     _ck(_lib.lib().vsx_attn_bwd(_ptr(qkv, qkv_off), _ptr(o, o_off), _ptr(d_o, o_off), _ptr(lse, lse_off),
                                        _ptr(dqkv, qkv_off), dt(qkv), batch, tokens, heads, head_dim, heads_keep, scale, impl,
-                                       _stream()))
+                                       _ptr(dbias), _stream()))
 
 
 # ------------------------------------------------------------------------------------------------ elementwise
@@ -114,9 +115,9 @@ def split_bf16(src, lds, hi, lo, ldd, rows, cols, src_off=0, dst_off=0, lo2=None
                                   _stream()))
 
 
-def scale_mask_cast(g, ldg, row_scale, rows_per_sample, n_keep, out, ldo, rows, cols, g_off=0, out_off=0, scale_off=0):
+def scale_mask_cast(g, ldg, row_scale, rows_per_sample, n_keep, out, ldo, rows, cols, g_off=0, out_off=0, scale_off=0, colsum=None):
     _ck(_lib.lib().vsx_scale_mask_cast(_ptr(g, g_off), ldg, _ptr(row_scale, scale_off), rows_per_sample, n_keep,
-                                              _ptr(out, out_off), dt(out), ldo, rows, cols, _stream()))
+                                              _ptr(out, out_off), dt(out), ldo, rows, cols, _ptr(colsum), _stream()))
 
 
 def colsum(x, ldx, rows, cols, out, x_off=0, out_off=0):
