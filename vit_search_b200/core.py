@@ -4,6 +4,7 @@ half-block forward/backward routines (attention half, MLP half) used by nets/sup
 All arithmetic happens in libvsx.so (see ops.py).  torch is used for allocation, streams and autograd wiring.
 """
 import math
+import weakref
 from contextlib import contextmanager
 
 import torch
@@ -50,8 +51,11 @@ def require_cuda(t, what):
 
 # ------------------------------------------------------------------------------------------------ operand preparation
 class _WeightCache:
-    """bf16 (hi[, lo]) copies of fp32 parameters, keyed on storage pointer + version counter, so a weight is cast
-    once per optimizer step and never after `rewiring` re-allocates it (nets/supernet_blocks.py:55-71,123-161)."""
+    """bf16 operand copies of fp32 parameters.  An entry is valid only for the SAME live parameter object (weak reference:
+    Python re-uses ids and the allocator re-uses addresses once a model dies), the same storage pointer (`rewiring`
+    re-allocates weights, nets/supernet_blocks.py:55-71,123-161), the same autograd version counter (in-place optimizer
+    updates) and the same `generation` (bumped by every model forward and by optimizers that write through raw pointers), so
+    a weight is cast once per step and a stale copy can never be served."""
 
     def __init__(self):
         self.entries = {}
@@ -61,8 +65,9 @@ class _WeightCache:
         key = (id(w), layout)
         tag = (w.data_ptr(), w._version, self.generation, _precision, tuple(w.shape))
         e = self.entries.get(key)
-        if e is not None and e[0] == tag:
+        if e is not None and e[0] == tag and e[2]() is w:
             return e[1]
+        ref = weakref.ref(w)
         src = w.detach()
         if layout in ('conv3x3_fwd', 'conv3x3_bwd'):
             # direct-conv operand [9 taps][32 n][32 k] bf16, zero padded (csrc/conv3x3.cu).  fwd: n = out ch, k = in ch;
@@ -71,7 +76,7 @@ class _WeightCache:
             t9 = src.permute(2, 3, 0, 1).reshape(9, o, i) if layout == 'conv3x3_fwd' else src.flip(2, 3).permute(2, 3, 1, 0).reshape(9, i, o)
             val = torch.zeros(9, 32, 32, device=w.device, dtype=torch.bfloat16)
             val[:, :t9.shape[1], :t9.shape[2]] = t9.to(torch.bfloat16)
-            self.entries[key] = (tag, val)
+            self.entries[key] = (tag, val, ref)
             return val
         if layout == 'ohwi':                       # conv weight [O, I, kh, kw] -> [O, kh*kw*I]
             src = src.permute(0, 2, 3, 1)
@@ -84,7 +89,9 @@ class _WeightCache:
         lo2 = torch.zeros_like(hi) if _precision == 'fp32' else None
         ops.split_bf16(src, cols, hi, lo, colsp, rows, cols, lo2=lo2) if cols % 4 == 0 else _split_slow(src, hi, lo, lo2)
         val = (hi, lo, lo2) if lo is not None else hi
-        self.entries[key] = (tag, val)
+        if len(self.entries) > 4096:            # dead models leave entries behind: drop them wholesale
+            self.entries = {k: v for k, v in self.entries.items() if v[2]() is not None}
+        self.entries[key] = (tag, val, ref)
         return val
 
     def clear(self):

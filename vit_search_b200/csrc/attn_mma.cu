@@ -1,7 +1,7 @@
 // Tensor-core attention for the ViT-Res shapes (N = 257 / 65 / 17 tokens, head_dim 32 / 48 / 64), bf16 in / fp32 softmax.
 //
-// One CTA per (sample, head); the two "column" operands of the head (K,V -- or Q,dO in the key-owner phase of the backward)
-// are staged in shared memory (<= 81 KB, two CTAs per SM), the row-owner operands come straight from global memory,
+// One CTA per (sample, head).  Forward: K and V of the head in shared memory (78 KB, two CTAs per SM), Q fragments straight
+// from global memory.  Backward: Q, K, V, dO in shared memory (<= 158 KB, one 12-warp CTA per SM);
 // every warp owns 16-row blocks and streams over the other dimension in 32/64-column chunks with mma.sync m16n8k16
 // (ldmatrix operand loads, online softmax in the forward, recomputation from the saved log-sum-exp in the backward).
 // Nothing of size N x N is written to HBM -- the reference materialises [B,H,N,N] scores three times
@@ -96,7 +96,7 @@ __device__ __forceinline__ void zero_slice(T* dst, long ld, int N, int D) {
 
 // ------------------------------------------------------------------------------------------------ forward
 template <int D>
-__global__ void __launch_bounds__(288) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, float* __restrict__ lse, int N, int H, int Hk,
+__global__ void __launch_bounds__(256, 2) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, float* __restrict__ lse, int N, int H, int Hk,
                                     float scale) {
   extern __shared__ __align__(16) uint8_t smem[];
   const int h = blockIdx.x, b = blockIdx.y;
@@ -126,12 +126,12 @@ __global__ void __launch_bounds__(288) attn_fwd_mma_kernel(const bf16* __restric
 #pragma unroll
     for (int i = 0; i < D / 8; ++i) oacc[i][0] = oacc[i][1] = oacc[i][2] = oacc[i][3] = 0.f;
     float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
-    for (int nt0 = 0; nt0 < ntiles; nt0 += 8) {
-      float s[8][4];
+    for (int nt0 = 0; nt0 < ntiles; nt0 += 4) {     // 32 keys per step (ntiles is even)
+      float s[4][4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+      for (int i = 0; i < 4; ++i) s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
 #pragma unroll
-      for (int p = 0; p < 4; ++p) {
+      for (int p = 0; p < 2; ++p) {
         if (nt0 + 2 * p < ntiles) {
 #pragma unroll
           for (int ks = 0; ks < D / 16; ++ks) {
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(288) attn_fwd_mma_kernel(const bf16* __restric
       }
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const int col = (nt0 + i) * 8 + 2 * t;
         s[i][0] = col < N ? s[i][0] * c : -INFINITY;
         s[i][1] = col + 1 < N ? s[i][1] * c : -INFINITY;
@@ -157,12 +157,12 @@ __global__ void __launch_bounds__(288) attn_fwd_mma_kernel(const bf16* __restric
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // every chunk has >= 1 valid column, so mn is finite
+      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);   // every chunk starts below N, so mn is finite
       const float cr0 = exp2f(m0 - mn0), cr1 = exp2f(m1 - mn1);
       m0 = mn0, m1 = mn1;
       float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
+      for (int i = 0; i < 4; ++i) {
         s[i][0] = exp2f(s[i][0] - mn0), s[i][1] = exp2f(s[i][1] - mn0);
         s[i][2] = exp2f(s[i][2] - mn1), s[i][3] = exp2f(s[i][3] - mn1);
         rs0 += s[i][0] + s[i][1];
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(288) attn_fwd_mma_kernel(const bf16* __restric
 #pragma unroll
       for (int i = 0; i < D / 8; ++i) oacc[i][0] *= cr0, oacc[i][1] *= cr0, oacc[i][2] *= cr1, oacc[i][3] *= cr1;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {   // k-steps of 16 keys
+      for (int j = 0; j < 2; ++j) {   // k-steps of 16 keys
         if (nt0 + 2 * j < ntiles) {
           uint32_t pa[4] = {pack_bf16(s[2 * j][0], s[2 * j][1]), pack_bf16(s[2 * j][2], s[2 * j][3]),
                             pack_bf16(s[2 * j + 1][0], s[2 * j + 1][1]), pack_bf16(s[2 * j + 1][2], s[2 * j + 1][3])};
@@ -317,7 +317,7 @@ __device__ __forceinline__ void colsum_block(float* cs, int row0, int N, int lan
 }
 
 template <int D>
-__global__ void __launch_bounds__(288) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ d_o,
+__global__ void __launch_bounds__(384, 1) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ d_o,
                                     const float* __restrict__ lse, bf16* __restrict__ dqkv, int N, int H, int Hk, float scale,
                                     float* __restrict__ dbias) {
   extern __shared__ __align__(16) uint8_t smem[];
@@ -334,14 +334,16 @@ __global__ void __launch_bounds__(288) attn_bwd_mma_kernel(const bf16* __restric
   const int Np = (N + 15) / 16 * 16;
   const uint32_t sbase = smem_u32(smem);
   constexpr int TB = (D + 8) * 2;
-  Tile<D> T0{sbase}, T1{sbase + (uint32_t)Np * TB};     // phase A: Q, dO     phase B: K, V   (two CTAs fit per SM)
-  float* lse2_s = reinterpret_cast<float*>(smem + 2 * (size_t)Np * TB);
+  Tile<D> Qs{sbase}, Ks{sbase + (uint32_t)Np * TB}, Vs{sbase + 2u * Np * TB}, Os{sbase + 3u * Np * TB};   // Os holds dO
+  float* lse2_s = reinterpret_cast<float*>(smem + 4 * (size_t)Np * TB);
   float* delta_s = lse2_s + Np + STAT_PAD;
   const bf16* base = qkv + (long)b * N * ldq + h * D;
   const bf16* ob = o + (long)b * N * ldo + h * D;
   const bf16* dob = d_o + (long)b * N * ldo + h * D;
-  stage_tile<D>(smem, T0, base, ldq, N, Np, sbase);
-  stage_tile<D>(smem, T1, dob, ldo, N, Np, sbase);
+  stage_tile<D>(smem, Qs, base, ldq, N, Np, sbase);
+  stage_tile<D>(smem, Ks, base + (long)H * D, ldq, N, Np, sbase);
+  stage_tile<D>(smem, Vs, base + 2L * H * D, ldq, N, Np, sbase);
+  stage_tile<D>(smem, Os, dob, ldo, N, Np, sbase);
   for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) cs[i] = 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   // delta_i = dO_i . O_i, lse in log2 units; padded rows get finite zeros
@@ -357,37 +359,42 @@ __global__ void __launch_bounds__(288) attn_bwd_mma_kernel(const bf16* __restric
   }
   __syncthreads();
   const float c = scale * LOG2E;
-  const int ntiles = Np / 8;
-  uint32_t xf[D / 16][4], yf[D / 16][4];
-  // ---- phase A: dK, dV (owner rows = keys; K, V fragments from global, Q and dO in shared memory)
-  for (int rb = warp; rb * 16 < N; rb += nwarps) {
-    float dv[D / 8][4], dk[D / 8][4];
+  const int ntiles = Np / 8, nrb = (N + 15) / 16;
+  // One work list: items [0, nrb) are key-owner row blocks (dK, dV), items [nrb, 2 nrb) query-owner row blocks (dQ).  With
+  // 257 tokens that is 34 similar items over 12 warps: three nearly full rounds.
+  for (int item = warp; item < 2 * nrb; item += nwarps) {
+    uint32_t xf[D / 16][4], yf[D / 16][4];
+    if (item < nrb) {
+      const int row0 = item * 16;
+      float dv[D / 8][4], dk[D / 8][4];
 #pragma unroll
-    for (int i = 0; i < D / 8; ++i) dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
-    load_a_global<D>(xf, base + (long)H * D, ldq, rb * 16, N, lane);
-    load_a_global<D>(yf, base + 2L * H * D, ldq, rb * 16, N, lane);
-    bwd_block<D, true>(xf, yf, T0, T1, lse2_s, delta_s, rb * 16, ntiles, c, lane, dv, dk);
-    store_block<D>(dbase + (long)H * D, ldq, rb * 16, N, lane, dk, scale);
-    store_block<D>(dbase + 2L * H * D, ldq, rb * 16, N, lane, dv, 1.0f);
-    if (dbias != nullptr) {
-      colsum_block<D>(cs + D, rb * 16, N, lane, dk, scale);
-      colsum_block<D>(cs + 2 * D, rb * 16, N, lane, dv, 1.0f);
+      for (int i = 0; i < D / 8; ++i) dv[i][0] = dv[i][1] = dv[i][2] = dv[i][3] = dk[i][0] = dk[i][1] = dk[i][2] = dk[i][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < D / 16; ++ks) {
+        Ks.load_a(xf[ks], row0, ks * 16, lane);
+        Vs.load_a(yf[ks], row0, ks * 16, lane);
+      }
+      bwd_block<D, true>(xf, yf, Qs, Os, lse2_s, delta_s, row0, ntiles, c, lane, dv, dk);
+      store_block<D>(dbase + (long)H * D, ldq, row0, N, lane, dk, scale);
+      store_block<D>(dbase + 2L * H * D, ldq, row0, N, lane, dv, 1.0f);
+      if (dbias != nullptr) {
+        colsum_block<D>(cs + D, row0, N, lane, dk, scale);
+        colsum_block<D>(cs + 2 * D, row0, N, lane, dv, 1.0f);
+      }
+    } else {
+      const int row0 = (item - nrb) * 16;
+      float unused[D / 8][4], dq[D / 8][4];
+#pragma unroll
+      for (int i = 0; i < D / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < D / 16; ++ks) {
+        Qs.load_a(xf[ks], row0, ks * 16, lane);
+        Os.load_a(yf[ks], row0, ks * 16, lane);
+      }
+      bwd_block<D, false>(xf, yf, Ks, Vs, lse2_s, delta_s, row0, ntiles, c, lane, unused, dq);
+      store_block<D>(dbase, ldq, row0, N, lane, dq, scale);
+      if (dbias != nullptr) colsum_block<D>(cs, row0, N, lane, dq, scale);
     }
-  }
-  __syncthreads();
-  stage_tile<D>(smem, T0, base + (long)H * D, ldq, N, Np, sbase);
-  stage_tile<D>(smem, T1, base + 2L * H * D, ldq, N, Np, sbase);
-  __syncthreads();
-  // ---- phase B: dQ (owner rows = queries; Q, dO fragments from global, K and V in shared memory)
-  for (int rb = warp; rb * 16 < N; rb += nwarps) {
-    float unused[D / 8][4], dq[D / 8][4];
-#pragma unroll
-    for (int i = 0; i < D / 8; ++i) dq[i][0] = dq[i][1] = dq[i][2] = dq[i][3] = 0.f;
-    load_a_global<D>(xf, base, ldq, rb * 16, N, lane);
-    load_a_global<D>(yf, dob, ldo, rb * 16, N, lane);
-    bwd_block<D, false>(xf, yf, T0, T1, lse2_s, delta_s, rb * 16, ntiles, c, lane, unused, dq);
-    store_block<D>(dbase, ldq, rb * 16, N, lane, dq, scale);
-    if (dbias != nullptr) colsum_block<D>(cs, rb * 16, N, lane, dq, scale);
   }
   if (dbias != nullptr) {
     __syncthreads();
@@ -395,11 +402,11 @@ __global__ void __launch_bounds__(288) attn_bwd_mma_kernel(const bf16* __restric
   }
 }
 
-// Warps per CTA.  257 tokens = 17 row blocks; the register file (168 regs/thread in the backward, 139 in the forward at
-// head_dim 64) allows two co-resident CTAs of 6 (backward) / 7 (forward) warps -- 3 rounds of row blocks each.
+// Warps per CTA.  Forward: 8 warps, <= 128 registers, two CTAs per SM (16 warps).  Backward: one CTA of 12 warps per SM
+// (~168 registers per thread fill the register file) walking the merged key-owner / query-owner work list.
 int warps_for(int N, bool bwd) {
   const int rb = (N + 15) / 16;
-  if (rb >= 12) return bwd ? 6 : 7;
+  if (bwd) return 2 * rb >= 12 ? 12 : 2 * rb;      // one item per warp when there are few
   return rb > 8 ? 8 : rb;
 }
 
@@ -412,6 +419,7 @@ int launch_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int Hk
     set_error("vsx_attn_fwd: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
     return VSX_ERR_CUDA;
   }
+  cudaFuncSetAttribute(attn_fwd_mma_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   attn_fwd_mma_kernel<D><<<dim3(H, B), warps_for(N, false) * 32, smem, st>>>((const bf16*)qkv, (bf16*)o, lse, N, H, Hk, scale);
   return check_launch("vsx_attn_fwd");
 }
@@ -419,7 +427,7 @@ template <int D>
 int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int N, int H, int Hk, float scale,
                float* dbias, cudaStream_t st) {
   const int Np = (N + 15) / 16 * 16;
-  const size_t smem = 2 * (size_t)Np * (D + 8) * 2 + 2 * (size_t)(Np + STAT_PAD) * sizeof(float);
+  const size_t smem = 4 * (size_t)Np * (D + 8) * 2 + 2 * (size_t)(Np + STAT_PAD) * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(attn_bwd_mma_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) {
     set_error("vsx_attn_bwd: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
@@ -435,7 +443,7 @@ int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse
 bool attn_mma_supported(int N, int D) {
   if (!(D == 32 || D == 48 || D == 64)) return false;
   const int Np = (N + 15) / 16 * 16;
-  return 2 * (size_t)Np * (D + 8) * 2 + 2 * (size_t)(Np + STAT_PAD) * sizeof(float) <= 227 * 1024;
+  return 4 * (size_t)Np * (D + 8) * 2 + 2 * (size_t)(Np + STAT_PAD) * sizeof(float) + 3 * 64 * 4 <= 227 * 1024;
 }
 
 int attn_fwd_mma(const void* qkv, void* o, float* lse, int B, int N, int H, int D, int Hk, float scale, cudaStream_t st) {

@@ -35,28 +35,57 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// Load the activated halo tile of image b around tile (ty0, tx0) into `halo` ([HH*HW][PITCH] bf16); OOB pixels and channels >= C are 0.
-__device__ __forceinline__ void load_halo(bf16* halo, const bf16* __restrict__ in, const float* sc_s, const float* sh_s, bool act, int b, int H,
-                                          int W, int C, int ty0, int tx0) {
-  for (int idx = threadIdx.x; idx < HH * HW * (CP / 8); idx += blockDim.x) {
-    const int pix = idx / (CP / 8), ch = (idx % (CP / 8)) * 8;
-    const int iy = ty0 - 1 + pix / HW, ix = tx0 - 1 + pix % HW;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (ch < C && iy >= 0 && iy < H && ix >= 0 && ix < W) {
-      v = *reinterpret_cast<const uint4*>(in + (((long)b * H + iy) * W + ix) * C + ch);
-      if (act) {
+// The halo tile of the NEXT tile is fetched into registers while the current tile is in the tensor cores (software
+// pipelining), then activated (BatchNorm-apply + ReLU of the producing layer) and committed to shared memory.
+// OOB pixels and channels >= C are zero (zero padding applies to the ACTIVATED map).
+constexpr int HALO_ITEMS = HH * HW * (CP / 8);   // 16-byte chunks
+
+template <int NT>
+struct HaloRegs {
+  static constexpr int N = (HALO_ITEMS + NT - 1) / NT;
+  uint4 v[N];
+  uint32_t valid;
+};
+
+template <int NT>
+__device__ __forceinline__ void halo_fetch(HaloRegs<NT>& r, const bf16* __restrict__ in, int b, int H, int W, int C, int ty0, int tx0) {
+  r.valid = 0;
+#pragma unroll
+  for (int j = 0; j < HaloRegs<NT>::N; ++j) {
+    const int idx = threadIdx.x + j * NT;
+    r.v[j] = make_uint4(0u, 0u, 0u, 0u);
+    if (idx < HALO_ITEMS) {
+      const int pix = idx / (CP / 8), ch = (idx % (CP / 8)) * 8;
+      const int iy = ty0 - 1 + pix / HW, ix = tx0 - 1 + pix % HW;
+      if (ch < C && iy >= 0 && iy < H && ix >= 0 && ix < W) {
+        r.v[j] = *reinterpret_cast<const uint4*>(in + (((long)b * H + iy) * W + ix) * C + ch);
+        r.valid |= 1u << j;
+      }
+    }
+  }
+}
+
+template <int NT>
+__device__ __forceinline__ void halo_commit(bf16* halo, const HaloRegs<NT>& r, const float* sc_s, const float* sh_s, bool act) {
+#pragma unroll
+  for (int j = 0; j < HaloRegs<NT>::N; ++j) {
+    const int idx = threadIdx.x + j * NT;
+    if (idx < HALO_ITEMS) {
+      const int pix = idx / (CP / 8), ch = (idx % (CP / 8)) * 8;
+      uint4 v = r.v[j];
+      if (act && (r.valid >> j & 1u)) {
         uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[j]));
-          f.x = fmaxf(f.x * sc_s[ch + 2 * j] + sh_s[ch + 2 * j], 0.f);
-          f.y = fmaxf(f.y * sc_s[ch + 2 * j + 1] + sh_s[ch + 2 * j + 1], 0.f);
-          w[j] = pack_bf16(f.x, f.y);
+        for (int k = 0; k < 4; ++k) {
+          float2 f = __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&w[k]));
+          f.x = fmaxf(f.x * sc_s[ch + 2 * k] + sh_s[ch + 2 * k], 0.f);
+          f.y = fmaxf(f.y * sc_s[ch + 2 * k + 1] + sh_s[ch + 2 * k + 1], 0.f);
+          w[k] = pack_bf16(f.x, f.y);
         }
         v = make_uint4(w[0], w[1], w[2], w[3]);
       }
+      *reinterpret_cast<uint4*>(halo + pix * PITCH + ch) = v;
     }
-    *reinterpret_cast<uint4*>(halo + pix * PITCH + ch) = v;
   }
 }
 
@@ -94,12 +123,24 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) conv3x3_fwd_kernel(const bf16*
   const uint32_t halo_a = smem_u32(halo), wts_a = smem_u32(wts);
   const int tiles_x = W / TW, tiles_y = H / TH, tiles = B * tiles_x * tiles_y;
   const int lj = lane >> 3, li = lane & 7;
+  HaloRegs<FWD_WARPS * 32> pre;
+  if ((int)blockIdx.x < tiles) {
+    const int rem0 = blockIdx.x % (tiles_x * tiles_y);
+    halo_fetch(pre, in, blockIdx.x / (tiles_x * tiles_y), H, W, C, (rem0 / tiles_x) * TH, (rem0 % tiles_x) * TW);
+  }
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int b = tile / (tiles_x * tiles_y), rem = tile % (tiles_x * tiles_y);
     const int ty0 = (rem / tiles_x) * TH, tx0 = (rem % tiles_x) * TW;
     __syncthreads();                       // previous tile's MMAs are done reading the halo (also orders the weight load)
-    load_halo(halo, in, sc_s, sh_s, act, b, H, W, C, ty0, tx0);
+    halo_commit(halo, pre, sc_s, sh_s, act);
     __syncthreads();
+    {
+      const int nxt = tile + gridDim.x;    // next tile's loads fly while this tile is in the tensor cores
+      if (nxt < tiles) {
+        const int remn = nxt % (tiles_x * tiles_y);
+        halo_fetch(pre, in, nxt / (tiles_x * tiles_y), H, W, C, (remn / tiles_x) * TH, (remn % tiles_x) * TW);
+      }
+    }
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
@@ -203,18 +244,34 @@ __global__ void __launch_bounds__(WG_WARPS * 32) conv3x3_wgrad_kernel(const bf16
   const int tiles_x = W / TW, tiles_y = H / TH, tiles = B * tiles_x * tiles_y;
   const int lj = lane >> 3, li = lane & 7;
   const int ky = warp / 3, kx = warp % 3;
-  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  constexpr int NT = WG_WARPS * 32, DY_ITEMS = TH * TW * (CP / 8), DY_N = (DY_ITEMS + NT - 1) / NT;
+  HaloRegs<NT> pre;
+  uint4 dpre[DY_N];
+  auto fetch = [&](int tile) {
     const int b = tile / (tiles_x * tiles_y), rem = tile % (tiles_x * tiles_y);
     const int ty0 = (rem / tiles_x) * TH, tx0 = (rem % tiles_x) * TW;
+    halo_fetch(pre, in, b, H, W, C, ty0, tx0);
+#pragma unroll
+    for (int j = 0; j < DY_N; ++j) {
+      const int idx = threadIdx.x + j * NT;
+      dpre[j] = make_uint4(0u, 0u, 0u, 0u);
+      if (idx < DY_ITEMS) {
+        const int pix = idx / (CP / 8), ch = (idx % (CP / 8)) * 8;
+        if (ch < C) dpre[j] = *reinterpret_cast<const uint4*>(dy + (((long)b * H + ty0 + pix / TW) * W + tx0 + pix % TW) * C + ch);
+      }
+    }
+  };
+  if ((int)blockIdx.x < tiles) fetch(blockIdx.x);
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     __syncthreads();
-    load_halo(halo, in, sc_s, sh_s, act, b, H, W, C, ty0, tx0);
-    for (int idx = threadIdx.x; idx < TH * TW * (CP / 8); idx += blockDim.x) {
-      const int pix = idx / (CP / 8), ch = (idx % (CP / 8)) * 8;
-      uint4 v = make_uint4(0u, 0u, 0u, 0u);
-      if (ch < C) v = *reinterpret_cast<const uint4*>(dy + (((long)b * H + ty0 + pix / TW) * W + tx0 + pix % TW) * C + ch);
-      *reinterpret_cast<uint4*>(dys + pix * PITCH + ch) = v;
+    halo_commit(halo, pre, sc_s, sh_s, act);
+#pragma unroll
+    for (int j = 0; j < DY_N; ++j) {
+      const int idx = threadIdx.x + j * NT;
+      if (idx < DY_ITEMS) *reinterpret_cast<uint4*>(dys + (idx / (CP / 8)) * PITCH + (idx % (CP / 8)) * 8) = dpre[j];
     }
     __syncthreads();
+    if (tile + (int)gridDim.x < tiles) fetch(tile + gridDim.x);
 #pragma unroll
     for (int r = 0; r < TH; ++r) {   // k-step = the 16 pixels of tile row r
       uint32_t a0[4], a1[4], b01[4], b23[4];

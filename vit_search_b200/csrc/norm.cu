@@ -102,8 +102,14 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T* __restri
     const T* dyr = (second ? dy2 : dy) + irow * lddy;
     const float* xr = x + r * ldx;
     const float mu = mean[r], rs = rstd[r];
-    float4 d[NV], z[NV];
+    float4 d[NV], z[NV], gi4[NV];
     float s1 = 0.f, s2 = 0.f;
+    const float* gi = g_in != nullptr ? g_in + r * ldg : nullptr;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {   // all global loads of the row are issued before the first reduction
+      const int c = (i * 32 + lane) * 4;
+      gi4[i] = (gi != nullptr && c < C) ? ld4(gi + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
@@ -128,12 +134,11 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T* __restri
     s1 = warp_sum(s1) * inv_keep;   // mean(dz)/p
     s2 = warp_sum(s2) * inv_keep;   // mean(z*dz)/p
     float* go = g_out + r * ldg;
-    const float* gi = g_in != nullptr ? g_in + r * ldg : nullptr;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
       if (c < C) {
-        float4 o = gi != nullptr ? ld4(gi + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 o = gi4[i];
         if (c < keep) {
           o.x += (d[i].x - s1 - z[i].x * s2) * rs;
           if (c + 1 < keep) o.y += (d[i].y - s1 - z[i].y * s2) * rs;
@@ -201,7 +206,7 @@ int ln_bwd_dispatch(const void* dy, const void* dy2, long lddy, const float* x, 
                     const float* gamma, const float* g_in, float* g_out, long ldg, float* dgamma, float* dbeta, int rows, int C,
                     int keep, int rps, int split, cudaStream_t st) {
   const int nv = ceil_div(C, 128);
-  const int grid = ln_grid(rows, 4);
+  const int grid = ln_grid(rows, nv <= 2 ? 8 : 4);
 #define VSX_LN_B(NV)                                                                                                      \
   case NV:                                                                                                                \
     ln_bwd_kernel<NV, T><<<grid, LN_WARPS * 32, 0, st>>>((const T*)dy, (const T*)dy2, lddy, x, ldx, mean, rstd, gamma, g_in, \

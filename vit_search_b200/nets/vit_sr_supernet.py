@@ -478,6 +478,7 @@ class FlexibleDistillVisionTransformerSR(nn.Module):
     def forward_features(self, x):
         core.require_cuda(x, 'FlexibleDistillVisionTransformerSR')
         assert self.num_tokens == 1, 'distillation-token path is outside the hot path (SURVEY.md §2)'
+        core.weights.generation += 1          # weights may have been updated since the last forward: re-derive operand copies
         B = x.shape[0]
         keeps = self.sample_keeps(B) if self.is_supernet else [{} for _ in self.network_def]
         self.last_keeps = keeps
