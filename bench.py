@@ -162,6 +162,7 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)')
     torch.cuda.set_device(local)
+    ops.set_device(local)
     _lib.check(_lib.lib().vsx_device_ok(local))
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')

@@ -402,7 +402,8 @@ class HalfBlockFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, meta, x, *params):
         require_cuda(x, 'Block')
-        x = x.contiguous()
+        if not x.is_contiguous():
+            x = x.contiguous()
         fwd = attn_half_forward if meta.kind == 'attn' else mlp_half_forward
         out, saved = fwd(meta, x, *params)
         ctx.meta, ctx.saved = meta, saved
@@ -413,6 +414,6 @@ class HalfBlockFn(torch.autograd.Function):
     def backward(ctx, g):
         x, *params = ctx.saved_tensors
         bwd = attn_half_backward if ctx.meta.kind == 'attn' else mlp_half_backward
-        g_in, pg = bwd(ctx.meta, g.contiguous(), ctx.saved, x, *params)
+        g_in, pg = bwd(ctx.meta, g if g.is_contiguous() else g.contiguous(), ctx.saved, x, *params)
         ctx.saved = None
         return (None, g_in) + tuple(pg)

@@ -74,29 +74,33 @@ class FusedAdamW:
             p.grad = None
 
     def _build_table(self):
+        """Pointer table of the fused kernel: one 64-byte record per tensor (struct vsx_adamw_tensor), packed with numpy."""
+        import numpy as np
         dev = self.entries[0][1].device
-        arr = (_lib.AdamWTensor * len(self.entries))()
-        ct, ci = [], []
+        n = len(self.entries)
+        rec = np.zeros(n, dtype=np.dtype([('param', '<u8'), ('grad', '<u8'), ('m', '<u8'), ('v', '<u8'), ('hi', '<u8'), ('lo', '<u8'),
+                                          ('numel', '<i8'), ('wd', '<f4'), ('pad', '<u4')]))
+        assert rec.itemsize == C.sizeof(_lib.AdamWTensor)
+        chunks = []
         for i, (name, p, wd) in enumerate(self.entries):
             if p.grad is None:
                 p.grad = torch.zeros_like(p)
+            elif not p.grad.is_contiguous():
+                p.grad = p.grad.contiguous()
             st = self.state.get(name)
             if st is None or st[0].shape != p.shape:
                 st = (torch.zeros_like(p), torch.zeros_like(p))
                 self.state[name] = st
-            g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
-            arr[i].param, arr[i].grad = p.data_ptr(), g.data_ptr()
-            arr[i].exp_avg, arr[i].exp_avg_sq = st[0].data_ptr(), st[1].data_ptr()
-            arr[i].shadow_hi = arr[i].shadow_lo = None
-            arr[i].numel, arr[i].weight_decay = p.numel(), wd
-            n = math.ceil(p.numel() / self.chunk)
-            ct += [i] * n
-            ci += list(range(n))
-        raw = bytes(arr)
-        self._tab = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
-        self._ct = torch.tensor(ct, dtype=torch.int32, device=dev)
-        self._ci = torch.tensor(ci, dtype=torch.int32, device=dev)
-        self._nchunks = len(ct)
+            rec[i] = (p.data_ptr(), p.grad.data_ptr(), st[0].data_ptr(), st[1].data_ptr(), 0, 0, p.numel(), wd, 0)
+            chunks.append(math.ceil(p.numel() / self.chunk))
+        if getattr(self, '_chunks', None) != chunks:
+            self._chunks = chunks
+            ct = np.repeat(np.arange(n, dtype=np.int32), chunks)
+            ci = np.concatenate([np.arange(c, dtype=np.int32) for c in chunks])
+            self._ct = torch.from_numpy(ct).to(dev)
+            self._ci = torch.from_numpy(ci).to(dev)
+            self._nchunks = int(ct.shape[0])
+        self._tab = torch.from_numpy(rec.view(np.uint8)).to(dev)
 
     def step(self):
         # gradient tensors are re-allocated by every backward, parameters by `rewiring`: re-derive the pointer table when

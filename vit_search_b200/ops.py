@@ -22,16 +22,36 @@ def _ck(rc):
     _lib.check(rc)
 
 
+_DEV = None
+_raw_stream = torch._C._cuda_getCurrentRawStream if hasattr(torch._C, '_cuda_getCurrentRawStream') else None
+
+
 def _stream():
-    return torch.cuda.current_stream().cuda_stream
+    """cudaStream_t of torch's current stream (fast path: the raw-stream query costs ~0.3 us, current_stream() ~14 us)."""
+    global _DEV
+    if _raw_stream is None:
+        return torch.cuda.current_stream().cuda_stream
+    if _DEV is None:
+        _DEV = torch.cuda.current_device()
+    return _raw_stream(_DEV)
+
+
+def set_device(index):
+    """Tell the bindings which device this process drives (one process per GPU)."""
+    global _DEV
+    _DEV = index
+
+
+_ESIZE = {torch.bfloat16: 2, torch.float32: 4, torch.float64: 8, torch.int32: 4, torch.int64: 8, torch.uint8: 1, torch.bool: 1}
 
 
 def _ptr(t, offset=0):
     """Device pointer of element `offset` of tensor t (None -> NULL)."""
     if t is None:
         return None
-    assert t.is_cuda, 'libvsx operates on CUDA tensors only (no CPU fallback)'
-    return t.data_ptr() + offset * t.element_size()
+    if not t.is_cuda:
+        raise RuntimeError('libvsx operates on CUDA tensors only (no CPU fallback)')
+    return t.data_ptr() + offset * _ESIZE[t.dtype]
 
 
 def dt(t):
@@ -55,40 +75,33 @@ def masked_ln_bwd(dy, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, dgamma,
 
 
 # ------------------------------------------------------------------------------------------------ GEMM
+_P6 = C.c_void_p * 6
+_PAIRS3 = [(0, 0), (1, 0), (0, 1)]
+_PAIRS6 = [(0, 0), (1, 0), (0, 1), (1, 1), (2, 0), (0, 2)]
+
 def gemm(a, b, lda, ldb, M, N, K, epilogue, out, ldo, *, a_off=0, b_off=0, out_off=0, a_layout=KMAJOR,
          b_layout=KMAJOR, n_out=None, out2=None, ldo2=0, out2_off=0, bias=None, bias_off=0, aux=None, ld_aux=0,
          aux_off=0, row_scale=None, row_scale_off=0, rows_per_sample=1, n_keep=0, split_k=1, colsum=None, colsum_off=0):
     """a, b: a bf16 tensor, or tuples of 2 (3 product terms, ~2^-16) or 3 (6 terms, fp32-exact) bf16 parts whose sum is
     the fp32 operand (split-bf16 high-precision mode)."""
-    d = _lib.GemmDesc()
     if isinstance(a, (tuple, list)):
         n = min(len(a), len(b))
-        pairs = [(0, 0), (1, 0), (0, 1)] if n == 2 else [(0, 0), (1, 0), (0, 1), (1, 1), (2, 0), (0, 2)]
-        terms = [(a[i], b[j]) for i, j in pairs]
+        pairs = _PAIRS3 if n == 2 else _PAIRS6
+        pa = _P6(*[_ptr(a[i], a_off) for i, _ in pairs])
+        pb = _P6(*[_ptr(b[j], b_off) for _, j in pairs])
+        nterms = len(pairs)
     else:
-        terms = [(a, b)]
-    for t, (ta, tb) in enumerate(terms):
-        assert ta.dtype == torch.bfloat16 and tb.dtype == torch.bfloat16
-        d.a[t] = _ptr(ta, a_off)
-        d.b[t] = _ptr(tb, b_off)
-    d.terms = len(terms)
-    d.lda, d.ldb, d.a_layout, d.b_layout = lda, ldb, a_layout, b_layout
-    d.M, d.N, d.K = M, N, K
-    d.epilogue, d.out_dtype = epilogue, dt(out)
-    d.out, d.ldo = _ptr(out, out_off), ldo
-    d.out2, d.ldo2 = _ptr(out2, out2_off), ldo2
-    d.n_out = N if n_out is None else n_out
-    d.bias = _ptr(bias, bias_off)
-    d.aux, d.ld_aux = _ptr(aux, aux_off), ld_aux
-    d.row_scale = _ptr(row_scale, row_scale_off)
-    d.rows_per_sample, d.n_keep, d.split_k = rows_per_sample, n_keep, split_k
-    d.colsum = _ptr(colsum, colsum_off)
+        pa, pb, nterms = _P6(_ptr(a, a_off)), _P6(_ptr(b, b_off)), 1
+    # positional construction: one C-level initialisation instead of ~25 Python-level field stores
+    d = _lib.GemmDesc(pa, pb, nterms, lda, ldb, a_layout, b_layout, M, N, K, epilogue, _DT[out.dtype], _ptr(out, out_off), ldo,
+                      _ptr(out2, out2_off), ldo2, N if n_out is None else n_out, _ptr(bias, bias_off), _ptr(aux, aux_off), ld_aux,
+                      _ptr(row_scale, row_scale_off), rows_per_sample, n_keep, split_k, _ptr(colsum, colsum_off))
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         _ck(_lib.lib().vsx_gemm(C.byref(d), _stream()))
         e1.record()
-        PROFILE.append((e0, e1, 2.0 * M * N * K, (M, N, K, epilogue, a_layout, b_layout, d.n_out, split_k, len(terms))))
+        PROFILE.append((e0, e1, 2.0 * M * N * K, (M, N, K, epilogue, a_layout, b_layout, d.n_out, split_k, nterms)))
         return
     _ck(_lib.lib().vsx_gemm(C.byref(d), _stream()))
 
