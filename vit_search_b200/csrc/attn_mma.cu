@@ -346,16 +346,26 @@ __global__ void __launch_bounds__(384, 1) attn_bwd_mma_kernel(const bf16* __rest
   stage_tile<D>(smem, Os, dob, ldo, N, Np, sbase);
   for (int i = threadIdx.x; i < 3 * D; i += blockDim.x) cs[i] = 0.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  // delta_i = dO_i . O_i, lse in log2 units; padded rows get finite zeros
-  for (int i = warp; i < Np + STAT_PAD; i += nwarps) {   // the padding keeps the 32-column chunk loads in bounds
+  // delta_i = dO_i . O_i and lse in log2 units (padded rows get finite zeros; the padding keeps the 32-column chunk loads in
+  // bounds).  One row per thread: all 2*D/8 16-byte loads of a row are independent and in flight together.
+  for (int r = threadIdx.x; r < Np + STAT_PAD; r += blockDim.x) {
     float acc = 0.f;
-    if (i < N)
-      for (int d = lane; d < D; d += 32) acc += __bfloat162float(dob[(long)i * ldo + d]) * __bfloat162float(ob[(long)i * ldo + d]);
-    acc = warp_sum(acc);
-    if (lane == 0) {
-      delta_s[i] = acc;
-      lse2_s[i] = i < N ? lse[((long)b * H + h) * N + i] * LOG2E : 0.f;
+    if (r < N) {
+#pragma unroll
+      for (int cc = 0; cc < D; cc += 8) {
+        const uint4 ov = *reinterpret_cast<const uint4*>(ob + (long)r * ldo + cc);
+        const uint4 dv = *reinterpret_cast<const uint4*>(dob + (long)r * ldo + cc);
+        const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[j]));
+          const float2 d2 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[j]));
+          acc += a.x * d2.x + a.y * d2.y;
+        }
+      }
     }
+    delta_s[r] = acc;
+    lse2_s[r] = r < N ? lse[((long)b * H + h) * N + r] * LOG2E : 0.f;
   }
   __syncthreads();
   const float c = scale * LOG2E;

@@ -60,25 +60,23 @@ __global__ void __launch_bounds__(SMC_WARPS * 32) scale_mask_cast_kernel(const f
     }
   }
   if (colsum == nullptr) return;
-  __shared__ float4 red[SMC_WARPS][32];
+  // one barrier: every warp parks its partials, then thread j sums column-quad j over the warps
+  __shared__ float4 red[SMC_WARPS][NV * 32];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    red[warp][lane] = acc[i];
-    __syncthreads();
-    if (warp == 0) {
-      float4 t = red[0][lane];
+  for (int i = 0; i < NV; ++i) red[warp][i * 32 + lane] = acc[i];
+  __syncthreads();
+  for (int q = threadIdx.x; q < NV * 32; q += SMC_WARPS * 32) {
+    float4 t = red[0][q];
 #pragma unroll
-      for (int w = 1; w < SMC_WARPS; ++w) {
-        const float4 u = red[w][lane];
-        t.x += u.x, t.y += u.y, t.z += u.z, t.w += u.w;
-      }
-      const int c = (i * 32 + lane) * 4;
-      if (c < n_keep) atomicAdd(colsum + c, t.x);
-      if (c + 1 < n_keep) atomicAdd(colsum + c + 1, t.y);
-      if (c + 2 < n_keep) atomicAdd(colsum + c + 2, t.z);
-      if (c + 3 < n_keep) atomicAdd(colsum + c + 3, t.w);
+    for (int w = 1; w < SMC_WARPS; ++w) {
+      const float4 u = red[w][q];
+      t.x += u.x, t.y += u.y, t.z += u.z, t.w += u.w;
     }
-    __syncthreads();
+    const int c = q * 4;
+    if (c < n_keep) atomicAdd(colsum + c, t.x);
+    if (c + 1 < n_keep) atomicAdd(colsum + c + 1, t.y);
+    if (c + 2 < n_keep) atomicAdd(colsum + c + 2, t.z);
+    if (c + 3 < n_keep) atomicAdd(colsum + c + 3, t.w);
   }
 }
 
@@ -120,6 +118,7 @@ int ew_grid(long work_items) {
 
 }  // namespace
 }  // namespace vsx
+
 
 using namespace vsx;
 

@@ -149,28 +149,26 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T* __restri
       }
     }
   }
-  // cross-warp reduction of the per-lane column partials, then one atomic per column per CTA
-  __shared__ float4 red[LN_WARPS][32];
+  // cross-warp reduction of the per-lane column partials (one barrier per statistic), then one atomic per column per CTA
+  __shared__ float4 red[LN_WARPS][NV * 32];
   for (int pass = 0; pass < 2; ++pass) {
     float* dst = pass == 0 ? dgamma : dbeta;
+    if (pass == 1) __syncthreads();
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      red[warp][lane] = pass == 0 ? ag[i] : ab[i];
-      __syncthreads();
-      if (warp == 0) {
-        float4 t = red[0][lane];
+    for (int i = 0; i < NV; ++i) red[warp][i * 32 + lane] = pass == 0 ? ag[i] : ab[i];
+    __syncthreads();
+    for (int q = threadIdx.x; q < NV * 32; q += LN_WARPS * 32) {
+      float4 t = red[0][q];
 #pragma unroll
-        for (int w = 1; w < LN_WARPS; ++w) {
-          const float4 u = red[w][lane];
-          t.x += u.x, t.y += u.y, t.z += u.z, t.w += u.w;
-        }
-        const int c = (i * 32 + lane) * 4;
-        if (c < keep) atomicAdd(dst + c, t.x);
-        if (c + 1 < keep) atomicAdd(dst + c + 1, t.y);
-        if (c + 2 < keep) atomicAdd(dst + c + 2, t.z);
-        if (c + 3 < keep) atomicAdd(dst + c + 3, t.w);
+      for (int w = 1; w < LN_WARPS; ++w) {
+        const float4 u = red[w][q];
+        t.x += u.x, t.y += u.y, t.z += u.z, t.w += u.w;
       }
-      __syncthreads();
+      const int c = q * 4;
+      if (c < keep) atomicAdd(dst + c, t.x);
+      if (c + 1 < keep) atomicAdd(dst + c + 1, t.y);
+      if (c + 2 < keep) atomicAdd(dst + c + 2, t.z);
+      if (c + 3 < keep) atomicAdd(dst + c + 3, t.w);
     }
   }
 }

@@ -80,6 +80,15 @@ __global__ void col2im_kernel(const T* __restrict__ dcol, long ldc, const T* __r
     const int ix = (int)(pix % W), iy = (int)((pix / W) % H), b = (int)(pix / ((long)W * H));
     const long off = (long)b * batch_pitch + ((long)iy * W + ix) * pix_pitch + c;
     float4 acc = add != nullptr ? ld4(add + off) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k == s && p == 0) {   // non-overlapping patches (conv_proj): exactly one tap per pixel, a pure permutation
+      const int oy = iy / k, ox = ix / k;
+      if (oy < Ho && ox < Wo) {
+        const float4 v = ld4(dcol + (((long)b * Ho + oy) * Wo + ox) * ldc + (long)((iy - oy * k) * k + (ix - ox * k)) * C + c);
+        acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
+      }
+      st4(din + off, acc);
+      continue;
+    }
     for (int ky = 0; ky < k; ++ky) {
       const int ty = iy + p - ky;
       if (ty < 0 || ty % s != 0) continue;
