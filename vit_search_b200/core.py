@@ -149,6 +149,18 @@ def up8(n):
     return (n + 7) // 8 * 8
 
 
+def zeros_like_many(*tensors):
+    """Zero-initialised fp32 gradient buffers for several parameters from ONE allocation + ONE memset (each view 16-byte
+    aligned, as the TMA reduce-add of the weight-gradient GEMMs requires)."""
+    sizes = [(t.numel() + 3) // 4 * 4 for t in tensors]
+    flat = torch.zeros(sum(sizes), device=tensors[0].device, dtype=torch.float32)
+    out, off = [], 0
+    for t, n in zip(tensors, sizes):
+        out.append(flat[off:off + t.numel()].view(t.shape))
+        off += n
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ segments
 class Seg:
     """A run of consecutive samples sharing one sub-architecture in this layer."""
@@ -260,9 +272,7 @@ def attn_half_backward(meta, g_out, saved, x, ln_w, ln_b, qkv_w, qkv_b, proj_w, 
     d_o = torch.empty(M, HD, device=dev, dtype=T)
     dqkv = torch.empty(M, 3 * HD, device=dev, dtype=T)
     dxn = torch.empty(M, C, device=dev, dtype=T) if meta.pre_norm else None
-    d_lnw, d_lnb = torch.zeros_like(ln_w), torch.zeros_like(ln_b)
-    d_qw, d_qb = torch.zeros_like(qkv_w), torch.zeros_like(qkv_b)
-    d_pw, d_pb = torch.zeros_like(proj_w), torch.zeros_like(proj_b)
+    d_lnw, d_lnb, d_qw, d_qb, d_pw, d_pb = zeros_like_many(ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b)
     wq, wp = weights.get(qkv_w), weights.get(proj_w)
     acts = _ActOperands()
     scale = D ** -0.5
@@ -355,9 +365,7 @@ def mlp_half_backward(meta, g_out, saved, x, ln_w, ln_b, fc1_w, fc1_b, fc2_w, fc
     df = torch.empty(M, C, device=dev, dtype=T)
     du = torch.empty(M, F, device=dev, dtype=T)
     dxn = torch.empty(M, C, device=dev, dtype=T) if meta.pre_norm else None
-    d_lnw, d_lnb = torch.zeros_like(ln_w), torch.zeros_like(ln_b)
-    d_w1, d_b1 = torch.zeros_like(fc1_w), torch.zeros_like(fc1_b)
-    d_w2, d_b2 = torch.zeros_like(fc2_w), torch.zeros_like(fc2_b)
+    d_lnw, d_lnb, d_w1, d_b1, d_w2, d_b2 = zeros_like_many(ln_w, ln_b, fc1_w, fc1_b, fc2_w, fc2_b)
     w1, w2 = weights.get(fc1_w), weights.get(fc2_w)
     acts = _ActOperands()
     for s in meta.segs:

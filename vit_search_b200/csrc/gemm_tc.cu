@@ -25,13 +25,16 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 2;              // x 3 co-resident CTAs per SM = 6 operand stages in flight per SM
 constexpr int STAGE_A = BM * BK * 2;
 constexpr int STAGE_B = BN * BK * 2;
-constexpr int TMEM_COLS = 128;
+constexpr int STAGE_BYTES = STAGE_A + STAGE_B;
+constexpr int TMEM_COLS = 256;          // two 128-column fp32 accumulators (double buffered across tiles)
 constexpr int EPI_WARPS = 8;            // two warps per TMEM lane quarter, each owning half of the tile's columns
-constexpr int GEMM_THREADS = 64 + EPI_WARPS * 32;
-constexpr int SMEM_BYTES = STAGES * (STAGE_A + STAGE_B) + 1024 /*align*/ + 128 /*barriers, tmem slot*/ + 512 /*bias tile*/;
+constexpr int EPI0 = 3;                 // warp 0 TMA producer, warp 1 MMA issuer, warp 2 store/aux warp, warps 3.. epilogue
+constexpr int GEMM_THREADS = (EPI0 + EPI_WARPS) * 32;
+constexpr int MAX_STAGES = 5;
+constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int SMEM_MISC = 1024 /*align*/ + 256 /*barriers, tmem slot*/ + 1024 /*two bias tiles*/;
 
 constexpr int MAX_TERMS = 6;
 struct TmapPack {
@@ -120,36 +123,63 @@ __device__ __forceinline__ void stage_read32<bf16>(const uint8_t* tile, int row,
   }
 }
 
+// Per-instantiation shared-memory plan: NBUF staging tiles (epilogue output / aux input), the rest is the operand ring.
+template <int EPI, typename OutT> struct Plan {
+  static constexpr int TILE_BYTES = BM * BN * (int)sizeof(OutT) * (EPI == VSX_EPI_GELU ? 2 : 1);
+  static constexpr int NBUF = (2 * TILE_BYTES + 2 * STAGE_BYTES + SMEM_MISC <= SMEM_LIMIT) ? 2 : 1;
+  static constexpr int ROOM = (SMEM_LIMIT - SMEM_MISC - NBUF * TILE_BYTES) / STAGE_BYTES;
+  static constexpr int STAGES = ROOM > MAX_STAGES ? MAX_STAGES : ROOM;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + NBUF * TILE_BYTES + SMEM_MISC;
+  static_assert(STAGES >= 2, "operand ring too small");
+};
+
+// Persistent, warp-specialised GEMM.  Each CTA (one per SM) walks tiles t = blockIdx.x, blockIdx.x + gridDim.x, ... with
+// n fastest (CTAs running at the same time share A rows in L2).  Four roles run as independent pipelines over that list:
+//   warp 0   producer : TMA operand loads into the ring, running ahead across tile boundaries
+//   warp 1   MMA      : tcgen05.mma into TMEM accumulator (tile & 1); tcgen05.commit frees ring slots / publishes the accumulator
+//   warp 2   store    : per tile, makes a staging buffer available (TMA-loading the aux tile into it when the epilogue needs one),
+//                       later TMA-stores / reduce-adds the staged result; staging is double buffered
+//   warps 3+ epilogue : TMEM -> registers -> fused math -> swizzled staging tile
+// so the loads of tile i+1, the MMAs of tile i+1 and the stores of tile i-1 overlap the epilogue of tile i.
 template <int EPI, typename OutT>
-__global__ void __launch_bounds__(GEMM_THREADS, 3) gemm_tc_kernel(const __grid_constant__ TmapPack maps, const GemmArgs g) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TmapPack maps, const GemmArgs g) {
+  using P = Plan<EPI, OutT>;
+  constexpr int STAGES = P::STAGES, NBUF = P::NBUF;
+  constexpr bool AUX = (EPI == VSX_EPI_RESIDUAL || EPI == VSX_EPI_GELUGRAD);
+  constexpr int BOXC = 128 / (int)sizeof(OutT);     // columns per 128-byte box row
+  constexpr int NBOX = BN / BOXC;                   // boxes per output tile
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;   // 128B-swizzle atoms need 1024-byte alignment
+  const uint32_t base = (raw + 1023u) & ~1023u;     // 128B-swizzle atoms need 1024-byte alignment
   uint8_t* smem = smem_raw + (base - raw);
-  const uint32_t sA = base, sB = base + STAGES * STAGE_A;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * (STAGE_A + STAGE_B));
-  const uint32_t bar0 = base + STAGES * (STAGE_A + STAGE_B);
-  // bars: [0,S) full, [S,2S) empty, [2S] accumulator ready, [2S+1] aux tile landed; then the TMEM base slot and the bias tile
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2);
-  float* bias_s = reinterpret_cast<float*>(bars + 2 * STAGES + 4);
+  const uint32_t ring = base, stg = base + STAGES * STAGE_BYTES;
+  uint8_t* stg_g = smem + STAGES * STAGE_BYTES;
+  const uint32_t bar0 = stg + NBUF * P::TILE_BYTES;
+  uint8_t* misc = stg_g + NBUF * P::TILE_BYTES;
+  // barriers (8 bytes each): full[S], empty[S], acc_full[2], acc_empty[2], ready[2] (staging writable / aux landed), staged[2]
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
-  auto empty_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
-  const uint32_t acc_bar = bar0 + 8u * (2 * STAGES);
-  const uint32_t aux_bar = bar0 + 8u * (2 * STAGES + 1);
+  auto empty_bar = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+  auto acc_full = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + b); };
+  auto acc_empty = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + 2 + b); };
+  auto ready_bar = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + 4 + b); };
+  auto staged_bar = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + 6 + b); };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (2 * MAX_STAGES + 8));
+  float* bias_s = reinterpret_cast<float*>(misc + 256);   // [2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.n_out + BN - 1) / BN;
+  const int splits = (EPI == VSX_EPI_ATOMIC) ? g.split_k : 1;
+  const int total = tiles_m * tiles_n * splits;
+  const int kb_per = (g.num_kb + splits - 1) / splits;
 
-  int kb_begin = 0, kb_end = g.num_kb;
-  if (EPI == VSX_EPI_ATOMIC) {
-    const int per = (g.num_kb + g.split_k - 1) / g.split_k;
-    kb_begin = blockIdx.z * per;
-    kb_end = min(g.num_kb, kb_begin + per);
-    if (kb_begin >= kb_end) return;   // uniform for the whole CTA
-  }
-  const int nkb = kb_end - kb_begin;
-  const int iters = nkb * g.terms;
-  const bool has_mma = (n0 < g.N) && iters > 0;
+  // tile t -> (m0, n0, k-block range); identical arithmetic in every role
+  auto tile_info = [&](int t, int& m0, int& n0, int& kb0, int& nkb) {
+    const int ni = t % tiles_n, mi = (t / tiles_n) % tiles_m, z = t / (tiles_n * tiles_m);
+    m0 = mi * BM, n0 = ni * BN;
+    kb0 = z * kb_per;
+    const int kb1 = min(g.num_kb, kb0 + kb_per);
+    nkb = (n0 < g.N && kb1 > kb0) ? kb1 - kb0 : 0;
+  };
 
   if (warp == 0 && lane == 0) {
     for (int t = 0; t < g.terms; ++t) {
@@ -164,8 +194,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 3) gemm_tc_kernel(const __grid_c
         mbar_init(full_bar(s), 1);
         mbar_init(empty_bar(s), 1);
       }
-      mbar_init(acc_bar, 1);
-      mbar_init(aux_bar, 1);
+      for (int b = 0; b < 2; ++b) {
+        mbar_init(acc_full(b), 1);
+        mbar_init(acc_empty(b), EPI_WARPS);
+        mbar_init(ready_bar(b), 1);
+        mbar_init(staged_bar(b), EPI_WARPS);
+      }
       fence_mbar_init();
     }
     __syncwarp();
@@ -176,145 +210,208 @@ __global__ void __launch_bounds__(GEMM_THREADS, 3) gemm_tc_kernel(const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (has_mma && warp == 0 && lane == 0) {
-    // ---------------- TMA producer ----------------
-    for (int it = 0; it < iters; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-      mbar_wait(empty_bar(s), ph ^ 1u);
-      const int term = it / nkb, k0 = (kb_begin + it % nkb) * BK;
-      const uint32_t dA = sA + s * STAGE_A, dB = sB + s * STAGE_B, fb = full_bar(s);
-      mbar_expect_tx(fb, STAGE_A + STAGE_B);
-      if (!g.a_mn) {
-        tma_load_2d(dA, &maps.a[term], fb, k0, m0);
-      } else {
-        tma_load_2d(dA, &maps.a[term], fb, m0, k0);
-        tma_load_2d(dA + BK * 128, &maps.a[term], fb, m0 + 64, k0);
-      }
-      if (!g.b_mn) {
-        tma_load_2d(dB, &maps.b[term], fb, k0, n0);
-      } else {
-        tma_load_2d(dB, &maps.b[term], fb, n0, k0);
-        tma_load_2d(dB + BK * 128, &maps.b[term], fb, n0 + 64, k0);
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------- TMA producer ----------------
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        int m0, n0, kb0, nkb;
+        tile_info(t, m0, n0, kb0, nkb);
+        for (int i = 0; i < nkb * g.terms; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const int term = i / nkb, k0 = (kb0 + i % nkb) * BK;
+          const uint32_t dA = ring + s * STAGE_BYTES, dB = dA + STAGE_A, fb = full_bar(s);
+          mbar_expect_tx(fb, STAGE_BYTES);
+          if (!g.a_mn) {
+            tma_load_2d(dA, &maps.a[term], fb, k0, m0);
+          } else {
+            tma_load_2d(dA, &maps.a[term], fb, m0, k0);
+            tma_load_2d(dA + BK * 128, &maps.a[term], fb, m0 + 64, k0);
+          }
+          if (!g.b_mn) {
+            tma_load_2d(dB, &maps.b[term], fb, k0, n0);
+          } else {
+            tma_load_2d(dB, &maps.b[term], fb, n0, k0);
+            tma_load_2d(dB + BK * 128, &maps.b[term], fb, n0 + 64, k0);
+          }
+        }
       }
     }
-  } else if (has_mma && warp == 1 && lane == 0) {
-    // ---------------- MMA issuer ----------------
-    const uint32_t idesc = make_idesc(g.a_mn != 0, g.b_mn != 0);
-    const uint32_t a_step = g.a_mn ? (UMMA_K * 128) : (UMMA_K * 2);   // bytes per 16-wide k step
-    const uint32_t b_step = g.b_mn ? (UMMA_K * 128) : (UMMA_K * 2);
-    for (int it = 0; it < iters; ++it) {
-      const int s = it % STAGES;
-      const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-      mbar_wait(full_bar(s), ph);
-      tc_fence_after();
-      const uint32_t aA = sA + s * STAGE_A, aB = sB + s * STAGE_B;
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------- MMA issuer ----------------
+      const uint32_t idesc = make_idesc(g.a_mn != 0, g.b_mn != 0);
+      const uint32_t a_step = g.a_mn ? (UMMA_K * 128) : (UMMA_K * 2);   // bytes per 16-wide k step
+      const uint32_t b_step = g.b_mn ? (UMMA_K * 128) : (UMMA_K * 2);
+      int it = 0, uses[2] = {0, 0}, j = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+        int m0, n0, kb0, nkb;
+        tile_info(t, m0, n0, kb0, nkb);
+        if (nkb == 0) continue;                       // epilogue-only tile: the accumulator is not involved
+        const int ab = j & 1;
+        mbar_wait(acc_empty(ab), ((uint32_t)uses[ab] & 1u) ^ 1u);   // epilogue has drained this accumulator
+        ++uses[ab];
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)ab * BN;
+        for (int i = 0; i < nkb * g.terms; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t aA = ring + s * STAGE_BYTES, aB = aA + STAGE_A;
 #pragma unroll
-      for (int k = 0; k < BK / UMMA_K; ++k) {
-        umma_bf16(tmem_base, make_smem_desc(aA + k * a_step, g.a_mn != 0), make_smem_desc(aB + k * b_step, g.b_mn != 0),
-                  idesc, (it | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            umma_bf16(acc, make_smem_desc(aA + k * a_step, g.a_mn != 0), make_smem_desc(aB + k * b_step, g.b_mn != 0), idesc,
+                      (i | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar(s));   // slot reusable once these MMAs have read it
+        }
+        umma_commit(acc_full(ab));     // accumulator complete
       }
-      umma_commit(empty_bar(s));   // slot reusable once these MMAs have read it
     }
-    umma_commit(acc_bar);          // accumulator complete
-  } else if (warp >= 2) {
-    // ---------------- epilogue: TMEM -> registers -> fused math -> swizzled smem tile -> TMA store / reduce-add ----------------
-    constexpr int BOXC = 128 / (int)sizeof(OutT);     // columns per 128-byte box row
+  } else if (warp == 2) {
+    if (lane == 0) {
+      // ---------------- store / aux warp ----------------
+      // announce(j): staging buffer j % NBUF is free (its previous store has been read out) -> TMA-load the aux tile into it
+      // (completing `ready`), or just arrive on `ready` when the epilogue needs no aux tile.
+      auto announce = [&](int t, int sb) {
+        int m0, n0, kb0, nkb;
+        tile_info(t, m0, n0, kb0, nkb);
+        const int ncols = min(BN, g.n_out - n0);
+        const int nbox = (ncols + BOXC - 1) / BOXC;
+        if (AUX) {
+          mbar_expect_tx(ready_bar(sb), (uint32_t)nbox * BOX_BYTES);
+          for (int bx = 0; bx < nbox; ++bx) tma_load_2d(stg + sb * P::TILE_BYTES + bx * BOX_BYTES, &maps.aux, ready_bar(sb), n0 + bx * BOXC, m0);
+        } else {
+          mbar_arrive(ready_bar(sb));
+        }
+      };
+      int j = 0;
+      if ((int)blockIdx.x < total) announce(blockIdx.x, 0);
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+        const int sb = j % NBUF;
+        const int tn = t + gridDim.x;
+        if (NBUF == 2 && tn < total) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // store of tile j-1 (same buffer as j+1) has been read
+          announce(tn, (j + 1) % NBUF);
+        }
+        int m0, n0, kb0, nkb;
+        tile_info(t, m0, n0, kb0, nkb);
+        const int ncols = min(BN, g.n_out - n0);
+        const int nbox = (ncols + BOXC - 1) / BOXC;
+        mbar_wait(staged_bar(sb), (uint32_t)(j / NBUF) & 1u);                // epilogue has staged tile j
+        const uint32_t src = stg + sb * P::TILE_BYTES;
+        for (int bx = 0; bx < nbox; ++bx) {
+          if (EPI == VSX_EPI_ATOMIC) {
+            tma_reduce_add_2d(&maps.out, src + bx * BOX_BYTES, n0 + bx * BOXC, m0);
+          } else {
+            tma_store_2d(&maps.out, src + bx * BOX_BYTES, n0 + bx * BOXC, m0);
+            if (EPI == VSX_EPI_GELU) tma_store_2d(&maps.out2, src + (NBOX + bx) * BOX_BYTES, n0 + bx * BOXC, m0);
+          }
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (NBUF == 1 && tn < total) {
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          announce(tn, 0);
+        }
+      }
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");        // shared memory must outlive the last store
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> fused math -> swizzled staging tile ----------------
+    const int ew = warp - EPI0;                       // 0..7
     const int q = warp & 3;                           // TMEM lane quarter this warp may access
     const int row = q * 32 + lane;                    // tile row == TMEM lane
-    const int et = (int)threadIdx.x - 64;             // 0..255 among the epilogue threads
-    const int chalf = (warp - 2) >> 2;                // which 64-column half of the tile this warp handles
-    const int m = m0 + row;
-    const int ncols = min(BN, g.n_out - n0);          // columns of this tile that exist in the output
-    if (et < BN) bias_s[et] = (g.bias != nullptr && n0 + et < g.N) ? __ldg(g.bias + n0 + et) : 0.f;
-    if (has_mma) {
-      mbar_wait(acc_bar, 0);                          // all MMAs done => the operand ring is free: reuse it as the staging tile
-      tc_fence_after();
+    const int et = ew * 32 + lane;                    // 0..255 among the epilogue threads
+    // the two warps that share a lane quarter split the columns
+    int chalf;
+    {
+      // warps (EPI0 + i) and (EPI0 + i + 4) have the same (warp & 3): the first takes columns [0,64), the second [64,128)
+      chalf = ew >> 2;
     }
-    uint8_t* tile = smem;                             // generic view of the (now idle) stage memory
-    // GELU writes two tiles (pre-activation and activation): side by side for bf16 (2 x 32 KB); for fp32 (2 x 64 KB > ring)
-    // the activation tile is produced in a second pass over the accumulator after the first tile has left.
-    constexpr bool TWO_PASS = (EPI == VSX_EPI_GELU) && sizeof(OutT) == 4;
-    uint8_t* tile2 = TWO_PASS ? smem : smem + (BN / BOXC) * BOX_BYTES;
-    const int nbox = (ncols + BOXC - 1) / BOXC;
-    if (EPI == VSX_EPI_RESIDUAL || EPI == VSX_EPI_GELUGRAD) {
-      if (et == 0) {                                  // aux tile (residual stream / pre-activation) by TMA, OOB zero-filled
-        mbar_expect_tx(aux_bar, (uint32_t)nbox * BOX_BYTES);
-        for (int bx = 0; bx < nbox; ++bx) tma_load_2d(base + bx * BOX_BYTES, &maps.aux, aux_bar, n0 + bx * BOXC, m0);
-      }
-    }
-    named_bar_sync(1, EPI_WARPS * 32);                           // bias tile visible
-    if (EPI == VSX_EPI_RESIDUAL || EPI == VSX_EPI_GELUGRAD) mbar_wait(aux_bar, 0);
-    float scale = 1.0f;
-    if (EPI == VSX_EPI_RESIDUAL && g.row_scale != nullptr && m < g.M) scale = __ldg(g.row_scale + m / g.rows_per_sample);
     const int lim = g.n_keep < g.N ? g.n_keep : g.N;
-    for (int pass = 0; pass < (TWO_PASS ? 2 : 1); ++pass) {
+    int uses[2] = {0, 0}, j = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+      int m0, n0, kb0, nkb;
+      tile_info(t, m0, n0, kb0, nkb);
+      const bool has_mma = nkb > 0;
+      const int ab = j & 1, sb = j % NBUF;
+      const int m = m0 + row;
+      const int ncols = min(BN, g.n_out - n0);
+      float* bs = bias_s + ab * BN;
+      if (et < BN) bs[et] = (g.bias != nullptr && n0 + et < g.N) ? __ldg(g.bias + n0 + et) : 0.f;
+      mbar_wait(ready_bar(sb), (uint32_t)(j / NBUF) & 1u);        // staging buffer writable (and aux tile landed)
+      named_bar_sync(1, EPI_WARPS * 32);                           // bias tile visible
+      if (has_mma) {
+        mbar_wait(acc_full(ab), (uint32_t)uses[ab] & 1u);
+        ++uses[ab];
+        tc_fence_after();
+      }
+      uint8_t* tile = stg_g + sb * P::TILE_BYTES;
+      uint8_t* tile2 = tile + NBOX * BOX_BYTES;
+      float scale = 1.0f;
+      if (EPI == VSX_EPI_RESIDUAL && g.row_scale != nullptr && m < g.M) scale = __ldg(g.row_scale + m / g.rows_per_sample);
+      const uint32_t acc = tmem_base + (uint32_t)ab * BN + ((uint32_t)(q * 32) << 16);
       for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
         if (c >= ncols) break;
         float v[32];
         if (has_mma) {
-          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+          tmem_ld32(acc + (uint32_t)c, v);
           tmem_ld_wait();
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+          for (int jj = 0; jj < 32; ++jj) v[jj] = 0.f;
         }
         const int n = n0 + c;
         if (EPI == VSX_EPI_ATOMIC) {
           stage_write32<float>(tile, row, c, v);
         } else if (EPI == VSX_EPI_STORE) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = (n + j < g.N) ? v[j] + bias_s[c + j] : 0.f;
+          for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] + bs[c + jj] : 0.f;
           stage_write32<OutT>(tile, row, c, v);
         } else if (EPI == VSX_EPI_GELU) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = (n + j < g.N) ? v[j] + bias_s[c + j] : 0.f;
-          if (!TWO_PASS || pass == 0) stage_write32<OutT>(tile, row, c, v);
-          if (!TWO_PASS || pass == 1) {
+          for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] + bs[c + jj] : 0.f;
+          stage_write32<OutT>(tile, row, c, v);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = gelu_f(v[j]);   // gelu(0) = 0 keeps the zero fill
-            stage_write32<OutT>(tile2, row, c, v);
-          }
+          for (int jj = 0; jj < 32; ++jj) v[jj] = gelu_f(v[jj]);   // gelu(0) = 0 keeps the zero fill
+          stage_write32<OutT>(tile2, row, c, v);
         } else if (EPI == VSX_EPI_RESIDUAL) {
           float r[32];
           stage_read32<float>(tile, row, c, r);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] += (n + j < lim) ? scale * (v[j] + bias_s[c + j]) : 0.f;
+          for (int jj = 0; jj < 32; ++jj) r[jj] += (n + jj < lim) ? scale * (v[jj] + bs[c + jj]) : 0.f;
           stage_write32<float>(tile, row, c, r);
         } else if (EPI == VSX_EPI_GELUGRAD) {
           float u[32];
           stage_read32<OutT>(tile, row, c, u);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = (n + j < g.N) ? v[j] * gelu_grad_f(u[j]) : 0.f;
+          for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] * gelu_grad_f(u[jj]) : 0.f;
           stage_write32<OutT>(tile, row, c, v);
         }
       }
-      fence_proxy_async();                            // generic-proxy smem writes -> visible to the TMA (async proxy)
-      named_bar_sync(1, EPI_WARPS * 32);
-      if ((EPI == VSX_EPI_GELUGRAD || EPI == VSX_EPI_STORE) && g.colsum != nullptr && et >= 128 && n0 + (et - 128) < g.N) {
+      if (has_mma) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty(ab));                 // this warp's TMEM reads of the accumulator are done
+      }
+      if ((EPI == VSX_EPI_GELUGRAD || EPI == VSX_EPI_STORE) && g.colsum != nullptr) {
         // bias gradient fused into the dgrad epilogue: column sums of the staged (already rounded) tile over its valid rows
-        const int cc = et - 128, rmax = min(BM, g.M - m0);
-        const uint8_t* colp = tile + (cc / BOXC) * BOX_BYTES + (cc % (16 / (int)sizeof(OutT))) * (int)sizeof(OutT);
-        const int chunk = (cc % BOXC) / (16 / (int)sizeof(OutT));
-        float acc = 0.f;
-        for (int r = 0; r < rmax; ++r) acc += Store<OutT>::ld(reinterpret_cast<const OutT*>(colp + box_off(r, chunk)));
-        atomicAdd(g.colsum + n0 + cc, acc);
-      }
-      if (et == 0) {
-        for (int bx = 0; bx < nbox; ++bx) {
-          if (EPI == VSX_EPI_ATOMIC) {
-            tma_reduce_add_2d(&maps.out, base + bx * BOX_BYTES, n0 + bx * BOXC, m0);
-          } else if (EPI == VSX_EPI_GELU) {
-            if (!TWO_PASS || pass == 0) tma_store_2d(&maps.out, base + bx * BOX_BYTES, n0 + bx * BOXC, m0);
-            if (!TWO_PASS) tma_store_2d(&maps.out2, base + (BN / BOXC + bx) * BOX_BYTES, n0 + bx * BOXC, m0);
-            if (TWO_PASS && pass == 1) tma_store_2d(&maps.out2, base + bx * BOX_BYTES, n0 + bx * BOXC, m0);
-          } else {
-            tma_store_2d(&maps.out, base + bx * BOX_BYTES, n0 + bx * BOXC, m0);
-          }
+        named_bar_sync(1, EPI_WARPS * 32);
+        if (et >= 128 && n0 + (et - 128) < g.N) {
+          const int cc = et - 128, rmax = min(BM, g.M - m0);
+          const uint8_t* colp = tile + (cc / BOXC) * BOX_BYTES + (cc % (16 / (int)sizeof(OutT))) * (int)sizeof(OutT);
+          const int chunk = (cc % BOXC) / (16 / (int)sizeof(OutT));
+          float a2 = 0.f;
+          for (int r = 0; r < rmax; ++r) a2 += Store<OutT>::ld(reinterpret_cast<const OutT*>(colp + box_off(r, chunk)));
+          atomicAdd(g.colsum + n0 + cc, a2);
         }
-        tma_store_commit_wait();                      // shared memory must stay valid until the TMA has read it
       }
-      if (TWO_PASS) named_bar_sync(1, EPI_WARPS * 32);           // the staging tile may be overwritten by the second pass
+      fence_proxy_async();                                         // generic-proxy smem writes -> visible to the TMA (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(staged_bar(sb));                  // 8 warps -> the store warp may ship the tile
     }
   }
   tc_fence_before();
@@ -323,17 +420,19 @@ __global__ void __launch_bounds__(GEMM_THREADS, 3) gemm_tc_kernel(const __grid_c
 }
 
 template <int EPI, typename OutT>
-int launch(const TmapPack& maps, const GemmArgs& g, dim3 grid, cudaStream_t st) {
+int launch(const TmapPack& maps, const GemmArgs& g, int total_tiles, cudaStream_t st) {
+  using P = Plan<EPI, OutT>;
   static bool configured = false;   // benign race: attribute set is idempotent
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM);
     if (e != cudaSuccess) {
-      set_error("vsx_gemm: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      set_error("vsx_gemm: cudaFuncSetAttribute(%d) failed: %s", P::SMEM, cudaGetErrorString(e));
       return VSX_ERR_CUDA;
     }
     configured = true;
   }
-  gemm_tc_kernel<EPI, OutT><<<grid, GEMM_THREADS, SMEM_BYTES, st>>>(maps, g);
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  gemm_tc_kernel<EPI, OutT><<<grid, GEMM_THREADS, P::SMEM, st>>>(maps, g);
   return check_launch("vsx_gemm");
 }
 
@@ -377,7 +476,7 @@ extern "C" int vsx_gemm(const vsx_gemm_desc* d, void* stream) {
     g.N = 0;   // nothing to contract: epilogue-only tiles
     memset(&maps, 0, sizeof(maps));
   }
-  dim3 grid(ceil_div(d->M, BM), ceil_div(d->n_out, BN), 1);
+  int tiles = ceil_div(d->M, BM) * ceil_div(d->n_out, BN);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   {  // epilogue tensor maps: [M rows, n_out columns], boxes of 128 rows x 128 bytes
     const int odt = f32 ? VSX_F32 : VSX_BF16;
@@ -402,22 +501,22 @@ extern "C" int vsx_gemm(const vsx_gemm_desc* d, void* stream) {
   switch (d->epilogue) {
     case VSX_EPI_STORE:
       VSX_REQUIRE(d->colsum == nullptr || d->bias == nullptr, "vsx_gemm: STORE with colsum must not add a bias");
-      return f32 ? launch<VSX_EPI_STORE, float>(maps, g, grid, st) : launch<VSX_EPI_STORE, bf16>(maps, g, grid, st);
+      return f32 ? launch<VSX_EPI_STORE, float>(maps, g, tiles, st) : launch<VSX_EPI_STORE, bf16>(maps, g, tiles, st);
     case VSX_EPI_GELU:
-      return f32 ? launch<VSX_EPI_GELU, float>(maps, g, grid, st) : launch<VSX_EPI_GELU, bf16>(maps, g, grid, st);
+      return f32 ? launch<VSX_EPI_GELU, float>(maps, g, tiles, st) : launch<VSX_EPI_GELU, bf16>(maps, g, tiles, st);
     case VSX_EPI_RESIDUAL:
       VSX_REQUIRE(f32 && d->aux != nullptr, "vsx_gemm: RESIDUAL epilogue is fp32 and needs aux");
-      return launch<VSX_EPI_RESIDUAL, float>(maps, g, grid, st);
+      return launch<VSX_EPI_RESIDUAL, float>(maps, g, tiles, st);
     case VSX_EPI_GELUGRAD:
       VSX_REQUIRE(d->aux != nullptr, "vsx_gemm: GELUGRAD epilogue needs aux (pre-activation)");
-      return f32 ? launch<VSX_EPI_GELUGRAD, float>(maps, g, grid, st) : launch<VSX_EPI_GELUGRAD, bf16>(maps, g, grid, st);
+      return f32 ? launch<VSX_EPI_GELUGRAD, float>(maps, g, tiles, st) : launch<VSX_EPI_GELUGRAD, bf16>(maps, g, tiles, st);
     case VSX_EPI_ATOMIC:
       VSX_REQUIRE(f32, "vsx_gemm: ATOMIC epilogue accumulates into fp32");
       if (g.N == 0) return VSX_OK;
-      grid.y = ceil_div(d->N, BN);
-      grid.z = g.split_k = (g.split_k > g.num_kb ? (g.num_kb > 0 ? g.num_kb : 1) : g.split_k);
+      g.split_k = (g.split_k > g.num_kb ? (g.num_kb > 0 ? g.num_kb : 1) : g.split_k);
       g.n_out = d->N;
-      return launch<VSX_EPI_ATOMIC, float>(maps, g, grid, st);
+      tiles = ceil_div(d->M, BM) * ceil_div(d->N, BN) * g.split_k;
+      return launch<VSX_EPI_ATOMIC, float>(maps, g, tiles, st);
     default:
       set_error("vsx_gemm: unknown epilogue %d", d->epilogue);
       return VSX_ERR_ARG;

@@ -151,11 +151,9 @@ class _SRFn(torch.autograd.Function):
         dA = torch.empty(B * g2 * g2, 9 * C1, device=dev, dtype=T)
         dxn = torch.empty(B * N1, C1, device=dev, dtype=T)
         g_in = torch.empty_like(x)
-        d_lnw, d_lnb = torch.zeros_like(ln_w), torch.zeros_like(ln_w)
-        d_cw = torch.zeros(C2, 9 * C1, device=dev)
-        d_cb, d_tb = torch.zeros(C2, device=dev), torch.zeros(C2, device=dev)
-        d_tw = torch.zeros_like(tok_w)
-        dpos = torch.zeros(1, g2 * g2, C2, device=dev)
+        d_lnw, d_lnb, d_cw, d_cb, d_tb, d_tw, dpos = core.zeros_like_many(
+            ln_w, ln_w, torch.empty(C2, 9 * C1, device='meta'), torch.empty(C2, device='meta'), torch.empty(C2, device='meta'), tok_w,
+            torch.empty(1, g2 * g2, C2, device='meta'))
         wc, wt = weights.get(conv_w, 'ohwi'), weights.get(tok_w)
         acts = _ActOperands()
         for b0, b1, k1, k2 in segs:
@@ -290,9 +288,8 @@ class _HeadFn(torch.autograd.Function):
         gcls = gcls.contiguous()
         dc = torch.empty(B, K, device=dev, dtype=T)
         ops.scale_mask_cast(gcls, K, None, 1, K, dc, K, B, K)
-        d_cw, d_cb = torch.zeros_like(cw), torch.zeros(K, device=dev)
-        d_pw, d_pb = torch.zeros_like(pw), torch.zeros(K, device=dev)
-        d_lnw, d_lnb = torch.zeros_like(ln_w), torch.zeros_like(ln_w)
+        d_cw, d_cb, d_pw, d_pb, d_lnw, d_lnb = core.zeros_like_many(cw, torch.empty(K, device='meta'), pw, torch.empty(K, device='meta'),
+                                                                    ln_w, ln_w)
         ops.colsum(dc, K, B, K, d_cb)
         dtokf = torch.empty(B, C, device=dev, dtype=T)
         g_in = torch.zeros_like(x) if not with_patches else torch.empty_like(x)
