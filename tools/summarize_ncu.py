@@ -28,8 +28,10 @@ def launches(path, out, steps=2):
     per = [(int(r['ID']), short(r['Kernel Name']), float(r['Metric Value'].replace(',', ''))) for r in rows if r['Metric Name'] == 'gpu__time_duration.sum']
     unit = [r['Metric Unit'] for r in rows if r['Metric Name'] == 'gpu__time_duration.sum'][0]
     scale = {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 'nsecond': 1e-3, 'usecond': 1.0, 'msecond': 1e3}.get(unit, 1.0)
-    half = len(per) // steps
-    second = per[-half:]          # the last step (the first one includes one-off operand casts / allocator warm-up)
+    # the last step = the launches after the previous step's adamw_kernel up to and including the last adamw_kernel (the first
+    # step also holds one-off work: optimizer-state zero fills, operand casts, allocator warm-up)
+    ends = [i for i, p in enumerate(per) if p[1].startswith('adamw_kernel')]
+    second = per[ends[-2] + 1:ends[-1] + 1] if len(ends) >= 2 else per[-(len(per) // steps):]
     agg = collections.OrderedDict()
     for _, k, v in second:
         a = agg.setdefault(k, [0, 0.0])
@@ -84,7 +86,11 @@ def gemm_dram(path, out, steps=2):
 
 
 if __name__ == '__main__':
+    import os
     tag = sys.argv[1] if len(sys.argv) > 1 else 'r1'
-    agg, tot = launches('gpurun_out/launches_%s.csv' % tag, 'profiles/%s_launches.md' % tag)
-    per_launch = gemm_dram('gpurun_out/gemm_dram_%s.csv' % tag, 'profiles/%s_gemm_dram.md' % tag)
-    print('kernel time %.2f ms; gemm dram bytes per launch %.3e' % (tot / 1e3, per_launch))
+    if os.path.exists('gpurun_out/launches_%s.csv' % tag):
+        agg, tot = launches('gpurun_out/launches_%s.csv' % tag, 'profiles/%s_launches.md' % tag)
+        print('kernel time %.2f ms' % (tot / 1e3))
+    if os.path.exists('gpurun_out/gemm_dram_%s.csv' % tag):
+        per_launch = gemm_dram('gpurun_out/gemm_dram_%s.csv' % tag, 'profiles/%s_gemm_dram.md' % tag)
+        print('gemm dram bytes per launch %.3e' % per_launch)

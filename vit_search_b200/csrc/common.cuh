@@ -71,6 +71,20 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// Column-sum flush: colsum[c..c+3] += t for the columns below `keep`.  One 16-byte vector reduction (red.global.add.v4.f32,
+// sm_90+) instead of four scalar atomics: thousands of CTAs flush the same few hundred addresses, and the L2 atomic units
+// serialise per operation, so the op count -- not the bytes -- bounds the tail of these kernels.
+__device__ __forceinline__ void red_add4(float* p, float4 t, int c, int keep) {
+  if (c + 3 < keep && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(t.x), "f"(t.y), "f"(t.z), "f"(t.w) : "memory");
+  } else {
+    if (c < keep) atomicAdd(p, t.x);
+    if (c + 1 < keep) atomicAdd(p + 1, t.y);
+    if (c + 2 < keep) atomicAdd(p + 2, t.z);
+    if (c + 3 < keep) atomicAdd(p + 3, t.w);
+  }
+}
+
 // exact (erf) GELU and its derivative -- torch.nn.GELU default used by nets/supernet_blocks.py:17
 __device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float gelu_grad_f(float x) {
@@ -78,6 +92,39 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   const float pdf = 0.39894228040143268f * __expf(-0.5f * x * x);
   return cdf + x * pdf;
 }
+
+// Cheap variants for the bf16 training path (GEMM epilogues are CUDA-core / SFU bound at K <= 256): erfc by
+// Abramowitz-Stegun 7.1.26 (|abs err| < 4.3e-7 on gelu and gelu' in fp32, i.e. ~1e-4 of a bf16 ulp at 1.0) -- one
+// MUFU.RCP + one MUFU.EX2 + 8 FMA-pipe ops instead of erff's ~30; gelu' re-uses the same exponential.
+__device__ __forceinline__ float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float half_erfc_abs(float x, float& e) {   // 0.5*erfc(|x|/sqrt2); e = exp(-x^2/2)
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  e = __expf(-z * z);
+  float p = fmaf(t, 1.061405429f * 0.5f, -1.453152027f * 0.5f);
+  p = fmaf(t, p, 1.421413741f * 0.5f);
+  p = fmaf(t, p, -0.284496736f * 0.5f);
+  p = fmaf(t, p, 0.254829592f * 0.5f);
+  return p * t * e;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+  float e;
+  const float q = half_erfc_abs(x, e);
+  return x * (x >= 0.f ? 1.0f - q : q);
+}
+__device__ __forceinline__ float gelu_grad_fast(float x) {
+  float e;
+  const float q = half_erfc_abs(x, e);
+  return (x >= 0.f ? 1.0f - q : q) + x * 0.39894228040143268f * e;
+}
+template <typename OutT> __device__ __forceinline__ float gelu_sel(float x) { return gelu_fast(x); }
+template <> __device__ __forceinline__ float gelu_sel<float>(float x) { return gelu_f(x); }
+template <typename OutT> __device__ __forceinline__ float gelu_grad_sel(float x) { return gelu_grad_fast(x); }
+template <> __device__ __forceinline__ float gelu_grad_sel<float>(float x) { return gelu_grad_f(x); }
 
 // ---------------------------------------------------------------- PTX wrappers: mbarrier / TMA / tcgen05
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

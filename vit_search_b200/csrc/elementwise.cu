@@ -72,11 +72,7 @@ __global__ void __launch_bounds__(SMC_WARPS * 32) scale_mask_cast_kernel(const f
       const float4 u = red[w][q];
       t.x += u.x, t.y += u.y, t.z += u.z, t.w += u.w;
     }
-    const int c = q * 4;
-    if (c < n_keep) atomicAdd(colsum + c, t.x);
-    if (c + 1 < n_keep) atomicAdd(colsum + c + 1, t.y);
-    if (c + 2 < n_keep) atomicAdd(colsum + c + 2, t.z);
-    if (c + 3 < n_keep) atomicAdd(colsum + c + 3, t.w);
+    red_add4(colsum + q * 4, t, q * 4, n_keep);
   }
 }
 
@@ -134,7 +130,7 @@ template <typename T>
 static int smc_dispatch(const float* g, long ldg, const float* row_scale, int rps, int n_keep, void* out, long ldo, int rows, int cols,
                         float* colsum, cudaStream_t st) {
   const int nv = ceil_div(cols, 128);
-  const int need = ceil_div(rows, SMC_WARPS), cap = num_sms() * 8;
+  const int need = ceil_div(rows, SMC_WARPS), cap = num_sms() * (colsum != nullptr ? 4 : 8);
   const int grid = need < cap ? need : cap;
 #define VSX_SMC(NV)                                                                                                                 \
   case NV:                                                                                                                          \

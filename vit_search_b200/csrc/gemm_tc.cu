@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] + bs[c + jj] : 0.f;
           stage_write32<OutT>(tile, row, c, v);
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) v[jj] = gelu_f(v[jj]);   // gelu(0) = 0 keeps the zero fill
+          for (int jj = 0; jj < 32; ++jj) v[jj] = gelu_sel<OutT>(v[jj]);   // gelu(0) = 0 keeps the zero fill
           stage_write32<OutT>(tile2, row, c, v);
         } else if (EPI == VSX_EPI_RESIDUAL) {
           float r[32];
@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           float u[32];
           stage_read32<OutT>(tile, row, c, u);
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] * gelu_grad_f(u[jj]) : 0.f;
+          for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] * gelu_grad_sel<OutT>(u[jj]) : 0.f;
           stage_write32<OutT>(tile, row, c, v);
         }
       }
@@ -399,14 +399,23 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
       if ((EPI == VSX_EPI_GELUGRAD || EPI == VSX_EPI_STORE) && g.colsum != nullptr) {
         // bias gradient fused into the dgrad epilogue: column sums of the staged (already rounded) tile over its valid rows
+        // all 256 epilogue threads: thread (cc, half) sums column cc over 64 rows, 8 independent loads in flight
         named_bar_sync(1, EPI_WARPS * 32);
-        if (et >= 128 && n0 + (et - 128) < g.N) {
-          const int cc = et - 128, rmax = min(BM, g.M - m0);
+        const int cc = et & 127, rh = et >> 7;
+        if (n0 + cc < g.N) {
+          const int rbeg = rh * (BM / 2), rend = min(rbeg + BM / 2, g.M - m0);
           const uint8_t* colp = tile + (cc / BOXC) * BOX_BYTES + (cc % (16 / (int)sizeof(OutT))) * (int)sizeof(OutT);
           const int chunk = (cc % BOXC) / (16 / (int)sizeof(OutT));
-          float a2 = 0.f;
-          for (int r = 0; r < rmax; ++r) a2 += Store<OutT>::ld(reinterpret_cast<const OutT*>(colp + box_off(r, chunk)));
-          atomicAdd(g.colsum + n0 + cc, a2);
+          float part[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) part[i] = 0.f;
+          for (int r = rbeg; r < rend; r += 8) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (r + i < rend) part[i] += Store<OutT>::ld(reinterpret_cast<const OutT*>(colp + box_off(r + i, chunk)));
+          }
+          const float a2 = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
+          if (rend > rbeg) atomicAdd(g.colsum + n0 + cc, a2);
         }
       }
       fence_proxy_async();                                         // generic-proxy smem writes -> visible to the TMA (async proxy)

@@ -164,11 +164,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T* __restri
         const float4 u = red[w][q];
         t.x += u.x, t.y += u.y, t.z += u.z, t.w += u.w;
       }
-      const int c = q * 4;
-      if (c < keep) atomicAdd(dst + c, t.x);
-      if (c + 1 < keep) atomicAdd(dst + c + 1, t.y);
-      if (c + 2 < keep) atomicAdd(dst + c + 2, t.z);
-      if (c + 3 < keep) atomicAdd(dst + c + 3, t.w);
+      red_add4(dst + q * 4, t, q * 4, keep);
     }
   }
 }
@@ -204,7 +200,7 @@ int ln_bwd_dispatch(const void* dy, const void* dy2, long lddy, const float* x, 
                     const float* gamma, const float* g_in, float* g_out, long ldg, float* dgamma, float* dbeta, int rows, int C,
                     int keep, int rps, int split, cudaStream_t st) {
   const int nv = ceil_div(C, 128);
-  const int grid = ln_grid(rows, nv <= 2 ? 8 : 4);
+  const int grid = ln_grid(rows, 4);
 #define VSX_LN_B(NV)                                                                                                      \
   case NV:                                                                                                                \
     ln_bwd_kernel<NV, T><<<grid, LN_WARPS * 32, 0, st>>>((const T*)dy, (const T*)dy2, lddy, x, ldx, mean, rstd, gamma, g_in, \
