@@ -117,11 +117,15 @@ int vsx_gemm(const vsx_gemm_desc* d, void* stream);
  * (nets/supernet_blocks.py:103-112) and their autograd.  qkv: [batch*tokens, 3*heads*head_dim] with features
  * ordered (3, heads, head_dim) (:102); o: [batch*tokens, heads*head_dim]; lse: fp32 [batch, heads, tokens]
  * (log-sum-exp of the scaled scores, saved for the backward).  Heads >= heads_keep are not computed: their o /
- * dqkv slices are written as zeros.  impl: VSX_ATTN_IMPL_AUTO picks the tensor-core kernel when the shape is
- * supported; VSX_ATTN_IMPL_FP32 forces the fp32-math kernel (always used for dtype VSX_F32).
+ * dqkv slices are written as zeros.  impl: VSX_ATTN_IMPL_AUTO picks the fastest kernel that supports the shape:
+ * the tcgen05/TMEM kernel (head_dim 64, tokens <= 288), else the mma.sync kernel (head_dim 32/48/64), else fp32 math;
+ * VSX_ATTN_IMPL_FP32 forces the fp32-math kernel (always used for dtype VSX_F32), VSX_ATTN_IMPL_MMA_SYNC the legacy
+ * tensor-core kernel, VSX_ATTN_IMPL_TCGEN05 the tcgen05 kernel (error when the shape is unsupported).
  * -------------------------------------------------------------------------------------------------- */
 #define VSX_ATTN_IMPL_AUTO 0
 #define VSX_ATTN_IMPL_FP32 1
+#define VSX_ATTN_IMPL_MMA_SYNC 2
+#define VSX_ATTN_IMPL_TCGEN05 3
 int vsx_attn_fwd(const void* qkv, void* o, float* lse, int dtype, int batch, int tokens, int heads, int head_dim,
                  int heads_keep, float scale, int impl, void* stream);
 int vsx_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int dtype, int batch,

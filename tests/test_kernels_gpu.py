@@ -203,8 +203,9 @@ def test_gemm_epilogues(ops):
 
 # ---------------------------------------------------------------------------------------------- attention core
 @pytest.mark.parametrize('N,H,D,Hk', [(257, 3, 64, 3), (257, 6, 32, 5), (65, 4, 48, 2), (17, 4, 64, 3), (50, 2, 32, 2), (197, 2, 64, 1)])
-@pytest.mark.parametrize('mode', ['bf16_mma', 'bf16_fp32math', 'fp32'])
+@pytest.mark.parametrize('mode', ['bf16_auto', 'bf16_mma', 'bf16_fp32math', 'fp32'])
 def test_attention_core(ops, N, H, D, Hk, mode):
+    """bf16_auto = the tcgen05 kernel for head_dim 64 (csrc/attn_tc.cu), mma.sync otherwise; bf16_mma forces the mma.sync kernel."""
     B = 3
     g = torch.Generator().manual_seed(N + H + D)
     dt_ = torch.float32 if mode == 'fp32' else torch.bfloat16
@@ -221,7 +222,7 @@ def test_attention_core(ops, N, H, D, Hk, mode):
     o_ref = o_ref.detach() * keep.view(1, 1, H, 1)
     lse_ref = torch.logsumexp(s.detach(), -1)                                 # [B,H,N]
 
-    impl = ops.ATTN_FP32 if mode == 'bf16_fp32math' else ops.ATTN_AUTO
+    impl = {'bf16_fp32math': ops.ATTN_FP32, 'bf16_mma': ops.ATTN_MMA_SYNC}.get(mode, ops.ATTN_AUTO)
     qd = qkv.cuda().view(B * N, 3 * H * D)
     o = torch.full((B * N, H * D), float('nan'), device='cuda', dtype=dt_)
     lse = torch.zeros(B, H, N, device='cuda')
@@ -235,6 +236,36 @@ def test_attention_core(ops, N, H, D, Hk, mode):
     assert torch.all(dq[:, :, :, Hk:] == 0) and torch.all(o.view(B, N, H, D)[:, :, Hk:] == 0)
     for i, nm in enumerate('qkv'):
         assert rel(dq[:, :, i], dqkv_ref[:, :, i]) < (2e-5 if mode == 'fp32' else 1.5e-2), nm
+
+
+@pytest.mark.parametrize('B,N,H,Hk', [(70, 257, 4, 3), (200, 65, 8, 5), (256, 17, 12, 12), (40, 288, 2, 2), (33, 128, 3, 3), (5, 97, 2, 1)])
+def test_attention_tcgen05_persistent(ops, B, N, H, Hk):
+    """The tcgen05 attention kernels with more (sample, head) pairs than SMs, so every CTA walks several pairs through its
+    TMA / TMEM / mbarrier pipelines, against the fp32-math CUDA-core kernel on the same bf16 inputs (outputs, lse, dqkv and
+    the fused qkv-bias gradient)."""
+    D = 64
+    g = torch.Generator().manual_seed(B + N + H)
+    qkv = (torch.randn(B * N, 3 * H * D, generator=g) * 1.2).to(torch.bfloat16).cuda()
+    do = torch.randn(B * N, H * D, generator=g).to(torch.bfloat16).cuda()
+    res = {}
+    for name, impl in (('ref', ops.ATTN_FP32), ('tc', ops.ATTN_TCGEN05)):
+        o = torch.full((B * N, H * D), float('nan'), device='cuda', dtype=torch.bfloat16)
+        lse = torch.zeros(B, H, N, device='cuda')
+        ops.attn_fwd(qkv, o, lse, B, N, H, D, Hk, D ** -0.5, impl=impl)
+        dq = torch.full((B * N, 3 * H * D), float('nan'), device='cuda', dtype=torch.bfloat16)
+        db = torch.zeros(3 * H * D, device='cuda')
+        ops.attn_bwd(qkv, res['ref'][0] if name == 'tc' else o, do, res['ref'][1] if name == 'tc' else lse, dq, B, N, H, D, Hk, D ** -0.5,
+                     impl=impl, dbias=db)
+        res[name] = (o, lse, dq, db)
+    torch.cuda.synchronize()
+    o_r, lse_r, dq_r, db_r = res['ref']
+    o_t, lse_t, dq_t, db_t = res['tc']
+    assert torch.all(o_t.view(B, N, H, D)[:, :, Hk:] == 0) and torch.all(dq_t.view(B, N, 3, H, D)[:, :, :, Hk:] == 0)
+    assert rel(o_t, o_r) < 8e-3
+    assert rel(lse_t[:, :Hk], lse_r[:, :Hk]) < 1e-5
+    for i, nm in enumerate('qkv'):
+        assert rel(dq_t.view(B, N, 3, H, D)[:, :, i], dq_r.view(B, N, 3, H, D)[:, :, i]) < 1.5e-2, nm
+    assert rel(db_t, db_r) < 5e-3
 
 
 # ---------------------------------------------------------------------------------------------- direct 3x3 conv (stem)

@@ -78,6 +78,36 @@ int make_tmap_2d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows,
   return VSX_OK;
 }
 
+// 3-D bf16 tensor [batch][rows][cols] (row pitch ld, batch pitch batch_stride elements); box = box_cols x box_rows x 1, 128B
+// swizzle.  Coordinates beyond `rows` inside a batch entry are zero-filled, which is what lets the attention kernels load
+// 128-row tiles of a 257-token sample without touching the next sample.
+int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t ld_elems,
+                 uint64_t batch_stride_elems, uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return VSX_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld_elems * 2) % 16 != 0 || (batch_stride_elems * 2) % 16 != 0 || cols == 0 || rows == 0 ||
+      batch == 0) {
+    set_error("make_tmap_3d: operand must be 16-byte aligned with 16-byte-multiple pitches (base=%p ld=%llu batch_stride=%llu)", base,
+              (unsigned long long)ld_elems, (unsigned long long)batch_stride_elems);
+    return VSX_ERR_ARG;
+  }
+  cuuint64_t dims[3] = {cols, rows, batch};
+  cuuint64_t strides[2] = {ld_elems * 2, batch_stride_elems * 2};
+  cuuint32_t box[3] = {box_cols, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3-D) failed with CUresult %d (cols=%llu rows=%llu batch=%llu ld=%llu box=%ux%u)", (int)r,
+              (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)batch, (unsigned long long)ld_elems, box_cols, box_rows);
+    return VSX_ERR_CUDA;
+  }
+  return VSX_OK;
+}
+
 }  // namespace vsx
 
 extern "C" const char* vsx_last_error(void) { return vsx::g_err; }

@@ -1,0 +1,604 @@
+// tcgen05 / TMEM / TMA attention for the ViT-Res shapes (head_dim 64, N = 257 / 65 / 17 tokens, N <= 288), bf16 in / fp32 softmax.
+//
+// Replaces q@k^T*scale -> softmax -> attn@v and their autograd (nets/supernet_blocks.py:103-112).  Nothing of size N x N
+// touches HBM (the reference materialises [B,H,N,N] three times); masked heads are never computed.
+//
+// Both kernels are persistent (one CTA per SM walking a list of (sample, head) pairs) and warp specialised:
+//   warp 0      TMA producer: 3-D tensor maps over [B, N, features] so that rows >= N are hardware zero-filled
+//   warp 1      MMA issuer  : one thread issues every tcgen05.mma; tcgen05.commit publishes results / frees operand buffers
+//   warps 2..9  softmax + epilogue: thread = TMEM lane = one query (or key) row; two warps share a lane quarter and split the
+//               columns; exp2 on the SFU, P / dS written as bf16 into 128B-swizzled shared-memory atoms that the next MMA reads
+//
+// forward, per 128-query tile:  S[128 x N] = Q K^T (TMEM) -> row max / exp2 / row sum -> P (smem) -> O[128 x 64] = P V (TMEM)
+//                               -> O / l -> global, lse = max*scale + ln(l)
+// backward, key blocks j of 96 keys (outer) x query tiles i of 128 (inner), everything accumulated in tensor memory:
+//     S = Q_i K_j^T, dP = dO_i V_j^T            (TMEM columns   0.. 95,  96..191)
+//     P = exp2(S*c - lse), dS = P o (dP - delta) (registers -> smem, bf16)
+//     dV_j += P^T dO_i,  dK_j += dS^T Q_i        (TMEM columns 192..255, 256..319; MN-major A and B operands: no transposes)
+//     dQ_i += dS K_j                             (TMEM columns 320 + 64 i .. : all query tiles stay resident, 512 columns in total)
+//   the qkv-bias gradient (column sums of dQ, dK, dV) is reduced with a shuffle butterfly into shared memory and flushed once per CTA
+//   (every CTA works on ONE head).
+#include <string.h>
+
+#include "common.cuh"
+
+namespace vsx {
+
+int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t ld_elems,
+                 uint64_t batch_stride_elems, uint32_t box_cols, uint32_t box_rows);
+
+namespace {
+
+constexpr int HD_ = 64;                    // head dim: one 128-byte swizzle row
+constexpr int KV_BOX = 96;                 // rows per K / V TMA box (= backward key block)
+constexpr int ATT_MAX_N = 288;             // 3 boxes of keys, 3 query tiles
+constexpr int TILE16K = 128 * 128;         // [128 rows][64 bf16] tile = one swizzle atom column
+constexpr int BOX12K = KV_BOX * 128;
+constexpr int ATT_THREADS = 320;           // 10 warps
+constexpr int SM_WARP0 = 2;                // first softmax warp
+constexpr int SM_THREADS = 256;
+constexpr float LOG2E_F = 1.4426950408889634f;
+constexpr float LN2_F = 0.6931471805599453f;
+
+struct AttnMaps {
+  CUtensorMap q;    // qkv [B][N][3*H*64], box 64 x 128 x 1
+  CUtensorMap kv;   // qkv, box 64 x 96 x 1
+  CUtensorMap d_o;  // d_o [B][N][H*64], box 64 x 128 x 1 (backward only)
+};
+
+struct AttnArgs {
+  int B, N, H, Hk;
+  float scale;
+  bf16* o;             // fwd: output; bwd: forward output (for delta)
+  const bf16* d_o;     // bwd
+  float* lse;          // fwd: written; bwd: read
+  bf16* dqkv;          // bwd
+  float* dbias;        // bwd, may be null
+};
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+// Shared-memory matrix descriptors (128B swizzle, 8-row groups 1024 B apart).
+// K-major: rows of 64 contiguous k elements (128 B); a 16-wide k step advances the start address by 32 B.
+__device__ __forceinline__ uint64_t desc_k(uint32_t addr) {
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// MN-major: rows are k, 64 contiguous MN elements per row (128 B); a 16-wide k step advances by 16 rows = 2048 B;
+// lbo = distance between consecutive 64-element MN atoms.
+__device__ __forceinline__ uint64_t desc_mn(uint32_t addr, uint32_t lbo_bytes) {
+  return (uint64_t)((addr & 0x3FFFF) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// kind::f16 instruction descriptor: D = f32, A = B = bf16, M = 128.
+__device__ __forceinline__ uint32_t idesc_m128(int n, bool a_mn, bool b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// byte offset of 16-byte chunk `chunk` (0..7) of row `row` inside a [rows][128 B] 128B-swizzled atom column
+__device__ __forceinline__ uint32_t swz(int row, int chunk) { return (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4)); }
+
+// 32 consecutive columns (col0 % 32 == 0) of row `row` -> bf16 -> staging [atoms of 64 columns][128 rows][128 B]
+__device__ __forceinline__ void stage_bf16_32(uint8_t* stg, int row, int col0, const float (&v)[32]) {
+  uint8_t* atom = stg + (col0 >> 6) * TILE16K;
+  const int ch0 = (col0 & 63) >> 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 r;
+    r.x = pack_bf16(v[8 * i], v[8 * i + 1]);
+    r.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+    r.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+    r.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+    *reinterpret_cast<uint4*>(atom + swz(row, ch0 + i)) = r;
+  }
+}
+
+// 32 fp32 values -> bf16 -> 64 contiguous bytes of global memory
+__device__ __forceinline__ void store_bf16_32(bf16* dst, const float (&v)[32]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 r;
+    r.x = pack_bf16(v[8 * i], v[8 * i + 1]);
+    r.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+    r.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+    r.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+    *reinterpret_cast<uint4*>(dst + 8 * i) = r;
+  }
+}
+
+// Column sums over the 32 lanes of a warp: on return lane l holds sum_lanes v[l] (31 shuffles: recursive halving).
+__device__ __forceinline__ float butterfly_colsum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int k = 0; k < s; ++k) {
+      const float send = up ? v[k] : v[k + s];
+      const float keep = up ? v[k + s] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ int round16(int x) { return (x + 15) & ~15; }
+
+// ------------------------------------------------------------------------------------------------ forward
+constexpr int F_K = 0, F_V = 3 * BOX12K, F_Q = 6 * BOX12K, F_P = F_Q + 2 * TILE16K, F_END = F_P + 5 * TILE16K;
+constexpr int F_SMEM = F_END + 1024 /*align*/ + 128 /*barriers*/ + 4 * 128 * 4 /*xm, xl*/;
+constexpr int F_OCOL = 448;   // O accumulator columns 448..511; S occupies 0..287
+
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bar0 = base + F_END;
+  // barriers: 0 k_full, 1 k_empty, 2 v_full, 3 v_empty, 4-5 q_full, 6-7 q_empty, 8 s_full, 9 p_ready, 10 o_full
+  auto bar = [&](int i) { return bar0 + 8u * i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + F_END + 96);
+  float* xm = reinterpret_cast<float*>(smem + F_END + 128);   // [2][128] partial row maxima
+  float* xl = xm + 256;                                       // [2][128] partial row sums
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = a.N, HD = a.H * HD_;
+  const int QT = (N + 127) / 128, NKP = round16(N), nkb = (N + KV_BOX - 1) / KV_BOX;
+  const int total = a.B * a.Hk;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.q);
+    tma_prefetch_desc(&maps.kv);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < 11; ++i) mbar_init(bar(i), i == 9 ? 8 : 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 512);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int nw = 0, qit = 0;
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++nw) {
+        const int b = w / a.Hk, h = w % a.Hk;
+        mbar_wait(bar(1), ((uint32_t)nw & 1u) ^ 1u);
+        mbar_expect_tx(bar(0), (uint32_t)nkb * BOX12K);
+        for (int c = 0; c < nkb; ++c) tma_load_3d(base + F_K + c * BOX12K, &maps.kv, bar(0), HD + h * HD_, c * KV_BOX, b);
+        for (int i = 0; i < QT; ++i, ++qit) {
+          const int s = qit & 1;
+          mbar_wait(bar(6 + s), (((uint32_t)qit >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(bar(4 + s), TILE16K);
+          tma_load_3d(base + F_Q + s * TILE16K, &maps.q, bar(4 + s), h * HD_, i * 128, b);
+          if (i == 0) {
+            mbar_wait(bar(3), ((uint32_t)nw & 1u) ^ 1u);
+            mbar_expect_tx(bar(2), (uint32_t)nkb * BOX12K);
+            for (int c = 0; c < nkb; ++c) tma_load_3d(base + F_V + c * BOX12K, &maps.kv, bar(2), 2 * HD + h * HD_, c * KV_BOX, b);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int nw = 0, qit = 0, blk = 0;
+      const uint32_t id_o = idesc_m128(64, false, true);
+      for (int w = blockIdx.x; w < total; w += gridDim.x, ++nw) {
+        mbar_wait(bar(0), (uint32_t)nw & 1u);
+        for (int i = 0; i < QT; ++i, ++qit, ++blk) {
+          const int s = qit & 1;
+          mbar_wait(bar(4 + s), ((uint32_t)qit >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t qa = base + F_Q + s * TILE16K;
+          for (int c = 0; c < nkb; ++c) {
+            const int ncols = min(KV_BOX, NKP - c * KV_BOX);
+            const uint32_t id_s = idesc_m128(ncols, false, false);
+            const uint32_t ka = base + F_K + c * BOX12K;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem + c * KV_BOX, desc_k(qa + k * 32), desc_k(ka + k * 32), id_s, k > 0 ? 1u : 0u);
+          }
+          umma_commit(bar(6 + s));
+          umma_commit(bar(8));
+          if (i == QT - 1) umma_commit(bar(1));
+          mbar_wait(bar(9), (uint32_t)blk & 1u);
+          tc_fence_after();
+          if (i == 0) {
+            mbar_wait(bar(2), (uint32_t)nw & 1u);
+            tc_fence_after();
+          }
+          for (int kk = 0; kk < NKP / 16; ++kk)
+            umma_bf16(tmem + F_OCOL, desc_k(base + F_P + (kk >> 2) * TILE16K + (kk & 3) * 32), desc_mn(base + F_V + kk * 2048, TILE16K), id_o,
+                      kk > 0 ? 1u : 0u);
+          umma_commit(bar(10));
+          if (i == QT - 1) umma_commit(bar(3));
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3, hf = (warp - SM_WARP0) >> 2, row = q * 32 + lane;
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    const float c = a.scale * LOG2E_F;
+    const int nch = (NKP + 31) / 32;
+    uint8_t* Ps = smem + F_P;
+    int blk = 0;
+    for (int w = blockIdx.x; w < total; w += gridDim.x) {
+      const int b = w / a.Hk, h = w % a.Hk;
+      for (int i = 0; i < QT; ++i, ++blk) {
+        const int rows_valid = min(128, N - i * 128);
+        const bool active = q * 32 < rows_valid;
+        mbar_wait(bar(8), (uint32_t)blk & 1u);
+        tc_fence_after();
+        float m = -INFINITY;
+        if (active) {
+          for (int cc = hf; cc < nch; cc += 2) {
+            float v[32];
+            tmem_ld32(tlane + cc * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m = fmaxf(m, cc * 32 + j < N ? v[j] : -INFINITY);
+          }
+        }
+        xm[hf * 128 + row] = m;
+        named_bar_sync(1, SM_THREADS);
+        m = fmaxf(xm[row], xm[128 + row]);
+        const float mc = m * c;
+        float l = 0.f;
+        if (active) {
+          for (int cc = hf; cc < nch; cc += 2) {
+            float v[32];
+            tmem_ld32(tlane + cc * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float p = cc * 32 + j < N ? ex2(fmaf(v[j], c, -mc)) : 0.f;
+              l += p;
+              v[j] = p;
+            }
+            stage_bf16_32(Ps, row, cc * 32, v);
+          }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(9));
+        xl[hf * 128 + row] = l;
+        named_bar_sync(2, SM_THREADS);
+        l = xl[row] + xl[128 + row];
+        mbar_wait(bar(10), (uint32_t)blk & 1u);
+        tc_fence_after();
+        if (active) {
+          float v[32];
+          tmem_ld32(tlane + F_OCOL + hf * 32, v);
+          tmem_ld_wait();
+          if (row < rows_valid) {
+            const float inv = 1.0f / l;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= inv;
+            const long r = (long)b * N + i * 128 + row;
+            store_bf16_32(a.o + r * HD + h * HD_ + hf * 32, v);
+            if (hf == 0) a.lse[((long)b * a.H + h) * N + i * 128 + row] = (mc + log2f(l)) * LN2_F;
+          }
+        }
+        tc_fence_before();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ backward
+constexpr int B_KV = 0, B_QDO = 4 * BOX12K, B_P = B_QDO + 4 * TILE16K, B_DS = B_P + 2 * TILE16K, B_END = B_DS + 2 * TILE16K;
+constexpr int B_SMEM = B_END + 1024 + 128 + 3 * 64 * 4;
+constexpr int C_S = 0, C_DP = 96, C_DV = 192, C_DK = 256, C_DQ = 320;
+
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bar0 = base + B_END;
+  // barriers: 0-1 kv_full, 2-3 kv_empty, 4-5 q_full, 6-7 q_empty, 8 sdp_full, 9 pds_ready, 10 dkv_full, 11 dq_full
+  auto bar = [&](int i) { return bar0 + 8u * i; };
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + B_END + 104);
+  float* cs = reinterpret_cast<float*>(smem + B_END + 128);   // [3][64] column sums of dQ, dK, dV (this CTA's head)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = a.N, HD = a.H * HD_;
+  const int QT = (N + 127) / 128, KB = (N + KV_BOX - 1) / KV_BOX;
+  // this CTA's head and its samples: gridDim.x is a multiple of Hk
+  const int h = blockIdx.x % a.Hk, slot = blockIdx.x / a.Hk, nslots = gridDim.x / a.Hk;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&maps.q);
+    tma_prefetch_desc(&maps.kv);
+    tma_prefetch_desc(&maps.d_o);
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int i = 0; i < 12; ++i) mbar_init(bar(i), i == 9 ? 8 : 1);
+      fence_mbar_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 512);
+  }
+  if (threadIdx.x < 192) cs[threadIdx.x] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int kvit = 0, qit = 0;
+      for (int b = slot; b < a.B; b += nslots) {
+        for (int j = 0; j < KB; ++j, ++kvit) {
+          const int ks = kvit & 1;
+          mbar_wait(bar(2 + ks), (((uint32_t)kvit >> 1) & 1u) ^ 1u);
+          mbar_expect_tx(bar(ks), 2 * BOX12K);
+          tma_load_3d(base + B_KV + ks * 2 * BOX12K, &maps.kv, bar(ks), HD + h * HD_, j * KV_BOX, b);
+          tma_load_3d(base + B_KV + ks * 2 * BOX12K + BOX12K, &maps.kv, bar(ks), 2 * HD + h * HD_, j * KV_BOX, b);
+          for (int i = 0; i < QT; ++i, ++qit) {
+            const int qs = qit & 1;
+            mbar_wait(bar(6 + qs), (((uint32_t)qit >> 1) & 1u) ^ 1u);
+            mbar_expect_tx(bar(4 + qs), 2 * TILE16K);
+            tma_load_3d(base + B_QDO + qs * 2 * TILE16K, &maps.q, bar(4 + qs), h * HD_, i * 128, b);
+            tma_load_3d(base + B_QDO + qs * 2 * TILE16K + TILE16K, &maps.d_o, bar(4 + qs), h * HD_, i * 128, b);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int kvit = 0, qit = 0, blk = 0;
+      const uint32_t id_t = idesc_m128(64, true, true);     // dV, dK: both operands MN-major
+      const uint32_t id_q = idesc_m128(64, false, true);    // dQ: A = dS K-major, B = K MN-major
+      for (int b = slot; b < a.B; b += nslots) {
+        for (int j = 0; j < KB; ++j, ++kvit) {
+          const int ks = kvit & 1;
+          mbar_wait(bar(ks), ((uint32_t)kvit >> 1) & 1u);
+          tc_fence_after();
+          const int kw = round16(min(KV_BOX, N - j * KV_BOX));
+          const uint32_t id_s = idesc_m128(kw, false, false);
+          const uint32_t ka = base + B_KV + ks * 2 * BOX12K, va = ka + BOX12K;
+          for (int i = 0; i < QT; ++i, ++qit, ++blk) {
+            const int qs = qit & 1;
+            mbar_wait(bar(4 + qs), ((uint32_t)qit >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t qa = base + B_QDO + qs * 2 * TILE16K, doa = qa + TILE16K;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem + C_S, desc_k(qa + k * 32), desc_k(ka + k * 32), id_s, k > 0 ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tmem + C_DP, desc_k(doa + k * 32), desc_k(va + k * 32), id_s, k > 0 ? 1u : 0u);
+            umma_commit(bar(8));
+            mbar_wait(bar(9), (uint32_t)blk & 1u);
+            tc_fence_after();
+            const int kq = (min(128, N - i * 128) + 15) / 16;     // 16-row k steps over the valid queries of this tile
+            for (int k = 0; k < kq; ++k)
+              umma_bf16(tmem + C_DV, desc_mn(base + B_P + k * 2048, TILE16K), desc_mn(doa + k * 2048, TILE16K), id_t, (i | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < kq; ++k)
+              umma_bf16(tmem + C_DK, desc_mn(base + B_DS + k * 2048, TILE16K), desc_mn(qa + k * 2048, TILE16K), id_t, (i | k) != 0 ? 1u : 0u);
+            for (int kk = 0; kk < kw / 16; ++kk)
+              umma_bf16(tmem + C_DQ + 64 * i, desc_k(base + B_DS + (kk >> 2) * TILE16K + (kk & 3) * 32), desc_mn(ka + kk * 2048, TILE16K), id_q,
+                        (j | kk) != 0 ? 1u : 0u);
+            umma_commit(bar(6 + qs));
+            if (i == QT - 1) {
+              umma_commit(bar(2 + ks));
+              umma_commit(bar(10));
+              if (j == KB - 1) umma_commit(bar(11));
+            }
+          }
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3, hf = (warp - SM_WARP0) >> 2, row = q * 32 + lane;
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    const float c = a.scale * LOG2E_F;
+    const long ldq = 3L * HD;
+    uint8_t* Ps = smem + B_P;
+    uint8_t* dSs = smem + B_DS;
+    int blk = 0, nkv = 0, nb = 0;
+    for (int b = slot; b < a.B; b += nslots, ++nb) {
+      // per-row statistics of this thread's query rows: lse in log2 units, delta = dO . O
+      float lse2[3], delta[3];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        lse2[i] = 0.f, delta[i] = 0.f;
+        const int r = i * 128 + row;
+        if (i < QT && r < N) {
+          lse2[i] = a.lse[((long)b * a.H + h) * N + r] * LOG2E_F;
+          const bf16* op = a.o + ((long)b * N + r) * HD + h * HD_;
+          const bf16* dp = a.d_o + ((long)b * N + r) * HD + h * HD_;
+          float acc = 0.f;
+#pragma unroll
+          for (int cc = 0; cc < HD_; cc += 8) {
+            const uint4 ov = *reinterpret_cast<const uint4*>(op + cc);
+            const uint4 dv = *reinterpret_cast<const uint4*>(dp + cc);
+            const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[t]));
+              const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[t]));
+              acc += x.x * y.x + x.y * y.y;
+            }
+          }
+          delta[i] = acc;
+        }
+      }
+      for (int j = 0; j < KB; ++j) {
+        const int keys_valid = min(KV_BOX, N - j * KV_BOX);
+        const int kw = round16(keys_valid);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          if (i < QT) {
+            const int rows_valid = min(128, N - i * 128);
+            const bool active = q * 32 < round16(rows_valid);
+            const bool rv = row < rows_valid;
+            mbar_wait(bar(8), (uint32_t)blk & 1u);
+            tc_fence_after();
+            if (active) {
+              for (int cc = hf; cc * 32 < kw; cc += 2) {
+                float s[32], dp[32];
+                tmem_ld32(tlane + C_S + cc * 32, s);
+                tmem_ld32(tlane + C_DP + cc * 32, dp);
+                tmem_ld_wait();
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                  const bool ok = rv && (cc * 32 + t < keys_valid);
+                  const float p = ok ? ex2(fmaf(s[t], c, -lse2[i])) : 0.f;
+                  s[t] = p;
+                  dp[t] = ok ? p * (dp[t] - delta[i]) : 0.f;
+                }
+                stage_bf16_32(Ps, row, cc * 32, s);
+                stage_bf16_32(dSs, row, cc * 32, dp);
+              }
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar(9));
+            ++blk;
+          }
+        }
+        // dK_j, dV_j: TMEM lane = key row of this block
+        mbar_wait(bar(10), (uint32_t)nkv & 1u);
+        ++nkv;
+        tc_fence_after();
+        if (q * 32 < kw) {
+          const int key = j * KV_BOX + row;
+          const bool kvalid = row < keys_valid;
+          bf16* dst = a.dqkv + ((long)b * N + key) * ldq + h * HD_ + hf * 32;
+          float v[32];
+          tmem_ld32(tlane + C_DV + hf * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) v[t] = kvalid ? v[t] : 0.f;
+          if (kvalid) store_bf16_32(dst + 2 * HD, v);
+          if (a.dbias != nullptr) atomicAdd(cs + 128 + hf * 32 + lane, butterfly_colsum(v, lane));
+          tmem_ld32(tlane + C_DK + hf * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int t = 0; t < 32; ++t) v[t] = kvalid ? v[t] * a.scale : 0.f;
+          if (kvalid) store_bf16_32(dst + HD, v);
+          if (a.dbias != nullptr) atomicAdd(cs + 64 + hf * 32 + lane, butterfly_colsum(v, lane));
+        }
+        tc_fence_before();
+      }
+      // dQ: all query tiles are complete after the last key block
+      mbar_wait(bar(11), (uint32_t)nb & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (i < QT) {
+          const int rows_valid = min(128, N - i * 128);
+          if (q * 32 < rows_valid) {
+            const bool rv = row < rows_valid;
+            float v[32];
+            tmem_ld32(tlane + C_DQ + 64 * i + hf * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int t = 0; t < 32; ++t) v[t] = rv ? v[t] * a.scale : 0.f;
+            if (rv) store_bf16_32(a.dqkv + ((long)b * N + i * 128 + row) * ldq + h * HD_ + hf * 32, v);
+            if (a.dbias != nullptr) atomicAdd(cs + hf * 32 + lane, butterfly_colsum(v, lane));
+          }
+        }
+      }
+      tc_fence_before();
+    }
+    if (a.dbias != nullptr) {
+      named_bar_sync(1, SM_THREADS);
+      const int t = threadIdx.x - SM_WARP0 * 32;
+      if (t < 192) atomicAdd(a.dbias + (long)(t >> 6) * HD + h * HD_ + (t & 63), cs[t]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+int set_smem(const void* fn, int bytes, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaFuncSetAttribute(%d) failed: %s", what, bytes, cudaGetErrorString(e));
+    return VSX_ERR_CUDA;
+  }
+  return VSX_OK;
+}
+
+// masked heads: their slices are defined to be zero (consumers contract over the full feature width in places)
+int zero_cols(void* base, long ld_elems, long rows, long col0, long ncols, cudaStream_t st, const char* what) {
+  if (ncols <= 0 || rows <= 0) return VSX_OK;
+  cudaError_t e = cudaMemset2DAsync(static_cast<uint8_t*>(base) + col0 * 2, (size_t)ld_elems * 2, 0, (size_t)ncols * 2, (size_t)rows, st);
+  if (e != cudaSuccess) {
+    set_error("%s: cudaMemset2DAsync failed: %s", what, cudaGetErrorString(e));
+    return VSX_ERR_CUDA;
+  }
+  return VSX_OK;
+}
+
+}  // namespace
+
+bool attn_tc_supported(int N, int D) { return D == HD_ && N >= 1 && N <= ATT_MAX_N; }
+
+int attn_fwd_tc(const void* qkv, void* o, float* lse, int B, int N, int H, int Hk, float scale, cudaStream_t st) {
+  const long HD = (long)H * HD_;
+  int rc = zero_cols(o, HD, (long)B * N, (long)Hk * HD_, (long)(H - Hk) * HD_, st, "vsx_attn_fwd");
+  if (rc || Hk == 0) return rc;
+  AttnMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  if ((rc = make_tmap_3d(&maps.q, qkv, 3 * HD, N, B, 3 * HD, (uint64_t)N * 3 * HD, 64, 128))) return rc;
+  if ((rc = make_tmap_3d(&maps.kv, qkv, 3 * HD, N, B, 3 * HD, (uint64_t)N * 3 * HD, 64, KV_BOX))) return rc;
+  static bool configured = false;
+  if (!configured) {
+    if ((rc = set_smem((const void*)attn_fwd_tc_kernel, F_SMEM, "vsx_attn_fwd"))) return rc;
+    configured = true;
+  }
+  AttnArgs a;
+  a.B = B, a.N = N, a.H = H, a.Hk = Hk, a.scale = scale, a.o = (bf16*)o, a.d_o = nullptr, a.lse = lse, a.dqkv = nullptr, a.dbias = nullptr;
+  const int total = B * Hk;
+  const int grid = total < num_sms() ? total : num_sms();
+  attn_fwd_tc_kernel<<<grid, ATT_THREADS, F_SMEM, st>>>(maps, a);
+  return check_launch("vsx_attn_fwd");
+}
+
+int attn_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int N, int H, int Hk, float scale,
+                float* dbias, cudaStream_t st) {
+  const long HD = (long)H * HD_;
+  int rc = VSX_OK;
+  for (int j = 0; j < 3 && rc == VSX_OK; ++j)
+    rc = zero_cols(dqkv, 3 * HD, (long)B * N, j * HD + (long)Hk * HD_, (long)(H - Hk) * HD_, st, "vsx_attn_bwd");
+  if (rc || Hk == 0) return rc;
+  AttnMaps maps;
+  if ((rc = make_tmap_3d(&maps.q, qkv, 3 * HD, N, B, 3 * HD, (uint64_t)N * 3 * HD, 64, 128))) return rc;
+  if ((rc = make_tmap_3d(&maps.kv, qkv, 3 * HD, N, B, 3 * HD, (uint64_t)N * 3 * HD, 64, KV_BOX))) return rc;
+  if ((rc = make_tmap_3d(&maps.d_o, d_o, HD, N, B, HD, (uint64_t)N * HD, 64, 128))) return rc;
+  static bool configured = false;
+  if (!configured) {
+    if ((rc = set_smem((const void*)attn_bwd_tc_kernel, B_SMEM, "vsx_attn_bwd"))) return rc;
+    configured = true;
+  }
+  AttnArgs a;
+  a.B = B, a.N = N, a.H = H, a.Hk = Hk, a.scale = scale, a.o = (bf16*)const_cast<void*>(o), a.d_o = (const bf16*)d_o,
+  a.lse = const_cast<float*>(lse), a.dqkv = (bf16*)dqkv, a.dbias = dbias;
+  int per_head = num_sms() / Hk;
+  if (per_head < 1) per_head = 1;
+  if (per_head > B) per_head = B;
+  attn_bwd_tc_kernel<<<per_head * Hk, ATT_THREADS, B_SMEM, st>>>(maps, a);
+  return check_launch("vsx_attn_bwd");
+}
+
+}  // namespace vsx

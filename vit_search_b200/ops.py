@@ -107,7 +107,7 @@ def gemm(a, b, lda, ldb, M, N, K, epilogue, out, ldo, *, a_off=0, b_off=0, out_o
 
 
 # ------------------------------------------------------------------------------------------------ attention core
-ATTN_AUTO, ATTN_FP32 = 0, 1
+ATTN_AUTO, ATTN_FP32, ATTN_MMA_SYNC, ATTN_TCGEN05 = 0, 1, 2, 3
 
 
 def attn_fwd(qkv, o, lse, batch, tokens, heads, head_dim, heads_keep, scale, *, qkv_off=0, o_off=0, lse_off=0, impl=ATTN_AUTO):
