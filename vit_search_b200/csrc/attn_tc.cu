@@ -131,6 +131,61 @@ __device__ __forceinline__ float butterfly_colsum(float (&v)[32], int lane) {
 
 __device__ __forceinline__ int round16(int x) { return (x + 15) & ~15; }
 
+// 32 lanes x 16 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+// 16 consecutive columns (col0 % 16 == 0) of row `row` -> bf16 -> staging
+__device__ __forceinline__ void stage_bf16_16(uint8_t* stg, int row, int col0, const float (&v)[16]) {
+  uint8_t* atom = stg + (col0 >> 6) * TILE16K;
+  const int ch0 = (col0 & 63) >> 3;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint4 r;
+    r.x = pack_bf16(v[8 * i], v[8 * i + 1]);
+    r.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+    r.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+    r.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+    *reinterpret_cast<uint4*>(atom + swz(row, ch0 + i)) = r;
+  }
+}
+
+// Producer-side wait: the TMA thread is never on the critical path, so it backs off instead of competing for issue slots
+// with the softmax warps of its scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    __nanosleep(64);
+    if (clock64() - t0 > 3000000000LL) {
+      printf("vsx: attention producer wait timed out (block %d)\n", blockIdx.x);
+      __trap();
+    }
+  }
+}
+
+// Zero the slices of the masked heads (columns [col0, col0 + ncols) of `nslices` feature groups `slice_stride` apart) for this
+// CTA's share of the rows: consumers contract over the full feature width in places, so masked slices are defined as zero.
+__device__ __forceinline__ void zero_masked(bf16* base, long ld, long rows, int col0, int ncols, int nslices, long slice_stride, int tid,
+                                            int nthreads) {
+  if (ncols <= 0) return;
+  const int cpr = ncols >> 3, per_row = cpr * nslices;
+  const long my_rows = (rows - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  for (long idx = tid; idx < my_rows * per_row; idx += nthreads) {
+    const long rl = idx / per_row;
+    const int i = (int)(idx - rl * per_row), sl = i / cpr, ch = i - sl * cpr;
+    const long r = blockIdx.x + rl * gridDim.x;
+    *reinterpret_cast<uint4*>(base + r * ld + sl * slice_stride + col0 + ch * 8) = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ forward
 constexpr int F_K = 0, F_V = 3 * BOX12K, F_Q = 6 * BOX12K, F_P = F_Q + 2 * TILE16K, F_END = F_P + 5 * TILE16K;
 constexpr int F_SMEM = F_END + 1024 /*align*/ + 128 /*barriers*/ + 4 * 128 * 4 /*xm, xl*/;
@@ -175,16 +230,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_tc_kernel(const __gri
       int nw = 0, qit = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++nw) {
         const int b = w / a.Hk, h = w % a.Hk;
-        mbar_wait(bar(1), ((uint32_t)nw & 1u) ^ 1u);
+        mbar_wait_relaxed(bar(1), ((uint32_t)nw & 1u) ^ 1u);
         mbar_expect_tx(bar(0), (uint32_t)nkb * BOX12K);
         for (int c = 0; c < nkb; ++c) tma_load_3d(base + F_K + c * BOX12K, &maps.kv, bar(0), HD + h * HD_, c * KV_BOX, b);
         for (int i = 0; i < QT; ++i, ++qit) {
           const int s = qit & 1;
-          mbar_wait(bar(6 + s), (((uint32_t)qit >> 1) & 1u) ^ 1u);
+          mbar_wait_relaxed(bar(6 + s), (((uint32_t)qit >> 1) & 1u) ^ 1u);
           mbar_expect_tx(bar(4 + s), TILE16K);
           tma_load_3d(base + F_Q + s * TILE16K, &maps.q, bar(4 + s), h * HD_, i * 128, b);
           if (i == 0) {
-            mbar_wait(bar(3), ((uint32_t)nw & 1u) ^ 1u);
+            mbar_wait_relaxed(bar(3), ((uint32_t)nw & 1u) ^ 1u);
             mbar_expect_tx(bar(2), (uint32_t)nkb * BOX12K);
             for (int c = 0; c < nkb; ++c) tma_load_3d(base + F_V + c * BOX12K, &maps.kv, bar(2), 2 * HD + h * HD_, c * KV_BOX, b);
           }
@@ -233,6 +288,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_tc_kernel(const __gri
     const int nch = (NKP + 31) / 32;
     uint8_t* Ps = smem + F_P;
     int blk = 0;
+    zero_masked(a.o, HD, (long)a.B * N, a.Hk * HD_, (a.H - a.Hk) * HD_, 1, 0, threadIdx.x - SM_WARP0 * 32, SM_THREADS);
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int b = w / a.Hk, h = w % a.Hk;
       for (int i = 0; i < QT; ++i, ++blk) {
@@ -246,8 +302,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_tc_kernel(const __gri
             float v[32];
             tmem_ld32(tlane + cc * 32, v);
             tmem_ld_wait();
+            if (cc * 32 + 32 <= N) {      // only the last chunk needs the key mask
 #pragma unroll
-            for (int j = 0; j < 32; ++j) m = fmaxf(m, cc * 32 + j < N ? v[j] : -INFINITY);
+              for (int j = 0; j < 32; ++j) m = fmaxf(m, v[j]);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) m = fmaxf(m, cc * 32 + j < N ? v[j] : -INFINITY);
+            }
           }
         }
         xm[hf * 128 + row] = m;
@@ -260,11 +321,19 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_tc_kernel(const __gri
             float v[32];
             tmem_ld32(tlane + cc * 32, v);
             tmem_ld_wait();
+            if (cc * 32 + 32 <= N) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float p = cc * 32 + j < N ? ex2(fmaf(v[j], c, -mc)) : 0.f;
-              l += p;
-              v[j] = p;
+              for (int j = 0; j < 32; ++j) {
+                v[j] = ex2(fmaf(v[j], c, -mc));
+                l += v[j];
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float p = cc * 32 + j < N ? ex2(fmaf(v[j], c, -mc)) : 0.f;
+                l += p;
+                v[j] = p;
+              }
             }
             stage_bf16_32(Ps, row, cc * 32, v);
           }
@@ -347,13 +416,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_tc_kernel(const __gri
       for (int b = slot; b < a.B; b += nslots) {
         for (int j = 0; j < KB; ++j, ++kvit) {
           const int ks = kvit & 1;
-          mbar_wait(bar(2 + ks), (((uint32_t)kvit >> 1) & 1u) ^ 1u);
+          mbar_wait_relaxed(bar(2 + ks), (((uint32_t)kvit >> 1) & 1u) ^ 1u);
           mbar_expect_tx(bar(ks), 2 * BOX12K);
           tma_load_3d(base + B_KV + ks * 2 * BOX12K, &maps.kv, bar(ks), HD + h * HD_, j * KV_BOX, b);
           tma_load_3d(base + B_KV + ks * 2 * BOX12K + BOX12K, &maps.kv, bar(ks), 2 * HD + h * HD_, j * KV_BOX, b);
           for (int i = 0; i < QT; ++i, ++qit) {
             const int qs = qit & 1;
-            mbar_wait(bar(6 + qs), (((uint32_t)qit >> 1) & 1u) ^ 1u);
+            mbar_wait_relaxed(bar(6 + qs), (((uint32_t)qit >> 1) & 1u) ^ 1u);
             mbar_expect_tx(bar(4 + qs), 2 * TILE16K);
             tma_load_3d(base + B_QDO + qs * 2 * TILE16K, &maps.q, bar(4 + qs), h * HD_, i * 128, b);
             tma_load_3d(base + B_QDO + qs * 2 * TILE16K + TILE16K, &maps.d_o, bar(4 + qs), h * HD_, i * 128, b);
@@ -412,12 +481,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_tc_kernel(const __gri
     uint8_t* Ps = smem + B_P;
     uint8_t* dSs = smem + B_DS;
     int blk = 0, nkv = 0, nb = 0;
+    zero_masked(a.dqkv, ldq, (long)a.B * N, a.Hk * HD_, (a.H - a.Hk) * HD_, 3, HD, threadIdx.x - SM_WARP0 * 32, SM_THREADS);
     for (int b = slot; b < a.B; b += nslots, ++nb) {
       // per-row statistics of this thread's query rows: lse in log2 units, delta = dO . O
       float lse2[3], delta[3];
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        lse2[i] = 0.f, delta[i] = 0.f;
+        lse2[i] = INFINITY, delta[i] = 0.f;      // rows >= N: P = exp2(S*c - inf) = 0 and dS = 0 (S, dP are exact zeros there)
         const int r = i * 128 + row;
         if (i < QT && r < N) {
           lse2[i] = a.lse[((long)b * a.H + h) * N + r] * LOG2E_F;
@@ -447,24 +517,34 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_tc_kernel(const __gri
           if (i < QT) {
             const int rows_valid = min(128, N - i * 128);
             const bool active = q * 32 < round16(rows_valid);
-            const bool rv = row < rows_valid;
             mbar_wait(bar(8), (uint32_t)blk & 1u);
             tc_fence_after();
             if (active) {
-              for (int cc = hf; cc * 32 < kw; cc += 2) {
-                float s[32], dp[32];
-                tmem_ld32(tlane + C_S + cc * 32, s);
-                tmem_ld32(tlane + C_DP + cc * 32, dp);
+              // the two warps of a lane quarter split the kw columns in 16-column units: [0, kh) and [kh, kw)
+              const int kh = round16(kw >> 1);
+              const int c0 = hf == 0 ? 0 : kh, c1 = hf == 0 ? kh : kw;
+              for (int col = c0; col < c1; col += 16) {
+                float s[16], dp[16];
+                tmem_ld16(tlane + C_S + col, s);
+                tmem_ld16(tlane + C_DP + col, dp);
                 tmem_ld_wait();
+                if (col + 16 <= keys_valid) {
 #pragma unroll
-                for (int t = 0; t < 32; ++t) {
-                  const bool ok = rv && (cc * 32 + t < keys_valid);
-                  const float p = ok ? ex2(fmaf(s[t], c, -lse2[i])) : 0.f;
-                  s[t] = p;
-                  dp[t] = ok ? p * (dp[t] - delta[i]) : 0.f;
+                  for (int t = 0; t < 16; ++t) {
+                    s[t] = ex2(fmaf(s[t], c, -lse2[i]));
+                    dp[t] = s[t] * (dp[t] - delta[i]);
+                  }
+                } else {
+#pragma unroll
+                  for (int t = 0; t < 16; ++t) {
+                    const bool ok = col + t < keys_valid;
+                    const float p = ok ? ex2(fmaf(s[t], c, -lse2[i])) : 0.f;
+                    s[t] = p;
+                    dp[t] = ok ? p * (dp[t] - delta[i]) : 0.f;
+                  }
                 }
-                stage_bf16_32(Ps, row, cc * 32, s);
-                stage_bf16_32(dSs, row, cc * 32, dp);
+                stage_bf16_16(Ps, row, col, s);
+                stage_bf16_16(dSs, row, col, dp);
               }
             }
             fence_proxy_async();
@@ -556,8 +636,8 @@ bool attn_tc_supported(int N, int D) { return D == HD_ && N >= 1 && N <= ATT_MAX
 
 int attn_fwd_tc(const void* qkv, void* o, float* lse, int B, int N, int H, int Hk, float scale, cudaStream_t st) {
   const long HD = (long)H * HD_;
-  int rc = zero_cols(o, HD, (long)B * N, (long)Hk * HD_, (long)(H - Hk) * HD_, st, "vsx_attn_fwd");
-  if (rc || Hk == 0) return rc;
+  int rc = VSX_OK;
+  if (Hk == 0) return zero_cols(o, HD, (long)B * N, 0, HD, st, "vsx_attn_fwd");
   AttnMaps maps;
   memset(&maps, 0, sizeof(maps));
   if ((rc = make_tmap_3d(&maps.q, qkv, 3 * HD, N, B, 3 * HD, (uint64_t)N * 3 * HD, 64, 128))) return rc;
@@ -579,9 +659,7 @@ int attn_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* ls
                 float* dbias, cudaStream_t st) {
   const long HD = (long)H * HD_;
   int rc = VSX_OK;
-  for (int j = 0; j < 3 && rc == VSX_OK; ++j)
-    rc = zero_cols(dqkv, 3 * HD, (long)B * N, j * HD + (long)Hk * HD_, (long)(H - Hk) * HD_, st, "vsx_attn_bwd");
-  if (rc || Hk == 0) return rc;
+  if (Hk == 0) return zero_cols(dqkv, 3 * HD, (long)B * N, 0, 3 * HD, st, "vsx_attn_bwd");
   AttnMaps maps;
   if ((rc = make_tmap_3d(&maps.q, qkv, 3 * HD, N, B, 3 * HD, (uint64_t)N * 3 * HD, 64, 128))) return rc;
   if ((rc = make_tmap_3d(&maps.kv, qkv, 3 * HD, N, B, 3 * HD, (uint64_t)N * 3 * HD, 64, KV_BOX))) return rc;
