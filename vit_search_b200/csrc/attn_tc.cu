@@ -131,6 +131,18 @@ __device__ __forceinline__ float butterfly_colsum(float (&v)[32], int lane) {
 
 __device__ __forceinline__ int round16(int x) { return (x + 15) & ~15; }
 
+// One lane of a converged warp.  The MMA warp runs its loops converged (so descriptor arithmetic stays on the uniform
+// datapath instead of per-thread registers + R2UR round trips) and only the tcgen05 instructions are predicated on the leader.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // 32 lanes x 16 consecutive fp32 columns
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -247,38 +259,47 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_tc_kernel(const __gri
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int nw = 0, qit = 0, blk = 0;
-      const uint32_t id_o = idesc_m128(64, false, true);
-      for (int w = blockIdx.x; w < total; w += gridDim.x, ++nw) {
-        mbar_wait(bar(0), (uint32_t)nw & 1u);
-        for (int i = 0; i < QT; ++i, ++qit, ++blk) {
-          const int s = qit & 1;
-          mbar_wait(bar(4 + s), ((uint32_t)qit >> 1) & 1u);
-          tc_fence_after();
-          const uint32_t qa = base + F_Q + s * TILE16K;
-          for (int c = 0; c < nkb; ++c) {
-            const int ncols = min(KV_BOX, NKP - c * KV_BOX);
-            const uint32_t id_s = idesc_m128(ncols, false, false);
-            const uint32_t ka = base + F_K + c * BOX12K;
+    const bool leader = elect_one();
+    int nw = 0, qit = 0, blk = 0;
+    const uint32_t id_o = idesc_m128(64, false, true);
+    for (int w = blockIdx.x; w < total; w += gridDim.x, ++nw) {
+      mbar_wait(bar(0), (uint32_t)nw & 1u);
+      for (int i = 0; i < QT; ++i, ++qit, ++blk) {
+        const int s = qit & 1;
+        mbar_wait(bar(4 + s), ((uint32_t)qit >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t qa = base + F_Q + s * TILE16K;
+        for (int c = 0; c < nkb; ++c) {
+          const int ncols = min(KV_BOX, NKP - c * KV_BOX);
+          const uint32_t id_s = idesc_m128(ncols, false, false);
+          const uint64_t dq = desc_k(qa), dk = desc_k(base + F_K + c * BOX12K);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem + c * KV_BOX, desc_k(qa + k * 32), desc_k(ka + k * 32), id_s, k > 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)
+            if (leader) umma_bf16(tmem + c * KV_BOX, dq + 2 * k, dk + 2 * k, id_s, k > 0 ? 1u : 0u);
+        }
+        if (leader) {
           umma_commit(bar(6 + s));
           umma_commit(bar(8));
           if (i == QT - 1) umma_commit(bar(1));
-          mbar_wait(bar(9), (uint32_t)blk & 1u);
+        }
+        __syncwarp();
+        mbar_wait(bar(9), (uint32_t)blk & 1u);
+        tc_fence_after();
+        if (i == 0) {
+          mbar_wait(bar(2), (uint32_t)nw & 1u);
           tc_fence_after();
-          if (i == 0) {
-            mbar_wait(bar(2), (uint32_t)nw & 1u);
-            tc_fence_after();
-          }
-          for (int kk = 0; kk < NKP / 16; ++kk)
-            umma_bf16(tmem + F_OCOL, desc_k(base + F_P + (kk >> 2) * TILE16K + (kk & 3) * 32), desc_mn(base + F_V + kk * 2048, TILE16K), id_o,
-                      kk > 0 ? 1u : 0u);
+        }
+        const uint64_t dp0 = desc_k(base + F_P), dv0 = desc_mn(base + F_V, TILE16K);
+        for (int kk = 0; kk < NKP / 16; ++kk) {
+          // P atom kk / 4 (16 KB apart = 1024 descriptor units), 32 B (2 units) per k step inside it; V advances 16 rows = 2048 B
+          const uint64_t dp = dp0 + (uint64_t)((kk >> 2) * (TILE16K >> 4) + (kk & 3) * 2), dv = dv0 + (uint64_t)(kk * 128);
+          if (leader) umma_bf16(tmem + F_OCOL, dp, dv, id_o, kk > 0 ? 1u : 0u);
+        }
+        if (leader) {
           umma_commit(bar(10));
           if (i == QT - 1) umma_commit(bar(3));
         }
+        __syncwarp();
       }
     }
   } else {
@@ -370,9 +391,32 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_tc_kernel(const __gri
 }
 
 // ------------------------------------------------------------------------------------------------ backward
-constexpr int B_KV = 0, B_QDO = 4 * BOX12K, B_P = B_QDO + 4 * TILE16K, B_DS = B_P + 2 * TILE16K, B_END = B_DS + 2 * TILE16K;
+// Key blocks of 64 (one swizzle atom of P / dS per block) so that the P / dS staging can be double buffered: the MMA thread
+// issues S / dP of block g+1 BEFORE dV / dK / dQ of block g, and the softmax warps work on block g+1 while the tensor pipe
+// drains block g.  tcgen05.commit covers every MMA issued before it, which orders all buffer re-use without extra barriers:
+//   sdp_full(g+1) fires after S/dP(g+1) and therefore after dV/dK/dQ(g-1), the last readers of staging buffer (g+1) & 1.
+constexpr int BKW = 64;                    // backward key block
+constexpr int BOX8K = BKW * 128;
+// staging: [P0 | dS0 | P1 | dS1 | pad]; the MN-major A operands of dV / dK span M = 128 = two 64-key atoms, so the atom after each
+// P / dS atom is read as well (its result rows 64..127 are never used): the pad keeps that read inside the allocation
+constexpr int B_KV = 0, B_QDO = 4 * BOX8K, B_STG = B_QDO + 4 * TILE16K, B_END = B_STG + 5 * TILE16K;
 constexpr int B_SMEM = B_END + 1024 + 128 + 3 * 64 * 4;
-constexpr int C_S = 0, C_DP = 96, C_DV = 192, C_DK = 256, C_DQ = 320;
+constexpr int C_S = 0, C_DP = 64, C_DV = 128, C_DK = 192, C_DQ = 256;
+
+struct BwdCursor {   // position in this CTA's flattened (sample, key block, query tile) sequence
+  int b, j, i, n, kvit;
+  __device__ __forceinline__ void advance(int QT, int KB, int nslots) {
+    ++n;
+    if (++i == QT) {
+      i = 0;
+      ++kvit;
+      if (++j == KB) {
+        j = 0;
+        b += nslots;
+      }
+    }
+  }
+};
 
 __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -387,7 +431,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_tc_kernel(const __gri
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = a.N, HD = a.H * HD_;
-  const int QT = (N + 127) / 128, KB = (N + KV_BOX - 1) / KV_BOX;
+  const int QT = (N + 127) / 128, KB = (N + BKW - 1) / BKW;
   // this CTA's head and its samples: gridDim.x is a multiple of Hk
   const int h = blockIdx.x % a.Hk, slot = blockIdx.x / a.Hk, nslots = gridDim.x / a.Hk;
 
@@ -417,9 +461,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_tc_kernel(const __gri
         for (int j = 0; j < KB; ++j, ++kvit) {
           const int ks = kvit & 1;
           mbar_wait_relaxed(bar(2 + ks), (((uint32_t)kvit >> 1) & 1u) ^ 1u);
-          mbar_expect_tx(bar(ks), 2 * BOX12K);
-          tma_load_3d(base + B_KV + ks * 2 * BOX12K, &maps.kv, bar(ks), HD + h * HD_, j * KV_BOX, b);
-          tma_load_3d(base + B_KV + ks * 2 * BOX12K + BOX12K, &maps.kv, bar(ks), 2 * HD + h * HD_, j * KV_BOX, b);
+          mbar_expect_tx(bar(ks), 2 * BOX8K);
+          tma_load_3d(base + B_KV + ks * 2 * BOX8K, &maps.kv, bar(ks), HD + h * HD_, j * BKW, b);
+          tma_load_3d(base + B_KV + ks * 2 * BOX8K + BOX8K, &maps.kv, bar(ks), 2 * HD + h * HD_, j * BKW, b);
           for (int i = 0; i < QT; ++i, ++qit) {
             const int qs = qit & 1;
             mbar_wait_relaxed(bar(6 + qs), (((uint32_t)qit >> 1) & 1u) ^ 1u);
@@ -431,155 +475,102 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_tc_kernel(const __gri
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      int kvit = 0, qit = 0, blk = 0;
-      const uint32_t id_t = idesc_m128(64, true, true);     // dV, dK: both operands MN-major
-      const uint32_t id_q = idesc_m128(64, false, true);    // dQ: A = dS K-major, B = K MN-major
-      for (int b = slot; b < a.B; b += nslots) {
-        for (int j = 0; j < KB; ++j, ++kvit) {
-          const int ks = kvit & 1;
-          mbar_wait(bar(ks), ((uint32_t)kvit >> 1) & 1u);
-          tc_fence_after();
-          const int kw = round16(min(KV_BOX, N - j * KV_BOX));
-          const uint32_t id_s = idesc_m128(kw, false, false);
-          const uint32_t ka = base + B_KV + ks * 2 * BOX12K, va = ka + BOX12K;
-          for (int i = 0; i < QT; ++i, ++qit, ++blk) {
-            const int qs = qit & 1;
-            mbar_wait(bar(4 + qs), ((uint32_t)qit >> 1) & 1u);
-            tc_fence_after();
-            const uint32_t qa = base + B_QDO + qs * 2 * TILE16K, doa = qa + TILE16K;
+    const bool leader = elect_one();
+    const uint32_t id_t = idesc_m128(64, true, true);     // dV, dK: both operands MN-major
+    const uint32_t id_q = idesc_m128(64, false, true);    // dQ: A = dS K-major, B = K MN-major
+    // S = Q_i K_j^T and dP = dO_i V_j^T of the block under cursor c (waits for its operands)
+    auto issue_sdp = [&](const BwdCursor& c) {
+      const int ks = c.kvit & 1, qs = c.n & 1;
+      if (c.i == 0) mbar_wait(bar(ks), ((uint32_t)c.kvit >> 1) & 1u);
+      mbar_wait(bar(4 + qs), ((uint32_t)c.n >> 1) & 1u);
+      tc_fence_after();
+      const int kw = round16(min(BKW, N - c.j * BKW));
+      const uint32_t id_s = idesc_m128(kw, false, false);
+      const uint32_t ka = base + B_KV + ks * 2 * BOX8K, qa = base + B_QDO + qs * 2 * TILE16K;
+      const uint64_t dq = desc_k(qa), dk = desc_k(ka), ddo = desc_k(qa + TILE16K), dv = desc_k(ka + BOX8K);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem + C_S, desc_k(qa + k * 32), desc_k(ka + k * 32), id_s, k > 0 ? 1u : 0u);
+      for (int k = 0; k < 4; ++k)
+        if (leader) umma_bf16(tmem + C_S, dq + 2 * k, dk + 2 * k, id_s, k > 0 ? 1u : 0u);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) umma_bf16(tmem + C_DP, desc_k(doa + k * 32), desc_k(va + k * 32), id_s, k > 0 ? 1u : 0u);
-            umma_commit(bar(8));
-            mbar_wait(bar(9), (uint32_t)blk & 1u);
-            tc_fence_after();
-            const int kq = (min(128, N - i * 128) + 15) / 16;     // 16-row k steps over the valid queries of this tile
-            for (int k = 0; k < kq; ++k)
-              umma_bf16(tmem + C_DV, desc_mn(base + B_P + k * 2048, TILE16K), desc_mn(doa + k * 2048, TILE16K), id_t, (i | k) != 0 ? 1u : 0u);
-            for (int k = 0; k < kq; ++k)
-              umma_bf16(tmem + C_DK, desc_mn(base + B_DS + k * 2048, TILE16K), desc_mn(qa + k * 2048, TILE16K), id_t, (i | k) != 0 ? 1u : 0u);
-            for (int kk = 0; kk < kw / 16; ++kk)
-              umma_bf16(tmem + C_DQ + 64 * i, desc_k(base + B_DS + (kk >> 2) * TILE16K + (kk & 3) * 32), desc_mn(ka + kk * 2048, TILE16K), id_q,
-                        (j | kk) != 0 ? 1u : 0u);
-            umma_commit(bar(6 + qs));
-            if (i == QT - 1) {
-              umma_commit(bar(2 + ks));
-              umma_commit(bar(10));
-              if (j == KB - 1) umma_commit(bar(11));
-            }
-          }
+      for (int k = 0; k < 4; ++k)
+        if (leader) umma_bf16(tmem + C_DP, ddo + 2 * k, dv + 2 * k, id_s, k > 0 ? 1u : 0u);
+      if (leader) umma_commit(bar(8));
+      __syncwarp();
+    };
+    BwdCursor c = {slot, 0, 0, 0, 0};
+    if (c.b < a.B) issue_sdp(c);
+    BwdCursor nx = c;
+    nx.advance(QT, KB, nslots);
+    while (c.b < a.B) {
+      mbar_wait(bar(9), (uint32_t)c.n & 1u);      // P / dS of block c staged; S / dP columns free again
+      tc_fence_after();
+      if (nx.b < a.B) issue_sdp(nx);
+      const int ks = c.kvit & 1, qs = c.n & 1;
+      const uint32_t ka = base + B_KV + ks * 2 * BOX8K, qa = base + B_QDO + qs * 2 * TILE16K;
+      const uint32_t ps = base + B_STG + (c.n & 1) * 2 * TILE16K;
+      const uint64_t d_p = desc_mn(ps, TILE16K), d_ds = desc_mn(ps + TILE16K, TILE16K), d_do = desc_mn(qa + TILE16K, TILE16K),
+                     d_q = desc_mn(qa, TILE16K), d_dsk = desc_k(ps + TILE16K), d_k = desc_mn(ka, TILE16K);
+      const int kw = round16(min(BKW, N - c.j * BKW));
+      const int kq = (min(128, N - c.i * 128) + 15) / 16;     // 16-row k steps over the valid queries of this tile
+      const uint32_t acc_i = c.i != 0 ? 1u : 0u, acc_j = c.j != 0 ? 1u : 0u;
+#pragma unroll
+      for (int k = 0; k < 8; ++k)       // a 16-row k step = 2048 B = 128 descriptor units
+        if (leader && k < kq) umma_bf16(tmem + C_DV, d_p + 128 * k, d_do + 128 * k, id_t, k > 0 ? 1u : acc_i);
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (leader && k < kq) umma_bf16(tmem + C_DK, d_ds + 128 * k, d_q + 128 * k, id_t, k > 0 ? 1u : acc_i);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+        if (leader && kk * 16 < kw) umma_bf16(tmem + C_DQ + 64 * c.i, d_dsk + 2 * kk, d_k + 128 * kk, id_q, kk > 0 ? 1u : acc_j);
+      if (leader) {
+        umma_commit(bar(6 + qs));
+        if (c.i == QT - 1) {
+          umma_commit(bar(2 + ks));
+          umma_commit(bar(10));
+          if (c.j == KB - 1) umma_commit(bar(11));
         }
       }
+      __syncwarp();
+      c = nx;
+      nx.advance(QT, KB, nslots);
     }
   } else {
     const int q = warp & 3, hf = (warp - SM_WARP0) >> 2, row = q * 32 + lane;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
-    const float c = a.scale * LOG2E_F;
+    const float c_exp = a.scale * LOG2E_F;
     const long ldq = 3L * HD;
-    uint8_t* Ps = smem + B_P;
-    uint8_t* dSs = smem + B_DS;
-    int blk = 0, nkv = 0, nb = 0;
+    int nkv = 0, nq = 0;
     zero_masked(a.dqkv, ldq, (long)a.B * N, a.Hk * HD_, (a.H - a.Hk) * HD_, 3, HD, threadIdx.x - SM_WARP0 * 32, SM_THREADS);
-    for (int b = slot; b < a.B; b += nslots, ++nb) {
-      // per-row statistics of this thread's query rows: lse in log2 units, delta = dO . O
-      float lse2[3], delta[3];
+
+    // dK_j, dV_j of (sample pb, key block pj): TMEM lane = key row of the block (rows 0..63: lane quarters 0 and 1)
+    auto epilogue_kv = [&](int pb, int pj) {
+      mbar_wait(bar(10), (uint32_t)nkv & 1u);
+      ++nkv;
+      tc_fence_after();
+      const int keys_valid = min(BKW, N - pj * BKW);
+      if (q * 32 < keys_valid) {
+        const bool kvalid = row < keys_valid;
+        bf16* dst = a.dqkv + ((long)pb * N + pj * BKW + row) * ldq + h * HD_ + hf * 32;
+        float v[32];
+        tmem_ld32(tlane + C_DV + hf * 32, v);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        lse2[i] = INFINITY, delta[i] = 0.f;      // rows >= N: P = exp2(S*c - inf) = 0 and dS = 0 (S, dP are exact zeros there)
-        const int r = i * 128 + row;
-        if (i < QT && r < N) {
-          lse2[i] = a.lse[((long)b * a.H + h) * N + r] * LOG2E_F;
-          const bf16* op = a.o + ((long)b * N + r) * HD + h * HD_;
-          const bf16* dp = a.d_o + ((long)b * N + r) * HD + h * HD_;
-          float acc = 0.f;
+        for (int t = 0; t < 32; ++t) v[t] = kvalid ? v[t] : 0.f;
+        if (kvalid) store_bf16_32(dst + 2 * HD, v);
+        if (a.dbias != nullptr) atomicAdd(cs + 128 + hf * 32 + lane, butterfly_colsum(v, lane));
+        tmem_ld32(tlane + C_DK + hf * 32, v);
+        tmem_ld_wait();
 #pragma unroll
-          for (int cc = 0; cc < HD_; cc += 8) {
-            const uint4 ov = *reinterpret_cast<const uint4*>(op + cc);
-            const uint4 dv = *reinterpret_cast<const uint4*>(dp + cc);
-            const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[t]));
-              const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[t]));
-              acc += x.x * y.x + x.y * y.y;
-            }
-          }
-          delta[i] = acc;
-        }
+        for (int t = 0; t < 32; ++t) v[t] = kvalid ? v[t] * a.scale : 0.f;
+        if (kvalid) store_bf16_32(dst + HD, v);
+        if (a.dbias != nullptr) atomicAdd(cs + 64 + hf * 32 + lane, butterfly_colsum(v, lane));
       }
-      for (int j = 0; j < KB; ++j) {
-        const int keys_valid = min(KV_BOX, N - j * KV_BOX);
-        const int kw = round16(keys_valid);
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          if (i < QT) {
-            const int rows_valid = min(128, N - i * 128);
-            const bool active = q * 32 < round16(rows_valid);
-            mbar_wait(bar(8), (uint32_t)blk & 1u);
-            tc_fence_after();
-            if (active) {
-              // the two warps of a lane quarter split the kw columns in 16-column units: [0, kh) and [kh, kw)
-              const int kh = round16(kw >> 1);
-              const int c0 = hf == 0 ? 0 : kh, c1 = hf == 0 ? kh : kw;
-              for (int col = c0; col < c1; col += 16) {
-                float s[16], dp[16];
-                tmem_ld16(tlane + C_S + col, s);
-                tmem_ld16(tlane + C_DP + col, dp);
-                tmem_ld_wait();
-                if (col + 16 <= keys_valid) {
-#pragma unroll
-                  for (int t = 0; t < 16; ++t) {
-                    s[t] = ex2(fmaf(s[t], c, -lse2[i]));
-                    dp[t] = s[t] * (dp[t] - delta[i]);
-                  }
-                } else {
-#pragma unroll
-                  for (int t = 0; t < 16; ++t) {
-                    const bool ok = col + t < keys_valid;
-                    const float p = ok ? ex2(fmaf(s[t], c, -lse2[i])) : 0.f;
-                    s[t] = p;
-                    dp[t] = ok ? p * (dp[t] - delta[i]) : 0.f;
-                  }
-                }
-                stage_bf16_16(Ps, row, col, s);
-                stage_bf16_16(dSs, row, col, dp);
-              }
-            }
-            fence_proxy_async();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar(9));
-            ++blk;
-          }
-        }
-        // dK_j, dV_j: TMEM lane = key row of this block
-        mbar_wait(bar(10), (uint32_t)nkv & 1u);
-        ++nkv;
-        tc_fence_after();
-        if (q * 32 < kw) {
-          const int key = j * KV_BOX + row;
-          const bool kvalid = row < keys_valid;
-          bf16* dst = a.dqkv + ((long)b * N + key) * ldq + h * HD_ + hf * 32;
-          float v[32];
-          tmem_ld32(tlane + C_DV + hf * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int t = 0; t < 32; ++t) v[t] = kvalid ? v[t] : 0.f;
-          if (kvalid) store_bf16_32(dst + 2 * HD, v);
-          if (a.dbias != nullptr) atomicAdd(cs + 128 + hf * 32 + lane, butterfly_colsum(v, lane));
-          tmem_ld32(tlane + C_DK + hf * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int t = 0; t < 32; ++t) v[t] = kvalid ? v[t] * a.scale : 0.f;
-          if (kvalid) store_bf16_32(dst + HD, v);
-          if (a.dbias != nullptr) atomicAdd(cs + 64 + hf * 32 + lane, butterfly_colsum(v, lane));
-        }
-        tc_fence_before();
-      }
-      // dQ: all query tiles are complete after the last key block
-      mbar_wait(bar(11), (uint32_t)nb & 1u);
+      tc_fence_before();
+    };
+    // dQ of sample pb: all query tiles are complete after the last key block
+    auto epilogue_q = [&](int pb) {
+      mbar_wait(bar(11), (uint32_t)nq & 1u);
+      ++nq;
       tc_fence_after();
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
@@ -592,13 +583,106 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_tc_kernel(const __gri
             tmem_ld_wait();
 #pragma unroll
             for (int t = 0; t < 32; ++t) v[t] = rv ? v[t] * a.scale : 0.f;
-            if (rv) store_bf16_32(a.dqkv + ((long)b * N + i * 128 + row) * ldq + h * HD_ + hf * 32, v);
+            if (rv) store_bf16_32(a.dqkv + ((long)pb * N + i * 128 + row) * ldq + h * HD_ + hf * 32, v);
             if (a.dbias != nullptr) atomicAdd(cs + hf * 32 + lane, butterfly_colsum(v, lane));
           }
         }
       }
       tc_fence_before();
+    };
+
+    BwdCursor c = {slot, 0, 0, 0, 0};
+    bool pend_kv = false, pend_q = false;
+    int pkv_b = 0, pkv_j = 0, pq_b = 0;
+    float lse2[3] = {INFINITY, INFINITY, INFINITY}, delta[3] = {0.f, 0.f, 0.f};
+    while (c.b < a.B) {
+      if (c.j == 0 && c.i == 0) {
+        // per-row statistics of this thread's query rows: lse in log2 units, delta = dO . O.
+        // rows >= N: lse = +inf, so P = exp2(S*c - inf) = 0 and dS = 0 (S and dP are exact zeros there: TMA zero fill)
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          lse2[i] = INFINITY, delta[i] = 0.f;
+          const int r = i * 128 + row;
+          if (i < QT && r < N) {
+            lse2[i] = a.lse[((long)c.b * a.H + h) * N + r] * LOG2E_F;
+            const bf16* op = a.o + ((long)c.b * N + r) * HD + h * HD_;
+            const bf16* dp = a.d_o + ((long)c.b * N + r) * HD + h * HD_;
+            float acc = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < HD_; cc += 8) {
+              const uint4 ov = *reinterpret_cast<const uint4*>(op + cc);
+              const uint4 dv = *reinterpret_cast<const uint4*>(dp + cc);
+              const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[t]));
+                const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[t]));
+                acc += x.x * y.x + x.y * y.y;
+              }
+            }
+            delta[i] = acc;
+          }
+        }
+      }
+      const int keys_valid = min(BKW, N - c.j * BKW);
+      const int kw = round16(keys_valid);
+      const int rows_valid = min(128, N - c.i * 128);
+      const bool active = q * 32 < round16(rows_valid);
+      const float my_lse = c.i == 0 ? lse2[0] : (c.i == 1 ? lse2[1] : lse2[2]);
+      const float my_delta = c.i == 0 ? delta[0] : (c.i == 1 ? delta[1] : delta[2]);
+      uint8_t* Ps = smem + B_STG + (c.n & 1) * 2 * TILE16K;
+      uint8_t* dSs = Ps + TILE16K;
+      mbar_wait(bar(8), (uint32_t)c.n & 1u);
+      tc_fence_after();
+      if (active) {
+        // the two warps of a lane quarter split the kw columns in 16-column units: [0, kh) and [kh, kw)
+        const int kh = round16(kw >> 1);
+        const int c0 = hf == 0 ? 0 : kh, c1 = hf == 0 ? kh : kw;
+        for (int col = c0; col < c1; col += 16) {
+          float s[16], dp[16];
+          tmem_ld16(tlane + C_S + col, s);
+          tmem_ld16(tlane + C_DP + col, dp);
+          tmem_ld_wait();
+          if (col + 16 <= keys_valid) {
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              s[t] = ex2(fmaf(s[t], c_exp, -my_lse));
+              dp[t] = s[t] * (dp[t] - my_delta);
+            }
+          } else {
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+              const bool ok = col + t < keys_valid;
+              const float p = ok ? ex2(fmaf(s[t], c_exp, -my_lse)) : 0.f;
+              s[t] = p;
+              dp[t] = ok ? p * (dp[t] - my_delta) : 0.f;
+            }
+          }
+          stage_bf16_16(Ps, row, col, s);
+          stage_bf16_16(dSs, row, col, dp);
+        }
+      }
+      // results of earlier blocks that this block's MMAs are about to overwrite in tensor memory
+      if (c.i == 0 && pend_kv) {
+        epilogue_kv(pkv_b, pkv_j);
+        pend_kv = false;
+      }
+      if (c.i == 0 && c.j == 0 && pend_q) {
+        epilogue_q(pq_b);
+        pend_q = false;
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(9));
+      if (c.i == QT - 1) {
+        pend_kv = true, pkv_b = c.b, pkv_j = c.j;
+        if (c.j == KB - 1) pend_q = true, pq_b = c.b;
+      }
+      c.advance(QT, KB, nslots);
     }
+    if (pend_kv) epilogue_kv(pkv_b, pkv_j);
+    if (pend_q) epilogue_q(pq_b);
     if (a.dbias != nullptr) {
       named_bar_sync(1, SM_THREADS);
       const int t = threadIdx.x - SM_WARP0 * 32;
@@ -662,7 +746,7 @@ int attn_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* ls
   if (Hk == 0) return zero_cols(dqkv, 3 * HD, (long)B * N, 0, 3 * HD, st, "vsx_attn_bwd");
   AttnMaps maps;
   if ((rc = make_tmap_3d(&maps.q, qkv, 3 * HD, N, B, 3 * HD, (uint64_t)N * 3 * HD, 64, 128))) return rc;
-  if ((rc = make_tmap_3d(&maps.kv, qkv, 3 * HD, N, B, 3 * HD, (uint64_t)N * 3 * HD, 64, KV_BOX))) return rc;
+  if ((rc = make_tmap_3d(&maps.kv, qkv, 3 * HD, N, B, 3 * HD, (uint64_t)N * 3 * HD, 64, BKW))) return rc;
   if ((rc = make_tmap_3d(&maps.d_o, d_o, HD, N, B, HD, (uint64_t)N * HD, 64, 128))) return rc;
   static bool configured = false;
   if (!configured) {
