@@ -131,6 +131,8 @@ int vsx_attn_fwd(const void* qkv, void* o, float* lse, int dtype, int batch, int
 int vsx_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int dtype, int batch,
                  int tokens, int heads, int head_dim, int heads_keep, float scale, int impl,
                  float* dbias /* NULL, or [3*heads*head_dim]: += column sums of dqkv (the qkv bias gradient) */, void* stream);
+/* Development aid: device buffer of 64 x 8 int64 clock stamps written by CTA 0 of the tcgen05 backward kernel (NULL = off). */
+int vsx_attn_debug_buffer(void* buffer);
 
 /* ----------------------------------------------------------------------------------------------------
  * Elementwise helpers around the GEMMs.

@@ -15,6 +15,7 @@ int attn_fwd_tc(const void* qkv, void* o, float* lse, int B, int N, int H, int H
 int attn_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int N, int H, int Hk, float scale,
                 float* dbias, cudaStream_t st);
 bool attn_tc_supported(int N, int D);
+void attn_set_debug(long long* p);
 }  // namespace vsx
 
 using namespace vsx;
@@ -70,4 +71,10 @@ extern "C" int vsx_attn_bwd(const void* qkv, const void* o, const void* d_o, con
   }
   set_error("vsx_attn_bwd: bad dtype %d", dtype);
   return VSX_ERR_ARG;
+}
+
+/* Development aid (tools/attn_timeline.py): device buffer of 64 x 8 clock64 stamps written by CTA 0 of the tcgen05 backward kernel. */
+extern "C" int vsx_attn_debug_buffer(void* p) {
+  attn_set_debug(static_cast<long long*>(p));
+  return VSX_OK;
 }

@@ -54,6 +54,7 @@ struct AttnArgs {
   float* lse;          // fwd: written; bwd: read
   bf16* dqkv;          // bwd
   float* dbias;        // bwd, may be null
+  long long* dbg;      // optional timeline buffer (tools/attn_timeline.py); null in production
 };
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
@@ -395,16 +396,26 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_tc_kernel(const __gri
 // issues S / dP of block g+1 BEFORE dV / dK / dQ of block g, and the softmax warps work on block g+1 while the tensor pipe
 // drains block g.  tcgen05.commit covers every MMA issued before it, which orders all buffer re-use without extra barriers:
 //   sdp_full(g+1) fires after S/dP(g+1) and therefore after dV/dK/dQ(g-1), the last readers of staging buffer (g+1) & 1.
+// dV and dK come from ONE MMA chain per block: A = [P^T ; dS^T] (M = 128: the staging atoms P | dS are 16 KB apart = the MN-major
+// leading-dimension offset) times B = [Q | dO] (N = 128: the two tiles of a slot, again 16 KB apart):
+//   D[0..63, 64..127] = P^T dO = dV,   D[64..127, 0..63] = dS^T Q = dK   (the other two quadrants are by-products)
+// -- half the shared-memory operand traffic of two M=128 chains whose upper 64 rows would be padding.
+// Four extra warps own everything that is not on the per-block critical path: the per-row statistics (lse, delta = dO . O) of the
+// NEXT pair (global loads -> shared memory) and the dK / dV / dQ epilogues (TMEM -> bf16 -> global, bias-gradient column sums).
 constexpr int BKW = 64;                    // backward key block
 constexpr int BOX8K = BKW * 128;
-// staging: [P0 | dS0 | P1 | dS1 | pad]; the MN-major A operands of dV / dK span M = 128 = two 64-key atoms, so the atom after each
-// P / dS atom is read as well (its result rows 64..127 are never used): the pad keeps that read inside the allocation
-constexpr int B_KV = 0, B_QDO = 4 * BOX8K, B_STG = B_QDO + 4 * TILE16K, B_END = B_STG + 5 * TILE16K;
-constexpr int B_SMEM = B_END + 1024 + 128 + 3 * 64 * 4;
-constexpr int C_S = 0, C_DP = 64, C_DV = 128, C_DK = 192, C_DQ = 256;
+constexpr int BWD_THREADS = 448;           // 14 warps: producer, MMA, 8 softmax, 4 epilogue
+constexpr int EP_WARP0 = 10;
+// staging: [P0 | dS0 | P1 | dS1]
+constexpr int B_KV = 0, B_QDO = 4 * BOX8K, B_STG = B_QDO + 6 * TILE16K, B_END = B_STG + 4 * TILE16K;
+constexpr int B_MISC = 128 /*barriers*/ + 3 * 64 * 4 /*cs*/ + 2 * 3 * 128 * 8 /*stats*/ + 16 /*tmem slot*/;
+constexpr int B_SMEM = B_END + 1024 + B_MISC;
+constexpr int C_S = 0, C_DP = 64, C_DVK = 128, C_DQ = 256;
 
+// Q_i / dO_i tiles stay resident for all key blocks of their (sample, head): three 32 KB slots used as a ring over the global
+// tile counter t = (pairs done) * QT + i, loaded once per pair (at j == 0) and released after the last key block.
 struct BwdCursor {   // position in this CTA's flattened (sample, key block, query tile) sequence
-  int b, j, i, n, kvit;
+  int b, j, i, n, kvit, t0, pair;   // t0 = global tile counter of query tile 0 of the current pair
   __device__ __forceinline__ void advance(int QT, int KB, int nslots) {
     ++n;
     if (++i == QT) {
@@ -413,21 +424,27 @@ struct BwdCursor {   // position in this CTA's flattened (sample, key block, que
       if (++j == KB) {
         j = 0;
         b += nslots;
+        t0 += QT;
+        ++pair;
       }
     }
   }
+  __device__ __forceinline__ int tile() const { return t0 + i; }
 };
 
-__global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
+__global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - raw);
   const uint32_t bar0 = base + B_END;
-  // barriers: 0-1 kv_full, 2-3 kv_empty, 4-5 q_full, 6-7 q_empty, 8 sdp_full, 9 pds_ready, 10 dkv_full, 11 dq_full
   auto bar = [&](int i) { return bar0 + 8u * i; };
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + B_END + 104);
-  float* cs = reinterpret_cast<float*>(smem + B_END + 128);   // [3][64] column sums of dQ, dK, dV (this CTA's head)
+  // barriers: 0-1 kv_full, 2-3 kv_empty, 4-6 q_full, 7-9 q_empty
+  constexpr int BAR_SDP = 10, BAR_PDS = 11, BAR_DKV_FULL = 12, BAR_DKV_EMPTY = 13, BAR_DQ_FULL = 14, BAR_DQ_EMPTY = 15;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + B_END + 128 + 768 + 6144);
+  // stats are handed over with named barriers (ids 2, 3: one per buffer): epilogue warps arrive, softmax warps sync
+  float* cs = reinterpret_cast<float*>(smem + B_END + 128);        // [3][64] column sums of dQ, dK, dV (this CTA's head)
+  float2* stats = reinterpret_cast<float2*>(smem + B_END + 128 + 768);   // [2 buffers][3 tiles][128 rows] (lse * log2e, delta)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = a.N, HD = a.H * HD_;
@@ -442,7 +459,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_tc_kernel(const __gri
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < 12; ++i) mbar_init(bar(i), i == 9 ? 8 : 1);
+      for (int i = 0; i < 16; ++i) mbar_init(bar(i), i == BAR_PDS ? 8 : (i == BAR_DKV_EMPTY || i == BAR_DQ_EMPTY) ? 4 : 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -464,25 +481,27 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_tc_kernel(const __gri
           mbar_expect_tx(bar(ks), 2 * BOX8K);
           tma_load_3d(base + B_KV + ks * 2 * BOX8K, &maps.kv, bar(ks), HD + h * HD_, j * BKW, b);
           tma_load_3d(base + B_KV + ks * 2 * BOX8K + BOX8K, &maps.kv, bar(ks), 2 * HD + h * HD_, j * BKW, b);
-          for (int i = 0; i < QT; ++i, ++qit) {
-            const int qs = qit & 1;
-            mbar_wait_relaxed(bar(6 + qs), (((uint32_t)qit >> 1) & 1u) ^ 1u);
-            mbar_expect_tx(bar(4 + qs), 2 * TILE16K);
-            tma_load_3d(base + B_QDO + qs * 2 * TILE16K, &maps.q, bar(4 + qs), h * HD_, i * 128, b);
-            tma_load_3d(base + B_QDO + qs * 2 * TILE16K + TILE16K, &maps.d_o, bar(4 + qs), h * HD_, i * 128, b);
+          if (j == 0) {
+            for (int i = 0; i < QT; ++i, ++qit) {
+              const int qs = qit % 3;
+              mbar_wait_relaxed(bar(7 + qs), (((uint32_t)qit / 3) & 1u) ^ 1u);
+              mbar_expect_tx(bar(4 + qs), 2 * TILE16K);
+              tma_load_3d(base + B_QDO + qs * 2 * TILE16K, &maps.q, bar(4 + qs), h * HD_, i * 128, b);
+              tma_load_3d(base + B_QDO + qs * 2 * TILE16K + TILE16K, &maps.d_o, bar(4 + qs), h * HD_, i * 128, b);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     const bool leader = elect_one();
-    const uint32_t id_t = idesc_m128(64, true, true);     // dV, dK: both operands MN-major
+    const uint32_t id_vk = idesc_m128(128, true, true);   // [dV | dK] chain: both operands MN-major, N = 128
     const uint32_t id_q = idesc_m128(64, false, true);    // dQ: A = dS K-major, B = K MN-major
     // S = Q_i K_j^T and dP = dO_i V_j^T of the block under cursor c (waits for its operands)
     auto issue_sdp = [&](const BwdCursor& c) {
-      const int ks = c.kvit & 1, qs = c.n & 1;
+      const int ks = c.kvit & 1, qs = c.tile() % 3;
       if (c.i == 0) mbar_wait(bar(ks), ((uint32_t)c.kvit >> 1) & 1u);
-      mbar_wait(bar(4 + qs), ((uint32_t)c.n >> 1) & 1u);
+      if (c.j == 0) mbar_wait(bar(4 + qs), ((uint32_t)c.tile() / 3) & 1u);
       tc_fence_after();
       const int kw = round16(min(BKW, N - c.j * BKW));
       const uint32_t id_s = idesc_m128(kw, false, false);
@@ -494,134 +513,65 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_tc_kernel(const __gri
 #pragma unroll
       for (int k = 0; k < 4; ++k)
         if (leader) umma_bf16(tmem + C_DP, ddo + 2 * k, dv + 2 * k, id_s, k > 0 ? 1u : 0u);
-      if (leader) umma_commit(bar(8));
+      if (leader) umma_commit(bar(BAR_SDP));
       __syncwarp();
     };
-    BwdCursor c = {slot, 0, 0, 0, 0};
+    BwdCursor c = {slot, 0, 0, 0, 0, 0, 0};
     if (c.b < a.B) issue_sdp(c);
     BwdCursor nx = c;
     nx.advance(QT, KB, nslots);
     while (c.b < a.B) {
-      mbar_wait(bar(9), (uint32_t)c.n & 1u);      // P / dS of block c staged; S / dP columns free again
+      mbar_wait(bar(BAR_PDS), (uint32_t)c.n & 1u);      // P / dS of block c staged; S / dP columns free again
       tc_fence_after();
+      if (a.dbg != nullptr && blockIdx.x == 0 && leader && c.n < 64) a.dbg[c.n * 8 + 0] = clock64();
       if (nx.b < a.B) issue_sdp(nx);
-      const int ks = c.kvit & 1, qs = c.n & 1;
+      if (a.dbg != nullptr && blockIdx.x == 0 && leader && c.n < 64) a.dbg[c.n * 8 + 1] = clock64();
+      // accumulators about to be overwritten (first block of a key block / of a pair) must have been drained by the epilogue warps
+      if (c.i == 0) mbar_wait(bar(BAR_DKV_EMPTY), ((uint32_t)c.kvit & 1u) ^ 1u);
+      if (c.i == 0 && c.j == 0) mbar_wait(bar(BAR_DQ_EMPTY), ((uint32_t)c.pair & 1u) ^ 1u);
+      tc_fence_after();
+      const int ks = c.kvit & 1, qs = c.tile() % 3;
       const uint32_t ka = base + B_KV + ks * 2 * BOX8K, qa = base + B_QDO + qs * 2 * TILE16K;
       const uint32_t ps = base + B_STG + (c.n & 1) * 2 * TILE16K;
-      const uint64_t d_p = desc_mn(ps, TILE16K), d_ds = desc_mn(ps + TILE16K, TILE16K), d_do = desc_mn(qa + TILE16K, TILE16K),
-                     d_q = desc_mn(qa, TILE16K), d_dsk = desc_k(ps + TILE16K), d_k = desc_mn(ka, TILE16K);
+      const uint64_t d_pds = desc_mn(ps, TILE16K), d_qdo = desc_mn(qa, TILE16K), d_dsk = desc_k(ps + TILE16K), d_k = desc_mn(ka, TILE16K);
       const int kw = round16(min(BKW, N - c.j * BKW));
       const int kq = (min(128, N - c.i * 128) + 15) / 16;     // 16-row k steps over the valid queries of this tile
       const uint32_t acc_i = c.i != 0 ? 1u : 0u, acc_j = c.j != 0 ? 1u : 0u;
 #pragma unroll
       for (int k = 0; k < 8; ++k)       // a 16-row k step = 2048 B = 128 descriptor units
-        if (leader && k < kq) umma_bf16(tmem + C_DV, d_p + 128 * k, d_do + 128 * k, id_t, k > 0 ? 1u : acc_i);
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        if (leader && k < kq) umma_bf16(tmem + C_DK, d_ds + 128 * k, d_q + 128 * k, id_t, k > 0 ? 1u : acc_i);
+        if (leader && k < kq) umma_bf16(tmem + C_DVK, d_pds + 128 * k, d_qdo + 128 * k, id_vk, k > 0 ? 1u : acc_i);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
         if (leader && kk * 16 < kw) umma_bf16(tmem + C_DQ + 64 * c.i, d_dsk + 2 * kk, d_k + 128 * kk, id_q, kk > 0 ? 1u : acc_j);
       if (leader) {
-        umma_commit(bar(6 + qs));
+        if (c.j == KB - 1) umma_commit(bar(7 + qs));     // last key block: this query tile's slot may be reloaded
         if (c.i == QT - 1) {
           umma_commit(bar(2 + ks));
-          umma_commit(bar(10));
-          if (c.j == KB - 1) umma_commit(bar(11));
+          umma_commit(bar(BAR_DKV_FULL));
+          if (c.j == KB - 1) umma_commit(bar(BAR_DQ_FULL));
         }
       }
       __syncwarp();
+      if (a.dbg != nullptr && blockIdx.x == 0 && leader && c.n < 64) a.dbg[c.n * 8 + 2] = clock64();
       c = nx;
       nx.advance(QT, KB, nslots);
     }
-  } else {
+  } else if (warp < EP_WARP0) {
+    // ---------------- softmax warps: P = exp2(S*c - lse), dS = P o (dP - delta) -> bf16 staging ----------------
     const int q = warp & 3, hf = (warp - SM_WARP0) >> 2, row = q * 32 + lane;
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
     const float c_exp = a.scale * LOG2E_F;
-    const long ldq = 3L * HD;
-    int nkv = 0, nq = 0;
-    zero_masked(a.dqkv, ldq, (long)a.B * N, a.Hk * HD_, (a.H - a.Hk) * HD_, 3, HD, threadIdx.x - SM_WARP0 * 32, SM_THREADS);
-
-    // dK_j, dV_j of (sample pb, key block pj): TMEM lane = key row of the block (rows 0..63: lane quarters 0 and 1)
-    auto epilogue_kv = [&](int pb, int pj) {
-      mbar_wait(bar(10), (uint32_t)nkv & 1u);
-      ++nkv;
-      tc_fence_after();
-      const int keys_valid = min(BKW, N - pj * BKW);
-      if (q * 32 < keys_valid) {
-        const bool kvalid = row < keys_valid;
-        bf16* dst = a.dqkv + ((long)pb * N + pj * BKW + row) * ldq + h * HD_ + hf * 32;
-        float v[32];
-        tmem_ld32(tlane + C_DV + hf * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int t = 0; t < 32; ++t) v[t] = kvalid ? v[t] : 0.f;
-        if (kvalid) store_bf16_32(dst + 2 * HD, v);
-        if (a.dbias != nullptr) atomicAdd(cs + 128 + hf * 32 + lane, butterfly_colsum(v, lane));
-        tmem_ld32(tlane + C_DK + hf * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int t = 0; t < 32; ++t) v[t] = kvalid ? v[t] * a.scale : 0.f;
-        if (kvalid) store_bf16_32(dst + HD, v);
-        if (a.dbias != nullptr) atomicAdd(cs + 64 + hf * 32 + lane, butterfly_colsum(v, lane));
-      }
-      tc_fence_before();
-    };
-    // dQ of sample pb: all query tiles are complete after the last key block
-    auto epilogue_q = [&](int pb) {
-      mbar_wait(bar(11), (uint32_t)nq & 1u);
-      ++nq;
-      tc_fence_after();
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        if (i < QT) {
-          const int rows_valid = min(128, N - i * 128);
-          if (q * 32 < rows_valid) {
-            const bool rv = row < rows_valid;
-            float v[32];
-            tmem_ld32(tlane + C_DQ + 64 * i + hf * 32, v);
-            tmem_ld_wait();
-#pragma unroll
-            for (int t = 0; t < 32; ++t) v[t] = rv ? v[t] * a.scale : 0.f;
-            if (rv) store_bf16_32(a.dqkv + ((long)pb * N + i * 128 + row) * ldq + h * HD_ + hf * 32, v);
-            if (a.dbias != nullptr) atomicAdd(cs + hf * 32 + lane, butterfly_colsum(v, lane));
-          }
-        }
-      }
-      tc_fence_before();
-    };
-
-    BwdCursor c = {slot, 0, 0, 0, 0};
-    bool pend_kv = false, pend_q = false;
-    int pkv_b = 0, pkv_j = 0, pq_b = 0;
+    BwdCursor c = {slot, 0, 0, 0, 0, 0, 0};
     float lse2[3] = {INFINITY, INFINITY, INFINITY}, delta[3] = {0.f, 0.f, 0.f};
     while (c.b < a.B) {
       if (c.j == 0 && c.i == 0) {
-        // per-row statistics of this thread's query rows: lse in log2 units, delta = dO . O.
-        // rows >= N: lse = +inf, so P = exp2(S*c - inf) = 0 and dS = 0 (S and dP are exact zeros there: TMA zero fill)
+        // statistics of this pair, produced by the epilogue warps one pair ahead
+        named_bar_sync(2 + (c.pair & 1), SM_THREADS + 128);
+        const float2* st = stats + (c.pair & 1) * 3 * 128;
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          lse2[i] = INFINITY, delta[i] = 0.f;
-          const int r = i * 128 + row;
-          if (i < QT && r < N) {
-            lse2[i] = a.lse[((long)c.b * a.H + h) * N + r] * LOG2E_F;
-            const bf16* op = a.o + ((long)c.b * N + r) * HD + h * HD_;
-            const bf16* dp = a.d_o + ((long)c.b * N + r) * HD + h * HD_;
-            float acc = 0.f;
-#pragma unroll
-            for (int cc = 0; cc < HD_; cc += 8) {
-              const uint4 ov = *reinterpret_cast<const uint4*>(op + cc);
-              const uint4 dv = *reinterpret_cast<const uint4*>(dp + cc);
-              const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[t]));
-                const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[t]));
-                acc += x.x * y.x + x.y * y.y;
-              }
-            }
-            delta[i] = acc;
-          }
+          const float2 v = st[i * 128 + row];
+          lse2[i] = v.x, delta[i] = v.y;
         }
       }
       const int keys_valid = min(BKW, N - c.j * BKW);
@@ -632,24 +582,45 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_tc_kernel(const __gri
       const float my_delta = c.i == 0 ? delta[0] : (c.i == 1 ? delta[1] : delta[2]);
       uint8_t* Ps = smem + B_STG + (c.n & 1) * 2 * TILE16K;
       uint8_t* dSs = Ps + TILE16K;
-      mbar_wait(bar(8), (uint32_t)c.n & 1u);
+      const bool stamp = a.dbg != nullptr && blockIdx.x == 0 && warp == SM_WARP0 + 2 && lane == 0 && c.n < 64;   // warp 4: lane quarter 0
+      if (stamp) a.dbg[c.n * 8 + 3] = clock64();
+      mbar_wait(bar(BAR_SDP), (uint32_t)c.n & 1u);
       tc_fence_after();
+      if (stamp) a.dbg[c.n * 8 + 4] = clock64();
       if (active) {
-        // the two warps of a lane quarter split the kw columns in 16-column units: [0, kh) and [kh, kw)
-        const int kh = round16(kw >> 1);
-        const int c0 = hf == 0 ? 0 : kh, c1 = hf == 0 ? kh : kw;
-        for (int col = c0; col < c1; col += 16) {
-          float s[16], dp[16];
-          tmem_ld16(tlane + C_S + col, s);
-          tmem_ld16(tlane + C_DP + col, dp);
+        if (kw == BKW) {
+          // full block: each warp of the lane quarter takes 32 columns; both TMEM loads are in flight before the first use
+          const int col = hf * 32;
+          float s[32], dp[32];
+          tmem_ld32(tlane + C_S + col, s);
+          tmem_ld32(tlane + C_DP + col, dp);
           tmem_ld_wait();
-          if (col + 16 <= keys_valid) {
+          if (col + 32 <= keys_valid) {
 #pragma unroll
-            for (int t = 0; t < 16; ++t) {
+            for (int t = 0; t < 32; ++t) {
               s[t] = ex2(fmaf(s[t], c_exp, -my_lse));
               dp[t] = s[t] * (dp[t] - my_delta);
             }
           } else {
+#pragma unroll
+            for (int t = 0; t < 32; ++t) {
+              const bool ok = col + t < keys_valid;
+              const float p = ok ? ex2(fmaf(s[t], c_exp, -my_lse)) : 0.f;
+              s[t] = p;
+              dp[t] = ok ? p * (dp[t] - my_delta) : 0.f;
+            }
+          }
+          stage_bf16_32(Ps, row, col, s);
+          stage_bf16_32(dSs, row, col, dp);
+        } else {
+          // partial block: the two warps split the kw columns in 16-column units: [0, kh) and [kh, kw)
+          const int kh = round16(kw >> 1);
+          const int c0 = hf == 0 ? 0 : kh, c1 = hf == 0 ? kh : kw;
+          for (int col = c0; col < c1; col += 16) {
+            float s[16], dp[16];
+            tmem_ld16(tlane + C_S + col, s);
+            tmem_ld16(tlane + C_DP + col, dp);
+            tmem_ld_wait();
 #pragma unroll
             for (int t = 0; t < 16; ++t) {
               const bool ok = col + t < keys_valid;
@@ -657,36 +628,136 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_bwd_tc_kernel(const __gri
               s[t] = p;
               dp[t] = ok ? p * (dp[t] - my_delta) : 0.f;
             }
+            stage_bf16_16(Ps, row, col, s);
+            stage_bf16_16(dSs, row, col, dp);
           }
-          stage_bf16_16(Ps, row, col, s);
-          stage_bf16_16(dSs, row, col, dp);
         }
       }
-      // results of earlier blocks that this block's MMAs are about to overwrite in tensor memory
-      if (c.i == 0 && pend_kv) {
-        epilogue_kv(pkv_b, pkv_j);
-        pend_kv = false;
-      }
-      if (c.i == 0 && c.j == 0 && pend_q) {
-        epilogue_q(pq_b);
-        pend_q = false;
-      }
+      if (stamp) a.dbg[c.n * 8 + 5] = clock64();
       fence_proxy_async();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(9));
-      if (c.i == QT - 1) {
-        pend_kv = true, pkv_b = c.b, pkv_j = c.j;
-        if (c.j == KB - 1) pend_q = true, pq_b = c.b;
-      }
+      if (lane == 0) mbar_arrive(bar(BAR_PDS));
+      if (stamp) a.dbg[c.n * 8 + 6] = clock64();
       c.advance(QT, KB, nslots);
     }
-    if (pend_kv) epilogue_kv(pkv_b, pkv_j);
-    if (pend_q) epilogue_q(pq_b);
+  } else {
+    // ---------------- epilogue warps: statistics of the next pair, dK / dV / dQ -> global, bias-gradient column sums ----------------
+    const int q = warp & 3, row = q * 32 + lane, et = threadIdx.x - EP_WARP0 * 32;   // et = 0..127
+    const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
+    const long ldq = 3L * HD;
+    zero_masked(a.dqkv, ldq, (long)a.B * N, a.Hk * HD_, (a.H - a.Hk) * HD_, 3, HD, et, 128);
+    // lse (log2 units) and delta = dO . O of sample b's query rows -> stats buffer; rows >= N get lse = +inf, so P = exp2(S*c - inf) = 0
+    // and dS = 0 there (S and dP are exact zeros on those rows: TMA zero fill)
+    auto make_stats = [&](int b, int buf) {
+      float2* st = stats + buf * 3 * 128;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        float2 v = make_float2(INFINITY, 0.f);
+        const int r = i * 128 + et;
+        if (i < QT && r < N) {
+          v.x = a.lse[((long)b * a.H + h) * N + r] * LOG2E_F;
+          const bf16* op = a.o + ((long)b * N + r) * HD + h * HD_;
+          const bf16* dp = a.d_o + ((long)b * N + r) * HD + h * HD_;
+          float acc = 0.f;
+#pragma unroll
+          for (int cc = 0; cc < HD_; cc += 8) {
+            const uint4 ov = *reinterpret_cast<const uint4*>(op + cc);
+            const uint4 dv = *reinterpret_cast<const uint4*>(dp + cc);
+            const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[t]));
+              const float2 y = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&dw[t]));
+              acc += x.x * y.x + x.y * y.y;
+            }
+          }
+          v.y = acc;
+        }
+        st[i * 128 + et] = v;
+      }
+      // hand-over: the 8 softmax warps bar.sync on the same id; buffer `buf` was last read two pairs ago (program order of the
+      // softmax warps guarantees they passed that read long before they can reach this barrier again)
+      asm volatile("bar.arrive %0, %1;" ::"r"(2 + buf), "r"(SM_THREADS + 128) : "memory");
+    };
+    int nkv = 0, pair = 0;
+    const bool is_v = q < 2;          // lanes 0..63 hold dV (columns 64..127), lanes 64..127 hold dK (columns 0..63)
+    const int krow = row & 63;
+    const float kv_mul = is_v ? 1.0f : a.scale;
+    if (slot < a.B) make_stats(slot, 0);
+    for (int b = slot; b < a.B; b += nslots, ++pair) {
+      if (b + nslots < a.B) make_stats(b + nslots, (pair + 1) & 1);
+      float csum[2][32];              // this thread's rows, summed over the key blocks of the pair: the butterfly runs once per pair
+#pragma unroll
+      for (int t = 0; t < 32; ++t) csum[0][t] = 0.f, csum[1][t] = 0.f;
+      for (int j = 0; j < KB; ++j, ++nkv) {
+        mbar_wait(bar(BAR_DKV_FULL), (uint32_t)nkv & 1u);
+        tc_fence_after();
+        const int keys_valid = min(BKW, N - j * BKW);
+        if ((q & 1) * 32 < keys_valid) {
+          const bool kvalid = krow < keys_valid;
+          bf16* dst = a.dqkv + ((long)b * N + j * BKW + krow) * ldq + (is_v ? 2 * HD : HD) + h * HD_;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float v[32];
+            tmem_ld32(tlane + C_DVK + (is_v ? 64 : 0) + half * 32, v);
+            tmem_ld_wait();
+            if (kvalid) {
+#pragma unroll
+              for (int t = 0; t < 32; ++t) {
+                v[t] *= kv_mul;
+                csum[half][t] += v[t];
+              }
+              store_bf16_32(dst + half * 32, v);
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar(BAR_DKV_EMPTY));
+      }
+      if (a.dbias != nullptr) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) atomicAdd(cs + (is_v ? 128 : 64) + half * 32 + lane, butterfly_colsum(csum[half], lane));
+      }
+      // dQ: all query tiles are complete after the last key block
+      mbar_wait(bar(BAR_DQ_FULL), (uint32_t)pair & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int t = 0; t < 32; ++t) csum[0][t] = 0.f, csum[1][t] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        if (i < QT) {
+          const int rows_valid = min(128, N - i * 128);
+          if (q * 32 < rows_valid) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              float v[32];
+              tmem_ld32(tlane + C_DQ + 64 * i + half * 32, v);
+              tmem_ld_wait();
+              if (row < rows_valid) {
+#pragma unroll
+                for (int t = 0; t < 32; ++t) {
+                  v[t] *= a.scale;
+                  csum[half][t] += v[t];
+                }
+                store_bf16_32(a.dqkv + ((long)b * N + i * 128 + row) * ldq + h * HD_ + half * 32, v);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar(BAR_DQ_EMPTY));
+      if (a.dbias != nullptr) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) atomicAdd(cs + half * 32 + lane, butterfly_colsum(csum[half], lane));
+      }
+    }
     if (a.dbias != nullptr) {
-      named_bar_sync(1, SM_THREADS);
-      const int t = threadIdx.x - SM_WARP0 * 32;
-      if (t < 192) atomicAdd(a.dbias + (long)(t >> 6) * HD + h * HD_ + (t & 63), cs[t]);
+      named_bar_sync(1, 128);
+      for (int t = et; t < 192; t += 128) atomicAdd(a.dbias + (long)(t >> 6) * HD + h * HD_ + (t & 63), cs[t]);
     }
   }
   tc_fence_before();
@@ -716,6 +787,9 @@ int zero_cols(void* base, long ld_elems, long rows, long col0, long ncols, cudaS
 
 }  // namespace
 
+static long long* g_attn_dbg = nullptr;
+void attn_set_debug(long long* p) { g_attn_dbg = p; }
+
 bool attn_tc_supported(int N, int D) { return D == HD_ && N >= 1 && N <= ATT_MAX_N; }
 
 int attn_fwd_tc(const void* qkv, void* o, float* lse, int B, int N, int H, int Hk, float scale, cudaStream_t st) {
@@ -732,7 +806,7 @@ int attn_fwd_tc(const void* qkv, void* o, float* lse, int B, int N, int H, int H
     configured = true;
   }
   AttnArgs a;
-  a.B = B, a.N = N, a.H = H, a.Hk = Hk, a.scale = scale, a.o = (bf16*)o, a.d_o = nullptr, a.lse = lse, a.dqkv = nullptr, a.dbias = nullptr;
+  a.B = B, a.N = N, a.H = H, a.Hk = Hk, a.scale = scale, a.o = (bf16*)o, a.d_o = nullptr, a.lse = lse, a.dqkv = nullptr, a.dbias = nullptr, a.dbg = nullptr;
   const int total = B * Hk;
   const int grid = total < num_sms() ? total : num_sms();
   attn_fwd_tc_kernel<<<grid, ATT_THREADS, F_SMEM, st>>>(maps, a);
@@ -755,11 +829,11 @@ int attn_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* ls
   }
   AttnArgs a;
   a.B = B, a.N = N, a.H = H, a.Hk = Hk, a.scale = scale, a.o = (bf16*)const_cast<void*>(o), a.d_o = (const bf16*)d_o,
-  a.lse = const_cast<float*>(lse), a.dqkv = (bf16*)dqkv, a.dbias = dbias;
+  a.lse = const_cast<float*>(lse), a.dqkv = (bf16*)dqkv, a.dbias = dbias, a.dbg = g_attn_dbg;
   int per_head = num_sms() / Hk;
   if (per_head < 1) per_head = 1;
   if (per_head > B) per_head = B;
-  attn_bwd_tc_kernel<<<per_head * Hk, ATT_THREADS, B_SMEM, st>>>(maps, a);
+  attn_bwd_tc_kernel<<<per_head * Hk, BWD_THREADS, B_SMEM, st>>>(maps, a);
   return check_launch("vsx_attn_bwd");
 }
 
