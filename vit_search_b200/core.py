@@ -43,6 +43,17 @@ def act_dtype():
     return torch.bfloat16 if _precision == 'bf16' else torch.float32
 
 
+def h2d(data, device, dtype=None):
+    """Small host -> device upload that never synchronises the stream: the data goes through a pinned staging tensor (PyTorch's
+    caching host allocator recycles it only after the copy has completed) and an asynchronous copy.  A plain
+    `torch.tensor(data, device=...)` / `.to(device)` from pageable memory blocks the Python thread until the GPU has drained,
+    which keeps the launch queue empty at the start of every step."""
+    t = data if isinstance(data, torch.Tensor) else torch.tensor(data, dtype=dtype)
+    if torch.device(device).type != 'cuda':
+        return t.to(device)
+    return t.pin_memory().to(device, non_blocking=True)
+
+
 def require_cuda(t, what):
     if not (isinstance(t, torch.Tensor) and t.is_cuda):
         raise RuntimeError('%s: vit_search_b200 runs on a B200 through libvsx.so only -- got a %s tensor; there is no CPU '

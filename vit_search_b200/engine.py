@@ -97,10 +97,11 @@ class FusedAdamW:
             self._chunks = chunks
             ct = np.repeat(np.arange(n, dtype=np.int32), chunks)
             ci = np.concatenate([np.arange(c, dtype=np.int32) for c in chunks])
-            self._ct = torch.from_numpy(ct).to(dev)
-            self._ci = torch.from_numpy(ci).to(dev)
+            self._ct = core.h2d(torch.from_numpy(ct), dev)
+            self._ci = core.h2d(torch.from_numpy(ci), dev)
             self._nchunks = int(ct.shape[0])
-        self._tab = torch.from_numpy(rec.view(np.uint8)).to(dev)
+        # asynchronous upload through pinned memory: a blocking copy here would drain the GPU once per step
+        self._tab = core.h2d(torch.from_numpy(rec.view(np.uint8)), dev)
 
     def step(self):
         # gradient tensors are re-allocated by every backward, parameters by `rewiring`: re-derive the pointer table when

@@ -7,7 +7,8 @@ import torch
 
 def make_mask(keep, width, device):
     """list[int] -> torch.bool [B,1,width] tagged with its keep counts."""
-    k = torch.tensor(keep, dtype=torch.int32).view(-1, 1, 1).to(device, non_blocking=True)
+    k = torch.tensor(keep, dtype=torch.int32)
+    k = (k.pin_memory().to(device, non_blocking=True) if torch.device(device).type == 'cuda' else k.to(device)).view(-1, 1, 1)
     m = torch.arange(width, device=device, dtype=torch.int32).view(1, 1, -1) < k
     m._vsx_keep = [int(v) for v in keep]
     return m

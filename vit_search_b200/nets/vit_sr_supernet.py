@@ -481,7 +481,7 @@ class FlexibleDistillVisionTransformerSR(nn.Module):
         self.last_keeps = keeps
         perm = self._group_permutation(keeps, B)
         if perm is not None:       # make architecture groups contiguous; undone on the logits
-            idx = torch.tensor(perm, device=x.device)
+            idx = core.h2d(perm, x.device)
             x = x.index_select(0, idx)
             keeps = [{k: [v[p] for p in perm] for k, v in kd.items()} for kd in keeps]
         depth = sum(1 for b in self.blocks if isinstance(b, (Block, BypassBlock)))
@@ -489,7 +489,7 @@ class FlexibleDistillVisionTransformerSR(nn.Module):
         dp = None
         if self.training and any(r > 0 for r in rates):
             u = torch.rand((depth, 2, B), device=x.device)               # CUDA generator, like nets/drop.py:20
-            keep_prob = 1.0 - torch.tensor(rates, device=x.device).view(depth, 1, 1)
+            keep_prob = 1.0 - core.h2d(rates, x.device).view(depth, 1, 1)
             dp = ((keep_prob + u).floor_() / keep_prob).view(depth * 2, B).contiguous()
 
         h = self.patch_embed(x)
@@ -526,7 +526,7 @@ class FlexibleDistillVisionTransformerSR(nn.Module):
         if perm is not None:
             inv = torch.empty(len(perm), dtype=torch.long)
             inv[torch.tensor(perm)] = torch.arange(len(perm))
-            inv = inv.to(cls_pred.device)
+            inv = core.h2d(inv, cls_pred.device)
             cls_pred = cls_pred.index_select(0, inv)
             if with_patches:
                 patch_pred = patch_pred.index_select(0, inv)
