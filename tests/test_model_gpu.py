@@ -175,3 +175,37 @@ def test_drop_path_and_train_step():
             if not e < 2e-2:
                 bad[k] = e
     assert not bad, bad
+
+
+def test_fused_adamw_operand_shadows():
+    """The fused optimizer kernel also rewrites the bf16 GEMM-operand copies of the Linear weights: after every step the copy the
+    next forward will read must equal bf16(master weight), and training with shadows must match training with per-step re-casts."""
+    from vit_search_b200 import core
+    from vit_search_b200.engine import TrainStep, FusedAdamW
+    case = CASES['small_single']
+    B = case['batch']
+    x, t, pt = O.synthetic_batch(B, seed=9)
+    losses = {}
+    for mode in ('shadow', 'recast'):
+        torch.manual_seed(0)
+        m, nd = build(case)
+        m.train()
+        opt = FusedAdamW(m, lr=1e-3, weight_decay=0.05)
+        step = TrainStep(m, opt, arch_sample='single')
+        out = []
+        with core.precision('bf16'):
+            for it in range(3):
+                if mode == 'recast':
+                    core.weights.clear()          # forget every cached / adopted operand copy: the forward re-casts from the masters
+                out.append(step(x.cuda(), t.cuda(), pt.cuda(), epoch=1).item())
+                if mode == 'shadow':
+                    n_shadow = 0
+                    for name, p in m.named_parameters():
+                        if p.ndim == 2 and p.shape[1] % 8 == 0:
+                            got = core.weights.get(p)
+                            assert got.data_ptr() == opt.shadow[name].data_ptr(), name      # served from the optimizer's shadow ...
+                            assert torch.equal(got, p.detach().to(torch.bfloat16)), name    # ... which equals bf16(master)
+                            n_shadow += 1
+                    assert n_shadow > 10
+        losses[mode] = out
+    assert losses['shadow'] == losses['recast'], losses

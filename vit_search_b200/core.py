@@ -76,8 +76,13 @@ class _WeightCache:
         key = (id(w), layout)
         tag = (w.data_ptr(), w._version, self.generation, _precision, tuple(w.shape))
         e = self.entries.get(key)
-        if e is not None and e[0] == tag and e[2]() is w:
-            return e[1]
+        if e is not None and e[2]() is w:
+            if e[0] == tag:
+                return e[1]
+            # shadow copies are rewritten by the fused optimizer kernel in the same pass that updates the fp32 master, so they do
+            # not depend on `generation`; everything else in the tag must still match
+            if len(e) == 4 and e[0][:2] == tag[:2] and e[0][3:] == tag[3:]:
+                return e[1]
         ref = weakref.ref(w)
         src = w.detach()
         if layout in ('conv3x3_fwd', 'conv3x3_bwd'):
@@ -104,6 +109,12 @@ class _WeightCache:
             self.entries = {k: v for k, v in self.entries.items() if v[2]() is not None}
         self.entries[key] = (tag, val, ref)
         return val
+
+    def adopt_shadow(self, w, shadow):
+        """Register `shadow` (bf16, same [rows, cols] layout) as the GEMM operand copy of parameter w.  The caller (FusedAdamW)
+        guarantees that it rewrites the shadow whenever it rewrites w through raw pointers."""
+        tag = (w.data_ptr(), w._version, self.generation, 'bf16', tuple(w.shape))
+        self.entries[(id(w), None)] = (tag, shadow, weakref.ref(w), True)
 
     def clear(self):
         self.entries.clear()
@@ -160,11 +171,40 @@ def up8(n):
     return (n + 7) // 8 * 8
 
 
+class _GradPool:
+    """One zero-filled fp32 buffer per training step for ALL parameter gradients (one allocation + one memset instead of one per
+    half block).  engine.TrainStep opens it right before `backward()`; outside of that window (tests, ad-hoc backward calls)
+    zeros_like_many falls back to its own allocation."""
+
+    def __init__(self):
+        self.flat, self.off = None, 0
+
+    def begin(self, numel, device):
+        self.flat, self.off = torch.zeros(numel, device=device, dtype=torch.float32), 0
+
+    def end(self):
+        self.flat, self.off = None, 0
+
+    def take(self, numel, device):
+        f = self.flat
+        if f is None or f.device != device or self.off + numel > f.numel():
+            return None
+        v = f[self.off:self.off + numel]
+        self.off += numel
+        return v
+
+
+grad_pool = _GradPool()
+
+
 def zeros_like_many(*tensors):
     """Zero-initialised fp32 gradient buffers for several parameters from ONE allocation + ONE memset (each view 16-byte
-    aligned, as the TMA reduce-add of the weight-gradient GEMMs requires)."""
+    aligned, as the TMA reduce-add of the weight-gradient GEMMs requires); carved out of the per-step gradient pool when
+    engine.TrainStep has opened one."""
     sizes = [(t.numel() + 3) // 4 * 4 for t in tensors]
-    flat = torch.zeros(sum(sizes), device=tensors[0].device, dtype=torch.float32)
+    flat = grad_pool.take(sum(sizes), tensors[0].device)
+    if flat is None:
+        flat = torch.zeros(sum(sizes), device=tensors[0].device, dtype=torch.float32)
     out, off = [], 0
     for t, n in zip(tensors, sizes):
         out.append(flat[off:off + t.numel()].view(t.shape))

@@ -65,6 +65,7 @@ class FusedAdamW:
             no_decay = p.ndim <= 1 or name.endswith('.bias') or name in skip
             self.entries.append((name, p, 0.0 if no_decay else weight_decay))
         self.state = {}
+        self.shadow = {}          # name -> bf16 GEMM-operand copy refreshed by the optimizer kernel itself
         self._table_key = None
         self.param_groups = [{'lr': lr}]
         self.chunk = _lib.lib().vsx_adamw_chunk_elems()
@@ -91,7 +92,16 @@ class FusedAdamW:
             if st is None or st[0].shape != p.shape:
                 st = (torch.zeros_like(p), torch.zeros_like(p))
                 self.state[name] = st
-            rec[i] = (p.data_ptr(), p.grad.data_ptr(), st[0].data_ptr(), st[1].data_ptr(), 0, 0, p.numel(), wd, 0)
+            hi = 0
+            if core.get_precision() == 'bf16' and p.ndim == 2 and p.shape[1] % 8 == 0:
+                # Linear weights: the kernel also writes the bf16 operand copy the next forward's GEMMs read (saves one cast kernel per
+                # weight per step); conv weights keep their re-laid-out copies in core.weights
+                sh = self.shadow.get(name)
+                if sh is None or sh.shape != p.shape:
+                    sh = torch.empty(p.shape, device=p.device, dtype=torch.bfloat16)
+                    self.shadow[name] = sh
+                hi = sh.data_ptr()
+            rec[i] = (p.data_ptr(), p.grad.data_ptr(), st[0].data_ptr(), st[1].data_ptr(), hi, 0, p.numel(), wd, 0)
             chunks.append(math.ceil(p.numel() / self.chunk))
         if getattr(self, '_chunks', None) != chunks:
             self._chunks = chunks
@@ -102,19 +112,25 @@ class FusedAdamW:
             self._nchunks = int(ct.shape[0])
         # asynchronous upload through pinned memory: a blocking copy here would drain the GPU once per step
         self._tab = core.h2d(torch.from_numpy(rec.view(np.uint8)), dev)
+        self._tab_has_shadow = bool((rec['hi'] != 0).any())
 
     def step(self):
         # gradient tensors are re-allocated by every backward, parameters by `rewiring`: re-derive the pointer table when
         # any pointer changed (a host-side comparison of ~250 integers)
-        key = tuple((p.data_ptr(), 0 if p.grad is None else p.grad.data_ptr()) for _, p, _ in self.entries)
+        key = (core.get_precision(),) + tuple((p.data_ptr(), 0 if p.grad is None else p.grad.data_ptr()) for _, p, _ in self.entries)
         if key != self._table_key:
             self._build_table()
-            self._table_key = tuple((p.data_ptr(), p.grad.data_ptr()) for _, p, _ in self.entries)
+            self._table_key = (core.get_precision(),) + tuple((p.data_ptr(), p.grad.data_ptr()) for _, p, _ in self.entries)
         self.step_count += 1
         self.lr = self.param_groups[0]['lr']
         ops.call('adamw', self._tab, self._ct, self._ci, self._nchunks, float(self.lr), float(self.betas[0]), float(self.betas[1]),
                  float(self.eps), self.step_count, None)
-        core.weights.generation += 1      # parameters were written through raw pointers: operand copies are stale
+        core.weights.generation += 1      # parameters were written through raw pointers: operand copies are stale ...
+        if self._tab_has_shadow:          # ... except the shadows this launch has just rewritten
+            for name, p, _ in self.entries:
+                sh = self.shadow.get(name)
+                if sh is not None:
+                    core.weights.adopt_shadow(p, sh)
 
 
 # ------------------------------------------------------------------------------------------------ train step
@@ -129,6 +145,7 @@ class TrainStep:
         self.arch_sample = arch_sample
         self.world_size = world_size
         self.train_iter = 0
+        self._pool_numel = None
 
     def __call__(self, samples, targets, patch_targets, epoch=0):
         """samples [B,3,224,224], targets [B,K], patch_targets [B,16,K] on the GPU.  Returns the loss as a device scalar
@@ -146,7 +163,13 @@ class TrainStep:
             torch.random.set_rng_state(rng)                      # engine.py:164-165
         self.train_iter += 1
         self.optimizer.zero_grad()
-        loss.backward()
+        if self._pool_numel is None:          # every gradient buffer padded to a multiple of 4 elements + slack for meta placeholders
+            self._pool_numel = sum((p.numel() + 3) // 4 * 4 + 8 for p in self.model.parameters()) + 4096
+        core.grad_pool.begin(self._pool_numel, samples.device)
+        try:
+            loss.backward()
+        finally:
+            core.grad_pool.end()
         if self.world_size > 1 and self.net is self.model:
             allreduce_gradients(self.model, self.world_size)
         self.optimizer.step()
