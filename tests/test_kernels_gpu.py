@@ -21,6 +21,16 @@ def ops():
 
 
 # ---------------------------------------------------------------------------------------------- masked LN
+@pytest.fixture(params=[128, 256])
+def tile_rows(request, ops):
+    """Run every GEMM test with both CTA tile shapes of csrc/gemm_tc.cu (128 x 128, and 256 x 128 = two accumulators sharing one
+    B box per k block), including 256-row tiles whose second half lies beyond M."""
+    from vit_search_b200 import _lib
+    _lib.check(_lib.lib().vsx_gemm_force_tile_rows(request.param))
+    yield request.param
+    _lib.lib().vsx_gemm_force_tile_rows(0)
+
+
 @pytest.mark.parametrize('C,keep', [(64, 64), (64, 44), (256, 160), (320, 220), (1024, 704), (1280, 1280)])
 @pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
 def test_masked_ln(ops, C, keep, dtype):
@@ -103,7 +113,7 @@ def _mk(M, N, K, seed):
 
 @pytest.mark.parametrize('M,N,K', [(128, 128, 64), (256, 128, 128), (300, 200, 96), (1028, 576, 256), (514, 768, 160),
                                    (130, 1000, 1024), (64, 44, 220)])
-def test_gemm_store_kmajor(ops, M, N, K):
+def test_gemm_store_kmajor(ops, M, N, K, tile_rows):
     Kp = (K + 7) // 8 * 8 + 8            # pitch > K: junk beyond K must be clipped by the TMA descriptor
     A, W = _mk(M, N, Kp, M + N + K)
     bias = torch.randn(N)
@@ -118,7 +128,7 @@ def test_gemm_store_kmajor(ops, M, N, K):
         assert torch.all(out[:, N:] == 0)
 
 
-def test_gemm_split3_precision(ops):
+def test_gemm_split3_precision(ops, tile_rows):
     """bf16x3 split mode must recover ~fp32 accuracy (the high-precision parity path)."""
     M, N, K = 384, 256, 512
     A, W = _mk(M, N, K, 5)
@@ -145,7 +155,7 @@ def test_gemm_split3_precision(ops):
 
 
 @pytest.mark.parametrize('M,N,K', [(256, 128, 128), (300, 136, 200), (1028, 256, 576)])
-def test_gemm_dgrad_layout(ops, M, N, K):
+def test_gemm_dgrad_layout(ops, M, N, K, tile_rows):
     """dX[M,N] = dY[M,K] @ W[K,N]: A K-major, B MN-major (W stored [K rows, N contiguous])."""
     g = torch.Generator().manual_seed(M)
     dY = torch.randn(M, K, generator=g).to(torch.bfloat16)
@@ -157,7 +167,7 @@ def test_gemm_dgrad_layout(ops, M, N, K):
 
 
 @pytest.mark.parametrize('R,Nw,Kw,split', [(256, 128, 128, 1), (1000, 200, 136, 3), (4112, 576, 256, 8), (771, 44, 60, 2)])
-def test_gemm_wgrad_layout(ops, R, Nw, Kw, split):
+def test_gemm_wgrad_layout(ops, R, Nw, Kw, split, tile_rows):
     """dW[Nw,Kw] += dY[R,Nw]^T @ X[R,Kw]: both operands MN-major, split-K atomics."""
     g = torch.Generator().manual_seed(R)
     lda, ldb = (Nw + 7) // 8 * 8 + 8, (Kw + 7) // 8 * 8 + 16     # pitch > extent: exercises TMA OOB clipping
@@ -170,7 +180,7 @@ def test_gemm_wgrad_layout(ops, R, Nw, Kw, split):
     assert rel(out - 1, ref) < 2e-5
 
 
-def test_gemm_epilogues(ops):
+def test_gemm_epilogues(ops, tile_rows):
     M, N, K, C = 514, 200, 128, 256      # 2 samples x 257 rows
     A, W = _mk(M, N, K, 9)
     Ab, Wb = A.to(torch.bfloat16), W.to(torch.bfloat16)

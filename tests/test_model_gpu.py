@@ -208,4 +208,5 @@ def test_fused_adamw_operand_shadows():
                             n_shadow += 1
                     assert n_shadow > 10
         losses[mode] = out
-    assert losses['shadow'] == losses['recast'], losses
+    # split-K / bias-gradient reductions use atomics, so two runs agree to rounding, not bit for bit
+    assert all(abs(a - b) < 2e-3 * abs(b) for a, b in zip(losses['shadow'], losses['recast'])), losses

@@ -25,10 +25,16 @@ namespace {
 
 constexpr int BM = 128, BN = 128, BK = 64;
 constexpr int UMMA_K = 16;
-constexpr int STAGE_A = BM * BK * 2;
+constexpr int SUB_A = BM * BK * 2;      // one 128-row A sub-tile of a k block
 constexpr int STAGE_B = BN * BK * 2;
-constexpr int STAGE_BYTES = STAGE_A + STAGE_B;
-constexpr int TMEM_COLS = 256;          // two 128-column fp32 accumulators (double buffered across tiles)
+// MT = 128-row sub-tiles per CTA tile.  MT = 2 computes a 256 x 128 tile from ONE B box per k block (two accumulators share it):
+// 3/4 of the L2 -> shared-memory bytes per flop of two independent 128 x 128 tiles.  These GEMMs have K <= 1536 and run at the
+// L2 -> SM fabric limit (~45 B/clk/SM) long before the tensor pipe saturates, so bytes per flop is what sets their speed.
+template <int MT> struct Shape {
+  static constexpr int STAGE_A = MT * SUB_A;
+  static constexpr int STAGE_BYTES = STAGE_A + STAGE_B;
+  static constexpr int TMEM_COLS = 2 * MT * BN;      // two accumulator sets (double buffered across tiles)
+};
 constexpr int EPI_WARPS = 8;            // two warps per TMEM lane quarter, each owning half of the tile's columns
 constexpr int EPI0 = 3;                 // warp 0 TMA producer, warp 1 MMA issuer, warp 2 store/aux warp, warps 3.. epilogue
 constexpr int GEMM_THREADS = (EPI0 + EPI_WARPS) * 32;
@@ -42,6 +48,8 @@ struct TmapPack {
   CUtensorMap b[MAX_TERMS];
   CUtensorMap out, out2, aux;   // epilogue tiles (128B-swizzled boxes of 128 rows x 128 bytes)
 };
+
+static int g_force_mt = 0;   // 0 = heuristic, 1 / 2 = force the 128- / 256-row CTA tile (tests)
 
 struct GemmArgs {
   int M, N, K, num_kb, terms, a_mn, b_mn, n_out, split_k;
@@ -124,9 +132,11 @@ __device__ __forceinline__ void stage_read32<bf16>(const uint8_t* tile, int row,
 }
 
 // Per-instantiation shared-memory plan: NBUF staging tiles (epilogue output / aux input), the rest is the operand ring.
-template <int EPI, typename OutT> struct Plan {
+template <int EPI, typename OutT, int MT> struct Plan {
+  static constexpr int STAGE_BYTES = Shape<MT>::STAGE_BYTES;
   static constexpr int TILE_BYTES = BM * BN * (int)sizeof(OutT) * (EPI == VSX_EPI_GELU ? 2 : 1);
-  static constexpr int NBUF = (2 * TILE_BYTES + 2 * STAGE_BYTES + SMEM_MISC <= SMEM_LIMIT) ? 2 : 1;
+  // two staging tiles when at least three operand stages still fit (the ring has to cover the L2 latency: ~100 KB in flight)
+  static constexpr int NBUF = (2 * TILE_BYTES + 3 * STAGE_BYTES + SMEM_MISC <= SMEM_LIMIT) ? 2 : 1;
   static constexpr int ROOM = (SMEM_LIMIT - SMEM_MISC - NBUF * TILE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = ROOM > MAX_STAGES ? MAX_STAGES : ROOM;
   static constexpr int SMEM = STAGES * STAGE_BYTES + NBUF * TILE_BYTES + SMEM_MISC;
@@ -141,10 +151,11 @@ template <int EPI, typename OutT> struct Plan {
 //                       later TMA-stores / reduce-adds the staged result; staging is double buffered
 //   warps 3+ epilogue : TMEM -> registers -> fused math -> swizzled staging tile
 // so the loads of tile i+1, the MMAs of tile i+1 and the stores of tile i-1 overlap the epilogue of tile i.
-template <int EPI, typename OutT>
+template <int EPI, typename OutT, int MT>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TmapPack maps, const GemmArgs g) {
-  using P = Plan<EPI, OutT>;
+  using P = Plan<EPI, OutT, MT>;
   constexpr int STAGES = P::STAGES, NBUF = P::NBUF;
+  constexpr int STAGE_BYTES = P::STAGE_BYTES, STAGE_A = Shape<MT>::STAGE_A, TMEM_COLS = Shape<MT>::TMEM_COLS;
   constexpr bool AUX = (EPI == VSX_EPI_RESIDUAL || EPI == VSX_EPI_GELUGRAD);
   constexpr int BOXC = 128 / (int)sizeof(OutT);     // columns per 128-byte box row
   constexpr int NBOX = BN / BOXC;                   // boxes per output tile
@@ -167,7 +178,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   float* bias_s = reinterpret_cast<float*>(misc + 256);   // [2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (g.M + BM - 1) / BM, tiles_n = (g.n_out + BN - 1) / BN;
+  const int tiles_m = (g.M + BM * MT - 1) / (BM * MT), tiles_n = (g.n_out + BN - 1) / BN;
   const int splits = (EPI == VSX_EPI_ATOMIC) ? g.split_k : 1;
   const int total = tiles_m * tiles_n * splits;
   const int kb_per = (g.num_kb + splits - 1) / splits;
@@ -175,7 +186,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   // tile t -> (m0, n0, k-block range); identical arithmetic in every role
   auto tile_info = [&](int t, int& m0, int& n0, int& kb0, int& nkb) {
     const int ni = t % tiles_n, mi = (t / tiles_n) % tiles_m, z = t / (tiles_n * tiles_m);
-    m0 = mi * BM, n0 = ni * BN;
+    m0 = mi * BM * MT, n0 = ni * BN;
     kb0 = z * kb_per;
     const int kb1 = min(g.num_kb, kb0 + kb_per);
     nkb = (n0 < g.N && kb1 > kb0) ? kb1 - kb0 : 0;
@@ -224,11 +235,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           const int term = i / nkb, k0 = (kb0 + i % nkb) * BK;
           const uint32_t dA = ring + s * STAGE_BYTES, dB = dA + STAGE_A, fb = full_bar(s);
           mbar_expect_tx(fb, STAGE_BYTES);
-          if (!g.a_mn) {
-            tma_load_2d(dA, &maps.a[term], fb, k0, m0);
-          } else {
-            tma_load_2d(dA, &maps.a[term], fb, m0, k0);
-            tma_load_2d(dA + BK * 128, &maps.a[term], fb, m0 + 64, k0);
+#pragma unroll
+          for (int sub = 0; sub < MT; ++sub) {
+            const uint32_t dS = dA + sub * SUB_A;
+            const int ms = m0 + sub * BM;
+            if (!g.a_mn) {
+              tma_load_2d(dS, &maps.a[term], fb, k0, ms);
+            } else {
+              tma_load_2d(dS, &maps.a[term], fb, ms, k0);
+              tma_load_2d(dS + BK * 128, &maps.a[term], fb, ms + 64, k0);
+            }
           }
           if (!g.b_mn) {
             tma_load_2d(dB, &maps.b[term], fb, k0, n0);
@@ -254,7 +270,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         mbar_wait(acc_empty(ab), ((uint32_t)uses[ab] & 1u) ^ 1u);   // epilogue has drained this accumulator
         ++uses[ab];
         tc_fence_after();
-        const uint32_t acc = tmem_base + (uint32_t)ab * BN;
+        const uint32_t acc = tmem_base + (uint32_t)ab * (MT * BN);
         for (int i = 0; i < nkb * g.terms; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -263,8 +279,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           const uint32_t aA = ring + s * STAGE_BYTES, aB = aA + STAGE_A;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
-            umma_bf16(acc, make_smem_desc(aA + k * a_step, g.a_mn != 0), make_smem_desc(aB + k * b_step, g.b_mn != 0), idesc,
-                      (i | k) != 0 ? 1u : 0u);
+            const uint64_t db = make_smem_desc(aB + k * b_step, g.b_mn != 0);
+#pragma unroll
+            for (int sub = 0; sub < MT; ++sub)
+              umma_bf16(acc + sub * BN, make_smem_desc(aA + sub * SUB_A + k * a_step, g.a_mn != 0), db, idesc, (i | k) != 0 ? 1u : 0u);
           }
           umma_commit(empty_bar(s));   // slot reusable once these MMAs have read it
         }
@@ -276,46 +294,51 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       // ---------------- store / aux warp ----------------
       // announce(j): staging buffer j % NBUF is free (its previous store has been read out) -> TMA-load the aux tile into it
       // (completing `ready`), or just arrive on `ready` when the epilogue needs no aux tile.
-      auto announce = [&](int t, int sb) {
+      // A CTA tile is MT units of 128 rows; units are staged / stored one at a time through the NBUF staging buffers.
+      auto announce = [&](int t, int sub, int sb) {
         int m0, n0, kb0, nkb;
         tile_info(t, m0, n0, kb0, nkb);
         const int ncols = min(BN, g.n_out - n0);
         const int nbox = (ncols + BOXC - 1) / BOXC;
         if (AUX) {
           mbar_expect_tx(ready_bar(sb), (uint32_t)nbox * BOX_BYTES);
-          for (int bx = 0; bx < nbox; ++bx) tma_load_2d(stg + sb * P::TILE_BYTES + bx * BOX_BYTES, &maps.aux, ready_bar(sb), n0 + bx * BOXC, m0);
+          for (int bx = 0; bx < nbox; ++bx)
+            tma_load_2d(stg + sb * P::TILE_BYTES + bx * BOX_BYTES, &maps.aux, ready_bar(sb), n0 + bx * BOXC, m0 + sub * BM);
         } else {
           mbar_arrive(ready_bar(sb));
         }
       };
-      int j = 0;
-      if ((int)blockIdx.x < total) announce(blockIdx.x, 0);
-      for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
-        const int sb = j % NBUF;
-        const int tn = t + gridDim.x;
+      int un = 0, t = blockIdx.x, sub = 0;
+      if (t < total) announce(t, 0, 0);
+      while (t < total) {
+        const int sb = un % NBUF;
+        int tn = t, subn = sub + 1;
+        if (subn == MT) subn = 0, tn = t + gridDim.x;
         if (NBUF == 2 && tn < total) {
-          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // store of tile j-1 (same buffer as j+1) has been read
-          announce(tn, (j + 1) % NBUF);
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // store of unit un-1 (same buffer as un+1) has been read
+          announce(tn, subn, (un + 1) % NBUF);
         }
         int m0, n0, kb0, nkb;
         tile_info(t, m0, n0, kb0, nkb);
+        const int ms = m0 + sub * BM;
         const int ncols = min(BN, g.n_out - n0);
         const int nbox = (ncols + BOXC - 1) / BOXC;
-        mbar_wait(staged_bar(sb), (uint32_t)(j / NBUF) & 1u);                // epilogue has staged tile j
+        mbar_wait(staged_bar(sb), (uint32_t)(un / NBUF) & 1u);               // epilogue has staged unit un
         const uint32_t src = stg + sb * P::TILE_BYTES;
         for (int bx = 0; bx < nbox; ++bx) {
           if (EPI == VSX_EPI_ATOMIC) {
-            tma_reduce_add_2d(&maps.out, src + bx * BOX_BYTES, n0 + bx * BOXC, m0);
+            tma_reduce_add_2d(&maps.out, src + bx * BOX_BYTES, n0 + bx * BOXC, ms);
           } else {
-            tma_store_2d(&maps.out, src + bx * BOX_BYTES, n0 + bx * BOXC, m0);
-            if (EPI == VSX_EPI_GELU) tma_store_2d(&maps.out2, src + (NBOX + bx) * BOX_BYTES, n0 + bx * BOXC, m0);
+            tma_store_2d(&maps.out, src + bx * BOX_BYTES, n0 + bx * BOXC, ms);
+            if (EPI == VSX_EPI_GELU) tma_store_2d(&maps.out2, src + (NBOX + bx) * BOX_BYTES, n0 + bx * BOXC, ms);
           }
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         if (NBUF == 1 && tn < total) {
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          announce(tn, 0);
+          announce(tn, subn, 0);
         }
+        t = tn, sub = subn, ++un;
       }
       asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");        // shared memory must outlive the last store
     }
@@ -337,90 +360,94 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       int m0, n0, kb0, nkb;
       tile_info(t, m0, n0, kb0, nkb);
       const bool has_mma = nkb > 0;
-      const int ab = j & 1, sb = j % NBUF;
-      const int m = m0 + row;
+      const int ab = j & 1;
       const int ncols = min(BN, g.n_out - n0);
       float* bs = bias_s + ab * BN;
       if (et < BN) bs[et] = (g.bias != nullptr && n0 + et < g.N) ? __ldg(g.bias + n0 + et) : 0.f;
-      mbar_wait(ready_bar(sb), (uint32_t)(j / NBUF) & 1u);        // staging buffer writable (and aux tile landed)
       named_bar_sync(1, EPI_WARPS * 32);                           // bias tile visible
       if (has_mma) {
         mbar_wait(acc_full(ab), (uint32_t)uses[ab] & 1u);
         ++uses[ab];
         tc_fence_after();
       }
-      uint8_t* tile = stg_g + sb * P::TILE_BYTES;
-      uint8_t* tile2 = tile + NBOX * BOX_BYTES;
-      float scale = 1.0f;
-      if (EPI == VSX_EPI_RESIDUAL && g.row_scale != nullptr && m < g.M) scale = __ldg(g.row_scale + m / g.rows_per_sample);
-      const uint32_t acc = tmem_base + (uint32_t)ab * BN + ((uint32_t)(q * 32) << 16);
-      for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
-        if (c >= ncols) break;
-        float v[32];
-        if (has_mma) {
-          tmem_ld32(acc + (uint32_t)c, v);
-          tmem_ld_wait();
-        } else {
+#pragma unroll 1
+      for (int sub = 0; sub < MT; ++sub) {
+        const int un = j * MT + sub, sb = un % NBUF;
+        const int ms = m0 + sub * BM, m = ms + row;
+        mbar_wait(ready_bar(sb), (uint32_t)(un / NBUF) & 1u);      // staging buffer writable (and aux tile landed)
+        uint8_t* tile = stg_g + sb * P::TILE_BYTES;
+        uint8_t* tile2 = tile + NBOX * BOX_BYTES;
+        float scale = 1.0f;
+        if (EPI == VSX_EPI_RESIDUAL && g.row_scale != nullptr && m < g.M) scale = __ldg(g.row_scale + m / g.rows_per_sample);
+        const uint32_t acc = tmem_base + (uint32_t)(ab * MT + sub) * BN + ((uint32_t)(q * 32) << 16);
+        for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
+          if (c >= ncols) break;
+          float v[32];
+          if (has_mma) {
+            tmem_ld32(acc + (uint32_t)c, v);
+            tmem_ld_wait();
+          } else {
 #pragma unroll
-          for (int jj = 0; jj < 32; ++jj) v[jj] = 0.f;
-        }
-        const int n = n0 + c;
-        if (EPI == VSX_EPI_ATOMIC) {
-          stage_write32<float>(tile, row, c, v);
-        } else if (EPI == VSX_EPI_STORE) {
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] + bs[c + jj] : 0.f;
-          stage_write32<OutT>(tile, row, c, v);
-        } else if (EPI == VSX_EPI_GELU) {
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] + bs[c + jj] : 0.f;
-          stage_write32<OutT>(tile, row, c, v);
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) v[jj] = gelu_sel<OutT>(v[jj]);   // gelu(0) = 0 keeps the zero fill
-          stage_write32<OutT>(tile2, row, c, v);
-        } else if (EPI == VSX_EPI_RESIDUAL) {
-          float r[32];
-          stage_read32<float>(tile, row, c, r);
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) r[jj] += (n + jj < lim) ? scale * (v[jj] + bs[c + jj]) : 0.f;
-          stage_write32<float>(tile, row, c, r);
-        } else if (EPI == VSX_EPI_GELUGRAD) {
-          float u[32];
-          stage_read32<OutT>(tile, row, c, u);
-#pragma unroll
-          for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] * gelu_grad_sel<OutT>(u[jj]) : 0.f;
-          stage_write32<OutT>(tile, row, c, v);
-        }
-      }
-      if (has_mma) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(acc_empty(ab));                 // this warp's TMEM reads of the accumulator are done
-      }
-      if ((EPI == VSX_EPI_GELUGRAD || EPI == VSX_EPI_STORE) && g.colsum != nullptr) {
-        // bias gradient fused into the dgrad epilogue: column sums of the staged (already rounded) tile over its valid rows
-        // all 256 epilogue threads: thread (cc, half) sums column cc over 64 rows, 8 independent loads in flight
-        named_bar_sync(1, EPI_WARPS * 32);
-        const int cc = et & 127, rh = et >> 7;
-        if (n0 + cc < g.N) {
-          const int rbeg = rh * (BM / 2), rend = min(rbeg + BM / 2, g.M - m0);
-          const uint8_t* colp = tile + (cc / BOXC) * BOX_BYTES + (cc % (16 / (int)sizeof(OutT))) * (int)sizeof(OutT);
-          const int chunk = (cc % BOXC) / (16 / (int)sizeof(OutT));
-          float part[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) part[i] = 0.f;
-          for (int r = rbeg; r < rend; r += 8) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              if (r + i < rend) part[i] += Store<OutT>::ld(reinterpret_cast<const OutT*>(colp + box_off(r + i, chunk)));
+            for (int jj = 0; jj < 32; ++jj) v[jj] = 0.f;
           }
-          const float a2 = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
-          if (rend > rbeg) atomicAdd(g.colsum + n0 + cc, a2);
+          const int n = n0 + c;
+          if (EPI == VSX_EPI_ATOMIC) {
+            stage_write32<float>(tile, row, c, v);
+          } else if (EPI == VSX_EPI_STORE) {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] + bs[c + jj] : 0.f;
+            stage_write32<OutT>(tile, row, c, v);
+          } else if (EPI == VSX_EPI_GELU) {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] + bs[c + jj] : 0.f;
+            stage_write32<OutT>(tile, row, c, v);
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) v[jj] = gelu_sel<OutT>(v[jj]);   // gelu(0) = 0 keeps the zero fill
+            stage_write32<OutT>(tile2, row, c, v);
+          } else if (EPI == VSX_EPI_RESIDUAL) {
+            float r[32];
+            stage_read32<float>(tile, row, c, r);
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) r[jj] += (n + jj < lim) ? scale * (v[jj] + bs[c + jj]) : 0.f;
+            stage_write32<float>(tile, row, c, r);
+          } else if (EPI == VSX_EPI_GELUGRAD) {
+            float u[32];
+            stage_read32<OutT>(tile, row, c, u);
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] * gelu_grad_sel<OutT>(u[jj]) : 0.f;
+            stage_write32<OutT>(tile, row, c, v);
+          }
         }
+        if (has_mma && sub == MT - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty(ab));               // this warp's TMEM reads of the accumulator set are done
+        }
+        if ((EPI == VSX_EPI_GELUGRAD || EPI == VSX_EPI_STORE) && g.colsum != nullptr) {
+          // bias gradient fused into the dgrad epilogue: column sums of the staged (already rounded) tile over its valid rows;
+          // all 256 epilogue threads: thread (cc, half) sums column cc over 64 rows, 8 independent loads in flight
+          named_bar_sync(1, EPI_WARPS * 32);
+          const int cc = et & 127, rh = et >> 7;
+          if (n0 + cc < g.N) {
+            const int rbeg = rh * (BM / 2), rend = min(rbeg + BM / 2, g.M - ms);
+            const uint8_t* colp = tile + (cc / BOXC) * BOX_BYTES + (cc % (16 / (int)sizeof(OutT))) * (int)sizeof(OutT);
+            const int chunk = (cc % BOXC) / (16 / (int)sizeof(OutT));
+            float part[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) part[i] = 0.f;
+            for (int r = rbeg; r < rend; r += 8) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                if (r + i < rend) part[i] += Store<OutT>::ld(reinterpret_cast<const OutT*>(colp + box_off(r + i, chunk)));
+            }
+            const float a2 = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
+            if (rend > rbeg) atomicAdd(g.colsum + n0 + cc, a2);
+          }
+        }
+        fence_proxy_async();                                       // generic-proxy smem writes -> visible to the TMA (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(staged_bar(sb));                // 8 warps -> the store warp may ship the unit
       }
-      fence_proxy_async();                                         // generic-proxy smem writes -> visible to the TMA (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(staged_bar(sb));                  // 8 warps -> the store warp may ship the tile
     }
   }
   tc_fence_before();
@@ -428,12 +455,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int EPI, typename OutT>
-int launch(const TmapPack& maps, const GemmArgs& g, int total_tiles, cudaStream_t st) {
-  using P = Plan<EPI, OutT>;
+template <int EPI, typename OutT, int MT>
+int launch_mt(const TmapPack& maps, const GemmArgs& g, int total_tiles, cudaStream_t st) {
+  using P = Plan<EPI, OutT, MT>;
   static bool configured = false;   // benign race: attribute set is idempotent
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, OutT>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, OutT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM);
     if (e != cudaSuccess) {
       set_error("vsx_gemm: cudaFuncSetAttribute(%d) failed: %s", P::SMEM, cudaGetErrorString(e));
       return VSX_ERR_CUDA;
@@ -441,14 +468,44 @@ int launch(const TmapPack& maps, const GemmArgs& g, int total_tiles, cudaStream_
     configured = true;
   }
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  gemm_tc_kernel<EPI, OutT><<<grid, GEMM_THREADS, P::SMEM, st>>>(maps, g);
+  gemm_tc_kernel<EPI, OutT, MT><<<grid, GEMM_THREADS, P::SMEM, st>>>(maps, g);
   return check_launch("vsx_gemm");
+}
+
+// 256-row CTA tiles when they still fill the machine at least once; 128-row tiles for small problems (more CTAs in flight)
+template <int EPI, typename OutT>
+int launch(const TmapPack& maps, const GemmArgs& g, int tiles128, cudaStream_t st) {
+  const int tiles_n = ceil_div(g.n_out, BN);
+  const int t128 = ceil_div(g.M, BM), t256 = ceil_div(g.M, 2 * BM);
+  if (EPI == VSX_EPI_ATOMIC) {
+    // weight gradients: few output tiles, long reductions.  256-row tiles unless the second sub-tile would be mostly padding;
+    // the reduction is then re-split so that about two work items per SM exist (the caller's split_k > 1 only permits splitting).
+    const bool mt2 = g_force_mt == 2 || (g_force_mt == 0 && 2 * t256 * 5 <= t128 * 6);
+    if (mt2) {
+      GemmArgs g2 = g;
+      if (g.split_k > 1) {
+        const int want = (2 * num_sms()) / (t256 * tiles_n);
+        g2.split_k = want < 1 ? 1 : (want > g.num_kb ? g.num_kb : want);
+      }
+      return launch_mt<EPI, OutT, 2>(maps, g2, t256 * tiles_n * g2.split_k, st);
+    }
+    return launch_mt<EPI, OutT, 1>(maps, g, tiles128, st);
+  }
+  const int tiles256 = t256 * tiles_n;
+  if (g_force_mt != 1 && (g_force_mt == 2 || tiles256 >= num_sms())) return launch_mt<EPI, OutT, 2>(maps, g, tiles256, st);
+  return launch_mt<EPI, OutT, 1>(maps, g, tiles128, st);
 }
 
 }  // namespace
 }  // namespace vsx
 
 using namespace vsx;
+
+extern "C" int vsx_gemm_force_tile_rows(int rows) {
+  VSX_REQUIRE(rows == 0 || rows == 128 || rows == 256, "vsx_gemm_force_tile_rows: 0 (heuristic), 128 or 256");
+  g_force_mt = rows / 128;
+  return VSX_OK;
+}
 
 extern "C" int vsx_gemm(const vsx_gemm_desc* d, void* stream) {
   VSX_REQUIRE(d != nullptr, "vsx_gemm: null descriptor");
