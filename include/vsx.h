@@ -113,6 +113,8 @@ typedef struct vsx_gemm_desc {
 int vsx_gemm(const vsx_gemm_desc* d, void* stream);
 /* CTA tile rows: 0 = heuristic (256-row tiles sharing one B box per k block when they fill the machine), 128 / 256 = forced (tests). */
 int vsx_gemm_force_tile_rows(int rows);
+/* Development aid: device buffer of 64 x 8 int64 clock stamps written by CTA 0 of the next GEMM launches (NULL = off). */
+int vsx_gemm_debug_buffer(void* buffer);
 
 /* ----------------------------------------------------------------------------------------------------
  * Attention core -- replaces q@k^T*scale, softmax, attn@v, the head transpose/reshape and the head ChannelDrop

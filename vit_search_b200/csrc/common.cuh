@@ -101,10 +101,15 @@ __device__ __forceinline__ float rcp_approx(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
   return r;
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float half_erfc_abs(float x, float& e) {   // 0.5*erfc(|x|/sqrt2); e = exp(-x^2/2)
   const float z = fabsf(x) * 0.70710678118654752f;
   const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
-  e = __expf(-z * z);
+  e = ex2_approx(z * z * -1.4426950408889634f);      // one MUFU, no range fix-up: underflow to zero is the right answer here
   float p = fmaf(t, 1.061405429f * 0.5f, -1.453152027f * 0.5f);
   p = fmaf(t, p, 1.421413741f * 0.5f);
   p = fmaf(t, p, -0.284496736f * 0.5f);

@@ -42,6 +42,7 @@ constexpr int MAX_STAGES = 5;
 constexpr int SMEM_LIMIT = 227 * 1024;
 constexpr int SMEM_MISC = 1024 /*align*/ + 256 /*barriers, tmem slot*/ + 1024 /*two bias tiles*/;
 
+constexpr int COLACC_MAX = 3072;      // widest output whose bias-gradient column sums are accumulated in shared memory
 constexpr int MAX_TERMS = 6;
 struct TmapPack {
   CUtensorMap a[MAX_TERMS];
@@ -49,6 +50,7 @@ struct TmapPack {
   CUtensorMap out, out2, aux;   // epilogue tiles (128B-swizzled boxes of 128 rows x 128 bytes)
 };
 
+static long long* g_gemm_dbg = nullptr;   // development aid: clock stamps of CTA 0 (tools/gemm_timeline.py)
 static int g_force_mt = 0;   // 0 = heuristic, 1 / 2 = force the 128- / 256-row CTA tile (tests)
 
 struct GemmArgs {
@@ -57,6 +59,7 @@ struct GemmArgs {
   const float* row_scale;
   float* colsum;
   int rows_per_sample, n_keep;
+  long long* dbg;
 };
 
 // Shared-memory matrix descriptor (tcgen05), 128B swizzle.  K-major: rows of 128 B, 8-row groups 1024 B apart (SBO).
@@ -131,15 +134,36 @@ __device__ __forceinline__ void stage_read32<bf16>(const uint8_t* tile, int row,
   }
 }
 
+// Column sums over the 32 lanes (= 32 tile rows) of a warp: on return lane l holds sum_lanes v[l] (31 shuffles, recursive halving).
+__device__ __forceinline__ float warp_colsum32(const float (&in)[32], int lane) {
+  float v[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) v[k] = in[k];
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int k = 0; k < s; ++k) {
+      const float send = up ? v[k] : v[k + s];
+      const float keep = up ? v[k + s] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
 // Per-instantiation shared-memory plan: NBUF staging tiles (epilogue output / aux input), the rest is the operand ring.
 template <int EPI, typename OutT, int MT> struct Plan {
   static constexpr int STAGE_BYTES = Shape<MT>::STAGE_BYTES;
   static constexpr int TILE_BYTES = BM * BN * (int)sizeof(OutT) * (EPI == VSX_EPI_GELU ? 2 : 1);
+  // per-CTA accumulator of the fused bias-gradient column sums (flushed once at the end of the persistent loop: thousands of
+  // per-tile global atomics on a few hundred addresses serialise in L2 and used to dominate the GELU' dgrad GEMMs)
+  static constexpr int COLACC = (EPI == VSX_EPI_GELUGRAD || EPI == VSX_EPI_STORE) ? COLACC_MAX * 4 : 0;
   // two staging tiles when at least three operand stages still fit (the ring has to cover the L2 latency: ~100 KB in flight)
-  static constexpr int NBUF = (2 * TILE_BYTES + 3 * STAGE_BYTES + SMEM_MISC <= SMEM_LIMIT) ? 2 : 1;
-  static constexpr int ROOM = (SMEM_LIMIT - SMEM_MISC - NBUF * TILE_BYTES) / STAGE_BYTES;
+  static constexpr int NBUF = (2 * TILE_BYTES + 3 * STAGE_BYTES + SMEM_MISC + COLACC <= SMEM_LIMIT) ? 2 : 1;
+  static constexpr int ROOM = (SMEM_LIMIT - SMEM_MISC - COLACC - NBUF * TILE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = ROOM > MAX_STAGES ? MAX_STAGES : ROOM;
-  static constexpr int SMEM = STAGES * STAGE_BYTES + NBUF * TILE_BYTES + SMEM_MISC;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + NBUF * TILE_BYTES + SMEM_MISC + COLACC;
   static_assert(STAGES >= 2, "operand ring too small");
 };
 
@@ -176,6 +200,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   auto staged_bar = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + 6 + b); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (2 * MAX_STAGES + 8));
   float* bias_s = reinterpret_cast<float*>(misc + 256);   // [2][BN]
+  float* colacc = reinterpret_cast<float*>(misc + SMEM_MISC - 1024);   // [COLACC_MAX] when P::COLACC != 0 (after the 1 KB alignment slack)
+  const bool use_colacc = P::COLACC != 0 && g.colsum != nullptr && g.n_out <= COLACC_MAX;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (g.M + BM * MT - 1) / (BM * MT), tiles_n = (g.n_out + BN - 1) / BN;
@@ -287,6 +313,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           umma_commit(empty_bar(s));   // slot reusable once these MMAs have read it
         }
         umma_commit(acc_full(ab));     // accumulator complete
+        if (g.dbg != nullptr && blockIdx.x == 0 && j * MT < 64) g.dbg[j * MT * 8 + 7] = clock64();
       }
     }
   } else if (warp == 2) {
@@ -323,6 +350,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         const int ms = m0 + sub * BM;
         const int ncols = min(BN, g.n_out - n0);
         const int nbox = (ncols + BOXC - 1) / BOXC;
+        if (g.dbg != nullptr && blockIdx.x == 0 && un < 64) g.dbg[un * 8 + 5] = clock64();   // store warp starts waiting for unit un
         mbar_wait(staged_bar(sb), (uint32_t)(un / NBUF) & 1u);               // epilogue has staged unit un
         const uint32_t src = stg + sb * P::TILE_BYTES;
         for (int bx = 0; bx < nbox; ++bx) {
@@ -334,6 +362,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           }
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (g.dbg != nullptr && blockIdx.x == 0 && un < 64) g.dbg[un * 8 + 6] = clock64();   // store of unit un issued
         if (NBUF == 1 && tn < total) {
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           announce(tn, subn, 0);
@@ -355,6 +384,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       chalf = ew >> 2;
     }
     const int lim = g.n_keep < g.N ? g.n_keep : g.N;
+    if (use_colacc) {
+      for (int i = et; i < g.n_out; i += EPI_WARPS * 32) colacc[i] = 0.f;
+      named_bar_sync(1, EPI_WARPS * 32);
+    }
     int uses[2] = {0, 0}, j = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
       int m0, n0, kb0, nkb;
@@ -370,11 +403,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         ++uses[ab];
         tc_fence_after();
       }
+      if (g.dbg != nullptr && blockIdx.x == 0 && warp == EPI0 && lane == 0 && j * MT < 64) g.dbg[j * MT * 8 + 4] = clock64();
 #pragma unroll 1
       for (int sub = 0; sub < MT; ++sub) {
         const int un = j * MT + sub, sb = un % NBUF;
         const int ms = m0 + sub * BM, m = ms + row;
+        const bool stamp = g.dbg != nullptr && blockIdx.x == 0 && warp == EPI0 && lane == 0 && un < 64;
+        if (stamp) g.dbg[un * 8 + 0] = clock64();
         mbar_wait(ready_bar(sb), (uint32_t)(un / NBUF) & 1u);      // staging buffer writable (and aux tile landed)
+        if (stamp) g.dbg[un * 8 + 1] = clock64();
         uint8_t* tile = stg_g + sb * P::TILE_BYTES;
         uint8_t* tile2 = tile + NBOX * BOX_BYTES;
         float scale = 1.0f;
@@ -391,15 +428,36 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             for (int jj = 0; jj < 32; ++jj) v[jj] = 0.f;
           }
           const int n = n0 + c;
+          // `full`: all 32 columns of the chunk are real output columns -- the common case runs without per-element predicates
+          // (a predicated expensive expression compiles to one branch per element, which serialises the whole chunk)
+          const bool full = n + 32 <= g.N;
           if (EPI == VSX_EPI_ATOMIC) {
             stage_write32<float>(tile, row, c, v);
           } else if (EPI == VSX_EPI_STORE) {
+            if (full) {
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] + bs[c + jj] : 0.f;
+              for (int jj = 0; jj < 32; ++jj) v[jj] += bs[c + jj];
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] + bs[c + jj] : 0.f;
+            }
             stage_write32<OutT>(tile, row, c, v);
-          } else if (EPI == VSX_EPI_GELU) {
+            if (g.colsum != nullptr) {     // bias gradient of the producing Linear: column sums over the valid rows, from registers
+              if (m >= g.M) {
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] + bs[c + jj] : 0.f;
+                for (int jj = 0; jj < 32; ++jj) v[jj] = 0.f;
+              }
+              const float cs = warp_colsum32(v, lane);
+              if (n + lane < g.N) atomicAdd((use_colacc ? colacc : g.colsum) + n + lane, cs);
+            }
+          } else if (EPI == VSX_EPI_GELU) {
+            if (full) {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) v[jj] += bs[c + jj];
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] + bs[c + jj] : 0.f;
+            }
             stage_write32<OutT>(tile, row, c, v);
 #pragma unroll
             for (int jj = 0; jj < 32; ++jj) v[jj] = gelu_sel<OutT>(v[jj]);   // gelu(0) = 0 keeps the zero fill
@@ -407,46 +465,51 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           } else if (EPI == VSX_EPI_RESIDUAL) {
             float r[32];
             stage_read32<float>(tile, row, c, r);
+            if (n + 32 <= lim) {
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) r[jj] += (n + jj < lim) ? scale * (v[jj] + bs[c + jj]) : 0.f;
+              for (int jj = 0; jj < 32; ++jj) r[jj] = fmaf(scale, v[jj] + bs[c + jj], r[jj]);
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) r[jj] += (n + jj < lim) ? scale * (v[jj] + bs[c + jj]) : 0.f;
+            }
             stage_write32<float>(tile, row, c, r);
           } else if (EPI == VSX_EPI_GELUGRAD) {
             float u[32];
             stage_read32<OutT>(tile, row, c, u);
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] * gelu_grad_sel<OutT>(u[jj]) : 0.f;
+            for (int jj = 0; jj < 32; ++jj) v[jj] *= gelu_grad_sel<OutT>(u[jj]);     // computed for every column, masked below
+            if (!full) {
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] : 0.f;
+            }
             stage_write32<OutT>(tile, row, c, v);
+            if (g.colsum != nullptr) {     // fc1 bias gradient fused into the dgrad epilogue
+              if (m >= g.M) {
+#pragma unroll
+                for (int jj = 0; jj < 32; ++jj) v[jj] = 0.f;
+              }
+              const float cs = warp_colsum32(v, lane);
+              if (n + lane < g.N) atomicAdd((use_colacc ? colacc : g.colsum) + n + lane, cs);
+            }
           }
         }
+        if (stamp) g.dbg[un * 8 + 2] = clock64();
         if (has_mma && sub == MT - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(acc_empty(ab));               // this warp's TMEM reads of the accumulator set are done
         }
-        if ((EPI == VSX_EPI_GELUGRAD || EPI == VSX_EPI_STORE) && g.colsum != nullptr) {
-          // bias gradient fused into the dgrad epilogue: column sums of the staged (already rounded) tile over its valid rows;
-          // all 256 epilogue threads: thread (cc, half) sums column cc over 64 rows, 8 independent loads in flight
-          named_bar_sync(1, EPI_WARPS * 32);
-          const int cc = et & 127, rh = et >> 7;
-          if (n0 + cc < g.N) {
-            const int rbeg = rh * (BM / 2), rend = min(rbeg + BM / 2, g.M - ms);
-            const uint8_t* colp = tile + (cc / BOXC) * BOX_BYTES + (cc % (16 / (int)sizeof(OutT))) * (int)sizeof(OutT);
-            const int chunk = (cc % BOXC) / (16 / (int)sizeof(OutT));
-            float part[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) part[i] = 0.f;
-            for (int r = rbeg; r < rend; r += 8) {
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                if (r + i < rend) part[i] += Store<OutT>::ld(reinterpret_cast<const OutT*>(colp + box_off(r + i, chunk)));
-            }
-            const float a2 = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
-            if (rend > rbeg) atomicAdd(g.colsum + n0 + cc, a2);
-          }
-        }
         fence_proxy_async();                                       // generic-proxy smem writes -> visible to the TMA (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(staged_bar(sb));                // 8 warps -> the store warp may ship the unit
+        if (stamp) g.dbg[un * 8 + 3] = clock64();
+      }
+    }
+    if (use_colacc) {
+      named_bar_sync(1, EPI_WARPS * 32);
+      for (int i = et * 4; i < g.N; i += EPI_WARPS * 32 * 4) {
+        const float4 t4 = *reinterpret_cast<const float4*>(colacc + i);
+        red_add4(g.colsum + i, t4, i, g.N);
       }
     }
   }
@@ -492,7 +555,9 @@ int launch(const TmapPack& maps, const GemmArgs& g, int tiles128, cudaStream_t s
     return launch_mt<EPI, OutT, 1>(maps, g, tiles128, st);
   }
   const int tiles256 = t256 * tiles_n;
-  if (g_force_mt != 1 && (g_force_mt == 2 || tiles256 >= num_sms())) return launch_mt<EPI, OutT, 2>(maps, g, tiles256, st);
+  // GELU writes two output tiles per unit: two staging buffers + three operand stages only fit with 128-row tiles, and its
+  // epilogue (not operand traffic) bounds it
+  if (g_force_mt != 1 && (g_force_mt == 2 || (tiles256 >= num_sms() && EPI != VSX_EPI_GELU))) return launch_mt<EPI, OutT, 2>(maps, g, tiles256, st);
   return launch_mt<EPI, OutT, 1>(maps, g, tiles128, st);
 }
 
@@ -500,6 +565,11 @@ int launch(const TmapPack& maps, const GemmArgs& g, int tiles128, cudaStream_t s
 }  // namespace vsx
 
 using namespace vsx;
+
+extern "C" int vsx_gemm_debug_buffer(void* p) {
+  g_gemm_dbg = static_cast<long long*>(p);
+  return VSX_OK;
+}
 
 extern "C" int vsx_gemm_force_tile_rows(int rows) {
   VSX_REQUIRE(rows == 0 || rows == 128 || rows == 256, "vsx_gemm_force_tile_rows: 0 (heuristic), 128 or 256");
@@ -525,6 +595,7 @@ extern "C" int vsx_gemm(const vsx_gemm_desc* d, void* stream) {
   g.bias = d->bias;
   g.colsum = d->colsum;
   g.row_scale = d->row_scale, g.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1, g.n_keep = d->n_keep;
+  g.dbg = g_gemm_dbg;
 
   TmapPack maps;
   if (d->N > 0 && d->K > 0) {
