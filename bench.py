@@ -55,6 +55,16 @@ def peaks():
         return dict(tflops=1400.0, hbm=6650.0, src='fallback (B200_PROFILING.md)')
 
 
+def gemm_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per GEMM launch (average over the launches of one train step), from the ncu pass
+    summarised by tools/summarize_ncu.py into profiles/gemm_traffic.json; None when that capture is missing."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'gemm_traffic.json')) as f:
+            return json.load(f)['dram_bytes_per_launch']
+    except Exception:
+        return None
+
+
 # ---------------------------------------------------------------------------------------------- CPU arm (oracle port)
 def cpu_steps(space, batch, steps, warmup):
     """The reference's algorithm for this path on the host cores: oracle/vit_res_oracle.py (a restatement of the reference's
@@ -215,11 +225,16 @@ def run_ours(args):
 
     h_loss = torch.empty((), dtype=torch.float32).pin_memory()
 
+    # end to end through the public API: every step uploads its own batch from pinned host memory (engine.DeviceFeeder: side
+    # stream, two device slots, so batch i+1 travels while batch i computes) and reads the loss back
+    from vit_search_b200.engine import DeviceFeeder
+    feeder = DeviceFeeder(dev)
+
     def e2e_step():
-        xs = hx.to(dev, non_blocking=True)
-        ts = ht.to(dev, non_blocking=True)
-        pts = hpt.to(dev, non_blocking=True)
+        feeder.submit(hx, ht, hpt)             # batch i+1 (the first call of a window primes the pipeline with an extra submit)
+        xs, ts, pts = feeder.next()
         loss = step(xs, ts, pts, epoch=0)
+        feeder.release()
         h_loss.copy_(loss, non_blocking=True)
 
     n_warm = max(args.warmup, 3 if world == 1 else 8)   # DDP rebuilds its buckets after the first backward and the caching
@@ -230,8 +245,10 @@ def run_ours(args):
     ms = timed(dev_step, args.steps)
     launches = ops.LAUNCHES
     clk = clocks.stop() if clocks is not None else None
+    feeder.submit(hx, ht, hpt)
     e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)
+    ms_e2e = timed(e2e_step, args.steps)       # K steps = K uploads + K train steps + K loss read-backs inside the window
+    feeder.next(), feeder.release()            # drain the batch left in flight
     torch.cuda.synchronize()
     loss_val = float(h_loss)
 
@@ -242,7 +259,12 @@ def run_ours(args):
     torch.cuda.synchronize()
     gemm_ms = sum(r[0].elapsed_time(r[1]) for r in ops.PROFILE)
     gemm_flops = sum(r[2] for r in ops.PROFILE)
+    gemm_bytes = sum(r[4] for r in ops.PROFILE)
     n_gemm = len(ops.PROFILE)
+    pk0 = peaks()
+    # two-resource roofline of the same launches: each launch can be no faster than max(flops / tensor peak, bytes / HBM peak)
+    gemm_floor_ms = sum(max(r[2] / (pk0['tflops'] * 1e12), r[4] / (pk0['hbm'] * 1e9)) for r in ops.PROFILE) * 1e3
+    n_hbm_bound = sum(1 for r in ops.PROFILE if r[4] / (pk0['hbm'] * 1e9) > r[2] / (pk0['tflops'] * 1e12))
     ops.PROFILE = None
     keeps = model.last_keeps
     step_macs = sum(macs.network_macs(macs.effective_network_def(nd, keeps, b)) for b in range(B))
@@ -263,7 +285,11 @@ def run_ours(args):
                     'ms_per_step': ms_e2e / args.steps},
             'gpu_launches': launches,
             'roofline': {'bound': 'tensor', 'kernel': 'gemm_tc_kernel (tcgen05 GEMM, all epilogues: fwd, dgrad, wgrad)',
-                         'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'], 'traffic': None,
+                         'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
+                         'traffic': gemm_traffic(), 'algorithmic_bytes_per_launch': gemm_bytes / max(n_gemm, 1),
+                         'hbm_view': {'achieved': gemm_bytes / (gemm_ms * 1e-3) / 1e9 if gemm_ms > 0 else 0.0, 'peak': pk['hbm'], 'unit': 'GB/s',
+                                      'launches_hbm_bound': n_hbm_bound, 'launches': n_gemm,
+                                      'frac_of_two_resource_floor': gemm_floor_ms / gemm_ms if gemm_ms > 0 else 0.0},
                          'peak_source': pk['src'], 'launches_per_step': n_gemm // 2, 'kernel_ms_per_step': gemm_ms / 2,
                          'kernel_share_of_step': (gemm_ms / 2) / ms_step,
                          'how': 'algorithmic 2*M*N*K of the kept extents per launch / CUDA-event time of each launch, 2 instrumented steps after the timed region',

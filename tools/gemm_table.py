@@ -29,7 +29,7 @@ ops.PROFILE = []
 step(x, t, pt)
 torch.cuda.synchronize()
 agg = collections.OrderedDict()
-for e0, e1, fl, key in ops.PROFILE:
+for e0, e1, fl, key, _nbytes in ops.PROFILE:
     a = agg.setdefault(key, [0, 0.0, 0.0])
     a[0] += 1
     a[1] += e0.elapsed_time(e1)

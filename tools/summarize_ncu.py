@@ -55,7 +55,7 @@ def gemm_dram(path, out, steps=2):
         d = by_id.setdefault(int(r['ID']), {'name': short(r['Kernel Name'])})
         d[r['Metric Name']] = (float(r['Metric Value'].replace(',', '')), r['Metric Unit'])
     ids = list(by_id)
-    ids = ids[-(len(ids) // steps):]
+    ids = ids[-(len(ids) // steps):]          # GEMM launches of the last step (both steps launch the same number)
 
     def val(d, k, want):
         v, u = d[k]
@@ -82,7 +82,12 @@ def gemm_dram(path, out, steps=2):
             T += t
             B += b
         f.write('| **all** | %d | %.3f | %.3f | %.0f | | |\n' % (sum(v[0] for v in agg.values()), T * 1e3, B / 1e9, B / T / 1e9))
-    return B / max(1, sum(v[0] for v in agg.values()))
+    per_launch = B / max(1, sum(v[0] for v in agg.values()))
+    import json
+    with open(out.replace('_gemm_dram.md', '').rsplit('/', 1)[0] + '/gemm_traffic.json', 'w') as f:
+        json.dump({'dram_bytes_per_launch': per_launch, 'launches': sum(v[0] for v in agg.values()), 'total_ms': T * 1e3,
+                   'source': out, 'command': 'ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,... -k regex:gemm_tc python tools/ncu_step.py sr_tiny 256 2'}, f)
+    return per_launch
 
 
 if __name__ == '__main__':

@@ -408,9 +408,13 @@ constexpr int BWD_THREADS = 448;           // 14 warps: producer, MMA, 8 softmax
 constexpr int EP_WARP0 = 10;
 // staging: [P0 | dS0 | P1 | dS1]
 constexpr int B_KV = 0, B_QDO = 4 * BOX8K, B_STG = B_QDO + 6 * TILE16K, B_END = B_STG + 4 * TILE16K;
-constexpr int B_MISC = 128 /*barriers*/ + 3 * 64 * 4 /*cs*/ + 2 * 3 * 128 * 8 /*stats*/ + 16 /*tmem slot*/;
+constexpr int B_MISC = 256 /*barriers*/ + 3 * 64 * 4 /*cs*/ + 2 * 3 * 128 * 8 /*stats*/ + 16 /*tmem slot*/;
 constexpr int B_SMEM = B_END + 1024 + B_MISC;
 constexpr int C_S = 0, C_DP = 64, C_DVK = 128, C_DQ = 256;
+// N <= 128 (one query tile): the accumulators are double buffered across key blocks / pairs so that the MMA thread never waits for the
+// epilogue warps: [dV|dK] at 128 / 256, dQ at 384 / 448.  N > 128: single buffers, dQ tiles at 256, 320, 384.
+__device__ __forceinline__ int dvk_col(int nbuf, int kvit) { return C_DVK + (nbuf == 2 ? 128 * (kvit & 1) : 0); }
+__device__ __forceinline__ int dq_col(int nbuf, int pair, int i) { return nbuf == 2 ? 384 + 64 * (pair & 1) : C_DQ + 64 * i; }
 
 // Q_i / dO_i tiles stay resident for all key blocks of their (sample, head): three 32 KB slots used as a ring over the global
 // tile counter t = (pairs done) * QT + i, loaded once per pair (at j == 0) and released after the last key block.
@@ -440,15 +444,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
   const uint32_t bar0 = base + B_END;
   auto bar = [&](int i) { return bar0 + 8u * i; };
   // barriers: 0-1 kv_full, 2-3 kv_empty, 4-6 q_full, 7-9 q_empty
-  constexpr int BAR_SDP = 10, BAR_PDS = 11, BAR_DKV_FULL = 12, BAR_DKV_EMPTY = 13, BAR_DQ_FULL = 14, BAR_DQ_EMPTY = 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + B_END + 128 + 768 + 6144);
+  constexpr int BAR_SDP = 10, BAR_PDS = 11, BAR_DKV_FULL = 12, BAR_DKV_EMPTY = 14, BAR_DQ_FULL = 16, BAR_DQ_EMPTY = 18;   // two of each
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + B_END + 256 + 768 + 6144);
   // stats are handed over with named barriers (ids 2, 3: one per buffer): epilogue warps arrive, softmax warps sync
-  float* cs = reinterpret_cast<float*>(smem + B_END + 128);        // [3][64] column sums of dQ, dK, dV (this CTA's head)
-  float2* stats = reinterpret_cast<float2*>(smem + B_END + 128 + 768);   // [2 buffers][3 tiles][128 rows] (lse * log2e, delta)
+  float* cs = reinterpret_cast<float*>(smem + B_END + 256);        // [3][64] column sums of dQ, dK, dV (this CTA's head)
+  float2* stats = reinterpret_cast<float2*>(smem + B_END + 256 + 768);   // [2 buffers][3 tiles][128 rows] (lse * log2e, delta)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = a.N, HD = a.H * HD_;
   const int QT = (N + 127) / 128, KB = (N + BKW - 1) / BKW;
+  const int nbuf = QT == 1 ? 2 : 1;          // accumulator buffers (see dvk_col / dq_col)
   // this CTA's head and its samples: gridDim.x is a multiple of Hk
   const int h = blockIdx.x % a.Hk, slot = blockIdx.x / a.Hk, nslots = gridDim.x / a.Hk;
 
@@ -459,7 +464,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int i = 0; i < 16; ++i) mbar_init(bar(i), i == BAR_PDS ? 8 : (i == BAR_DKV_EMPTY || i == BAR_DQ_EMPTY) ? 4 : 1);
+      for (int i = 0; i < 20; ++i) mbar_init(bar(i), i == BAR_PDS ? 8 : ((i >= BAR_DKV_EMPTY && i < BAR_DKV_EMPTY + 2) || i >= BAR_DQ_EMPTY) ? 4 : 1);
       fence_mbar_init();
     }
     __syncwarp();
@@ -527,8 +532,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
       if (nx.b < a.B) issue_sdp(nx);
       if (a.dbg != nullptr && blockIdx.x == 0 && leader && c.n < 64) a.dbg[c.n * 8 + 1] = clock64();
       // accumulators about to be overwritten (first block of a key block / of a pair) must have been drained by the epilogue warps
-      if (c.i == 0) mbar_wait(bar(BAR_DKV_EMPTY), ((uint32_t)c.kvit & 1u) ^ 1u);
-      if (c.i == 0 && c.j == 0) mbar_wait(bar(BAR_DQ_EMPTY), ((uint32_t)c.pair & 1u) ^ 1u);
+      if (c.i == 0) mbar_wait(bar(BAR_DKV_EMPTY + c.kvit % nbuf), ((uint32_t)(c.kvit / nbuf) & 1u) ^ 1u);
+      if (c.i == 0 && c.j == 0) mbar_wait(bar(BAR_DQ_EMPTY + c.pair % nbuf), ((uint32_t)(c.pair / nbuf) & 1u) ^ 1u);
       tc_fence_after();
       const int ks = c.kvit & 1, qs = c.tile() % 3;
       const uint32_t ka = base + B_KV + ks * 2 * BOX8K, qa = base + B_QDO + qs * 2 * TILE16K;
@@ -539,16 +544,16 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
       const uint32_t acc_i = c.i != 0 ? 1u : 0u, acc_j = c.j != 0 ? 1u : 0u;
 #pragma unroll
       for (int k = 0; k < 8; ++k)       // a 16-row k step = 2048 B = 128 descriptor units
-        if (leader && k < kq) umma_bf16(tmem + C_DVK, d_pds + 128 * k, d_qdo + 128 * k, id_vk, k > 0 ? 1u : acc_i);
+        if (leader && k < kq) umma_bf16(tmem + dvk_col(nbuf, c.kvit), d_pds + 128 * k, d_qdo + 128 * k, id_vk, k > 0 ? 1u : acc_i);
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
-        if (leader && kk * 16 < kw) umma_bf16(tmem + C_DQ + 64 * c.i, d_dsk + 2 * kk, d_k + 128 * kk, id_q, kk > 0 ? 1u : acc_j);
+        if (leader && kk * 16 < kw) umma_bf16(tmem + dq_col(nbuf, c.pair, c.i), d_dsk + 2 * kk, d_k + 128 * kk, id_q, kk > 0 ? 1u : acc_j);
       if (leader) {
         if (c.j == KB - 1) umma_commit(bar(7 + qs));     // last key block: this query tile's slot may be reloaded
         if (c.i == QT - 1) {
           umma_commit(bar(2 + ks));
-          umma_commit(bar(BAR_DKV_FULL));
-          if (c.j == KB - 1) umma_commit(bar(BAR_DQ_FULL));
+          umma_commit(bar(BAR_DKV_FULL + c.kvit % nbuf));
+          if (c.j == KB - 1) umma_commit(bar(BAR_DQ_FULL + c.pair % nbuf));
         }
       }
       __syncwarp();
@@ -691,7 +696,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
 #pragma unroll
       for (int t = 0; t < 32; ++t) csum[0][t] = 0.f, csum[1][t] = 0.f;
       for (int j = 0; j < KB; ++j, ++nkv) {
-        mbar_wait(bar(BAR_DKV_FULL), (uint32_t)nkv & 1u);
+        mbar_wait(bar(BAR_DKV_FULL + nkv % nbuf), (uint32_t)(nkv / nbuf) & 1u);
         tc_fence_after();
         const int keys_valid = min(BKW, N - j * BKW);
         if ((q & 1) * 32 < keys_valid) {
@@ -700,7 +705,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             float v[32];
-            tmem_ld32(tlane + C_DVK + (is_v ? 64 : 0) + half * 32, v);
+            tmem_ld32(tlane + dvk_col(nbuf, nkv) + (is_v ? 64 : 0) + half * 32, v);
             tmem_ld_wait();
             if (kvalid) {
 #pragma unroll
@@ -714,14 +719,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(bar(BAR_DKV_EMPTY));
+        if (lane == 0) mbar_arrive(bar(BAR_DKV_EMPTY + nkv % nbuf));
       }
       if (a.dbias != nullptr) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) atomicAdd(cs + (is_v ? 128 : 64) + half * 32 + lane, butterfly_colsum(csum[half], lane));
       }
       // dQ: all query tiles are complete after the last key block
-      mbar_wait(bar(BAR_DQ_FULL), (uint32_t)pair & 1u);
+      mbar_wait(bar(BAR_DQ_FULL + pair % nbuf), (uint32_t)(pair / nbuf) & 1u);
       tc_fence_after();
 #pragma unroll
       for (int t = 0; t < 32; ++t) csum[0][t] = 0.f, csum[1][t] = 0.f;
@@ -733,7 +738,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
               float v[32];
-              tmem_ld32(tlane + C_DQ + 64 * i + half * 32, v);
+              tmem_ld32(tlane + dq_col(nbuf, pair, i) + half * 32, v);
               tmem_ld_wait();
               if (row < rows_valid) {
 #pragma unroll
@@ -749,7 +754,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(bar(BAR_DQ_EMPTY));
+      if (lane == 0) mbar_arrive(bar(BAR_DQ_EMPTY + pair % nbuf));
       if (a.dbias != nullptr) {
 #pragma unroll
         for (int half = 0; half < 2; ++half) atomicAdd(cs + half * 32 + lane, butterfly_colsum(csum[half], lane));

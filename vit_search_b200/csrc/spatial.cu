@@ -66,6 +66,37 @@ __global__ void im2col_kernel(const TI* __restrict__ in1, const float* __restric
   }
 }
 
+// conv1 of the stem (patch_conv.py:25-30): fp32 NCHW image, 3 channels, 3x3, stride 2, pad 1 -> bf16 rows of 27 (+5 zero) columns.
+// One thread per output pixel: 27 image loads (neighbouring threads share them through L1) and ONE 64-byte row written with four
+// 16-byte stores, instead of one thread per (pixel, tap) writing three 2-byte values.
+__global__ void __launch_bounds__(256) im2col_conv1_kernel(const float* __restrict__ img, int B, int H, int W, int Ho, int Wo,
+                                                           bf16* __restrict__ out) {
+  const long total = (long)B * Ho * Wo;
+  for (long pix = (long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long)gridDim.x * blockDim.x) {
+    const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long)Wo * Ho));
+    const float* src = img + (long)b * 3 * H * W;
+    float v[32];
+#pragma unroll
+    for (int i = 27; i < 32; ++i) v[i] = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = 2 * oy - 1 + ky;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = 2 * ox - 1 + kx;
+        const bool in = iy >= 0 && iy < H && ix >= 0 && ix < W;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) v[(ky * 3 + kx) * 3 + c] = in ? __ldg(src + ((long)c * H + iy) * W + ix) : 0.f;
+      }
+    }
+    uint4* o = reinterpret_cast<uint4*>(out + pix * 32);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      o[i] = make_uint4(pack_bf16(v[8 * i], v[8 * i + 1]), pack_bf16(v[8 * i + 2], v[8 * i + 3]), pack_bf16(v[8 * i + 4], v[8 * i + 5]),
+                        pack_bf16(v[8 * i + 6], v[8 * i + 7]));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ col2im
 // din[b, iy, ix, c] = (add ? add[...] : 0) + sum over taps (ky,kx) with oy = (iy+p-ky)/s, ox = (ix+p-kx)/s integral and in
 // range of dcol[(b,oy,ox), (ky*k+kx)*C + c].  One thread per (input pixel, 4 channels).
@@ -349,7 +380,10 @@ __global__ void sr_combine_bwd_kernel(const float* __restrict__ gy, T* __restric
     const int c = (int)(i % c4n) * 4;
     const int t = (int)(i / c4n);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int b = 0; b < nb; ++b) {
+    // blockIdx.y splits the batch (the position-embedding gradient is the only cross-sample reduction: one atomic per chunk)
+    const int bper = (nb + gridDim.y - 1) / gridDim.y;
+    const int b_lo = blockIdx.y * bper, b_hi = min(nb, b_lo + bper);
+    for (int b = b_lo; b < b_hi; ++b) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < keep2) {
         v = ld4(gy + ((long)b * N2 + t) * C2 + c);
@@ -373,7 +407,7 @@ __global__ void sr_combine_bwd_kernel(const float* __restrict__ gy, T* __restric
         }
       }
     }
-    if (t > 0) {
+    if (t > 0 && b_hi > b_lo) {
       float* dp = dpos + (long)(t - 1) * C2 + c;
       atomicAdd(dp, acc.x), atomicAdd(dp + 1, acc.y), atomicAdd(dp + 2, acc.z), atomicAdd(dp + 3, acc.w);
     }
@@ -402,6 +436,11 @@ extern "C" int vsx_im2col(const void* in1, const float* scale1, const float* shi
   const int grid = grid_for((long)B * Ho * Wo * k * k);
   if (nchw) {
     VSX_REQUIRE(in_dtype == VSX_F32 && in2 == nullptr && scale1 == nullptr, "vsx_im2col: NCHW input is the fp32 image, no fused activation");
+    if (out_dtype == VSX_BF16 && C == 3 && k == 3 && stride == 2 && pad == 1 && ldo == 32 && batch_pitch == 3L * H * W &&
+        (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+      im2col_conv1_kernel<<<grid_for((long)B * Ho * Wo), 256, 0, ST>>>((const float*)in1, B, H, W, Ho, Wo, (bf16*)out);
+      return check_launch("vsx_im2col");
+    }
     if (out_dtype == VSX_BF16)
       im2col_kernel<float, bf16, true><<<grid, 256, 0, ST>>>((const float*)in1, nullptr, nullptr, nullptr, nullptr, nullptr, batch_pitch,
                                                               pix_pitch, B, H, W, C, k, stride, pad, Ho, Wo, (bf16*)out, ldo);
@@ -508,7 +547,11 @@ extern "C" int vsx_sr_combine_bwd(const float* gy, void* dconv, void* dtok, int 
   VSX_REQUIRE(C1 % 4 == 0 && C2 % 4 == 0 && C2 >= C1 && grid_in % 2 == 0 && keep2 >= 0 && keep2 <= C2, "vsx_sr_combine_bwd: bad shape");
   if (batch == 0) return VSX_OK;
   const int N2 = 1 + (grid_in / 2) * (grid_in / 2);
-  const int grid = grid_for((long)N2 * C2 / 4);
+  const int gx = grid_for((long)N2 * C2 / 4);
+  int gy_ = (4 * num_sms() + gx - 1) / gx;          // enough batch chunks for ~4 CTAs per SM
+  if (gy_ > batch) gy_ = batch;
+  if (gy_ < 1) gy_ = 1;
+  const dim3 grid(gx, gy_);
   if (dtype == VSX_BF16) sr_combine_bwd_kernel<bf16><<<grid, 256, 0, ST>>>(gy, (bf16*)dconv, (bf16*)dtok, dpos, gres, batch, grid_in, C1, C2, keep2);
   else sr_combine_bwd_kernel<float><<<grid, 256, 0, ST>>>(gy, (float*)dconv, (float*)dtok, dpos, gres, batch, grid_in, C1, C2, keep2);
   return check_launch("vsx_sr_combine_bwd");

@@ -176,6 +176,53 @@ class TrainStep:
         return loss.detach()
 
 
+class DeviceFeeder:
+    """Host -> device input pipeline of the train step (the reference does `samples.to(device, non_blocking=True)` on the compute
+    stream, engine.py:104-105, so every step waits for its own 170 MB upload).  Uploads run on a side stream into one of two
+    device slots while the previous step computes; `next()` hands the slot to the compute stream through an event.
+
+        feeder = DeviceFeeder(device)
+        feeder.submit(samples, targets, patch_targets)        # pinned host tensors of batch i+1
+        x, t, pt = feeder.next()                              # device tensors of batch i (waits only for its copy)
+    """
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.slots = [None, None]
+        self.events = [torch.cuda.Event(), torch.cuda.Event()]
+        self.free = [torch.cuda.Event(), torch.cuda.Event()]     # recorded on the compute stream when a slot's step has been queued
+        self.used = [False, False]
+        self.head = self.tail = 0
+
+    def submit(self, *host_tensors):
+        i = self.head & 1
+        assert self.head - self.tail < 2, 'DeviceFeeder: two batches are already in flight'
+        with torch.cuda.stream(self.stream):
+            if self.used[i]:
+                self.stream.wait_event(self.free[i])        # the step that read this slot has finished
+            if self.slots[i] is None or any(d.shape != h.shape or d.dtype != h.dtype for d, h in zip(self.slots[i], host_tensors)):
+                self.slots[i] = tuple(torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in host_tensors)
+            for d, h in zip(self.slots[i], host_tensors):
+                d.copy_(h, non_blocking=True)
+            self.events[i].record(self.stream)
+        self.head += 1
+
+    def next(self):
+        assert self.tail < self.head, 'DeviceFeeder: nothing submitted'
+        i = self.tail & 1
+        torch.cuda.current_stream(self.device).wait_event(self.events[i])
+        self.tail += 1
+        self._last = i
+        return self.slots[i]
+
+    def release(self):
+        """Call after the step that consumed the last `next()` has been queued on the compute stream."""
+        i = self._last
+        self.free[i].record(torch.cuda.current_stream(self.device))
+        self.used[i] = True
+
+
 def allreduce_gradients(model, world_size):
     """Gradient all-reduce (SUM / world) over NCCL when the model is not wrapped in DistributedDataParallel: one flat
     fp32 bucket per ~64 MB, reduced in place."""

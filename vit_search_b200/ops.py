@@ -101,7 +101,14 @@ def gemm(a, b, lda, ldb, M, N, K, epilogue, out, ldo, *, a_off=0, b_off=0, out_o
         e0.record()
         _ck(_lib.lib().vsx_gemm(C.byref(d), _stream()))
         e1.record()
-        PROFILE.append((e0, e1, 2.0 * M * N * K, (M, N, K, epilogue, a_layout, b_layout, d.n_out, split_k, nterms)))
+        # algorithmic HBM bytes of the launch: both operands once + the output tile(s) + the aux tile the epilogue reads
+        es = 4 if out.dtype == torch.float32 else 2
+        nbytes = 2.0 * nterms * (M * K + N * K) + es * M * d.n_out * (2 if epilogue == EPI_GELU else 1)
+        if epilogue in (EPI_RESIDUAL, EPI_GELUGRAD):
+            nbytes += es * M * d.n_out
+        if epilogue == EPI_ATOMIC:
+            nbytes += es * M * d.n_out          # read-modify-write of the fp32 gradient tile
+        PROFILE.append((e0, e1, 2.0 * M * N * K, (M, N, K, epilogue, a_layout, b_layout, d.n_out, split_k, nterms), nbytes))
         return
     _ck(_lib.lib().vsx_gemm(C.byref(d), _stream()))
 
