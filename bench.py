@@ -187,11 +187,15 @@ def run_ours(args):
     model.set_epoch(0)
     model.train()
     core.set_precision('bf16')
+    use_ddp = bool(int(os.environ.get('VSX_BENCH_DDP', '0')))      # 1: torch DistributedDataParallel wrapper instead of the native exchange
     net = model
-    if world > 1:
+    if world > 1 and use_ddp:
         net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], gradient_as_bucket_view=True)
+    elif world > 1:
+        from vit_search_b200.engine import broadcast_parameters
+        broadcast_parameters(model)
     opt = FusedAdamW(model, lr=LR * B * world / 512.0, weight_decay=WD)
-    step = TrainStep(model, opt, arch_sample='single', world_size=world, ddp_model=net if world > 1 else None)
+    step = TrainStep(model, opt, arch_sample='single', world_size=world, ddp_model=net if (world > 1 and use_ddp) else None)
 
     g = torch.Generator().manual_seed(1234 + rank)
     hx = torch.randn(B, 3, 224, 224, generator=g).pin_memory()
@@ -279,6 +283,7 @@ def run_ours(args):
             'dtype': 'bf16', 'data': 'synthetic',
             'config': {'workload': WORKLOAD, 'space': args.space, 'batch_per_gpu': B, 'archs_per_step': 1, 'drop_path': DROP_PATH,
                        'optimizer': 'AdamW (fused)', 'parallelism': 'dp%d' % world,
+                       'grad_exchange': 'none' if world == 1 else ('torch DDP' if use_ddp else 'in-place NCCL all-reduce of the flat gradient pool, overlapped with the stem backward'),
                        'l2': 'inputs larger than L2: every step streams >10 GB of activations, no tensor survives in the 126 MB L2'},
             'e2e': {'value': world * B * args.steps / (ms_e2e * 1e-3), 'unit': 'images/sec',
                     'h2d_bytes_per_step': hx.numel() * 4 + ht.numel() * 4 + hpt.numel() * 4, 'd2h_bytes_per_step': 4,

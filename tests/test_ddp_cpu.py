@@ -25,6 +25,23 @@ def _worker(rank, world, port, q):
         p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
     allreduce_gradients(m, world)
     ok = all(torch.allclose(p.grad, torch.full_like(p, 1.5 * (i + 1))) for i, p in enumerate(m.parameters()))
+    # the native exchange of engine.TrainStep: gradients are views of one flat pool (all-reduced in place, the first part possibly
+    # already done by the backward hook) + gradients living outside the pool (one flattened bucket); SUM, scaled later by the optimizer
+    from vit_search_b200.engine import exchange_pool_gradients
+    ps = list(m.parameters())
+    flat = torch.zeros(2048)
+    off = 0
+    for i, p in enumerate(ps[:3]):
+        n = (p.numel() + 3) // 4 * 4
+        p.grad = flat[off:off + p.numel()].view(p.shape)
+        p.grad.fill_(float(rank + 1) * (i + 1))
+        off += n
+    ps[3].grad = torch.full_like(ps[3], float(rank + 1) * 4)          # outside the pool
+    first = (ps[0].numel() + 3) // 4 * 4
+    dist.all_reduce(flat[:first])                                      # what the hook does for the early part
+    exchange_pool_gradients(flat, off, first, ps)
+    ok = ok and all(torch.allclose(p.grad, torch.full_like(p, 3.0 * (i + 1))) for i, p in enumerate(ps))
+    ok = ok and all(p.grad.data_ptr() >= flat.data_ptr() and p.grad.data_ptr() < flat.data_ptr() + 4 * off for p in ps[:3])
     q.put((rank, ok))
     dist.destroy_process_group()
 

@@ -195,6 +195,7 @@ class _GradPool:
 
 
 grad_pool = _GradPool()
+trunk_grads_ready_hook = None    # set by engine.TrainStep for data-parallel runs (see nets/vit_sr_supernet.py forward_features)
 
 
 def zeros_like_many(*tensors):

@@ -453,7 +453,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = a.N, HD = a.H * HD_;
   const int QT = (N + 127) / 128, KB = (N + BKW - 1) / BKW;
-  const int nbuf = QT == 1 ? 2 : 1;          // accumulator buffers (see dvk_col / dq_col)
+  // accumulator buffers (see dvk_col / dq_col).  Double buffering for N <= 128 is wired up but measured 10 % SLOWER on the N = 17
+  // launches (profiles/: r1l vs r1k; the epilogue warps then compete with the softmax warps for tcgen05.ld bandwidth instead of
+  // running in the shadow of the MMA wait), so every shape runs single buffered.
+  const int nbuf = 1;
   // this CTA's head and its samples: gridDim.x is a multiple of Hk
   const int h = blockIdx.x % a.Hk, slot = blockIdx.x / a.Hk, nslots = gridDim.x / a.Hk;
 

@@ -114,7 +114,9 @@ class FusedAdamW:
         self._tab = core.h2d(torch.from_numpy(rec.view(np.uint8)), dev)
         self._tab_has_shadow = bool((rec['hi'] != 0).any())
 
-    def step(self):
+    def step(self, grad_scale=None):
+        """grad_scale: optional fp32 device scalar multiplied into every gradient inside the kernel (1 / world_size after a SUM
+        all-reduce; a loss-scaler's inverse scale)."""
         # gradient tensors are re-allocated by every backward, parameters by `rewiring`: re-derive the pointer table when
         # any pointer changed (a host-side comparison of ~250 integers)
         key = (core.get_precision(),) + tuple((p.data_ptr(), 0 if p.grad is None else p.grad.data_ptr()) for _, p, _ in self.entries)
@@ -124,7 +126,7 @@ class FusedAdamW:
         self.step_count += 1
         self.lr = self.param_groups[0]['lr']
         ops.call('adamw', self._tab, self._ct, self._ci, self._nchunks, float(self.lr), float(self.betas[0]), float(self.betas[1]),
-                 float(self.eps), self.step_count, None)
+                 float(self.eps), self.step_count, grad_scale)
         core.weights.generation += 1      # parameters were written through raw pointers: operand copies are stale ...
         if self._tab_has_shadow:          # ... except the shadows this launch has just rewritten
             for name, p, _ in self.entries:
@@ -146,6 +148,13 @@ class TrainStep:
         self.world_size = world_size
         self.train_iter = 0
         self._pool_numel = None
+        # native data parallelism (world_size > 1 and no DDP wrapper): all parameter gradients of a step live in ONE flat pool
+        # (core.grad_pool), so the exchange is an in-place NCCL all-reduce of that buffer -- no bucket copies, no per-parameter hooks.
+        # The part produced by the transformer / SR blocks is reduced on a side stream while the stem backward still runs.
+        self._native_dp = world_size > 1 and ddp_model is None
+        self._comm_stream = None
+        self._inv_world = None
+        self._hook_off = 0
 
     def __call__(self, samples, targets, patch_targets, epoch=0):
         """samples [B,3,224,224], targets [B,K], patch_targets [B,16,K] on the GPU.  Returns the loss as a device scalar
@@ -166,14 +175,71 @@ class TrainStep:
         if self._pool_numel is None:          # every gradient buffer padded to a multiple of 4 elements + slack for meta placeholders
             self._pool_numel = sum((p.numel() + 3) // 4 * 4 + 8 for p in self.model.parameters()) + 4096
         core.grad_pool.begin(self._pool_numel, samples.device)
+        flat = core.grad_pool.flat
+        if self._native_dp:
+            self._arm_overlap(flat)
         try:
             loss.backward()
+            used = core.grad_pool.off
         finally:
             core.grad_pool.end()
-        if self.world_size > 1 and self.net is self.model:
-            allreduce_gradients(self.model, self.world_size)
-        self.optimizer.step()
+            core.trunk_grads_ready_hook = None
+        if self._native_dp:
+            self._finish_allreduce(flat, used)
+            self.optimizer.step(grad_scale=self._inv_world)
+        else:
+            self.optimizer.step()
         return loss.detach()
+
+    # ------------------------------------------------------------------ native data parallelism
+    def _arm_overlap(self, flat):
+        import torch.distributed as dist
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream(device=flat.device)
+            self._inv_world = torch.full((1,), 1.0 / self.world_size, device=flat.device)
+        self._hook_off = 0
+
+        def hook(grad):
+            # gradients of every block are complete in flat[:off]; the stem backward that follows only appends behind `off`
+            off = core.grad_pool.off
+            if off > 0:
+                ready = torch.cuda.Event()
+                ready.record()
+                with torch.cuda.stream(self._comm_stream):
+                    self._comm_stream.wait_event(ready)
+                    dist.all_reduce(flat[:off])
+                self._hook_off = off
+            return grad
+        core.trunk_grads_ready_hook = hook
+
+    def _finish_allreduce(self, flat, used):
+        exchange_pool_gradients(flat, used, self._hook_off, self.model.parameters(), self._comm_stream)
+
+
+def exchange_pool_gradients(flat, used, reduced_upto, params, comm_stream=None):
+    """SUM all-reduce of one step's gradients: flat[reduced_upto:used] in place (flat[:reduced_upto] was already put on
+    `comm_stream` by the backward hook), plus one small flattened bucket for gradients that do not live in the pool (re-laid-out conv
+    weights, BN affine parameters).  The 1/world factor is applied by the optimizer kernel (FusedAdamW.step(grad_scale=...))."""
+    import torch.distributed as dist
+    if used > reduced_upto:
+        dist.all_reduce(flat[reduced_upto:used])
+    lo, hi = flat.data_ptr(), flat.data_ptr() + used * flat.element_size()
+    rest = [p.grad for p in params if p.grad is not None and not (lo <= p.grad.data_ptr() < hi)]
+    if rest:
+        bucket = torch._utils._flatten_dense_tensors(rest)
+        dist.all_reduce(bucket)
+        for g, f in zip(rest, torch._utils._unflatten_dense_tensors(bucket, rest)):
+            g.copy_(f)
+    if comm_stream is not None and flat.is_cuda:
+        torch.cuda.current_stream(flat.device).wait_stream(comm_stream)   # the overlapped part must have landed before the optimizer
+        flat.record_stream(comm_stream)
+
+
+def broadcast_parameters(model, src=0):
+    """Make every rank start from rank `src`'s parameters and buffers (what DistributedDataParallel does at construction)."""
+    import torch.distributed as dist
+    for t in list(model.parameters()) + list(model.buffers()):
+        dist.broadcast(t.data, src)
 
 
 class DeviceFeeder:

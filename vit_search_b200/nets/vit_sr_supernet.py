@@ -495,6 +495,10 @@ class FlexibleDistillVisionTransformerSR(nn.Module):
         h = self.patch_embed(x)
         embed_keep = keeps[0].get('embed')
         h = _EmbedAssembleFn.apply(h, self.tokens, self.pos_embed, embed_keep)
+        if core.trunk_grads_ready_hook is not None and h.requires_grad:
+            # fires in backward once every transformer / SR block has produced its parameter gradients and only the stem is left:
+            # engine.TrainStep starts the gradient all-reduce of that part of the gradient pool there (overlaps the stem backward)
+            h.register_hook(core.trunk_grads_ready_hook)
         layer_keep = None
         j = t = 0
         for i, d in enumerate(self.network_def):
