@@ -6,6 +6,8 @@
 // The reference spends ~15 ATen passes over [B,N,C] per direction; here each direction is one pass:
 //   forward : read x fp32 (4 B/ch), write y bf16 (2 B/ch) + 8 B/row of statistics
 //   backward: read dy (2 B) + x (4 B) + g_in (4 B), write g_out (4 B); dgamma/dbeta via per-CTA partials + atomics
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace vsx {
@@ -169,6 +171,114 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T* __restri
   }
 }
 
+
+// ---------------------------------------------------------------- backward with bulk-copy (TMA 1-D) row prefetch
+// Same arithmetic as ln_bwd_kernel, different memory pipeline: every warp owns two shared-memory row slots; lane 0 issues
+// cp.async.bulk copies of the NEXT row (dy, x, g_in: up to 10 B/channel) into one slot while the warp works on the other, completion
+// on one mbarrier per slot.  The per-warp register tile (d, z, g_in) of the plain kernel disappears -- rows are re-read from shared
+// memory -- so occupancy is no longer register-bound at C = 512 / 1024, and ~100 KB of loads are in flight per SM.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+
+template <int NV, typename T>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_bulk_kernel(const T* __restrict__ dy, long lddy, const float* __restrict__ x, long ldx,
+                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                     const float* __restrict__ gamma, const float* __restrict__ g_in,
+                                                                     float* __restrict__ g_out, long ldg, float* __restrict__ dgamma,
+                                                                     float* __restrict__ dbeta, int rows, int C, int keep) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t xb = (uint32_t)keep * 4, gb = g_in != nullptr ? (uint32_t)C * 4 : 0u, db = (uint32_t)keep * (uint32_t)sizeof(T);
+  const uint32_t slot = ((xb + gb + db) + 127u) & ~127u;
+  uint8_t* my = ln_smem + (size_t)warp * 2 * slot;
+  __shared__ __align__(8) unsigned long long bars[LN_WARPS][2];
+  const uint32_t bar0 = smem_u32(&bars[warp][0]), bar1 = smem_u32(&bars[warp][1]);
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar1, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  const long stride = (long)gridDim.x * LN_WARPS;
+  auto issue = [&](long r, int sl) {     // lane 0 only
+    const uint32_t dst = smem_u32(my + (size_t)sl * slot), bar = sl ? bar1 : bar0;
+    mbar_expect_tx(bar, xb + gb + db);
+    bulk_g2s(dst, x + r * ldx, xb, bar);
+    if (gb) bulk_g2s(dst + xb, g_in + r * ldg, gb, bar);
+    bulk_g2s(dst + xb + gb, dy + r * lddy, db, bar);
+  };
+  const float inv_keep = 1.0f / (float)keep;
+  float4 ag[NV], ab[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) ag[i] = make_float4(0.f, 0.f, 0.f, 0.f), ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  long r = (long)blockIdx.x * LN_WARPS + warp;
+  if (r < rows && lane == 0) issue(r, 0);
+  int it = 0;
+  for (; r < rows; r += stride, ++it) {
+    const int sl = it & 1;
+    if (r + stride < rows && lane == 0) issue(r + stride, sl ^ 1);      // the other slot was fully consumed one iteration ago
+    mbar_wait(sl ? bar1 : bar0, (uint32_t)(it >> 1) & 1u);
+    const float* xs = reinterpret_cast<const float*>(my + (size_t)sl * slot);
+    const float* gs = reinterpret_cast<const float*>(my + (size_t)sl * slot + xb);
+    const T* ds = reinterpret_cast<const T*>(my + (size_t)sl * slot + xb + gb);
+    const float mu = mean[r], rs = rstd[r];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < keep) {
+        float4 d = ld4(ds + c);
+        const float4 xv = ld4(xs + c), gm = ld4(gamma + c);
+        const float4 z = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        ag[i].x += d.x * z.x, ag[i].y += d.y * z.y, ag[i].z += d.z * z.z, ag[i].w += d.w * z.w;
+        ab[i].x += d.x, ab[i].y += d.y, ab[i].z += d.z, ab[i].w += d.w;
+        d.x *= gm.x, d.y *= gm.y, d.z *= gm.z, d.w *= gm.w;
+        s1 += (d.x + d.y) + (d.z + d.w);
+        s2 += (d.x * z.x + d.y * z.y) + (d.z * z.z + d.w * z.w);
+      }
+    }
+    s1 = warp_sum(s1) * inv_keep;
+    s2 = warp_sum(s2) * inv_keep;
+    float* go = g_out + r * ldg;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < C) {
+        float4 o = gb ? ld4(gs + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < keep) {
+          const float4 d0 = ld4(ds + c), xv = ld4(xs + c), gm = ld4(gamma + c);
+          o.x += (d0.x * gm.x - s1 - (xv.x - mu) * rs * s2) * rs;
+          o.y += (d0.y * gm.y - s1 - (xv.y - mu) * rs * s2) * rs;
+          o.z += (d0.z * gm.z - s1 - (xv.z - mu) * rs * s2) * rs;
+          o.w += (d0.w * gm.w - s1 - (xv.w - mu) * rs * s2) * rs;
+        }
+        st4(go + c, o);
+      }
+    }
+    __syncwarp();      // every lane is done with this slot before lane 0 re-arms it (two iterations from now it is the target again)
+  }
+  __shared__ float4 red[LN_WARPS][NV * 32];
+  for (int pass = 0; pass < 2; ++pass) {
+    float* dst = pass == 0 ? dgamma : dbeta;
+    if (pass == 1) __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) red[warp][i * 32 + lane] = pass == 0 ? ag[i] : ab[i];
+    __syncthreads();
+    for (int q = threadIdx.x; q < NV * 32; q += LN_WARPS * 32) {
+      float4 t = red[0][q];
+#pragma unroll
+      for (int w = 1; w < LN_WARPS; ++w) {
+        const float4 u = red[w][q];
+        t.x += u.x, t.y += u.y, t.z += u.z, t.w += u.w;
+      }
+      red_add4(dst + q * 4, t, q * 4, keep);
+    }
+  }
+}
+
 int ln_grid(int rows, int per_sm) {
   const int need = ceil_div(rows, LN_WARPS);
   const int cap = num_sms() * per_sm;
@@ -200,6 +310,32 @@ int ln_bwd_dispatch(const void* dy, const void* dy2, long lddy, const float* x, 
                     const float* gamma, const float* g_in, float* g_out, long ldg, float* dgamma, float* dbeta, int rows, int C,
                     int keep, int rps, int split, cudaStream_t st) {
   const int nv = ceil_div(C, 128);
+  // bulk-copy prefetch variant: whole kept prefix in 16-byte units, no final-norm row remap, 16-byte aligned rows
+  const size_t esz = sizeof(T);
+  const bool bulk = rps <= 0 && keep % 8 == 0 && C % 4 == 0 && lddy % 8 == 0 && ldx % 4 == 0 && ldg % 4 == 0 &&
+                    ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g_in)) & 15) == 0;
+  if (bulk && (((size_t)keep * 4 + (g_in != nullptr ? (size_t)C * 4 : 0) + (size_t)keep * esz + 127) & ~(size_t)127) * 2 * LN_WARPS + 4096 * (size_t)nv + 512 <= 227 * 1024) {
+    const size_t slot = (((size_t)keep * 4 + (g_in != nullptr ? (size_t)C * 4 : 0) + (size_t)keep * esz) + 127) & ~(size_t)127;
+    const size_t smem = slot * 2 * LN_WARPS, stat = 4096 * (size_t)nv + 512;     // dynamic row slots + the static reduction buffer
+    const int per_sm = (int)std::min<size_t>(4, (227 * 1024) / (smem + stat + 1024));
+    const int gridb = ln_grid(rows, per_sm < 1 ? 1 : per_sm);
+#define VSX_LN_BB(NV)                                                                                                               \
+  case NV: {                                                                                                                        \
+    static bool cfg = false;                                                                                                        \
+    if (!cfg) {                                                                                                                     \
+      cudaFuncSetAttribute(ln_bwd_bulk_kernel<NV, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096 * NV - 512);   \
+      cfg = true;                                                                                                                   \
+    }                                                                                                                               \
+    ln_bwd_bulk_kernel<NV, T><<<gridb, LN_WARPS * 32, smem, st>>>((const T*)dy, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg,   \
+                                                                   dgamma, dbeta, rows, C, keep);                                    \
+    return check_launch("vsx_masked_ln_bwd");                                                                                       \
+  }
+    switch (nv) {
+      VSX_LN_BB(1) VSX_LN_BB(2) VSX_LN_BB(3) VSX_LN_BB(4) VSX_LN_BB(5) VSX_LN_BB(6) VSX_LN_BB(7) VSX_LN_BB(8) VSX_LN_BB(9) VSX_LN_BB(10)
+      default: break;
+    }
+#undef VSX_LN_BB
+  }
   const int grid = ln_grid(rows, 4);
 #define VSX_LN_B(NV)                                                                                                      \
   case NV:                                                                                                                \
