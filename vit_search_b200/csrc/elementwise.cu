@@ -76,6 +76,74 @@ __global__ void __launch_bounds__(SMC_WARPS * 32) scale_mask_cast_kernel(const f
   }
 }
 
+
+// Same operation with bulk-copy row prefetch (see ln_bwd_bulk_kernel in norm.cu): g rows arrive in shared memory one iteration ahead.
+template <int NV, typename T>
+__global__ void __launch_bounds__(SMC_WARPS * 32) scale_mask_cast_bulk_kernel(const float* __restrict__ g, long ldg, const float* __restrict__ row_scale,
+                                                                             int rps, int n_keep, T* __restrict__ out, long ldo, int rows, int cols,
+                                                                             float* __restrict__ colsum) {
+  extern __shared__ __align__(128) uint8_t smc_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t gb = (uint32_t)n_keep * 4;
+  const uint32_t slot = (gb + 127u) & ~127u;
+  uint8_t* my = smc_smem + (size_t)warp * 2 * slot;
+  __shared__ __align__(8) unsigned long long bars[SMC_WARPS][2];
+  const uint32_t bar0 = smem_u32(&bars[warp][0]), bar1 = smem_u32(&bars[warp][1]);
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar1, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  const long stride = (long)gridDim.x * SMC_WARPS;
+  auto issue = [&](long r, int sl) {
+    const uint32_t bar = sl ? bar1 : bar0;
+    mbar_expect_tx(bar, gb);
+    bulk_g2s(smem_u32(my + (size_t)sl * slot), g + r * ldg, gb, bar);
+  };
+  float4 acc[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  long r = (long)blockIdx.x * SMC_WARPS + warp;
+  if (r < rows && lane == 0) issue(r, 0);
+  int it = 0;
+  for (; r < rows; r += stride, ++it) {
+    const int sl = it & 1;
+    if (r + stride < rows && lane == 0) issue(r + stride, sl ^ 1);
+    const float s = row_scale != nullptr ? __ldg(row_scale + r / rps) : 1.0f;
+    mbar_wait(sl ? bar1 : bar0, (uint32_t)(it >> 1) & 1u);
+    const float* gs = reinterpret_cast<const float*>(my + (size_t)sl * slot);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < cols) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < n_keep) {
+          v = ld4(gs + c);
+          v.x *= s, v.y *= s, v.z *= s, v.w *= s;
+        }
+        st4(out + r * ldo + c, v);
+        acc[i].x += v.x, acc[i].y += v.y, acc[i].z += v.z, acc[i].w += v.w;
+      }
+    }
+    __syncwarp();
+  }
+  if (colsum == nullptr) return;
+  __shared__ float4 red[SMC_WARPS][NV * 32];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) red[warp][i * 32 + lane] = acc[i];
+  __syncthreads();
+  for (int q = threadIdx.x; q < NV * 32; q += SMC_WARPS * 32) {
+    float4 t = red[0][q];
+#pragma unroll
+    for (int w = 1; w < SMC_WARPS; ++w) {
+      const float4 u = red[w][q];
+      t.x += u.x, t.y += u.y, t.z += u.z, t.w += u.w;
+    }
+    red_add4(colsum + q * 4, t, q * 4, n_keep);
+  }
+}
+
 // out[c] += sum_r x[r, c].  CTA = 256 threads = 32 column-quads x 8 row lanes, covers 128 columns x ROWS_PER_CTA rows.
 constexpr int CS_ROWS = 512;
 template <typename T>
@@ -132,6 +200,25 @@ static int smc_dispatch(const float* g, long ldg, const float* row_scale, int rp
   const int nv = ceil_div(cols, 128);
   const int need = ceil_div(rows, SMC_WARPS), cap = num_sms() * (colsum != nullptr ? 4 : 8);
   const int grid = need < cap ? need : cap;
+  if (n_keep > 0 && n_keep % 4 == 0 && ldg % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 && nv <= 10) {
+    const size_t smem = (((size_t)n_keep * 4 + 127) & ~(size_t)127) * 2 * SMC_WARPS;
+    const int cap4 = num_sms() * 4, gridb = need < cap4 ? need : cap4;
+#define VSX_SMCB(NV)                                                                                                                       \
+  case NV: {                                                                                                                               \
+    static bool cfg = false;                                                                                                               \
+    if (!cfg) {                                                                                                                            \
+      cudaFuncSetAttribute(scale_mask_cast_bulk_kernel<NV, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                    \
+      cfg = true;                                                                                                                          \
+    }                                                                                                                                      \
+    scale_mask_cast_bulk_kernel<NV, T><<<gridb, SMC_WARPS * 32, smem, st>>>(g, ldg, row_scale, rps, n_keep, (T*)out, ldo, rows, cols, colsum); \
+    return check_launch("vsx_scale_mask_cast");                                                                                            \
+  }
+    switch (nv) {
+      VSX_SMCB(1) VSX_SMCB(2) VSX_SMCB(3) VSX_SMCB(4) VSX_SMCB(5) VSX_SMCB(6) VSX_SMCB(7) VSX_SMCB(8) VSX_SMCB(9) VSX_SMCB(10)
+      default: break;
+    }
+#undef VSX_SMCB
+  }
 #define VSX_SMC(NV)                                                                                                                 \
   case NV:                                                                                                                          \
     scale_mask_cast_kernel<NV, T><<<grid, SMC_WARPS * 32, 0, st>>>(g, ldg, row_scale, rps, n_keep, (T*)out, ldo, rows, cols, colsum); \

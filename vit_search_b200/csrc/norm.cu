@@ -177,12 +177,6 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T* __restri
 // cp.async.bulk copies of the NEXT row (dy, x, g_in: up to 10 B/channel) into one slot while the warp works on the other, completion
 // on one mbarrier per slot.  The per-warp register tile (d, z, g_in) of the plain kernel disappears -- rows are re-read from shared
 // memory -- so occupancy is no longer register-bound at C = 512 / 1024, and ~100 KB of loads are in flight per SM.
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
-               "r"(bar)
-               : "memory");
-}
-
 template <int NV, typename T>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_bulk_kernel(const T* __restrict__ dy, long lddy, const float* __restrict__ x, long ldx,
                                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
@@ -279,6 +273,79 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_bulk_kernel(const T* __r
   }
 }
 
+
+// Forward with the same bulk-copy row prefetch (see ln_bwd_bulk_kernel): x rows arrive in shared memory one iteration ahead.
+template <int NV, typename T>
+__global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_bulk_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ gamma,
+                                                                     const float* __restrict__ beta, T* __restrict__ y, long ldy,
+                                                                     float* __restrict__ mean, float* __restrict__ rstd, int rows, int C,
+                                                                     int keep, float eps) {
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t xb = (uint32_t)keep * 4;
+  const uint32_t slot = (xb + 127u) & ~127u;
+  uint8_t* my = ln_smem + (size_t)warp * 2 * slot;
+  __shared__ __align__(8) unsigned long long bars[LN_WARPS][2];
+  const uint32_t bar0 = smem_u32(&bars[warp][0]), bar1 = smem_u32(&bars[warp][1]);
+  if (lane == 0) {
+    mbar_init(bar0, 1);
+    mbar_init(bar1, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  const long stride = (long)gridDim.x * LN_WARPS;
+  auto issue = [&](long r, int sl) {
+    const uint32_t bar = sl ? bar1 : bar0;
+    mbar_expect_tx(bar, xb);
+    bulk_g2s(smem_u32(my + (size_t)sl * slot), x + r * ldx, xb, bar);
+  };
+  const float inv_keep = 1.0f / (float)keep;
+  long r = (long)blockIdx.x * LN_WARPS + warp;
+  if (r < rows && lane == 0) issue(r, 0);
+  int it = 0;
+  for (; r < rows; r += stride, ++it) {
+    const int sl = it & 1;
+    if (r + stride < rows && lane == 0) issue(r + stride, sl ^ 1);
+    mbar_wait(sl ? bar1 : bar0, (uint32_t)(it >> 1) & 1u);
+    const float* xs = reinterpret_cast<const float*>(my + (size_t)sl * slot);
+    float4 v[NV];
+    float s = 0.f, ss = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      v[i] = c < keep ? ld4(xs + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      ss += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    s = warp_sum(s);
+    ss = warp_sum(ss);
+    const float mu = s * inv_keep;
+    const float var = ss * inv_keep - mu * mu;
+    const float rs = 1.0f / sqrtf(var + eps);
+    if (lane == 0) {
+      mean[r] = mu;
+      rstd[r] = rs;
+    }
+    T* yr = y + r * ldy;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = (i * 32 + lane) * 4;
+      if (c < C) {
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < keep) {
+          const float4 gm = ld4(gamma + c), bt = ld4(beta + c);
+          o.x = gm.x * ((v[i].x - mu) * rs) + bt.x;
+          o.y = gm.y * ((v[i].y - mu) * rs) + bt.y;
+          o.z = gm.z * ((v[i].z - mu) * rs) + bt.z;
+          o.w = gm.w * ((v[i].w - mu) * rs) + bt.w;
+        }
+        st4(yr + c, o);
+      }
+    }
+    __syncwarp();
+  }
+}
+
 int ln_grid(int rows, int per_sm) {
   const int need = ceil_div(rows, LN_WARPS);
   const int cap = num_sms() * per_sm;
@@ -289,6 +356,27 @@ template <typename T>
 int ln_fwd_dispatch(const float* x, long ldx, const float* gamma, const float* beta, void* y, void* y2, long ldy, float* mean,
                     float* rstd, int rows, int C, int keep, float eps, int rps, int split, cudaStream_t st) {
   const int nv = ceil_div(C, 128);
+  // bulk-copy prefetch variant: kept prefix in whole float4s (the masked tail of a row is then exactly c >= keep), no row remap
+  if (rps <= 0 && keep % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const size_t slot = ((size_t)keep * 4 + 127) & ~(size_t)127;
+    const size_t smem = slot * 2 * LN_WARPS;
+    const int gridb = ln_grid(rows, 4);
+#define VSX_LN_FB(NV)                                                                                                            \
+  case NV: {                                                                                                                     \
+    static bool cfg = false;                                                                                                     \
+    if (!cfg) {                                                                                                                  \
+      cudaFuncSetAttribute(ln_fwd_bulk_kernel<NV, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                   \
+      cfg = true;                                                                                                                \
+    }                                                                                                                            \
+    ln_fwd_bulk_kernel<NV, T><<<gridb, LN_WARPS * 32, smem, st>>>(x, ldx, gamma, beta, (T*)y, ldy, mean, rstd, rows, C, keep, eps); \
+    return check_launch("vsx_masked_ln_fwd");                                                                                    \
+  }
+    switch (nv) {
+      VSX_LN_FB(1) VSX_LN_FB(2) VSX_LN_FB(3) VSX_LN_FB(4) VSX_LN_FB(5) VSX_LN_FB(6) VSX_LN_FB(7) VSX_LN_FB(8) VSX_LN_FB(9) VSX_LN_FB(10)
+      default: break;
+    }
+#undef VSX_LN_FB
+  }
   const int grid = ln_grid(rows, 8);
 #define VSX_LN_F(NV)                                                                                                        \
   case NV:                                                                                                                  \
