@@ -243,13 +243,22 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restric
                                     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const double* __restrict__ sums, T* __restrict__ dy, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta) {
+  // per-channel constants once per CTA: zhat = y*a + b, pre-activation = gamma*zhat + beta, dy = s*(dz - m1 - zhat*m2)
+  __shared__ float ca[BN_MAXC], cb[BN_MAXC], cg[BN_MAXC], cbeta[BN_MAXC], cs[BN_MAXC], cm1[BN_MAXC], cm2[BN_MAXC];
   const int c4n = C / 4;
   const long total = P * c4n;
-  const double invP = 1.0 / (double)P;
-  if (blockIdx.x == 0 && threadIdx.x < C) {
-    dbeta[threadIdx.x] += (float)sums[threadIdx.x];
-    dgamma[threadIdx.x] += (float)sums[C + threadIdx.x];
+  if (threadIdx.x < C) {
+    const int c = threadIdx.x;
+    const double invP = 1.0 / (double)P;
+    ca[c] = rstd[c], cb[c] = -mean[c] * rstd[c];
+    cg[c] = gamma[c], cbeta[c] = beta[c], cs[c] = gamma[c] * rstd[c];
+    cm1[c] = (float)(sums[c] * invP), cm2[c] = (float)(sums[C + c] * invP);
+    if (blockIdx.x == 0) {
+      dbeta[c] += (float)sums[c];
+      dgamma[c] += (float)sums[C + c];
+    }
   }
+  __syncthreads();
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int c = (int)(i % c4n) * 4;
     const long pidx = i / c4n;
@@ -258,10 +267,9 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restric
     float o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float zh = (yy[j] - mean[c + j]) * rstd[c + j];
-      const float dz = (gamma[c + j] * zh + beta[c + j] > 0.f) ? dd[j] : 0.f;
-      const float m1 = (float)(sums[c + j] * invP), m2 = (float)(sums[C + c + j] * invP);
-      o[j] = gamma[c + j] * rstd[c + j] * (dz - m1 - zh * m2);
+      const float zh = fmaf(yy[j], ca[c + j], cb[c + j]);
+      const float dz = fmaf(cg[c + j], zh, cbeta[c + j]) > 0.f ? dd[j] : 0.f;
+      o[j] = cs[c + j] * (dz - cm1[c + j] - zh * cm2[c + j]);
     }
     st4(dy + pidx * C + c, make_float4(o[0], o[1], o[2], o[3]));
   }
@@ -302,7 +310,10 @@ __global__ void embed_assemble_bwd_kernel(const float* __restrict__ g, T* __rest
     const int c = (int)(i % c4n) * 4;
     const int t = (int)(i / c4n);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int b = 0; b < nb; ++b) {
+    const int bper = (nb + gridDim.y - 1) / gridDim.y;       // blockIdx.y splits the batch; one atomic per chunk for dpos / dtokens
+    const int b_lo = blockIdx.y * bper, b_hi = min(nb, b_lo + bper);
+    if (b_lo >= b_hi) continue;
+    for (int b = b_lo; b < b_hi; ++b) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (c < keep) {
         v = ld4(g + ((long)b * N + t) * C + c);
@@ -527,7 +538,10 @@ extern "C" int vsx_embed_assemble_bwd(const float* g, void* dpatches, int dtype,
                                       int tokens_per_sample, int C, int keep, void* stream) {
   VSX_REQUIRE(C % 4 == 0 && keep >= 0 && keep <= C, "vsx_embed_assemble_bwd: bad C/keep");
   if (batch == 0) return VSX_OK;
-  const int grid = grid_for((long)tokens_per_sample * C / 4);
+  const int gx = grid_for((long)tokens_per_sample * C / 4);
+  int gyy = (4 * num_sms() + gx - 1) / gx;
+  gyy = gyy > batch ? batch : (gyy < 1 ? 1 : gyy);
+  const dim3 grid(gx, gyy);
   if (dtype == VSX_BF16) embed_assemble_bwd_kernel<bf16><<<grid, 256, 0, ST>>>(g, (bf16*)dpatches, dpos, dtokens, batch, tokens_per_sample, C, keep);
   else embed_assemble_bwd_kernel<float><<<grid, 256, 0, ST>>>(g, (float*)dpatches, dpos, dtokens, batch, tokens_per_sample, C, keep);
   return check_launch("vsx_embed_assemble_bwd");
