@@ -17,6 +17,8 @@
 //
 // Replaces: nn.Linear forward/backward at nets/supernet_blocks.py:38,50,102,118 and the elementwise tails at
 // :39 (GELU), :238-253 (mask, residual), nets/drop.py:11-26 (drop-path scale); see include/vsx.h.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vsx {
@@ -30,6 +32,7 @@ constexpr int STAGE_B = BN * BK * 2;
 // MT = 128-row sub-tiles per CTA tile.  MT = 2 computes a 256 x 128 tile from ONE B box per k block (two accumulators share it):
 // 3/4 of the L2 -> shared-memory bytes per flop of two independent 128 x 128 tiles.  These GEMMs have K <= 1536 and run at the
 // L2 -> SM fabric limit (~45 B/clk/SM) long before the tensor pipe saturates, so bytes per flop is what sets their speed.
+constexpr bool RESID_NBUF2 = false;   // measured: helps K <= 384 (48 -> 37 us), hurts K >= 768 (61 -> 68 us): the ring then is too shallow
 template <int MT> struct Shape {
   static constexpr int STAGE_A = MT * SUB_A;
   static constexpr int STAGE_BYTES = STAGE_A + STAGE_B;
@@ -160,7 +163,10 @@ template <int EPI, typename OutT, int MT> struct Plan {
   // per-tile global atomics on a few hundred addresses serialise in L2 and used to dominate the GELU' dgrad GEMMs)
   static constexpr int COLACC = (EPI == VSX_EPI_GELUGRAD || EPI == VSX_EPI_STORE) ? COLACC_MAX * 4 : 0;
   // two staging tiles when at least three operand stages still fit (the ring has to cover the L2 latency: ~100 KB in flight)
-  static constexpr int NBUF = (2 * TILE_BYTES + 3 * STAGE_BYTES + SMEM_MISC + COLACC <= SMEM_LIMIT) ? 2 : 1;
+  // GELU (two output tiles per unit) and RESIDUAL (fp32 tile in, fp32 tile out): double buffering the 64 KB staging tile matters
+  // more than ring depth (measured: GELU 88 -> 76 us at 65792 x 768 x 224 with two stages + two staging tiles)
+  static constexpr int MIN_STAGES2 = (EPI == VSX_EPI_GELU || (EPI == VSX_EPI_RESIDUAL && RESID_NBUF2)) ? 2 : 3;
+  static constexpr int NBUF = (2 * TILE_BYTES + MIN_STAGES2 * STAGE_BYTES + SMEM_MISC + COLACC <= SMEM_LIMIT) ? 2 : 1;
   static constexpr int ROOM = (SMEM_LIMIT - SMEM_MISC - COLACC - NBUF * TILE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = ROOM > MAX_STAGES ? MAX_STAGES : ROOM;
   static constexpr int SMEM = STAGES * STAGE_BYTES + NBUF * TILE_BYTES + SMEM_MISC + COLACC;
@@ -547,7 +553,8 @@ int launch(const TmapPack& maps, const GemmArgs& g, int tiles128, cudaStream_t s
     if (mt2) {
       GemmArgs g2 = g;
       if (g.split_k > 1) {
-        const int want = (2 * num_sms()) / (t256 * tiles_n);
+        static const int per_sm = getenv("VSX_WGRAD_ITEMS_PER_SM") ? atoi(getenv("VSX_WGRAD_ITEMS_PER_SM")) : 2;
+        const int want = (per_sm * num_sms()) / (t256 * tiles_n);
         g2.split_k = want < 1 ? 1 : (want > g.num_kb ? g.num_kb : want);
       }
       return launch_mt<EPI, OutT, 2>(maps, g2, t256 * tiles_n * g2.split_k, st);
@@ -555,9 +562,7 @@ int launch(const TmapPack& maps, const GemmArgs& g, int tiles128, cudaStream_t s
     return launch_mt<EPI, OutT, 1>(maps, g, tiles128, st);
   }
   const int tiles256 = t256 * tiles_n;
-  // GELU writes two output tiles per unit: two staging buffers + three operand stages only fit with 128-row tiles, and its
-  // epilogue (not operand traffic) bounds it
-  if (g_force_mt != 1 && (g_force_mt == 2 || (tiles256 >= num_sms() && EPI != VSX_EPI_GELU))) return launch_mt<EPI, OutT, 2>(maps, g, tiles256, st);
+  if (g_force_mt != 1 && (g_force_mt == 2 || tiles256 >= num_sms())) return launch_mt<EPI, OutT, 2>(maps, g, tiles256, st);
   return launch_mt<EPI, OutT, 1>(maps, g, tiles128, st);
 }
 
