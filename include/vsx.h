@@ -111,6 +111,9 @@ typedef struct vsx_gemm_desc {
 } vsx_gemm_desc;
 
 int vsx_gemm(const vsx_gemm_desc* d, void* stream);
+/* Up to 4 independent problems with the same epilogue and output dtype in ONE launch (the q / k / v row blocks of a head-masked
+ * qkv projection; all weight gradients of a half block): their tiles form one work list for the persistent CTAs. */
+int vsx_gemm_grouped(const vsx_gemm_desc* descs, int count, void* stream);
 /* CTA tile rows: 0 = heuristic (256-row tiles sharing one B box per k block when they fill the machine), 128 / 256 = forced (tests). */
 int vsx_gemm_force_tile_rows(int rows);
 /* Development aid: device buffer of 64 x 8 int64 clock stamps written by CTA 0 of the next GEMM launches (NULL = off). */

@@ -211,6 +211,36 @@ def test_gemm_epilogues(ops, tile_rows):
     assert rel(out, ref) < 1e-5
 
 
+def test_gemm_grouped(ops, tile_rows):
+    """vsx_gemm_grouped: several problems of different shapes in ONE launch -- the q/k/v row blocks of a head-masked qkv projection
+    (shared A, three weight / output / bias windows) and a set of split-K weight gradients -- against per-problem fp64 references."""
+    g = torch.Generator().manual_seed(5)
+    M, C, H, D, hk = 700, 160, 4, 64, 3
+    HD = H * D
+    x = torch.randn(M, C, generator=g).to(torch.bfloat16)
+    w = (torch.randn(3 * HD, C, generator=g) * 0.1).to(torch.bfloat16)
+    b = torch.randn(3 * HD, generator=g)
+    qkv = torch.full((M, 3 * HD), float('nan'), device='cuda', dtype=torch.bfloat16)
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    ops.gemm_grouped([((xd, wd, C, C, M, hk * D, 144, ops.EPI_STORE, qkv, 3 * HD),
+                       dict(b_off=j * HD * C, out_off=j * HD, bias=bd, bias_off=j * HD)) for j in range(3)])
+    ref = x[:, :144].double() @ w[:, :144].double().t() + b.double()
+    got = qkv.view(M, 3, H, D)[:, :, :hk].double().cpu()
+    assert rel(got, ref.view(M, 3, H, D)[:, :, :hk]) < 6e-3
+    assert torch.isnan(qkv.view(M, 3, H, D)[:, :, hk:].float()).all()          # masked heads are not touched
+    # weight gradients of different shapes: dW_i[n_i, k_i] += dy_i^T a_i, reductions over R rows split across CTAs
+    R = 3000
+    shapes = [(192, 160), (64, 96), (320, 40), (24, 200)]
+    dys = [torch.randn(R, n, generator=g).to(torch.bfloat16) for n, _ in shapes]
+    acs = [torch.randn(R, k, generator=g).to(torch.bfloat16) for _, k in shapes]
+    dws = [torch.zeros(n, (k + 3) // 4 * 4, device='cuda') for n, k in shapes]
+    dyd, acd = [t.cuda() for t in dys], [t.cuda() for t in acs]
+    ops.gemm_grouped([((dyd[i], acd[i], n, k, n, k, R, ops.EPI_ATOMIC, dws[i], dws[i].shape[1]),
+                       dict(a_layout=ops.MNMAJOR, b_layout=ops.MNMAJOR, split_k=7)) for i, (n, k) in enumerate(shapes)])
+    for i, (n, k) in enumerate(shapes):
+        assert rel(dws[i][:, :k], dys[i].double().t() @ acs[i].double()) < 1e-5, shapes[i]
+
+
 # ---------------------------------------------------------------------------------------------- attention core
 @pytest.mark.parametrize('N,H,D,Hk', [(257, 3, 64, 3), (257, 6, 32, 5), (65, 4, 48, 2), (17, 4, 64, 3), (50, 2, 32, 2), (197, 2, 64, 1)])
 @pytest.mark.parametrize('mode', ['bf16_auto', 'bf16_mma', 'bf16_fp32math', 'fp32'])

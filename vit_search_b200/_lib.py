@@ -36,6 +36,7 @@ SIGNATURES = {
     'vsx_attn_bwd': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p],
     'vsx_attn_debug_buffer': [_p],
     'vsx_gemm_force_tile_rows': [_i],
+    'vsx_gemm_grouped': [_p, _i, _p],
     'vsx_gemm_debug_buffer': [_p],
     'vsx_split_bf16': [_p, _l, _p, _p, _p, _l, _i, _i, _p],
     'vsx_scale_mask_cast': [_p, _l, _p, _i, _i, _p, _i, _l, _i, _i, _p, _p],

@@ -296,9 +296,9 @@ def attn_half_forward(meta, x, ln_w, ln_b, qkv_w, qkv_b, proj_w, proj_b):
         if hk == H:
             ops.gemm(a, wq, C, C, rows, 3 * HD, s.ek, ops.EPI_STORE, qkv, 3 * HD, a_off=r0 * C, out_off=r0 * 3 * HD, bias=qkv_b)
         else:
-            for j in range(3):   # q / k / v row blocks of the kept heads only  (features ordered (3,H,D))
-                ops.gemm(a, wq, C, C, rows, hk * D, s.ek, ops.EPI_STORE, qkv, 3 * HD, a_off=r0 * C, b_off=j * HD * C,
-                         out_off=r0 * 3 * HD + j * HD, bias=qkv_b, bias_off=j * HD)
+            # q / k / v row blocks of the kept heads only (features ordered (3,H,D)): three problems, one launch
+            ops.gemm_grouped([((a, wq, C, C, rows, hk * D, s.ek, ops.EPI_STORE, qkv, 3 * HD),
+                               dict(a_off=r0 * C, b_off=j * HD * C, out_off=r0 * 3 * HD + j * HD, bias=qkv_b, bias_off=j * HD)) for j in range(3)])
         ops.attn_fwd(qkv, o, lse, nb, N, H, D, hk, scale, qkv_off=r0 * 3 * HD, o_off=r0 * HD, lse_off=s.b0 * H * N)
         ao = acts.get(o, HD, r0, rows, hk * D)
         if meta.residual:
@@ -343,9 +343,9 @@ def attn_half_backward(meta, g_out, saved, x, ln_w, ln_b, qkv_w, qkv_b, proj_w, 
                             scale_off=meta.scale_off + s.b0, colsum=d_pb)
         a_df = acts.get(df, C, r0, rows, ck)
         a_o = acts.get(o, HD, r0, rows, hkd)
-        # dWproj[ck, hkd] += df^T o
-        ops.gemm(a_df, a_o, C, HD, ck, hkd, rows, ops.EPI_ATOMIC, d_pw, HD, a_off=r0 * C, b_off=r0 * HD, a_layout=ops.MNMAJOR,
-                 b_layout=ops.MNMAJOR, split_k=split_k_for(ck, hkd, rows))
+        # dWproj[ck, hkd] += df^T o : launched together with the qkv weight gradients below (one grouped launch per half block)
+        wgrads = [((a_df, a_o, C, HD, ck, hkd, rows, ops.EPI_ATOMIC, d_pw, HD),
+                   dict(a_off=r0 * C, b_off=r0 * HD, a_layout=ops.MNMAJOR, b_layout=ops.MNMAJOR, split_k=split_k_for(ck, hkd, rows)))]
         # d_o[rows, hkd] = df[rows, ck] Wproj[ck, hkd]
         ops.gemm(a_df, wp, C, HD, rows, hkd, ck, ops.EPI_STORE, d_o, HD, a_off=r0 * C, out_off=r0 * HD, b_layout=ops.MNMAJOR)
         ops.attn_bwd(qkv, o, d_o, lse, dqkv, nb, N, H, D, hk, scale, qkv_off=r0 * 3 * HD, o_off=r0 * HD, lse_off=s.b0 * H * N, dbias=d_qb)
@@ -353,8 +353,10 @@ def attn_half_backward(meta, g_out, saved, x, ln_w, ln_b, qkv_w, qkv_b, proj_w, 
         a_xn = acts.get(xn, C, r0, rows, s.ek)
         for j in (range(3) if hk < H else range(1)):
             nrow = hkd if hk < H else 3 * HD
-            ops.gemm(a_dq, a_xn, 3 * HD, C, nrow, s.ek, rows, ops.EPI_ATOMIC, d_qw, C, a_off=r0 * 3 * HD + j * HD, b_off=r0 * C,
-                     out_off=j * HD * C, a_layout=ops.MNMAJOR, b_layout=ops.MNMAJOR, split_k=split_k_for(nrow, s.ek, rows))
+            wgrads.append(((a_dq, a_xn, 3 * HD, C, nrow, s.ek, rows, ops.EPI_ATOMIC, d_qw, C),
+                           dict(a_off=r0 * 3 * HD + j * HD, b_off=r0 * C, out_off=j * HD * C, a_layout=ops.MNMAJOR, b_layout=ops.MNMAJOR,
+                                split_k=split_k_for(nrow, s.ek, rows))))
+        ops.gemm_grouped(wgrads)
         # dxn[rows, ek] = dqkv[rows, 3HD] Wqkv[3HD, ek]   (masked heads are zero columns of dqkv)
         if meta.pre_norm:
             ops.gemm(a_dq, wq, 3 * HD, C, rows, s.ek, 3 * HD, ops.EPI_STORE, dxn, C, a_off=r0 * 3 * HD, out_off=r0 * C,
@@ -433,17 +435,18 @@ def mlp_half_backward(meta, g_out, saved, x, ln_w, ln_b, fc1_w, fc1_b, fc2_w, fc
                             scale_off=meta.scale_off + s.b0, colsum=d_b2)
         a_df = acts.get(df, C, r0, rows, ck)
         a_h = acts.get(h, F, r0, rows, s.ik)
-        # dW2[ck, ik] += df^T h
-        ops.gemm(a_df, a_h, C, F, ck, s.ik, rows, ops.EPI_ATOMIC, d_w2, F, a_off=r0 * C, b_off=r0 * F, a_layout=ops.MNMAJOR,
-                 b_layout=ops.MNMAJOR, split_k=split_k_for(ck, s.ik, rows))
+        # dW2[ck, ik] += df^T h : launched together with dW1 below
+        wgrads = [((a_df, a_h, C, F, ck, s.ik, rows, ops.EPI_ATOMIC, d_w2, F),
+                   dict(a_off=r0 * C, b_off=r0 * F, a_layout=ops.MNMAJOR, b_layout=ops.MNMAJOR, split_k=split_k_for(ck, s.ik, rows)))]
         # du[rows, ik] = (df[rows, ck] W2[ck, ik]) * gelu'(u)
         ops.gemm(a_df, w2, C, F, rows, s.ik, ck, ops.EPI_GELUGRAD, du, F, a_off=r0 * C, out_off=r0 * F, n_out=up8(s.ik), aux=u,
                  ld_aux=F, aux_off=r0 * F, b_layout=ops.MNMAJOR, colsum=d_b1)
         a_du = acts.get(du, F, r0, rows, s.ik)
         a_xn = acts.get(xn, C, r0, rows, s.ek)
         # dW1[ik, ek] += du^T xn
-        ops.gemm(a_du, a_xn, F, C, s.ik, s.ek, rows, ops.EPI_ATOMIC, d_w1, C, a_off=r0 * F, b_off=r0 * C, a_layout=ops.MNMAJOR,
-                 b_layout=ops.MNMAJOR, split_k=split_k_for(s.ik, s.ek, rows))
+        wgrads.append(((a_du, a_xn, F, C, s.ik, s.ek, rows, ops.EPI_ATOMIC, d_w1, C),
+                       dict(a_off=r0 * F, b_off=r0 * C, a_layout=ops.MNMAJOR, b_layout=ops.MNMAJOR, split_k=split_k_for(s.ik, s.ek, rows))))
+        ops.gemm_grouped(wgrads)
         # dxn[rows, ek] = du[rows, ik] W1[ik, ek]
         if meta.pre_norm:
             ops.gemm(a_du, w1, F, C, rows, s.ek, s.ik, ops.EPI_STORE, dxn, C, a_off=r0 * F, out_off=r0 * C, n_out=up8(s.ek),

@@ -65,6 +65,16 @@ struct GemmArgs {
   long long* dbg;
 };
 
+// A launch computes up to G independent problems that share epilogue, output type and tile shape (same kernel instantiation):
+// the q / k / v row blocks of a head-masked qkv projection, or all weight gradients of a half block.  Tiles of all problems form
+// one list that the persistent CTAs walk, so small problems fill the machine together instead of paying one launch each.
+template <int G> struct Group {
+  TmapPack maps[G];
+  GemmArgs args[G];
+  int tile_end[G];     // exclusive prefix sums of the problems' tile counts
+  int count, total;
+};
+
 // Shared-memory matrix descriptor (tcgen05), 128B swizzle.  K-major: rows of 128 B, 8-row groups 1024 B apart (SBO).
 // MN-major: 64-element (128 B) MN atoms, k-rows 128 B apart, 8-row groups SBO = 1024 B, MN atoms LBO = BK*128 B apart.
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, bool mn_major) {
@@ -181,8 +191,8 @@ template <int EPI, typename OutT, int MT> struct Plan {
 //                       later TMA-stores / reduce-adds the staged result; staging is double buffered
 //   warps 3+ epilogue : TMEM -> registers -> fused math -> swizzled staging tile
 // so the loads of tile i+1, the MMAs of tile i+1 and the stores of tile i-1 overlap the epilogue of tile i.
-template <int EPI, typename OutT, int MT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ TmapPack maps, const GemmArgs g) {
+template <int EPI, typename OutT, int MT, int G>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ Group<G> grp) {
   using P = Plan<EPI, OutT, MT>;
   constexpr int STAGES = P::STAGES, NBUF = P::NBUF;
   constexpr int STAGE_BYTES = P::STAGE_BYTES, STAGE_A = Shape<MT>::STAGE_A, TMEM_COLS = Shape<MT>::TMEM_COLS;
@@ -207,17 +217,27 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (2 * MAX_STAGES + 8));
   float* bias_s = reinterpret_cast<float*>(misc + 256);   // [2][BN]
   float* colacc = reinterpret_cast<float*>(misc + SMEM_MISC - 1024);   // [COLACC_MAX] when P::COLACC != 0 (after the 1 KB alignment slack)
-  const bool use_colacc = P::COLACC != 0 && g.colsum != nullptr && g.n_out <= COLACC_MAX;
+  const bool use_colacc = G == 1 && P::COLACC != 0 && grp.args[0].colsum != nullptr && grp.args[0].n_out <= COLACC_MAX;
+  long long* const dbg = grp.args[0].dbg;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (g.M + BM * MT - 1) / (BM * MT), tiles_n = (g.n_out + BN - 1) / BN;
-  const int splits = (EPI == VSX_EPI_ATOMIC) ? g.split_k : 1;
-  const int total = tiles_m * tiles_n * splits;
-  const int kb_per = (g.num_kb + splits - 1) / splits;
+  const int total = grp.total;
 
-  // tile t -> (m0, n0, k-block range); identical arithmetic in every role
-  auto tile_info = [&](int t, int& m0, int& n0, int& kb0, int& nkb) {
-    const int ni = t % tiles_n, mi = (t / tiles_n) % tiles_m, z = t / (tiles_n * tiles_m);
+  // tile t -> (problem, m0, n0, k-block range); identical arithmetic in every role
+  auto tile_info = [&](int t, int& pi, int& m0, int& n0, int& kb0, int& nkb) {
+    pi = 0;
+    int t0 = 0;
+    if (G > 1) {
+#pragma unroll
+      for (int q = 0; q < G - 1; ++q)
+        if (q < grp.count - 1 && t >= grp.tile_end[q]) pi = q + 1, t0 = grp.tile_end[q];
+    }
+    const GemmArgs& g = grp.args[pi];
+    const int tl = t - t0;
+    const int tiles_m = (g.M + BM * MT - 1) / (BM * MT), tiles_n = (g.n_out + BN - 1) / BN;
+    const int splits = (EPI == VSX_EPI_ATOMIC) ? g.split_k : 1;
+    const int kb_per = (g.num_kb + splits - 1) / splits;
+    const int ni = tl % tiles_n, mi = (tl / tiles_n) % tiles_m, z = tl / (tiles_n * tiles_m);
     m0 = mi * BM * MT, n0 = ni * BN;
     kb0 = z * kb_per;
     const int kb1 = min(g.num_kb, kb0 + kb_per);
@@ -225,11 +245,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   };
 
   if (warp == 0 && lane == 0) {
-    for (int t = 0; t < g.terms; ++t) {
-      tma_prefetch_desc(&maps.a[t]);
-      tma_prefetch_desc(&maps.b[t]);
+    for (int q = 0; q < grp.count; ++q) {
+      for (int t = 0; t < grp.args[q].terms; ++t) {
+        tma_prefetch_desc(&grp.maps[q].a[t]);
+        tma_prefetch_desc(&grp.maps[q].b[t]);
+      }
+      tma_prefetch_desc(&grp.maps[q].out);
     }
-    tma_prefetch_desc(&maps.out);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -258,8 +280,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       // ---------------- TMA producer ----------------
       int it = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x) {
-        int m0, n0, kb0, nkb;
-        tile_info(t, m0, n0, kb0, nkb);
+        int pi, m0, n0, kb0, nkb;
+        tile_info(t, pi, m0, n0, kb0, nkb);
+        const GemmArgs& g = grp.args[pi];
+        const TmapPack& maps = grp.maps[pi];
         for (int i = 0; i < nkb * g.terms; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -290,14 +314,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   } else if (warp == 1) {
     if (lane == 0) {
       // ---------------- MMA issuer ----------------
-      const uint32_t idesc = make_idesc(g.a_mn != 0, g.b_mn != 0);
-      const uint32_t a_step = g.a_mn ? (UMMA_K * 128) : (UMMA_K * 2);   // bytes per 16-wide k step
-      const uint32_t b_step = g.b_mn ? (UMMA_K * 128) : (UMMA_K * 2);
       int it = 0, uses[2] = {0, 0}, j = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
-        int m0, n0, kb0, nkb;
-        tile_info(t, m0, n0, kb0, nkb);
+        int pi, m0, n0, kb0, nkb;
+        tile_info(t, pi, m0, n0, kb0, nkb);
         if (nkb == 0) continue;                       // epilogue-only tile: the accumulator is not involved
+        const GemmArgs& g = grp.args[pi];
+        const uint32_t idesc = make_idesc(g.a_mn != 0, g.b_mn != 0);
+        const uint32_t a_step = g.a_mn ? (UMMA_K * 128) : (UMMA_K * 2);   // bytes per 16-wide k step
+        const uint32_t b_step = g.b_mn ? (UMMA_K * 128) : (UMMA_K * 2);
         const int ab = j & 1;
         mbar_wait(acc_empty(ab), ((uint32_t)uses[ab] & 1u) ^ 1u);   // epilogue has drained this accumulator
         ++uses[ab];
@@ -319,7 +344,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           umma_commit(empty_bar(s));   // slot reusable once these MMAs have read it
         }
         umma_commit(acc_full(ab));     // accumulator complete
-        if (g.dbg != nullptr && blockIdx.x == 0 && j * MT < 64) g.dbg[j * MT * 8 + 7] = clock64();
+        if (dbg != nullptr && blockIdx.x == 0 && j * MT < 64) dbg[j * MT * 8 + 7] = clock64();
       }
     }
   } else if (warp == 2) {
@@ -329,8 +354,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       // (completing `ready`), or just arrive on `ready` when the epilogue needs no aux tile.
       // A CTA tile is MT units of 128 rows; units are staged / stored one at a time through the NBUF staging buffers.
       auto announce = [&](int t, int sub, int sb) {
-        int m0, n0, kb0, nkb;
-        tile_info(t, m0, n0, kb0, nkb);
+        int pi, m0, n0, kb0, nkb;
+        tile_info(t, pi, m0, n0, kb0, nkb);
+        const GemmArgs& g = grp.args[pi];
+        const TmapPack& maps = grp.maps[pi];
         const int ncols = min(BN, g.n_out - n0);
         const int nbox = (ncols + BOXC - 1) / BOXC;
         if (AUX) {
@@ -351,12 +378,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // store of unit un-1 (same buffer as un+1) has been read
           announce(tn, subn, (un + 1) % NBUF);
         }
-        int m0, n0, kb0, nkb;
-        tile_info(t, m0, n0, kb0, nkb);
+        int pi, m0, n0, kb0, nkb;
+        tile_info(t, pi, m0, n0, kb0, nkb);
+        const GemmArgs& g = grp.args[pi];
+        const TmapPack& maps = grp.maps[pi];
         const int ms = m0 + sub * BM;
         const int ncols = min(BN, g.n_out - n0);
         const int nbox = (ncols + BOXC - 1) / BOXC;
-        if (g.dbg != nullptr && blockIdx.x == 0 && un < 64) g.dbg[un * 8 + 5] = clock64();   // store warp starts waiting for unit un
+        if (dbg != nullptr && blockIdx.x == 0 && un < 64) dbg[un * 8 + 5] = clock64();   // store warp starts waiting for unit un
         mbar_wait(staged_bar(sb), (uint32_t)(un / NBUF) & 1u);               // epilogue has staged unit un
         const uint32_t src = stg + sb * P::TILE_BYTES;
         for (int bx = 0; bx < nbox; ++bx) {
@@ -368,7 +397,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           }
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        if (g.dbg != nullptr && blockIdx.x == 0 && un < 64) g.dbg[un * 8 + 6] = clock64();   // store of unit un issued
+        if (dbg != nullptr && blockIdx.x == 0 && un < 64) dbg[un * 8 + 6] = clock64();   // store of unit un issued
         if (NBUF == 1 && tn < total) {
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           announce(tn, subn, 0);
@@ -389,15 +418,16 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       // warps (EPI0 + i) and (EPI0 + i + 4) have the same (warp & 3): the first takes columns [0,64), the second [64,128)
       chalf = ew >> 2;
     }
-    const int lim = g.n_keep < g.N ? g.n_keep : g.N;
     if (use_colacc) {
-      for (int i = et; i < g.n_out; i += EPI_WARPS * 32) colacc[i] = 0.f;
+      for (int i = et; i < grp.args[0].n_out; i += EPI_WARPS * 32) colacc[i] = 0.f;
       named_bar_sync(1, EPI_WARPS * 32);
     }
     int uses[2] = {0, 0}, j = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
-      int m0, n0, kb0, nkb;
-      tile_info(t, m0, n0, kb0, nkb);
+      int pi, m0, n0, kb0, nkb;
+      tile_info(t, pi, m0, n0, kb0, nkb);
+      const GemmArgs& g = grp.args[pi];
+      const int lim = g.n_keep < g.N ? g.n_keep : g.N;
       const bool has_mma = nkb > 0;
       const int ab = j & 1;
       const int ncols = min(BN, g.n_out - n0);
@@ -409,15 +439,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         ++uses[ab];
         tc_fence_after();
       }
-      if (g.dbg != nullptr && blockIdx.x == 0 && warp == EPI0 && lane == 0 && j * MT < 64) g.dbg[j * MT * 8 + 4] = clock64();
+      if (dbg != nullptr && blockIdx.x == 0 && warp == EPI0 && lane == 0 && j * MT < 64) dbg[j * MT * 8 + 4] = clock64();
 #pragma unroll 1
       for (int sub = 0; sub < MT; ++sub) {
         const int un = j * MT + sub, sb = un % NBUF;
         const int ms = m0 + sub * BM, m = ms + row;
-        const bool stamp = g.dbg != nullptr && blockIdx.x == 0 && warp == EPI0 && lane == 0 && un < 64;
-        if (stamp) g.dbg[un * 8 + 0] = clock64();
+        const bool stamp = dbg != nullptr && blockIdx.x == 0 && warp == EPI0 && lane == 0 && un < 64;
+        if (stamp) dbg[un * 8 + 0] = clock64();
         mbar_wait(ready_bar(sb), (uint32_t)(un / NBUF) & 1u);      // staging buffer writable (and aux tile landed)
-        if (stamp) g.dbg[un * 8 + 1] = clock64();
+        if (stamp) dbg[un * 8 + 1] = clock64();
         uint8_t* tile = stg_g + sb * P::TILE_BYTES;
         uint8_t* tile2 = tile + NBOX * BOX_BYTES;
         float scale = 1.0f;
@@ -499,7 +529,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             }
           }
         }
-        if (stamp) g.dbg[un * 8 + 2] = clock64();
+        if (stamp) dbg[un * 8 + 2] = clock64();
         if (has_mma && sub == MT - 1) {
           tc_fence_before();
           __syncwarp();
@@ -508,14 +538,14 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         fence_proxy_async();                                       // generic-proxy smem writes -> visible to the TMA (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(staged_bar(sb));                // 8 warps -> the store warp may ship the unit
-        if (stamp) g.dbg[un * 8 + 3] = clock64();
+        if (stamp) dbg[un * 8 + 3] = clock64();
       }
     }
     if (use_colacc) {
       named_bar_sync(1, EPI_WARPS * 32);
-      for (int i = et * 4; i < g.N; i += EPI_WARPS * 32 * 4) {
+      for (int i = et * 4; i < grp.args[0].N; i += EPI_WARPS * 32 * 4) {
         const float4 t4 = *reinterpret_cast<const float4*>(colacc + i);
-        red_add4(g.colsum + i, t4, i, g.N);
+        red_add4(grp.args[0].colsum + i, t4, i, grp.args[0].N);
       }
     }
   }
@@ -524,46 +554,157 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
-template <int EPI, typename OutT, int MT>
-int launch_mt(const TmapPack& maps, const GemmArgs& g, int total_tiles, cudaStream_t st) {
+constexpr int MAX_GROUP = 4;
+
+template <int EPI, typename OutT, int MT, int G>
+int launch_g(const Group<G>& grp, cudaStream_t st) {
   using P = Plan<EPI, OutT, MT>;
   static bool configured = false;   // benign race: attribute set is idempotent
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, OutT, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, OutT, MT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM);
     if (e != cudaSuccess) {
       set_error("vsx_gemm: cudaFuncSetAttribute(%d) failed: %s", P::SMEM, cudaGetErrorString(e));
       return VSX_ERR_CUDA;
     }
     configured = true;
   }
-  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  gemm_tc_kernel<EPI, OutT, MT><<<grid, GEMM_THREADS, P::SMEM, st>>>(maps, g);
+  const int grid = grp.total < num_sms() ? grp.total : num_sms();
+  gemm_tc_kernel<EPI, OutT, MT, G><<<grid, GEMM_THREADS, P::SMEM, st>>>(grp);
   return check_launch("vsx_gemm");
 }
 
-// 256-row CTA tiles when they still fill the machine at least once; 128-row tiles for small problems (more CTAs in flight)
-template <int EPI, typename OutT>
-int launch(const TmapPack& maps, const GemmArgs& g, int tiles128, cudaStream_t st) {
-  const int tiles_n = ceil_div(g.n_out, BN);
-  const int t128 = ceil_div(g.M, BM), t256 = ceil_div(g.M, 2 * BM);
-  if (EPI == VSX_EPI_ATOMIC) {
-    // weight gradients: few output tiles, long reductions.  256-row tiles unless the second sub-tile would be mostly padding;
-    // the reduction is then re-split so that about two work items per SM exist (the caller's split_k > 1 only permits splitting).
-    const bool mt2 = g_force_mt == 2 || (g_force_mt == 0 && 2 * t256 * 5 <= t128 * 6);
-    if (mt2) {
-      GemmArgs g2 = g;
-      if (g.split_k > 1) {
-        static const int per_sm = getenv("VSX_WGRAD_ITEMS_PER_SM") ? atoi(getenv("VSX_WGRAD_ITEMS_PER_SM")) : 2;
-        const int want = (per_sm * num_sms()) / (t256 * tiles_n);
-        g2.split_k = want < 1 ? 1 : (want > g.num_kb ? g.num_kb : want);
-      }
-      return launch_mt<EPI, OutT, 2>(maps, g2, t256 * tiles_n * g2.split_k, st);
-    }
-    return launch_mt<EPI, OutT, 1>(maps, g, tiles128, st);
+// Tile shape and reduction splits for a list of problems that run in one launch.
+//  * forward / dgrad: 256-row CTA tiles when they still fill the machine at least once; 128-row tiles for small problems.
+//  * weight gradients (ATOMIC): few output tiles, long reductions.  256-row tiles unless the second sub-tile would be mostly padding;
+//    the reductions are then split so that about two work items per SM exist over ALL problems (split_k > 1 only permits splitting).
+template <int EPI, typename OutT, int G>
+int launch(Group<G>& grp, cudaStream_t st) {
+  int t128 = 0, t256 = 0;
+  for (int q = 0; q < grp.count; ++q) {
+    const int tn = ceil_div(grp.args[q].n_out, BN);
+    t128 += ceil_div(grp.args[q].M, BM) * tn, t256 += ceil_div(grp.args[q].M, 2 * BM) * tn;
   }
-  const int tiles256 = t256 * tiles_n;
-  if (g_force_mt != 1 && (g_force_mt == 2 || tiles256 >= num_sms())) return launch_mt<EPI, OutT, 2>(maps, g, tiles256, st);
-  return launch_mt<EPI, OutT, 1>(maps, g, tiles128, st);
+  bool mt2;
+  if (EPI == VSX_EPI_ATOMIC) {
+    mt2 = g_force_mt == 2 || (g_force_mt == 0 && 2 * t256 * 5 <= t128 * 6);
+    static const int per_sm = getenv("VSX_WGRAD_ITEMS_PER_SM") ? atoi(getenv("VSX_WGRAD_ITEMS_PER_SM")) : 2;
+    const int tiles_mn = mt2 ? t256 : t128;
+    for (int q = 0; q < grp.count; ++q) {
+      GemmArgs& g = grp.args[q];
+      if (mt2 || grp.count > 1) {        // single 128-row problems keep the caller's split (tuned for that shape)
+        if (g.split_k > 1) {
+          const int want = (per_sm * num_sms()) / (tiles_mn > 0 ? tiles_mn : 1);
+          g.split_k = want < 1 ? 1 : (want > g.num_kb ? g.num_kb : want);
+        }
+      }
+    }
+  } else {
+    mt2 = g_force_mt != 1 && (g_force_mt == 2 || t256 >= num_sms());
+  }
+  int total = 0;
+  for (int q = 0; q < grp.count; ++q) {
+    const GemmArgs& g = grp.args[q];
+    const int tm = ceil_div(g.M, mt2 ? 2 * BM : BM), tn = ceil_div(g.n_out, BN);
+    total += tm * tn * (EPI == VSX_EPI_ATOMIC ? g.split_k : 1);
+    grp.tile_end[q] = total;
+  }
+  grp.total = total;
+  if (total == 0) return VSX_OK;
+  return mt2 ? launch_g<EPI, OutT, 2, G>(grp, st) : launch_g<EPI, OutT, 1, G>(grp, st);
+}
+
+// One problem descriptor -> kernel arguments + tensor maps.  Returns VSX_OK, an error, or 1 when there is nothing to do.
+int build_problem(const vsx_gemm_desc* d, TmapPack& maps, GemmArgs& g) {
+  VSX_REQUIRE(d->terms >= 1 && d->terms <= MAX_TERMS, "vsx_gemm: terms must be 1..6 (got %d)", d->terms);
+  VSX_REQUIRE(d->M > 0 && d->N >= 0 && d->K >= 0, "vsx_gemm: bad extents M=%d N=%d K=%d", d->M, d->N, d->K);
+  VSX_REQUIRE(d->lda % 8 == 0 && d->ldb % 8 == 0, "vsx_gemm: operand pitches must be multiples of 8 elements (lda=%ld ldb=%ld)", d->lda, d->ldb);
+  VSX_REQUIRE(d->out != nullptr && d->n_out >= d->N && d->n_out <= d->ldo, "vsx_gemm: need N <= n_out <= ldo (N=%d n_out=%d ldo=%ld)", d->N, d->n_out, d->ldo);
+  const bool f32 = d->out_dtype == VSX_F32;
+  VSX_REQUIRE(d->out_dtype == VSX_F32 || d->out_dtype == VSX_BF16, "vsx_gemm: bad out_dtype %d", d->out_dtype);
+  VSX_REQUIRE(d->ldo % (f32 ? 4 : 8) == 0, "vsx_gemm: ldo must be a multiple of %d elements (16 bytes) for the TMA store (ldo=%ld)", f32 ? 4 : 8, d->ldo);
+  if (d->n_out == 0) return 1;
+  g.M = d->M, g.N = d->N, g.K = d->K, g.num_kb = ceil_div(d->K, BK), g.terms = d->terms;
+  g.a_mn = d->a_layout == VSX_MNMAJOR, g.b_mn = d->b_layout == VSX_MNMAJOR;
+  g.n_out = d->n_out, g.split_k = d->split_k < 1 ? 1 : d->split_k;
+  g.bias = d->bias;
+  g.colsum = d->colsum;
+  g.row_scale = d->row_scale, g.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1, g.n_keep = d->n_keep;
+  g.dbg = g_gemm_dbg;
+  if (d->N > 0 && d->K > 0) {
+    for (int t = 0; t < d->terms; ++t) {
+      VSX_REQUIRE(d->a[t] != nullptr && d->b[t] != nullptr, "vsx_gemm: null operand for term %d", t);
+      int rc;
+      if (!g.a_mn) rc = make_tmap_2d(&maps.a[t], d->a[t], (uint64_t)d->K, (uint64_t)d->M, (uint64_t)d->lda, BK, BM);
+      else         rc = make_tmap_2d(&maps.a[t], d->a[t], (uint64_t)d->M, (uint64_t)d->K, (uint64_t)d->lda, 64, BK);
+      if (rc) return rc;
+      if (!g.b_mn) rc = make_tmap_2d(&maps.b[t], d->b[t], (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldb, BK, BN);
+      else         rc = make_tmap_2d(&maps.b[t], d->b[t], (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->ldb, 64, BK);
+      if (rc) return rc;
+    }
+  } else {
+    g.N = 0;   // nothing to contract: epilogue-only tiles
+  }
+  // epilogue tensor maps: [M rows, n_out columns], boxes of 128 rows x 128 bytes
+  const int odt = f32 ? VSX_F32 : VSX_BF16;
+  const uint32_t boxc = f32 ? 32 : 64;
+  const uint64_t ocols = d->epilogue == VSX_EPI_ATOMIC ? (uint64_t)d->N : (uint64_t)d->n_out;
+  if (ocols == 0) return 1;
+  int rc = make_tmap_2d(&maps.out, d->out, ocols, (uint64_t)d->M, (uint64_t)d->ldo, boxc, BM, odt);
+  if (rc) return rc;
+  maps.out2 = maps.out;
+  maps.aux = maps.out;
+  switch (d->epilogue) {
+    case VSX_EPI_STORE:
+      VSX_REQUIRE(d->colsum == nullptr || d->bias == nullptr, "vsx_gemm: STORE with colsum must not add a bias");
+      break;
+    case VSX_EPI_GELU:
+      VSX_REQUIRE(d->out2 != nullptr && d->ldo2 >= d->n_out && d->ldo2 % (f32 ? 4 : 8) == 0, "vsx_gemm: GELU epilogue needs out2 with a 16-byte-multiple pitch");
+      if ((rc = make_tmap_2d(&maps.out2, d->out2, ocols, (uint64_t)d->M, (uint64_t)d->ldo2, boxc, BM, odt))) return rc;
+      break;
+    case VSX_EPI_RESIDUAL:
+      VSX_REQUIRE(f32 && d->aux != nullptr, "vsx_gemm: RESIDUAL epilogue is fp32 and needs aux");
+    /* fall through */
+    case VSX_EPI_GELUGRAD:
+      VSX_REQUIRE(d->aux != nullptr && d->ld_aux % (f32 ? 4 : 8) == 0, "vsx_gemm: this epilogue needs aux with a 16-byte-multiple pitch");
+      if ((rc = make_tmap_2d(&maps.aux, d->aux, ocols, (uint64_t)d->M, (uint64_t)d->ld_aux, boxc, BM, odt))) return rc;
+      break;
+    case VSX_EPI_ATOMIC:
+      VSX_REQUIRE(f32, "vsx_gemm: ATOMIC epilogue accumulates into fp32");
+      if (g.N == 0) return 1;
+      g.split_k = (g.split_k > g.num_kb ? (g.num_kb > 0 ? g.num_kb : 1) : g.split_k);
+      g.n_out = d->N;
+      break;
+    default:
+      set_error("vsx_gemm: unknown epilogue %d", d->epilogue);
+      return VSX_ERR_ARG;
+  }
+  return VSX_OK;
+}
+
+template <int G>
+int run_group(const vsx_gemm_desc* descs, int count, cudaStream_t st) {
+  static thread_local Group<G>* tl = nullptr;     // host staging of the kernel parameter block (forward and backward threads each own one)
+  if (tl == nullptr) tl = new Group<G>();
+  Group<G>& gr = *tl;
+  gr.count = 0;
+  for (int i = 0; i < count; ++i) {
+    VSX_REQUIRE(descs[i].epilogue == descs[0].epilogue && descs[i].out_dtype == descs[0].out_dtype,
+                "vsx_gemm_grouped: all problems of a launch must share the epilogue and the output dtype");
+    const int rc = build_problem(&descs[i], gr.maps[gr.count], gr.args[gr.count]);
+    if (rc < 0) return rc;
+    if (rc == 0) ++gr.count;
+  }
+  if (gr.count == 0) return VSX_OK;
+  const bool f32 = descs[0].out_dtype == VSX_F32;
+  switch (descs[0].epilogue) {
+    case VSX_EPI_STORE: return f32 ? launch<VSX_EPI_STORE, float, G>(gr, st) : launch<VSX_EPI_STORE, bf16, G>(gr, st);
+    case VSX_EPI_GELU: return f32 ? launch<VSX_EPI_GELU, float, G>(gr, st) : launch<VSX_EPI_GELU, bf16, G>(gr, st);
+    case VSX_EPI_RESIDUAL: return launch<VSX_EPI_RESIDUAL, float, G>(gr, st);
+    case VSX_EPI_GELUGRAD: return f32 ? launch<VSX_EPI_GELUGRAD, float, G>(gr, st) : launch<VSX_EPI_GELUGRAD, bf16, G>(gr, st);
+    case VSX_EPI_ATOMIC: return launch<VSX_EPI_ATOMIC, float, G>(gr, st);
+  }
+  set_error("vsx_gemm: unknown epilogue %d", descs[0].epilogue);
+  return VSX_ERR_ARG;
 }
 
 }  // namespace
@@ -584,83 +725,11 @@ extern "C" int vsx_gemm_force_tile_rows(int rows) {
 
 extern "C" int vsx_gemm(const vsx_gemm_desc* d, void* stream) {
   VSX_REQUIRE(d != nullptr, "vsx_gemm: null descriptor");
-  VSX_REQUIRE(d->terms >= 1 && d->terms <= MAX_TERMS, "vsx_gemm: terms must be 1..6 (got %d)", d->terms);
-  VSX_REQUIRE(d->M > 0 && d->N >= 0 && d->K >= 0, "vsx_gemm: bad extents M=%d N=%d K=%d", d->M, d->N, d->K);
-  VSX_REQUIRE(d->lda % 8 == 0 && d->ldb % 8 == 0, "vsx_gemm: operand pitches must be multiples of 8 elements (lda=%ld ldb=%ld)", d->lda, d->ldb);
-  VSX_REQUIRE(d->out != nullptr && d->n_out >= d->N && d->n_out <= d->ldo, "vsx_gemm: need N <= n_out <= ldo (N=%d n_out=%d ldo=%ld)", d->N, d->n_out, d->ldo);
-  const bool f32 = d->out_dtype == VSX_F32;
-  VSX_REQUIRE(d->out_dtype == VSX_F32 || d->out_dtype == VSX_BF16, "vsx_gemm: bad out_dtype %d", d->out_dtype);
-  VSX_REQUIRE(d->ldo % (f32 ? 4 : 8) == 0, "vsx_gemm: ldo must be a multiple of %d elements (16 bytes) for the TMA store (ldo=%ld)", f32 ? 4 : 8, d->ldo);
-  if (d->n_out == 0) return VSX_OK;
+  return run_group<1>(d, 1, reinterpret_cast<cudaStream_t>(stream));
+}
 
-  GemmArgs g;
-  g.M = d->M, g.N = d->N, g.K = d->K, g.num_kb = ceil_div(d->K, BK), g.terms = d->terms;
-  g.a_mn = d->a_layout == VSX_MNMAJOR, g.b_mn = d->b_layout == VSX_MNMAJOR;
-  g.n_out = d->n_out, g.split_k = d->split_k < 1 ? 1 : d->split_k;
-  g.bias = d->bias;
-  g.colsum = d->colsum;
-  g.row_scale = d->row_scale, g.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1, g.n_keep = d->n_keep;
-  g.dbg = g_gemm_dbg;
-
-  TmapPack maps;
-  if (d->N > 0 && d->K > 0) {
-    for (int t = 0; t < d->terms; ++t) {
-      VSX_REQUIRE(d->a[t] != nullptr && d->b[t] != nullptr, "vsx_gemm: null operand for term %d", t);
-      int rc;
-      if (!g.a_mn) rc = make_tmap_2d(&maps.a[t], d->a[t], (uint64_t)d->K, (uint64_t)d->M, (uint64_t)d->lda, BK, BM);
-      else         rc = make_tmap_2d(&maps.a[t], d->a[t], (uint64_t)d->M, (uint64_t)d->K, (uint64_t)d->lda, 64, BK);
-      if (rc) return rc;
-      if (!g.b_mn) rc = make_tmap_2d(&maps.b[t], d->b[t], (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldb, BK, BN);
-      else         rc = make_tmap_2d(&maps.b[t], d->b[t], (uint64_t)d->N, (uint64_t)d->K, (uint64_t)d->ldb, 64, BK);
-      if (rc) return rc;
-    }
-  } else {
-    g.N = 0;   // nothing to contract: epilogue-only tiles
-    memset(&maps, 0, sizeof(maps));
-  }
-  int tiles = ceil_div(d->M, BM) * ceil_div(d->n_out, BN);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  {  // epilogue tensor maps: [M rows, n_out columns], boxes of 128 rows x 128 bytes
-    const int odt = f32 ? VSX_F32 : VSX_BF16;
-    const uint32_t boxc = f32 ? 32 : 64;
-    const uint64_t ocols = d->epilogue == VSX_EPI_ATOMIC ? (uint64_t)d->N : (uint64_t)d->n_out;
-    if (ocols == 0) return VSX_OK;
-    int rc = make_tmap_2d(&maps.out, d->out, ocols, (uint64_t)d->M, (uint64_t)d->ldo, boxc, BM, odt);
-    if (rc) return rc;
-    maps.out2 = maps.out;
-    maps.aux = maps.out;
-    if (d->epilogue == VSX_EPI_GELU) {
-      VSX_REQUIRE(d->out2 != nullptr && d->ldo2 >= d->n_out && d->ldo2 % (f32 ? 4 : 8) == 0, "vsx_gemm: GELU epilogue needs out2 with a 16-byte-multiple pitch");
-      rc = make_tmap_2d(&maps.out2, d->out2, ocols, (uint64_t)d->M, (uint64_t)d->ldo2, boxc, BM, odt);
-      if (rc) return rc;
-    }
-    if (d->epilogue == VSX_EPI_RESIDUAL || d->epilogue == VSX_EPI_GELUGRAD) {
-      VSX_REQUIRE(d->aux != nullptr && d->ld_aux % (f32 ? 4 : 8) == 0, "vsx_gemm: this epilogue needs aux with a 16-byte-multiple pitch");
-      rc = make_tmap_2d(&maps.aux, d->aux, ocols, (uint64_t)d->M, (uint64_t)d->ld_aux, boxc, BM, odt);
-      if (rc) return rc;
-    }
-  }
-  switch (d->epilogue) {
-    case VSX_EPI_STORE:
-      VSX_REQUIRE(d->colsum == nullptr || d->bias == nullptr, "vsx_gemm: STORE with colsum must not add a bias");
-      return f32 ? launch<VSX_EPI_STORE, float>(maps, g, tiles, st) : launch<VSX_EPI_STORE, bf16>(maps, g, tiles, st);
-    case VSX_EPI_GELU:
-      return f32 ? launch<VSX_EPI_GELU, float>(maps, g, tiles, st) : launch<VSX_EPI_GELU, bf16>(maps, g, tiles, st);
-    case VSX_EPI_RESIDUAL:
-      VSX_REQUIRE(f32 && d->aux != nullptr, "vsx_gemm: RESIDUAL epilogue is fp32 and needs aux");
-      return launch<VSX_EPI_RESIDUAL, float>(maps, g, tiles, st);
-    case VSX_EPI_GELUGRAD:
-      VSX_REQUIRE(d->aux != nullptr, "vsx_gemm: GELUGRAD epilogue needs aux (pre-activation)");
-      return f32 ? launch<VSX_EPI_GELUGRAD, float>(maps, g, tiles, st) : launch<VSX_EPI_GELUGRAD, bf16>(maps, g, tiles, st);
-    case VSX_EPI_ATOMIC:
-      VSX_REQUIRE(f32, "vsx_gemm: ATOMIC epilogue accumulates into fp32");
-      if (g.N == 0) return VSX_OK;
-      g.split_k = (g.split_k > g.num_kb ? (g.num_kb > 0 ? g.num_kb : 1) : g.split_k);
-      g.n_out = d->N;
-      tiles = ceil_div(d->M, BM) * ceil_div(d->N, BN) * g.split_k;
-      return launch<VSX_EPI_ATOMIC, float>(maps, g, tiles, st);
-    default:
-      set_error("vsx_gemm: unknown epilogue %d", d->epilogue);
-      return VSX_ERR_ARG;
-  }
+extern "C" int vsx_gemm_grouped(const vsx_gemm_desc* descs, int count, void* stream) {
+  VSX_REQUIRE(descs != nullptr && count >= 1 && count <= MAX_GROUP, "vsx_gemm_grouped: 1..%d problems per launch (got %d)", MAX_GROUP, count);
+  if (count == 1) return run_group<1>(descs, 1, reinterpret_cast<cudaStream_t>(stream));
+  return run_group<MAX_GROUP>(descs, count, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -79,11 +79,11 @@ _P6 = C.c_void_p * 6
 _PAIRS3 = [(0, 0), (1, 0), (0, 1)]
 _PAIRS6 = [(0, 0), (1, 0), (0, 1), (1, 1), (2, 0), (0, 2)]
 
-def gemm(a, b, lda, ldb, M, N, K, epilogue, out, ldo, *, a_off=0, b_off=0, out_off=0, a_layout=KMAJOR,
-         b_layout=KMAJOR, n_out=None, out2=None, ldo2=0, out2_off=0, bias=None, bias_off=0, aux=None, ld_aux=0,
-         aux_off=0, row_scale=None, row_scale_off=0, rows_per_sample=1, n_keep=0, split_k=1, colsum=None, colsum_off=0):
-    """a, b: a bf16 tensor, or tuples of 2 (3 product terms, ~2^-16) or 3 (6 terms, fp32-exact) bf16 parts whose sum is
-    the fp32 operand (split-bf16 high-precision mode)."""
+def _gemm_desc(a, b, lda, ldb, M, N, K, epilogue, out, ldo, *, a_off=0, b_off=0, out_off=0, a_layout=KMAJOR,
+               b_layout=KMAJOR, n_out=None, out2=None, ldo2=0, out2_off=0, bias=None, bias_off=0, aux=None, ld_aux=0,
+               aux_off=0, row_scale=None, row_scale_off=0, rows_per_sample=1, n_keep=0, split_k=1, colsum=None, colsum_off=0):
+    """-> (vsx_gemm_desc, profile record).  a, b: a bf16 tensor, or tuples of 2 (3 product terms, ~2^-16) or 3 (6 terms, fp32-exact)
+    bf16 parts whose sum is the fp32 operand (split-bf16 high-precision mode)."""
     if isinstance(a, (tuple, list)):
         n = min(len(a), len(b))
         pairs = _PAIRS3 if n == 2 else _PAIRS6
@@ -96,21 +96,45 @@ def gemm(a, b, lda, ldb, M, N, K, epilogue, out, ldo, *, a_off=0, b_off=0, out_o
     d = _lib.GemmDesc(pa, pb, nterms, lda, ldb, a_layout, b_layout, M, N, K, epilogue, _DT[out.dtype], _ptr(out, out_off), ldo,
                       _ptr(out2, out2_off), ldo2, N if n_out is None else n_out, _ptr(bias, bias_off), _ptr(aux, aux_off), ld_aux,
                       _ptr(row_scale, row_scale_off), rows_per_sample, n_keep, split_k, _ptr(colsum, colsum_off))
-    if PROFILE is not None:
+    if PROFILE is None:
+        return d, None
+    # algorithmic HBM bytes of the launch: both operands once + the output tile(s) + the aux tile the epilogue reads
+    es = 4 if out.dtype == torch.float32 else 2
+    nbytes = 2.0 * nterms * (M * K + N * K) + es * M * d.n_out * (2 if epilogue == EPI_GELU else 1)
+    if epilogue in (EPI_RESIDUAL, EPI_GELUGRAD):
+        nbytes += es * M * d.n_out
+    if epilogue == EPI_ATOMIC:
+        nbytes += es * M * d.n_out          # read-modify-write of the fp32 gradient tile
+    return d, (2.0 * M * N * K, (M, N, K, epilogue, a_layout, b_layout, d.n_out, split_k, nterms), nbytes)
+
+
+def gemm(*args, **kw):
+    """One GEMM launch (see _gemm_desc for the arguments)."""
+    d, rec = _gemm_desc(*args, **kw)
+    if rec is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         _ck(_lib.lib().vsx_gemm(C.byref(d), _stream()))
         e1.record()
-        # algorithmic HBM bytes of the launch: both operands once + the output tile(s) + the aux tile the epilogue reads
-        es = 4 if out.dtype == torch.float32 else 2
-        nbytes = 2.0 * nterms * (M * K + N * K) + es * M * d.n_out * (2 if epilogue == EPI_GELU else 1)
-        if epilogue in (EPI_RESIDUAL, EPI_GELUGRAD):
-            nbytes += es * M * d.n_out
-        if epilogue == EPI_ATOMIC:
-            nbytes += es * M * d.n_out          # read-modify-write of the fp32 gradient tile
-        PROFILE.append((e0, e1, 2.0 * M * N * K, (M, N, K, epilogue, a_layout, b_layout, d.n_out, split_k, nterms), nbytes))
+        PROFILE.append((e0, e1, rec[0], rec[1], rec[2]))
         return
     _ck(_lib.lib().vsx_gemm(C.byref(d), _stream()))
+
+
+def gemm_grouped(problems):
+    """Up to 4 problems (each a (args, kwargs) pair for _gemm_desc) with the same epilogue / output dtype in ONE launch."""
+    if len(problems) == 1:
+        return gemm(*problems[0][0], **problems[0][1])
+    built = [_gemm_desc(*a, **k) for a, k in problems]
+    arr = (_lib.GemmDesc * len(built))(*[b[0] for b in built])
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _ck(_lib.lib().vsx_gemm_grouped(arr, len(built), _stream()))
+        e1.record()
+        PROFILE.append((e0, e1, sum(b[1][0] for b in built), (sum(b[1][1][0] for b in built),) + built[0][1][1][1:], sum(b[1][2] for b in built)))
+        return
+    _ck(_lib.lib().vsx_gemm_grouped(arr, len(built), _stream()))
 
 
 # ------------------------------------------------------------------------------------------------ attention core
