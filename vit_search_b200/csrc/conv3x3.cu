@@ -144,21 +144,45 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) conv3x3_fwd_kernel(const bf16*
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+    if (C <= 24) {
+      // Packed reduction for the 24-channel stem: K = 9 taps x 3 channel groups of 8 = 27 groups (+1 zero group) = 14 k16 steps instead of
+      // 18, and 3 output-channel tiles instead of 4: 42 MMAs per warp and tile instead of 72.  Every ldmatrix row address is per lane, so
+      // the two k8 halves of a step may come from different taps; group 27 reads the zero-padded channels 24..31 of a pixel / weight row.
 #pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int ky = tap / 3, kx = tap % 3;
-#pragma unroll
-      for (int kc = 0; kc < 2; ++kc) {
+      for (int ks = 0; ks < 14; ++ks) {
+        constexpr int NG = 27;
+        const int q0 = 2 * ks, q1 = 2 * ks + 1;
+        const int t0 = q0 < NG ? q0 / 3 : 0, c0 = q0 < NG ? q0 % 3 : 3;
+        const int t1 = q1 < NG ? q1 / 3 : 0, c1 = q1 < NG ? q1 % 3 : 3;
+        // A: matrix lj covers pixels li + (lj & 1) * 8, k group (lj >> 1)
+        const int a0 = (((t0 / 3) * HW + t0 % 3) * PITCH + c0 * 8), a1 = (((t1 / 3) * HW + t1 % 3) * PITCH + c1 * 8);
+        // B: matrix lj covers n rows li + (lj >> 1) * 8, k group (lj & 1)
+        const int b0 = (t0 * CP * PITCH + c0 * 8), b1 = (t1 * CP * PITCH + c1 * 8);
         uint32_t a[4], w01[4], w23[4];
-        // A: 16 pixels of tile row `warp` (x = 0..15) shifted by the tap, 16 channels
-        ldsm4(a, halo_a + (uint32_t)(((warp + ky) * HW + kx + li + (lj & 1) * 8) * PITCH + kc * 16 + (lj >> 1) * 8) * 2u);
-        // B: weights [n][k]: n-tiles (0,1) and (2,3)
-        ldsm4(w01, wts_a + (uint32_t)((tap * CP + li + (lj >> 1) * 8) * PITCH + kc * 16 + (lj & 1) * 8) * 2u);
-        ldsm4(w23, wts_a + (uint32_t)((tap * CP + 16 + li + (lj >> 1) * 8) * PITCH + kc * 16 + (lj & 1) * 8) * 2u);
+        ldsm4(a, halo_a + (uint32_t)((warp * HW + li + (lj & 1) * 8) * PITCH + ((lj >> 1) ? a1 : a0)) * 2u);
+        ldsm4(w01, wts_a + (uint32_t)((li + (lj >> 1) * 8) * PITCH + ((lj & 1) ? b1 : b0)) * 2u);
+        ldsm4(w23, wts_a + (uint32_t)((16 + li + (lj >> 1) * 8) * PITCH + ((lj & 1) ? b1 : b0)) * 2u);
         mma16816(acc[0], a, w01[0], w01[1]);
         mma16816(acc[1], a, w01[2], w01[3]);
         mma16816(acc[2], a, w23[0], w23[1]);
-        mma16816(acc[3], a, w23[2], w23[3]);
+      }
+    } else {
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const int ky = tap / 3, kx = tap % 3;
+#pragma unroll
+        for (int kc = 0; kc < 2; ++kc) {
+          uint32_t a[4], w01[4], w23[4];
+          // A: 16 pixels of tile row `warp` (x = 0..15) shifted by the tap, 16 channels
+          ldsm4(a, halo_a + (uint32_t)(((warp + ky) * HW + kx + li + (lj & 1) * 8) * PITCH + kc * 16 + (lj >> 1) * 8) * 2u);
+          // B: weights [n][k]: n-tiles (0,1) and (2,3)
+          ldsm4(w01, wts_a + (uint32_t)((tap * CP + li + (lj >> 1) * 8) * PITCH + kc * 16 + (lj & 1) * 8) * 2u);
+          ldsm4(w23, wts_a + (uint32_t)((tap * CP + 16 + li + (lj >> 1) * 8) * PITCH + kc * 16 + (lj & 1) * 8) * 2u);
+          mma16816(acc[0], a, w01[0], w01[1]);
+          mma16816(acc[1], a, w01[2], w01[3]);
+          mma16816(acc[2], a, w23[0], w23[1]);
+          mma16816(acc[3], a, w23[2], w23[3]);
+        }
       }
     }
     // epilogue: thread holds pixels x = g, g+8 of row `warp`, channels nt*8 + 2t + {0,1}
