@@ -222,7 +222,8 @@ int vsx_sr_combine_bwd(const float* gy, void* dconv, void* dtok, int dtype, floa
  *              (timm SoftTargetCrossEntropy, main.py:392-394; dlogits may be NULL).
  * vsx_adamw  : one launch over all parameters (torch.optim.AdamW semantics: decoupled decay, bias correction); each
  *              chunk i of vsx_adamw_chunk_elems() elements belongs to tensor chunk_tensor[i] at chunk_index[i].
- *              shadow_hi / shadow_lo (bf16, may be NULL) receive the refreshed GEMM operand copies of the weight.
+ *              shadow_hi / shadow_lo (bf16, may be NULL) receive the refreshed GEMM operand copies of the weight;
+ *              ema (fp32, may be NULL) the updated moving average.
  * -------------------------------------------------------------------------------------------------- */
 typedef struct vsx_adamw_tensor {
   float* param;
@@ -233,6 +234,9 @@ typedef struct vsx_adamw_tensor {
   void* shadow_lo;
   long numel;
   float weight_decay;
+  float ema_decay;   /* used when ema != NULL */
+  float* ema;        /* NULL, or the exponential moving average of the parameter (timm ModelEmaV2, main.py:357-363, engine.py:179-180):
+                        ema = ema_decay * ema + (1 - ema_decay) * param_new, written in the same pass */
 } vsx_adamw_tensor;
 int vsx_soft_ce(const float* logits, long ld, const float* target, long ldt, int rows, int cols, float loss_scale,
                 float grad_scale, float* loss_sum, float* dlogits, long ldd, void* stream);

@@ -492,3 +492,13 @@ def synthetic_batch(batch, seed=1234, num_classes=1000, num_patch_targets=16, dt
     t = torch.full((batch, num_classes), 0.1 / num_classes)
     t[torch.arange(batch), y] += 0.9
     return x.to(dtype), t.to(dtype), t.unsqueeze(1).repeat(1, num_patch_targets, 1).to(dtype)
+
+
+def ema_update(ema_state, model_state, decay):
+    """timm 0.3.2 ModelEmaV2._update (source absent from /root/reference; call sites main.py:357-363, engine.py:179-180): every
+    state_dict entry, parameters and buffers alike, follows ema = decay * ema + (1 - decay) * model.  "parity unpinned": the
+    reference ships no test for it; this restates the published formula."""
+    for k, m in model_state.items():
+        e = ema_state[k]
+        ema_state[k] = (decay * e.double() + (1.0 - decay) * m.double()).to(e.dtype)
+    return ema_state

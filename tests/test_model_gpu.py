@@ -210,3 +210,35 @@ def test_fused_adamw_operand_shadows():
         losses[mode] = out
     # split-K / bias-gradient reductions use atomics, so two runs agree to rounding, not bit for bit
     assert all(abs(a - b) < 2e-3 * abs(b) for a, b in zip(losses['shadow'], losses['recast'])), losses
+
+
+def test_model_ema_fused_into_optimizer():
+    """ModelEma (timm ModelEmaV2 semantics) with the parameter averages updated inside the fused AdamW kernel and the buffers by
+    ModelEma.update: after every step the EMA state must equal the oracle's recursion over the model's own post-step states."""
+    from vit_search_b200 import core
+    from vit_search_b200.engine import TrainStep, FusedAdamW, ModelEma
+    case = CASES['small_single']
+    B = case['batch']
+    x, t, pt = O.synthetic_batch(B, seed=11)
+    m, nd = build(case)
+    m.train()
+    decay = 0.9
+    ema = ModelEma(m, decay=decay)
+    step = TrainStep(m, FusedAdamW(m, lr=1e-3, weight_decay=0.05), arch_sample='single', model_ema=ema)
+    ref = {k: v.detach().clone().cpu() for k, v in m.state_dict().items()}
+    with core.precision('bf16'):
+        for it in range(3):
+            step(x.cuda(), t.cuda(), pt.cuda(), epoch=2)
+            torch.cuda.synchronize()
+            ref = O.ema_update(ref, {k: v.detach().cpu() for k, v in m.state_dict().items()}, decay)
+    assert ema.fused
+    got = ema.module.state_dict()
+    assert set(got) == set(ref)
+    for k in ref:
+        if ref[k].is_floating_point():
+            assert rel(got[k], ref[k]) < 1e-6, k
+        else:
+            assert torch.equal(got[k].cpu(), ref[k]), k
+    # the average really moved away from the initial weights and differs from the live model
+    name = next(n for n, p in m.named_parameters() if p.ndim == 2)
+    assert rel(got[name], m.state_dict()[name]) > 1e-6

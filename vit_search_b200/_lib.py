@@ -64,7 +64,7 @@ _RESTYPES = {'vsx_last_error': C.c_char_p}
 
 class AdamWTensor(C.Structure):
     _fields_ = [('param', _p), ('grad', _p), ('exp_avg', _p), ('exp_avg_sq', _p), ('shadow_hi', _p), ('shadow_lo', _p),
-                ('numel', _l), ('weight_decay', _f)]
+                ('numel', _l), ('weight_decay', _f), ('ema_decay', _f), ('ema', _p)]
 
 
 _lib = None

@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(const vsx_adamw_tensor* __re
   const float inv_sqrt_bc2 = rsqrtf(bc2);
   bf16* hi = reinterpret_cast<bf16*>(t.shadow_hi);
   bf16* lo = reinterpret_cast<bf16*>(t.shadow_lo);
+  float* ema = t.ema;
+  const float ed = t.ema_decay, ed1 = 1.0f - t.ema_decay;
   auto update = [&](float& p, float g, float& m, float& v) {
     g *= gs;
     p *= decay;
@@ -89,7 +91,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const vsx_adamw_tensor* __re
     p -= step * m / (sqrtf(v) * inv_sqrt_bc2 + eps);
   };
   // 16-byte path: 4 elements per thread per access (28 B/parameter of traffic is all this kernel does)
-  const bool vec = (((uintptr_t)t.param | (uintptr_t)t.grad | (uintptr_t)t.exp_avg | (uintptr_t)t.exp_avg_sq) & 15) == 0 &&
+  const bool vec = (((uintptr_t)t.param | (uintptr_t)t.grad | (uintptr_t)t.exp_avg | (uintptr_t)t.exp_avg_sq | (uintptr_t)ema) & 15) == 0 &&
                    ((uintptr_t)hi & 7) == 0 && ((uintptr_t)lo & 7) == 0;
   const long vend = vec ? begin + ((end - begin) & ~3L) : begin;
   for (long i = begin + 4L * threadIdx.x; i < vend; i += 4 * 256) {
@@ -102,6 +104,11 @@ __global__ void __launch_bounds__(256) adamw_kernel(const vsx_adamw_tensor* __re
     st4(t.param + i, p);
     st4(t.exp_avg + i, m);
     st4(t.exp_avg_sq + i, v);
+    if (ema != nullptr) {
+      float4 e = ld4(ema + i);
+      e.x = ed * e.x + ed1 * p.x, e.y = ed * e.y + ed1 * p.y, e.z = ed * e.z + ed1 * p.z, e.w = ed * e.w + ed1 * p.w;
+      st4(ema + i, e);
+    }
     if (hi != nullptr) {
       st4(hi + i, p);
       if (lo != nullptr) {
@@ -116,6 +123,7 @@ __global__ void __launch_bounds__(256) adamw_kernel(const vsx_adamw_tensor* __re
     t.param[i] = p;
     t.exp_avg[i] = m;
     t.exp_avg_sq[i] = v;
+    if (ema != nullptr) ema[i] = ed * ema[i] + ed1 * p;
     if (hi != nullptr) {
       const bf16 h = __float2bfloat16_rn(p);
       hi[i] = h;

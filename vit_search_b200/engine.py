@@ -66,9 +66,15 @@ class FusedAdamW:
             self.entries.append((name, p, 0.0 if no_decay else weight_decay))
         self.state = {}
         self.shadow = {}          # name -> bf16 GEMM-operand copy refreshed by the optimizer kernel itself
+        self.ema = None           # ModelEma attached with attach_ema(): parameter averages are then updated inside the same kernel
         self._table_key = None
         self.param_groups = [{'lr': lr}]
         self.chunk = _lib.lib().vsx_adamw_chunk_elems()
+
+    def attach_ema(self, ema):
+        """Fold `ema.update(model)` for the PARAMETERS into the optimizer kernel (buffers are averaged by ModelEma.update_buffers)."""
+        self.ema = ema
+        self._table_key = None
 
     def zero_grad(self, set_to_none=True):
         for _, p, _ in self.entries:
@@ -80,7 +86,7 @@ class FusedAdamW:
         dev = self.entries[0][1].device
         n = len(self.entries)
         rec = np.zeros(n, dtype=np.dtype([('param', '<u8'), ('grad', '<u8'), ('m', '<u8'), ('v', '<u8'), ('hi', '<u8'), ('lo', '<u8'),
-                                          ('numel', '<i8'), ('wd', '<f4'), ('pad', '<u4')]))
+                                          ('numel', '<i8'), ('wd', '<f4'), ('ema_decay', '<f4'), ('ema', '<u8')]))
         assert rec.itemsize == C.sizeof(_lib.AdamWTensor)
         chunks = []
         for i, (name, p, wd) in enumerate(self.entries):
@@ -101,7 +107,10 @@ class FusedAdamW:
                     sh = torch.empty(p.shape, device=p.device, dtype=torch.bfloat16)
                     self.shadow[name] = sh
                 hi = sh.data_ptr()
-            rec[i] = (p.data_ptr(), p.grad.data_ptr(), st[0].data_ptr(), st[1].data_ptr(), hi, 0, p.numel(), wd, 0)
+            ema_ptr, ema_decay = 0, 0.0
+            if self.ema is not None:
+                ema_ptr, ema_decay = self.ema.param_of(name).data_ptr(), self.ema.decay
+            rec[i] = (p.data_ptr(), p.grad.data_ptr(), st[0].data_ptr(), st[1].data_ptr(), hi, 0, p.numel(), wd, ema_decay, ema_ptr)
             chunks.append(math.ceil(p.numel() / self.chunk))
         if getattr(self, '_chunks', None) != chunks:
             self._chunks = chunks
@@ -119,10 +128,10 @@ class FusedAdamW:
         all-reduce; a loss-scaler's inverse scale)."""
         # gradient tensors are re-allocated by every backward, parameters by `rewiring`: re-derive the pointer table when
         # any pointer changed (a host-side comparison of ~250 integers)
-        key = (core.get_precision(),) + tuple((p.data_ptr(), 0 if p.grad is None else p.grad.data_ptr()) for _, p, _ in self.entries)
+        key = (core.get_precision(), id(self.ema)) + tuple((p.data_ptr(), 0 if p.grad is None else p.grad.data_ptr()) for _, p, _ in self.entries)
         if key != self._table_key:
             self._build_table()
-            self._table_key = (core.get_precision(),) + tuple((p.data_ptr(), p.grad.data_ptr()) for _, p, _ in self.entries)
+            self._table_key = (core.get_precision(), id(self.ema)) + tuple((p.data_ptr(), p.grad.data_ptr()) for _, p, _ in self.entries)
         self.step_count += 1
         self.lr = self.param_groups[0]['lr']
         ops.call('adamw', self._tab, self._ct, self._ci, self._nchunks, float(self.lr), float(self.betas[0]), float(self.betas[1]),
@@ -135,11 +144,44 @@ class FusedAdamW:
                     core.weights.adopt_shadow(p, sh)
 
 
+class ModelEma:
+    """timm's ModelEmaV2 (main.py:26,69,357-363; engine.py:179-180): `module` is a deep copy of the model whose state_dict entries
+    follow `ema = decay * ema + (1 - decay) * model` after every optimizer step.  With `FusedAdamW.attach_ema(ema)` the parameter part
+    of that update happens inside the optimizer kernel (one extra 8 B/parameter of traffic instead of a second pass over all
+    weights); `update(model)` then only averages the buffers (BatchNorm running statistics), or everything when not attached."""
+
+    def __init__(self, model, decay=0.99996):
+        import copy
+        self.module = copy.deepcopy(model)
+        self.module.eval()
+        for p in self.module.parameters():
+            p.requires_grad_(False)
+        self.decay = decay
+        self._params = dict(self.module.named_parameters())
+        self.fused = False
+
+    def param_of(self, name):
+        self.fused = True
+        return self._params[name]
+
+    @torch.no_grad()
+    def update(self, model):
+        ema_sd, sd = self.module.state_dict(), model.state_dict()
+        for k, e in ema_sd.items():
+            if self.fused and k in self._params:
+                continue                      # already averaged by the optimizer kernel
+            m = sd[k]
+            if e.is_floating_point():
+                e.mul_(self.decay).add_(m.detach().to(e.dtype), alpha=1.0 - self.decay)
+            else:
+                e.copy_((self.decay * e + (1.0 - self.decay) * m).to(e.dtype))      # num_batches_tracked: timm applies the same formula
+
+
 # ------------------------------------------------------------------------------------------------ train step
 class TrainStep:
     """One data-parallel training step, the drop-in for the body of engine.train_one_epoch."""
 
-    def __init__(self, model, optimizer=None, criterion=None, arch_sample='multi', world_size=1, ddp_model=None):
+    def __init__(self, model, optimizer=None, criterion=None, arch_sample='multi', world_size=1, ddp_model=None, model_ema=None):
         self.model = model
         self.net = ddp_model if ddp_model is not None else model
         self.optimizer = optimizer if optimizer is not None else FusedAdamW(model)
@@ -148,6 +190,9 @@ class TrainStep:
         self.world_size = world_size
         self.train_iter = 0
         self._pool_numel = None
+        self.model_ema = model_ema
+        if model_ema is not None and hasattr(self.optimizer, 'attach_ema'):
+            self.optimizer.attach_ema(model_ema)
         # native data parallelism (world_size > 1 and no DDP wrapper): all parameter gradients of a step live in ONE flat pool
         # (core.grad_pool), so the exchange is an in-place NCCL all-reduce of that buffer -- no bucket copies, no per-parameter hooks.
         # The part produced by the transformer / SR blocks is reduced on a side stream while the stem backward still runs.
@@ -189,6 +234,8 @@ class TrainStep:
             self.optimizer.step(grad_scale=self._inv_world)
         else:
             self.optimizer.step()
+        if self.model_ema is not None:
+            self.model_ema.update(self.model)                    # engine.py:179-180
         return loss.detach()
 
     # ------------------------------------------------------------------ native data parallelism
