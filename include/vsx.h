@@ -142,6 +142,57 @@ int vsx_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* l
 int vsx_attn_debug_buffer(void* buffer);
 
 /* ----------------------------------------------------------------------------------------------------
+ * One half of a transformer Block in one call (bf16 training path) -- replaces Block.forward's
+ *     x = x + mask * drop_path(attn(norm1(x)))      /      x = x + mask * drop_path(mlp(norm2(x)))
+ * (nets/supernet_blocks.py:213-253 with Attention.forward :100-120 and Mlp.forward :37-52) and its autograd.
+ * The call only sequences the kernels declared in this header, once per SEGMENT: a run of consecutive samples [b0, b1) that
+ * share one sub-architecture in this layer.  embed_keep: kept input (embedding) channels; inner_keep: kept heads * head_dim
+ * (attention) or hidden channels (MLP); out_keep: channels of the branch output that reach the residual (layer & embed
+ * mask); active == 0: the block is dropped for these samples (x passes through).  All buffers are caller-allocated with FULL
+ * widths as pitches ([batch*tokens, width | 3*heads*head_dim | heads*head_dim | hidden]); only kept prefixes are touched.
+ * -------------------------------------------------------------------------------------------------- */
+#define VSX_HALF_ATTN 0
+#define VSX_HALF_MLP 1
+typedef struct vsx_segment {
+  int b0, b1, embed_keep, inner_keep, out_keep, active;
+} vsx_segment;
+typedef struct vsx_half_block {
+  int kind;                  /* VSX_HALF_ATTN | VSX_HALF_MLP */
+  int batch, tokens, width;
+  int heads, head_dim;       /* attention half */
+  int hidden;                /* MLP half */
+  int pre_norm, residual;    /* 0: no LayerNorm in front (input is only masked) / no residual add (SR token transform style use) */
+  float eps;
+  int num_segments;
+  const vsx_segment* segments;   /* host memory */
+  const float* x;            /* [batch*tokens, width] fp32 residual stream in */
+  float* out;                /* [batch*tokens, width] fp32 residual stream out */
+  const float *ln_w, *ln_b;
+  const void *w1, *w2;       /* bf16 operand copies: qkv [3*H*D, width] / fc1 [hidden, width];  proj [width, H*D] / fc2 [width, hidden] */
+  const float *b1, *b2;
+  const float* row_scale;    /* NULL or the per-sample drop-path scale table; entry scale_off + sample is used */
+  int scale_off;
+  void* xn;                  /* bf16 [batch*tokens, width]: LayerNorm output (saved for the backward) */
+  float *mean, *rstd;        /* [batch*tokens] */
+  void* act1;                /* bf16: qkv [.., 3*H*D]  | fc1 pre-activation u [.., hidden] */
+  void* act2;                /* bf16: attention output o [.., H*D] | gelu(u) [.., hidden] */
+  float* lse;                /* attention: [batch, heads, tokens] */
+} vsx_half_block;
+typedef struct vsx_half_block_grad {
+  vsx_half_block fwd;        /* the forward call's descriptor (`out` is not used) */
+  const float* g_out;        /* [batch*tokens, width] fp32 gradient of `out` */
+  float* g_in;               /* [batch*tokens, width] fp32 gradient of `x` */
+  void *df, *dxn;            /* bf16 scratch [batch*tokens, width] */
+  void* d_act1;              /* bf16 scratch: dqkv [.., 3*H*D] | du [.., hidden] */
+  void* d_act2;              /* bf16 scratch: d_o [.., H*D] (attention only) */
+  float *d_ln_w, *d_ln_b, *d_w1, *d_b1, *d_w2, *d_b2;   /* fp32 parameter gradients, ACCUMULATED into (zero them once per step) */
+} vsx_half_block_grad;
+int vsx_half_block_fwd(const vsx_half_block* d, void* stream);
+int vsx_half_block_bwd(const vsx_half_block_grad* d, void* stream);
+/* Kernels launched by this thread through the library so far (bench.py's gpu_launches). */
+long vsx_launch_count(void);
+
+/* ----------------------------------------------------------------------------------------------------
  * Elementwise helpers around the GEMMs.
  * vsx_split_bf16     : hi = bf16(src), lo = bf16(src - hi), lo2 = bf16(src - hi - lo) (lo / lo2 may be NULL: plain
  *                      cast / 2-way split).  Operand preparation for vsx_gemm (weights every step; activations only

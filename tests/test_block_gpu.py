@@ -23,7 +23,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+@pytest.mark.parametrize('prec', ['fp32', 'bf16', 'bf16_python'])     # bf16: native half-block calls; bf16_python: core.py orchestration
 @pytest.mark.parametrize('ci', range(len(CASES)))
 def test_block_parity(ci, prec):
     from vit_search_b200 import core
@@ -59,10 +59,16 @@ def test_block_parity(ci, prec):
     blk.load_state_dict(w)
     xd = x.cuda().requires_grad_(True)
     dpt = None if dp is None else torch.tensor(dp, dtype=torch.float32).cuda().contiguous()
-    with core.precision(prec):
-        y, cur = blk.forward_keeps(xd, c['embed'], c.get('layer_in'), keeps, dpt, 0)
-        y.backward(gout.cuda())
-    torch.cuda.synchronize()
+    native0 = core.USE_NATIVE_HALF
+    core.USE_NATIVE_HALF = prec != 'bf16_python'
+    prec = 'bf16' if prec == 'bf16_python' else prec
+    try:
+        with core.precision(prec):
+            y, cur = blk.forward_keeps(xd, c['embed'], c.get('layer_in'), keeps, dpt, 0)
+            y.backward(gout.cuda())
+        torch.cuda.synchronize()
+    finally:
+        core.USE_NATIVE_HALF = native0
     assert cur == cur_o
     tol = 2e-5 if prec == 'fp32' else 2e-2      # fp32 parity path / bf16 training path, rel-L2 vs the fp64 oracle
     errs = {'y': rel(y, yo)}

@@ -37,6 +37,9 @@ SIGNATURES = {
     'vsx_attn_debug_buffer': [_p],
     'vsx_gemm_force_tile_rows': [_i],
     'vsx_gemm_grouped': [_p, _i, _p],
+    'vsx_half_block_fwd': [_p, _p],
+    'vsx_half_block_bwd': [_p, _p],
+    'vsx_launch_count': [],
     'vsx_gemm_debug_buffer': [_p],
     'vsx_split_bf16': [_p, _l, _p, _p, _p, _l, _i, _i, _p],
     'vsx_scale_mask_cast': [_p, _l, _p, _i, _i, _p, _i, _l, _i, _i, _p, _p],
@@ -58,13 +61,29 @@ SIGNATURES = {
     'vsx_adamw_chunk_elems': [],
     'vsx_adamw': [_p, _p, _p, _i, _f, _f, _f, _f, _i, _p, _p],
 }
-_RESTYPES = {'vsx_last_error': C.c_char_p}
+_RESTYPES = {'vsx_last_error': C.c_char_p, 'vsx_launch_count': C.c_long}
 
 
 
 class AdamWTensor(C.Structure):
     _fields_ = [('param', _p), ('grad', _p), ('exp_avg', _p), ('exp_avg_sq', _p), ('shadow_hi', _p), ('shadow_lo', _p),
                 ('numel', _l), ('weight_decay', _f), ('ema_decay', _f), ('ema', _p)]
+
+
+class Segment(C.Structure):
+    _fields_ = [('b0', _i), ('b1', _i), ('embed_keep', _i), ('inner_keep', _i), ('out_keep', _i), ('active', _i)]
+
+
+class HalfBlock(C.Structure):
+    _fields_ = [('kind', _i), ('batch', _i), ('tokens', _i), ('width', _i), ('heads', _i), ('head_dim', _i), ('hidden', _i),
+                ('pre_norm', _i), ('residual', _i), ('eps', _f), ('num_segments', _i), ('segments', _p),
+                ('x', _p), ('out', _p), ('ln_w', _p), ('ln_b', _p), ('w1', _p), ('w2', _p), ('b1', _p), ('b2', _p),
+                ('row_scale', _p), ('scale_off', _i), ('xn', _p), ('mean', _p), ('rstd', _p), ('act1', _p), ('act2', _p), ('lse', _p)]
+
+
+class HalfBlockGrad(C.Structure):
+    _fields_ = [('fwd', HalfBlock), ('g_out', _p), ('g_in', _p), ('df', _p), ('dxn', _p), ('d_act1', _p), ('d_act2', _p),
+                ('d_ln_w', _p), ('d_ln_b', _p), ('d_w1', _p), ('d_b1', _p), ('d_w2', _p), ('d_b2', _p)]
 
 
 _lib = None

@@ -459,6 +459,78 @@ def mlp_half_backward(meta, g_out, saved, x, ln_w, ln_b, fc1_w, fc1_b, fc2_w, fc
     return g_in, (d_lnw, d_lnb, d_w1, d_b1, d_w2, d_b2)
 
 
+# ------------------------------------------------------------------------------------------------ native fast path
+# bf16 training path: one C-ABI call per half block and direction (csrc/half_block.cu sequences exactly the launches that the Python
+# routines above issue).  The Python routines remain the implementation of the fp32 parity mode (split-bf16 operands) and of the
+# instrumented runs (ops.PROFILE), and are the readable specification of the native one.
+import ctypes as _C
+
+from . import _lib
+
+USE_NATIVE_HALF = True
+
+
+def _segments_c(meta):
+    arr = getattr(meta, '_cseg', None)
+    if arr is None:
+        arr = (_lib.Segment * len(meta.segs))(*[(s.b0, s.b1, s.ek, s.ik, s.ck, 1 if s.active else 0) for s in meta.segs])
+        meta._cseg = arr
+    return arr
+
+
+def _half_desc(meta, x, out, params, ws16, ws32):
+    """vsx_half_block for this call.  ws16: bf16 workspace [xn | act1 | act2]; ws32: fp32 [mean | rstd | lse]."""
+    B, N, C = x.shape
+    M = B * N
+    ln_w, ln_b, w1, b1, w2, b2 = params
+    attn = meta.kind == 'attn'
+    inner = 3 * meta.H * meta.D if attn else meta.F
+    a2 = meta.H * meta.D if attn else meta.F
+    p16, p32 = ws16.data_ptr(), ws32.data_ptr()
+    rs = meta.row_scale
+    wa, wb = weights.get(w1), weights.get(w2)
+    return _lib.HalfBlock(0 if attn else 1, B, N, C, meta.H, meta.D, meta.F, 1 if meta.pre_norm else 0, 1 if meta.residual else 0,
+                          meta.eps, len(meta.segs), _C.cast(_segments_c(meta), _C.c_void_p),
+                          x.data_ptr(), out.data_ptr() if out is not None else None, ln_w.data_ptr(), ln_b.data_ptr(), wa.data_ptr(), wb.data_ptr(),
+                          None if b1 is None else b1.data_ptr(), None if b2 is None else b2.data_ptr(),
+                          None if rs is None else rs.data_ptr(), meta.scale_off,
+                          p16, p32, p32 + 4 * M, p16 + 2 * M * C, p16 + 2 * M * (C + inner), (p32 + 8 * M) if attn else None), a2
+
+
+def native_half_forward(meta, x, params):
+    B, N, C = x.shape
+    M = B * N
+    attn = meta.kind == 'attn'
+    inner = 3 * meta.H * meta.D if attn else meta.F
+    a2 = meta.H * meta.D if attn else meta.F
+    dev = x.device
+    out = torch.empty_like(x)
+    ws16 = torch.empty(M * (C + inner + a2), device=dev, dtype=torch.bfloat16)
+    ws32 = torch.empty(2 * M + (B * meta.H * N if attn else 0), device=dev, dtype=torch.float32)
+    d, _ = _half_desc(meta, x, out, params, ws16, ws32)
+    ops._ck(_lib.lib().vsx_half_block_fwd(_C.byref(d), ops._stream()))
+    return out, (ws16, ws32)
+
+
+def native_half_backward(meta, g_out, saved, x, params):
+    ws16, ws32 = saved
+    B, N, C = x.shape
+    M = B * N
+    attn = meta.kind == 'attn'
+    inner = 3 * meta.H * meta.D if attn else meta.F
+    a2 = meta.H * meta.D if attn else 0
+    dev = x.device
+    g_in = torch.empty_like(x)
+    sc = torch.empty(M * (2 * C + inner + a2), device=dev, dtype=torch.bfloat16)      # [df | dxn | d_act1 | d_act2]
+    grads = zeros_like_many(*params)
+    fd, _ = _half_desc(meta, x, None, params, ws16, ws32)
+    ps = sc.data_ptr()
+    d = _lib.HalfBlockGrad(fd, g_out.data_ptr(), g_in.data_ptr(), ps, ps + 2 * M * C, ps + 4 * M * C, (ps + 2 * M * (2 * C + inner)) if attn else None,
+                           *[t.data_ptr() for t in grads])
+    ops._ck(_lib.lib().vsx_half_block_bwd(_C.byref(d), ops._stream()))
+    return g_in, tuple(grads)
+
+
 class HalfBlockFn(torch.autograd.Function):
     """x_out = x + mask * drop_path(branch(LN(x)))  for one half of a Block (nets/supernet_blocks.py:213-253)."""
 
@@ -467,16 +539,24 @@ class HalfBlockFn(torch.autograd.Function):
         require_cuda(x, 'Block')
         if not x.is_contiguous():
             x = x.contiguous()
-        fwd = attn_half_forward if meta.kind == 'attn' else mlp_half_forward
-        out, saved = fwd(meta, x, *params)
-        ctx.meta, ctx.saved = meta, saved
+        native = USE_NATIVE_HALF and _precision == 'bf16' and ops.PROFILE is None and all(p is not None for p in params)
+        if native:
+            out, saved = native_half_forward(meta, x, params)
+        else:
+            fwd = attn_half_forward if meta.kind == 'attn' else mlp_half_forward
+            out, saved = fwd(meta, x, *params)
+        ctx.meta, ctx.saved, ctx.native = meta, saved, native
         ctx.save_for_backward(x, *params)
         return out
 
     @staticmethod
     def backward(ctx, g):
         x, *params = ctx.saved_tensors
-        bwd = attn_half_backward if ctx.meta.kind == 'attn' else mlp_half_backward
-        g_in, pg = bwd(ctx.meta, g if g.is_contiguous() else g.contiguous(), ctx.saved, x, *params)
+        g = g if g.is_contiguous() else g.contiguous()
+        if ctx.native:
+            g_in, pg = native_half_backward(ctx.meta, g, ctx.saved, x, params)
+        else:
+            bwd = attn_half_backward if ctx.meta.kind == 'attn' else mlp_half_backward
+            g_in, pg = bwd(ctx.meta, g, ctx.saved, x, *params)
         ctx.saved = None
         return (None, g_in) + tuple(pg)

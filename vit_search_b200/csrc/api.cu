@@ -16,7 +16,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static long g_launches = 0;     // kernels launched through the library (every launcher ends in check_launch)
+
 int check_launch(const char* what) {
+  __atomic_fetch_add(&g_launches, 1L, __ATOMIC_RELAXED);     // forward and autograd threads both launch
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -111,6 +114,7 @@ int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows,
 }  // namespace vsx
 
 extern "C" const char* vsx_last_error(void) { return vsx::g_err; }
+extern "C" long vsx_launch_count(void) { return vsx::g_launches; }
 extern "C" int vsx_abi_version(void) { return VSX_ABI_VERSION; }
 extern "C" int vsx_device_ok(int dev) {
   int major = 0, count = 0;
