@@ -108,6 +108,9 @@ typedef struct vsx_gemm_desc {
   int n_keep;             /* RESIDUAL: columns < n_keep receive the branch                                    */
   int split_k;            /* ATOMIC: number of reduction splits (>= 1)                                        */
   float* colsum;          /* GELUGRAD (or STORE without bias): colsum[n] += sum_m out[m,n] (bias gradient), or NULL  */
+  int k_segments;         /* 0 / 1: the reduction runs over [0, K).  s > 1: over s windows [j*k_seg_stride, j*k_seg_stride + k_seg_len),  */
+  int k_seg_len;          /* j < s, all inside [0, K) -- the kept heads of a (3, heads, head_dim)-ordered qkv gradient: masked heads   */
+  int k_seg_stride;       /* are skipped instead of multiplied as zeros.  Windows are walked in 64-element steps.                      */
 } vsx_gemm_desc;
 
 int vsx_gemm(const vsx_gemm_desc* d, void* stream);

@@ -21,7 +21,8 @@ class GemmDesc(C.Structure):
     _fields_ = [('a', _p * 6), ('b', _p * 6), ('terms', _i), ('lda', _l), ('ldb', _l), ('a_layout', _i), ('b_layout', _i),
                 ('M', _i), ('N', _i), ('K', _i), ('epilogue', _i), ('out_dtype', _i), ('out', _p), ('ldo', _l),
                 ('out2', _p), ('ldo2', _l), ('n_out', _i), ('bias', _p), ('aux', _p), ('ld_aux', _l),
-                ('row_scale', _p), ('rows_per_sample', _i), ('n_keep', _i), ('split_k', _i), ('colsum', _p)]
+                ('row_scale', _p), ('rows_per_sample', _i), ('n_keep', _i), ('split_k', _i), ('colsum', _p),
+                ('k_segments', _i), ('k_seg_len', _i), ('k_seg_stride', _i)]
 
 
 # name -> argtypes (restype is int unless listed in _RESTYPES); mirrors include/vsx.h one to one

@@ -357,15 +357,17 @@ def attn_half_backward(meta, g_out, saved, x, ln_w, ln_b, qkv_w, qkv_b, proj_w, 
                            dict(a_off=r0 * 3 * HD + j * HD, b_off=r0 * C, out_off=j * HD * C, a_layout=ops.MNMAJOR, b_layout=ops.MNMAJOR,
                                 split_k=split_k_for(nrow, s.ek, rows))))
         ops.gemm_grouped(wgrads)
-        # dxn[rows, ek] = dqkv[rows, 3HD] Wqkv[3HD, ek]   (masked heads are zero columns of dqkv)
+        # dxn[rows, ek] = dqkv[rows, 3HD] Wqkv[3HD, ek]: the reduction walks the three windows of kept heads only
+        # (the 64-wide k steps may overrun a window only into masked, i.e. zero, columns of dqkv)
+        kseg = dict(k_segments=3, k_seg_len=hkd, k_seg_stride=HD) if (hk < H and (hkd + 63) // 64 * 64 <= HD) else {}
         if meta.pre_norm:
             ops.gemm(a_dq, wq, 3 * HD, C, rows, s.ek, 3 * HD, ops.EPI_STORE, dxn, C, a_off=r0 * 3 * HD, out_off=r0 * C,
-                     n_out=up8(s.ek), b_layout=ops.MNMAJOR)
+                     n_out=up8(s.ek), b_layout=ops.MNMAJOR, **kseg)
             ops.masked_ln_bwd(dxn, C, x2, C, mean, rstd, ln_w, g2 if meta.residual else None, gi2, C, d_lnw, d_lnb, rows, C, s.ek,
                               dy_off=r0 * C, x_off=r0 * C, stat_off=r0, g_off=r0 * C)
         else:
             ops.gemm(a_dq, wq, 3 * HD, C, rows, s.ek, 3 * HD, ops.EPI_STORE, gi2, C, a_off=r0 * 3 * HD, out_off=r0 * C, n_out=C,
-                     b_layout=ops.MNMAJOR)
+                     b_layout=ops.MNMAJOR, **kseg)
     return g_in, (d_lnw, d_lnb, d_qw, d_qb, d_pw, d_pb)
 
 

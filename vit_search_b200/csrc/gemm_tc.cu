@@ -62,6 +62,7 @@ struct GemmArgs {
   const float* row_scale;
   float* colsum;
   int rows_per_sample, n_keep;
+  int kseg_kb, kseg_stride;   // k-blocks per reduction window and distance between windows (0: one contiguous reduction)
   long long* dbg;
 };
 
@@ -288,7 +289,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
-          const int term = i / nkb, k0 = (kb0 + i % nkb) * BK;
+          const int term = i / nkb, kbi = kb0 + i % nkb;
+          const int k0 = g.kseg_kb > 0 ? (kbi / g.kseg_kb) * g.kseg_stride + (kbi % g.kseg_kb) * BK : kbi * BK;
           const uint32_t dA = ring + s * STAGE_BYTES, dB = dA + STAGE_A, fb = full_bar(s);
           mbar_expect_tx(fb, STAGE_BYTES);
 #pragma unroll
@@ -624,6 +626,12 @@ int build_problem(const vsx_gemm_desc* d, TmapPack& maps, GemmArgs& g) {
   VSX_REQUIRE(d->ldo % (f32 ? 4 : 8) == 0, "vsx_gemm: ldo must be a multiple of %d elements (16 bytes) for the TMA store (ldo=%ld)", f32 ? 4 : 8, d->ldo);
   if (d->n_out == 0) return 1;
   g.M = d->M, g.N = d->N, g.K = d->K, g.num_kb = ceil_div(d->K, BK), g.terms = d->terms;
+  g.kseg_kb = 0, g.kseg_stride = 0;
+  if (d->k_segments > 1) {
+    VSX_REQUIRE(d->k_seg_len > 0 && d->k_seg_stride >= d->k_seg_len && (long)(d->k_segments - 1) * d->k_seg_stride + d->k_seg_len <= d->K,
+                "vsx_gemm: reduction windows must lie inside [0, K) (segments=%d len=%d stride=%d K=%d)", d->k_segments, d->k_seg_len, d->k_seg_stride, d->K);
+    g.kseg_kb = ceil_div(d->k_seg_len, BK), g.kseg_stride = d->k_seg_stride, g.num_kb = d->k_segments * g.kseg_kb;
+  }
   g.a_mn = d->a_layout == VSX_MNMAJOR, g.b_mn = d->b_layout == VSX_MNMAJOR;
   g.n_out = d->n_out, g.split_k = d->split_k < 1 ? 1 : d->split_k;
   g.bias = d->bias;

@@ -14,6 +14,7 @@ using namespace vsx;
 namespace {
 
 inline int up8(int n) { return (n + 7) / 8 * 8; }
+inline int up64(int n) { return (n + 63) / 64 * 64; }
 
 inline int split_k_for(int m_rows, int n_cols, int red_rows) {
   const int tiles = ceil_div(m_rows, 128) * ceil_div(n_cols, 128);
@@ -191,10 +192,13 @@ extern "C" int vsx_half_block_bwd(const vsx_half_block_grad* b, void* stream) {
       if (h->pre_norm) {
         Gemm g(dqkv, 3 * HD, VSX_KMAJOR, h->w1, C, VSX_MNMAJOR, rows, s.embed_keep, 3 * HD, VSX_EPI_STORE, VSX_BF16, dxn, C);
         g.d.n_out = up8(s.embed_keep);
+        // reduce over the kept heads only (the 64-wide k steps may overrun a window only into masked, i.e. zero, columns)
+        if (hk < H && up64(hkd) <= HD) g.d.k_segments = 3, g.d.k_seg_len = hkd, g.d.k_seg_stride = HD;
         HB_CHECK(vsx_gemm(&g.d, stream));
       } else {
         Gemm g(dqkv, 3 * HD, VSX_KMAJOR, h->w1, C, VSX_MNMAJOR, rows, s.embed_keep, 3 * HD, VSX_EPI_STORE, VSX_F32, b->g_in + r0 * C, C);
         g.d.n_out = C;
+        if (hk < H && up64(hkd) <= HD) g.d.k_segments = 3, g.d.k_seg_len = hkd, g.d.k_seg_stride = HD;
         HB_CHECK(vsx_gemm(&g.d, stream));
       }
     } else {

@@ -132,9 +132,8 @@ class _StemFn(torch.autograd.Function):
         acts = _ActOperands()
         g2d = g.contiguous().view(R, C)
         dtok = torch.empty(R, C, device=dev, dtype=T)
-        ops.scale_mask_cast(g2d, C, None, 1, C, dtok, C, R, C)
         d_bp = torch.zeros(C, device=dev)
-        ops.colsum(dtok, C, R, C, d_bp)
+        ops.scale_mask_cast(g2d, C, None, 1, C, dtok, C, R, C, colsum=d_bp)        # cast + conv_proj bias gradient in one pass
 
         def wgrad(dy, a_col, kdim, like):
             """dW (ohwi layout [O, kdim]) = dy^T a_col, then back to the parameter's [O, I, kh, kw] layout."""
@@ -258,9 +257,8 @@ class _PatchProjFn(torch.autograd.Function):
         T = core.act_dtype()
         acts = _ActOperands()
         dtok = torch.empty(R, C, device=g.device, dtype=T)
-        ops.scale_mask_cast(g.contiguous().view(R, C), C, None, 1, C, dtok, C, R, C)
         db = torch.zeros(C, device=g.device)
-        ops.colsum(dtok, C, R, C, db)
+        ops.scale_mask_cast(g.contiguous().view(R, C), C, None, 1, C, dtok, C, R, C, colsum=db)
         ldw = (kd + 3) // 4 * 4
         dw = torch.zeros(C, ldw, device=g.device)
         ops.gemm(acts.get(dtok, C, 0, R, C), acts.get(A, A.shape[1], 0, R, kd), C, A.shape[1], C, kd, R, ops.EPI_ATOMIC, dw, ldw,

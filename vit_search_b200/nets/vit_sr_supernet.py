@@ -287,10 +287,9 @@ class _HeadFn(torch.autograd.Function):
         x2 = x.view(B * N, C)
         gcls = gcls.contiguous()
         dc = torch.empty(B, K, device=dev, dtype=T)
-        ops.scale_mask_cast(gcls, K, None, 1, K, dc, K, B, K)
         d_cw, d_cb, d_pw, d_pb, d_lnw, d_lnb = core.zeros_like_many(cw, torch.empty(K, device='meta'), pw, torch.empty(K, device='meta'),
                                                                     ln_w, ln_w)
-        ops.colsum(dc, K, B, K, d_cb)
+        ops.scale_mask_cast(gcls, K, None, 1, K, dc, K, B, K, colsum=d_cb)           # cast + head bias gradient in one pass
         dtokf = torch.empty(B, C, device=dev, dtype=T)
         g_in = torch.zeros_like(x) if not with_patches else torch.empty_like(x)
         wcl = weights.get(cw)
@@ -298,8 +297,7 @@ class _HeadFn(torch.autograd.Function):
         if with_patches:
             R = B * (N - 1)
             dp = torch.empty(R, K, device=dev, dtype=T)
-            ops.scale_mask_cast(gpatch.contiguous().view(R, K), K, None, 1, K, dp, K, R, K)
-            ops.colsum(dp, K, R, K, d_pb)
+            ops.scale_mask_cast(gpatch.contiguous().view(R, K), K, None, 1, K, dp, K, R, K, colsum=d_pb)
             dpatchf = torch.empty(R, C, device=dev, dtype=T)
             wpa = weights.get(pw)
         for b0, b1, k in _runs(keep, B, C):

@@ -81,7 +81,8 @@ _PAIRS6 = [(0, 0), (1, 0), (0, 1), (1, 1), (2, 0), (0, 2)]
 
 def _gemm_desc(a, b, lda, ldb, M, N, K, epilogue, out, ldo, *, a_off=0, b_off=0, out_off=0, a_layout=KMAJOR,
                b_layout=KMAJOR, n_out=None, out2=None, ldo2=0, out2_off=0, bias=None, bias_off=0, aux=None, ld_aux=0,
-               aux_off=0, row_scale=None, row_scale_off=0, rows_per_sample=1, n_keep=0, split_k=1, colsum=None, colsum_off=0):
+               aux_off=0, row_scale=None, row_scale_off=0, rows_per_sample=1, n_keep=0, split_k=1, colsum=None, colsum_off=0,
+               k_segments=0, k_seg_len=0, k_seg_stride=0):
     """-> (vsx_gemm_desc, profile record).  a, b: a bf16 tensor, or tuples of 2 (3 product terms, ~2^-16) or 3 (6 terms, fp32-exact)
     bf16 parts whose sum is the fp32 operand (split-bf16 high-precision mode)."""
     if isinstance(a, (tuple, list)):
@@ -95,7 +96,8 @@ def _gemm_desc(a, b, lda, ldb, M, N, K, epilogue, out, ldo, *, a_off=0, b_off=0,
     # positional construction: one C-level initialisation instead of ~25 Python-level field stores
     d = _lib.GemmDesc(pa, pb, nterms, lda, ldb, a_layout, b_layout, M, N, K, epilogue, _DT[out.dtype], _ptr(out, out_off), ldo,
                       _ptr(out2, out2_off), ldo2, N if n_out is None else n_out, _ptr(bias, bias_off), _ptr(aux, aux_off), ld_aux,
-                      _ptr(row_scale, row_scale_off), rows_per_sample, n_keep, split_k, _ptr(colsum, colsum_off))
+                      _ptr(row_scale, row_scale_off), rows_per_sample, n_keep, split_k, _ptr(colsum, colsum_off), k_segments, k_seg_len,
+                      k_seg_stride)
     if PROFILE is None:
         return d, None
     # algorithmic HBM bytes of the launch: both operands once + the output tile(s) + the aux tile the epilogue reads
@@ -105,7 +107,8 @@ def _gemm_desc(a, b, lda, ldb, M, N, K, epilogue, out, ldo, *, a_off=0, b_off=0,
         nbytes += es * M * d.n_out
     if epilogue == EPI_ATOMIC:
         nbytes += es * M * d.n_out          # read-modify-write of the fp32 gradient tile
-    return d, (2.0 * M * N * K, (M, N, K, epilogue, a_layout, b_layout, d.n_out, split_k, nterms), nbytes)
+    keff = k_segments * k_seg_len if k_segments > 1 else K        # algorithmic reduction length
+    return d, (2.0 * M * N * keff, (M, N, keff, epilogue, a_layout, b_layout, d.n_out, split_k, nterms), nbytes)
 
 
 def gemm(*args, **kw):
