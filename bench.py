@@ -120,7 +120,7 @@ class ClockSampler:
     def __init__(self, dev):
         self.f = tempfile.NamedTemporaryFile('w+', suffix='.csv', delete=False)
         try:
-            self.p = subprocess.Popen(['nvidia-smi', '-i', str(dev), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '200'],
+            self.p = subprocess.Popen(['nvidia-smi', '-i', str(dev), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '50'],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -242,9 +242,9 @@ def run_ours(args):
         h_loss.copy_(loss, non_blocking=True)
 
     n_warm = max(args.warmup, 3 if world == 1 else 8)   # DDP rebuilds its buckets after the first backward and the caching
+    clocks = ClockSampler(local) if rank == 0 else None   # started before the warm-up: nvidia-smi needs ~0.2 s to deliver its first sample
     for _ in range(n_warm):                              # allocator needs a few steps to settle: extra untimed steps when N > 1
         dev_step()
-    clocks = ClockSampler(local) if rank == 0 else None
     ops.LAUNCHES = 0
     launches0 = _lib.lib().vsx_launch_count()
     ms = timed(dev_step, args.steps)
