@@ -78,3 +78,46 @@ def test_block_parity(ci, prec):
         errs[k] = rel(prm.grad, p['b.' + k].grad)
     bad = {k: v for k, v in errs.items() if not v < tol}
     assert not bad, (prec, bad, errs)
+
+
+@pytest.mark.parametrize('prec', ['fp32', 'bf16', 'bf16_python'])
+def test_standalone_mlp_and_attention_modules(prec):
+    """Mlp.forward / Attention.forward used on their own (reference nets/supernet_blocks.py:37-52, :100-120: no LayerNorm in front, no
+    residual) against plain torch fp64 math, forward and backward -- the pre_norm=False / residual=False route of the half-block calls."""
+    import torch.nn.functional as Fn
+    from vit_search_b200 import core
+    from vit_search_b200.nets import Attention, Mlp
+    B, N, C, H, D, F = 3, 65, 128, 2, 64, 256
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(B, N, C, generator=g)
+    gout = torch.randn(B, N, C, generator=g)
+    native0 = core.USE_NATIVE_HALF
+    core.USE_NATIVE_HALF = prec != 'bf16_python'
+    p = 'bf16' if prec == 'bf16_python' else prec
+    tol = 2e-5 if p == 'fp32' else 2e-2
+    try:
+        for mod in (Mlp(C, F).cuda(), Attention(C, H, D).cuda()):
+            for prm in mod.parameters():
+                with torch.no_grad():
+                    prm.copy_(torch.randn(prm.shape, generator=g) * (0.2 if prm.ndim == 2 else 0.1))
+            xd = x.cuda().requires_grad_(True)
+            with core.precision(p):
+                y = mod(xd)
+                y.backward(gout.cuda())
+            torch.cuda.synchronize()
+            w = {k: v.detach().double().cpu().requires_grad_(True) for k, v in mod.named_parameters()}
+            xo = x.double().requires_grad_(True)
+            if isinstance(mod, Mlp):
+                yo = Fn.linear(Fn.gelu(Fn.linear(xo, w['fc1.weight'], w['fc1.bias'])), w['fc2.weight'], w['fc2.bias'])
+            else:
+                qkv = Fn.linear(xo, w['qkv.weight'], w['qkv.bias']).view(B, N, 3, H, D).permute(2, 0, 3, 1, 4)
+                att = ((qkv[0] @ qkv[1].transpose(-1, -2)) * D ** -0.5).softmax(-1)
+                yo = Fn.linear((att @ qkv[2]).transpose(1, 2).reshape(B, N, H * D), w['proj.weight'], w['proj.bias'])
+            yo.backward(gout.double())
+            errs = {'y': rel(y, yo), 'gx': rel(xd.grad, xo.grad)}
+            for k, prm in mod.named_parameters():
+                errs[k] = rel(prm.grad, w[k].grad)
+            bad = {k: v for k, v in errs.items() if not v < tol}
+            assert not bad, (type(mod).__name__, prec, bad)
+    finally:
+        core.USE_NATIVE_HALF = native0

@@ -242,3 +242,27 @@ def test_model_ema_fused_into_optimizer():
     # the average really moved away from the initial weights and differs from the live model
     name = next(n for n, p in m.named_parameters() if p.ndim == 2)
     assert rel(got[name], m.state_dict()[name]) > 1e-6
+
+
+def test_device_feeder_pipeline():
+    """engine.DeviceFeeder: batches submitted from pinned host memory come out in order with the right contents while a later batch is
+    already in flight on the side stream, and a slot is not overwritten before its consumer has been released."""
+    from vit_search_b200.engine import DeviceFeeder
+    dev = torch.device('cuda', 0)
+    feeder = DeviceFeeder(dev)
+    host = [(torch.full((64, 3, 32, 32), float(i)).pin_memory(), torch.full((64, 10), float(-i)).pin_memory()) for i in range(5)]
+    feeder.submit(*host[0])
+    sums = []
+    for i in range(5):
+        if i + 1 < 5:
+            feeder.submit(*host[i + 1])
+        a, b = feeder.next()
+        # a long-ish consumer on the compute stream: the next submit must wait for release() before it reuses this slot
+        acc = a.float().sum() + b.float().sum()
+        for _ in range(20):
+            acc = acc + (a * 0).sum()
+        sums.append(acc)
+        feeder.release()
+    torch.cuda.synchronize()
+    for i, sacc in enumerate(sums):
+        assert sacc.item() == float(i) * 64 * 3 * 32 * 32 - float(i) * 64 * 10, i
