@@ -72,71 +72,107 @@ int check_desc(const vsx_half_block* h, const char* what) {
   return VSX_OK;
 }
 
+// Problems of the same epilogue collected over the segments of a half block and launched in groups of up to four: a step with
+// several sub-architectures (multi / hybrid sampling) then costs about as many GEMM launches as a single-architecture step.
+struct GemmBatch {
+  vsx_gemm_desc d[4];
+  int n = 0;
+  void* stream;
+  explicit GemmBatch(void* st) : stream(st) {}
+  int flush() {
+    if (n == 0) return VSX_OK;
+    const int rc = n == 1 ? vsx_gemm(&d[0], stream) : vsx_gemm_grouped(d, n, stream);
+    n = 0;
+    return rc;
+  }
+  int add(const vsx_gemm_desc& g) {
+    d[n++] = g;
+    return n == 4 ? flush() : VSX_OK;
+  }
+};
+
+struct SegView {
+  const vsx_segment* s;
+  long r0;
+  int nb, rows;
+};
+
 }  // namespace
 
 extern "C" int vsx_half_block_fwd(const vsx_half_block* h, void* stream) {
   HB_CHECK(check_desc(h, "vsx_half_block_fwd"));
   const int N = h->tokens, C = h->width, H = h->heads, D = h->head_dim, HD = H * D, F = h->hidden;
   const float scale = h->kind == VSX_HALF_ATTN ? 1.0f / sqrtf((float)D) : 0.f;
+  // phase 1: dropped layers pass through; LayerNorm (or the bare input mask) of every active segment
   for (int si = 0; si < h->num_segments; ++si) {
     const vsx_segment& s = h->segments[si];
     const long r0 = (long)s.b0 * N;
-    const int nb = s.b1 - s.b0, rows = nb * N;
+    const int rows = (s.b1 - s.b0) * N;
     if (rows <= 0) continue;
     if (!s.active) {
       HB_CHECK(passthrough(h->x + r0 * C, h->out + r0 * C, (long)rows * C, h->residual != 0, stream));
       continue;
     }
     HB_CHECK(pre_norm_or_cast(h, s, r0, rows, stream));
-    const bf16* xn = B16(h->xn) + r0 * C;
-    if (h->kind == VSX_HALF_ATTN) {
-      const int hk = s.inner_keep / D, hkd = hk * D;
-      bf16* qkv = B16(h->act1) + r0 * 3 * HD;
-      bf16* o = B16(h->act2) + r0 * HD;
-      if (hk == H) {
-        Gemm g(xn, C, VSX_KMAJOR, h->w1, C, VSX_KMAJOR, rows, 3 * HD, s.embed_keep, VSX_EPI_STORE, VSX_BF16, qkv, 3 * HD);
-        g.d.bias = h->b1;
-        HB_CHECK(vsx_gemm(&g.d, stream));
-      } else {
-        // q / k / v row blocks of the kept heads only (features ordered (3,H,D)): three problems, one launch
-        vsx_gemm_desc ds[3];
-        for (int j = 0; j < 3; ++j) {
-          Gemm g(xn, C, VSX_KMAJOR, B16(h->w1) + (long)j * HD * C, C, VSX_KMAJOR, rows, hkd, s.embed_keep, VSX_EPI_STORE, VSX_BF16, qkv + j * HD, 3 * HD);
-          g.d.bias = h->b1 != nullptr ? h->b1 + j * HD : nullptr;
-          ds[j] = g.d;
-        }
-        HB_CHECK(vsx_gemm_grouped(ds, 3, stream));
-      }
-      HB_CHECK(vsx_attn_fwd(qkv, o, h->lse + (long)s.b0 * H * N, VSX_BF16, nb, N, H, D, hk, scale, VSX_ATTN_IMPL_AUTO, stream));
-      if (h->residual) {
-        Gemm g(o, HD, VSX_KMAJOR, h->w2, HD, VSX_KMAJOR, rows, s.out_keep, hkd, VSX_EPI_RESIDUAL, VSX_F32, h->out + r0 * C, C);
-        g.d.n_out = C, g.d.bias = h->b2, g.d.aux = h->x + r0 * C, g.d.ld_aux = C;
-        g.d.row_scale = h->row_scale != nullptr ? h->row_scale + h->scale_off + s.b0 : nullptr, g.d.rows_per_sample = N, g.d.n_keep = s.out_keep;
-        HB_CHECK(vsx_gemm(&g.d, stream));
-      } else {
-        Gemm g(o, HD, VSX_KMAJOR, h->w2, HD, VSX_KMAJOR, rows, C, hkd, VSX_EPI_STORE, VSX_F32, h->out + r0 * C, C);
-        g.d.bias = h->b2;
-        HB_CHECK(vsx_gemm(&g.d, stream));
-      }
-    } else {
-      bf16* u = B16(h->act1) + r0 * F;
-      bf16* hh = B16(h->act2) + r0 * F;
-      {
-        Gemm g(xn, C, VSX_KMAJOR, h->w1, C, VSX_KMAJOR, rows, s.inner_keep, s.embed_keep, VSX_EPI_GELU, VSX_BF16, u, F);
-        g.d.n_out = up8(s.inner_keep), g.d.out2 = hh, g.d.ldo2 = F, g.d.bias = h->b1;
-        HB_CHECK(vsx_gemm(&g.d, stream));
-      }
-      if (h->residual) {
-        Gemm g(hh, F, VSX_KMAJOR, h->w2, F, VSX_KMAJOR, rows, s.out_keep, s.inner_keep, VSX_EPI_RESIDUAL, VSX_F32, h->out + r0 * C, C);
-        g.d.n_out = C, g.d.bias = h->b2, g.d.aux = h->x + r0 * C, g.d.ld_aux = C;
-        g.d.row_scale = h->row_scale != nullptr ? h->row_scale + h->scale_off + s.b0 : nullptr, g.d.rows_per_sample = N, g.d.n_keep = s.out_keep;
-        HB_CHECK(vsx_gemm(&g.d, stream));
-      } else {
-        Gemm g(hh, F, VSX_KMAJOR, h->w2, F, VSX_KMAJOR, rows, C, s.inner_keep, VSX_EPI_STORE, VSX_F32, h->out + r0 * C, C);
-        g.d.bias = h->b2;
-        HB_CHECK(vsx_gemm(&g.d, stream));
-      }
+  }
+  auto for_active = [&](auto&& fn) -> int {
+    for (int si = 0; si < h->num_segments; ++si) {
+      const vsx_segment& s = h->segments[si];
+      SegView v{&s, (long)s.b0 * N, s.b1 - s.b0, (s.b1 - s.b0) * N};
+      if (v.rows <= 0 || !s.active) continue;
+      HB_CHECK(fn(v));
     }
+    return VSX_OK;
+  };
+  GemmBatch batch(stream);
+  auto out_gemm = [&](const SegView& v, const bf16* a, long lda, int kdim) {   // proj / fc2 with the residual tail (or a plain store)
+    const vsx_segment& s = *v.s;
+    if (h->residual) {
+      Gemm g(a, lda, VSX_KMAJOR, h->w2, lda, VSX_KMAJOR, v.rows, s.out_keep, kdim, VSX_EPI_RESIDUAL, VSX_F32, h->out + v.r0 * C, C);
+      g.d.n_out = C, g.d.bias = h->b2, g.d.aux = h->x + v.r0 * C, g.d.ld_aux = C;
+      g.d.row_scale = h->row_scale != nullptr ? h->row_scale + h->scale_off + s.b0 : nullptr, g.d.rows_per_sample = N, g.d.n_keep = s.out_keep;
+      return batch.add(g.d);
+    }
+    Gemm g(a, lda, VSX_KMAJOR, h->w2, lda, VSX_KMAJOR, v.rows, C, kdim, VSX_EPI_STORE, VSX_F32, h->out + v.r0 * C, C);
+    g.d.bias = h->b2;
+    return batch.add(g.d);
+  };
+  if (h->kind == VSX_HALF_ATTN) {
+    // phase 2: qkv projections -- one problem per segment, or the q / k / v row blocks of the kept heads (features ordered (3,H,D))
+    HB_CHECK(for_active([&](const SegView& v) -> int {
+      const vsx_segment& s = *v.s;
+      const int hk = s.inner_keep / D, hkd = hk * D;
+      const bf16* xn = B16(h->xn) + v.r0 * C;
+      bf16* qkv = B16(h->act1) + v.r0 * 3 * HD;
+      const int parts = hk == H ? 1 : 3;
+      for (int j = 0; j < parts; ++j) {
+        Gemm g(xn, C, VSX_KMAJOR, B16(h->w1) + (long)j * HD * C, C, VSX_KMAJOR, v.rows, hk == H ? 3 * HD : hkd, s.embed_keep, VSX_EPI_STORE, VSX_BF16,
+               qkv + j * HD, 3 * HD);
+        g.d.bias = h->b1 != nullptr ? h->b1 + j * HD : nullptr;
+        HB_CHECK(batch.add(g.d));
+      }
+      return VSX_OK;
+    }));
+    HB_CHECK(batch.flush());
+    // phase 3: attention core per segment (heads_keep differs)
+    HB_CHECK(for_active([&](const SegView& v) -> int {
+      return vsx_attn_fwd(B16(h->act1) + v.r0 * 3 * HD, B16(h->act2) + v.r0 * HD, h->lse + (long)v.s->b0 * H * N, VSX_BF16, v.nb, N, H, D,
+                          v.s->inner_keep / D, scale, VSX_ATTN_IMPL_AUTO, stream);
+    }));
+    // phase 4: output projections
+    HB_CHECK(for_active([&](const SegView& v) -> int { return out_gemm(v, B16(h->act2) + v.r0 * HD, HD, (v.s->inner_keep / D) * D); }));
+    HB_CHECK(batch.flush());
+  } else {
+    HB_CHECK(for_active([&](const SegView& v) -> int {
+      const vsx_segment& s = *v.s;
+      Gemm g(B16(h->xn) + v.r0 * C, C, VSX_KMAJOR, h->w1, C, VSX_KMAJOR, v.rows, s.inner_keep, s.embed_keep, VSX_EPI_GELU, VSX_BF16,
+             B16(h->act1) + v.r0 * F, F);
+      g.d.n_out = up8(s.inner_keep), g.d.out2 = B16(h->act2) + v.r0 * F, g.d.ldo2 = F, g.d.bias = h->b1;
+      return batch.add(g.d);
+    }));
+    HB_CHECK(batch.flush());
+    HB_CHECK(for_active([&](const SegView& v) -> int { return out_gemm(v, B16(h->act2) + v.r0 * F, F, v.s->inner_keep); }));
+    HB_CHECK(batch.flush());
   }
   return VSX_OK;
 }
@@ -147,94 +183,111 @@ extern "C" int vsx_half_block_bwd(const vsx_half_block_grad* b, void* stream) {
   HB_CHECK(check_desc(h, "vsx_half_block_bwd"));
   const int N = h->tokens, C = h->width, H = h->heads, D = h->head_dim, HD = H * D, F = h->hidden;
   const float scale = h->kind == VSX_HALF_ATTN ? 1.0f / sqrtf((float)D) : 0.f;
+  // phase 1: dropped layers pass the gradient through; gradient of the branch output of every active segment: drop-path scale,
+  // output mask, cast -- its column sums are the bias gradient of proj / fc2
   for (int si = 0; si < h->num_segments; ++si) {
     const vsx_segment& s = h->segments[si];
     const long r0 = (long)s.b0 * N;
-    const int nb = s.b1 - s.b0, rows = nb * N;
+    const int rows = (s.b1 - s.b0) * N;
     if (rows <= 0) continue;
     if (!s.active) {
       HB_CHECK(passthrough(b->g_out + r0 * C, b->g_in + r0 * C, (long)rows * C, h->residual != 0, stream));
       continue;
     }
     const int ck = h->residual ? s.out_keep : C;
-    bf16* df = B16(b->df) + r0 * C;
-    const bf16* xn = B16(h->xn) + r0 * C;
-    bf16* dxn = B16(b->dxn) + r0 * C;
-    // gradient of the branch output: drop-path scale, output mask, cast; its column sums are the bias gradient of proj / fc2
     HB_CHECK(vsx_scale_mask_cast(b->g_out + r0 * C, C, (h->residual && h->row_scale != nullptr) ? h->row_scale + h->scale_off + s.b0 : nullptr, N, ck,
-                                 df, VSX_BF16, C, rows, C, b->d_b2, stream));
-    vsx_gemm_desc wg[4];
-    int nwg = 0;
-    if (h->kind == VSX_HALF_ATTN) {
-      const int hk = s.inner_keep / D, hkd = hk * D;
-      const bf16* qkv = B16(h->act1) + r0 * 3 * HD;
-      const bf16* o = B16(h->act2) + r0 * HD;
-      bf16* d_o = B16(b->d_act2) + r0 * HD;
-      bf16* dqkv = B16(b->d_act1) + r0 * 3 * HD;
-      {  // dWproj[ck, hkd] += df^T o
-        Gemm g(df, C, VSX_MNMAJOR, o, HD, VSX_MNMAJOR, ck, hkd, rows, VSX_EPI_ATOMIC, VSX_F32, b->d_w2, HD);
-        g.d.split_k = split_k_for(ck, hkd, rows);
-        wg[nwg++] = g.d;
-      }
-      {  // d_o[rows, hkd] = df[rows, ck] Wproj[ck, hkd]
-        Gemm g(df, C, VSX_KMAJOR, h->w2, HD, VSX_MNMAJOR, rows, hkd, ck, VSX_EPI_STORE, VSX_BF16, d_o, HD);
-        HB_CHECK(vsx_gemm(&g.d, stream));
-      }
-      HB_CHECK(vsx_attn_bwd(qkv, o, d_o, h->lse + (long)s.b0 * H * N, dqkv, VSX_BF16, nb, N, H, D, hk, scale, VSX_ATTN_IMPL_AUTO, b->d_b1, stream));
-      const int parts = hk < H ? 3 : 1, nrow = hk < H ? hkd : 3 * HD;
-      for (int j = 0; j < parts; ++j) {   // dWqkv[j] += dqkv_j^T xn
-        Gemm g(dqkv + j * HD, 3 * HD, VSX_MNMAJOR, xn, C, VSX_MNMAJOR, nrow, s.embed_keep, rows, VSX_EPI_ATOMIC, VSX_F32, b->d_w1 + (long)j * HD * C, C);
-        g.d.split_k = split_k_for(nrow, s.embed_keep, rows);
-        wg[nwg++] = g.d;
-      }
-      HB_CHECK(vsx_gemm_grouped(wg, nwg, stream));
-      // dxn[rows, ek] = dqkv[rows, 3HD] Wqkv[3HD, ek]   (masked heads are zero columns of dqkv)
-      if (h->pre_norm) {
-        Gemm g(dqkv, 3 * HD, VSX_KMAJOR, h->w1, C, VSX_MNMAJOR, rows, s.embed_keep, 3 * HD, VSX_EPI_STORE, VSX_BF16, dxn, C);
-        g.d.n_out = up8(s.embed_keep);
-        // reduce over the kept heads only (the 64-wide k steps may overrun a window only into masked, i.e. zero, columns)
-        if (hk < H && up64(hkd) <= HD) g.d.k_segments = 3, g.d.k_seg_len = hkd, g.d.k_seg_stride = HD;
-        HB_CHECK(vsx_gemm(&g.d, stream));
-      } else {
-        Gemm g(dqkv, 3 * HD, VSX_KMAJOR, h->w1, C, VSX_MNMAJOR, rows, s.embed_keep, 3 * HD, VSX_EPI_STORE, VSX_F32, b->g_in + r0 * C, C);
-        g.d.n_out = C;
-        if (hk < H && up64(hkd) <= HD) g.d.k_segments = 3, g.d.k_seg_len = hkd, g.d.k_seg_stride = HD;
-        HB_CHECK(vsx_gemm(&g.d, stream));
-      }
-    } else {
-      const bf16* u = B16(h->act1) + r0 * F;
-      const bf16* hh = B16(h->act2) + r0 * F;
-      bf16* du = B16(b->d_act1) + r0 * F;
-      {  // dW2[ck, ik] += df^T h
-        Gemm g(df, C, VSX_MNMAJOR, hh, F, VSX_MNMAJOR, ck, s.inner_keep, rows, VSX_EPI_ATOMIC, VSX_F32, b->d_w2, F);
-        g.d.split_k = split_k_for(ck, s.inner_keep, rows);
-        wg[nwg++] = g.d;
-      }
-      {  // du[rows, ik] = (df[rows, ck] W2[ck, ik]) * gelu'(u); its column sums are the fc1 bias gradient
-        Gemm g(df, C, VSX_KMAJOR, h->w2, F, VSX_MNMAJOR, rows, s.inner_keep, ck, VSX_EPI_GELUGRAD, VSX_BF16, du, F);
-        g.d.n_out = up8(s.inner_keep), g.d.aux = u, g.d.ld_aux = F, g.d.colsum = b->d_b1;
-        HB_CHECK(vsx_gemm(&g.d, stream));
-      }
-      {  // dW1[ik, ek] += du^T xn
-        Gemm g(du, F, VSX_MNMAJOR, xn, C, VSX_MNMAJOR, s.inner_keep, s.embed_keep, rows, VSX_EPI_ATOMIC, VSX_F32, b->d_w1, C);
-        g.d.split_k = split_k_for(s.inner_keep, s.embed_keep, rows);
-        wg[nwg++] = g.d;
-      }
-      HB_CHECK(vsx_gemm_grouped(wg, nwg, stream));
-      // dxn[rows, ek] = du[rows, ik] W1[ik, ek]
-      if (h->pre_norm) {
-        Gemm g(du, F, VSX_KMAJOR, h->w1, C, VSX_MNMAJOR, rows, s.embed_keep, s.inner_keep, VSX_EPI_STORE, VSX_BF16, dxn, C);
-        g.d.n_out = up8(s.embed_keep);
-        HB_CHECK(vsx_gemm(&g.d, stream));
-      } else {
-        Gemm g(du, F, VSX_KMAJOR, h->w1, C, VSX_MNMAJOR, rows, s.embed_keep, s.inner_keep, VSX_EPI_STORE, VSX_F32, b->g_in + r0 * C, C);
-        g.d.n_out = C;
-        HB_CHECK(vsx_gemm(&g.d, stream));
-      }
+                                 B16(b->df) + r0 * C, VSX_BF16, C, rows, C, b->d_b2, stream));
+  }
+  auto for_active = [&](auto&& fn) -> int {
+    for (int si = 0; si < h->num_segments; ++si) {
+      const vsx_segment& s = h->segments[si];
+      SegView v{&s, (long)s.b0 * N, s.b1 - s.b0, (s.b1 - s.b0) * N};
+      if (v.rows <= 0 || !s.active) continue;
+      HB_CHECK(fn(v));
     }
-    if (h->pre_norm)
-      HB_CHECK(vsx_masked_ln_bwd(dxn, nullptr, VSX_BF16, C, h->x + r0 * C, C, h->mean + r0, h->rstd + r0, h->ln_w, h->residual ? b->g_out + r0 * C : nullptr,
-                                 b->g_in + r0 * C, C, b->d_ln_w, b->d_ln_b, rows, C, s.embed_keep, 0, 0, stream));
+    return VSX_OK;
+  };
+  GemmBatch batch(stream);
+  auto dxn_gemm = [&](const SegView& v, const bf16* a, long lda, int kdim, int hk) {     // gradient w.r.t. the (normalised) branch input
+    const vsx_segment& s = *v.s;
+    const int odt = h->pre_norm ? VSX_BF16 : VSX_F32;
+    void* out = h->pre_norm ? static_cast<void*>(B16(b->dxn) + v.r0 * C) : static_cast<void*>(b->g_in + v.r0 * C);
+    Gemm g(a, lda, VSX_KMAJOR, h->w1, C, VSX_MNMAJOR, v.rows, s.embed_keep, kdim, VSX_EPI_STORE, odt, out, C);
+    g.d.n_out = h->pre_norm ? up8(s.embed_keep) : C;
+    // attention: reduce over the kept-head windows only (the 64-wide k steps may overrun a window only into masked, i.e. zero, columns)
+    if (hk >= 0 && hk < H && up64(hk * D) <= HD) g.d.k_segments = 3, g.d.k_seg_len = hk * D, g.d.k_seg_stride = HD;
+    return batch.add(g.d);
+  };
+  if (h->kind == VSX_HALF_ATTN) {
+    // phase 2: d_o[rows, hkd] = df[rows, ck] Wproj[ck, hkd]
+    HB_CHECK(for_active([&](const SegView& v) -> int {
+      const int ck = h->residual ? v.s->out_keep : C, hkd = (v.s->inner_keep / D) * D;
+      Gemm g(B16(b->df) + v.r0 * C, C, VSX_KMAJOR, h->w2, HD, VSX_MNMAJOR, v.rows, hkd, ck, VSX_EPI_STORE, VSX_BF16, B16(b->d_act2) + v.r0 * HD, HD);
+      return batch.add(g.d);
+    }));
+    HB_CHECK(batch.flush());
+    // phase 3: attention backward per segment (also accumulates the qkv bias gradient)
+    HB_CHECK(for_active([&](const SegView& v) -> int {
+      return vsx_attn_bwd(B16(h->act1) + v.r0 * 3 * HD, B16(h->act2) + v.r0 * HD, B16(b->d_act2) + v.r0 * HD, h->lse + (long)v.s->b0 * H * N,
+                          B16(b->d_act1) + v.r0 * 3 * HD, VSX_BF16, v.nb, N, H, D, v.s->inner_keep / D, scale, VSX_ATTN_IMPL_AUTO, b->d_b1, stream);
+    }));
+    // phase 4: weight gradients: dWproj[ck, hkd] += df^T o and dWqkv[j] += dqkv_j^T xn
+    HB_CHECK(for_active([&](const SegView& v) -> int {
+      const vsx_segment& s = *v.s;
+      const int ck = h->residual ? s.out_keep : C, hk = s.inner_keep / D, hkd = hk * D;
+      {
+        Gemm g(B16(b->df) + v.r0 * C, C, VSX_MNMAJOR, B16(h->act2) + v.r0 * HD, HD, VSX_MNMAJOR, ck, hkd, v.rows, VSX_EPI_ATOMIC, VSX_F32, b->d_w2, HD);
+        g.d.split_k = split_k_for(ck, hkd, v.rows);
+        HB_CHECK(batch.add(g.d));
+      }
+      const int parts = hk < H ? 3 : 1, nrow = hk < H ? hkd : 3 * HD;
+      for (int j = 0; j < parts; ++j) {
+        Gemm g(B16(b->d_act1) + v.r0 * 3 * HD + j * HD, 3 * HD, VSX_MNMAJOR, B16(h->xn) + v.r0 * C, C, VSX_MNMAJOR, nrow, s.embed_keep, v.rows,
+               VSX_EPI_ATOMIC, VSX_F32, b->d_w1 + (long)j * HD * C, C);
+        g.d.split_k = split_k_for(nrow, s.embed_keep, v.rows);
+        HB_CHECK(batch.add(g.d));
+      }
+      return VSX_OK;
+    }));
+    HB_CHECK(batch.flush());
+    // phase 5: dxn[rows, ek] = dqkv[rows, 3HD] Wqkv[3HD, ek]
+    HB_CHECK(for_active([&](const SegView& v) -> int { return dxn_gemm(v, B16(b->d_act1) + v.r0 * 3 * HD, 3 * HD, 3 * HD, v.s->inner_keep / D); }));
+    HB_CHECK(batch.flush());
+  } else {
+    // phase 2: du[rows, ik] = (df[rows, ck] W2[ck, ik]) * gelu'(u); its column sums are the fc1 bias gradient.  One launch per
+    // segment: the per-CTA shared-memory accumulation of those sums only exists for single-problem launches
+    HB_CHECK(for_active([&](const SegView& v) -> int {
+      const vsx_segment& s = *v.s;
+      const int ck = h->residual ? s.out_keep : C;
+      Gemm g(B16(b->df) + v.r0 * C, C, VSX_KMAJOR, h->w2, F, VSX_MNMAJOR, v.rows, s.inner_keep, ck, VSX_EPI_GELUGRAD, VSX_BF16, B16(b->d_act1) + v.r0 * F, F);
+      g.d.n_out = up8(s.inner_keep), g.d.aux = B16(h->act1) + v.r0 * F, g.d.ld_aux = F, g.d.colsum = b->d_b1;
+      return vsx_gemm(&g.d, stream);
+    }));
+    // phase 3: weight gradients: dW2[ck, ik] += df^T h and dW1[ik, ek] += du^T xn
+    HB_CHECK(for_active([&](const SegView& v) -> int {
+      const vsx_segment& s = *v.s;
+      const int ck = h->residual ? s.out_keep : C;
+      {
+        Gemm g(B16(b->df) + v.r0 * C, C, VSX_MNMAJOR, B16(h->act2) + v.r0 * F, F, VSX_MNMAJOR, ck, s.inner_keep, v.rows, VSX_EPI_ATOMIC, VSX_F32, b->d_w2, F);
+        g.d.split_k = split_k_for(ck, s.inner_keep, v.rows);
+        HB_CHECK(batch.add(g.d));
+      }
+      Gemm g(B16(b->d_act1) + v.r0 * F, F, VSX_MNMAJOR, B16(h->xn) + v.r0 * C, C, VSX_MNMAJOR, s.inner_keep, s.embed_keep, v.rows, VSX_EPI_ATOMIC, VSX_F32,
+             b->d_w1, C);
+      g.d.split_k = split_k_for(s.inner_keep, s.embed_keep, v.rows);
+      return batch.add(g.d);
+    }));
+    HB_CHECK(batch.flush());
+    // phase 4: dxn[rows, ek] = du[rows, ik] W1[ik, ek]
+    HB_CHECK(for_active([&](const SegView& v) -> int { return dxn_gemm(v, B16(b->d_act1) + v.r0 * F, F, v.s->inner_keep, -1); }));
+    HB_CHECK(batch.flush());
+  }
+  if (h->pre_norm) {
+    HB_CHECK(for_active([&](const SegView& v) -> int {
+      return vsx_masked_ln_bwd(B16(b->dxn) + v.r0 * C, nullptr, VSX_BF16, C, h->x + v.r0 * C, C, h->mean + v.r0, h->rstd + v.r0, h->ln_w,
+                               h->residual ? b->g_out + v.r0 * C : nullptr, b->g_in + v.r0 * C, C, b->d_ln_w, b->d_ln_b, v.rows, C, v.s->embed_keep, 0, 0,
+                               stream);
+    }));
   }
   return VSX_OK;
 }
