@@ -126,6 +126,72 @@ __device__ __forceinline__ float gelu_grad_fast(float x) {
   const float q = half_erfc_abs(x, e);
   return (x >= 0.f ? 1.0f - q : q) + x * 0.39894228040143268f * e;
 }
+// ---- packed fp32x2 versions (Blackwell FFMA2 / FMUL2 / FADD2: two fp32 lanes per issued instruction).  The GELU / GELU' epilogues
+// of the K <= 256 GEMMs are bound by CUDA-core instruction issue, so halving the FMA-pipe instruction count is a direct win; the two
+// SFU operations per element (rcp, ex2) stay scalar.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// (cdf(x0), cdf(x1)) of the standard normal and e = exp(-x^2/2) for a pair, same A-S 7.1.26 evaluation as half_erfc_abs
+__device__ __forceinline__ f32x2 normal_cdf2(float x0, float x1, f32x2& e2) {
+  const f32x2 x = pk2(x0, x1), ax = pk2(fabsf(x0), fabsf(x1));
+  const f32x2 d = fma2(pk2(0.3275911f * 0.70710678118654752f, 0.3275911f * 0.70710678118654752f), ax, pk2(1.0f, 1.0f));
+  float d0, d1;
+  unpk2(d, d0, d1);
+  const f32x2 t = pk2(rcp_approx(d0), rcp_approx(d1));
+  const f32x2 zz = mul2(mul2(x, x), pk2(-0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f));
+  float z0, z1;
+  unpk2(zz, z0, z1);
+  e2 = pk2(ex2_approx(z0), ex2_approx(z1));
+  f32x2 p = fma2(t, pk2(1.061405429f * 0.5f, 1.061405429f * 0.5f), pk2(-1.453152027f * 0.5f, -1.453152027f * 0.5f));
+  p = fma2(t, p, pk2(1.421413741f * 0.5f, 1.421413741f * 0.5f));
+  p = fma2(t, p, pk2(-0.284496736f * 0.5f, -0.284496736f * 0.5f));
+  p = fma2(t, p, pk2(0.254829592f * 0.5f, 0.254829592f * 0.5f));
+  const f32x2 q = mul2(mul2(p, t), e2);                 // 0.5 * erfc(|x| / sqrt 2)
+  // cdf = 0.5 + copysign(0.5 - q, x)
+  float h0, h1;
+  unpk2(add2(pk2(0.5f, 0.5f), mul2(q, pk2(-1.0f, -1.0f))), h0, h1);
+  return add2(pk2(0.5f, 0.5f), pk2(copysignf(h0, x0), copysignf(h1, x1)));
+}
+// in place on 32 values: v = gelu(v)   /   v = v * gelu'(u)
+__device__ __forceinline__ void gelu_fast32(float (&v)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    f32x2 e2;
+    const f32x2 cdf = normal_cdf2(v[j], v[j + 1], e2);
+    unpk2(mul2(pk2(v[j], v[j + 1]), cdf), v[j], v[j + 1]);
+  }
+}
+__device__ __forceinline__ void gelu_grad_fast32(float (&v)[32], const float (&u)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    f32x2 e2;
+    const f32x2 cdf = normal_cdf2(u[j], u[j + 1], e2);
+    const f32x2 uu = pk2(u[j], u[j + 1]);
+    const f32x2 gp = fma2(mul2(uu, pk2(0.39894228040143268f, 0.39894228040143268f)), e2, cdf);      // cdf + u * pdf
+    unpk2(mul2(pk2(v[j], v[j + 1]), gp), v[j], v[j + 1]);
+  }
+}
+
 template <typename OutT> __device__ __forceinline__ float gelu_sel(float x) { return gelu_fast(x); }
 template <> __device__ __forceinline__ float gelu_sel<float>(float x) { return gelu_f(x); }
 template <typename OutT> __device__ __forceinline__ float gelu_grad_sel(float x) { return gelu_grad_fast(x); }

@@ -497,8 +497,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] + bs[c + jj] : 0.f;
             }
             stage_write32<OutT>(tile, row, c, v);
+            if (sizeof(OutT) == 2) {
+              gelu_fast32(v);                                                 // bf16 training path: packed fp32x2 math
+            } else {
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) v[jj] = gelu_sel<OutT>(v[jj]);   // gelu(0) = 0 keeps the zero fill
+              for (int jj = 0; jj < 32; ++jj) v[jj] = gelu_sel<OutT>(v[jj]);   // gelu(0) = 0 keeps the zero fill
+            }
             stage_write32<OutT>(tile2, row, c, v);
           } else if (EPI == VSX_EPI_RESIDUAL) {
             float r[32];
@@ -514,8 +518,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
           } else if (EPI == VSX_EPI_GELUGRAD) {
             float u[32];
             stage_read32<OutT>(tile, row, c, u);
+            if (sizeof(OutT) == 2) {
+              gelu_grad_fast32(v, u);                                                // computed for every column, masked below
+            } else {
 #pragma unroll
-            for (int jj = 0; jj < 32; ++jj) v[jj] *= gelu_grad_sel<OutT>(u[jj]);     // computed for every column, masked below
+              for (int jj = 0; jj < 32; ++jj) v[jj] *= gelu_grad_sel<OutT>(u[jj]);
+            }
             if (!full) {
 #pragma unroll
               for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] : 0.f;
