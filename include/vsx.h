@@ -271,6 +271,18 @@ int vsx_sr_combine_bwd(const float* gy, void* dconv, void* dtok, int dtype, floa
                        int C1, int C2, int keep2, void* stream);
 
 /* ----------------------------------------------------------------------------------------------------
+ * SwitchTokenMix (token_mixup.py:101-162; call site engine.py:109-110): batch augmentation in front of the train step.
+ * Samples [batch, channels, height, width] fp32 -> `out` (a different buffer); hard labels (int64) -> targets [batch, num_classes] and
+ * patch_targets [batch, patch_len^2, num_classes].  First batch/2 samples: the patch box [box_y0, box_y1) x [box_x0, box_x1) is pasted
+ * from sample perm_patch[b] (and the per-patch targets with it), target = y*lam_patch + y[perm]*(1 - lam_patch); the remaining samples:
+ * image-level mixup with partner batch/2 + perm_image[b - batch/2] and lam_image.  on_value / off_value: the smoothed one-hot levels.
+ * All draws are the caller's (host RNG protocol of the reference); the arithmetic reproduces the reference's fp32 results bit for bit.
+ * -------------------------------------------------------------------------------------------------- */
+int vsx_token_mix(const float* samples, float* out, const long* labels, const int* perm_patch, const int* perm_image, float* targets,
+                  float* patch_targets, int batch, int channels, int height, int width, int patch_len, int num_classes, int box_y0,
+                  int box_y1, int box_x0, int box_x1, float on_value, float off_value, float lam_patch, float lam_image, void* stream);
+
+/* ----------------------------------------------------------------------------------------------------
  * Loss and optimizer ends of the step (engine.py:152-157, :175-177).
  * vsx_soft_ce: *loss_sum += loss_scale * sum_rows(-sum_c t*log_softmax(x)); dlogits = grad_scale*(softmax*sum(t) - t)
  *              (timm SoftTargetCrossEntropy, main.py:392-394; dlogits may be NULL).

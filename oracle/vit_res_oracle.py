@@ -502,3 +502,72 @@ def ema_update(ema_state, model_state, decay):
         e = ema_state[k]
         ema_state[k] = (decay * e.double() + (1.0 - decay) * m.double()).to(e.dtype)
     return ema_state
+
+
+# ------------------------------------------------------------------------------------------------ SwitchTokenMix (token_mixup.py)
+def token_mix_draws(batch, patch_len):
+    """The random draws of one SwitchTokenMix.__call__ (token_mixup.py:146-162), consumed in the reference's order from the global
+    torch CPU generator and numpy's global RandomState: first half of the batch -> _patch_mixup_fn (:112-128: randperm, then
+    _gen_random_bbox :75-99), second half -> _image_mixup_fn (:131-137: randperm, then beta(0.8, 0.8))."""
+    import numpy as np
+    n1 = batch // 2
+    n2 = batch - n1
+    perm1 = torch.randperm(n1)
+    lam = np.random.beta(1., 1.)
+    area = int(patch_len * patch_len * lam)
+    max_length = min(patch_len, area)
+
+    def my_randint(low, high, size=None):                    # token_mixup.py:32-35
+        if low == high:
+            high = low + 1
+        return np.random.randint(low, high, size=size)
+    cut_h = my_randint(1, max(1, max_length - 1))
+    cut_w = area // cut_h
+    if cut_w > patch_len:
+        cut_w = patch_len
+        cut_h = area // cut_w
+    yl = my_randint(0, max(0, patch_len - cut_h), size=2)
+    xl = my_randint(0, max(0, patch_len - cut_w), size=2)
+    y0, x0 = int(yl[1]), int(xl[1])                          # :90-91: both boxes are forced to the second draw
+    lam1 = 1 - (cut_h * cut_w + 0.0) / (patch_len * patch_len)
+    perm2 = torch.randperm(n2)
+    lam2 = np.random.beta(0.8, 0.8)
+    return dict(perm1=perm1, box=(y0, y0 + int(cut_h), x0, x0 + int(cut_w)), lam1=float(lam1), perm2=perm2, lam2=float(lam2))
+
+
+def switch_token_mix(samples, labels, draws, patch_len, num_classes=1000, smoothing=0.1):
+    """SwitchTokenMix.__call__ for given draws: first half patch-level mix (a box of patches pasted from a permuted image, per-patch
+    targets switched with it, image-level target mixed with lam = 1 - box area), second half image-level mixup.  Returns NEW tensors
+    (the reference overwrites `samples` in place with the same values).  fp32 arithmetic in the reference's operation order."""
+    B, C, H, W = samples.shape
+    n1 = B // 2
+    ps = H // patch_len
+    off = smoothing / num_classes
+    on = 1. - smoothing + off
+    y = torch.full((B, num_classes), off, dtype=torch.float32)
+    y.scatter_(1, labels.long().view(-1, 1), on)
+    out = samples.clone()
+    targets = torch.zeros(B, num_classes)
+    ptargets = torch.zeros(B, patch_len * patch_len, num_classes)
+    # patch half (:112-128)
+    p1 = draws['perm1']
+    y0, y1, x0, x1 = draws['box']
+    s1 = samples[:n1]
+    o1 = s1.clone()
+    o1[:, :, ps * y0:ps * y1, ps * x0:ps * x1] = s1[p1][:, :, ps * y0:ps * y1, ps * x0:ps * x1]
+    out[:n1] = o1
+    yt = y[:n1]
+    pt = yt.reshape(n1, 1, 1, -1).repeat(1, patch_len, patch_len, 1)
+    pt[:, y0:y1, x0:x1, :] = pt[p1][:, y0:y1, x0:x1, :]
+    ptargets[:n1] = pt.flatten(1, 2)
+    targets[:n1] = yt * draws['lam1'] + yt[p1] * (1. - draws['lam1'])
+    # image half (:131-143)
+    p2 = draws['perm2']
+    s2 = samples[n1:]
+    lam = draws['lam2']
+    out[n1:] = s2 * lam + s2[p2] * (1. - lam)
+    y2 = y[n1:]
+    t2 = y2 * lam + y2[p2] * (1. - lam)
+    targets[n1:] = t2
+    ptargets[n1:] = t2.reshape(B - n1, 1, -1).repeat(1, patch_len * patch_len, 1)
+    return out, targets, ptargets

@@ -101,3 +101,28 @@ def test_oracle_fp64_noise_floor():
         a = O.forward(w32, SMALL_DEF, x, keeps)[0]
         b = O.forward(w64, SMALL_DEF, x.double(), keeps)[0]
     assert rel(a.numpy(), b.numpy()) < 1e-5
+
+
+def test_switch_token_mix_oracle_vs_reference_golden():
+    """oracle.switch_token_mix / token_mix_draws against the REFERENCE's SwitchTokenMix outputs stored by oracle/make_golden_mixup.py
+    (bit exact), including the RNG protocol: re-seeding and re-drawing must reproduce the stored permutations, box and lambdas."""
+    import numpy as np
+    import os
+    import torch
+    from oracle import vit_res_oracle as O
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'token_mix.npz'))
+    ncase = len([k for k in z.files if k.endswith('_meta')])
+    assert ncase >= 4
+    for c in range(ncase):
+        y0, y1, x0, x1, pl, seed = [int(v) for v in z['c%d_meta' % c]]
+        samples, labels = torch.from_numpy(z['c%d_samples' % c]), torch.from_numpy(z['c%d_labels' % c])
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        d = O.token_mix_draws(samples.shape[0], pl)
+        assert d['box'] == (y0, y1, x0, x1)
+        assert torch.equal(d['perm1'], torch.from_numpy(z['c%d_perm1' % c])) and torch.equal(d['perm2'], torch.from_numpy(z['c%d_perm2' % c]))
+        assert [d['lam1'], d['lam2']] == list(z['c%d_lams' % c])
+        out, t, pt = O.switch_token_mix(samples, labels, d, pl)
+        assert torch.equal(out, torch.from_numpy(z['c%d_out' % c]))
+        assert torch.equal(t, torch.from_numpy(z['c%d_targets' % c]))
+        assert torch.equal(pt, torch.from_numpy(z['c%d_ptargets' % c]))
