@@ -280,7 +280,7 @@ int vsx_sr_combine_bwd(const float* gy, void* dconv, void* dtok, int dtype, floa
  * -------------------------------------------------------------------------------------------------- */
 int vsx_token_mix(const float* samples, float* out, const long* labels, const int* perm_patch, const int* perm_image, float* targets,
                   float* patch_targets, int batch, int channels, int height, int width, int patch_len, int num_classes, int box_y0,
-                  int box_y1, int box_x0, int box_x1, float on_value, float off_value, float lam_patch, float lam_image, void* stream);
+                  int box_y1, int box_x0, int box_x1, float on_value, float off_value, double lam_patch, double lam_image, void* stream);
 
 /* ----------------------------------------------------------------------------------------------------
  * Loss and optimizer ends of the step (engine.py:152-157, :175-177).

@@ -71,7 +71,7 @@ using namespace vsx;
 
 extern "C" int vsx_token_mix(const float* samples, float* out, const long* labels, const int* perm_patch, const int* perm_image, float* targets,
                              float* patch_targets, int batch, int channels, int height, int width, int patch_len, int num_classes, int box_y0,
-                             int box_y1, int box_x0, int box_x1, float on_value, float off_value, float lam_patch, float lam_image, void* stream) {
+                             int box_y1, int box_x0, int box_x1, float on_value, float off_value, double lam_patch, double lam_image, void* stream) {
   VSX_REQUIRE(batch >= 2 && channels > 0 && patch_len > 0 && height % patch_len == 0 && width % patch_len == 0 && width % 4 == 0,
               "vsx_token_mix: need batch >= 2, image sides divisible by patch_len and width %% 4 == 0 (batch=%d %dx%d patch_len=%d)", batch, height,
               width, patch_len);
@@ -81,17 +81,19 @@ extern "C" int vsx_token_mix(const float* samples, float* out, const long* label
   const int n1 = batch / 2, ph = height / patch_len, pw = width / patch_len;
   const long CHW = (long)channels * height * width;
   VSX_REQUIRE(CHW < (1L << 31), "vsx_token_mix: sample too large");
-  // the reference forms 1 - lam in double and rounds to fp32 when it multiplies the fp32 tensor
-  const float oml1 = (float)(1.0 - (double)lam_patch), oml2 = (float)(1.0 - (double)lam_image);
+  // the reference holds lam as a Python float (double), forms 1 - lam in double, and each is rounded to fp32 when it multiplies the fp32
+  // tensor: the lambdas cross the ABI as doubles so that (float)(1 - lam) is not formed from an already rounded lam
+  const float oml1 = (float)(1.0 - lam_patch), oml2 = (float)(1.0 - lam_image);
+  const float lam1f = (float)lam_patch, lam2f = (float)lam_image;
   long blocks = ((long)batch * CHW / 4 + 255) / 256;
   const long cap = (long)num_sms() * 16;
   token_mix_samples_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(samples, out, perm_patch, perm_image, batch, n1, (int)CHW, height * width,
-                                                                               width, box_y0 * ph, box_y1 * ph, box_x0 * pw, box_x1 * pw, lam_image, oml2);
+                                                                               width, box_y0 * ph, box_y1 * ph, box_x0 * pw, box_x1 * pw, lam2f, oml2);
   int rc = check_launch("vsx_token_mix");
   if (rc) return rc;
   blocks = ((long)batch * num_classes + 255) / 256;
   token_mix_targets_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(labels, perm_patch, perm_image, targets, patch_targets, batch, n1,
                                                                                num_classes, patch_len, box_y0, box_y1, box_x0, box_x1, on_value, off_value,
-                                                                               lam_patch, oml1, lam_image, oml2);
+                                                                               lam1f, oml1, lam2f, oml2);
   return check_launch("vsx_token_mix");
 }

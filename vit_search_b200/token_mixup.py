@@ -65,5 +65,5 @@ class SwitchTokenMix:
         on = 1. - self.smoothing + off
         y0, y1, x0, x1 = d['box']
         ops.call('token_mix', x, out, labels, p1, p2, new_targets, patch_targets, B, C, H, W, self.patch_len, K, y0, y1, x0, x1,
-                 float(np.float32(on)), float(np.float32(off)), float(np.float32(d['lam1'])), float(np.float32(d['lam2'])))
+                 float(np.float32(on)), float(np.float32(off)), float(d['lam1']), float(d['lam2']))
         return out, new_targets, patch_targets, 'seq'
