@@ -282,6 +282,16 @@ int vsx_token_mix(const float* samples, float* out, const long* labels, const in
                   float* patch_targets, int batch, int channels, int height, int width, int patch_len, int num_classes, int box_y0,
                   int box_y1, int box_x0, int box_x1, float on_value, float off_value, double lam_patch, double lam_image, void* stream);
 
+/* --------------------------------------------------------------------------------------------------
+ * Evaluation tail of one batch (replaces torch.nn.CrossEntropyLoss + timm accuracy(topk=(1,5)) + three .item() synchronisations per
+ * batch, engine.py:195,222-233): logits [rows, cols] fp32 (row stride ld), hard labels int64.  row_loss / row_rank: caller scratch of
+ * `rows` elements.  totals (fp64[5], device) accumulate: sum of per-batch MEAN losses, top-1 hits, top-5 hits, samples, batches -- the
+ * numerators / denominators of the reference's meters (loss is averaged per batch, accuracies per sample).  A sample is a top-k hit
+ * when fewer than k logits are strictly larger than its label's logit.  Deterministic (fixed-order reduction).
+ * -------------------------------------------------------------------------------------------------- */
+int vsx_eval_metrics(const float* logits, long ld, const long* labels, int rows, int cols, float* row_loss, int* row_rank, double* totals,
+                     void* stream);
+
 /* ----------------------------------------------------------------------------------------------------
  * Loss and optimizer ends of the step (engine.py:152-157, :175-177).
  * vsx_soft_ce: *loss_sum += loss_scale * sum_rows(-sum_c t*log_softmax(x)); dlogits = grad_scale*(softmax*sum(t) - t)

@@ -41,3 +41,33 @@ CASES = {
     # BASELINE.json configs[0]: ViT-Res-Tiny reference net, forward + loss on CPU, batch 2
     'vit_res_tiny_b2': dict(net='vit_res_tiny', supernet=False, batch=2, epa=None, warmup=0, epoch=0, seed=16),
 }
+
+
+# Candidate evaluation (BASELINE configs[4]): a super-network definition in which every block exists, and dense
+# sub-network definitions in the form search_utils/gen_utils.py produces (same entry count, prefix extents, exists flags).
+EVO_SUPER_DEF = tuple((1,) + d[1:3] + (1,) if d[0] == 1 else d for d in SMALL_DEF)
+
+
+def _sub(c1, c2, c3, blocks):
+    """blocks: per transformer block (heads, mlp_features, exists)."""
+    out, width, j = [(4, c1)], c1, 0
+    for d in EVO_SUPER_DEF[1:]:
+        if d[0] == 1:
+            h, f, e = blocks[j]
+            j += 1
+            out.append((1, (width, h, d[1][2]), (width, f), e))
+        elif d[0] == 3:
+            nxt = c2 if d[2] == 128 else c3
+            out.append((3, width, nxt))
+            width = nxt
+        else:
+            out.append((2, width, 1000))
+    return tuple(out)
+
+
+EVO_CANDIDATES = {
+    'largest': EVO_SUPER_DEF,
+    'narrow':  _sub(56, 112, 224, [(2, 96, 1), (1, 64, 1), (2, 256, 1), (1, 192, 1), (2, 128, 0), (3, 384, 1), (4, 512, 1)]),
+    'odd':     _sub(44, 100, 200, [(1, 128, 1), (2, 128, 0), (1, 128, 1), (2, 256, 0), (2, 256, 0), (2, 256, 1), (3, 384, 0)]),
+    'mixed':   _sub(64, 80, 256, [(2, 64, 1), (2, 96, 1), (2, 192, 1), (1, 256, 1), (1, 128, 1), (4, 256, 1), (2, 512, 1)]),
+}

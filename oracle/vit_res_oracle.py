@@ -454,7 +454,7 @@ def param_shapes(network_def, num_tokens=1, patch_output=True, img_size=224, pat
     return s
 
 
-def keyed_fill(shapes, seed=0, dtype=torch.float32):
+def keyed_fill(shapes, seed=0, dtype=torch.float32, running_stats=False):
     """Deterministic, key-addressed synthetic weights (order independent, so the reference, the oracle
     and the CUDA modules can all be filled identically via their state_dict keys).  Scales imitate the
     reference init (trunc-normal 0.02 Linear weights, LN gamma ~ 1) but biases/betas are non-zero so
@@ -467,9 +467,9 @@ def keyed_fill(shapes, seed=0, dtype=torch.float32):
             continue
         r = torch.randn(tuple(shp), generator=g, dtype=torch.float64)
         if k.endswith('running_mean'):
-            t = torch.zeros_like(r)
+            t = 0.1 * r if running_stats else torch.zeros_like(r)           # running_stats: a trained net's buffers (eval-mode cases)
         elif k.endswith('running_var'):
-            t = torch.ones_like(r)
+            t = 1.0 + 0.3 * r.abs() if running_stats else torch.ones_like(r)
         elif k.endswith('norm.weight') or k.endswith('norm1.weight') or k.endswith('norm2.weight') or k.endswith('bn.weight'):
             t = 1.0 + 0.1 * r
         elif k.endswith('conv.weight'):
@@ -571,3 +571,54 @@ def switch_token_mix(samples, labels, draws, patch_len, num_classes=1000, smooth
     targets[n1:] = t2
     ptargets[n1:] = t2.reshape(B - n1, 1, -1).repeat(1, patch_len * patch_len, 1)
     return out, targets, ptargets
+
+
+# --------------------------------------------------------------------------------------
+# evolutionary-search candidate evaluation (BASELINE configs[4])
+# --------------------------------------------------------------------------------------
+def sub_state_dict(source, sub_shapes):
+    """nets/net_utils.py:11-57 (get_qkv_subnet_state_dict + get_sub_state_dict): the dense sub-network's weights are prefix slices of
+    the super-network's -- every dimension of every tensor is cut to the sub-network's extent; q, k and v rows are cut separately
+    inside the stacked qkv tensor (:22-26); 4-D conv kernels keep their spatial extent (:48-51); 0-d entries (BatchNorm's
+    num_batches_tracked) keep the freshly built sub-network's own value (:52-53), which is 0."""
+    out = {}
+    for k, shp in sub_shapes.items():
+        src = source[k]
+        shp = tuple(shp)
+        if 'qkv' in k:
+            n_sub, n_src = shp[0] // 3, src.shape[0] // 3
+            t = torch.cat([src[0:n_sub], src[n_src:n_src + n_sub], src[2 * n_src:2 * n_src + n_sub]], dim=0)
+            out[k] = t[:, :shp[1]] if len(shp) == 2 else t
+        elif len(shp) == 0:
+            out[k] = torch.zeros((), dtype=torch.long)
+        elif len(shp) == 4:
+            assert src.shape[2:] == shp[2:]
+            out[k] = src[:shp[0], :shp[1]]
+        else:
+            out[k] = src[tuple(slice(0, n) for n in shp)]
+    return out
+
+
+def candidate_logits(p_super, sub_network_def, x, patch_output=True):
+    """evo_search.py:256-273 + engine.py:201-212 for one batch: build the dense sub-network `sub_network_def`, load the prefix slices of
+    the super-network state dict, eval-mode forward (BatchNorm running statistics, no ChannelDrop, no drop-path) -> class logits."""
+    p_sub = sub_state_dict(p_super, param_shapes(sub_network_def, patch_output=patch_output))
+    return forward(p_sub, sub_network_def, x, None, training=False, patch_output=patch_output)
+
+
+def eval_metrics(logits, labels):
+    """One batch of engine.evaluate (engine.py:195,222-228): mean hard-label cross entropy and timm's accuracy(topk=(1, 5)) in
+    percent.  A sample counts for top-k when fewer than k logits are strictly larger than its target logit (no ties in practice)."""
+    z = logits.double()
+    loss = (torch.logsumexp(z, dim=1) - z.gather(1, labels.view(-1, 1)).squeeze(1)).mean()
+    rank = (z > z.gather(1, labels.view(-1, 1))).sum(dim=1)
+    return dict(loss=loss.item(), acc1=100.0 * (rank < 1).double().mean().item(), acc5=100.0 * (rank < 5).double().mean().item())
+
+
+def evaluate_meters(batches):
+    """The averaging of engine.evaluate over a loader (engine.py:230-233, utils.MetricLogger): `loss` is the mean of the per-batch mean
+    losses (each update has n=1), acc1 / acc5 are weighted by batch size.  batches: list of (metrics dict, batch_size)."""
+    nb = len(batches)
+    n = sum(b for _, b in batches)
+    return dict(loss=sum(m['loss'] for m, _ in batches) / nb, acc1=sum(m['acc1'] * b for m, b in batches) / n,
+                acc5=sum(m['acc5'] * b for m, b in batches) / n)

@@ -156,3 +156,26 @@ def test_fused_adamw_grouping_matches_timm_rules():
     assert wd['tokens'] == 0.0 and wd['pos_embed'] == 0.05 and wd['blocks.0.attn.qkv.weight'] == 0.05
     assert wd['blocks.0.attn.qkv.bias'] == 0.0 and wd['blocks.0.norm1.weight'] == 0.0 and wd['patch_embed.conv1.bn.weight'] == 0.0
     assert wd['blocks.2.pos_embed'] == 0.05
+
+
+def test_subnet_extents_of_search_candidates():
+    """Candidate definitions (search_utils/gen_utils.py form) -> prefix extents on the resident super-network; misfits are rejected."""
+    import pytest
+    from oracle.cases import EVO_SUPER_DEF, EVO_CANDIDATES
+    from vit_search_b200.nets import create_model
+    m = create_model('flexible_vit_sr_patch14_224_patch_output', network_def=EVO_SUPER_DEF, num_classes=1000)
+    e = m.subnet_extents(EVO_CANDIDATES['narrow'])
+    assert e[0] == {'embed': 56} and e[1] == {'attn': 64, 'mlp': 96} and e[2] == {'attn': 32, 'mlp': 64}
+    assert e[3] == {'embed': 112} and e[6] == {'skip': True} and e[7] == {'embed': 224} and e[-1] == {}
+    full = m.subnet_extents(EVO_SUPER_DEF)
+    assert full[8] == {'attn': 256, 'mlp': 512}
+    bad = list(EVO_CANDIDATES['narrow'])
+    bad[3] = (3, 64, 112)                                   # SR input width must follow the embedding width
+    with pytest.raises(ValueError):
+        m.subnet_extents(tuple(bad))
+    with pytest.raises(ValueError):
+        m.subnet_extents(EVO_CANDIDATES['narrow'][:-1])
+    bad = list(EVO_CANDIDATES['narrow'])
+    bad[8] = (1, (224, 3, 32), (224, 384), 1)               # head_dim differs from the super-network's 64
+    with pytest.raises(ValueError):
+        m.subnet_extents(tuple(bad))

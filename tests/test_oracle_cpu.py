@@ -126,3 +126,27 @@ def test_switch_token_mix_oracle_vs_reference_golden():
         assert torch.equal(out, torch.from_numpy(z['c%d_out' % c]))
         assert torch.equal(t, torch.from_numpy(z['c%d_targets' % c]))
         assert torch.equal(pt, torch.from_numpy(z['c%d_ptargets' % c]))
+
+
+def test_candidate_evaluation_oracle_vs_reference_golden():
+    """oracle.candidate_logits (prefix-sliced dense sub-network, eval forward) and eval_metrics against the REFERENCE's outputs stored by
+    oracle/make_golden_evo.py (evo_search.py:256-273 + engine.py:195-228)."""
+    import numpy as np
+    import os
+    import torch
+    from oracle import vit_res_oracle as O
+    from oracle.cases import EVO_SUPER_DEF, EVO_CANDIDATES
+    z = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'evo_eval.npz'))
+    sup = O.keyed_fill(O.param_shapes(EVO_SUPER_DEF), seed=int(z['w_seed']), running_stats=True)
+    x, _, _ = O.synthetic_batch(8, seed=int(z['x_seed']))
+    for name, sub_def in EVO_CANDIDATES.items():
+        ref = torch.from_numpy(z[name + '_logits'])
+        got = O.candidate_logits(sup, sub_def, x)
+        assert ((got - ref).norm() / ref.norm()).item() < 2e-6, name
+        m = O.eval_metrics(ref, torch.from_numpy(z[name + '_labels']))
+        loss, acc1, acc5 = z[name + '_metrics']
+        assert abs(m['loss'] - loss) < 1e-5 and m['acc1'] == acc1 and m['acc5'] == acc5
+    # the q / k / v row blocks are cut separately (nets/net_utils.py:22-26)
+    sub = O.sub_state_dict(sup, O.param_shapes(EVO_CANDIDATES['narrow']))
+    w, ws = sup['blocks.1.attn.qkv.weight'], sub['blocks.1.attn.qkv.weight']
+    assert ws.shape == (96, 56) and torch.equal(ws[32:64], w[64:96, :56]) and torch.equal(ws[64:96], w[128:160, :56])

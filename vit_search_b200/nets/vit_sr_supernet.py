@@ -409,6 +409,8 @@ class FlexibleDistillVisionTransformerSR(nn.Module):
         self.is_supernet = supernet
         self.example_per_arch = example_per_arch
         self.last_keeps = None       # per-entry keep dicts of the most recent forward (original sample order)
+        self.active_subnet = None    # candidate evaluation: a dense sub-network definition run on THESE weights (set_active_subnet)
+        self.weights_resident = False
 
     def _init_weights(self, m):
         if isinstance(m, nn.Linear):
@@ -469,15 +471,66 @@ class FlexibleDistillVisionTransformerSR(nn.Module):
         order = sorted(range(batch), key=lambda b: (first[sig[b]], b))
         return None if order == list(range(batch)) else order
 
+    # ------------------------------------------------------------------ candidate evaluation on resident weights
+    def subnet_extents(self, sub_network_def):
+        """Prefix extents that make this network compute exactly what the reference's evolutionary search evaluates for
+        `sub_network_def` (evo_search.py:256-273: a freshly built dense sub-network loaded with nets/net_utils.get_sub_state_dict
+        prefix slices of these weights): embed / SR widths, heads * head_dim, MLP features; sub-network blocks with exists=0 are
+        skipped (BypassBlock).  -> list aligned with network_def of {'embed' | 'attn' + 'mlp' | 'skip'}."""
+        sup = self.network_def
+        if len(sub_network_def) != len(sup):
+            raise ValueError('sub-network definition has %d entries, this network %d' % (len(sub_network_def), len(sup)))
+        out, width_sup, width = [], None, None
+        for i, (d, u) in enumerate(zip(sub_network_def, sup)):
+            if i == 0:
+                if d[_BLOCK_TYPE] != u[_BLOCK_TYPE] or d[1] > u[1] or tuple(d[2:]) != tuple(u[2:]):
+                    raise ValueError('entry 0: embedding %s does not fit %s' % (d, u))
+                width, width_sup = d[1], u[1]
+                out.append({'embed': width})
+            elif u[_BLOCK_TYPE] == _TYPE_IS_TRANS:
+                if d[_BLOCK_TYPE] != _TYPE_IS_TRANS or d[1][0] != width or d[2][0] != width:
+                    raise ValueError('entry %d: %s is not a transformer block of width %d' % (i, d, width))
+                if not d[3]:
+                    out.append({'skip': True})
+                    continue
+                if not u[3] or d[1][2] != u[1][2] or d[1][1] > u[1][1] or d[2][1] > u[2][1]:
+                    raise ValueError('entry %d: block %s does not fit inside %s' % (i, d, u))
+                out.append({'attn': d[1][1] * d[1][2], 'mlp': d[2][1]})
+            elif u[_BLOCK_TYPE] == _TYPE_IS_SR:
+                if d[_BLOCK_TYPE] != _TYPE_IS_SR or d[1] != width or d[2] > u[2]:
+                    raise ValueError('entry %d: SR block %s does not fit %s at width %d' % (i, d, u, width))
+                width, width_sup = d[2], u[2]
+                out.append({'embed': width})
+            else:
+                if d[_BLOCK_TYPE] != u[_BLOCK_TYPE] or d[1] != width or d[2] != u[2]:
+                    raise ValueError('entry %d: head %s does not fit %s at width %d' % (i, d, u, width))
+                out.append({})
+        return out
+
+    def set_active_subnet(self, sub_network_def, weights_resident=True):
+        """Evaluate `sub_network_def` (None: back to the network's own behaviour) with eval-mode forwards of THIS module: no model
+        build, no state-dict slicing or copy, no device upload per candidate.  weights_resident: the
+        parameters do not change between forwards, so the bf16 GEMM operand copies are derived once, not once per forward."""
+        self.active_subnet = None if sub_network_def is None else self.subnet_extents(sub_network_def)
+        self.weights_resident = bool(weights_resident) and sub_network_def is not None
+        if self.weights_resident:
+            core.weights.generation += 1
+
     # ------------------------------------------------------------------ forward
     def forward_features(self, x):
         core.require_cuda(x, 'FlexibleDistillVisionTransformerSR')
         assert self.num_tokens == 1, 'distillation-token path is outside the hot path (SURVEY.md §2)'
-        core.weights.generation += 1          # weights may have been updated since the last forward: re-derive operand copies
         B = x.shape[0]
-        keeps = self.sample_keeps(B) if self.is_supernet else [{} for _ in self.network_def]
+        if self.active_subnet is not None:
+            if self.training:
+                raise RuntimeError('set_active_subnet() is the evaluation path of the evolutionary search: call model.eval() first')
+            keeps = [{k: ([v] * B if k != 'skip' else v) for k, v in e.items()} for e in self.active_subnet]
+        else:
+            keeps = self.sample_keeps(B) if self.is_supernet else [{} for _ in self.network_def]
+        if self.training or not self.weights_resident:
+            core.weights.generation += 1      # weights may have been updated since the last forward: re-derive operand copies
         self.last_keeps = keeps
-        perm = self._group_permutation(keeps, B)
+        perm = None if self.active_subnet is not None else self._group_permutation(keeps, B)
         if perm is not None:       # make architecture groups contiguous; undone on the logits
             idx = core.h2d(perm, x.device)
             x = x.index_select(0, idx)
@@ -502,7 +555,7 @@ class FlexibleDistillVisionTransformerSR(nn.Module):
         for i, d in enumerate(self.network_def):
             if d[_BLOCK_TYPE] == _TYPE_IS_TRANS:
                 blk = self.blocks[j]
-                if isinstance(blk, Block):
+                if isinstance(blk, Block) and not keeps[i].get('skip'):
                     use_dp = dp if rates[t] > 0 else None
                     h, layer_keep = blk.forward_keeps(h, embed_keep, layer_keep, keeps[i], use_dp, 2 * t)
                 else:
