@@ -254,6 +254,9 @@ int vsx_conv3x3(const void* in, const float* in_scale, const float* in_shift, co
                 const float* mean, const float* rstd, double* sums, void* stream);
 int vsx_conv3x3_wgrad(const void* dy, const void* in, const float* in_scale, const float* in_shift, float* dw, int B, int H,
                       int W, int C, void* stream);
+/* Development aid: 0 = pick the kernel automatically, 1 = legacy direct kernel (csrc/conv3x3.cu), 2 = TMA warp-specialised kernel
+ * (csrc/conv3x3_tma.cu; C == 24, H and W multiples of 16). */
+int vsx_conv3x3_force_impl(int impl);
 
 /* Token assembly: x0[b,t,:] = mask * ((t == 0 ? tokens : patches[b,t-1]) + pos_embed[t])  -- replaces cat / expand /
  * add / embed ChannelDrop at nets/vit_sr_supernet.py:399-407; backward gives dpatches (activation dtype), and

@@ -309,12 +309,23 @@ def test_attention_tcgen05_persistent(ops, B, N, H, Hk):
 
 
 # ---------------------------------------------------------------------------------------------- direct 3x3 conv (stem)
-@pytest.mark.parametrize('C', [24, 32])
-def test_conv3x3_direct(ops, C):
+@pytest.fixture
+def conv_impl():
+    from vit_search_b200 import _lib
+
+    def force(impl):
+        _lib.check(_lib.lib().vsx_conv3x3_force_impl(impl))
+    yield force
+    force(0)
+
+
+@pytest.mark.parametrize('C,impl', [(24, 0), (24, 1), (24, 2), (32, 0)])
+def test_conv3x3_direct(ops, conv_impl, C, impl):
     """Tensor-core direct conv (forward with fused BN+ReLU input and batch statistics, data gradient with the BN-backward
-    reductions, weight gradient) against torch fp64 math on the same bf16-rounded operands."""
+    reductions, weight gradient) against torch fp64 math on the same bf16-rounded operands.  impl 1: legacy kernel, 2: TMA kernel."""
     import torch.nn.functional as F
     from vit_search_b200 import core
+    conv_impl(impl)
     B, H, W = 2, 16, 32
     g = torch.Generator().manual_seed(C)
     y_in = torch.randn(B, H, W, C, generator=g).to(torch.bfloat16)
@@ -351,3 +362,36 @@ def test_conv3x3_direct(ops, C):
     dw = torch.zeros(C, 9 * C, device='cuda')
     ops.call('conv3x3_wgrad', dy.cuda(), y_in.cuda(), sc.cuda(), sh.cuda(), dw, B, H, W, C)
     assert rel(dw.view(C, 3, 3, C).permute(0, 3, 1, 2), wref.grad) < 2e-3
+
+
+def test_conv3x3_tma_matches_legacy_at_stem_size(ops, conv_impl):
+    """The TMA warp-specialised kernel (csrc/conv3x3_tma.cu) against the legacy direct kernel at the stem's map size, enough tiles
+    per CTA to wrap the 4-stage ring several times: both accumulate the same packed reduction in the same order, so the bf16
+    outputs must be bit-identical; the fused statistics agree to fp32 summation order.  Every mode: activated input + forward
+    statistics, plain, data gradient with / without the residual gradient."""
+    from vit_search_b200 import core
+    B, H, W, C = 24, 112, 112, 24
+    g = torch.Generator(device='cuda').manual_seed(7)
+    x = torch.randn(B, H, W, C, device='cuda', generator=g).to(torch.bfloat16)
+    y_prev = torch.randn(B, H, W, C, device='cuda', generator=g).to(torch.bfloat16)
+    add = torch.randn(B, H, W, C, device='cuda', generator=g).to(torch.bfloat16)
+    sc, sh = 1 + 0.2 * torch.randn(C, device='cuda', generator=g), 0.3 * torch.randn(C, device='cuda', generator=g)
+    gam, bet = 1 + 0.1 * torch.randn(C, device='cuda', generator=g), 0.1 * torch.randn(C, device='cuda', generator=g)
+    mean, rstd = 0.1 * torch.randn(C, device='cuda', generator=g), 1 + 0.1 * torch.rand(C, device='cuda', generator=g)
+    wparam = torch.nn.Parameter(torch.randn(C, C, 3, 3, device='cuda', generator=g) * 0.1)
+    wf, wb = core.weights.get(wparam, 'conv3x3_fwd'), core.weights.get(wparam, 'conv3x3_bwd')
+    modes = [(sc, sh, wf, None, 1, None), (None, None, wf, None, 0, None), (None, None, wb, add, 2, y_prev), (None, None, wb, None, 2, y_prev),
+             (sc, sh, wf, add, 0, None)]
+    for a_sc, a_sh, w, ad, stats, yp in modes:
+        res = []
+        for impl in (1, 2):
+            conv_impl(impl)
+            out = torch.full((B, H, W, C), float('nan'), device='cuda', dtype=torch.bfloat16)
+            sums = torch.zeros(2 * C, device='cuda', dtype=torch.float64)
+            bn = (gam, bet, mean, rstd) if stats == 2 else (None,) * 4
+            ops.call('conv3x3', x, a_sc, a_sh, w, ad, out, B, H, W, C, stats, yp, *bn, sums if stats else None)
+            torch.cuda.synchronize()
+            res.append((out, sums))
+        assert torch.equal(res[0][0], res[1][0]), (stats, ad is not None)
+        if stats:
+            assert rel(res[1][1], res[0][1]) < 1e-6

@@ -111,6 +111,32 @@ int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows,
   return VSX_OK;
 }
 
+// 4-D channels-last bf16 map [B][H][W][C]; box = C x box_w x box_h x 1, no swizzle (dense [box_h][box_w][C] in shared memory).
+// Out-of-range coordinates (negative included) are zero-filled on loads and clipped on stores: the halo of a convolution tile.
+int make_tmap_nhwc(CUtensorMap* m, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint32_t box_w, uint32_t box_h) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return VSX_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (C * 2) % 16 != 0 || C == 0 || W == 0 || H == 0 || B == 0) {
+    set_error("make_tmap_nhwc: map must be 16-byte aligned with a 16-byte-multiple pixel pitch (base=%p C=%llu)", base, (unsigned long long)C);
+    return VSX_ERR_ARG;
+  }
+  cuuint64_t dims[4] = {C, W, H, B};
+  cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)C, box_w, box_h, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (NHWC) failed with CUresult %d (C=%llu W=%llu H=%llu B=%llu box=%ux%u)", (int)r, (unsigned long long)C,
+              (unsigned long long)W, (unsigned long long)H, (unsigned long long)B, box_w, box_h);
+    return VSX_ERR_CUDA;
+  }
+  return VSX_OK;
+}
+
 }  // namespace vsx
 
 extern "C" const char* vsx_last_error(void) { return vsx::g_err; }

@@ -309,11 +309,13 @@ __global__ void __launch_bounds__(WG_WARPS * 32) conv3x3_wgrad_kernel(const bf16
       mma16816(acc[0][0], a0, b01[0], b01[1]);
       mma16816(acc[0][1], a0, b01[2], b01[3]);
       mma16816(acc[0][2], a0, b23[0], b23[1]);
-      mma16816(acc[0][3], a0, b23[2], b23[3]);
       mma16816(acc[1][0], a1, b01[0], b01[1]);
       mma16816(acc[1][1], a1, b01[2], b01[3]);
       mma16816(acc[1][2], a1, b23[0], b23[1]);
-      mma16816(acc[1][3], a1, b23[2], b23[3]);
+      if (C > 24) {                                  // input channels 24..31 exist only for C = 32
+        mma16816(acc[0][3], a0, b23[2], b23[3]);
+        mma16816(acc[1][3], a1, b23[2], b23[3]);
+      }
     }
   }
   // dw layout: [co][tap][ci] fp32 (the GEMM-side 'ohwi' layout), accumulated with atomics (one per element per CTA)
@@ -331,7 +333,22 @@ __global__ void __launch_bounds__(WG_WARPS * 32) conv3x3_wgrad_kernel(const bf16
 }  // namespace
 }  // namespace vsx
 
+namespace vsx {
+// csrc/conv3x3_tma.cu: TMA + warp-specialised kernel for the 24-channel stem
+bool conv3x3_tma_supported(int H, int W, int C);
+int conv3x3_tma_launch(const void* in, const float* in_scale, const float* in_shift, const void* wt, const void* add, void* out, int B, int H, int W,
+                       int stats_mode, const void* y_prev, const float* gamma, const float* beta, const float* mean, const float* rstd, double* sums,
+                       cudaStream_t st);
+static int g_conv_impl = 0;   // 0 auto, 1 legacy direct kernel, 2 TMA kernel (error if unsupported)
+}  // namespace vsx
+
 using namespace vsx;
+
+extern "C" int vsx_conv3x3_force_impl(int impl) {
+  VSX_REQUIRE(impl >= 0 && impl <= 2, "vsx_conv3x3_force_impl: 0 auto, 1 legacy, 2 tma (got %d)", impl);
+  g_conv_impl = impl;
+  return VSX_OK;
+}
 
 extern "C" int vsx_conv3x3(const void* in, const float* in_scale, const float* in_shift, const void* wt, const void* add, void* out, int B,
                            int H, int W, int C, int stats_mode, const void* y_prev, const float* gamma, const float* beta, const float* mean,
@@ -343,6 +360,9 @@ extern "C" int vsx_conv3x3(const void* in, const float* in_scale, const float* i
   const int tiles = B * (H / TH) * (W / TW);
   const int grid = std::min(tiles, num_sms() * 2);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  VSX_REQUIRE(g_conv_impl != 2 || conv3x3_tma_supported(H, W, C), "vsx_conv3x3: the TMA kernel needs C == 24, H %% 16 == 0, W %% 16 == 0");
+  if (g_conv_impl != 1 && conv3x3_tma_supported(H, W, C))
+    return conv3x3_tma_launch(in, in_scale, in_shift, wt, add, out, B, H, W, stats_mode, y_prev, gamma, beta, mean, rstd, sums, st);
 #define VSX_CONV_ARGS (const bf16*)in, in_scale, in_shift, (const bf16*)wt, (const bf16*)add, (bf16*)out, B, H, W, C, (const bf16*)y_prev, gamma, beta, mean, rstd, sums
   if (stats_mode == 0) conv3x3_fwd_kernel<0><<<grid, FWD_WARPS * 32, 0, st>>>(VSX_CONV_ARGS);
   else if (stats_mode == 1) conv3x3_fwd_kernel<1><<<grid, FWD_WARPS * 32, 0, st>>>(VSX_CONV_ARGS);
