@@ -395,3 +395,13 @@ def test_conv3x3_tma_matches_legacy_at_stem_size(ops, conv_impl):
         assert torch.equal(res[0][0], res[1][0]), (stats, ad is not None)
         if stats:
             assert rel(res[1][1], res[0][1]) < 1e-6
+    # weight gradient: same products, different fp32 summation order
+    dws = []
+    for impl in (1, 2):
+        conv_impl(impl)
+        for a_sc, a_sh in ((sc, sh), (None, None)):
+            dw = torch.zeros(C, 9 * C, device='cuda')
+            ops.call('conv3x3_wgrad', add, x, a_sc, a_sh, dw, B, H, W, C)
+            torch.cuda.synchronize()
+            dws.append(dw)
+    assert rel(dws[2], dws[0]) < 2e-5 and rel(dws[3], dws[1]) < 2e-5

@@ -339,6 +339,8 @@ bool conv3x3_tma_supported(int H, int W, int C);
 int conv3x3_tma_launch(const void* in, const float* in_scale, const float* in_shift, const void* wt, const void* add, void* out, int B, int H, int W,
                        int stats_mode, const void* y_prev, const float* gamma, const float* beta, const float* mean, const float* rstd, double* sums,
                        cudaStream_t st);
+int conv3x3_wgrad_tma_launch(const void* dy, const void* in, const float* in_scale, const float* in_shift, float* dw, int B, int H, int W,
+                             cudaStream_t st);
 static int g_conv_impl = 0;   // 0 auto, 1 legacy direct kernel, 2 TMA kernel (error if unsupported)
 }  // namespace vsx
 
@@ -375,6 +377,9 @@ extern "C" int vsx_conv3x3_wgrad(const void* dy, const void* in, const float* in
                                  int C, void* stream) {
   VSX_REQUIRE(C % 8 == 0 && C <= CP && H % TH == 0 && W % TW == 0, "vsx_conv3x3_wgrad: needs C %% 8 == 0, C <= 32, H %% 8 == 0, W %% 16 == 0");
   if (B <= 0) return VSX_OK;
+  VSX_REQUIRE(g_conv_impl != 2 || conv3x3_tma_supported(H, W, C), "vsx_conv3x3_wgrad: the TMA kernel needs C == 24, H %% 16 == 0, W %% 16 == 0");
+  if (g_conv_impl != 1 && conv3x3_tma_supported(H, W, C))
+    return conv3x3_wgrad_tma_launch(dy, in, in_scale, in_shift, dw, B, H, W, reinterpret_cast<cudaStream_t>(stream));
   const int tiles = B * (H / TH) * (W / TW);
   const int grid = std::min(tiles, num_sms() * 2);
   conv3x3_wgrad_kernel<<<grid, WG_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const bf16*)dy, (const bf16*)in, in_scale, in_shift, dw, B,

@@ -42,12 +42,6 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
-  uint32_t v;
-  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
@@ -344,6 +338,189 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tma_kernel(const __grid_co
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------ weight gradient
+// dW[co][tap][ci] += sum_p dy[p][co] * act(in[p + tap - 1][ci]).  Same ring / producer / activation warps; 12 MMA warps = 3 kernel rows (ky) x 4
+// row quarters of the tile: a warp accumulates its three taps (kx = 0..2) x 2 m-tiles (co) x 3 n-tiles (ci) over the whole kernel, so the
+// dy fragments are loaded once per three taps.  Partial sums of the four row quarters are added in shared memory at the end: one atomic
+// per weight-gradient element per CTA.
+constexpr int WG_MMA_WARPS = 12, WG_ACT_WARPS = 3;
+constexpr int WG_THREADS = (WG_ACT_WARPS + WG_MMA_WARPS + 1) * 32;      // 512
+constexpr int WG_STAGE = HALO_SLOT + TILE_BYTES;
+
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm2t(uint32_t (&r)[2], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(addr));
+}
+
+struct WgradMaps {
+  CUtensorMap in, dy;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tma_kernel(const __grid_constant__ WgradMaps maps, const float* __restrict__ in_scale,
+                                                                          const float* __restrict__ in_shift, float* __restrict__ dw, int B, int H,
+                                                                          int W) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
+  uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
+  const bool act = in_scale != nullptr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = base + NSTAGE * WG_STAGE;
+  auto bar_full = [&](int s) { return bar0 + (uint32_t)s * 8u; };
+  auto bar_act = [&](int s) { return bar0 + (uint32_t)(NSTAGE + s) * 8u; };
+  auto bar_empty = [&](int s) { return bar0 + (uint32_t)(2 * NSTAGE + s) * 8u; };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; ++s) {
+      mbar_init(bar_full(s), 1);
+      mbar_init(bar_act(s), WG_ACT_WARPS);
+      mbar_init(bar_empty(s), WG_MMA_WARPS);
+    }
+    fence_mbar_init();
+  }
+  __syncthreads();
+  const int tiles_x = W / T2, tiles_y = H / T2, per_img = tiles_x * tiles_y, tiles = B * per_img;
+
+  if (warp == WG_ACT_WARPS + WG_MMA_WARPS) {
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.in);
+      tma_prefetch_desc(&maps.dy);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const int s = it % NSTAGE, n = it / NSTAGE;
+        if (n > 0) mbar_wait(bar_empty(s), (uint32_t)(n - 1) & 1u);
+        const int b = tile / per_img, rem = tile % per_img;
+        const int ty0 = (rem / tiles_x) * T2, tx0 = (rem % tiles_x) * T2;
+        const uint32_t st = base + (uint32_t)(s * WG_STAGE);
+        mbar_expect_tx(bar_full(s), HALO_BYTES + TILE_BYTES);
+        tma_load_4d(st, &maps.in, bar_full(s), 0, tx0 - 1, ty0 - 1, b);
+        tma_load_4d(st + HALO_SLOT, &maps.dy, bar_full(s), 0, tx0, ty0, b);
+      }
+    }
+    return;
+  }
+
+  if (warp < WG_ACT_WARPS) {
+    if (!act) return;
+    const int a = threadIdx.x;                       // 0..95: thread a owns the 16-byte channel group a % 3 of every 32nd pixel
+    const int cg = a % 3, p0 = a / 3;
+    constexpr int ACT_PIX = (WG_ACT_WARPS * 32) / 3, ACT_ITERS = (HL * HL + ACT_PIX - 1) / ACT_PIX;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sc[k] = in_scale[cg * 8 + k], sh[k] = in_shift[cg * 8 + k];
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int s = it % NSTAGE, n = it / NSTAGE;
+      const int rem = tile % per_img;
+      const int ty0 = (rem / tiles_x) * T2 - 1, tx0 = (rem % tiles_x) * T2 - 1;
+      const uint32_t st = base + (uint32_t)(s * WG_STAGE);
+      mbar_wait(bar_full(s), (uint32_t)n & 1u);
+#pragma unroll
+      for (int j = 0; j < ACT_ITERS; ++j) {
+        const int pix = p0 + ACT_PIX * j;
+        if (pix < HL * HL) {
+          const int hy = pix / HL, hx = pix - hy * HL;
+          const int iy = ty0 + hy, ix = tx0 + hx;
+          if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
+            const uint32_t addr = st + (uint32_t)(pix * PIXB + cg * 16);
+            uint4 v = lds128(addr);
+            uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              float2 f = bf2(w[k]);
+              f.x = fmaxf(fmaf(f.x, sc[2 * k], sh[2 * k]), 0.f);
+              f.y = fmaxf(fmaf(f.y, sc[2 * k + 1], sh[2 * k + 1]), 0.f);
+              w[k] = pack_bf16(f.x, f.y);
+            }
+            sts128(addr, make_uint4(w[0], w[1], w[2], w[3]));
+          }
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_act(s));
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------------------------------- MMA warps
+  const int mw = warp - WG_ACT_WARPS;                // 0..11
+  const int ky = mw % 3, quarter = mw / 3;           // tile rows 4*quarter .. 4*quarter + 3
+  const int g = lane >> 2, t = lane & 3, lj = lane >> 3, li = lane & 7;
+  float acc[3][2][3][4];                             // [kx][m-tile: 16 output channels][n-tile: 8 input channels]
+#pragma unroll
+  for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int nt = 0; nt < 3; ++nt) acc[kx][m][nt][0] = acc[kx][m][nt][1] = acc[kx][m][nt][2] = acc[kx][m][nt][3] = 0.f;
+  // A[m = co][k = pixel] from dy[pixel][co] (transposed): blocks (k lo, co lo), (k lo, co hi), (k hi, co lo), (k hi, co hi)
+  const uint32_t a_lane = (uint32_t)((((lj >> 1) * 8 + li) * CH) * 2 + (lj & 1) * 16);
+  // B[k = pixel][n = ci] from the halo row shifted by the tap (transposed): (k lo, n0), (k hi, n0), (k lo, n1), (k hi, n1); x2: n2 only
+  const uint32_t b_lane = (uint32_t)((((lj & 1) * 8 + li) * CH) * 2 + (lj >> 1) * 16);
+  const uint32_t b2_lane = (uint32_t)(((((lane >> 3) & 1) * 8 + li) * CH) * 2 + 32);
+  int it = 0;
+  for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    const int s = it % NSTAGE, n = it / NSTAGE;
+    const uint32_t halo = base + (uint32_t)(s * WG_STAGE), dys = halo + HALO_SLOT;
+    mbar_wait(bar_full(s), (uint32_t)n & 1u);
+    if (act) mbar_wait(bar_act(s), (uint32_t)n & 1u);
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {                 // k-step = the 16 pixels of tile row r
+      const int r = quarter * 4 + rr;
+      uint32_t a0[4], a1[4];
+      ldsm4t(a0, dys + (uint32_t)(r * T2 * PIXB) + a_lane);
+      ldsm4t(a1, dys + (uint32_t)(r * T2 * PIXB) + a_lane + 32);
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const uint32_t hp = halo + (uint32_t)(((r + ky) * HL + kx) * PIXB);
+        uint32_t b01[4], b2[2];
+        ldsm4t(b01, hp + b_lane);
+        ldsm2t(b2, hp + b2_lane);
+        mma16816(acc[kx][0][0], a0, b01[0], b01[1]);
+        mma16816(acc[kx][0][1], a0, b01[2], b01[3]);
+        mma16816(acc[kx][0][2], a0, b2[0], b2[1]);
+        mma16816(acc[kx][1][0], a1, b01[0], b01[1]);
+        mma16816(acc[kx][1][1], a1, b01[2], b01[3]);
+        mma16816(acc[kx][1][2], a1, b2[0], b2[1]);
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_empty(s));
+  }
+  // add the four row quarters in shared memory (the ring is idle now), then one atomic per element per CTA
+  named_bar_sync(1, WG_MMA_WARPS * 32);
+  float* red = reinterpret_cast<float*>(gbase);      // [quarter 1..3][ky][72][32 lanes]
+  if (quarter > 0) {
+    float* dst = red + (((quarter - 1) * 3 + ky) * 72) * 32 + lane;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) dst[(((kx * 2 + m) * 3 + nt) * 4 + e) * 32] = acc[kx][m][nt][e];
+  }
+  named_bar_sync(1, WG_MMA_WARPS * 32);
+  if (quarter == 0) {
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx)
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int nt = 0; nt < 3; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int i = (((kx * 2 + m) * 3 + nt) * 4 + e) * 32 + lane;
+            const float v = acc[kx][m][nt][e] + red[(0 * 3 + ky) * 72 * 32 + i] + red[(1 * 3 + ky) * 72 * 32 + i] + red[(2 * 3 + ky) * 72 * 32 + i];
+            const int co = m * 16 + g + (e >> 1) * 8, ci = nt * 8 + 2 * t + (e & 1);
+            if (co < CH) atomicAdd(dw + ((long)co * 9 + ky * 3 + kx) * CH + ci, v);
+          }
+  }
+}
+
 }  // namespace
 
 bool conv3x3_tma_supported(int H, int W, int C) { return C == CH && H % T2 == 0 && W % T2 == 0; }
@@ -380,6 +557,26 @@ int conv3x3_tma_launch(const void* in, const float* in_scale, const float* in_sh
 #undef VSX_CONV2_LAUNCH
 #undef VSX_CONV2_ARGS
   return check_launch("vsx_conv3x3");
+}
+
+int conv3x3_wgrad_tma_launch(const void* dy, const void* in, const float* in_scale, const float* in_shift, float* dw, int B, int H, int W,
+                             cudaStream_t st) {
+  WgradMaps maps;
+  int rc;
+  if ((rc = make_tmap_nhwc(&maps.in, in, CH, W, H, B, HL, HL))) return rc;
+  if ((rc = make_tmap_nhwc(&maps.dy, dy, CH, W, H, B, T2, T2))) return rc;
+  const int smem = NSTAGE * WG_STAGE + 3 * NSTAGE * 8 + 128;
+  static bool attr = false;
+  if (!attr) {
+    if (cudaFuncSetAttribute(conv3x3_wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024) != cudaSuccess) {
+      set_error("vsx_conv3x3_wgrad: cannot raise the dynamic shared memory limit");
+      return VSX_ERR_CUDA;
+    }
+    attr = true;
+  }
+  const int tiles = B * (H / T2) * (W / T2);
+  conv3x3_wgrad_tma_kernel<<<std::min(tiles, num_sms()), WG_THREADS, smem, st>>>(maps, in_scale, in_shift, dw, B, H, W);
+  return check_launch("vsx_conv3x3_wgrad");
 }
 
 }  // namespace vsx
