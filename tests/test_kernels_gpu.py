@@ -405,3 +405,58 @@ def test_conv3x3_tma_matches_legacy_at_stem_size(ops, conv_impl):
             torch.cuda.synchronize()
             dws.append(dw)
     assert rel(dws[2], dws[0]) < 2e-5 and rel(dws[3], dws[1]) < 2e-5
+
+
+@pytest.mark.parametrize('shape', [dict(B=3, H=28, W=28, C=24, k=7, s=7, p=0, dual=True),      # conv_proj: patches, BN+ReLU of two maps
+                                   dict(B=2, H=16, W=16, C=64, k=3, s=2, p=1, tok=True),        # SR conv on a token tensor (class token skipped)
+                                   dict(B=2, H=8, W=8, C=128, k=3, s=2, p=1, tok=True),
+                                   dict(B=2, H=12, W=12, C=12, k=3, s=1, p=1)])                 # C % 8 != 0: the generic kernels
+def test_im2col_col2im_bf16(ops, shape):
+    """im2col / col2im (bf16 channels-last; the 16-byte row kernels where C % 8 == 0) against torch unfold / fold."""
+    import torch.nn.functional as F
+    B, H, W, C, k, s, p = (shape[n] for n in 'B H W C k s p'.split())
+    tok, dual = shape.get('tok', False), shape.get('dual', False)
+    g = torch.Generator().manual_seed(H * C + k)
+    N = H * W + (1 if tok else 0)
+    x = torch.randn(B, N, C, generator=g).to(torch.bfloat16)
+    x2 = torch.randn(B, N, C, generator=g).to(torch.bfloat16)
+    sc1, sh1 = 1 + 0.2 * torch.randn(C, generator=g), 0.3 * torch.randn(C, generator=g)
+    sc2, sh2 = 1 + 0.2 * torch.randn(C, generator=g), 0.3 * torch.randn(C, generator=g)
+    off = C if tok else 0
+    Ho, Wo = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+
+    def to_cols(t):          # [B, H*W, C] fp32 -> [B*Ho*Wo, k*k*C] with tap-major, channel-minor columns
+        u = F.unfold(t.view(B, H, W, C).permute(0, 3, 1, 2), k, padding=p, stride=s)
+        return u.view(B, C, k * k, Ho * Wo).permute(0, 3, 2, 1).reshape(B * Ho * Wo, k * k * C)
+
+    img = x[:, 1:] if tok else x
+    if dual:
+        a = F.relu(img.float() * sc1 + sh1) + F.relu((x2[:, 1:] if tok else x2).float() * sc2 + sh2)
+    else:
+        a = img.float()
+    ref = to_cols(a).to(torch.bfloat16)
+    out = torch.full((B * Ho * Wo, k * k * C), float('nan'), device='cuda', dtype=torch.bfloat16)
+    xd, x2d = x.cuda(), x2.cuda()
+    if dual:
+        ops.call('im2col', (xd, off), sc1.cuda(), sh1.cuda(), (x2d, off), sc2.cuda(), sh2.cuda(), ops.BF16, 0, N * C, C, B, H, W, C, k, s, p, out,
+                 ops.BF16, k * k * C)
+    else:
+        ops.call('im2col', (xd, off), None, None, None, None, None, ops.BF16, 0, N * C, C, B, H, W, C, k, s, p, out, ops.BF16, k * k * C)
+    if dual:       # the kernel's fused multiply-add rounds once where torch rounds twice: rare 1-ulp differences after the bf16 rounding
+        assert rel(out.cpu(), ref) < 1e-3 and not torch.isnan(out).any()
+    else:
+        assert torch.equal(out.cpu(), ref)
+    # col2im: the adjoint (+ optional add), fp32 accumulation, one rounding
+    dcol = torch.randn(B * Ho * Wo, k * k * C, generator=g).to(torch.bfloat16)
+    add = torch.randn(B, N, C, generator=g).to(torch.bfloat16)
+    fold_in = dcol.float().view(B, Ho * Wo, k * k, C).permute(0, 3, 2, 1).reshape(B, C * k * k, Ho * Wo)
+    ref_d = F.fold(fold_in, (H, W), k, padding=p, stride=s).permute(0, 2, 3, 1).reshape(B, H * W, C)
+    for use_add in (False, True):
+        din = torch.zeros(B, N, C, device='cuda', dtype=torch.bfloat16)
+        addd = add.cuda()
+        ops.call('col2im', dcol.cuda(), k * k * C, (addd, off) if use_add else None, ops.BF16, B, H, W, C, k, s, p, (din, off), N * C, C)
+        want = ref_d + ((add[:, 1:] if tok else add).float() if use_add else 0)
+        got = din.cpu()[:, 1:] if tok else din.cpu()
+        assert rel(got, want) < 4e-3
+        if tok:
+            assert torch.all(din[:, 0] == 0)          # the class-token row is not touched

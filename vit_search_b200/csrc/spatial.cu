@@ -138,6 +138,123 @@ __global__ void col2im_kernel(const T* __restrict__ dcol, long ldc, const T* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------ bf16 row kernels
+// Same semantics as im2col_kernel / col2im_kernel for bf16 channels-last maps with C % 8 == 0, re-mapped for bandwidth: one CTA per
+// output (im2col) / input (col2im) image row, 16-byte chunks, consecutive lanes on consecutive chunks of a contiguous run (the k taps
+// of one kernel row are contiguous both in the source row and in the column matrix), 32-bit index math hoisted out of the chunk loop.
+// The generic kernels above used one thread per (pixel, tap) with 8-byte accesses 2*C bytes apart and 64-bit divisions per element.
+struct F8 {
+  float v[8];
+};
+__device__ __forceinline__ F8 unpack8(uint4 r) {
+  F8 o;
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[i]));
+    o.v[2 * i] = f.x, o.v[2 * i + 1] = f.y;
+  }
+  return o;
+}
+__device__ __forceinline__ uint4 pack8(const F8& f) {
+  return make_uint4(pack_bf16(f.v[0], f.v[1]), pack_bf16(f.v[2], f.v[3]), pack_bf16(f.v[4], f.v[5]), pack_bf16(f.v[6], f.v[7]));
+}
+__device__ __forceinline__ void bn_relu8(F8& f, const float* __restrict__ sc, const float* __restrict__ sh, int c) {
+  const float4 a0 = ld4(sc + c), a1 = ld4(sc + c + 4), d0 = ld4(sh + c), d1 = ld4(sh + c + 4);
+  const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, d[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f.v[i] = fmaxf(f.v[i] * a[i] + d[i], 0.f);
+}
+
+__global__ void __launch_bounds__(256) im2col_rows_kernel(const bf16* __restrict__ in1, const float* __restrict__ sc1, const float* __restrict__ sh1,
+                                                          const bf16* __restrict__ in2, const float* __restrict__ sc2,
+                                                          const float* __restrict__ sh2, long batch_pitch, int pix_pitch, int H, int W, int C, int k,
+                                                          int s, int p, int Ho, int Wo, bf16* __restrict__ out, long ldo) {
+  const int b = blockIdx.x / Ho, oy = blockIdx.x - b * Ho;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int cpc = C >> 3, run = k * cpc;
+  const long in_b = (long)b * batch_pitch;
+  bf16* orow = out + ((long)b * Ho + oy) * Wo * ldo;
+  for (int u = warp; u < Wo * k; u += nwarps) {      // unit: (output pixel, kernel row)
+    const int ox = u / k, ky = u - ox * k;
+    const int iy = oy * s - p + ky, ix0 = ox * s - p;
+    const bool row_in = iy >= 0 && iy < H;
+    bf16* o = orow + (long)ox * ldo + (long)ky * k * C;
+    const long src_row = in_b + ((long)iy * W + ix0) * pix_pitch;
+    for (int j = lane; j < run; j += 32) {
+      const int kx = j / cpc, c = (j - kx * cpc) << 3;
+      const int ix = ix0 + kx;
+      uint4 r = make_uint4(0u, 0u, 0u, 0u);
+      if (row_in && ix >= 0 && ix < W) {
+        const long off = src_row + (long)kx * pix_pitch + c;
+        r = *reinterpret_cast<const uint4*>(in1 + off);
+        if (sc1 != nullptr || in2 != nullptr) {
+          F8 f = unpack8(r);
+          if (sc1 != nullptr) bn_relu8(f, sc1, sh1, c);
+          if (in2 != nullptr) {
+            F8 g = unpack8(*reinterpret_cast<const uint4*>(in2 + off));
+            if (sc2 != nullptr) bn_relu8(g, sc2, sh2, c);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f.v[i] += g.v[i];
+          }
+          r = pack8(f);
+        }
+      }
+      *reinterpret_cast<uint4*>(o + (j << 3)) = r;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) col2im_rows_kernel(const bf16* __restrict__ dcol, long ldc, const bf16* __restrict__ add, int H, int W, int C,
+                                                          int k, int s, int p, int Ho, int Wo, bf16* __restrict__ din, long batch_pitch,
+                                                          int pix_pitch) {
+  const int b = blockIdx.x / H, iy = blockIdx.x - b * H;
+  const int cpc = C >> 3;
+  const long row_off = (long)b * batch_pitch + (long)iy * W * pix_pitch;
+  const bf16* dc_b = dcol + (long)b * Ho * Wo * ldc;
+  const bool patches = (k == s && p == 0);           // non-overlapping patches (conv_proj): exactly one tap per pixel, a pure permutation
+  const int oy_p = iy / k, ky_p = iy - oy_p * k;
+  for (int j = threadIdx.x; j < W * cpc; j += blockDim.x) {
+    const int ix = j / cpc, c = (j - ix * cpc) << 3;
+    const long off = row_off + (long)ix * pix_pitch + c;
+    if (patches) {
+      const int ox = ix / k, kx = ix - ox * k;
+      uint4 r = make_uint4(0u, 0u, 0u, 0u);
+      if (oy_p < Ho && ox < Wo) r = *reinterpret_cast<const uint4*>(dc_b + ((long)oy_p * Wo + ox) * ldc + (long)(ky_p * k + kx) * C + c);
+      if (add != nullptr) {
+        F8 f = unpack8(r), g = unpack8(*reinterpret_cast<const uint4*>(add + off));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f.v[i] = g.v[i] + f.v[i];
+        r = pack8(f);
+      }
+      *reinterpret_cast<uint4*>(din + off) = r;
+      continue;
+    }
+    F8 acc;
+    if (add != nullptr) acc = unpack8(*reinterpret_cast<const uint4*>(add + off));
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
+    }
+    for (int ky = 0; ky < k; ++ky) {
+      const int ty = iy + p - ky;
+      if (ty < 0 || ty % s != 0) continue;
+      const int oy = ty / s;
+      if (oy >= Ho) continue;
+      for (int kx = 0; kx < k; ++kx) {
+        const int tx = ix + p - kx;
+        if (tx < 0 || tx % s != 0) continue;
+        const int ox = tx / s;
+        if (ox >= Wo) continue;
+        const F8 v = unpack8(*reinterpret_cast<const uint4*>(dc_b + ((long)oy * Wo + ox) * ldc + (long)(ky * k + kx) * C + c));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc.v[i] += v.v[i];
+      }
+    }
+    *reinterpret_cast<uint4*>(din + off) = pack8(acc);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ BatchNorm (training)
 // Per-channel reductions over a channels-last map y[P, C] (C <= 32, C % 4 == 0).  Thread = pixel; per-thread channel
 // accumulators, shared-memory tree over the CTA, one double atomic per channel per CTA.
@@ -461,7 +578,11 @@ extern "C" int vsx_im2col(const void* in1, const float* scale1, const float* shi
   } else {
     VSX_REQUIRE(C % 4 == 0 && pix_pitch % 4 == 0 && batch_pitch % 4 == 0 && ldo % 4 == 0, "vsx_im2col: channels-last needs C, pitches %% 4 == 0");
     VSX_REQUIRE(in_dtype == out_dtype, "vsx_im2col: channels-last input and output share the activation dtype");
-    if (out_dtype == VSX_BF16)
+    const bool al16 = ((reinterpret_cast<uintptr_t>(in1) | reinterpret_cast<uintptr_t>(in2) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (out_dtype == VSX_BF16 && C % 8 == 0 && pix_pitch % 8 == 0 && batch_pitch % 8 == 0 && ldo % 8 == 0 && al16 && pix_pitch < (1L << 30))
+      im2col_rows_kernel<<<B * Ho, 256, 0, ST>>>((const bf16*)in1, scale1, shift1, (const bf16*)in2, scale2, shift2, batch_pitch, (int)pix_pitch, H,
+                                                 W, C, k, stride, pad, Ho, Wo, (bf16*)out, ldo);
+    else if (out_dtype == VSX_BF16)
       im2col_kernel<bf16, bf16, false><<<grid, 256, 0, ST>>>((const bf16*)in1, scale1, shift1, (const bf16*)in2, scale2, shift2, batch_pitch,
                                                               pix_pitch, B, H, W, C, k, stride, pad, Ho, Wo, (bf16*)out, ldo);
     else
@@ -477,7 +598,11 @@ extern "C" int vsx_col2im(const void* dcol, long ldc, const void* add, int dtype
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   if (B == 0) return VSX_OK;
   const int grid = grid_for((long)B * H * W * C / 4);
-  if (dtype == VSX_BF16)
+  const bool al16 = ((reinterpret_cast<uintptr_t>(dcol) | reinterpret_cast<uintptr_t>(add) | reinterpret_cast<uintptr_t>(din)) & 15) == 0;
+  if (dtype == VSX_BF16 && C % 8 == 0 && ldc % 8 == 0 && pix_pitch % 8 == 0 && batch_pitch % 8 == 0 && al16 && pix_pitch < (1L << 30))
+    col2im_rows_kernel<<<B * H, 256, 0, ST>>>((const bf16*)dcol, ldc, (const bf16*)add, H, W, C, k, stride, pad, Ho, Wo, (bf16*)din, batch_pitch,
+                                              (int)pix_pitch);
+  else if (dtype == VSX_BF16)
     col2im_kernel<bf16><<<grid, 256, 0, ST>>>((const bf16*)dcol, ldc, (const bf16*)add, B, H, W, C, k, stride, pad, Ho, Wo, (bf16*)din,
                                               batch_pitch, pix_pitch);
   else
