@@ -60,6 +60,13 @@ int vsx_masked_ln_bwd(const void* dy, const void* dy2, int dtype, long lddy, con
                       const float* mean, const float* rstd, const float* gamma, const float* g_in, float* g_out,
                       long ldg, float* dgamma, float* dbeta, int rows, int C, int keep, int rows_per_sample,
                       int split_tokens, void* stream);
+/* vsx_masked_ln_bwd (no row remap) that ALSO writes cast_out = T(cast_scale[row / cast_rows_per_sample] * g_out) masked to the first
+ * cast_keep channels (zeros beyond) and accumulates its column sums into cast_colsum (may be NULL): the first step of the backward of
+ * the half block that consumes g_out next (vsx_scale_mask_cast fused into this kernel's store).  cast_scale may be NULL (1.0). */
+int vsx_masked_ln_bwd_cast(const void* dy, int dtype, long lddy, const float* x, long ldx, const float* mean, const float* rstd,
+                           const float* gamma, const float* g_in, float* g_out, long ldg, float* dgamma, float* dbeta, int rows, int C,
+                           int keep, void* cast_out, long ld_cast, const float* cast_scale, int cast_rows_per_sample, int cast_keep,
+                           float* cast_colsum, void* stream);
 
 /* ----------------------------------------------------------------------------------------------------
  * Tensor-core GEMM (tcgen05 / TMEM / TMA) -- replaces every nn.Linear on the path and its autograd:
@@ -189,6 +196,16 @@ typedef struct vsx_half_block_grad {
   void* d_act1;              /* bf16 scratch: dqkv [.., 3*H*D] | du [.., hidden] */
   void* d_act2;              /* bf16 scratch: d_o [.., H*D] (attention only) */
   float *d_ln_w, *d_ln_b, *d_w1, *d_b1, *d_w2, *d_b2;   /* fp32 parameter gradients, ACCUMULATED into (zero them once per step) */
+  /* Optional fusion across consecutive half blocks (single-segment, pre-norm, residual calls; all zero / NULL = off).
+   * df_ready != 0: `df` already holds the scaled / masked gradient of the branch output and d_b2 its column sums -- they were written by
+   * the call that produced g_out (its next_* fields) -- so the cast pass over g_out is skipped.
+   * next_df != NULL: the LayerNorm backward of THIS call also writes next_df = bf16(next_row_scale[next_scale_off + sample] * g_in) masked
+   * to next_keep channels and accumulates its column sums into next_d_b2: the `df` / `d_b2` of the half block that consumes g_in. */
+  int df_ready;
+  void* next_df;
+  const float* next_row_scale;
+  int next_scale_off, next_keep;
+  float* next_d_b2;
 } vsx_half_block_grad;
 int vsx_half_block_fwd(const vsx_half_block* d, void* stream);
 int vsx_half_block_bwd(const vsx_half_block_grad* d, void* stream);

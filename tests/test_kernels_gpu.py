@@ -460,3 +460,33 @@ def test_im2col_col2im_bf16(ops, shape):
         assert rel(got, want) < 4e-3
         if tok:
             assert torch.all(din[:, 0] == 0)          # the class-token row is not touched
+
+
+@pytest.mark.parametrize('C,keep,cast_keep', [(256, 256, 256), (512, 448, 384), (1024, 1024, 640), (64, 40, 64)])
+def test_ln_bwd_with_fused_cast(ops, C, keep, cast_keep):
+    """vsx_masked_ln_bwd_cast == vsx_masked_ln_bwd followed by vsx_scale_mask_cast on its output (the fused kernel where the bulk-copy
+    variant applies, the two-launch fallback otherwise: keep = 40 is not a multiple of 8)."""
+    B, N = 3, 65
+    rows = B * N
+    g = torch.Generator(device='cuda').manual_seed(C + keep)
+    dy = torch.randn(rows, C, device='cuda', generator=g).to(torch.bfloat16)
+    x = torch.randn(rows, C, device='cuda', generator=g)
+    g_in = torch.randn(rows, C, device='cuda', generator=g)
+    gamma = 1 + 0.1 * torch.randn(C, device='cuda', generator=g)
+    scale = torch.rand(B + 2, device='cuda', generator=g) + 0.5
+    mean = x[:, :keep].mean(1).contiguous()
+    rstd = (1.0 / torch.sqrt(x[:, :keep].var(1, unbiased=False) + 1e-6)).contiguous()
+    ref_g = torch.empty(rows, C, device='cuda')
+    dgam, dbet = torch.zeros(C, device='cuda'), torch.zeros(C, device='cuda')
+    ops.masked_ln_bwd(dy, C, x, C, mean, rstd, gamma, g_in, ref_g, C, dgam, dbet, rows, C, keep)
+    ref_cast = torch.empty(rows, C, device='cuda', dtype=torch.bfloat16)
+    ref_cs = torch.zeros(C, device='cuda')
+    ops.scale_mask_cast(ref_g, C, scale, N, cast_keep, ref_cast, C, rows, C, scale_off=1, colsum=ref_cs)
+    got_g = torch.empty(rows, C, device='cuda')
+    got_cast = torch.full((rows, C), float('nan'), device='cuda', dtype=torch.bfloat16)
+    dgam2, dbet2, got_cs = torch.zeros(C, device='cuda'), torch.zeros(C, device='cuda'), torch.zeros(C, device='cuda')
+    ops.call('masked_ln_bwd_cast', dy, ops.BF16, C, x, C, mean, rstd, gamma, g_in, got_g, C, dgam2, dbet2, rows, C, keep, got_cast, C, (scale, 1), N,
+             cast_keep, got_cs)
+    assert torch.equal(got_g, ref_g) and torch.equal(got_cast, ref_cast)
+    assert rel(dgam2, dgam) < 1e-5 and rel(dbet2, dbet) < 1e-5 and rel(got_cs, ref_cs) < 1e-5
+    assert torch.all(got_cast[:, cast_keep:] == 0)

@@ -31,6 +31,7 @@ SIGNATURES = {
     'vsx_abi_version': [],
     'vsx_device_ok': [_i],
     'vsx_masked_ln_fwd': [_p, _l, _p, _p, _p, _p, _i, _l, _p, _p, _i, _i, _i, _f, _i, _i, _p],
+    'vsx_masked_ln_bwd_cast': [_p, _i, _l, _p, _l, _p, _p, _p, _p, _p, _l, _p, _p, _i, _i, _i, _p, _l, _p, _i, _i, _p, _p],
     'vsx_masked_ln_bwd': [_p, _p, _i, _l, _p, _l, _p, _p, _p, _p, _p, _l, _p, _p, _i, _i, _i, _i, _i, _p],
     'vsx_gemm': [C.POINTER(GemmDesc), _p],
     'vsx_attn_fwd': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p],
@@ -87,7 +88,8 @@ class HalfBlock(C.Structure):
 
 class HalfBlockGrad(C.Structure):
     _fields_ = [('fwd', HalfBlock), ('g_out', _p), ('g_in', _p), ('df', _p), ('dxn', _p), ('d_act1', _p), ('d_act2', _p),
-                ('d_ln_w', _p), ('d_ln_b', _p), ('d_w1', _p), ('d_b1', _p), ('d_w2', _p), ('d_b2', _p)]
+                ('d_ln_w', _p), ('d_ln_b', _p), ('d_w1', _p), ('d_b1', _p), ('d_w2', _p), ('d_b2', _p),
+                ('df_ready', _i), ('next_df', _p), ('next_row_scale', _p), ('next_scale_off', _i), ('next_keep', _i), ('next_d_b2', _p)]
 
 
 _lib = None

@@ -514,23 +514,68 @@ def native_half_forward(meta, x, params):
     return out, (ws16, ws32)
 
 
-def native_half_backward(meta, g_out, saved, x, params):
-    ws16, ws32 = saved
+FUSE_CAST = True      # LayerNorm backward of half block i also writes the scaled / masked bf16 gradient half block i-1 starts from
+
+
+def _fusable(meta):
+    """Single active segment covering the batch, pre-norm, residual: the shape of every half block of a 1-arch step."""
+    if len(meta.segs) != 1:
+        return False
+    return bool(meta.segs[0].active) and meta.residual and meta.pre_norm
+
+
+def _half_backward_buffers(meta, x, params):
     B, N, C = x.shape
     M = B * N
     attn = meta.kind == 'attn'
     inner = 3 * meta.H * meta.D if attn else meta.F
     a2 = meta.H * meta.D if attn else 0
-    dev = x.device
+    sc = torch.empty(M * (2 * C + inner + a2), device=x.device, dtype=torch.bfloat16)      # [df | dxn | d_act1 | d_act2]
+    return sc, zeros_like_many(*params)
+
+
+def native_half_backward(meta, g_out, saved, x, params, ctx=None):
+    ws16, ws32 = saved
+    B, N, C = x.shape
+    M = B * N
+    attn = meta.kind == 'attn'
+    inner = 3 * meta.H * meta.D if attn else meta.F
     g_in = torch.empty_like(x)
-    sc = torch.empty(M * (2 * C + inner + a2), device=dev, dtype=torch.bfloat16)      # [df | dxn | d_act1 | d_act2]
-    grads = zeros_like_many(*params)
+    pre = getattr(ctx, 'prefetched', None) if ctx is not None else None
+    df_ready = 0
+    if pre is not None:
+        # buffers were allocated (in this order, so gradient-pool offsets are unchanged) by the half block that produced g_out
+        sc, grads, g_ref, g_ver = pre
+        ctx.prefetched = None
+        if g_out.data_ptr() == g_ref.data_ptr() and g_out._version == g_ver and g_out.shape == g_ref.shape:
+            df_ready = 1
+        else:                       # the gradient was re-materialised or accumulated into: redo the cast from the tensor we were given
+            grads[5].zero_()
+    else:
+        sc, grads = _half_backward_buffers(meta, x, params)
     fd, _ = _half_desc(meta, x, None, params, ws16, ws32)
     ps = sc.data_ptr()
+    nxt = (None, None, 0, 0, None)
+    prev = getattr(ctx, 'prev', None) if ctx is not None else None
+    if FUSE_CAST and prev is not None and _fusable(meta) and _fusable(prev.meta) and prev.saved is not None:
+        px, *pparams = prev.saved_tensors
+        if px.shape == x.shape:
+            psc, pgrads = _half_backward_buffers(prev.meta, px, pparams)
+            pm = prev.meta
+            rs = pm.row_scale
+            nxt = (psc.data_ptr(), None if rs is None else rs.data_ptr(), pm.scale_off if rs is not None else 0, pm.segs[0].ck,
+                   pgrads[5].data_ptr())
+            prev.prefetched = (psc, pgrads, g_in, None)
     d = _lib.HalfBlockGrad(fd, g_out.data_ptr(), g_in.data_ptr(), ps, ps + 2 * M * C, ps + 4 * M * C, (ps + 2 * M * (2 * C + inner)) if attn else None,
-                           *[t.data_ptr() for t in grads])
+                           *[t.data_ptr() for t in grads], df_ready, *nxt)
     ops._ck(_lib.lib().vsx_half_block_bwd(_C.byref(d), ops._stream()))
+    if nxt[0] is not None:
+        psc, pgrads, g_ref, _ = prev.prefetched
+        prev.prefetched = (psc, pgrads, g_ref, g_in._version)
     return g_in, tuple(grads)
+
+
+_chain_tail = None     # (data_ptr of the last native half block's output, its ctx, shape, version)
 
 
 class HalfBlockFn(torch.autograd.Function):
@@ -549,6 +594,13 @@ class HalfBlockFn(torch.autograd.Function):
             out, saved = fwd(meta, x, *params)
         ctx.meta, ctx.saved, ctx.native = meta, saved, native
         ctx.save_for_backward(x, *params)
+        # chain of consecutive half blocks (this one consumes exactly what the previous one produced): lets the backward of this node
+        # hand the previous node its scaled / masked gradient copy (FUSE_CAST)
+        global _chain_tail
+        ctx.prev = ctx.prefetched = None
+        if native and _chain_tail is not None and _chain_tail[0] == x.data_ptr() and _chain_tail[2] == x.shape and _chain_tail[3] == x._version:
+            ctx.prev = _chain_tail[1]
+        _chain_tail = (out.data_ptr(), ctx, out.shape, out._version) if (native and any(ctx.needs_input_grad)) else None
         return out
 
     @staticmethod
@@ -556,9 +608,9 @@ class HalfBlockFn(torch.autograd.Function):
         x, *params = ctx.saved_tensors
         g = g if g.is_contiguous() else g.contiguous()
         if ctx.native:
-            g_in, pg = native_half_backward(ctx.meta, g, ctx.saved, x, params)
+            g_in, pg = native_half_backward(ctx.meta, g, ctx.saved, x, params, ctx)
         else:
             bwd = attn_half_backward if ctx.meta.kind == 'attn' else mlp_half_backward
             g_in, pg = bwd(ctx.meta, g, ctx.saved, x, *params)
-        ctx.saved = None
+        ctx.saved = ctx.prev = None
         return (None, g_in) + tuple(pg)

@@ -183,6 +183,9 @@ extern "C" int vsx_half_block_bwd(const vsx_half_block_grad* b, void* stream) {
   HB_CHECK(check_desc(h, "vsx_half_block_bwd"));
   const int N = h->tokens, C = h->width, H = h->heads, D = h->head_dim, HD = H * D, F = h->hidden;
   const float scale = h->kind == VSX_HALF_ATTN ? 1.0f / sqrtf((float)D) : 0.f;
+  VSX_REQUIRE((!b->df_ready && b->next_df == nullptr) || (h->num_segments == 1 && h->segments[0].active && h->segments[0].b0 == 0 &&
+                                                           h->segments[0].b1 == h->batch && h->pre_norm && h->residual),
+              "vsx_half_block_bwd: df_ready / next_df need a single active segment covering the batch, pre_norm and residual");
   // phase 1: dropped layers pass the gradient through; gradient of the branch output of every active segment: drop-path scale,
   // output mask, cast -- its column sums are the bias gradient of proj / fc2
   for (int si = 0; si < h->num_segments; ++si) {
@@ -195,6 +198,7 @@ extern "C" int vsx_half_block_bwd(const vsx_half_block_grad* b, void* stream) {
       continue;
     }
     const int ck = h->residual ? s.out_keep : C;
+    if (b->df_ready) continue;               // written by the LayerNorm backward of the call that produced g_out
     HB_CHECK(vsx_scale_mask_cast(b->g_out + r0 * C, C, (h->residual && h->row_scale != nullptr) ? h->row_scale + h->scale_off + s.b0 : nullptr, N, ck,
                                  B16(b->df) + r0 * C, VSX_BF16, C, rows, C, b->d_b2, stream));
   }
@@ -284,6 +288,12 @@ extern "C" int vsx_half_block_bwd(const vsx_half_block_grad* b, void* stream) {
   }
   if (h->pre_norm) {
     HB_CHECK(for_active([&](const SegView& v) -> int {
+      if (b->next_df != nullptr)
+        return vsx_masked_ln_bwd_cast(B16(b->dxn) + v.r0 * C, VSX_BF16, C, h->x + v.r0 * C, C, h->mean + v.r0, h->rstd + v.r0, h->ln_w,
+                                      h->residual ? b->g_out + v.r0 * C : nullptr, b->g_in + v.r0 * C, C, b->d_ln_w, b->d_ln_b, v.rows, C,
+                                      v.s->embed_keep, B16(b->next_df) + v.r0 * C, C,
+                                      b->next_row_scale != nullptr ? b->next_row_scale + b->next_scale_off + v.s->b0 : nullptr, N, b->next_keep,
+                                      b->next_d_b2, stream);
       return vsx_masked_ln_bwd(B16(b->dxn) + v.r0 * C, nullptr, VSX_BF16, C, h->x + v.r0 * C, C, h->mean + v.r0, h->rstd + v.r0, h->ln_w,
                                h->residual ? b->g_out + v.r0 * C : nullptr, b->g_in + v.r0 * C, C, b->d_ln_w, b->d_ln_b, v.rows, C, v.s->embed_keep, 0, 0,
                                stream);

@@ -177,12 +177,23 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T* __restri
 // cp.async.bulk copies of the NEXT row (dy, x, g_in: up to 10 B/channel) into one slot while the warp works on the other, completion
 // on one mbarrier per slot.  The per-warp register tile (d, z, g_in) of the plain kernel disappears -- rows are re-read from shared
 // memory -- so occupancy is no longer register-bound at C = 512 / 1024, and ~100 KB of loads are in flight per SM.
-template <int NV, typename T>
+// CAST: the kernel also emits what the NEXT half block's backward starts with -- cast.out = T(cast.scale[row / rps] * g_out) masked to the first
+// cast.keep channels, and its column sums (that block's proj / fc2 bias gradient) -- so the fp32 gradient is not read back by a separate
+// vsx_scale_mask_cast launch.
+struct LnCast {
+  void* out;
+  long ld;
+  const float* scale;
+  int rps, keep;
+  float* colsum;
+};
+
+template <int NV, typename T, bool CAST>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_bulk_kernel(const T* __restrict__ dy, long lddy, const float* __restrict__ x, long ldx,
                                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                      const float* __restrict__ gamma, const float* __restrict__ g_in,
                                                                      float* __restrict__ g_out, long ldg, float* __restrict__ dgamma,
-                                                                     float* __restrict__ dbeta, int rows, int C, int keep) {
+                                                                     float* __restrict__ dbeta, int rows, int C, int keep, const LnCast cast) {
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t xb = (uint32_t)keep * 4, gb = g_in != nullptr ? (uint32_t)C * 4 : 0u, db = (uint32_t)keep * (uint32_t)sizeof(T);
@@ -205,15 +216,19 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_bulk_kernel(const T* __r
     bulk_g2s(dst + xb + gb, dy + r * lddy, db, bar);
   };
   const float inv_keep = 1.0f / (float)keep;
-  float4 ag[NV], ab[NV];
+  float4 ag[NV], ab[NV], ac[CAST ? NV : 1];
 #pragma unroll
   for (int i = 0; i < NV; ++i) ag[i] = make_float4(0.f, 0.f, 0.f, 0.f), ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < (CAST ? NV : 1); ++i) ac[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   long r = (long)blockIdx.x * LN_WARPS + warp;
   if (r < rows && lane == 0) issue(r, 0);
   int it = 0;
   for (; r < rows; r += stride, ++it) {
     const int sl = it & 1;
     if (r + stride < rows && lane == 0) issue(r + stride, sl ^ 1);      // the other slot was fully consumed one iteration ago
+    float cs = 1.0f;
+    if (CAST && cast.scale != nullptr) cs = __ldg(cast.scale + r / cast.rps);
     mbar_wait(sl ? bar1 : bar0, (uint32_t)(it >> 1) & 1u);
     const float* xs = reinterpret_cast<const float*>(my + (size_t)sl * slot);
     const float* gs = reinterpret_cast<const float*>(my + (size_t)sl * slot + xb);
@@ -250,16 +265,23 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_bulk_kernel(const T* __r
           o.w += (d0.w * gm.w - s1 - (xv.w - mu) * rs * s2) * rs;
         }
         st4(go + c, o);
+        if (CAST) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c < cast.keep) v = make_float4(o.x * cs, o.y * cs, o.z * cs, o.w * cs);
+          st4(static_cast<T*>(cast.out) + r * cast.ld + c, v);
+          ac[i].x += v.x, ac[i].y += v.y, ac[i].z += v.z, ac[i].w += v.w;
+        }
       }
     }
     __syncwarp();      // every lane is done with this slot before lane 0 re-arms it (two iterations from now it is the target again)
   }
   __shared__ float4 red[LN_WARPS][NV * 32];
-  for (int pass = 0; pass < 2; ++pass) {
-    float* dst = pass == 0 ? dgamma : dbeta;
-    if (pass == 1) __syncthreads();
+  const int npass = (CAST && cast.colsum != nullptr) ? 3 : 2;
+  for (int pass = 0; pass < npass; ++pass) {
+    float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : cast.colsum);
+    if (pass >= 1) __syncthreads();
 #pragma unroll
-    for (int i = 0; i < NV; ++i) red[warp][i * 32 + lane] = pass == 0 ? ag[i] : ab[i];
+    for (int i = 0; i < NV; ++i) red[warp][i * 32 + lane] = pass == 0 ? ag[i] : (pass == 1 ? ab[i] : ac[CAST ? i : 0]);
     __syncthreads();
     for (int q = threadIdx.x; q < NV * 32; q += LN_WARPS * 32) {
       float4 t = red[0][q];
@@ -268,7 +290,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_bulk_kernel(const T* __r
         const float4 u = red[w][q];
         t.x += u.x, t.y += u.y, t.z += u.z, t.w += u.w;
       }
-      red_add4(dst + q * 4, t, q * 4, keep);
+      red_add4(dst + q * 4, t, q * 4, pass == 2 ? cast.keep : keep);
     }
   }
 }
@@ -396,7 +418,7 @@ int ln_fwd_dispatch(const float* x, long ldx, const float* gamma, const float* b
 template <typename T>
 int ln_bwd_dispatch(const void* dy, const void* dy2, long lddy, const float* x, long ldx, const float* mean, const float* rstd,
                     const float* gamma, const float* g_in, float* g_out, long ldg, float* dgamma, float* dbeta, int rows, int C,
-                    int keep, int rps, int split, cudaStream_t st) {
+                    int keep, int rps, int split, cudaStream_t st, const LnCast* cast = nullptr, bool* cast_done = nullptr) {
   const int nv = ceil_div(C, 128);
   // bulk-copy prefetch variant: whole kept prefix in 16-byte units, no final-norm row remap, 16-byte aligned rows
   const size_t esz = sizeof(T);
@@ -411,11 +433,22 @@ int ln_bwd_dispatch(const void* dy, const void* dy2, long lddy, const float* x, 
   case NV: {                                                                                                                        \
     static bool cfg = false;                                                                                                        \
     if (!cfg) {                                                                                                                     \
-      cudaFuncSetAttribute(ln_bwd_bulk_kernel<NV, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096 * NV - 512);   \
+      cudaFuncSetAttribute(ln_bwd_bulk_kernel<NV, T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096 * NV - 512);   \
       cfg = true;                                                                                                                   \
     }                                                                                                                               \
-    ln_bwd_bulk_kernel<NV, T><<<gridb, LN_WARPS * 32, smem, st>>>((const T*)dy, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg,   \
-                                                                   dgamma, dbeta, rows, C, keep);                                    \
+    if (cast != nullptr && cast->ld % 4 == 0) {                                                                                      \
+      static bool cfg2 = false;                                                                                                     \
+      if (!cfg2) {                                                                                                                  \
+        cudaFuncSetAttribute(ln_bwd_bulk_kernel<NV, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096 * NV - 512); \
+        cfg2 = true;                                                                                                                \
+      }                                                                                                                             \
+      ln_bwd_bulk_kernel<NV, T, true><<<gridb, LN_WARPS * 32, smem, st>>>((const T*)dy, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, \
+                                                                           dgamma, dbeta, rows, C, keep, *cast);                    \
+      if (cast_done != nullptr) *cast_done = true;                                                                                  \
+      return check_launch("vsx_masked_ln_bwd");                                                                                     \
+    }                                                                                                                               \
+    ln_bwd_bulk_kernel<NV, T, false><<<gridb, LN_WARPS * 32, smem, st>>>((const T*)dy, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, \
+                                                                          dgamma, dbeta, rows, C, keep, LnCast{});                  \
     return check_launch("vsx_masked_ln_bwd");                                                                                       \
   }
     switch (nv) {
@@ -479,4 +512,28 @@ extern "C" int vsx_masked_ln_bwd(const void* dy, const void* dy2, int dtype, lon
                                   rows_per_sample, split_tokens, st);
   set_error("vsx_masked_ln_bwd: bad dtype %d", dtype);
   return VSX_ERR_ARG;
+}
+
+// LayerNorm backward that also emits the scaled / masked low-precision copy of g_out (and its column sums) the next half block's
+// backward starts from.  Falls back to vsx_masked_ln_bwd + vsx_scale_mask_cast when the fused kernel does not apply.
+extern "C" int vsx_masked_ln_bwd_cast(const void* dy, int dtype, long lddy, const float* x, long ldx, const float* mean, const float* rstd,
+                                      const float* gamma, const float* g_in, float* g_out, long ldg, float* dgamma, float* dbeta, int rows, int C,
+                                      int keep, void* cast_out, long ld_cast, const float* cast_scale, int cast_rows_per_sample, int cast_keep,
+                                      float* cast_colsum, void* stream) {
+  VSX_REQUIRE(rows >= 0 && C > 0 && keep > 0 && keep <= C, "vsx_masked_ln_bwd_cast: need 0 < keep <= C (keep=%d C=%d)", keep, C);
+  VSX_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0 && ldg % 4 == 0 && ld_cast % 4 == 0, "vsx_masked_ln_bwd_cast: C and pitches must be multiples of 4");
+  VSX_REQUIRE(cast_out != nullptr && cast_keep >= 0 && cast_keep <= C, "vsx_masked_ln_bwd_cast: bad cast output / keep");
+  VSX_REQUIRE(dtype == VSX_BF16 || dtype == VSX_F32, "vsx_masked_ln_bwd_cast: bad dtype %d", dtype);
+  if (rows == 0) return VSX_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int rps = cast_rows_per_sample > 0 ? cast_rows_per_sample : 1;
+  const LnCast cast{cast_out, ld_cast, cast_scale, rps, cast_keep, cast_colsum};
+  bool done = false;
+  int rc;
+  if (dtype == VSX_BF16)
+    rc = ln_bwd_dispatch<bf16>(dy, nullptr, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, dgamma, dbeta, rows, C, keep, 0, 0, st, &cast, &done);
+  else
+    rc = ln_bwd_dispatch<float>(dy, nullptr, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, dgamma, dbeta, rows, C, keep, 0, 0, st, &cast, &done);
+  if (rc != VSX_OK || done) return rc;
+  return vsx_scale_mask_cast(g_out, ldg, cast_scale, rps, cast_keep, cast_out, dtype, ld_cast, rows, C, cast_colsum, stream);
 }
