@@ -275,13 +275,14 @@ int vsx_conv3x3_wgrad(const void* dy, const void* in, const float* in_scale, con
  * (csrc/conv3x3_tma.cu; C == 24, H and W multiples of 16). */
 int vsx_conv3x3_force_impl(int impl);
 
-/* Token assembly: x0[b,t,:] = mask * ((t == 0 ? tokens : patches[b,t-1]) + pos_embed[t])  -- replaces cat / expand /
+/* Token assembly: x0[b,t,:] = mask * ((t < num_tokens ? tokens[t] : patches[b,t-num_tokens]) + pos_embed[t])  -- replaces cat / expand /
  * add / embed ChannelDrop at nets/vit_sr_supernet.py:399-407; backward gives dpatches (activation dtype), and
- * ACCUMULATES dpos_embed [N,C] and dtokens [C]. */
+ * ACCUMULATES dpos_embed [N,C] and dtokens [num_tokens,C] (1 class token; 2 with the distillation token,
+ * nets/vision_transformer_supernet.py:82-84). */
 int vsx_embed_assemble(const float* patches, const float* tokens, const float* pos, float* x0, int batch,
-                       int tokens_per_sample, int C, int keep, void* stream);
+                       int tokens_per_sample, int C, int keep, int num_tokens, void* stream);
 int vsx_embed_assemble_bwd(const float* g, void* dpatches, int dtype, float* dpos, float* dtokens, int batch,
-                           int tokens_per_sample, int C, int keep, void* stream);
+                           int tokens_per_sample, int C, int keep, int num_tokens, void* stream);
 
 /* SR block combine (nets/vit_sr_supernet.py:131-166): y = mask2 * (cat(tok, conv + pos) + zero-pad(cat(x[:,0], avgpool2x2(x[:,1:])))).
  * Backward: dconv / dtok (activation dtype), dpos ACCUMULATED, and the residual-path gradient gres [B,1+g*g,C1]. */

@@ -71,3 +71,19 @@ EVO_CANDIDATES = {
     'odd':     _sub(44, 100, 200, [(1, 128, 1), (2, 128, 0), (1, 128, 1), (2, 256, 0), (2, 256, 0), (2, 256, 1), (3, 384, 0)]),
     'mixed':   _sub(64, 80, 256, [(2, 64, 1), (2, 96, 1), (2, 192, 1), (1, 256, 1), (1, 128, 1), (4, 256, 1), (2, 512, 1)]),
 }
+
+
+# Patch-16 super-network with a distillation token (nets/vision_transformer_supernet.py): N = 196 + 2 tokens,
+# head dims 32 and 64 (both attention kernels), a droppable block and a BypassBlock.
+VIT16_DEF = ((0, 64),
+             (1, (64, 2, 32), (64, 128), 1), (1, (64, 1, 64), (64, 192), 1), (1, (64, 2, 32), (64, 128), 0), (1, (64, 2, 64), (64, 128), 1),
+             (2, 64, 1000))
+VIT16_SPACE = [np.array([64, 56, 40]),
+               _blk([64, 32], [128, 96, 64]), _blk([64], [192, 128], [64, 64, 0]), _blk([64, 32], [128, 64]), _blk([128, 64], [128, 96]),
+               None]
+VIT16_CASES = {
+    'vit16_multi': dict(supernet=True, batch=8, epa=2, warmup=0, epoch=0, seed=21),
+    'vit16_single': dict(supernet=True, batch=4, epa=2, warmup=0, epoch=2, seed=22, single=True),
+    'vit16_eval': dict(supernet=True, batch=4, epa=2, warmup=0, epoch=0, seed=23, train=False),
+    'vit16_dense': dict(supernet=False, batch=4, epa=None, warmup=0, epoch=0, seed=24),
+}

@@ -59,7 +59,7 @@ def test_state_dict_surface_matches_reference_layout():
         assert all(tuple(sd[k].shape) == tuple(sh[k]) for k in sd)
     assert len(sd) == 258                                    # SURVEY.md §8b probe for sr_tiny_mh
     assert m.no_weight_decay() == {'tokens'}
-    assert len(list_models()) == 9
+    assert len([n for n in list_models() if n.startswith('flexible_vit_sr_')]) == 9
 
 
 @pytest.mark.parametrize('name', [n for n, c in CASES.items() if c['supernet'] and c.get('train', True)])
@@ -179,3 +179,33 @@ def test_subnet_extents_of_search_candidates():
     bad[8] = (1, (224, 3, 32), (224, 384), 1)               # head_dim differs from the super-network's 64
     with pytest.raises(ValueError):
         m.subnet_extents(tuple(bad))
+
+
+def test_vit16_module_surface():
+    """nets/vision_transformer_supernet.py drop-in: factories, state_dict keys / shapes (= the reference's, checked against it in
+    oracle/make_golden_vit16.py), no_weight_decay, draw order."""
+    import numpy as np
+    import os
+    import torch
+    from oracle import vit_res_oracle as O
+    from oracle.cases import VIT16_CASES, VIT16_DEF, VIT16_SPACE
+    from vit_search_b200.nets import create_model, list_models
+    for n in ('flexible_vit_patch16_224', 'flexible_vit_patch16_224_supernet', 'flexible_vit_patch16_192', 'flexible_vit_patch16_192_supernet'):
+        assert n in list_models()
+    case = VIT16_CASES['vit16_multi']
+    m = create_model('flexible_vit_patch16_224_supernet', network_def=VIT16_DEF, num_classes=1000, num_channels_to_keep=VIT16_SPACE,
+                     example_per_arch=case['epa'], num_warmup_epochs=case['warmup'])
+    shapes = O.param_shapes(VIT16_DEF, num_tokens=2, patch_output=False, patch_size=16)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(shapes.keys())
+    assert all(tuple(sd[k].shape) == tuple(shapes[k]) for k in sd)
+    assert m.no_weight_decay() == {'pos_embed', 'tokens'} and m.num_tokens == 2
+    m.set_epoch(case['epoch'])
+    m.train()
+    torch.manual_seed(case['seed'])
+    keeps = m.sample_keeps(case['batch'])
+    flat = [k[n] for k in keeps for n in ('embed', 'attn', 'layer', 'mlp') if n in k]
+    G = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'vit16_multi.npz'))
+    assert flat == G['keeps'].tolist()
+    m192 = create_model('flexible_vit_patch16_192', network_def=VIT16_DEF, num_classes=1000)
+    assert m192.pos_embed.shape == (1, 144 + 2, 64)

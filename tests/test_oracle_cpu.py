@@ -150,3 +150,32 @@ def test_candidate_evaluation_oracle_vs_reference_golden():
     sub = O.sub_state_dict(sup, O.param_shapes(EVO_CANDIDATES['narrow']))
     w, ws = sup['blocks.1.attn.qkv.weight'], sub['blocks.1.attn.qkv.weight']
     assert ws.shape == (96, 56) and torch.equal(ws[32:64], w[64:96, :56]) and torch.equal(ws[64:96], w[128:160, :56])
+
+
+def test_vit16_oracle_vs_reference_golden():
+    """Patch-16 super-network with a distillation token: oracle forward (+ sub-architecture draws) against the reference's outputs."""
+    import numpy as np
+    import os
+    import torch
+    from oracle import vit_res_oracle as O
+    from oracle.cases import VIT16_CASES, VIT16_DEF, VIT16_SPACE
+    shapes = O.param_shapes(VIT16_DEF, num_tokens=2, patch_output=False, patch_size=16)
+    p = O.keyed_fill(shapes, seed=5)
+    for name, case in VIT16_CASES.items():
+        G = np.load(os.path.join(os.path.dirname(__file__), 'golden', name + '.npz'))
+        x, _, _ = O.synthetic_batch(case['batch'], seed=99)
+        train = case.get('train', True)
+        keeps = None
+        if case['supernet'] and train:
+            smp = O.Sampler(VIT16_DEF, VIT16_SPACE, case['epa'], case['warmup'], case.get('single', False))
+            smp.set_epoch(case['epoch'])
+            torch.manual_seed(case['seed'])
+            keeps = smp.sample(case['batch'])
+            flat = [k[n] for k in keeps for n in ('embed', 'attn', 'layer', 'mlp') if n in k]
+            assert flat == G['keeps'].tolist()
+        with torch.no_grad():
+            cls, dst = O.forward(p, VIT16_DEF, x, keeps, training=train, patch_output=False, num_tokens=2,
+                                 eval_full_mask=case['supernet'] and not train)
+        for got, want in ((cls, G['cls']), (dst, G['dst'])):
+            want = torch.from_numpy(want)
+            assert ((got - want).norm() / want.norm()).item() < 2e-6, name

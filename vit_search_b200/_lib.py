@@ -57,8 +57,8 @@ SIGNATURES = {
     'vsx_bn_bwd_apply': [_p, _p, _i, _l, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     'vsx_conv3x3': [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p],
     'vsx_conv3x3_wgrad': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
-    'vsx_embed_assemble': [_p, _p, _p, _p, _i, _i, _i, _i, _p],
-    'vsx_embed_assemble_bwd': [_p, _p, _i, _p, _p, _i, _i, _i, _i, _p],
+    'vsx_embed_assemble': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    'vsx_embed_assemble_bwd': [_p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p],
     'vsx_sr_combine': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     'vsx_sr_combine_bwd': [_p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _p],
     'vsx_soft_ce': [_p, _l, _p, _l, _i, _i, _f, _f, _p, _p, _l, _p],

@@ -395,7 +395,7 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restric
 // ------------------------------------------------------------------------------------------------ embedding assembly
 // x0[b, t, c] = [c < keep] * ((t == 0 ? tokens[c] : patches[b, t-1, c]) + pos[t, c])        (vit_sr_supernet.py:399-407)
 __global__ void embed_assemble_kernel(const float* __restrict__ patches, const float* __restrict__ tokens, const float* __restrict__ pos,
-                                      float* __restrict__ x0, int nb, int N, int C, int keep) {
+                                      float* __restrict__ x0, int nb, int N, int C, int keep, int T) {
   const int c4n = C / 4;
   const long total = (long)nb * N * c4n;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -405,7 +405,7 @@ __global__ void embed_assemble_kernel(const float* __restrict__ patches, const f
     const long b = row / N;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < keep) {
-      const float4 a = t == 0 ? ld4(tokens + c) : ld4(patches + (b * (N - 1) + (t - 1)) * C + c);
+      const float4 a = t < T ? ld4(tokens + (long)t * C + c) : ld4(patches + (b * (N - T) + (t - T)) * C + c);
       const float4 q = ld4(pos + (long)t * C + c);
       v = make_float4(a.x + q.x, a.y + q.y, a.z + q.z, a.w + q.w);
       if (c + 1 >= keep) v.y = 0.f;
@@ -416,11 +416,11 @@ __global__ void embed_assemble_kernel(const float* __restrict__ patches, const f
   }
 }
 
-// Backward: dpatches[b,p,c] = [c<keep] g[b,1+p,c] (cast to T);  dpos[t,c] += sum_b [c<keep] g[b,t,c];  dtokens[c] += sum_b g[b,0,c].
+// Backward: dpatches[b,p,c] = [c<keep] g[b,NT+p,c] (cast to T);  dpos[t,c] += sum_b [c<keep] g[b,t,c];  dtokens[t,c] += sum_b g[b,t,c], t < NT.
 // One thread per (t, 4 channels) loops over the segment's samples -> no atomics within a segment.
 template <typename T>
 __global__ void embed_assemble_bwd_kernel(const float* __restrict__ g, T* __restrict__ dpatches, float* __restrict__ dpos,
-                                          float* __restrict__ dtokens, int nb, int N, int C, int keep) {
+                                          float* __restrict__ dtokens, int nb, int N, int C, int keep, int NT) {
   const int c4n = C / 4;
   const long total = (long)N * c4n;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -438,13 +438,14 @@ __global__ void embed_assemble_bwd_kernel(const float* __restrict__ g, T* __rest
         if (c + 2 >= keep) v.z = 0.f;
         if (c + 3 >= keep) v.w = 0.f;
       }
-      if (t > 0) st4(dpatches + ((long)b * (N - 1) + (t - 1)) * C + c, v);
+      if (t >= NT) st4(dpatches + ((long)b * (N - NT) + (t - NT)) * C + c, v);
       acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
     }
     float* dp = dpos + (long)t * C + c;
     atomicAdd(dp, acc.x), atomicAdd(dp + 1, acc.y), atomicAdd(dp + 2, acc.z), atomicAdd(dp + 3, acc.w);
-    if (t == 0) {
-      atomicAdd(dtokens + c, acc.x), atomicAdd(dtokens + c + 1, acc.y), atomicAdd(dtokens + c + 2, acc.z), atomicAdd(dtokens + c + 3, acc.w);
+    if (t < NT) {
+      float* dt_ = dtokens + (long)t * C + c;
+      atomicAdd(dt_, acc.x), atomicAdd(dt_ + 1, acc.y), atomicAdd(dt_ + 2, acc.z), atomicAdd(dt_ + 3, acc.w);
     }
   }
 }
@@ -652,23 +653,26 @@ extern "C" int vsx_bn_bwd_apply(const void* da, const void* y, int dtype, long P
 }
 
 extern "C" int vsx_embed_assemble(const float* patches, const float* tokens, const float* pos, float* x0, int batch, int tokens_per_sample,
-                                  int C, int keep, void* stream) {
+                                  int C, int keep, int num_tokens, void* stream) {
   VSX_REQUIRE(C % 4 == 0 && keep >= 0 && keep <= C, "vsx_embed_assemble: bad C/keep");
+  VSX_REQUIRE(num_tokens >= 1 && num_tokens < tokens_per_sample, "vsx_embed_assemble: bad num_tokens %d", num_tokens);
   if (batch == 0) return VSX_OK;
-  embed_assemble_kernel<<<grid_for((long)batch * tokens_per_sample * C / 4), 256, 0, ST>>>(patches, tokens, pos, x0, batch, tokens_per_sample, C, keep);
+  embed_assemble_kernel<<<grid_for((long)batch * tokens_per_sample * C / 4), 256, 0, ST>>>(patches, tokens, pos, x0, batch, tokens_per_sample, C, keep,
+                                                                                            num_tokens);
   return check_launch("vsx_embed_assemble");
 }
 
 extern "C" int vsx_embed_assemble_bwd(const float* g, void* dpatches, int dtype, float* dpos, float* dtokens, int batch,
-                                      int tokens_per_sample, int C, int keep, void* stream) {
+                                      int tokens_per_sample, int C, int keep, int num_tokens, void* stream) {
   VSX_REQUIRE(C % 4 == 0 && keep >= 0 && keep <= C, "vsx_embed_assemble_bwd: bad C/keep");
+  VSX_REQUIRE(num_tokens >= 1 && num_tokens < tokens_per_sample, "vsx_embed_assemble_bwd: bad num_tokens %d", num_tokens);
   if (batch == 0) return VSX_OK;
   const int gx = grid_for((long)tokens_per_sample * C / 4);
   int gyy = (4 * num_sms() + gx - 1) / gx;
   gyy = gyy > batch ? batch : (gyy < 1 ? 1 : gyy);
   const dim3 grid(gx, gyy);
-  if (dtype == VSX_BF16) embed_assemble_bwd_kernel<bf16><<<grid, 256, 0, ST>>>(g, (bf16*)dpatches, dpos, dtokens, batch, tokens_per_sample, C, keep);
-  else embed_assemble_bwd_kernel<float><<<grid, 256, 0, ST>>>(g, (float*)dpatches, dpos, dtokens, batch, tokens_per_sample, C, keep);
+  if (dtype == VSX_BF16) embed_assemble_bwd_kernel<bf16><<<grid, 256, 0, ST>>>(g, (bf16*)dpatches, dpos, dtokens, batch, tokens_per_sample, C, keep, num_tokens);
+  else embed_assemble_bwd_kernel<float><<<grid, 256, 0, ST>>>(g, (float*)dpatches, dpos, dtokens, batch, tokens_per_sample, C, keep, num_tokens);
   return check_launch("vsx_embed_assemble_bwd");
 }
 

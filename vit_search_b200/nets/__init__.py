@@ -7,3 +7,5 @@ from .supernet_blocks import Attention, Block, Mlp  # noqa: F401
 from .vit_sr_supernet import (BypassBlock, FlexibleDistillVisionTransformerSR,  # noqa: F401
                               SpatialReductionPatchEmbedding)
 from . import vit_sr_supernet  # noqa: F401
+from .vision_transformer_supernet import FlexibleDistillVisionTransformer  # noqa: F401
+from . import vision_transformer_supernet  # noqa: F401

@@ -71,23 +71,23 @@ class _EmbedAssembleFn(torch.autograd.Function):
     def forward(ctx, patches, tokens, pos, keep):
         core.require_cuda(patches, 'FlexibleDistillVisionTransformerSR')
         B, Np, C = patches.shape
-        assert tokens.shape[1] == 1, 'token assembly kernel handles one class token'
+        T = tokens.shape[1]                  # 1 class token (+ 1 distillation token in the patch16 network)
         patches = patches.contiguous()
-        x0 = torch.empty(B, Np + 1, C, device=patches.device)
+        x0 = torch.empty(B, Np + T, C, device=patches.device)
         for b0, b1, k in _runs(keep, B, C):
-            ops.call('embed_assemble', (patches, b0 * Np * C), tokens, pos, (x0, b0 * (Np + 1) * C), b1 - b0, Np + 1, C, k)
-        ctx.keep, ctx.shape = keep, (B, Np, C)
+            ops.call('embed_assemble', (patches, b0 * Np * C), tokens, pos, (x0, b0 * (Np + T) * C), b1 - b0, Np + T, C, k, T)
+        ctx.keep, ctx.shape = keep, (B, Np, C, T)
         return x0
 
     @staticmethod
     def backward(ctx, g):
-        B, Np, C = ctx.shape
+        B, Np, C, T = ctx.shape
         g = g.contiguous()
         dpatches = torch.empty(B, Np, C, device=g.device)
-        dpos = torch.zeros(1, Np + 1, C, device=g.device)
-        dtok = torch.zeros(1, 1, C, device=g.device)
+        dpos = torch.zeros(1, Np + T, C, device=g.device)
+        dtok = torch.zeros(1, T, C, device=g.device)
         for b0, b1, k in _runs(ctx.keep, B, C):
-            ops.call('embed_assemble_bwd', (g, b0 * (Np + 1) * C), (dpatches, b0 * Np * C), ops.F32, dpos, dtok, b1 - b0, Np + 1, C, k)
+            ops.call('embed_assemble_bwd', (g, b0 * (Np + T) * C), (dpatches, b0 * Np * C), ops.F32, dpos, dtok, b1 - b0, Np + T, C, k, T)
         return dpatches, dtok, dpos, None
 
 
