@@ -189,7 +189,7 @@ struct LnCast {
 };
 
 template <int NV, typename T, bool CAST>
-__global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_bulk_kernel(const T* __restrict__ dy, long lddy, const float* __restrict__ x, long ldx,
+__global__ void __launch_bounds__(LN_WARPS * 32, NV <= 2 ? 4 : 1) ln_bwd_bulk_kernel(const T* __restrict__ dy, long lddy, const float* __restrict__ x, long ldx,
                                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                      const float* __restrict__ gamma, const float* __restrict__ g_in,
                                                                      float* __restrict__ g_out, long ldg, float* __restrict__ dgamma,
