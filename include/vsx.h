@@ -271,6 +271,12 @@ int vsx_conv3x3(const void* in, const float* in_scale, const float* in_shift, co
                 const float* mean, const float* rstd, double* sums, void* stream);
 int vsx_conv3x3_wgrad(const void* dy, const void* in, const float* in_scale, const float* in_shift, float* dw, int B, int H,
                       int W, int C, void* stream);
+/* First convolution of the stem (nets/patch_conv.py:25-30: 3 -> 24 channels, 3x3, stride 2, pad 1) as one kernel per direction, no
+ * im2col matrix in HBM.  image: fp32 NCHW [B, 3, H, W] (values are rounded to bf16 like every GEMM operand); weight: bf16 [24, ldw >= 32],
+ * column (ky*3+kx)*3 + c, zero padded; y: bf16 channels-last [B, H/2, W/2, 24]; sums (may be NULL): fp64[48] += (sum y, sum y^2).
+ * vsx_conv1_wgrad: dw[co][ (ky*3+kx)*3 + c ] (fp32, pitch ldw >= 27) += sum_p dy[p][co] * image[p, tap, c]. */
+int vsx_conv1_fwd(const float* image, const void* weight, long ldw, void* y, int B, int H, int W, double* sums, void* stream);
+int vsx_conv1_wgrad(const float* image, const void* dy, float* dw, long ldw, int B, int H, int W, void* stream);
 /* Development aid: 0 = pick the kernel automatically, 1 = legacy direct kernel (csrc/conv3x3.cu), 2 = TMA warp-specialised kernel
  * (csrc/conv3x3_tma.cu; C == 24, H and W multiples of 16). */
 int vsx_conv3x3_force_impl(int impl);

@@ -490,3 +490,34 @@ def test_ln_bwd_with_fused_cast(ops, C, keep, cast_keep):
     assert torch.equal(got_g, ref_g) and torch.equal(got_cast, ref_cast)
     assert rel(dgam2, dgam) < 1e-5 and rel(dbet2, dbet) < 1e-5 and rel(got_cs, ref_cs) < 1e-5
     assert torch.all(got_cast[:, cast_keep:] == 0)
+
+
+@pytest.mark.parametrize('B,H,W', [(2, 32, 48), (3, 224, 224), (1, 6, 10)])
+def test_conv1_direct(ops, B, H, W):
+    """First stem convolution (3 -> 24, 3x3, stride 2, pad 1) straight from the fp32 image: output map, fused batch statistics and the
+    weight gradient against torch fp64 math on the same bf16-rounded operands (ragged tails: 15 and 3 * 5 pixels are not multiples of 32)."""
+    import torch.nn.functional as F
+    from vit_search_b200 import core
+    g = torch.Generator().manual_seed(H + W)
+    x = torch.randn(B, 3, H, W, generator=g)
+    wgt = torch.randn(24, 3, 3, 3, generator=g) * 0.2
+    wparam = torch.nn.Parameter(wgt.cuda())
+    wc = core.weights.get(wparam, 'ohwi')
+    xq, wq = x.to(torch.bfloat16).double(), wgt.to(torch.bfloat16).double()
+    ref = F.conv2d(xq, wq, stride=2, padding=1).permute(0, 2, 3, 1)                # [B, H/2, W/2, 24]
+    y = torch.full((B, H // 2, W // 2, 24), float('nan'), device='cuda', dtype=torch.bfloat16)
+    sums = torch.zeros(48, device='cuda', dtype=torch.float64)
+    ops.call('conv1_fwd', x.cuda(), wc, core.ld_of(wc), y, B, H, W, sums)
+    assert rel(y, ref) < 4e-3 and not torch.isnan(y.float()).any()
+    y64 = y.double().cpu()
+    assert rel(sums[:24], y64.sum((0, 1, 2))) < 1e-5 and rel(sums[24:], (y64 * y64).sum((0, 1, 2))) < 1e-5
+    y2 = torch.empty_like(y)
+    ops.call('conv1_fwd', x.cuda(), wc, core.ld_of(wc), y2, B, H, W, None)          # eval mode: no statistics
+    assert torch.equal(y2, y)
+    dy = torch.randn(B, H // 2, W // 2, 24, generator=g).to(torch.bfloat16)
+    wref = wq.clone().requires_grad_(True)
+    (F.conv2d(xq, wref, stride=2, padding=1) * dy.double().permute(0, 3, 1, 2)).sum().backward()
+    dw = torch.zeros(24, 28, device='cuda')
+    ops.call('conv1_wgrad', x.cuda(), dy.cuda(), dw, 28, B, H, W)
+    assert rel(dw[:, :27].reshape(24, 3, 3, 3).permute(0, 3, 1, 2), wref.grad) < 2e-3
+    assert torch.all(dw[:, 27] == 0)

@@ -44,6 +44,8 @@ SIGNATURES = {
     'vsx_launch_count': [],
     'vsx_token_mix': [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, C.c_double, C.c_double, _p],
     'vsx_conv3x3_force_impl': [_i],
+    'vsx_conv1_fwd': [_p, _p, _l, _p, _i, _i, _i, _p, _p],
+    'vsx_conv1_wgrad': [_p, _p, _p, _l, _i, _i, _i, _p],
     'vsx_eval_metrics': [_p, _l, _p, _i, _i, _p, _p, _p, _p],
     'vsx_gemm_debug_buffer': [_p],
     'vsx_split_bf16': [_p, _l, _p, _p, _p, _l, _i, _i, _p],

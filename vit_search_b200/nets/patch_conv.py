@@ -76,11 +76,20 @@ class _StemFn(torch.autograd.Function):
             ops.gemm(a, wc, a_col.shape[1], core.ld_of(wc), a_col.shape[0], y.shape[1], kdim, ops.EPI_STORE, y, y.shape[1])
 
         k1 = 9 * Cin
-        A1 = torch.empty(P, core.up8(k1), device=dev, dtype=T)
-        ops.call('im2col', x, None, None, None, None, None, ops.F32, 1, Cin * H * W, 1, B, H, W, Cin, 3, 2, 1, A1, dt, A1.shape[1])
         y1 = torch.empty(P, Cm, device=dev, dtype=T)
-        conv(A1, k1, w1, y1)
-        s1 = _bn_train(y1, P, Cm, bns[0], dt) if train else _bn_eval(bns[0])
+        # conv1 as one kernel (csrc/conv1.cu): image -> y1 (+ its batch statistics), no im2col matrix in HBM
+        direct1 = T == torch.bfloat16 and Cin == 3 and Cm == 24 and H % 2 == 0 and W % 2 == 0 and x.dtype == torch.float32
+        if direct1:
+            A1 = None
+            wc1 = weights.get(w1, 'ohwi')
+            sums1 = torch.zeros(2 * Cm, device=dev, dtype=torch.float64) if train else None
+            ops.call('conv1_fwd', x, wc1, core.ld_of(wc1), y1, B, H, W, sums1)
+            s1 = _bn_finalize(sums1, P, Cm, bns[0]) if train else _bn_eval(bns[0])
+        else:
+            A1 = torch.empty(P, core.up8(k1), device=dev, dtype=T)
+            ops.call('im2col', x, None, None, None, None, None, ops.F32, 1, Cin * H * W, 1, B, H, W, Cin, 3, 2, 1, A1, dt, A1.shape[1])
+            conv(A1, k1, w1, y1)
+            s1 = _bn_train(y1, P, Cm, bns[0], dt) if train else _bn_eval(bns[0])
         direct = T == torch.bfloat16 and Cm % 8 == 0 and H1 % 8 == 0 and W1 % 16 == 0     # tensor-core direct conv (csrc/conv3x3.cu)
         A2 = A3 = None
         y2 = torch.empty(P, Cm, device=dev, dtype=T)
@@ -115,7 +124,7 @@ class _StemFn(torch.autograd.Function):
         a4 = acts.get(A4, A4.shape[1], 0, A4.shape[0], kp)
         ops.gemm(a4, wpc, A4.shape[1], core.ld_of(wpc), A4.shape[0], C, kp, ops.EPI_STORE, out, C, bias=bp)
         ctx.save_for_backward(w1, g1, b1, w2, g2, b2, w3, g3, b3, wp)
-        ctx.stuff = (A1, A2, A3, A4, y1, y2, y3, s1, s2, s3, (B, Cin, H1, W1, Cm, k, Hp, Wp, C, k1, kp))
+        ctx.stuff = (A1 if A1 is not None else x, A2, A3, A4, y1, y2, y3, s1, s2, s3, (B, Cin, H1, W1, Cm, k, Hp, Wp, C, k1, kp, A1 is None))
         return out.view(B, Hp * Wp, C)
 
     @staticmethod
@@ -123,7 +132,7 @@ class _StemFn(torch.autograd.Function):
         w1, g1, b1, w2, g2, b2, w3, g3, b3, wp = ctx.saved_tensors
         A1, A2, A3, A4, y1, y2, y3, s1, s2, s3, dims = ctx.stuff
         ctx.stuff = None
-        B, Cin, H1, W1, Cm, k, Hp, Wp, C, k1, kp = dims
+        B, Cin, H1, W1, Cm, k, Hp, Wp, C, k1, kp, direct1 = dims
         T = core.act_dtype()
         dt = ops._DT[T]
         dev = g.device
@@ -199,7 +208,12 @@ class _StemFn(torch.autograd.Function):
             dgrad(dy2, w2, 9 * Cm, dA)
             ops.call('col2im', dA, 9 * Cm, d_out, dt, B, H1, W1, Cm, 3, 1, 1, d_a1, H1 * W1 * Cm, Cm)
             dy1, d_g1, d_b1 = bn_bwd(d_a1, y1, g1, b1, s1)
-        d_w1 = wgrad(dy1, A1, k1, w1)
+        if direct1:            # A1 holds the image: weight gradient straight from it (csrc/conv1.cu)
+            dw1 = torch.zeros(Cm, 28, device=dev)
+            ops.call('conv1_wgrad', A1, dy1, dw1, 28, B, 2 * H1, 2 * W1)
+            d_w1 = dw1[:, :k1].reshape(Cm, 3, 3, Cin).permute(0, 3, 1, 2).contiguous()
+        else:
+            d_w1 = wgrad(dy1, A1, k1, w1)
         return (None, None, d_w1, d_g1, d_b1, d_w2, d_g2, d_b2, d_w3, d_g3, d_b3, d_wp, d_bp)
 
 
