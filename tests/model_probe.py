@@ -1,4 +1,5 @@
-"""Debug helper: per-tensor errors of the CUDA model vs the fp64 oracle for one case (prints everything)."""
+"""Debug helper (not a test; lives under tests/ because it uses the oracle): per-tensor errors of the CUDA model vs the fp64 oracle for
+one case (prints everything).  Usage: python tests/model_probe.py"""
 import os
 import sys
 
