@@ -17,7 +17,7 @@ from .masked_layer_norm import MaskedLayerNorm
 from .patch_conv import PatchEmbed
 from .registry import register_model
 from .supernet_blocks import Block
-from .vit_sr_supernet import BypassBlock, _EmbedAssembleFn, _cfg, _runs, trunc_normal_
+from .vit_sr_supernet import BypassBlock, FlexibleDistillVisionTransformerSR, _EmbedAssembleFn, _cfg, _runs, trunc_normal_
 
 _BLOCK_EMBED_INDEX, _EMBED_CHANNEL = 0, 1
 _BLOCK_HEAD_INDEX, _HEAD_CHANNEL = -1, 2
@@ -170,16 +170,7 @@ class FlexibleDistillVisionTransformer(nn.Module):
             out.append({k: v for k, v in blk.draw(batch).items() if v is not None} if isinstance(blk, Block) else {})
         return out
 
-    @staticmethod
-    def _group_permutation(keeps, batch):
-        sig = [tuple(v[b] for k in keeps for v in k.values()) for b in range(batch)]
-        if len(set(sig)) <= 1:
-            return None
-        first = {}
-        for b, s in enumerate(sig):
-            first.setdefault(s, b)
-        order = sorted(range(batch), key=lambda b: (first[sig[b]], b))
-        return None if order == list(range(batch)) else order
+    _group_permutation = staticmethod(FlexibleDistillVisionTransformerSR._group_permutation)
 
     def forward(self, x):
         core.require_cuda(x, 'FlexibleDistillVisionTransformer')
