@@ -578,6 +578,13 @@ def native_half_backward(meta, g_out, saved, x, params, ctx=None):
 _chain_tail = None     # (data_ptr of the last native half block's output, its ctx, shape, version)
 
 
+def reset_half_chain():
+    """Forget the previous half block: called at the start of every model forward so that a chain never spans two forwards (the caching
+    allocator may hand the new step's first activation the address of the previous step's last one)."""
+    global _chain_tail
+    _chain_tail = None
+
+
 class HalfBlockFn(torch.autograd.Function):
     """x_out = x + mask * drop_path(branch(LN(x)))  for one half of a Block (nets/supernet_blocks.py:213-253)."""
 

@@ -175,6 +175,7 @@ class FlexibleDistillVisionTransformer(nn.Module):
     def forward(self, x):
         core.require_cuda(x, 'FlexibleDistillVisionTransformer')
         core.weights.generation += 1
+        core.reset_half_chain()
         B = x.shape[0]
         keeps = self.sample_keeps(B) if self.is_supernet else [{} for _ in range(len(self.blocks) + 1)]
         self.last_keeps = keeps

@@ -520,6 +520,7 @@ class FlexibleDistillVisionTransformerSR(nn.Module):
     def forward_features(self, x):
         core.require_cuda(x, 'FlexibleDistillVisionTransformerSR')
         assert self.num_tokens == 1, 'distillation-token path is outside the hot path (SURVEY.md §2)'
+        core.reset_half_chain()
         B = x.shape[0]
         if self.active_subnet is not None:
             if self.training:
