@@ -209,3 +209,67 @@ def test_vit16_module_surface():
     assert flat == G['keeps'].tolist()
     m192 = create_model('flexible_vit_patch16_192', network_def=VIT16_DEF, num_classes=1000)
     assert m192.pos_embed.shape == (1, 144 + 2, 64)
+
+
+def test_abi_signatures_match_the_header():
+    """Every ctypes signature in _lib.SIGNATURES has the arity and the scalar / pointer kinds of its prototype in include/vsx.h, and the
+    ctypes mirrors of the descriptor structs have the header's field order (ABI drift would otherwise only show up as garbage on a GPU)."""
+    import ctypes as C
+    hdr = open(os.path.join(ROOT, 'include', 'vsx.h')).read()
+    hdr = re.sub(r'/\*.*?\*/', ' ', hdr, flags=re.S)
+    kinds = {C.c_void_p: 'p', C.c_int: 'i', C.c_long: 'l', C.c_float: 'f', C.c_double: 'd'}
+    protos = dict(re.findall(r'\b(?:int|long|const char\*)\s+(vsx_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;', hdr, flags=re.S))
+    assert set(protos) >= set(_lib.SIGNATURES)
+    for name, sig in _lib.SIGNATURES.items():
+        params = [p.strip() for p in protos[name].replace('\n', ' ').split(',')]
+        if params == ['void'] or params == ['']:
+            params = []
+        want = ''
+        for p in params:
+            if '*' in p:
+                want += 'p'
+            else:
+                ty = p.split()[0] if not p.startswith('const ') else p.split()[1]
+                want += {'int': 'i', 'long': 'l', 'float': 'f', 'double': 'd'}[ty]
+        got = ''.join(kinds.get(t, 'p') for t in sig)          # POINTER(struct) arguments are pointers
+        assert got == want, (name, got, want)
+    for cname, cls in (('vsx_segment', _lib.Segment), ('vsx_half_block', _lib.HalfBlock), ('vsx_half_block_grad', _lib.HalfBlockGrad),
+                       ('vsx_gemm_desc', _lib.GemmDesc), ('vsx_adamw_tensor', _lib.AdamWTensor)):
+        body = re.search(r'typedef struct %s \{(.*?)\} %s;' % (cname, cname), hdr, flags=re.S).group(1)
+        names = []
+        for decl in body.split(';'):
+            decl = decl.strip()
+            if not decl:
+                continue
+            for part in decl.split(','):
+                nm = re.sub(r'\[.*?\]', '', part.strip().split()[-1]).lstrip('*')
+                names.append(nm)
+        assert names == [f[0] for f in cls._fields_], (cname, names, [f[0] for f in cls._fields_])
+
+
+def test_random_search_candidates_fit_the_supernet():
+    """Candidates drawn from the sr_tiny search space (tools/evo_eval_bench.sample_candidate: uniform choices, removed blocks propagate like
+    search_utils/gen_utils.update_depth) are accepted by subnet_extents, stay inside the super-network and skip exactly the removed blocks."""
+    import random
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    from evo_eval_bench import sample_candidate
+    from vit_search_b200 import supernet_config as sc
+    from vit_search_b200.nets import create_model
+    nd, ks = sc.network_def('sr_tiny'), sc.num_channels_to_keep('sr_tiny')
+    m = create_model('flexible_vit_sr_patch14_224_patch_output', network_def=nd, num_classes=1000)
+    rng = random.Random(3)
+    seen_skip = False
+    for _ in range(20):
+        cand = sample_candidate(nd, ks, rng)
+        ext = m.subnet_extents(cand)
+        assert len(ext) == len(nd)
+        for d, u, e in zip(cand, nd, ext):
+            if d[0] == 1:
+                assert e == ({'skip': True} if not d[3] else {'attn': d[1][1] * d[1][2], 'mlp': d[2][1]})
+                assert d[1][1] <= u[1][1] and d[2][1] <= u[2][1]
+                seen_skip |= not d[3]
+            elif d[0] in (3, 4):
+                assert e == {'embed': d[2] if d[0] == 3 else d[1]}
+    assert seen_skip
+    assert m.subnet_extents(nd)[1] == {'attn': 256, 'mlp': 768}
