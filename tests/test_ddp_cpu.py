@@ -57,3 +57,31 @@ def test_gradient_allreduce_world2_gloo():
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _meters_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from vit_search_b200.evo_eval import EvalMeters
+    m = EvalMeters('cpu')
+    # what vsx_eval_metrics would have accumulated on this rank's shard: [sum of batch-mean losses, top-1, top-5, samples, batches]
+    m.totals.copy_(torch.tensor([2.0 * (rank + 1), 10.0 + rank, 40.0 + rank, 100.0, 2.0], dtype=torch.float64))
+    m.synchronize_between_processes()            # utils.MetricLogger.synchronize_between_processes (engine.py:233)
+    r = m.result()
+    ok = abs(r['loss'] - 6.0 / 4.0) < 1e-12 and abs(r['acc1'] - 100.0 * 21 / 200) < 1e-12 and abs(r['acc5'] - 100.0 * 81 / 200) < 1e-12
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_eval_meters_sum_over_ranks_world2_gloo():
+    """Candidate evaluation shards the validation set over ranks; the meters are summed over ranks like the reference's MetricLogger."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_meters_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(0, True), (1, True)]
