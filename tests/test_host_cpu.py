@@ -273,3 +273,43 @@ def test_random_search_candidates_fit_the_supernet():
                 assert e == {'embed': d[2] if d[0] == 3 else d[1]}
     assert seen_skip
     assert m.subnet_extents(nd)[1] == {'attn': 256, 'mlp': 768}
+
+
+def test_segments_and_group_permutation_properties():
+    """Host-side segment logic on random keep lists: make_segments partitions the batch into maximal runs of identical extents, and the
+    group permutation is a stable permutation that makes samples of one architecture contiguous."""
+    from hypothesis import given, settings, strategies as st
+    from vit_search_b200 import core
+    from vit_search_b200.nets.vit_sr_supernet import FlexibleDistillVisionTransformerSR as M, _runs
+
+    keeps = st.lists(st.tuples(st.sampled_from([64, 56, 40]), st.sampled_from([64, 32, 0]), st.sampled_from([64, 0])), min_size=1, max_size=24)
+
+    @settings(max_examples=60, deadline=None)
+    @given(keeps)
+    def check(rows):
+        B = len(rows)
+        ek, ik, ck = [r[0] for r in rows], [r[1] for r in rows], [r[2] for r in rows]
+        segs = core.make_segments(B, 64, ek, ik, 64, ck)
+        assert segs[0].b0 == 0 and segs[-1].b1 == B and all(a.b1 == b.b0 for a, b in zip(segs, segs[1:]))
+        for s in segs:
+            assert all((ek[b], ik[b], ck[b]) == (s.ek, s.ik, s.ck) for b in range(s.b0, s.b1))
+            assert s.active == (s.ek > 0 and s.ik > 0 and s.ck > 0)
+        assert all(a.key() != b.key() for a, b in zip(segs, segs[1:]))             # runs are maximal
+        runs = _runs(ek, B, 64)
+        assert runs[0][0] == 0 and runs[-1][1] == B and all(k == ek[b0] for b0, _, k in runs)
+        kd = [{'embed': ek}, {'attn': ik, 'layer': ck}]
+        perm = M._group_permutation(kd, B)
+        sig = [(ek[b], ik[b], ck[b]) for b in range(B)]
+        order = list(range(B)) if perm is None else perm
+        assert sorted(order) == list(range(B))
+        seen, last = set(), None
+        for b in order:                                                            # contiguous groups
+            if sig[b] != last:
+                assert sig[b] not in seen
+                seen.add(sig[b])
+                last = sig[b]
+        for s in set(sig):                                                         # stable inside a group
+            idx = [b for b in order if sig[b] == s]
+            assert idx == sorted(idx)
+
+    check()
