@@ -179,3 +179,30 @@ def test_vit16_oracle_vs_reference_golden():
         for got, want in ((cls, G['cls']), (dst, G['dst'])):
             want = torch.from_numpy(want)
             assert ((got - want).norm() / want.norm()).item() < 2e-6, name
+
+
+def test_switch_token_mix_properties():
+    """Size-independent properties of the augmentation (any batch / seed): soft targets are distributions; in the patch half the image-level
+    target equals the mean of the per-patch targets (lam = 1 - box area); in the image half every patch target equals the image target;
+    pixels outside the box are untouched and pixels inside come from the permuted partner."""
+    import numpy as np
+    import torch
+    from oracle import vit_res_oracle as O
+    for B, seed in ((10, 3), (7, 11), (32, 5)):
+        g = torch.Generator().manual_seed(seed)
+        x = torch.randn(B, 3, 56, 56, generator=g)
+        y = torch.randint(0, 1000, (B,), generator=g)
+        torch.manual_seed(seed)
+        np.random.seed(seed)
+        d = O.token_mix_draws(B, 4)
+        out, t, pt = O.switch_token_mix(x, y, d, 4)
+        n1 = B // 2
+        assert torch.allclose(t.sum(-1), torch.ones(B), atol=1e-5) and torch.allclose(pt.sum(-1), torch.ones(B, 16), atol=1e-5)
+        assert torch.allclose(pt[:n1].mean(1), t[:n1], atol=1e-6)
+        assert torch.equal(pt[n1:], t[n1:].unsqueeze(1).expand(-1, 16, -1))
+        y0, y1, x0, x1 = d['box']
+        ps = 56 // 4
+        inside = torch.zeros(56, 56, dtype=torch.bool)
+        inside[ps * y0:ps * y1, ps * x0:ps * x1] = True
+        assert torch.equal(out[:n1][..., ~inside], x[:n1][..., ~inside])
+        assert torch.equal(out[:n1][..., inside], x[:n1][d['perm1']][..., inside])
