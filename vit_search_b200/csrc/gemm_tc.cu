@@ -63,6 +63,8 @@ struct GemmArgs {
   float* colsum;
   int rows_per_sample, n_keep;
   int kseg_kb, kseg_stride;   // k-blocks per reduction window and distance between windows (0: one contiguous reduction)
+  int m_fastest;              // tile order: 0 = consecutive tiles walk the N tiles of one row block (they share the A tile), 1 = they walk the row blocks of one
+                              // column block (they share the B tile).  Development switch VSX_GEMM_TILE_ORDER; default 0.
   long long* dbg;
 };
 
@@ -238,7 +240,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     const int tiles_m = (g.M + BM * MT - 1) / (BM * MT), tiles_n = (g.n_out + BN - 1) / BN;
     const int splits = (EPI == VSX_EPI_ATOMIC) ? g.split_k : 1;
     const int kb_per = (g.num_kb + splits - 1) / splits;
-    const int ni = tl % tiles_n, mi = (tl / tiles_n) % tiles_m, z = tl / (tiles_n * tiles_m);
+    const int z = tl / (tiles_n * tiles_m);
+    const int ni = g.m_fastest ? (tl / tiles_m) % tiles_n : tl % tiles_n, mi = g.m_fastest ? tl % tiles_m : (tl / tiles_n) % tiles_m;
     m0 = mi * BM * MT, n0 = ni * BN;
     kb0 = z * kb_per;
     const int kb1 = min(g.num_kb, kb0 + kb_per);
@@ -635,6 +638,8 @@ int build_problem(const vsx_gemm_desc* d, TmapPack& maps, GemmArgs& g) {
   if (d->n_out == 0) return 1;
   g.M = d->M, g.N = d->N, g.K = d->K, g.num_kb = ceil_div(d->K, BK), g.terms = d->terms;
   g.kseg_kb = 0, g.kseg_stride = 0;
+  static const int tile_order = getenv("VSX_GEMM_TILE_ORDER") ? atoi(getenv("VSX_GEMM_TILE_ORDER")) : 0;
+  g.m_fastest = tile_order == 1 ? 1 : 0;
   if (d->k_segments > 1) {
     VSX_REQUIRE(d->k_seg_len > 0 && d->k_seg_stride >= d->k_seg_len && (long)(d->k_segments - 1) * d->k_seg_stride + d->k_seg_len <= d->K,
                 "vsx_gemm: reduction windows must lie inside [0, K) (segments=%d len=%d stride=%d K=%d)", d->k_segments, d->k_seg_len, d->k_seg_stride, d->K);
