@@ -35,7 +35,7 @@ extern "C" {
 #define VSX_BF16 0
 #define VSX_F32 1
 
-#define VSX_ABI_VERSION 3
+#define VSX_ABI_VERSION 4
 
 const char* vsx_last_error(void);
 int vsx_abi_version(void);
@@ -326,7 +326,10 @@ int vsx_eval_metrics(const float* logits, long ld, const long* labels, int rows,
  * vsx_adamw  : one launch over all parameters (torch.optim.AdamW semantics: decoupled decay, bias correction); each
  *              chunk i of vsx_adamw_chunk_elems() elements belongs to tensor chunk_tensor[i] at chunk_index[i].
  *              shadow_hi / shadow_lo (bf16, may be NULL) receive the refreshed GEMM operand copies of the weight;
- *              ema (fp32, may be NULL) the updated moving average.
+ *              ema (fp32, may be NULL) the updated moving average.  guard_loss_dev (may be NULL): the step's loss on the device;
+ *              when it is not finite the launch updates NOTHING and increments *nonfinite_count_dev -- the device-side form of the
+ *              reference's `if not math.isfinite(loss_value): sys.exit(1)` (engine.py:168-173), read by the host once per logging
+ *              interval instead of once per step.
  * -------------------------------------------------------------------------------------------------- */
 typedef struct vsx_adamw_tensor {
   float* param;
@@ -346,7 +349,8 @@ int vsx_soft_ce(const float* logits, long ld, const float* target, long ldt, int
 int vsx_scale_by_scalar(float* x, long n, const float* scalar_dev, void* stream);
 int vsx_adamw_chunk_elems(void);
 int vsx_adamw(const vsx_adamw_tensor* tensors_dev, const int* chunk_tensor_dev, const int* chunk_index_dev, int num_chunks,
-              float lr, float beta1, float beta2, float eps, int step, const float* grad_scale_dev, void* stream);
+              float lr, float beta1, float beta2, float eps, int step, const float* grad_scale_dev, const float* guard_loss_dev,
+              int* nonfinite_count_dev, void* stream);
 
 #ifdef __cplusplus
 }

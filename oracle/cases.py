@@ -87,3 +87,58 @@ VIT16_CASES = {
     'vit16_eval': dict(supernet=True, batch=4, epa=2, warmup=0, epoch=0, seed=23, train=False),
     'vit16_dense': dict(supernet=False, batch=4, epa=None, warmup=0, epoch=0, seed=24),
 }
+
+
+# BASELINE-size parity cases (oracle/make_golden_baseline.py): the real search spaces of BASELINE.json configs[1] / [2] and of the
+# published Tiny recipe, at a batch the CPU reference finishes in seconds.  `single` = one architecture per step (engine.py:121-122
+# seeds the draw per iteration), `multi` = example_per_arch 2 -> four architectures in a batch of 8.
+BASELINE_CASES = {
+    'sr_tiny_single':    dict(space='sr_tiny', supernet=True, batch=8, epa=2, warmup=0, epoch=2, seed=20003, single=True),
+    'sr_tiny_multi':     dict(space='sr_tiny', supernet=True, batch=8, epa=2, warmup=0, epoch=0, seed=41),
+    'sr_tiny_mh_single': dict(space='sr_tiny_mh', supernet=True, batch=8, epa=2, warmup=0, epoch=1, seed=10005, single=True),
+    'sr_tiny_mh_multi':  dict(space='sr_tiny_mh', supernet=True, batch=8, epa=2, warmup=0, epoch=0, seed=42),
+    'sr_small_single':   dict(space='sr_small', supernet=True, batch=8, epa=2, warmup=0, epoch=0, seed=7, single=True),
+    'sr_small_multi':    dict(space='sr_small', supernet=True, batch=8, epa=2, warmup=0, epoch=0, seed=43),
+}
+
+
+def baseline_net(space):
+    """(network_def, num_channels_to_keep) of a named search space (tables restated in vit_search_b200/supernet_config)."""
+    from vit_search_b200 import supernet_config as sc
+    return sc.network_def(space), sc.num_channels_to_keep(space)
+
+
+def probe_vectors(shape):
+    """Seeded +-1 vectors (l [rows], r [cols]) for the gradient projections stored in the BASELINE-size goldens."""
+    import torch
+    g = torch.Generator().manual_seed(1000003 * shape[0] + shape[1])
+    lv = torch.randint(0, 2, (shape[0],), generator=g).float() * 2 - 1
+    rv = torch.randint(0, 2, (shape[1],), generator=g).float() * 2 - 1
+    return lv, rv
+
+
+def element_keys(network_def, full):
+    """Parameters whose gradients are stored with element-level evidence: the four Linear weights of the first transformer block of
+    every stage, both SR convolutions / token Linears and both heads.  Returns (stored in full, stored as sample + projections)."""
+    first, stage_start = [], True
+    bi = 0
+    for d in network_def[1:]:
+        if d[0] == 1:
+            if stage_start:
+                first.append(bi)
+                stage_start = False
+            bi += 1
+        elif d[0] == 3:
+            bi += 1
+            stage_start = True
+    names = []
+    for j, b in enumerate(first):
+        names.append([('blocks.%d.%s.weight' % (b, n)) for n in ('attn.qkv', 'attn.proj', 'mlp.fc1', 'mlp.fc2')])
+    full = set(names[0]) if full else set()
+    full_set = full
+    sampled = set(k for grp in names for k in grp) - full_set
+    sampled |= {'cls_head.weight', 'patch_head.weight'}
+    for i, d in enumerate(network_def[1:]):
+        if d[0] == 3:
+            sampled |= {'blocks.%d.patch_reduce.weight' % i, 'blocks.%d.token_transform.weight' % i}
+    return full, sampled

@@ -121,3 +121,64 @@ def test_standalone_mlp_and_attention_modules(prec):
             assert not bad, (type(mod).__name__, prec, bad)
     finally:
         core.USE_NATIVE_HALF = native0
+
+
+@pytest.mark.parametrize('with_embed', [True, False])
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+def test_block_reference_signature_with_bool_masks(with_embed, prec):
+    """Block.forward(x, embed_mask, layer_mask) exactly as the reference calls it (nets/supernet_blocks.py:209-255): UNTAGGED [B,1,C]
+    bool tensors in (keep counts are read back from the device), the block draws its own attn / layer / mlp masks from its
+    ChannelDrops, and returns (x, embed_mask, current_layer_mask) as bool tensors.  `with_embed=False` is the case in which the
+    reference masks the attention branch with the block's OWN layer mask only and the MLP branch with own & incoming (:220-251)."""
+    import numpy as np
+    from vit_search_b200 import core
+    from vit_search_b200.nets import Block, ChannelDrop
+    C, H, D, F, N, B = 128, 2, 64, 256, 65, 8
+    attn_ch, mlp_ch, layer_ch = [128, 64], [256, 192, 128], [128, 128, 0, 0]
+    blk = Block(C, H, D, F, num_chs_to_keep_attn=np.array(attn_ch), num_chs_to_keep_mlp=np.array(mlp_ch),
+                num_chs_to_keep_block=np.array(layer_ch), num_warmup_epochs=0, example_per_arch=2).cuda()
+    shapes = {k: tuple(v.shape) for k, v in blk.state_dict().items()}
+    w = O.keyed_fill(shapes, seed=5)
+    for k in w:
+        if k.endswith('weight') and w[k].ndim == 2:
+            w[k] = w[k] * 3
+    blk.load_state_dict(w)
+    for mod in blk.modules():
+        if isinstance(mod, ChannelDrop):
+            mod.set_epoch(0)
+    blk.train()
+    embed = [128, 128, 112, 112, 100, 100, 80, 80]
+    layer_in = [128, 0, 128, 128, 0, 128, 128, 128]
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(B, N, C, generator=g)
+    if with_embed:
+        x = x * O.prefix_mask(embed, C, torch.float32)
+    gout = torch.randn(B, N, C, generator=g)
+    embed_mask = O.prefix_mask(embed, C).cuda() if with_embed else None          # plain bool tensors, no keep-count tag
+    layer_mask = O.prefix_mask(layer_in, C).cuda()
+    xd = x.cuda().requires_grad_(True)
+    with core.precision(prec):
+        torch.manual_seed(77)
+        y, em, cur = blk(xd, embed_mask, layer_mask)
+        y.backward(gout.cuda())
+    torch.cuda.synchronize()
+    # the same draws through the oracle's restatement of ChannelDrop (order: attn, layer, mlp -- SURVEY.md A3)
+    torch.manual_seed(77)
+    keeps = {}
+    for key, ch in (('attn', attn_ch), ('layer', layer_ch), ('mlp', mlp_ch)):
+        keeps[key] = O.draw_keep(O.keep_table(ch, B, 2, False, 0, 0), B, 2, False)
+    p = {'b.' + k: v.double().requires_grad_(True) for k, v in w.items()}
+    xo = x.double().requires_grad_(True)
+    yo, _, cur_o = O.block(xo, p, 'b.', H, D, embed if with_embed else None, layer_in, keeps)
+    yo.backward(gout.double())
+    assert em is embed_mask
+    assert cur.dtype == torch.bool and tuple(cur.shape) == (B, 1, C)
+    assert cur.sum(dim=(1, 2)).tolist() == cur_o
+    assert len(set(zip(keeps['attn'], keeps['layer'], keeps['mlp']))) > 1          # the draw really mixed architectures
+    tol = 2e-5 if prec == 'fp32' else 2e-2
+    m = O.prefix_mask(embed, C, torch.float64) if with_embed else 1.0
+    errs = {'y': rel(y, yo), 'gx': rel(xd.grad.double().cpu() * m, xo.grad * m)}
+    for k, prm in blk.named_parameters():
+        errs[k] = rel(prm.grad, p['b.' + k].grad)
+    bad = {k: v for k, v in errs.items() if not v < tol}
+    assert not bad, (prec, with_embed, bad)

@@ -313,3 +313,82 @@ def test_segments_and_group_permutation_properties():
             assert idx == sorted(idx)
 
     check()
+
+
+def test_train_step_seed_sequence_resets_every_epoch():
+    """engine.py:98-122: `train_iter = 0` at the top of every epoch and, for 'single' / 'hybrid' sampling, torch.manual_seed(epoch *
+    10000 + train_iter) before the forward.  TrainStep must seed identically when one object is reused across epochs."""
+    from vit_search_b200.engine import TrainStep
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.ones(4))
+            self.seeds = []
+
+        def forward(self, x, patch_output_type=None):
+            self.seeds.append(torch.initial_seed())
+            return self.w * x.sum(), self.w * 2.0
+
+    class Opt:
+        guard = None
+
+        def zero_grad(self):
+            pass
+
+        def step(self, **kw):
+            pass
+
+    net = Net()
+    step = TrainStep(net, Opt(), criterion=lambda a, b: a.sum(), arch_sample='single')
+    torch.manual_seed(99)
+    before = torch.random.get_rng_state()
+    for epoch, iters in ((0, 3), (1, 2), (2, 2)):
+        for _ in range(iters):
+            step(torch.ones(2), None, None, epoch=epoch)
+    assert net.seeds == [0, 1, 2, 10000, 10001, 20000, 20001]
+    assert torch.equal(torch.random.get_rng_state(), before)          # engine.py:164-165: the RNG state is restored after the draw
+    step.reset_epoch(2)
+    step(torch.ones(2), None, None, epoch=2)
+    assert net.seeds[-1] == 20000
+    # 'multi' sampling never reseeds
+    net2 = Net()
+    step2 = TrainStep(net2, Opt(), criterion=lambda a, b: a.sum(), arch_sample='multi')
+    torch.manual_seed(5)
+    step2(torch.ones(2), None, None, epoch=3)
+    assert net2.seeds == [5]
+
+
+def test_fused_adamw_state_dict_layout_and_round_trip():
+    """main.py saves optimizer.state_dict() in every checkpoint and restores it on --resume: FusedAdamW must produce / accept the
+    torch.optim.AdamW layout of timm's two parameter groups (no-decay first), so reference checkpoints interoperate."""
+    from vit_search_b200.engine import FusedAdamW
+    m = _small(example_per_arch=2, num_warmup_epochs=0)
+    opt = FusedAdamW(m, lr=1e-3, weight_decay=0.05)
+    # the same grouping built the way timm's add_weight_decay + torch.optim.AdamW does it
+    decay, no_decay = [], []
+    for name, p in m.named_parameters():
+        (no_decay if (p.ndim <= 1 or name.endswith('.bias') or name in m.no_weight_decay()) else decay).append(p)
+    ref = torch.optim.AdamW([{'params': no_decay, 'weight_decay': 0.}, {'params': decay, 'weight_decay': 0.05}], lr=1e-3)
+    for p in m.parameters():
+        p.grad = torch.randn_like(p) * 1e-2
+    ref.step()
+    ref.step()
+    rsd = ref.state_dict()
+    assert [g['params'] for g in opt.param_groups] == [g['params'] for g in rsd['param_groups']]
+    assert [g['weight_decay'] for g in opt.param_groups] == [0.0, 0.05]
+    opt.load_state_dict(rsd)                              # a reference checkpoint loads ...
+    assert opt.step_count == 2
+    by_index = {opt._index[n]: n for n, _, _ in opt.entries}
+    params = dict(m.named_parameters())
+    flat_ref = no_decay + decay
+    for i, name in by_index.items():
+        assert params[name] is flat_ref[i]                # ... index i means the same parameter on both sides
+        assert torch.equal(opt.state[name][0], rsd['state'][i]['exp_avg']) and torch.equal(opt.state[name][1], rsd['state'][i]['exp_avg_sq'])
+    out = opt.state_dict()                                # ... and what we save, torch.optim.AdamW loads
+    ref2 = torch.optim.AdamW([{'params': no_decay, 'weight_decay': 0.}, {'params': decay, 'weight_decay': 0.05}], lr=1e-3)
+    ref2.load_state_dict(out)
+    for i in by_index:
+        assert torch.equal(ref2.state_dict()['state'][i]['exp_avg'], rsd['state'][i]['exp_avg'])
+        assert float(ref2.state_dict()['state'][i]['step']) == 2.0
+    assert all(k in opt.param_groups[0] for k in ('lr', 'betas', 'eps', 'weight_decay'))

@@ -266,3 +266,165 @@ def test_device_feeder_pipeline():
     torch.cuda.synchronize()
     for i, sacc in enumerate(sums):
         assert sacc.item() == float(i) * 64 * 3 * 32 * 32 - float(i) * 64 * 10, i
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE-size networks
+def _build_baseline(case):
+    from vit_search_b200.nets import create_model
+    from oracle.cases import baseline_net
+    nd, space = baseline_net(case['space'])
+    m = create_model('flexible_vit_sr_patch14_224_patch_output_supernet', network_def=nd, num_classes=1000, drop_rate=0., drop_path_rate=0.,
+                     num_channels_to_keep=space, example_per_arch=case['epa'], num_warmup_epochs=0, single_arch=case.get('single', False)).cuda()
+    m.set_epoch(case['epoch'])
+    m.load_state_dict(O.keyed_fill(O.param_shapes(nd), seed=0))
+    return m, nd
+
+
+def _baseline_cases():
+    from oracle.cases import BASELINE_CASES
+    return BASELINE_CASES
+
+
+@pytest.mark.parametrize('name', list(_baseline_cases()))
+@pytest.mark.parametrize('prec', ['fp32', 'bf16'])
+def test_baseline_size_vs_reference_golden(name, prec):
+    """The real search spaces (sr_tiny = BASELINE configs[1], sr_tiny_mh = the published Tiny recipe, sr_small = configs[2]) at B = 8,
+    one and four architectures per step, against the REFERENCE's outputs (oracle/make_golden_baseline.py): logits, loss, mask draws,
+    the norm of every parameter gradient and, for the first block of every stage, the SR blocks and the heads, gradient ELEMENTS
+    (full tensors, strided samples and +-1 projections that involve every element).
+
+    Tolerances: fp32 parity path logits 2e-4, gradients 2e-4 (conv stem 5e-3).  bf16 training path: logits within 1.5 x the
+    reference's OWN bf16-autocast error against fp64 (stored in the golden, ~6.5e-3) and <= 2e-2; gradients 8e-2 in
+    norm and as elements (stem 0.3)."""
+    from vit_search_b200 import core
+    from vit_search_b200.engine import SoftTargetCrossEntropy
+    from oracle.cases import probe_vectors
+    case = _baseline_cases()[name]
+    G = np.load(os.path.join(GOLD, name + '.npz'))
+    m, nd = _build_baseline(case)
+    B = case['batch']
+    x, t, pt = O.synthetic_batch(B, seed=case.get('xseed', 1234))
+    x, t, pt = x.cuda(), t.cuda(), pt.cuda()
+    m.train()
+    crit = SoftTargetCrossEntropy()
+    with core.precision(prec):
+        torch.manual_seed(case['seed'])
+        cls, patch = m(x, patch_output_type='seq')
+        loss = crit(cls, t) + crit(patch, pt)
+        loss.backward()
+    torch.cuda.synchronize()
+    flat = [k[n] for k in m.last_keeps for n in ('embed', 'attn', 'layer', 'mlp') if n in k]
+    assert flat == G['keeps'].tolist(), 'sub-architecture draws differ from the reference'
+    errs = {'cls': rel(cls, G['cls']), 'patch': rel(patch, G['patch'])}
+    if prec == 'fp32':
+        tol_cls = tol_patch = 2e-4
+        tol_grad, tol_stem, tol_loss = 2e-4, 5e-3, 1e-4
+    else:
+        tol_cls = min(2e-2, 1.5 * float(G['bf16_ref_err_cls']))
+        tol_patch = min(2e-2, 1.5 * float(G['bf16_ref_err_patch']))
+        tol_grad, tol_stem, tol_loss = 8e-2, 0.3, 3e-2
+    print('%s %s logits err cls %.2e patch %.2e (reference bf16 autocast: %.2e / %.2e)' %
+          (name, prec, errs['cls'], errs['patch'], float(G['bf16_ref_err_cls']), float(G['bf16_ref_err_patch'])))
+    assert errs['cls'] < tol_cls and errs['patch'] < tol_patch, (errs, tol_cls, tol_patch)
+    assert abs(loss.item() - float(G['loss'])) < tol_loss
+    stem = lambda k: k.startswith('patch_embed.conv') and 'conv_proj' not in k    # noqa: E731
+    bad, n_elem = {}, 0
+    for k, p in m.named_parameters():
+        gn = float(G['gn:' + k])
+        tol = tol_stem if stem(k) else tol_grad
+        g = p.grad
+        if gn == 0:
+            if not g.norm().item() == 0:
+                bad[k] = ('nonzero', g.norm().item())
+            continue
+        e = abs(g.double().norm().item() - gn) / gn
+        if not e < tol:
+            bad[k] = ('norm', e)
+        if 'g:' + k in G.files:
+            e = rel(g, G['g:' + k])
+            n_elem += 1
+            if not e < tol:
+                bad[k] = ('elements', e)
+        elif 'gs:' + k in G.files:
+            g2 = g.reshape(g.shape[0], -1).double().cpu()
+            lv, rv = probe_vectors(tuple(g2.shape))
+            # sample: relative to the RMS of the whole tensor x sqrt(sample size) (a sample may be mostly masked-out zeros)
+            s_ref = torch.from_numpy(G['gs:' + k]).double()
+            e_s = ((g2[::7, ::11] - s_ref).norm() / max(s_ref.norm().item(), 1e-30)).item()
+            # projections: their error is a sum of g.numel() / len independent element errors -> compare against the same scale
+            e_l = ((lv.double() @ g2 - torch.from_numpy(G['gl:' + k]).double()).norm() / (gn * 1.0)).item()
+            e_r = ((g2 @ rv.double() - torch.from_numpy(G['gr:' + k]).double()).norm() / (gn * 1.0)).item()
+            n_elem += 1
+            if not (e_s < tol and e_l < tol and e_r < tol):
+                bad[k] = ('sample/left/right', e_s, e_l, e_r)
+    assert n_elem >= 14
+    assert not bad, (prec, bad)
+
+
+def test_fused_adamw_multi_step_vs_oracle_moments():
+    """Five fused AdamW steps on fixed synthetic gradients (so that nothing but the optimizer is compared): parameters, both moments
+    and the bf16 operand shadows against O.adamw_step, which tests/test_oracle_cpu.py pins to torch.optim.AdamW.  After five steps
+    with gradients of alternating scale the update depends on the moment history and both bias corrections."""
+    from vit_search_b200 import core
+    from vit_search_b200.engine import FusedAdamW
+    case = CASES['small_single']
+    m, nd = build(case)
+    opt = FusedAdamW(m, lr=2e-3, weight_decay=0.05)
+    names = [n for n, _ in m.named_parameters()]
+    params = {n: p.detach().double().cpu().clone() for n, p in m.named_parameters()}
+    state = {}
+    g = torch.Generator().manual_seed(3)
+    with core.precision('bf16'):
+        for step in range(1, 6):
+            grads = {n: torch.randn(params[n].shape, generator=g) * (1e-3 if step % 2 else 0.5) for n in names}
+            for n, p in m.named_parameters():
+                p.grad = grads[n].cuda()
+            opt.step()
+            O.adamw_step(params, {n: grads[n].double() for n in names}, state, lr=2e-3, weight_decay=0.05, step=step)
+    torch.cuda.synchronize()
+    bad = {}
+    for n, p in m.named_parameters():
+        e = [rel(p.detach(), params[n]), rel(opt.state[n][0], state[n][0]), rel(opt.state[n][1], state[n][1])]
+        if not max(e) < 2e-6:
+            bad[n] = e
+        if n in opt.shadow:
+            assert torch.equal(opt.shadow[n], p.detach().to(torch.bfloat16)), n
+    assert not bad, bad
+    # checkpoint round trip on the device: a fresh optimizer that loads the state continues identically
+    sd = opt.state_dict()
+    opt2 = FusedAdamW(m, lr=2e-3, weight_decay=0.05)
+    opt2.load_state_dict(sd)
+    assert opt2.step_count == 5
+    n0 = names[3]
+    assert torch.equal(opt2.state[n0][0], opt.state[n0][0]) and opt2.state[n0][0].data_ptr() != opt.state[n0][0].data_ptr()
+
+
+def test_finite_loss_guard_skips_the_update_on_the_device():
+    """engine.py:168-173 aborts on a non-finite loss after a host read-back every step.  Here the optimizer kernel checks the loss on the
+    device: a step with an inf / nan loss changes nothing and raises a sticky counter that TrainStep.check_finite() turns into the
+    reference's abort at the logging interval."""
+    from vit_search_b200 import core
+    from vit_search_b200.engine import TrainStep, FusedAdamW
+    case = CASES['small_single']
+    m, nd = build(case)
+    m.train()
+    B = case['batch']
+    x, t, pt = O.synthetic_batch(B, seed=5)
+    step = TrainStep(m, FusedAdamW(m, lr=1e-3), arch_sample='single')
+    with core.precision('bf16'):
+        step(x.cuda(), t.cuda(), pt.cuda(), epoch=0)
+        torch.cuda.synchronize()
+        step.check_finite()                                   # finite so far
+        w1 = {k: v.detach().clone() for k, v in m.named_parameters()}
+        m1 = {k: v[0].clone() for k, v in step.optimizer.state.items()}
+        xb = x.clone()
+        xb[0, 0, 0, 0] = float('nan')
+        loss = step(xb.cuda(), t.cuda(), pt.cuda(), epoch=0)
+        torch.cuda.synchronize()
+        assert not torch.isfinite(loss).item()
+        for k, v in m.named_parameters():
+            assert torch.equal(v.detach(), w1[k]), k           # nothing moved
+        for k, v in step.optimizer.state.items():
+            assert torch.equal(v[0], m1[k]), k
+        with pytest.raises(FloatingPointError, match='not finite'):
+            step.check_finite()

@@ -206,3 +206,63 @@ def test_switch_token_mix_properties():
         inside[ps * y0:ps * y1, ps * x0:ps * x1] = True
         assert torch.equal(out[:n1][..., ~inside], x[:n1][..., ~inside])
         assert torch.equal(out[:n1][..., inside], x[:n1][d['perm1']][..., inside])
+
+
+def test_oracle_adamw_pinned_to_torch_optim():
+    """O.adamw_step (the checker of the fused optimizer kernel) against the installed torch.optim.AdamW with timm's grouping, over
+    several steps so that both moments and the bias corrections matter (not just lr * sign(g) of a first step)."""
+    torch.manual_seed(0)
+    shapes = {'blocks.0.attn.qkv.weight': (24, 16), 'blocks.0.attn.qkv.bias': (24,), 'blocks.0.norm1.weight': (16,), 'tokens': (1, 1, 16),
+              'pos_embed': (1, 5, 16)}
+    w0 = {k: torch.randn(s, dtype=torch.float64) for k, s in shapes.items()}
+    mine = {k: v.clone() for k, v in w0.items()}
+    theirs = {k: torch.nn.Parameter(v.clone()) for k, v in w0.items()}
+    nd = lambda k, v: v.ndim <= 1 or k.endswith('.bias') or k == 'tokens'      # noqa: E731
+    opt = torch.optim.AdamW([{'params': [v for k, v in theirs.items() if nd(k, v)], 'weight_decay': 0.},
+                             {'params': [v for k, v in theirs.items() if not nd(k, v)], 'weight_decay': 0.05}], lr=3e-3, betas=(0.9, 0.999), eps=1e-8)
+    state = {}
+    for step in range(1, 8):
+        grads = {k: torch.randn(s, dtype=torch.float64) * (0.1 if step % 2 else 3.0) for k, s in shapes.items()}
+        for k in theirs:
+            theirs[k].grad = grads[k].clone()
+        opt.step()
+        O.adamw_step(mine, grads, state, lr=3e-3, weight_decay=0.05, step=step)
+        for k in shapes:
+            assert rel(mine[k].numpy(), theirs[k].detach().numpy()) < 1e-12, (step, k)
+    for k in shapes:
+        st = opt.state[theirs[k]]
+        assert rel(state[k][0].numpy(), st['exp_avg'].numpy()) < 1e-12 and rel(state[k][1].numpy(), st['exp_avg_sq'].numpy()) < 1e-12
+
+
+def test_oracle_matches_baseline_size_golden():
+    """The oracle at the real widths (sr_tiny, BASELINE configs[1]) against the reference's outputs, incl. gradient elements."""
+    from oracle.cases import BASELINE_CASES, baseline_net, probe_vectors
+    name = 'sr_tiny_multi'
+    case = BASELINE_CASES[name]
+    G = np.load(os.path.join(GOLD, name + '.npz'))
+    nd, space = baseline_net(case['space'])
+    w = O.keyed_fill(O.param_shapes(nd), seed=0)
+    p = {k: v.clone().requires_grad_(v.is_floating_point() and 'running' not in k) for k, v in w.items()}
+    B = case['batch']
+    x, t, pt = O.synthetic_batch(B, seed=1234)
+    smp = O.Sampler(nd, space, case['epa'], 0, case.get('single', False), False)
+    smp.set_epoch(case['epoch'])
+    torch.manual_seed(case['seed'])
+    keeps = smp.sample(B)
+    flat = [k[n] for k in keeps for n in ('embed', 'attn', 'layer', 'mlp') if n in k]
+    assert flat == G['keeps'].tolist()
+    loss, cls, patch = O.train_loss(p, nd, x, t, pt, keeps)
+    loss.backward()
+    assert rel(cls.detach().numpy(), G['cls']) < TOL and rel(patch.detach().numpy(), G['patch']) < TOL
+    n = 0
+    for k in G.files:
+        if k.startswith('gs:'):
+            g = p[k[3:]].grad
+            g2 = g.reshape(g.shape[0], -1).double()
+            lv, rv = probe_vectors(tuple(g2.shape))
+            gn = float(G['gn:' + k[3:]])
+            assert (g2[::7, ::11] - torch.from_numpy(G[k]).double()).norm().item() < TOL * gn, k
+            assert (lv.double() @ g2 - torch.from_numpy(G['gl:' + k[3:]]).double()).norm().item() < TOL * gn, k
+            assert (g2 @ rv.double() - torch.from_numpy(G['gr:' + k[3:]]).double()).norm().item() < TOL * gn, k
+            n += 1
+    assert n >= 14

@@ -8,7 +8,7 @@ import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libvsx.so')
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 BF16, F32 = 0, 1
 KMAJOR, MNMAJOR = 0, 1
@@ -66,7 +66,7 @@ SIGNATURES = {
     'vsx_soft_ce': [_p, _l, _p, _l, _i, _i, _f, _f, _p, _p, _l, _p],
     'vsx_scale_by_scalar': [_p, _l, _p, _p],
     'vsx_adamw_chunk_elems': [],
-    'vsx_adamw': [_p, _p, _p, _i, _f, _f, _f, _f, _i, _p, _p],
+    'vsx_adamw': [_p, _p, _p, _i, _f, _f, _f, _f, _i, _p, _p, _p, _p],
 }
 _RESTYPES = {'vsx_last_error': C.c_char_p, 'vsx_launch_count': C.c_long}
 

@@ -71,7 +71,17 @@ constexpr int ADAM_CHUNK = 16384;   // elements per CTA
 
 __global__ void __launch_bounds__(256) adamw_kernel(const vsx_adamw_tensor* __restrict__ tensors, const int* __restrict__ chunk_tensor,
                                                     const int* __restrict__ chunk_index, float lr, float beta1, float beta2, float eps,
-                                                    float bc1, float bc2, const float* __restrict__ grad_scale_dev) {
+                                                    float bc1, float bc2, const float* __restrict__ grad_scale_dev,
+                                                    const float* __restrict__ guard_dev, int* __restrict__ nonfinite_dev) {
+  if (guard_dev != nullptr) {
+    // finite-loss guard (engine.py:168-173): a step whose loss is inf / nan leaves parameters, moments, shadows and averages untouched
+    // and raises the sticky device flag the host reads at its logging interval -- no host sync on the step itself
+    const float l = *guard_dev;
+    if (!(fabsf(l) <= 3.402823466e38f)) {
+      if (blockIdx.x == 0 && threadIdx.x == 0 && nonfinite_dev != nullptr) atomicAdd(nonfinite_dev, 1);
+      return;
+    }
+  }
   const vsx_adamw_tensor t = tensors[chunk_tensor[blockIdx.x]];
   const long begin = (long)chunk_index[blockIdx.x] * ADAM_CHUNK;
   const long end = begin + ADAM_CHUNK < t.numel ? begin + ADAM_CHUNK : t.numel;
@@ -158,10 +168,12 @@ extern "C" int vsx_scale_by_scalar(float* x, long n, const float* scalar_dev, vo
 extern "C" int vsx_adamw_chunk_elems(void) { return ADAM_CHUNK; }
 
 extern "C" int vsx_adamw(const vsx_adamw_tensor* tensors_dev, const int* chunk_tensor_dev, const int* chunk_index_dev, int num_chunks,
-                         float lr, float beta1, float beta2, float eps, int step, const float* grad_scale_dev, void* stream) {
+                         float lr, float beta1, float beta2, float eps, int step, const float* grad_scale_dev, const float* guard_loss_dev,
+                         int* nonfinite_count_dev, void* stream) {
   VSX_REQUIRE(step >= 1, "vsx_adamw: step counts from 1");
   if (num_chunks <= 0) return VSX_OK;
   const float bc1 = (float)(1.0 - pow((double)beta1, (double)step)), bc2 = (float)(1.0 - pow((double)beta2, (double)step));
-  adamw_kernel<<<num_chunks, 256, 0, ST>>>(tensors_dev, chunk_tensor_dev, chunk_index_dev, lr, beta1, beta2, eps, bc1, bc2, grad_scale_dev);
+  adamw_kernel<<<num_chunks, 256, 0, ST>>>(tensors_dev, chunk_tensor_dev, chunk_index_dev, lr, beta1, beta2, eps, bc1, bc2, grad_scale_dev, guard_loss_dev,
+                                             nonfinite_count_dev);
   return check_launch("vsx_adamw");
 }

@@ -68,8 +68,54 @@ class FusedAdamW:
         self.shadow = {}          # name -> bf16 GEMM-operand copy refreshed by the optimizer kernel itself
         self.ema = None           # ModelEma attached with attach_ema(): parameter averages are then updated inside the same kernel
         self._table_key = None
-        self.param_groups = [{'lr': lr}]
+        # timm's add_weight_decay (optim_factory.py, used by create_optimizer at main.py:385): group 0 = no-decay parameters, group 1 =
+        # decayed ones, each in named_parameters() order.  `params` holds torch.optim-style indices so that state_dict() has the
+        # layout of torch.optim.AdamW.state_dict() for the reference's optimizer and checkpoints interoperate.
+        order = [e for e in self.entries if e[2] == 0.0] + [e for e in self.entries if e[2] != 0.0]
+        self._index = {e[0]: i for i, e in enumerate(order)}
+        n0 = sum(1 for e in self.entries if e[2] == 0.0)
+        common = dict(lr=lr, betas=tuple(betas), eps=eps, amsgrad=False)
+        self.param_groups = [dict(common, weight_decay=0.0, params=list(range(n0))),
+                             dict(common, weight_decay=weight_decay, params=list(range(n0, len(order))))]
         self.chunk = _lib.lib().vsx_adamw_chunk_elems()
+        self.guard = None         # (loss device scalar, int32 device counter) of the current step: see TrainStep / vsx_adamw
+
+    # ---- checkpointing (main.py saves optimizer.state_dict() in every checkpoint and restores it on --resume)
+    def state_dict(self):
+        """torch.optim.AdamW layout: {'state': {index: {'step', 'exp_avg', 'exp_avg_sq'}}, 'param_groups': [...]}."""
+        state = {}
+        for name, p, _ in self.entries:
+            st = self.state.get(name)
+            if st is not None:
+                state[self._index[name]] = {'step': torch.tensor(float(self.step_count)), 'exp_avg': st[0].clone(), 'exp_avg_sq': st[1].clone()}
+        return {'state': state, 'param_groups': [dict(g) for g in self.param_groups]}
+
+    def load_state_dict(self, sd):
+        groups = sd['param_groups']
+        if [len(g['params']) for g in groups] != [len(g['params']) for g in self.param_groups]:
+            raise ValueError('FusedAdamW.load_state_dict: parameter groups do not match this model (%s vs %s)' %
+                             ([len(g['params']) for g in groups], [len(g['params']) for g in self.param_groups]))
+        for mine, theirs in zip(self.param_groups, groups):
+            for k in ('lr', 'betas', 'eps', 'weight_decay'):
+                if k in theirs:
+                    mine[k] = tuple(theirs[k]) if k == 'betas' else theirs[k]
+        self.betas, self.eps = tuple(self.param_groups[0]['betas']), self.param_groups[0]['eps']
+        steps = set()
+        for name, p, _ in self.entries:
+            st = sd['state'].get(self._index[name], sd['state'].get(str(self._index[name])))
+            if st is None:
+                self.state.pop(name, None)
+                continue
+            if tuple(st['exp_avg'].shape) != tuple(p.shape):
+                raise ValueError('FusedAdamW.load_state_dict: moment shape %s of %s does not match the parameter %s' %
+                                 (tuple(st['exp_avg'].shape), name, tuple(p.shape)))
+            self.state[name] = (st['exp_avg'].to(device=p.device, dtype=torch.float32).clone().contiguous(),
+                                st['exp_avg_sq'].to(device=p.device, dtype=torch.float32).clone().contiguous())
+            steps.add(int(float(st['step'])))
+        if len(steps) > 1:
+            raise ValueError('FusedAdamW.load_state_dict: per-parameter step counts differ (%s); the fused kernel keeps one' % sorted(steps))
+        self.step_count = steps.pop() if steps else 0
+        self._table_key = None      # moment buffers were replaced: rebuild the pointer table
 
     def attach_ema(self, ema):
         """Fold `ema.update(model)` for the PARAMETERS into the optimizer kernel (buffers are averaged by ModelEma.update_buffers)."""
@@ -133,9 +179,14 @@ class FusedAdamW:
             self._build_table()
             self._table_key = (core.get_precision(), id(self.ema)) + tuple((p.data_ptr(), p.grad.data_ptr()) for _, p, _ in self.entries)
         self.step_count += 1
-        self.lr = self.param_groups[0]['lr']
+        lrs = set(float(g['lr']) for g in self.param_groups)
+        if len(lrs) != 1:
+            raise ValueError('FusedAdamW: all parameter groups must share one learning rate (got %s)' % sorted(lrs))
+        self.lr = lrs.pop()
+        guard, flag = self.guard if self.guard is not None else (None, None)
+        self.guard = None
         ops.call('adamw', self._tab, self._ct, self._ci, self._nchunks, float(self.lr), float(self.betas[0]), float(self.betas[1]),
-                 float(self.eps), self.step_count, grad_scale)
+                 float(self.eps), self.step_count, grad_scale, guard, flag)
         core.weights.generation += 1      # parameters were written through raw pointers: operand copies are stale ...
         if self._tab_has_shadow:          # ... except the shadows this launch has just rewritten
             for name, p, _ in self.entries:
@@ -188,8 +239,10 @@ class TrainStep:
         self.criterion = criterion if criterion is not None else SoftTargetCrossEntropy()
         self.arch_sample = arch_sample
         self.world_size = world_size
-        self.train_iter = 0
+        self.train_iter = 0           # iteration WITHIN the current epoch (the reference resets it per epoch, engine.py:100)
+        self._epoch = None
         self._pool_numel = None
+        self.nonfinite = None         # int32 device counter of steps whose loss was inf / nan (those steps update nothing)
         self.model_ema = model_ema
         if model_ema is not None and hasattr(self.optimizer, 'attach_ema'):
             self.optimizer.attach_ema(model_ema)
@@ -204,6 +257,8 @@ class TrainStep:
     def __call__(self, samples, targets, patch_targets, epoch=0):
         """samples [B,3,224,224], targets [B,K], patch_targets [B,16,K] on the GPU.  Returns the loss as a device scalar
         (no host sync)."""
+        if epoch != self._epoch:                                 # engine.py:100: `train_iter = 0` at the top of every epoch, so the
+            self._epoch, self.train_iter = epoch, 0              # sampling seed is epoch * 10000 + iteration-in-epoch
         rng = None
         if self.arch_sample is not None:                         # engine.py:119-131
             rng = torch.random.get_rng_state()
@@ -229,6 +284,10 @@ class TrainStep:
         finally:
             core.grad_pool.end()
             core.trunk_grads_ready_hook = None
+        if self.nonfinite is None:
+            self.nonfinite = torch.zeros(1, dtype=torch.int32, device=samples.device)
+        if hasattr(self.optimizer, 'guard'):
+            self.optimizer.guard = (loss.detach(), self.nonfinite)
         if self._native_dp:
             self._finish_allreduce(flat, used)
             self.optimizer.step(grad_scale=self._inv_world)
@@ -237,6 +296,19 @@ class TrainStep:
         if self.model_ema is not None:
             self.model_ema.update(self.model)                    # engine.py:179-180
         return loss.detach()
+
+    def reset_epoch(self, epoch=None):
+        """Start of an epoch (engine.py:100): the sampling seed counts iterations from 0 again."""
+        self._epoch, self.train_iter = epoch, 0
+
+    def check_finite(self):
+        """The reference aborts on a non-finite loss after a host read-back every step (engine.py:168-173).  Here the optimizer kernel
+        skips such a step on the device and counts it; call this at the logging interval (one 4-byte read-back) to abort like the
+        reference does."""
+        if self.nonfinite is not None:
+            n = int(self.nonfinite.item())
+            if n:
+                raise FloatingPointError('Loss was not finite in %d step(s) since the last check, stopping training' % n)
 
     # ------------------------------------------------------------------ native data parallelism
     def _arm_overlap(self, flat):

@@ -141,14 +141,16 @@ class Block(nn.Module):
         """x [B,N,C] fp32.  keeps = self.draw(B).  dp_scale: optional fp32 device table whose rows dp_off and dp_off+1
         hold the per-sample drop-path scales of the attention and MLP branches.  Returns (x, current_layer_keep)."""
         B, N, C = x.shape
-        cur = None
-        if keeps.get('layer') is not None:                      # reference :220-223
-            cur = and_keep(list(keeps['layer']), layer_keep_in)
-        if embed_keep is not None:                              # reference :238-243
-            cur = and_keep(cur, embed_keep)
+        cur = attn_ck = None
+        if keeps.get('layer') is not None:                      # reference :220-223: layer_drop(f_x) masks the attention branch with
+            attn_ck = list(keeps['layer'])                      # this block's OWN layer mask; the incoming one only joins `cur`
+            cur = and_keep(attn_ck, layer_keep_in)
+        if embed_keep is not None:                              # reference :238-243: with an embed mask the attention branch is
+            cur = and_keep(cur, embed_keep)                     # multiplied by the full AND as well
+            attn_ck = cur
         a, m = self.attn, self.mlp
         hd = a.num_heads * a.head_dim
-        segs = core.make_segments(B, C, embed_keep, keeps.get('attn'), hd, cur)
+        segs = core.make_segments(B, C, embed_keep, keeps.get('attn'), hd, attn_ck)
         meta = core.HalfMeta('attn', segs, N, C, heads=a.num_heads, head_dim=a.head_dim, row_scale=dp_scale, scale_off=dp_off * B,
                              eps=self.norm1.eps)
         x = core.HalfBlockFn.apply(meta, x, self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias)
