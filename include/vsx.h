@@ -126,6 +126,9 @@ int vsx_gemm(const vsx_gemm_desc* d, void* stream);
 int vsx_gemm_grouped(const vsx_gemm_desc* descs, int count, void* stream);
 /* CTA tile rows: 0 = heuristic (256-row tiles sharing one B box per k block when they fill the machine), 128 / 256 = forced (tests). */
 int vsx_gemm_force_tile_rows(int rows);
+/* CTA group: 0 = heuristic, 1 = single-CTA tiles only, 2 = every launch on CTA pairs (tcgen05.mma.cta_group::2: a cluster of two SMs
+ * computes a 256 x 256 tile, each CTA staging half of each operand).  Tests and A/B measurements. */
+int vsx_gemm_force_cta_group(int cta_group);
 /* Development aid: device buffer of 64 x 8 int64 clock stamps written by CTA 0 of the next GEMM launches (NULL = off). */
 int vsx_gemm_debug_buffer(void* buffer);
 
@@ -349,7 +352,7 @@ int vsx_soft_ce(const float* logits, long ld, const float* target, long ldt, int
 int vsx_scale_by_scalar(float* x, long n, const float* scalar_dev, void* stream);
 int vsx_adamw_chunk_elems(void);
 int vsx_adamw(const vsx_adamw_tensor* tensors_dev, const int* chunk_tensor_dev, const int* chunk_index_dev, int num_chunks,
-              float lr, float beta1, float beta2, float eps, int step, const float* grad_scale_dev, const float* guard_loss_dev,
+              double lr, double beta1, double beta2, double eps, int step, const float* grad_scale_dev, const float* guard_loss_dev,
               int* nonfinite_count_dev, void* stream);
 
 #ifdef __cplusplus

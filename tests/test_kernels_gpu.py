@@ -21,14 +21,20 @@ def ops():
 
 
 # ---------------------------------------------------------------------------------------------- masked LN
-@pytest.fixture(params=[128, 256])
+@pytest.fixture(params=[128, 256, 'pair'])
 def tile_rows(request, ops):
-    """Run every GEMM test with both CTA tile shapes of csrc/gemm_tc.cu (128 x 128, and 256 x 128 = two accumulators sharing one
-    B box per k block), including 256-row tiles whose second half lies beyond M."""
+    """Run every GEMM test with all CTA tile shapes of csrc/gemm_tc.cu: 128 x 128, 256 x 128 (two accumulators sharing one B box per k
+    block) and 256 x 256 on a CTA PAIR (tcgen05.mma.cta_group::2, a cluster of two SMs), including tiles whose second half lies beyond
+    M or N."""
     from vit_search_b200 import _lib
-    _lib.check(_lib.lib().vsx_gemm_force_tile_rows(request.param))
+    if request.param == 'pair':
+        _lib.check(_lib.lib().vsx_gemm_force_cta_group(2))
+    else:
+        _lib.check(_lib.lib().vsx_gemm_force_cta_group(1))
+        _lib.check(_lib.lib().vsx_gemm_force_tile_rows(request.param))
     yield request.param
     _lib.lib().vsx_gemm_force_tile_rows(0)
+    _lib.lib().vsx_gemm_force_cta_group(0)
 
 
 @pytest.mark.parametrize('C,keep', [(64, 64), (64, 44), (256, 160), (320, 220), (1024, 704), (1280, 1280)])

@@ -417,9 +417,9 @@ def test_finite_loss_guard_skips_the_update_on_the_device():
         step.check_finite()                                   # finite so far
         w1 = {k: v.detach().clone() for k, v in m.named_parameters()}
         m1 = {k: v[0].clone() for k, v in step.optimizer.state.items()}
-        xb = x.clone()
-        xb[0, 0, 0, 0] = float('nan')
-        loss = step(xb.cuda(), t.cuda(), pt.cuda(), epoch=0)
+        tb = t.clone()
+        tb[0, 0] = float('inf')           # (a NaN pixel would not do: the stem's ReLU is fmaxf, which maps NaN to 0)
+        loss = step(x.cuda(), tb.cuda(), pt.cuda(), epoch=0)
         torch.cuda.synchronize()
         assert not torch.isfinite(loss).item()
         for k, v in m.named_parameters():

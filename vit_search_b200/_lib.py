@@ -38,6 +38,7 @@ SIGNATURES = {
     'vsx_attn_bwd': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p],
     'vsx_attn_debug_buffer': [_p],
     'vsx_gemm_force_tile_rows': [_i],
+    'vsx_gemm_force_cta_group': [_i],
     'vsx_gemm_grouped': [_p, _i, _p],
     'vsx_half_block_fwd': [_p, _p],
     'vsx_half_block_bwd': [_p, _p],
@@ -66,7 +67,7 @@ SIGNATURES = {
     'vsx_soft_ce': [_p, _l, _p, _l, _i, _i, _f, _f, _p, _p, _l, _p],
     'vsx_scale_by_scalar': [_p, _l, _p, _p],
     'vsx_adamw_chunk_elems': [],
-    'vsx_adamw': [_p, _p, _p, _i, _f, _f, _f, _f, _i, _p, _p, _p, _p],
+    'vsx_adamw': [_p, _p, _p, _i, C.c_double, C.c_double, C.c_double, C.c_double, _i, _p, _p, _p, _p],
 }
 _RESTYPES = {'vsx_last_error': C.c_char_p, 'vsx_launch_count': C.c_long}
 

@@ -172,24 +172,59 @@ __device__ __forceinline__ f32x2 normal_cdf2(float x0, float x1, f32x2& e2) {
   unpk2(add2(pk2(0.5f, 0.5f), mul2(q, pk2(-1.0f, -1.0f))), h0, h1);
   return add2(pk2(0.5f, 0.5f), pk2(copysignf(h0, x0), copysignf(h1, x1)));
 }
+// ---- MUFU-free GELU / GELU' for the bf16 GEMM epilogues.  The A-S evaluation above needs two SFU operations per element (rcp, ex2);
+// the SFU issues one warp instruction per 8 clocks and scheduler, so a 128 x 128 epilogue unit paid 2048 clocks of SFU time -- more
+// than its tensor-core time at K <= 256 (tools/gemm_timeline.py: 3300 clocks of epilogue math per unit).  Both functions have the form
+// 0.5 + u * P(u^2) with P smooth, so P is evaluated as a polynomial in s = u^2 * (2 / 4.5^2) - 1 on |u| <= 4.5 (u is clamped: beyond
+// 4.5 both functions are within 4e-6 of their limits) with packed fp32x2 Horner steps on the FMA pipe only:
+//   Phi(u)   = 0.5 + u * P10(s)   |abs err| < 7e-6   (fp32 Horner, Chebyshev least-squares fit; tools/fit_gelu_poly.py)
+//   gelu'(u) = 0.5 + u * P11(s)   |abs err| < 5e-5
+// i.e. below 1/40 of a bf16 ulp of the values they scale.  The fp32 parity mode keeps erff (gelu_f / gelu_grad_f).
+__device__ __forceinline__ f32x2 poly_cdf2(float x0, float x1, f32x2& xc) {
+  xc = pk2(fminf(fmaxf(x0, -4.5f), 4.5f), fminf(fmaxf(x1, -4.5f), 4.5f));
+  const f32x2 s = fma2(mul2(xc, xc), pk2(0.0987654321f, 0.0987654321f), pk2(-1.0f, -1.0f));
+  f32x2 p = pk2(1.074221019e-03f, 1.074221019e-03f);
+  p = fma2(p, s, pk2(-2.304612824e-03f, -2.304612824e-03f));
+  p = fma2(p, s, pk2(2.497475973e-03f, 2.497475973e-03f));
+  p = fma2(p, s, pk2(-5.324486247e-03f, -5.324486247e-03f));
+  p = fma2(p, s, pk2(1.161688181e-02f, 1.161688181e-02f));
+  p = fma2(p, s, pk2(-1.897149445e-02f, -1.897149445e-02f));
+  p = fma2(p, s, pk2(2.822568407e-02f, 2.822568407e-02f));
+  p = fma2(p, s, pk2(-4.012141573e-02f, -4.012141573e-02f));
+  p = fma2(p, s, pk2(5.470778012e-02f, 5.470778012e-02f));
+  p = fma2(p, s, pk2(-7.719306673e-02f, -7.719306673e-02f));
+  p = fma2(p, s, pk2(1.569048135e-01f, 1.569048135e-01f));
+  return fma2(xc, p, pk2(0.5f, 0.5f));
+}
+__device__ __forceinline__ f32x2 poly_gelu_grad2(float x0, float x1) {
+  const f32x2 xc = pk2(fminf(fmaxf(x0, -4.5f), 4.5f), fminf(fmaxf(x1, -4.5f), 4.5f));
+  const f32x2 s = fma2(mul2(xc, xc), pk2(0.0987654321f, 0.0987654321f), pk2(-1.0f, -1.0f));
+  f32x2 p = pk2(-6.985080961e-03f, -6.985080961e-03f);
+  p = fma2(p, s, pk2(1.433847597e-02f, 1.433847597e-02f));
+  p = fma2(p, s, pk2(-1.157771896e-02f, -1.157771896e-02f));
+  p = fma2(p, s, pk2(2.306988463e-02f, 2.306988463e-02f));
+  p = fma2(p, s, pk2(-5.256838405e-02f, -5.256838405e-02f));
+  p = fma2(p, s, pk2(7.393936118e-02f, 7.393936118e-02f));
+  p = fma2(p, s, pk2(-8.730810965e-02f, -8.730810965e-02f));
+  p = fma2(p, s, pk2(9.659937234e-02f, 9.659937234e-02f));
+  p = fma2(p, s, pk2(-9.497554799e-02f, -9.497554799e-02f));
+  p = fma2(p, s, pk2(8.712603100e-02f, 8.712603100e-02f));
+  p = fma2(p, s, pk2(-8.996616928e-02f, -8.996616928e-02f));
+  p = fma2(p, s, pk2(1.594292470e-01f, 1.594292470e-01f));
+  return fma2(xc, p, pk2(0.5f, 0.5f));
+}
 // in place on 32 values: v = gelu(v)   /   v = v * gelu'(u)
 __device__ __forceinline__ void gelu_fast32(float (&v)[32]) {
 #pragma unroll
   for (int j = 0; j < 32; j += 2) {
-    f32x2 e2;
-    const f32x2 cdf = normal_cdf2(v[j], v[j + 1], e2);
+    f32x2 xc;
+    const f32x2 cdf = poly_cdf2(v[j], v[j + 1], xc);
     unpk2(mul2(pk2(v[j], v[j + 1]), cdf), v[j], v[j + 1]);
   }
 }
 __device__ __forceinline__ void gelu_grad_fast32(float (&v)[32], const float (&u)[32]) {
 #pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    f32x2 e2;
-    const f32x2 cdf = normal_cdf2(u[j], u[j + 1], e2);
-    const f32x2 uu = pk2(u[j], u[j + 1]);
-    const f32x2 gp = fma2(mul2(uu, pk2(0.39894228040143268f, 0.39894228040143268f)), e2, cdf);      // cdf + u * pdf
-    unpk2(mul2(pk2(v[j], v[j + 1]), gp), v[j], v[j + 1]);
-  }
+  for (int j = 0; j < 32; j += 2) unpk2(mul2(pk2(v[j], v[j + 1]), poly_gelu_grad2(u[j], u[j + 1])), v[j], v[j + 1]);
 }
 
 template <typename OutT> __device__ __forceinline__ float gelu_sel(float x) { return gelu_fast(x); }
@@ -303,6 +338,59 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 // mbarrier arrives once all previously issued MMAs of this thread have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// ---------------------------------------------------------------- CTA pairs (cta_group::2): cluster helpers
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_cluster(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on an mbarrier that may live in the peer CTA (shared::cluster address)
+// (.relaxed: the callers order their own tensor-memory reads with tcgen05.wait::ld + fence::before_thread_sync; a .release at cluster scope
+// costs ~1800 clocks here because it drains every outstanding shared-memory store of the thread first -- tools/gemm_timeline.py)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+// TMA tile load of a CTA pair: data lands in THIS CTA's shared memory (dst: own shared::cta address, valid in the cluster window), the
+// bytes are counted on `cluster_bar`, which may be the leader CTA's barrier
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* m, uint32_t cluster_bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.cta_group::2 [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(cluster_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem of both CTAs] (+)= A[256 x 16: 128 rows from each CTA's smem] * B[N x 16: N/2 columns from each CTA's smem]; issued by ONE thread
+// of the leader CTA
+__device__ __forceinline__ void umma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the barrier at this shared-memory offset in BOTH CTAs of the pair receives one arrival when the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
 }
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets lane (base+i), v[j] = column (col+j)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {

@@ -33,17 +33,26 @@ constexpr int STAGE_B = BN * BK * 2;
 // 3/4 of the L2 -> shared-memory bytes per flop of two independent 128 x 128 tiles.  These GEMMs have K <= 1536 and run at the
 // L2 -> SM fabric limit (~45 B/clk/SM) long before the tensor pipe saturates, so bytes per flop is what sets their speed.
 constexpr bool RESID_NBUF2 = false;   // measured: helps K <= 384 (48 -> 37 us), hurts K >= 768 (61 -> 68 us): the ring then is too shallow
-template <int MT> struct Shape {
+// CG = CTAs per tile (cta_group).  CG = 2: a CTA PAIR (one cluster of two SMs) computes a 256 x 256 tile with tcgen05.mma.cta_group::2
+// (M = 256, N = 256): each CTA stages its own 128 rows of A and its own 128 columns of B -- 32 KB per k block for 128 x 256 outputs per
+// CTA, i.e. 2/3 of the shared-memory fill bytes per flop of the 256 x 128 single-CTA tile and half of its MMA operand reads -- and owns
+// the 128 x 256 fp32 accumulator of its rows in its tensor memory (two sets = all 512 columns).
+template <int MT, int CG> struct Shape {
+  static_assert(CG == 1 || (CG == 2 && MT == 1), "CTA pairs use one 128-row A sub-tile per CTA");
+  static constexpr int NT = CG;                      // 128-column accumulator units per CTA
+  static constexpr int UNITS = MT * NT;              // 128 x 128 epilogue units per CTA and tile
   static constexpr int STAGE_A = MT * SUB_A;
   static constexpr int STAGE_BYTES = STAGE_A + STAGE_B;
-  static constexpr int TMEM_COLS = 2 * MT * BN;      // two accumulator sets (double buffered across tiles)
+  static constexpr int TILE_M = CG * MT * BM, TILE_N = NT * BN;
+  static constexpr int ACC_COLS = UNITS * BN;
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;     // two accumulator sets (double buffered across tiles)
 };
 constexpr int EPI_WARPS = 8;            // two warps per TMEM lane quarter, each owning half of the tile's columns
 constexpr int EPI0 = 3;                 // warp 0 TMA producer, warp 1 MMA issuer, warp 2 store/aux warp, warps 3.. epilogue
 constexpr int GEMM_THREADS = (EPI0 + EPI_WARPS) * 32;
 constexpr int MAX_STAGES = 5;
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int SMEM_MISC = 1024 /*align*/ + 256 /*barriers, tmem slot*/ + 1024 /*two bias tiles*/;
+constexpr int SMEM_MISC_BASE = 1024 /*align*/ + 256 /*barriers, tmem slot*/;      // + two bias tiles (Plan::SMEM_MISC)
 
 constexpr int COLACC_MAX = 3072;      // widest output whose bias-gradient column sums are accumulated in shared memory
 constexpr int MAX_TERMS = 6;
@@ -55,6 +64,7 @@ struct TmapPack {
 
 static long long* g_gemm_dbg = nullptr;   // development aid: clock stamps of CTA 0 (tools/gemm_timeline.py)
 static int g_force_mt = 0;   // 0 = heuristic, 1 / 2 = force the 128- / 256-row CTA tile (tests)
+static int g_force_cg = 0;   // 0 = heuristic, 1 = single-CTA tiles only, 2 = CTA pairs (cta_group::2) for every launch (tests, A/B runs)
 
 struct GemmArgs {
   int M, N, K, num_kb, terms, a_mn, b_mn, n_out, split_k;
@@ -87,9 +97,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, bool mn_major)
 }
 
 // Instruction descriptor, kind::f16: D=f32, A=B=bf16, M=128, N=128.
-__device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn) {
+__device__ __forceinline__ uint32_t make_idesc(bool a_mn, bool b_mn, int m = BM, int n = BN) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
-         ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 // ---------------------------------------------------------------- epilogue staging (shared memory, TMA layout)
@@ -169,8 +179,9 @@ __device__ __forceinline__ float warp_colsum32(const float (&in)[32], int lane) 
 }
 
 // Per-instantiation shared-memory plan: NBUF staging tiles (epilogue output / aux input), the rest is the operand ring.
-template <int EPI, typename OutT, int MT> struct Plan {
-  static constexpr int STAGE_BYTES = Shape<MT>::STAGE_BYTES;
+template <int EPI, typename OutT, int MT, int CG> struct Plan {
+  static constexpr int STAGE_BYTES = Shape<MT, CG>::STAGE_BYTES;
+  static constexpr int SMEM_MISC = SMEM_MISC_BASE + 2 * Shape<MT, CG>::TILE_N * 4;
   static constexpr int TILE_BYTES = BM * BN * (int)sizeof(OutT) * (EPI == VSX_EPI_GELU ? 2 : 1);
   // per-CTA accumulator of the fused bias-gradient column sums (flushed once at the end of the persistent loop: thousands of
   // per-tile global atomics on a few hundred addresses serialise in L2 and used to dominate the GELU' dgrad GEMMs)
@@ -194,11 +205,13 @@ template <int EPI, typename OutT, int MT> struct Plan {
 //                       later TMA-stores / reduce-adds the staged result; staging is double buffered
 //   warps 3+ epilogue : TMEM -> registers -> fused math -> swizzled staging tile
 // so the loads of tile i+1, the MMAs of tile i+1 and the stores of tile i-1 overlap the epilogue of tile i.
-template <int EPI, typename OutT, int MT, int G>
+template <int EPI, typename OutT, int MT, int G, int CG>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ Group<G> grp) {
-  using P = Plan<EPI, OutT, MT>;
+  using P = Plan<EPI, OutT, MT, CG>;
+  using S = Shape<MT, CG>;
   constexpr int STAGES = P::STAGES, NBUF = P::NBUF;
-  constexpr int STAGE_BYTES = P::STAGE_BYTES, STAGE_A = Shape<MT>::STAGE_A, TMEM_COLS = Shape<MT>::TMEM_COLS;
+  constexpr int STAGE_BYTES = P::STAGE_BYTES, STAGE_A = S::STAGE_A, TMEM_COLS = S::TMEM_COLS;
+  constexpr int NT = S::NT, UNITS = S::UNITS, TILE_M = S::TILE_M, TILE_N = S::TILE_N;
   constexpr bool AUX = (EPI == VSX_EPI_RESIDUAL || EPI == VSX_EPI_GELUGRAD);
   constexpr int BOXC = 128 / (int)sizeof(OutT);     // columns per 128-byte box row
   constexpr int NBOX = BN / BOXC;                   // boxes per output tile
@@ -218,13 +231,17 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   auto ready_bar = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + 4 + b); };
   auto staged_bar = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + 6 + b); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (2 * MAX_STAGES + 8));
-  float* bias_s = reinterpret_cast<float*>(misc + 256);   // [2][BN]
-  float* colacc = reinterpret_cast<float*>(misc + SMEM_MISC - 1024);   // [COLACC_MAX] when P::COLACC != 0 (after the 1 KB alignment slack)
+  float* bias_s = reinterpret_cast<float*>(misc + 256);   // [2][TILE_N]
+  float* colacc = reinterpret_cast<float*>(misc + P::SMEM_MISC - 1024);   // [COLACC_MAX] when P::COLACC != 0 (after the 1 KB alignment slack)
   const bool use_colacc = G == 1 && P::COLACC != 0 && grp.args[0].colsum != nullptr && grp.args[0].n_out <= COLACC_MAX;
   long long* const dbg = grp.args[0].dbg;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total = grp.total;
+  // CTA pairs: both CTAs of a cluster walk the SAME tile list; rank 0 (the leader) issues the MMAs for both
+  const int cta_rank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int tile_first = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_stride = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   // tile t -> (problem, m0, n0, k-block range); identical arithmetic in every role
   auto tile_info = [&](int t, int& pi, int& m0, int& n0, int& kb0, int& nkb) {
@@ -237,12 +254,12 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
     const GemmArgs& g = grp.args[pi];
     const int tl = t - t0;
-    const int tiles_m = (g.M + BM * MT - 1) / (BM * MT), tiles_n = (g.n_out + BN - 1) / BN;
+    const int tiles_m = (g.M + TILE_M - 1) / TILE_M, tiles_n = (g.n_out + TILE_N - 1) / TILE_N;
     const int splits = (EPI == VSX_EPI_ATOMIC) ? g.split_k : 1;
     const int kb_per = (g.num_kb + splits - 1) / splits;
     const int z = tl / (tiles_n * tiles_m);
     const int ni = g.m_fastest ? (tl / tiles_m) % tiles_n : tl % tiles_n, mi = g.m_fastest ? tl % tiles_m : (tl / tiles_n) % tiles_m;
-    m0 = mi * BM * MT, n0 = ni * BN;
+    m0 = mi * TILE_M + cta_rank * (MT * BM), n0 = ni * TILE_N;      // this CTA's rows; the tile's first column
     kb0 = z * kb_per;
     const int kb1 = min(g.num_kb, kb0 + kb_per);
     nkb = (n0 < g.N && kb1 > kb0) ? kb1 - kb0 : 0;
@@ -265,74 +282,88 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       }
       for (int b = 0; b < 2; ++b) {
         mbar_init(acc_full(b), 1);
-        mbar_init(acc_empty(b), EPI_WARPS);
+        mbar_init(acc_empty(b), CG * EPI_WARPS);        // pairs: the epilogue warps of BOTH CTAs release the leader's accumulator barrier
         mbar_init(ready_bar(b), 1);
         mbar_init(staged_bar(b), EPI_WARPS);
       }
       fence_mbar_init();
     }
     __syncwarp();
-    tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
+    if (CG == 2) tmem_alloc_pair(smem_u32(tmem_slot), TMEM_COLS);
+    else tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();      // barrier inits of both CTAs are visible cluster-wide before any remote arrive / multicast commit
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     if (lane == 0) {
       // ---------------- TMA producer ----------------
+      // pairs: each CTA loads its own A rows and its own 128 B columns into its own ring; all bytes are counted on the LEADER's full
+      // barrier (the leader's MMA thread is the only consumer), slots are released to both producers by a multicast commit
+      auto load = [&](uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+        if (CG == 2) tma_load_2d_pair(dst, m, bar, c0, c1);
+        else tma_load_2d(dst, m, bar, c0, c1);
+      };
       int it = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      for (int t = tile_first; t < total; t += tile_stride) {
         int pi, m0, n0, kb0, nkb;
         tile_info(t, pi, m0, n0, kb0, nkb);
         const GemmArgs& g = grp.args[pi];
         const TmapPack& maps = grp.maps[pi];
+        const int nb0 = n0 + cta_rank * BN;          // this CTA's B columns
         for (int i = 0; i < nkb * g.terms; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
           mbar_wait(empty_bar(s), ph ^ 1u);
           const int term = i / nkb, kbi = kb0 + i % nkb;
           const int k0 = g.kseg_kb > 0 ? (kbi / g.kseg_kb) * g.kseg_stride + (kbi % g.kseg_kb) * BK : kbi * BK;
-          const uint32_t dA = ring + s * STAGE_BYTES, dB = dA + STAGE_A, fb = full_bar(s);
-          mbar_expect_tx(fb, STAGE_BYTES);
+          const uint32_t dA = ring + s * STAGE_BYTES, dB = dA + STAGE_A;
+          const uint32_t fb = CG == 2 ? mapa_cluster(full_bar(s), 0) : full_bar(s);
+          if (cta_rank == 0) mbar_expect_tx(full_bar(s), CG * STAGE_BYTES);
 #pragma unroll
           for (int sub = 0; sub < MT; ++sub) {
             const uint32_t dS = dA + sub * SUB_A;
             const int ms = m0 + sub * BM;
             if (!g.a_mn) {
-              tma_load_2d(dS, &maps.a[term], fb, k0, ms);
+              load(dS, &maps.a[term], fb, k0, ms);
             } else {
-              tma_load_2d(dS, &maps.a[term], fb, ms, k0);
-              tma_load_2d(dS + BK * 128, &maps.a[term], fb, ms + 64, k0);
+              load(dS, &maps.a[term], fb, ms, k0);
+              load(dS + BK * 128, &maps.a[term], fb, ms + 64, k0);
             }
           }
           if (!g.b_mn) {
-            tma_load_2d(dB, &maps.b[term], fb, k0, n0);
+            load(dB, &maps.b[term], fb, k0, nb0);
           } else {
-            tma_load_2d(dB, &maps.b[term], fb, n0, k0);
-            tma_load_2d(dB + BK * 128, &maps.b[term], fb, n0 + 64, k0);
+            load(dB, &maps.b[term], fb, nb0, k0);
+            load(dB + BK * 128, &maps.b[term], fb, nb0 + 64, k0);
           }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ---------------- MMA issuer ----------------
+    if (lane == 0 && cta_rank == 0) {
+      // ---------------- MMA issuer (pairs: the leader CTA only) ----------------
+      auto commit = [&](uint32_t bar) {
+        if (CG == 2) umma_commit_pair(bar);
+        else umma_commit(bar);
+      };
       int it = 0, uses[2] = {0, 0}, j = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
+      for (int t = tile_first; t < total; t += tile_stride, ++j) {
         int pi, m0, n0, kb0, nkb;
         tile_info(t, pi, m0, n0, kb0, nkb);
         if (nkb == 0) continue;                       // epilogue-only tile: the accumulator is not involved
         const GemmArgs& g = grp.args[pi];
-        const uint32_t idesc = make_idesc(g.a_mn != 0, g.b_mn != 0);
+        const uint32_t idesc = CG == 2 ? make_idesc(g.a_mn != 0, g.b_mn != 0, 2 * BM, 2 * BN) : make_idesc(g.a_mn != 0, g.b_mn != 0);
         const uint32_t a_step = g.a_mn ? (UMMA_K * 128) : (UMMA_K * 2);   // bytes per 16-wide k step
         const uint32_t b_step = g.b_mn ? (UMMA_K * 128) : (UMMA_K * 2);
         const int ab = j & 1;
         mbar_wait(acc_empty(ab), ((uint32_t)uses[ab] & 1u) ^ 1u);   // epilogue has drained this accumulator
         ++uses[ab];
         tc_fence_after();
-        const uint32_t acc = tmem_base + (uint32_t)ab * (MT * BN);
+        const uint32_t acc = tmem_base + (uint32_t)ab * S::ACC_COLS;
         for (int i = 0; i < nkb * g.terms; ++i, ++it) {
           const int s = it % STAGES;
           const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
@@ -342,14 +373,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t db = make_smem_desc(aB + k * b_step, g.b_mn != 0);
+            if (CG == 2) {
+              umma_bf16_pair(acc, make_smem_desc(aA + k * a_step, g.a_mn != 0), db, idesc, (i | k) != 0 ? 1u : 0u);
+            } else {
 #pragma unroll
-            for (int sub = 0; sub < MT; ++sub)
-              umma_bf16(acc + sub * BN, make_smem_desc(aA + sub * SUB_A + k * a_step, g.a_mn != 0), db, idesc, (i | k) != 0 ? 1u : 0u);
+              for (int sub = 0; sub < MT; ++sub)
+                umma_bf16(acc + sub * BN, make_smem_desc(aA + sub * SUB_A + k * a_step, g.a_mn != 0), db, idesc, (i | k) != 0 ? 1u : 0u);
+            }
           }
-          umma_commit(empty_bar(s));   // slot reusable once these MMAs have read it
+          commit(empty_bar(s));        // slot reusable (in both CTAs of a pair) once these MMAs have read it
         }
-        umma_commit(acc_full(ab));     // accumulator complete
-        if (dbg != nullptr && blockIdx.x == 0 && j * MT < 64) dbg[j * MT * 8 + 7] = clock64();
+        commit(acc_full(ab));          // accumulator complete (signalled to the epilogue warps of both CTAs)
+        if (dbg != nullptr && blockIdx.x == 0 && j * UNITS < 64) dbg[j * UNITS * 8 + 7] = clock64();
       }
     }
   } else if (warp == 2) {
@@ -358,27 +393,29 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       // announce(j): staging buffer j % NBUF is free (its previous store has been read out) -> TMA-load the aux tile into it
       // (completing `ready`), or just arrive on `ready` when the epilogue needs no aux tile.
       // A CTA tile is MT units of 128 rows; units are staged / stored one at a time through the NBUF staging buffers.
+      // unit `sub` of a tile: rows m0 + (sub / NT) * 128, columns n0 + (sub % NT) * 128
       auto announce = [&](int t, int sub, int sb) {
         int pi, m0, n0, kb0, nkb;
         tile_info(t, pi, m0, n0, kb0, nkb);
         const GemmArgs& g = grp.args[pi];
         const TmapPack& maps = grp.maps[pi];
-        const int ncols = min(BN, g.n_out - n0);
+        const int nu = n0 + (sub % NT) * BN;
+        const int ncols = max(0, min(BN, g.n_out - nu));
         const int nbox = (ncols + BOXC - 1) / BOXC;
         if (AUX) {
           mbar_expect_tx(ready_bar(sb), (uint32_t)nbox * BOX_BYTES);
           for (int bx = 0; bx < nbox; ++bx)
-            tma_load_2d(stg + sb * P::TILE_BYTES + bx * BOX_BYTES, &maps.aux, ready_bar(sb), n0 + bx * BOXC, m0 + sub * BM);
+            tma_load_2d(stg + sb * P::TILE_BYTES + bx * BOX_BYTES, &maps.aux, ready_bar(sb), nu + bx * BOXC, m0 + (sub / NT) * BM);
         } else {
           mbar_arrive(ready_bar(sb));
         }
       };
-      int un = 0, t = blockIdx.x, sub = 0;
+      int un = 0, t = tile_first, sub = 0;
       if (t < total) announce(t, 0, 0);
       while (t < total) {
         const int sb = un % NBUF;
         int tn = t, subn = sub + 1;
-        if (subn == MT) subn = 0, tn = t + gridDim.x;
+        if (subn == UNITS) subn = 0, tn = t + tile_stride;
         if (NBUF == 2 && tn < total) {
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // store of unit un-1 (same buffer as un+1) has been read
           announce(tn, subn, (un + 1) % NBUF);
@@ -387,18 +424,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         tile_info(t, pi, m0, n0, kb0, nkb);
         const GemmArgs& g = grp.args[pi];
         const TmapPack& maps = grp.maps[pi];
-        const int ms = m0 + sub * BM;
-        const int ncols = min(BN, g.n_out - n0);
+        const int ms = m0 + (sub / NT) * BM, nu = n0 + (sub % NT) * BN;
+        const int ncols = max(0, min(BN, g.n_out - nu));
         const int nbox = (ncols + BOXC - 1) / BOXC;
         if (dbg != nullptr && blockIdx.x == 0 && un < 64) dbg[un * 8 + 5] = clock64();   // store warp starts waiting for unit un
         mbar_wait(staged_bar(sb), (uint32_t)(un / NBUF) & 1u);               // epilogue has staged unit un
         const uint32_t src = stg + sb * P::TILE_BYTES;
         for (int bx = 0; bx < nbox; ++bx) {
           if (EPI == VSX_EPI_ATOMIC) {
-            tma_reduce_add_2d(&maps.out, src + bx * BOX_BYTES, n0 + bx * BOXC, ms);
+            tma_reduce_add_2d(&maps.out, src + bx * BOX_BYTES, nu + bx * BOXC, ms);
           } else {
-            tma_store_2d(&maps.out, src + bx * BOX_BYTES, n0 + bx * BOXC, ms);
-            if (EPI == VSX_EPI_GELU) tma_store_2d(&maps.out2, src + (NBOX + bx) * BOX_BYTES, n0 + bx * BOXC, ms);
+            tma_store_2d(&maps.out, src + bx * BOX_BYTES, nu + bx * BOXC, ms);
+            if (EPI == VSX_EPI_GELU) tma_store_2d(&maps.out2, src + (NBOX + bx) * BOX_BYTES, nu + bx * BOXC, ms);
           }
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -427,28 +464,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       for (int i = et; i < grp.args[0].n_out; i += EPI_WARPS * 32) colacc[i] = 0.f;
       named_bar_sync(1, EPI_WARPS * 32);
     }
+    const uint32_t acc_empty_leader = CG == 2 ? mapa_cluster(acc_empty(0), 0) : 0u;      // + 8 * ab
+    float va[32];                                     // one 32-column chunk of this thread's accumulator row
     int uses[2] = {0, 0}, j = 0;
-    for (int t = blockIdx.x; t < total; t += gridDim.x, ++j) {
-      int pi, m0, n0, kb0, nkb;
-      tile_info(t, pi, m0, n0, kb0, nkb);
+    for (int t = tile_first; t < total; t += tile_stride, ++j) {
+      int pi, m0, n0t, kb0, nkb;
+      tile_info(t, pi, m0, n0t, kb0, nkb);
       const GemmArgs& g = grp.args[pi];
       const int lim = g.n_keep < g.N ? g.n_keep : g.N;
       const bool has_mma = nkb > 0;
       const int ab = j & 1;
-      const int ncols = min(BN, g.n_out - n0);
-      float* bs = bias_s + ab * BN;
-      if (et < BN) bs[et] = (g.bias != nullptr && n0 + et < g.N) ? __ldg(g.bias + n0 + et) : 0.f;
+      float* bst = bias_s + ab * TILE_N;
+      if (et < TILE_N) bst[et] = (g.bias != nullptr && n0t + et < g.N) ? __ldg(g.bias + n0t + et) : 0.f;
       named_bar_sync(1, EPI_WARPS * 32);                           // bias tile visible
       if (has_mma) {
         mbar_wait(acc_full(ab), (uint32_t)uses[ab] & 1u);
         ++uses[ab];
         tc_fence_after();
       }
-      if (dbg != nullptr && blockIdx.x == 0 && warp == EPI0 && lane == 0 && j * MT < 64) dbg[j * MT * 8 + 4] = clock64();
+      if (dbg != nullptr && blockIdx.x == 0 && warp == EPI0 && lane == 0 && j * UNITS < 64) dbg[j * UNITS * 8 + 4] = clock64();
 #pragma unroll 1
-      for (int sub = 0; sub < MT; ++sub) {
-        const int un = j * MT + sub, sb = un % NBUF;
-        const int ms = m0 + sub * BM, m = ms + row;
+      for (int sub = 0; sub < UNITS; ++sub) {
+        const int un = j * UNITS + sub, sb = un % NBUF;
+        const int ms = m0 + (sub / NT) * BM, m = ms + row;
+        const int n0 = n0t + (sub % NT) * BN;
+        const int ncols = max(0, min(BN, g.n_out - n0));
+        const float* bs = bst + (sub % NT) * BN;
         const bool stamp = dbg != nullptr && blockIdx.x == 0 && warp == EPI0 && lane == 0 && un < 64;
         if (stamp) dbg[un * 8 + 0] = clock64();
         mbar_wait(ready_bar(sb), (uint32_t)(un / NBUF) & 1u);      // staging buffer writable (and aux tile landed)
@@ -457,17 +498,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         uint8_t* tile2 = tile + NBOX * BOX_BYTES;
         float scale = 1.0f;
         if (EPI == VSX_EPI_RESIDUAL && g.row_scale != nullptr && m < g.M) scale = __ldg(g.row_scale + m / g.rows_per_sample);
-        const uint32_t acc = tmem_base + (uint32_t)(ab * MT + sub) * BN + ((uint32_t)(q * 32) << 16);
-        for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
-          if (c >= ncols) break;
-          float v[32];
-          if (has_mma) {
-            tmem_ld32(acc + (uint32_t)c, v);
-            tmem_ld_wait();
-          } else {
-#pragma unroll
-            for (int jj = 0; jj < 32; ++jj) v[jj] = 0.f;
-          }
+        const uint32_t acc = tmem_base + (uint32_t)(ab * UNITS + sub) * BN + ((uint32_t)(q * 32) << 16);
+        // fused math of one 32-column chunk (columns c .. c+31 of the unit) held in v
+        auto process = [&](float (&v)[32], const int c) {
           const int n = n0 + c;
           // `full`: all 32 columns of the chunk are real output columns -- the common case runs without per-element predicates
           // (a predicated expensive expression compiles to one branch per element, which serialises the whole chunk)
@@ -541,16 +574,32 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
               if (n + lane < g.N) atomicAdd((use_colacc ? colacc : g.colsum) + n + lane, cs);
             }
           }
+        };
+        // (Software pipelining of the tensor-memory reads -- the next chunk's tcgen05.ld in flight while this one is processed -- was
+        // measured: no gain for STORE / GELU, 6 % slower for GELU' (84 extra live registers); the epilogue warps are latency bound by
+        // their dependent FMA chains, not by the TMEM port.  tools/gemm_timeline.py, profiles/r2_gemm_epilogue.md.)
+        for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 32) {
+          if (c >= ncols) break;
+          if (has_mma) {
+            tmem_ld32(acc + (uint32_t)c, va);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 32; ++jj) va[jj] = 0.f;
+          }
+          process(va, c);
         }
         if (stamp) dbg[un * 8 + 2] = clock64();
-        if (has_mma && sub == MT - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(acc_empty(ab));               // this warp's TMEM reads of the accumulator set are done
-        }
         fence_proxy_async();                                       // generic-proxy smem writes -> visible to the TMA (async proxy)
+        if (has_mma && sub == UNITS - 1) tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(staged_bar(sb));                // 8 warps -> the store warp may ship the unit
+        if (lane == 0) {
+          mbar_arrive(staged_bar(sb));                             // 8 warps -> the store warp may ship the unit
+          if (has_mma && sub == UNITS - 1) {                       // this warp's TMEM reads of the accumulator set are done
+            if (CG == 2) mbar_arrive_cluster(acc_empty_leader + 8u * ab);
+            else mbar_arrive(acc_empty(ab));
+          }
+        }
         if (stamp) dbg[un * 8 + 3] = clock64();
       }
     }
@@ -563,67 +612,113 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
   }
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  if (CG == 2) {
+    cluster_sync_all();          // neither CTA may exit (or free tensor memory) while its peer can still signal its barriers / write its TMEM
+    if (warp == 1) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+  } else {
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, TMEM_COLS);
+  }
 }
 
 constexpr int MAX_GROUP = 4;
 
-template <int EPI, typename OutT, int MT, int G>
+template <int EPI, typename OutT, int MT, int G, int CG>
 int launch_g(const Group<G>& grp, cudaStream_t st) {
-  using P = Plan<EPI, OutT, MT>;
+  using P = Plan<EPI, OutT, MT, CG>;
+  auto kern = gemm_tc_kernel<EPI, OutT, MT, G, CG>;
   static bool configured = false;   // benign race: attribute set is idempotent
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI, OutT, MT, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM);
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM);
     if (e != cudaSuccess) {
       set_error("vsx_gemm: cudaFuncSetAttribute(%d) failed: %s", P::SMEM, cudaGetErrorString(e));
       return VSX_ERR_CUDA;
     }
     configured = true;
   }
-  const int grid = grp.total < num_sms() ? grp.total : num_sms();
-  gemm_tc_kernel<EPI, OutT, MT, G><<<grid, GEMM_THREADS, P::SMEM, st>>>(grp);
+  if (CG == 1) {
+    const int grid = grp.total < num_sms() ? grp.total : num_sms();
+    kern<<<grid, GEMM_THREADS, P::SMEM, st>>>(grp);
+    return check_launch("vsx_gemm");
+  }
+  // CTA pairs: clusters of two CTAs (the two SMs of a TPC), one cluster per tile at a time
+  const int pairs = num_sms() / 2;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * (grp.total < pairs ? grp.total : pairs));
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = P::SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr, cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, grp);
+  if (e != cudaSuccess) {
+    set_error("vsx_gemm: cluster launch failed: %s", cudaGetErrorString(e));
+    return VSX_ERR_CUDA;
+  }
   return check_launch("vsx_gemm");
 }
 
 // Tile shape and reduction splits for a list of problems that run in one launch.
-//  * forward / dgrad: 256-row CTA tiles when they still fill the machine at least once; 128-row tiles for small problems.
-//  * weight gradients (ATOMIC): few output tiles, long reductions.  256-row tiles unless the second sub-tile would be mostly padding;
-//    the reductions are then split so that about two work items per SM exist over ALL problems (split_k > 1 only permits splitting).
+//  * CTA pairs (256 x 256 tiles, cta_group::2) when those tiles fill the machine's 74 SM pairs at least once: the fewest shared-memory
+//    fill bytes and MMA operand reads per flop;
+//  * else 256 x 128 single-CTA tiles when they fill the 148 SMs at least once; 128 x 128 tiles for small problems;
+//  * weight gradients (ATOMIC): few output tiles, long reductions: the reductions are split so that about two work items per SM
+//    (pair) exist over ALL problems (split_k > 1 only permits splitting).
 template <int EPI, typename OutT, int G>
 int launch(Group<G>& grp, cudaStream_t st) {
-  int t128 = 0, t256 = 0;
+  int t128 = 0, t256 = 0, tpair = 0, max_kb = 0;
+  long m_sum = 0;
   for (int q = 0; q < grp.count; ++q) {
     const int tn = ceil_div(grp.args[q].n_out, BN);
     t128 += ceil_div(grp.args[q].M, BM) * tn, t256 += ceil_div(grp.args[q].M, 2 * BM) * tn;
+    tpair += ceil_div(grp.args[q].M, 2 * BM) * ceil_div(grp.args[q].n_out, 2 * BN);
+    max_kb = grp.args[q].num_kb * grp.args[q].terms > max_kb ? grp.args[q].num_kb * grp.args[q].terms : max_kb;
+    m_sum += grp.args[q].M;
   }
-  bool mt2;
+  static const int env_cg = getenv("VSX_GEMM_CTA_GROUP") ? atoi(getenv("VSX_GEMM_CTA_GROUP")) : 0;
+  const int force_cg = g_force_cg != 0 ? g_force_cg : env_cg;
+  const int pairs = num_sms() / 2;
+  // Measured per shape on the bench step (tools/gemm_table.py with VSX_GEMM_CTA_GROUP=1 / 2, profiles/r2_gemm_cta_pairs.md): pairs win
+  // when their 256-wide column tiles waste no more padding than 128-wide ones (0.70-0.95 x the single-CTA time; most at long
+  // reductions, where the operand fill dominates), and lose 5-20 % when a third or a fifth column tile of 128 becomes a half-empty
+  // pair tile (n_out = 384, 640) -- unless the reduction is long enough (K >= 1536) for the fill savings to outweigh the padding.
+  // area of the padded output in 128 x 128 units: 2 * t256 (256 x 128 tiles) vs 4 * tpair (256 x 256 tiles)
+  const bool no_extra_padding = 4 * tpair <= 2 * t256;
+  bool mt2, cg2;
   if (EPI == VSX_EPI_ATOMIC) {
-    mt2 = g_force_mt == 2 || (g_force_mt == 0 && 2 * t256 * 5 <= t128 * 6);
+    // weight gradients: pairs only for small row counts without extra padding (0.78-0.96 x); larger ones measured 4-8 % slower
+    cg2 = force_cg == 2 || (force_cg == 0 && g_force_mt == 0 && no_extra_padding && m_sum <= 1024 && 4 * tpair * 5 <= t128 * 6);
+    mt2 = !cg2 && (g_force_mt == 2 || (g_force_mt == 0 && 2 * t256 * 5 <= t128 * 6));
     static const int per_sm = getenv("VSX_WGRAD_ITEMS_PER_SM") ? atoi(getenv("VSX_WGRAD_ITEMS_PER_SM")) : 2;
-    const int tiles_mn = mt2 ? t256 : t128;
+    const int tiles_mn = cg2 ? tpair : (mt2 ? t256 : t128);
+    const int units = cg2 ? pairs : num_sms();
     for (int q = 0; q < grp.count; ++q) {
       GemmArgs& g = grp.args[q];
-      if (mt2 || grp.count > 1) {        // single 128-row problems keep the caller's split (tuned for that shape)
+      if (cg2 || mt2 || grp.count > 1) {        // single 128-row problems keep the caller's split (tuned for that shape)
         if (g.split_k > 1) {
-          const int want = (per_sm * num_sms()) / (tiles_mn > 0 ? tiles_mn : 1);
+          const int want = (per_sm * units) / (tiles_mn > 0 ? tiles_mn : 1);
           g.split_k = want < 1 ? 1 : (want > g.num_kb ? g.num_kb : want);
         }
       }
     }
   } else {
-    mt2 = g_force_mt != 1 && (g_force_mt == 2 || t256 >= num_sms());
+    const bool fills = 2 * tpair >= pairs;      // at least half of the SM pairs get a tile (a 256 x 128 tiling of such a problem does not fill 148 SMs either)
+    cg2 = force_cg == 2 || (force_cg == 0 && g_force_mt == 0 && fills && (no_extra_padding || (max_kb >= 24 && 4 * tpair * 4 <= 2 * t256 * 5)));
+    mt2 = !cg2 && g_force_mt != 1 && (g_force_mt == 2 || t256 >= num_sms());
   }
   int total = 0;
   for (int q = 0; q < grp.count; ++q) {
     const GemmArgs& g = grp.args[q];
-    const int tm = ceil_div(g.M, mt2 ? 2 * BM : BM), tn = ceil_div(g.n_out, BN);
+    const int tm = ceil_div(g.M, (cg2 || mt2) ? 2 * BM : BM), tn = ceil_div(g.n_out, cg2 ? 2 * BN : BN);
     total += tm * tn * (EPI == VSX_EPI_ATOMIC ? g.split_k : 1);
     grp.tile_end[q] = total;
   }
   grp.total = total;
   if (total == 0) return VSX_OK;
-  return mt2 ? launch_g<EPI, OutT, 2, G>(grp, st) : launch_g<EPI, OutT, 1, G>(grp, st);
+  if (cg2) return launch_g<EPI, OutT, 1, G, 2>(grp, st);
+  return mt2 ? launch_g<EPI, OutT, 2, G, 1>(grp, st) : launch_g<EPI, OutT, 1, G, 1>(grp, st);
 }
 
 // One problem descriptor -> kernel arguments + tensor maps.  Returns VSX_OK, an error, or 1 when there is nothing to do.
@@ -741,6 +836,12 @@ extern "C" int vsx_gemm_debug_buffer(void* p) {
 extern "C" int vsx_gemm_force_tile_rows(int rows) {
   VSX_REQUIRE(rows == 0 || rows == 128 || rows == 256, "vsx_gemm_force_tile_rows: 0 (heuristic), 128 or 256");
   g_force_mt = rows / 128;
+  return VSX_OK;
+}
+
+extern "C" int vsx_gemm_force_cta_group(int cta_group) {
+  VSX_REQUIRE(cta_group == 0 || cta_group == 1 || cta_group == 2, "vsx_gemm_force_cta_group: 0 (heuristic), 1 or 2");
+  g_force_cg = cta_group;
   return VSX_OK;
 }
 

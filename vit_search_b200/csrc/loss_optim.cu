@@ -70,8 +70,8 @@ __global__ void scale_by_scalar_kernel(float* __restrict__ x, long n, const floa
 constexpr int ADAM_CHUNK = 16384;   // elements per CTA
 
 __global__ void __launch_bounds__(256) adamw_kernel(const vsx_adamw_tensor* __restrict__ tensors, const int* __restrict__ chunk_tensor,
-                                                    const int* __restrict__ chunk_index, float lr, float beta1, float beta2, float eps,
-                                                    float bc1, float bc2, const float* __restrict__ grad_scale_dev,
+                                                    const int* __restrict__ chunk_index, float lr, float beta1, float beta2, float omb1,
+                                                    float omb2, float eps, float bc1, float bc2, const float* __restrict__ grad_scale_dev,
                                                     const float* __restrict__ guard_dev, int* __restrict__ nonfinite_dev) {
   if (guard_dev != nullptr) {
     // finite-loss guard (engine.py:168-173): a step whose loss is inf / nan leaves parameters, moments, shadows and averages untouched
@@ -96,8 +96,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(const vsx_adamw_tensor* __re
   auto update = [&](float& p, float g, float& m, float& v) {
     g *= gs;
     p *= decay;
-    m = beta1 * m + (1.0f - beta1) * g;
-    v = beta2 * v + (1.0f - beta2) * g * g;
+    m = beta1 * m + omb1 * g;
+    v = beta2 * v + omb2 * g * g;
     p -= step * m / (sqrtf(v) * inv_sqrt_bc2 + eps);
   };
   // 16-byte path: 4 elements per thread per access (28 B/parameter of traffic is all this kernel does)
@@ -168,12 +168,15 @@ extern "C" int vsx_scale_by_scalar(float* x, long n, const float* scalar_dev, vo
 extern "C" int vsx_adamw_chunk_elems(void) { return ADAM_CHUNK; }
 
 extern "C" int vsx_adamw(const vsx_adamw_tensor* tensors_dev, const int* chunk_tensor_dev, const int* chunk_index_dev, int num_chunks,
-                         float lr, float beta1, float beta2, float eps, int step, const float* grad_scale_dev, const float* guard_loss_dev,
+                         double lr, double beta1, double beta2, double eps, int step, const float* grad_scale_dev, const float* guard_loss_dev,
                          int* nonfinite_count_dev, void* stream) {
   VSX_REQUIRE(step >= 1, "vsx_adamw: step counts from 1");
   if (num_chunks <= 0) return VSX_OK;
-  const float bc1 = (float)(1.0 - pow((double)beta1, (double)step)), bc2 = (float)(1.0 - pow((double)beta2, (double)step));
-  adamw_kernel<<<num_chunks, 256, 0, ST>>>(tensors_dev, chunk_tensor_dev, chunk_index_dev, lr, beta1, beta2, eps, bc1, bc2, grad_scale_dev, guard_loss_dev,
+  // hyper-parameters arrive as doubles so that 1 - beta is rounded ONCE, like torch.optim.AdamW (`value=1 - beta2` is evaluated in
+  // Python's double arithmetic): 1.0f - 0.999f is 1.3e-5 away from float(0.001)
+  const float bc1 = (float)(1.0 - pow(beta1, (double)step)), bc2 = (float)(1.0 - pow(beta2, (double)step));
+  adamw_kernel<<<num_chunks, 256, 0, ST>>>(tensors_dev, chunk_tensor_dev, chunk_index_dev, (float)lr, (float)beta1, (float)beta2,
+                                             (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, bc1, bc2, grad_scale_dev, guard_loss_dev,
                                              nonfinite_count_dev);
   return check_launch("vsx_adamw");
 }

@@ -98,7 +98,7 @@ class ChannelDrop(nn.Module):
         if self.fixed_keep is not None:
             return [self.fixed_keep] * batch
         if self.keep_table is None:
-            self.set_mask(like if like is not None else torch.empty(batch, 1, width, device='meta'))
+            self.set_mask(torch.empty(batch, 1, width, device='meta'))      # the table depends on (batch, width) only; `like` may be a narrower tensor
         perm = torch.randperm(len(self.keep_table)).tolist()
         if self.single_arch:
             return [self.keep_table[perm[0]]] * batch
