@@ -42,7 +42,10 @@ def parse():
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--space', default=SPACE)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--cpu-batch', type=int, default=8)
+    ap.add_argument('--cpu-batch', type=int, default=32)      # the largest sample of the 256-image step the host cores finish in a few seconds
+    ap.add_argument('--no-extra', dest='extra', action='store_false')      # skip the extra_configs block (other BASELINE configurations)
+    ap.add_argument('--extra-steps', type=int, default=6)
+    ap.add_argument('--evo-candidates', type=int, default=64)
     return ap.parse_args()
 
 
@@ -98,16 +101,25 @@ def cpu_steps(space, batch, steps, warmup):
     return batch / sec, sec * 1e3, cores
 
 
+def bench_config(args, world):
+    """The `config` block both arms print: the workload BASELINE.json's metric is quoted on."""
+    return {'workload': WORKLOAD, 'space': args.space, 'batch_per_gpu': args.batch, 'archs_per_step': 1, 'drop_path': DROP_PATH,
+            'optimizer': 'AdamW', 'parallelism': 'dp%d' % world}
+
+
 def run_reference(args):
+    """The reference's own CPU implementation of the path on the host cores (the oracle port: the reference is Python and does not
+    travel to the GPU box), all host threads, each step a BOUNDED sample (--cpu-batch images of the 256-image step)."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     ips, ms, cores = cpu_steps(args.space, args.cpu_batch, args.steps, args.warmup)
-    sample = 'oracle port, fp32, %d host threads, %d-image steps of the same model/space (bounded sample of the 256-image step)' % (cores, args.cpu_batch)
+    sample = ('oracle port (restated reference modules), fp32, %d host threads, %d steps (after %d warm-up) of %d images = a bounded sample of the '
+              '%d-image step of the same model / space / optimizer' % (cores, args.steps, args.warmup, args.cpu_batch, args.batch))
     print(json.dumps({
         'impl': 'reference', 'metric': METRIC, 'value': ips, 'unit': 'images/sec', 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-        'data': 'synthetic', 'config': {'workload': WORKLOAD, 'space': args.space, 'sample_batch': args.cpu_batch},
+        'data': 'synthetic', 'config': dict(bench_config(args, args.gpus), sample_batch=args.cpu_batch),
         'cpu_baseline': {'value': ips, 'unit': 'images/sec', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': ips, 'unit': 'images/sec', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}, 'gpu_launches': 0}))
 
@@ -158,7 +170,136 @@ class ClockSampler:
         return out
 
 
+def _synthetic_batch(B, rank, dev):
+    """ImageNet-shaped synthetic batch: pinned host tensors (images fp32 [B,3,224,224], soft targets [B,1000], per-patch soft targets
+    [B,16,1000] as SwitchTokenMix produces them) and device-resident copies."""
+    import torch
+    g = torch.Generator().manual_seed(1234 + rank)
+    hx = torch.randn(B, 3, 224, 224, generator=g).pin_memory()
+    y = torch.randint(0, 1000, (B,), generator=g)
+    ht = torch.full((B, 1000), 0.1 / 1000)
+    ht[torch.arange(B), y] += 0.9
+    hpt = ht.unsqueeze(1).repeat(1, 16, 1).contiguous().pin_memory()
+    ht = ht.pin_memory()
+    return (hx, ht, hpt), (hx.to(dev), ht.to(dev), hpt.to(dev))
+
+
+def _timed_steps(fn, n, world, dev):
+    """n calls of fn bracketed by barrier + synchronize on both sides; one CUDA event per step boundary on the compute stream.
+    -> (window ms = MAX over ranks, per-step ms list of this rank)."""
+    import torch
+    import torch.distributed as dist
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(n + 1)]
+    ev[0].record()
+    for i in range(n):
+        fn()
+        ev[i + 1].record()
+    barrier()
+    ms = torch.tensor([ev[0].elapsed_time(ev[n])], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return ms.item(), [ev[i].elapsed_time(ev[i + 1]) for i in range(n)]
+
+
+def _p50(v):
+    return statistics.median(v) if v else None
+
+
+def _extra_configs(args, world, rank, dev):
+    """The other BASELINE.json configurations at full size (few steps each, same --gpus N, device-resident inputs):
+    configs[2] sr_small with 4 architectures per step, configs[3] the searched Medium network with EMA, configs[4] forward-only
+    evaluation of sampled sub-networks on the resident sr_tiny_mh super-network.  Not the headline: parity cases made measurable."""
+    import random
+    import torch
+    import torch.distributed as dist
+    from vit_search_b200 import _lib, core, macs
+    from vit_search_b200 import supernet_config as sc
+    from vit_search_b200.engine import FusedAdamW, ModelEma, TrainStep, broadcast_parameters
+    from vit_search_b200.evo_eval import CandidateEvaluator, sample_candidate
+    from vit_search_b200.nets import create_model
+    B = args.batch
+    out = {}
+    _, (x, t, pt) = _synthetic_batch(B, rank, dev)
+    W, K = 3, args.extra_steps
+
+    def train_case(name, model, mode, ema=None, note=''):
+        model.train()
+        if world > 1:
+            broadcast_parameters(model)
+        opt = FusedAdamW(model, lr=LR * B * world / 512.0, weight_decay=WD)
+        step = TrainStep(model, opt, arch_sample=mode, world_size=world, model_ema=ema)
+        for _ in range(W):
+            step(x, t, pt, epoch=0)
+        l0 = _lib.lib().vsx_launch_count()
+        ms, per = _timed_steps(lambda: step(x, t, pt, epoch=0), K, world, dev)
+        launches = _lib.lib().vsx_launch_count() - l0
+        loss = step(x, t, pt, epoch=0)
+        step.check_finite()
+        out[name] = {'value': world * B * K / (ms * 1e-3), 'unit': 'images/sec', 'ms_per_step': ms / K, 'ms_per_step_p50': _p50(per),
+                     'steps': K, 'warmup': W, 'loss': float(loss), 'gpu_launches_per_step': launches // K, 'config': note}
+        del step, opt
+
+    # configs[2]: ViT-ResNAS-Small supernet, multi-arch sampling, 4 architectures per step
+    nd, ks = sc.network_def('sr_small'), sc.num_channels_to_keep('sr_small')
+    torch.manual_seed(0)
+    m = create_model('flexible_vit_sr_patch14_224_patch_output_supernet', network_def=nd, num_classes=1000, drop_rate=0., drop_path_rate=0.3,
+                     num_channels_to_keep=ks, example_per_arch=B // 4, num_warmup_epochs=0, single_arch=False).to(dev)
+    m.set_epoch(0)
+    train_case('sr_small_4archs', m, 'multi', note='ViT-ResNAS-Small supernet (sr_small), multi-arch sampling, 4 archs/step, bs=%d/GPU, bf16, drop-path 0.3' % B)
+    del m
+    # the headline space with 4 architectures per step (north star: the multi-architectural-sampling inner loop)
+    nd, ks = sc.network_def('sr_tiny'), sc.num_channels_to_keep('sr_tiny')
+    torch.manual_seed(0)
+    m = create_model('flexible_vit_sr_patch14_224_patch_output_supernet', network_def=nd, num_classes=1000, drop_rate=0., drop_path_rate=DROP_PATH,
+                     num_channels_to_keep=ks, example_per_arch=B // 4, num_warmup_epochs=0, single_arch=False).to(dev)
+    m.set_epoch(0)
+    train_case('sr_tiny_4archs', m, 'multi', note='ViT-ResNAS-Tiny supernet (sr_tiny), multi-arch sampling, 4 archs/step, bs=%d/GPU, bf16' % B)
+    del m
+    # configs[3]: searched ViT-ResNAS-Medium network (4.6 G MACs), dense, EMA on
+    torch.manual_seed(0)
+    m = create_model('flexible_vit_sr_patch14_224_patch_output', network_def=sc.VIT_RESNAS_MEDIUM, num_classes=1000, drop_path_rate=0.3).to(dev)
+    ema = ModelEma(m)
+    train_case('medium_4g6_dense_ema', m, None, ema=ema,
+               note='searched ViT-ResNAS-Medium network_def (4.6 G MACs, %.2f G counted), dense, EMA on, bs=%d/GPU, bf16, drop-path 0.3' % (macs.network_macs(sc.VIT_RESNAS_MEDIUM) / 1e9, B))
+    del m, ema
+    torch.cuda.empty_cache()
+    # configs[4]: evolutionary-search candidate evaluation, forward only, on the RESIDENT super-network weights
+    nd, ks = sc.network_def('sr_tiny_mh'), sc.num_channels_to_keep('sr_tiny_mh')
+    torch.manual_seed(0)
+    m = create_model('flexible_vit_sr_patch14_224_patch_output', network_def=nd, num_classes=1000).to(dev).eval()
+    if world > 1:
+        broadcast_parameters(m)
+    evl = CandidateEvaluator(m, dev)
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    loader = [(torch.randn(B, 3, 224, 224, device=dev, generator=g), torch.randint(0, 1000, (B,), device=dev, generator=g)) for _ in range(2)]
+    rng = random.Random(0)                         # every rank scores the same candidates on its own shard of the sub-val set
+    cands = [sample_candidate(nd, ks, rng) for _ in range(args.evo_candidates)]
+    evl.score(cands[0], loader)
+    evl.score(nd, loader)
+    state = {'i': 0, 'acc': []}
+
+    def one():
+        state['acc'].append(evl.score(cands[state['i']], loader)['acc1'])
+        state['i'] += 1
+    ms, per = _timed_steps(one, len(cands), world, dev)
+    n_img = world * len(cands) * len(loader) * B
+    out['evo_eval_sr_tiny_mh'] = {'value': n_img / (ms * 1e-3), 'unit': 'images/sec', 'candidates': len(cands), 'images_per_candidate': world * len(loader) * B,
+                                  'ms_per_candidate': ms / len(cands), 'ms_per_candidate_p50': _p50(per),
+                                  'config': 'evolutionary-search eval: %d sampled sub-nets (uniform draws from sr_tiny_mh), forward only, synthetic sub-val of %d images per candidate, resident '
+                                            'super-network weights, CE / top-1 / top-5 meters summed over ranks once per candidate' % (len(cands), world * len(loader) * B)}
+    del m, evl
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
+    import gc
     import torch
     import torch.distributed as dist
     from vit_search_b200 import _lib, core, ops, macs
@@ -172,12 +313,14 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit('bench.py: no CUDA device -- the product path has no CPU fallback (use --impl reference for the CPU arm)')
     torch.cuda.set_device(local)
-    ops.set_device(local)
     _lib.check(_lib.lib().vsx_device_ok(local))
+    dev = torch.device('cuda', local)
     if world > 1:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl')
-    dev = torch.device('cuda', local)
+        warm = torch.ones(1 << 20, device=dev)          # NCCL communicator / channel set-up is not a train step: do it before the warm-up
+        dist.all_reduce(warm)
+        torch.cuda.synchronize()
     B = args.batch
     nd, ks = sc.network_def(args.space), sc.num_channels_to_keep(args.space)
     torch.manual_seed(0)
@@ -196,36 +339,12 @@ def run_ours(args):
         broadcast_parameters(model)
     opt = FusedAdamW(model, lr=LR * B * world / 512.0, weight_decay=WD)
     step = TrainStep(model, opt, arch_sample='single', world_size=world, ddp_model=net if (world > 1 and use_ddp) else None)
-
-    g = torch.Generator().manual_seed(1234 + rank)
-    hx = torch.randn(B, 3, 224, 224, generator=g).pin_memory()
-    y = torch.randint(0, 1000, (B,), generator=g)
-    ht = torch.full((B, 1000), 0.1 / 1000)
-    ht[torch.arange(B), y] += 0.9
-    hpt = ht.unsqueeze(1).repeat(1, 16, 1).contiguous().pin_memory()
-    ht = ht.pin_memory()
-    x, t, pt = hx.to(dev), ht.to(dev), hpt.to(dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, n):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(n):
-            fn()
-        e1.record()
-        barrier()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return ms.item()
+    (hx, ht, hpt), (x, t, pt) = _synthetic_batch(B, rank, dev)
+    step_macs = []
 
     def dev_step():
         step(x, t, pt, epoch=0)
+        step_macs.append(model.last_keeps)
 
     h_loss = torch.empty((), dtype=torch.float32).pin_memory()
 
@@ -241,21 +360,26 @@ def run_ours(args):
         feeder.release()
         h_loss.copy_(loss, non_blocking=True)
 
-    n_warm = max(args.warmup, 3 if world == 1 else 8)   # DDP rebuilds its buckets after the first backward and the caching
+    n_warm = max(args.warmup, 3)                          # exactly the driver's W (the contract asks for W >= 3)
     clocks = ClockSampler(local) if rank == 0 else None   # started before the warm-up: nvidia-smi needs ~0.2 s to deliver its first sample
-    for _ in range(n_warm):                              # allocator needs a few steps to settle: extra untimed steps when N > 1
+    for _ in range(n_warm):
         dev_step()
-    ops.LAUNCHES = 0
+    gc.collect()
+    gc.disable()                                          # a collector pause of the launching thread inside the window is not a property of the step
+    step_macs.clear()
     launches0 = _lib.lib().vsx_launch_count()
-    ms = timed(dev_step, args.steps)
+    ms, per_step = _timed_steps(dev_step, args.steps, world, dev)
     launches = _lib.lib().vsx_launch_count() - launches0      # kernels launched by libvsx.so (counted in csrc/api.cu: check_launch)
+    timed_keeps = list(step_macs)
     clk = clocks.stop() if clocks is not None else None
     feeder.submit(hx, ht, hpt)
     e2e_step()
-    ms_e2e = timed(e2e_step, args.steps)       # K steps = K uploads + K train steps + K loss read-backs inside the window
+    ms_e2e, per_step_e2e = _timed_steps(e2e_step, args.steps, world, dev)       # K steps = K uploads + K train steps + K loss read-backs
     feeder.next(), feeder.release()            # drain the batch left in flight
     torch.cuda.synchronize()
+    gc.enable()
     loss_val = float(h_loss)
+    step.check_finite()
 
     # ---- roofline of the dominant kernel: CUDA events around every tensor-core GEMM launch of 2 further steps
     ops.PROFILE = []
@@ -266,31 +390,32 @@ def run_ours(args):
     gemm_flops = sum(r[2] for r in ops.PROFILE)
     gemm_bytes = sum(r[4] for r in ops.PROFILE)
     n_gemm = len(ops.PROFILE)
-    pk0 = peaks()
-    # two-resource roofline of the same launches: each launch can be no faster than max(flops / tensor peak, bytes / HBM peak)
-    gemm_floor_ms = sum(max(r[2] / (pk0['tflops'] * 1e12), r[4] / (pk0['hbm'] * 1e9)) for r in ops.PROFILE) * 1e3
-    n_hbm_bound = sum(1 for r in ops.PROFILE if r[4] / (pk0['hbm'] * 1e9) > r[2] / (pk0['tflops'] * 1e12))
-    ops.PROFILE = None
-    keeps = model.last_keeps
-    step_macs = sum(macs.network_macs(macs.effective_network_def(nd, keeps, b)) for b in range(B))
     pk = peaks()
+    # two-resource roofline of the same launches: each launch can be no faster than max(flops / tensor peak, bytes / HBM peak)
+    gemm_floor_ms = sum(max(r[2] / (pk['tflops'] * 1e12), r[4] / (pk['hbm'] * 1e9)) for r in ops.PROFILE) * 1e3
+    n_hbm_bound = sum(1 for r in ops.PROFILE if r[4] / (pk['hbm'] * 1e9) > r[2] / (pk['tflops'] * 1e12))
+    ops.PROFILE = None
+    # algorithmic MACs of the TIMED steps (every step samples its own sub-network): mean over exactly those steps
+    mean_macs = statistics.mean(B * macs.network_macs(macs.effective_network_def(nd, k, 0)) for k in timed_keeps) if timed_keeps else 0.0
     ms_step = ms / args.steps
     achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    extra = _extra_configs(args, world, rank, dev) if args.extra else None
 
     if rank == 0:
         out = {
             'metric': METRIC, 'value': world * B * args.steps / (ms * 1e-3), 'unit': 'images/sec', 'n_gpus': world, 'steps': args.steps,
-            'warmup': n_warm, 'ms_per_step': ms_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'warmup': n_warm, 'ms_per_step': ms_step, 'ms_per_step_p50': _p50(per_step), 'ms_per_step_min': min(per_step), 'ms_per_step_max': max(per_step),
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'bf16', 'data': 'synthetic',
-            'config': {'workload': WORKLOAD, 'space': args.space, 'batch_per_gpu': B, 'archs_per_step': 1, 'drop_path': DROP_PATH,
-                       'optimizer': 'AdamW (fused)', 'parallelism': 'dp%d' % world,
-                       'grad_exchange': 'none' if world == 1 else ('torch DDP' if use_ddp else 'in-place NCCL all-reduce of the flat gradient pool, overlapped with the stem backward'),
-                       'l2': 'inputs larger than L2: every step streams >10 GB of activations, no tensor survives in the 126 MB L2'},
+            'config': dict(bench_config(args, world),
+                       grad_exchange= 'none' if world == 1 else ('torch DDP' if use_ddp else 'in-place NCCL all-reduce of the flat gradient pool, staged per stage and overlapped with the backward'),
+                       l2='inputs larger than L2: every step streams >10 GB of activations, no tensor survives in the 126 MB L2',
+                       timing='one CUDA event per step boundary; ms_per_step = window / K (the value), ms_per_step_p50 = median of the K step times of rank 0'),
             'e2e': {'value': world * B * args.steps / (ms_e2e * 1e-3), 'unit': 'images/sec',
                     'h2d_bytes_per_step': hx.numel() * 4 + ht.numel() * 4 + hpt.numel() * 4, 'd2h_bytes_per_step': 4,
-                    'ms_per_step': ms_e2e / args.steps},
+                    'ms_per_step': ms_e2e / args.steps, 'ms_per_step_p50': _p50(per_step_e2e)},
             'gpu_launches': launches,
-            'roofline': {'bound': 'tensor', 'kernel': 'gemm_tc_kernel (tcgen05 GEMM, all epilogues: fwd, dgrad, wgrad)',
+            'roofline': {'bound': 'tensor', 'kernel': 'gemm_tc_kernel (tcgen05 GEMM, all epilogues: fwd, dgrad, wgrad; single-CTA and cta_group::2 tiles)',
                          'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],
                          'traffic': gemm_traffic(), 'algorithmic_bytes_per_launch': gemm_bytes / max(n_gemm, 1),
                          'hbm_view': {'achieved': gemm_bytes / (gemm_ms * 1e-3) / 1e9 if gemm_ms > 0 else 0.0, 'peak': pk['hbm'], 'unit': 'GB/s',
@@ -299,14 +424,17 @@ def run_ours(args):
                          'peak_source': pk['src'], 'launches_per_step': n_gemm // 2, 'kernel_ms_per_step': gemm_ms / 2,
                          'kernel_share_of_step': (gemm_ms / 2) / ms_step,
                          'how': 'algorithmic 2*M*N*K of the kept extents per launch / CUDA-event time of each launch, 2 instrumented steps after the timed region',
-                         'step_algorithmic_tflops': 6.0 * step_macs / (ms_step * 1e-3) / 1e12,
-                         'step_frac': 6.0 * step_macs / (ms_step * 1e-3) / 1e12 / pk['tflops']},
+                         'step_algorithmic_tflops': 6.0 * mean_macs / (ms_step * 1e-3) / 1e12,
+                         'step_frac': 6.0 * mean_macs / (ms_step * 1e-3) / 1e12 / pk['tflops'],
+                         'step_macs_how': 'mean algorithmic MACs of the sub-networks sampled in the K timed steps'},
             'clocks': clk, 'loss': loss_val,
         }
+        if extra is not None:
+            out['extra_configs'] = extra
         if not args.no_cpu_baseline and world == 1:
-            ips, cms, cores = cpu_steps(args.space, args.cpu_batch, 3, 1)
+            ips, cms, cores = cpu_steps(args.space, args.cpu_batch, 2, 1)
             out['cpu_baseline'] = {'value': ips, 'unit': 'images/sec', 'cores': cores, 'kind': 'port',
-                                   'sample': 'oracle port (restated reference modules), fp32, %d-image steps x3 of the same model/space, %.0f ms/step' % (args.cpu_batch, cms)}
+                                   'sample': 'oracle port (restated reference modules), fp32, %d-image steps x2 (after 1 warm-up) of the same model/space, %.0f ms/step' % (args.cpu_batch, cms)}
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()

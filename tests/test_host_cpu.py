@@ -253,7 +253,7 @@ def test_random_search_candidates_fit_the_supernet():
     import random
     import sys
     sys.path.insert(0, os.path.join(ROOT, 'tools'))
-    from evo_eval_bench import sample_candidate
+    from vit_search_b200.evo_eval import sample_candidate
     from vit_search_b200 import supernet_config as sc
     from vit_search_b200.nets import create_model
     nd, ks = sc.network_def('sr_tiny'), sc.num_channels_to_keep('sr_tiny')

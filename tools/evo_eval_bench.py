@@ -9,33 +9,6 @@ import time
 import torch
 
 
-def sample_candidate(nd, ks, rng):
-    """A random dense sub-network definition of the search space (uniform choice per entry; a removed block removes the removable
-    blocks that follow it in the stage, like search_utils/gen_utils.update_depth)."""
-    out, width, removing = [], None, False
-    for d, k in zip(nd, ks):
-        if d[0] in (0, 4, 5):
-            width = int(rng.choice(list(k)))
-            out.append((d[0], width) + tuple(d[2:]))
-        elif d[0] == 1:
-            hd = d[1][2]
-            heads = int(rng.choice(list(k['attn']))) // hd
-            feat = int(rng.choice(list(k['mlp'])))
-            exists = 1
-            if k.get('layer') is None:
-                removing = False
-            elif removing or int(rng.choice(list(k['layer']))) == 0:
-                exists, removing = 0, True
-            out.append((1, (width, heads, hd), (width, feat), exists))
-        elif d[0] == 3:
-            nxt = int(rng.choice(list(k)))
-            out.append((3, width, nxt))
-            width, removing = nxt, False
-        else:
-            out.append((2, width, d[2]))
-    return tuple(out)
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--space', default='sr_tiny')
@@ -45,7 +18,7 @@ def main():
     args = ap.parse_args()
     from vit_search_b200 import supernet_config as sc, _lib
     from vit_search_b200.nets import create_model
-    from vit_search_b200.evo_eval import CandidateEvaluator
+    from vit_search_b200.evo_eval import CandidateEvaluator, sample_candidate
     nd, ks = sc.network_def(args.space), sc.num_channels_to_keep(args.space)
     torch.manual_seed(0)
     model = create_model('flexible_vit_sr_patch14_224_patch_output', network_def=nd, num_classes=1000).cuda().eval()

@@ -1,6 +1,7 @@
 // C-ABI plumbing shared by all kernels: error text, launch checks, TMA descriptor encoding.
 #include <cudaTypedefs.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -26,6 +27,11 @@ int check_launch(const char* what) {
     return VSX_ERR_CUDA;
   }
   return VSX_OK;
+}
+
+bool pdl_enabled() {
+  static const bool on = !(getenv("VSX_PDL") != nullptr && atoi(getenv("VSX_PDL")) == 0);
+  return on;
 }
 
 int num_sms() {

@@ -98,6 +98,8 @@ __device__ __forceinline__ void zero_slice(T* dst, long ld, int N, int D) {
 template <int D>
 __global__ void __launch_bounds__(256, 2) attn_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ o, float* __restrict__ lse, int N, int H, int Hk,
                                     float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t smem[];
   const int h = blockIdx.x, b = blockIdx.y;
   const long ldq = 3L * H * D, ldo = (long)H * D;
@@ -320,6 +322,8 @@ template <int D>
 __global__ void __launch_bounds__(384, 1) attn_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ d_o,
                                     const float* __restrict__ lse, bf16* __restrict__ dqkv, int N, int H, int Hk, float scale,
                                     float* __restrict__ dbias) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(16) uint8_t smem[];
   __shared__ float cs[3 * D];
   const int h = blockIdx.x, b = blockIdx.y;
@@ -430,7 +434,7 @@ int launch_fwd(const void* qkv, void* o, float* lse, int B, int N, int H, int Hk
     return VSX_ERR_CUDA;
   }
   cudaFuncSetAttribute(attn_fwd_mma_kernel<D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  attn_fwd_mma_kernel<D><<<dim3(H, B), warps_for(N, false) * 32, smem, st>>>((const bf16*)qkv, (bf16*)o, lse, N, H, Hk, scale);
+  launch_pdl(attn_fwd_mma_kernel<D>, dim3(dim3(H, B)), dim3(warps_for(N, false) * 32), smem, st, (const bf16*)qkv, (bf16*)o, lse, N, H, Hk, scale);
   return check_launch("vsx_attn_fwd");
 }
 template <int D>
@@ -443,7 +447,7 @@ int launch_bwd(const void* qkv, const void* o, const void* d_o, const float* lse
     set_error("vsx_attn_bwd: cudaFuncSetAttribute(%zu) failed: %s", smem, cudaGetErrorString(e));
     return VSX_ERR_CUDA;
   }
-  attn_bwd_mma_kernel<D><<<dim3(H, B), warps_for(N, true) * 32, smem, st>>>((const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse, (bf16*)dqkv, N,
+  launch_pdl(attn_bwd_mma_kernel<D>, dim3(dim3(H, B)), dim3(warps_for(N, true) * 32), smem, st, (const bf16*)qkv, (const bf16*)o, (const bf16*)d_o, lse, (bf16*)dqkv, N,
                                                                     H, Hk, scale, dbias);
   return check_launch("vsx_attn_bwd");
 }

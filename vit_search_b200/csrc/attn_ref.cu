@@ -40,6 +40,8 @@ template <typename T>
 __global__ void __launch_bounds__(AT_WARPS * 32) attn_fwd_ref_kernel(const T* __restrict__ qkv, T* __restrict__ o,
                                                                       float* __restrict__ lse, int N, int H, int D, int Hk,
                                                                       float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   const int h = blockIdx.x, b = blockIdx.y;
   const long ldq = 3L * H * D, ldo = (long)H * D;
@@ -98,6 +100,8 @@ template <typename T>
 __global__ void __launch_bounds__(AT_WARPS * 32) attn_bwd_ref_kernel(const T* __restrict__ qkv, const T* __restrict__ o,
                                                                       const T* __restrict__ d_o, const float* __restrict__ lse,
                                                                       T* __restrict__ dqkv, int N, int H, int D, int Hk, float scale) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   const int h = blockIdx.x, b = blockIdx.y;
   const long ldq = 3L * H * D, ldo = (long)H * D;
@@ -232,7 +236,7 @@ int attn_fwd_ref(const void* qkv, void* o, float* lse, int B, int N, int H, int 
   const size_t smem = fwd_smem(N, D);
   int rc = set_smem(attn_fwd_ref_kernel<T>, smem, "vsx_attn_fwd");
   if (rc) return rc;
-  attn_fwd_ref_kernel<T><<<dim3(H, B), AT_WARPS * 32, smem, st>>>((const T*)qkv, (T*)o, lse, N, H, D, Hk, scale);
+  launch_pdl(attn_fwd_ref_kernel<T>, dim3(dim3(H, B)), dim3(AT_WARPS * 32), smem, st, (const T*)qkv, (T*)o, lse, N, H, D, Hk, scale);
   return check_launch("vsx_attn_fwd");
 }
 template <typename T>
@@ -241,7 +245,7 @@ int attn_bwd_ref(const void* qkv, const void* o, const void* d_o, const float* l
   const size_t smem = bwd_smem(N, D);
   int rc = set_smem(attn_bwd_ref_kernel<T>, smem, "vsx_attn_bwd");
   if (rc) return rc;
-  attn_bwd_ref_kernel<T><<<dim3(H, B), AT_WARPS * 32, smem, st>>>((const T*)qkv, (const T*)o, (const T*)d_o, lse, (T*)dqkv, N, H, D, Hk, scale);
+  launch_pdl(attn_bwd_ref_kernel<T>, dim3(dim3(H, B)), dim3(AT_WARPS * 32), smem, st, (const T*)qkv, (const T*)o, (const T*)d_o, lse, (T*)dqkv, N, H, D, Hk, scale);
   return check_launch("vsx_attn_bwd");
 }
 

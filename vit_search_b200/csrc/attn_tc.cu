@@ -205,6 +205,7 @@ constexpr int F_SMEM = F_END + 1024 /*align*/ + 128 /*barriers*/ + 4 * 128 * 4 /
 constexpr int F_OCOL = 448;   // O accumulator columns 448..511; S occupies 0..287
 
 __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_tc_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -437,6 +439,7 @@ struct BwdCursor {   // position in this CTA's flattened (sample, key block, que
 };
 
 __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __grid_constant__ AttnMaps maps, const AttnArgs a) {
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -478,6 +481,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -817,7 +821,7 @@ int attn_fwd_tc(const void* qkv, void* o, float* lse, int B, int N, int H, int H
   a.B = B, a.N = N, a.H = H, a.Hk = Hk, a.scale = scale, a.o = (bf16*)o, a.d_o = nullptr, a.lse = lse, a.dqkv = nullptr, a.dbias = nullptr, a.dbg = nullptr;
   const int total = B * Hk;
   const int grid = total < num_sms() ? total : num_sms();
-  attn_fwd_tc_kernel<<<grid, ATT_THREADS, F_SMEM, st>>>(maps, a);
+  launch_pdl(attn_fwd_tc_kernel, dim3(grid), dim3(ATT_THREADS), F_SMEM, st, maps, a);
   return check_launch("vsx_attn_fwd");
 }
 
@@ -841,7 +845,7 @@ int attn_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* ls
   int per_head = num_sms() / Hk;
   if (per_head < 1) per_head = 1;
   if (per_head > B) per_head = B;
-  attn_bwd_tc_kernel<<<per_head * Hk, BWD_THREADS, B_SMEM, st>>>(maps, a);
+  launch_pdl(attn_bwd_tc_kernel, dim3(per_head * Hk), dim3(BWD_THREADS), B_SMEM, st, maps, a);
   return check_launch("vsx_attn_bwd");
 }
 

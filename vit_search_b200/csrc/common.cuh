@@ -24,6 +24,30 @@ int check_launch(const char* what);
     }                                          \
   } while (0)
 
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// Every converted kernel starts with pdl_launch_dependents() (the NEXT kernel of the stream may be scheduled onto SMs as this grid's CTAs
+// retire, instead of after the whole grid has drained and a fresh launch has travelled through the front end) and calls pdl_wait()
+// before its first global-memory access (blocks until the PREVIOUS grid has completed and its writes are visible).  Because every kernel
+// launched with the attribute waits before touching memory, and a grid cannot complete before its wait has returned, completion order
+// stays the stream order transitively; kernels launched without the attribute (torch's own, unconverted ones) serialise as usual.
+// VSX_PDL=0 in the environment launches everything without the attribute (the device-side instructions are then no-ops).
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid, cfg.blockDim = block, cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long ceil_div_l(long a, long b) { return (a + b - 1) / b; }
 int num_sms();

@@ -62,6 +62,8 @@ template <bool STATS>
 __global__ void __launch_bounds__(C1_WARPS * 32) conv1_fwd_kernel(const float* __restrict__ img, const bf16* __restrict__ wt, long ldw,
                                                                   bf16* __restrict__ y, int B, int H, int W, int Ho, int Wo,
                                                                   double* __restrict__ sums) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) uint8_t stage[C1_WARPS][32 * A_PITCH];
   __shared__ float red[C1_WARPS][2][C1_KP];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3, lj = lane >> 3, li = lane & 7;
@@ -155,6 +157,8 @@ __global__ void __launch_bounds__(C1_WARPS * 32) conv1_fwd_kernel(const float* _
 
 __global__ void __launch_bounds__(C1_WARPS * 32) conv1_wgrad_kernel(const float* __restrict__ img, const bf16* __restrict__ dy, float* __restrict__ dw,
                                                                     long ldw, int B, int H, int W, int Ho, int Wo) {
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int WSTAGE = 32 * A_PITCH + 32 * D_PITCH + 64;                  // +64: the second m-tile's loads of the last row overhang
   __shared__ __align__(16) uint8_t smem[C1_WARPS * WSTAGE];                  // 33 KB; re-used for the final reduction
   static_assert(C1_WARPS * C1_OUT * 28 * 4 <= C1_WARPS * WSTAGE, "reduction buffer must fit in the staging area");
@@ -237,8 +241,8 @@ extern "C" int vsx_conv1_fwd(const float* image, const void* weight, long ldw, v
   const long groups = ((long)B * Ho * Wo + 31) / 32;
   const int grid = (int)std::min<long>((groups + C1_WARPS - 1) / C1_WARPS, (long)num_sms() * 6);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  if (sums != nullptr) conv1_fwd_kernel<true><<<grid, C1_WARPS * 32, 0, st>>>(image, (const bf16*)weight, ldw, (bf16*)y, B, H, W, Ho, Wo, sums);
-  else conv1_fwd_kernel<false><<<grid, C1_WARPS * 32, 0, st>>>(image, (const bf16*)weight, ldw, (bf16*)y, B, H, W, Ho, Wo, nullptr);
+  if (sums != nullptr) launch_pdl(conv1_fwd_kernel<true>, dim3(grid), dim3(C1_WARPS * 32), 0, st, image, (const bf16*)weight, ldw, (bf16*)y, B, H, W, Ho, Wo, sums);
+  else launch_pdl(conv1_fwd_kernel<false>, dim3(grid), dim3(C1_WARPS * 32), 0, st, image, (const bf16*)weight, ldw, (bf16*)y, B, H, W, Ho, Wo, nullptr);
   return check_launch("vsx_conv1_fwd");
 }
 
@@ -249,6 +253,6 @@ extern "C" int vsx_conv1_wgrad(const float* image, const void* dy, float* dw, lo
   const int Ho = H / 2, Wo = W / 2;
   const long groups = ((long)B * Ho * Wo + 31) / 32;
   const int grid = (int)std::min<long>((groups + C1_WARPS - 1) / C1_WARPS, (long)num_sms() * 4);
-  conv1_wgrad_kernel<<<grid, C1_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>(image, (const bf16*)dy, dw, ldw, B, H, W, Ho, Wo);
+  launch_pdl(conv1_wgrad_kernel, dim3(grid), dim3(C1_WARPS * 32), 0, reinterpret_cast<cudaStream_t>(stream), image, (const bf16*)dy, dw, ldw, B, H, W, Ho, Wo);
   return check_launch("vsx_conv1_wgrad");
 }

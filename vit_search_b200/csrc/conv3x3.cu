@@ -99,6 +99,8 @@ __global__ void __launch_bounds__(FWD_WARPS * 32) conv3x3_fwd_kernel(const bf16*
                                                                      int C, const bf16* __restrict__ y_prev, const float* __restrict__ gamma,
                                                                      const float* __restrict__ beta, const float* __restrict__ mean,
                                                                      const float* __restrict__ rstd, double* __restrict__ sums) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) bf16 halo[HH * HW * PITCH];
   __shared__ __align__(16) bf16 wts[9 * CP * PITCH];
   __shared__ float sc_s[CP], sh_s[CP], g_s[CP], b_s[CP], m_s[CP], r_s[CP];
@@ -250,6 +252,8 @@ constexpr int WG_WARPS = 9;   // one warp per tap
 __global__ void __launch_bounds__(WG_WARPS * 32) conv3x3_wgrad_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ in,
                                                                       const float* __restrict__ in_scale, const float* __restrict__ in_shift,
                                                                       float* __restrict__ dw, int B, int H, int W, int C) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ __align__(16) bf16 halo[HH * HW * PITCH];
   __shared__ __align__(16) bf16 dys[TH * TW * PITCH];
   __shared__ float sc_s[CP], sh_s[CP];
@@ -366,9 +370,9 @@ extern "C" int vsx_conv3x3(const void* in, const float* in_scale, const float* i
   if (g_conv_impl != 1 && conv3x3_tma_supported(H, W, C))
     return conv3x3_tma_launch(in, in_scale, in_shift, wt, add, out, B, H, W, stats_mode, y_prev, gamma, beta, mean, rstd, sums, st);
 #define VSX_CONV_ARGS (const bf16*)in, in_scale, in_shift, (const bf16*)wt, (const bf16*)add, (bf16*)out, B, H, W, C, (const bf16*)y_prev, gamma, beta, mean, rstd, sums
-  if (stats_mode == 0) conv3x3_fwd_kernel<0><<<grid, FWD_WARPS * 32, 0, st>>>(VSX_CONV_ARGS);
-  else if (stats_mode == 1) conv3x3_fwd_kernel<1><<<grid, FWD_WARPS * 32, 0, st>>>(VSX_CONV_ARGS);
-  else conv3x3_fwd_kernel<2><<<grid, FWD_WARPS * 32, 0, st>>>(VSX_CONV_ARGS);
+  if (stats_mode == 0) launch_pdl(conv3x3_fwd_kernel<0>, dim3(grid), dim3(FWD_WARPS * 32), 0, st, VSX_CONV_ARGS);
+  else if (stats_mode == 1) launch_pdl(conv3x3_fwd_kernel<1>, dim3(grid), dim3(FWD_WARPS * 32), 0, st, VSX_CONV_ARGS);
+  else launch_pdl(conv3x3_fwd_kernel<2>, dim3(grid), dim3(FWD_WARPS * 32), 0, st, VSX_CONV_ARGS);
 #undef VSX_CONV_ARGS
   return check_launch("vsx_conv3x3");
 }
@@ -382,7 +386,7 @@ extern "C" int vsx_conv3x3_wgrad(const void* dy, const void* in, const float* in
     return conv3x3_wgrad_tma_launch(dy, in, in_scale, in_shift, dw, B, H, W, reinterpret_cast<cudaStream_t>(stream));
   const int tiles = B * (H / TH) * (W / TW);
   const int grid = std::min(tiles, num_sms() * 2);
-  conv3x3_wgrad_kernel<<<grid, WG_WARPS * 32, 0, reinterpret_cast<cudaStream_t>(stream)>>>((const bf16*)dy, (const bf16*)in, in_scale, in_shift, dw, B,
+  launch_pdl(conv3x3_wgrad_kernel, dim3(grid), dim3(WG_WARPS * 32), 0, reinterpret_cast<cudaStream_t>(stream), (const bf16*)dy, (const bf16*)in, in_scale, in_shift, dw, B,
                                                                                           H, W, C);
   return check_launch("vsx_conv3x3_wgrad");
 }

@@ -78,6 +78,8 @@ __global__ void __launch_bounds__(THREADS, 1) conv3x3_tma_kernel(const __grid_co
                                                                  int B, int H, int W, const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, const float* __restrict__ mean,
                                                                  const float* __restrict__ rstd, double* __restrict__ sums) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -362,6 +364,8 @@ struct WgradMaps {
 __global__ void __launch_bounds__(WG_THREADS, 1) conv3x3_wgrad_tma_kernel(const __grid_constant__ WgradMaps maps, const float* __restrict__ in_scale,
                                                                           const float* __restrict__ in_shift, float* __restrict__ dw, int B, int H,
                                                                           int W) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 127u) & ~127u;
   uint8_t* gbase = smem_raw + (base - smem_u32(smem_raw));
@@ -549,7 +553,7 @@ int conv3x3_tma_launch(const void* in, const float* in_scale, const float* in_sh
       }                                                                                                          \
       attr = true;                                                                                               \
     }                                                                                                            \
-    conv3x3_tma_kernel<S><<<grid, THREADS, smem, st>>>(VSX_CONV2_ARGS);                                           \
+    launch_pdl(conv3x3_tma_kernel<S>, dim3(grid), dim3(THREADS), smem, st, VSX_CONV2_ARGS);                                           \
   } while (0)
   if (stats_mode == 0) VSX_CONV2_LAUNCH(0);
   else if (stats_mode == 1) VSX_CONV2_LAUNCH(1);
@@ -575,7 +579,7 @@ int conv3x3_wgrad_tma_launch(const void* dy, const void* in, const float* in_sca
     attr = true;
   }
   const int tiles = B * (H / T2) * (W / T2);
-  conv3x3_wgrad_tma_kernel<<<std::min(tiles, num_sms()), WG_THREADS, smem, st>>>(maps, in_scale, in_shift, dw, B, H, W);
+  launch_pdl(conv3x3_wgrad_tma_kernel, dim3(std::min(tiles, num_sms())), dim3(WG_THREADS), smem, st, maps, in_scale, in_shift, dw, B, H, W);
   return check_launch("vsx_conv3x3_wgrad");
 }
 

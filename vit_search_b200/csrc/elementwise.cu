@@ -8,6 +8,8 @@ namespace {
 // hi = bf16(src); lo = bf16(src - hi) (optional); lo2 = bf16(src - hi - lo) (optional).  4 elements per thread.
 __global__ void split_kernel(const float* __restrict__ src, long lds, bf16* __restrict__ hi, bf16* __restrict__ lo, bf16* __restrict__ lo2,
                              long ldd, int rows, int cols4) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long total = (long)rows * cols4;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const long r = i / cols4;
@@ -36,6 +38,8 @@ template <int NV, typename T>
 __global__ void __launch_bounds__(SMC_WARPS * 32) scale_mask_cast_kernel(const float* __restrict__ g, long ldg, const float* __restrict__ row_scale,
                                                                         int rps, int n_keep, T* __restrict__ out, long ldo, int rows, int cols,
                                                                         float* __restrict__ colsum) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float4 acc[NV];
 #pragma unroll
@@ -82,6 +86,8 @@ template <int NV, typename T>
 __global__ void __launch_bounds__(SMC_WARPS * 32) scale_mask_cast_bulk_kernel(const float* __restrict__ g, long ldg, const float* __restrict__ row_scale,
                                                                              int rps, int n_keep, T* __restrict__ out, long ldo, int rows, int cols,
                                                                              float* __restrict__ colsum) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t smc_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t gb = (uint32_t)n_keep * 4;
@@ -148,6 +154,8 @@ __global__ void __launch_bounds__(SMC_WARPS * 32) scale_mask_cast_bulk_kernel(co
 constexpr int CS_ROWS = 512;
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ x, long ldx, int rows, int cols, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cq = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int c = blockIdx.x * 128 + cq * 4;
   const long r0 = (long)blockIdx.y * CS_ROWS;
@@ -189,7 +197,7 @@ using namespace vsx;
 extern "C" int vsx_split_bf16(const float* src, long lds, void* hi, void* lo, void* lo2, long ldd, int rows, int cols, void* stream) {
   VSX_REQUIRE(cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "vsx_split_bf16: cols and pitches must be multiples of 4");
   if (rows <= 0 || cols <= 0) return VSX_OK;
-  split_kernel<<<ew_grid((long)rows * cols / 4), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(src, lds, (bf16*)hi, (bf16*)lo, (bf16*)lo2,
+  launch_pdl(split_kernel, dim3(ew_grid((long)rows * cols / 4)), dim3(256), 0, reinterpret_cast<cudaStream_t>(stream), src, lds, (bf16*)hi, (bf16*)lo, (bf16*)lo2,
                                                                                                  ldd, rows, cols / 4);
   return check_launch("vsx_split_bf16");
 }
@@ -210,7 +218,7 @@ static int smc_dispatch(const float* g, long ldg, const float* row_scale, int rp
       cudaFuncSetAttribute(scale_mask_cast_bulk_kernel<NV, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                    \
       cfg = true;                                                                                                                          \
     }                                                                                                                                      \
-    scale_mask_cast_bulk_kernel<NV, T><<<gridb, SMC_WARPS * 32, smem, st>>>(g, ldg, row_scale, rps, n_keep, (T*)out, ldo, rows, cols, colsum); \
+    launch_pdl(scale_mask_cast_bulk_kernel<NV, T>, dim3(gridb), dim3(SMC_WARPS * 32), smem, st, g, ldg, row_scale, rps, n_keep, (T*)out, ldo, rows, cols, colsum); \
     return check_launch("vsx_scale_mask_cast");                                                                                            \
   }
     switch (nv) {
@@ -221,7 +229,7 @@ static int smc_dispatch(const float* g, long ldg, const float* row_scale, int rp
   }
 #define VSX_SMC(NV)                                                                                                                 \
   case NV:                                                                                                                          \
-    scale_mask_cast_kernel<NV, T><<<grid, SMC_WARPS * 32, 0, st>>>(g, ldg, row_scale, rps, n_keep, (T*)out, ldo, rows, cols, colsum); \
+    launch_pdl(scale_mask_cast_kernel<NV, T>, dim3(grid), dim3(SMC_WARPS * 32), 0, st, g, ldg, row_scale, rps, n_keep, (T*)out, ldo, rows, cols, colsum); \
     break;
   switch (nv) {
     VSX_SMC(1) VSX_SMC(2) VSX_SMC(3) VSX_SMC(4) VSX_SMC(5) VSX_SMC(6) VSX_SMC(7) VSX_SMC(8) VSX_SMC(9) VSX_SMC(10)
@@ -252,9 +260,9 @@ extern "C" int vsx_colsum(const void* x, int dtype, long ldx, int rows, int cols
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   dim3 grid(ceil_div(cols, 128), ceil_div(rows, CS_ROWS));
   if (dtype == VSX_BF16)
-    colsum_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)x, ldx, rows, cols, out);
+    launch_pdl(colsum_kernel<bf16>, dim3(grid), dim3(256), 0, st, (const bf16*)x, ldx, rows, cols, out);
   else if (dtype == VSX_F32)
-    colsum_kernel<float><<<grid, 256, 0, st>>>((const float*)x, ldx, rows, cols, out);
+    launch_pdl(colsum_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)x, ldx, rows, cols, out);
   else {
     set_error("vsx_colsum: bad dtype %d", dtype);
     return VSX_ERR_ARG;

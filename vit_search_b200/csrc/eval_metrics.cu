@@ -13,6 +13,8 @@ constexpr int EM_WARPS = 8;
 
 __global__ void __launch_bounds__(EM_WARPS * 32) eval_rows_kernel(const float* __restrict__ logits, long ld, const long* __restrict__ labels, int rows,
                                                                    int cols, float* __restrict__ row_loss, int* __restrict__ row_rank) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (long r = (long)blockIdx.x * EM_WARPS + warp; r < rows; r += (long)gridDim.x * EM_WARPS) {
     const float* x = logits + r * ld;
@@ -40,6 +42,8 @@ __global__ void __launch_bounds__(EM_WARPS * 32) eval_rows_kernel(const float* _
 
 __global__ void __launch_bounds__(256) eval_reduce_kernel(const float* __restrict__ row_loss, const int* __restrict__ row_rank, int rows,
                                                           double* __restrict__ totals) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ double s_loss[256];
   __shared__ int s_top1[256], s_top5[256];
   double l = 0.0;
@@ -80,9 +84,9 @@ extern "C" int vsx_eval_metrics(const float* logits, long ld, const long* labels
   VSX_REQUIRE(cols > 0 && ld >= cols, "vsx_eval_metrics: bad logits shape (cols=%d ld=%ld)", cols, ld);
   if (rows <= 0) return VSX_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  eval_rows_kernel<<<std::min(ceil_div(rows, EM_WARPS), num_sms() * 4), EM_WARPS * 32, 0, st>>>(logits, ld, labels, rows, cols, row_loss, row_rank);
+  launch_pdl(eval_rows_kernel, dim3(std::min(ceil_div(rows, EM_WARPS), num_sms() * 4)), dim3(EM_WARPS * 32), 0, st, logits, ld, labels, rows, cols, row_loss, row_rank);
   int rc = check_launch("vsx_eval_metrics");
   if (rc) return rc;
-  eval_reduce_kernel<<<1, 256, 0, st>>>(row_loss, row_rank, rows, totals);
+  launch_pdl(eval_reduce_kernel, dim3(1), dim3(256), 0, st, row_loss, row_rank, rows, totals);
   return check_launch("vsx_eval_metrics");
 }

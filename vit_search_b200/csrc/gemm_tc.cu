@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   constexpr bool AUX = (EPI == VSX_EPI_RESIDUAL || EPI == VSX_EPI_GELUGRAD);
   constexpr int BOXC = 128 / (int)sizeof(OutT);     // columns per 128-byte box row
   constexpr int NBOX = BN / BOXC;                   // boxes per output tile
+  pdl_launch_dependents();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;     // 128B-swizzle atoms need 1024-byte alignment
@@ -297,6 +298,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();      // barriers, tensor memory and descriptor prefetches are set up: from here on the previous kernel's results are read
 
   if (warp == 0) {
     if (lane == 0) {
@@ -638,7 +640,7 @@ int launch_g(const Group<G>& grp, cudaStream_t st) {
   }
   if (CG == 1) {
     const int grid = grp.total < num_sms() ? grp.total : num_sms();
-    kern<<<grid, GEMM_THREADS, P::SMEM, st>>>(grp);
+    launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), P::SMEM, st, grp);
     return check_launch("vsx_gemm");
   }
   // CTA pairs: clusters of two CTAs (the two SMs of a TPC), one cluster per tile at a time
@@ -648,10 +650,12 @@ int launch_g(const Group<G>& grp, cudaStream_t st) {
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = P::SMEM;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr, cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr, cfg.numAttrs = pdl_enabled() ? 2 : 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, grp);
   if (e != cudaSuccess) {
     set_error("vsx_gemm: cluster launch failed: %s", cudaGetErrorString(e));

@@ -14,6 +14,8 @@ constexpr int CE_MAX_PER_LANE = 40;   // up to 1280 classes
 __global__ void __launch_bounds__(CE_WARPS * 32) soft_ce_kernel(const float* __restrict__ logits, long ld, const float* __restrict__ target,
                                                                  long ldt, int rows, int cols, float loss_scale, float grad_scale,
                                                                  float* __restrict__ loss_sum, float* __restrict__ dlogits, long ldd) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float local = 0.f;
   for (long r = (long)blockIdx.x * CE_WARPS + warp; r < rows; r += (long)gridDim.x * CE_WARPS) {
@@ -63,6 +65,8 @@ __global__ void __launch_bounds__(CE_WARPS * 32) soft_ce_kernel(const float* __r
 }
 
 __global__ void scale_by_scalar_kernel(float* __restrict__ x, long n, const float* __restrict__ s) {
+  pdl_launch_dependents();
+  pdl_wait();
   const float v = *s;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) x[i] *= v;
 }
@@ -73,6 +77,8 @@ __global__ void __launch_bounds__(256) adamw_kernel(const vsx_adamw_tensor* __re
                                                     const int* __restrict__ chunk_index, float lr, float beta1, float beta2, float omb1,
                                                     float omb2, float eps, float bc1, float bc2, const float* __restrict__ grad_scale_dev,
                                                     const float* __restrict__ guard_dev, int* __restrict__ nonfinite_dev) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (guard_dev != nullptr) {
     // finite-loss guard (engine.py:168-173): a step whose loss is inf / nan leaves parameters, moments, shadows and averages untouched
     // and raises the sticky device flag the host reads at its logging interval -- no host sync on the step itself
@@ -154,14 +160,14 @@ extern "C" int vsx_soft_ce(const float* logits, long ld, const float* target, lo
   VSX_REQUIRE(cols > 0 && cols <= CE_MAX_PER_LANE * 32, "vsx_soft_ce: supports up to %d classes (got %d)", CE_MAX_PER_LANE * 32, cols);
   if (rows <= 0) return VSX_OK;
   const int grid = std::min(ceil_div(rows, CE_WARPS), num_sms() * 4);
-  soft_ce_kernel<<<grid, CE_WARPS * 32, 0, ST>>>(logits, ld, target, ldt, rows, cols, loss_scale, grad_scale, loss_sum, dlogits, ldd);
+  launch_pdl(soft_ce_kernel, dim3(grid), dim3(CE_WARPS * 32), 0, ST, logits, ld, target, ldt, rows, cols, loss_scale, grad_scale, loss_sum, dlogits, ldd);
   return check_launch("vsx_soft_ce");
 }
 
 extern "C" int vsx_scale_by_scalar(float* x, long n, const float* scalar_dev, void* stream) {
   if (n <= 0) return VSX_OK;
   const int grid = (int)std::min<long>(ceil_div_l(n, 1024), (long)num_sms() * 8);
-  scale_by_scalar_kernel<<<grid, 256, 0, ST>>>(x, n, scalar_dev);
+  launch_pdl(scale_by_scalar_kernel, dim3(grid), dim3(256), 0, ST, x, n, scalar_dev);
   return check_launch("vsx_scale_by_scalar");
 }
 
@@ -175,7 +181,7 @@ extern "C" int vsx_adamw(const vsx_adamw_tensor* tensors_dev, const int* chunk_t
   // hyper-parameters arrive as doubles so that 1 - beta is rounded ONCE, like torch.optim.AdamW (`value=1 - beta2` is evaluated in
   // Python's double arithmetic): 1.0f - 0.999f is 1.3e-5 away from float(0.001)
   const float bc1 = (float)(1.0 - pow(beta1, (double)step)), bc2 = (float)(1.0 - pow(beta2, (double)step));
-  adamw_kernel<<<num_chunks, 256, 0, ST>>>(tensors_dev, chunk_tensor_dev, chunk_index_dev, (float)lr, (float)beta1, (float)beta2,
+  launch_pdl(adamw_kernel, dim3(num_chunks), dim3(256), 0, ST, tensors_dev, chunk_tensor_dev, chunk_index_dev, (float)lr, (float)beta1, (float)beta2,
                                              (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps, bc1, bc2, grad_scale_dev, guard_loss_dev,
                                              nonfinite_count_dev);
   return check_launch("vsx_adamw");

@@ -32,6 +32,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const float* __re
                                                                 const float* __restrict__ beta, T* __restrict__ y, T* __restrict__ y2,
                                                                 long ldy, float* __restrict__ mean, float* __restrict__ rstd,
                                                                 int rows, int C, int keep, float eps, int rps, int split) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float inv_keep = 1.0f / (float)keep;
   for (long r = (long)blockIdx.x * LN_WARPS + warp; r < rows; r += (long)gridDim.x * LN_WARPS) {
@@ -88,6 +90,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_bwd_kernel(const T* __restri
                                                                 const float* __restrict__ g_in, float* __restrict__ g_out, long ldg,
                                                                 float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int C,
                                                                 int keep, int rps, int split) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float inv_keep = 1.0f / (float)keep;
   float4 gm[NV], ag[NV], ab[NV];
@@ -194,6 +198,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 2 ? 4 : 1) ln_bwd_bulk_ke
                                                                      const float* __restrict__ gamma, const float* __restrict__ g_in,
                                                                      float* __restrict__ g_out, long ldg, float* __restrict__ dgamma,
                                                                      float* __restrict__ dbeta, int rows, int C, int keep, const LnCast cast) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t xb = (uint32_t)keep * 4, gb = g_in != nullptr ? (uint32_t)C * 4 : 0u, db = (uint32_t)keep * (uint32_t)sizeof(T);
@@ -302,6 +308,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_bulk_kernel(const float*
                                                                      const float* __restrict__ beta, T* __restrict__ y, long ldy,
                                                                      float* __restrict__ mean, float* __restrict__ rstd, int rows, int C,
                                                                      int keep, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t xb = (uint32_t)keep * 4;
@@ -390,7 +398,7 @@ int ln_fwd_dispatch(const float* x, long ldx, const float* gamma, const float* b
       cudaFuncSetAttribute(ln_fwd_bulk_kernel<NV, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                   \
       cfg = true;                                                                                                                \
     }                                                                                                                            \
-    ln_fwd_bulk_kernel<NV, T><<<gridb, LN_WARPS * 32, smem, st>>>(x, ldx, gamma, beta, (T*)y, ldy, mean, rstd, rows, C, keep, eps); \
+    launch_pdl(ln_fwd_bulk_kernel<NV, T>, dim3(gridb), dim3(LN_WARPS * 32), smem, st, x, ldx, gamma, beta, (T*)y, ldy, mean, rstd, rows, C, keep, eps); \
     return check_launch("vsx_masked_ln_fwd");                                                                                    \
   }
     switch (nv) {
@@ -402,7 +410,7 @@ int ln_fwd_dispatch(const float* x, long ldx, const float* gamma, const float* b
   const int grid = ln_grid(rows, 8);
 #define VSX_LN_F(NV)                                                                                                        \
   case NV:                                                                                                                  \
-    ln_fwd_kernel<NV, T><<<grid, LN_WARPS * 32, 0, st>>>(x, ldx, gamma, beta, (T*)y, (T*)y2, ldy, mean, rstd, rows, C, keep, \
+    launch_pdl(ln_fwd_kernel<NV, T>, dim3(grid), dim3(LN_WARPS * 32), 0, st, x, ldx, gamma, beta, (T*)y, (T*)y2, ldy, mean, rstd, rows, C, keep, \
                                                           eps, rps, split);                                                  \
     break;
   switch (nv) {
@@ -442,12 +450,12 @@ int ln_bwd_dispatch(const void* dy, const void* dy2, long lddy, const float* x, 
         cudaFuncSetAttribute(ln_bwd_bulk_kernel<NV, T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 4096 * NV - 512); \
         cfg2 = true;                                                                                                                \
       }                                                                                                                             \
-      ln_bwd_bulk_kernel<NV, T, true><<<gridb, LN_WARPS * 32, smem, st>>>((const T*)dy, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, \
+      launch_pdl(ln_bwd_bulk_kernel<NV, T, true>, dim3(gridb), dim3(LN_WARPS * 32), smem, st, (const T*)dy, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, \
                                                                            dgamma, dbeta, rows, C, keep, *cast);                    \
       if (cast_done != nullptr) *cast_done = true;                                                                                  \
       return check_launch("vsx_masked_ln_bwd");                                                                                     \
     }                                                                                                                               \
-    ln_bwd_bulk_kernel<NV, T, false><<<gridb, LN_WARPS * 32, smem, st>>>((const T*)dy, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, \
+    launch_pdl(ln_bwd_bulk_kernel<NV, T, false>, dim3(gridb), dim3(LN_WARPS * 32), smem, st, (const T*)dy, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, \
                                                                           dgamma, dbeta, rows, C, keep, LnCast{});                  \
     return check_launch("vsx_masked_ln_bwd");                                                                                       \
   }
@@ -460,7 +468,7 @@ int ln_bwd_dispatch(const void* dy, const void* dy2, long lddy, const float* x, 
   const int grid = ln_grid(rows, 4);
 #define VSX_LN_B(NV)                                                                                                      \
   case NV:                                                                                                                \
-    ln_bwd_kernel<NV, T><<<grid, LN_WARPS * 32, 0, st>>>((const T*)dy, (const T*)dy2, lddy, x, ldx, mean, rstd, gamma, g_in, \
+    launch_pdl(ln_bwd_kernel<NV, T>, dim3(grid), dim3(LN_WARPS * 32), 0, st, (const T*)dy, (const T*)dy2, lddy, x, ldx, mean, rstd, gamma, g_in, \
                                                           g_out, ldg, dgamma, dbeta, rows, C, keep, rps, split);          \
     break;
   switch (nv) {

@@ -25,6 +25,8 @@ __global__ void im2col_kernel(const TI* __restrict__ in1, const float* __restric
                               const TI* __restrict__ in2, const float* __restrict__ sc2, const float* __restrict__ sh2,
                               long batch_pitch, long pix_pitch, int B, int H, int W, int C, int k, int s, int p, int Ho, int Wo,
                               TO* __restrict__ out, long ldo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long total = (long)B * Ho * Wo * k * k;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int tap = (int)(i % (k * k));
@@ -71,6 +73,8 @@ __global__ void im2col_kernel(const TI* __restrict__ in1, const float* __restric
 // 16-byte stores, instead of one thread per (pixel, tap) writing three 2-byte values.
 __global__ void __launch_bounds__(256) im2col_conv1_kernel(const float* __restrict__ img, int B, int H, int W, int Ho, int Wo,
                                                            bf16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long total = (long)B * Ho * Wo;
   for (long pix = (long)blockIdx.x * blockDim.x + threadIdx.x; pix < total; pix += (long)gridDim.x * blockDim.x) {
     const int ox = (int)(pix % Wo), oy = (int)((pix / Wo) % Ho), b = (int)(pix / ((long)Wo * Ho));
@@ -103,6 +107,8 @@ __global__ void __launch_bounds__(256) im2col_conv1_kernel(const float* __restri
 template <typename T>
 __global__ void col2im_kernel(const T* __restrict__ dcol, long ldc, const T* __restrict__ add, int B, int H, int W, int C, int k, int s,
                               int p, int Ho, int Wo, T* __restrict__ din, long batch_pitch, long pix_pitch) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c4n = C / 4;
   const long total = (long)B * H * W * c4n;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -170,6 +176,8 @@ __global__ void __launch_bounds__(256) im2col_rows_kernel(const bf16* __restrict
                                                           const bf16* __restrict__ in2, const float* __restrict__ sc2,
                                                           const float* __restrict__ sh2, long batch_pitch, int pix_pitch, int H, int W, int C, int k,
                                                           int s, int p, int Ho, int Wo, bf16* __restrict__ out, long ldo) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x / Ho, oy = blockIdx.x - b * Ho;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int cpc = C >> 3, run = k * cpc;
@@ -208,6 +216,8 @@ __global__ void __launch_bounds__(256) im2col_rows_kernel(const bf16* __restrict
 __global__ void __launch_bounds__(256) col2im_rows_kernel(const bf16* __restrict__ dcol, long ldc, const bf16* __restrict__ add, int H, int W, int C,
                                                           int k, int s, int p, int Ho, int Wo, bf16* __restrict__ din, long batch_pitch,
                                                           int pix_pitch) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x / H, iy = blockIdx.x - b * H;
   const int cpc = C >> 3;
   const long row_off = (long)b * batch_pitch + (long)iy * W * pix_pitch;
@@ -284,6 +294,8 @@ __device__ __forceinline__ void bn_block_reduce(float (&acc)[NACC][BN_MAXC], int
 // sums[0][c] = sum y, sums[1][c] = sum y^2
 template <typename T>
 __global__ void __launch_bounds__(BN_THREADS) bn_stats_kernel(const T* __restrict__ y, long P, int C, double* __restrict__ sums) {
+  pdl_launch_dependents();
+  pdl_wait();
   float acc[2][BN_MAXC];
 #pragma unroll
   for (int c = 0; c < BN_MAXC; ++c) acc[0][c] = acc[1][c] = 0.f;
@@ -307,6 +319,8 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, long P, int 
                                    const float* __restrict__ beta, float eps, float momentum, float* __restrict__ scale,
                                    float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                    float* __restrict__ running_mean, float* __restrict__ running_var, long long* __restrict__ tracked) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c = threadIdx.x;
   if (c < C) {
     const double m = sums[c] / (double)P;
@@ -332,6 +346,8 @@ __global__ void __launch_bounds__(BN_THREADS) bn_bwd_stats_kernel(const T* __res
                                                                   const float* __restrict__ gamma, const float* __restrict__ beta,
                                                                   const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                   double* __restrict__ sums) {
+  pdl_launch_dependents();
+  pdl_wait();
   float acc[2][BN_MAXC];
 #pragma unroll
   for (int c = 0; c < BN_MAXC; ++c) acc[0][c] = acc[1][c] = 0.f;
@@ -360,6 +376,8 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restric
                                     const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const double* __restrict__ sums, T* __restrict__ dy, float* __restrict__ dgamma,
                                     float* __restrict__ dbeta) {
+  pdl_launch_dependents();
+  pdl_wait();
   // per-channel constants once per CTA: zhat = y*a + b, pre-activation = gamma*zhat + beta, dy = s*(dz - m1 - zhat*m2)
   __shared__ float ca[BN_MAXC], cb[BN_MAXC], cg[BN_MAXC], cbeta[BN_MAXC], cs[BN_MAXC], cm1[BN_MAXC], cm2[BN_MAXC];
   const int c4n = C / 4;
@@ -396,6 +414,8 @@ __global__ void bn_bwd_apply_kernel(const T* __restrict__ da, const T* __restric
 // x0[b, t, c] = [c < keep] * ((t == 0 ? tokens[c] : patches[b, t-1, c]) + pos[t, c])        (vit_sr_supernet.py:399-407)
 __global__ void embed_assemble_kernel(const float* __restrict__ patches, const float* __restrict__ tokens, const float* __restrict__ pos,
                                       float* __restrict__ x0, int nb, int N, int C, int keep, int T) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c4n = C / 4;
   const long total = (long)nb * N * c4n;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -421,6 +441,8 @@ __global__ void embed_assemble_kernel(const float* __restrict__ patches, const f
 template <typename T>
 __global__ void embed_assemble_bwd_kernel(const float* __restrict__ g, T* __restrict__ dpatches, float* __restrict__ dpos,
                                           float* __restrict__ dtokens, int nb, int N, int C, int keep, int NT) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int c4n = C / 4;
   const long total = (long)N * c4n;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -455,6 +477,8 @@ __global__ void embed_assemble_bwd_kernel(const float* __restrict__ g, T* __rest
 // y[b,1+p,c] = [c<keep2] * (conv[b,p,c] + pos[p,c] + (c<C1 ? mean of the 2x2 block of x patch rows : 0))     (vit_sr_supernet.py:131-166)
 __global__ void sr_combine_kernel(const float* __restrict__ conv, const float* __restrict__ tok, const float* __restrict__ pos,
                                   const float* __restrict__ x, float* __restrict__ y, int nb, int g, int C1, int C2, int keep2) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int g2 = g / 2, N2 = 1 + g2 * g2, N1 = 1 + g * g;
   const int c4n = C2 / 4;
   const long total = (long)nb * N2 * c4n;
@@ -502,6 +526,8 @@ __global__ void sr_combine_kernel(const float* __restrict__ conv, const float* _
 template <typename T>
 __global__ void sr_combine_bwd_kernel(const float* __restrict__ gy, T* __restrict__ dconv, T* __restrict__ dtok, float* __restrict__ dpos,
                                       float* __restrict__ gres, int nb, int g, int C1, int C2, int keep2) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int g2 = g / 2, N2 = 1 + g2 * g2, N1 = 1 + g * g;
   const int c4n = C2 / 4;
   const long total = (long)N2 * c4n;
@@ -567,14 +593,14 @@ extern "C" int vsx_im2col(const void* in1, const float* scale1, const float* shi
     VSX_REQUIRE(in_dtype == VSX_F32 && in2 == nullptr && scale1 == nullptr, "vsx_im2col: NCHW input is the fp32 image, no fused activation");
     if (out_dtype == VSX_BF16 && C == 3 && k == 3 && stride == 2 && pad == 1 && ldo == 32 && batch_pitch == 3L * H * W &&
         (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
-      im2col_conv1_kernel<<<grid_for((long)B * Ho * Wo), 256, 0, ST>>>((const float*)in1, B, H, W, Ho, Wo, (bf16*)out);
+      launch_pdl(im2col_conv1_kernel, dim3(grid_for((long)B * Ho * Wo)), dim3(256), 0, ST, (const float*)in1, B, H, W, Ho, Wo, (bf16*)out);
       return check_launch("vsx_im2col");
     }
     if (out_dtype == VSX_BF16)
-      im2col_kernel<float, bf16, true><<<grid, 256, 0, ST>>>((const float*)in1, nullptr, nullptr, nullptr, nullptr, nullptr, batch_pitch,
+      launch_pdl(im2col_kernel<float, bf16, true>, dim3(grid), dim3(256), 0, ST, (const float*)in1, nullptr, nullptr, nullptr, nullptr, nullptr, batch_pitch,
                                                               pix_pitch, B, H, W, C, k, stride, pad, Ho, Wo, (bf16*)out, ldo);
     else
-      im2col_kernel<float, float, true><<<grid, 256, 0, ST>>>((const float*)in1, nullptr, nullptr, nullptr, nullptr, nullptr, batch_pitch,
+      launch_pdl(im2col_kernel<float, float, true>, dim3(grid), dim3(256), 0, ST, (const float*)in1, nullptr, nullptr, nullptr, nullptr, nullptr, batch_pitch,
                                                                pix_pitch, B, H, W, C, k, stride, pad, Ho, Wo, (float*)out, ldo);
   } else {
     VSX_REQUIRE(C % 4 == 0 && pix_pitch % 4 == 0 && batch_pitch % 4 == 0 && ldo % 4 == 0, "vsx_im2col: channels-last needs C, pitches %% 4 == 0");
@@ -583,13 +609,13 @@ extern "C" int vsx_im2col(const void* in1, const float* scale1, const float* shi
     // narrow maps (the 24-channel stem: conv_proj's 7x7 patches) keep the generic kernel: one thread per (pixel, tap) gives ~3 M independent
     // 48-byte copies, which measured faster inside the step (119 us) than one warp per run of taps (180 us)
     if (out_dtype == VSX_BF16 && C % 8 == 0 && C > 32 && pix_pitch % 8 == 0 && batch_pitch % 8 == 0 && ldo % 8 == 0 && al16 && pix_pitch < (1L << 30))
-      im2col_rows_kernel<<<B * Ho, 256, 0, ST>>>((const bf16*)in1, scale1, shift1, (const bf16*)in2, scale2, shift2, batch_pitch, (int)pix_pitch, H,
+      launch_pdl(im2col_rows_kernel, dim3(B * Ho), dim3(256), 0, ST, (const bf16*)in1, scale1, shift1, (const bf16*)in2, scale2, shift2, batch_pitch, (int)pix_pitch, H,
                                                  W, C, k, stride, pad, Ho, Wo, (bf16*)out, ldo);
     else if (out_dtype == VSX_BF16)
-      im2col_kernel<bf16, bf16, false><<<grid, 256, 0, ST>>>((const bf16*)in1, scale1, shift1, (const bf16*)in2, scale2, shift2, batch_pitch,
+      launch_pdl(im2col_kernel<bf16, bf16, false>, dim3(grid), dim3(256), 0, ST, (const bf16*)in1, scale1, shift1, (const bf16*)in2, scale2, shift2, batch_pitch,
                                                               pix_pitch, B, H, W, C, k, stride, pad, Ho, Wo, (bf16*)out, ldo);
     else
-      im2col_kernel<float, float, false><<<grid, 256, 0, ST>>>((const float*)in1, scale1, shift1, (const float*)in2, scale2, shift2,
+      launch_pdl(im2col_kernel<float, float, false>, dim3(grid), dim3(256), 0, ST, (const float*)in1, scale1, shift1, (const float*)in2, scale2, shift2,
                                                                 batch_pitch, pix_pitch, B, H, W, C, k, stride, pad, Ho, Wo, (float*)out, ldo);
   }
   return check_launch("vsx_im2col");
@@ -603,13 +629,13 @@ extern "C" int vsx_col2im(const void* dcol, long ldc, const void* add, int dtype
   const int grid = grid_for((long)B * H * W * C / 4);
   const bool al16 = ((reinterpret_cast<uintptr_t>(dcol) | reinterpret_cast<uintptr_t>(add) | reinterpret_cast<uintptr_t>(din)) & 15) == 0;
   if (dtype == VSX_BF16 && C % 8 == 0 && ldc % 8 == 0 && pix_pitch % 8 == 0 && batch_pitch % 8 == 0 && al16 && pix_pitch < (1L << 30))
-    col2im_rows_kernel<<<B * H, 256, 0, ST>>>((const bf16*)dcol, ldc, (const bf16*)add, H, W, C, k, stride, pad, Ho, Wo, (bf16*)din, batch_pitch,
+    launch_pdl(col2im_rows_kernel, dim3(B * H), dim3(256), 0, ST, (const bf16*)dcol, ldc, (const bf16*)add, H, W, C, k, stride, pad, Ho, Wo, (bf16*)din, batch_pitch,
                                               (int)pix_pitch);
   else if (dtype == VSX_BF16)
-    col2im_kernel<bf16><<<grid, 256, 0, ST>>>((const bf16*)dcol, ldc, (const bf16*)add, B, H, W, C, k, stride, pad, Ho, Wo, (bf16*)din,
+    launch_pdl(col2im_kernel<bf16>, dim3(grid), dim3(256), 0, ST, (const bf16*)dcol, ldc, (const bf16*)add, B, H, W, C, k, stride, pad, Ho, Wo, (bf16*)din,
                                               batch_pitch, pix_pitch);
   else
-    col2im_kernel<float><<<grid, 256, 0, ST>>>((const float*)dcol, ldc, (const float*)add, B, H, W, C, k, stride, pad, Ho, Wo, (float*)din,
+    launch_pdl(col2im_kernel<float>, dim3(grid), dim3(256), 0, ST, (const float*)dcol, ldc, (const float*)add, B, H, W, C, k, stride, pad, Ho, Wo, (float*)din,
                                                batch_pitch, pix_pitch);
   return check_launch("vsx_col2im");
 }
@@ -617,8 +643,8 @@ extern "C" int vsx_col2im(const void* dcol, long ldc, const void* add, int dtype
 extern "C" int vsx_bn_stats(const void* y, int dtype, long P, int C, double* sums, void* stream) {
   VSX_REQUIRE(C % 4 == 0 && C <= BN_MAXC, "vsx_bn_stats: C must be a multiple of 4 and <= 32 (got %d)", C);
   const int grid = (int)std::min<long>(ceil_div_l(P, BN_THREADS), (long)num_sms() * 4);
-  if (dtype == VSX_BF16) bn_stats_kernel<bf16><<<grid, BN_THREADS, 0, ST>>>((const bf16*)y, P, C, sums);
-  else bn_stats_kernel<float><<<grid, BN_THREADS, 0, ST>>>((const float*)y, P, C, sums);
+  if (dtype == VSX_BF16) launch_pdl(bn_stats_kernel<bf16>, dim3(grid), dim3(BN_THREADS), 0, ST, (const bf16*)y, P, C, sums);
+  else launch_pdl(bn_stats_kernel<float>, dim3(grid), dim3(BN_THREADS), 0, ST, (const float*)y, P, C, sums);
   return check_launch("vsx_bn_stats");
 }
 
@@ -626,7 +652,7 @@ extern "C" int vsx_bn_finalize(const double* sums, long P, int C, const float* g
                                float* scale, float* shift, float* mean, float* rstd, float* running_mean, float* running_var,
                                long long* num_batches_tracked, void* stream) {
   VSX_REQUIRE(C <= BN_MAXC && P > 1, "vsx_bn_finalize: bad C/P");
-  bn_finalize_kernel<<<1, 32, 0, ST>>>(sums, P, C, gamma, beta, eps, momentum, scale, shift, mean, rstd, running_mean, running_var,
+  launch_pdl(bn_finalize_kernel, dim3(1), dim3(32), 0, ST, sums, P, C, gamma, beta, eps, momentum, scale, shift, mean, rstd, running_mean, running_var,
                                       num_batches_tracked);
   return check_launch("vsx_bn_finalize");
 }
@@ -636,9 +662,9 @@ extern "C" int vsx_bn_bwd_stats(const void* da, const void* y, int dtype, long P
   VSX_REQUIRE(C % 4 == 0 && C <= BN_MAXC, "vsx_bn_bwd_stats: C must be a multiple of 4 and <= 32 (got %d)", C);
   const int grid = (int)std::min<long>(ceil_div_l(P, BN_THREADS), (long)num_sms() * 4);
   if (dtype == VSX_BF16)
-    bn_bwd_stats_kernel<bf16><<<grid, BN_THREADS, 0, ST>>>((const bf16*)da, (const bf16*)y, P, C, gamma, beta, mean, rstd, sums);
+    launch_pdl(bn_bwd_stats_kernel<bf16>, dim3(grid), dim3(BN_THREADS), 0, ST, (const bf16*)da, (const bf16*)y, P, C, gamma, beta, mean, rstd, sums);
   else
-    bn_bwd_stats_kernel<float><<<grid, BN_THREADS, 0, ST>>>((const float*)da, (const float*)y, P, C, gamma, beta, mean, rstd, sums);
+    launch_pdl(bn_bwd_stats_kernel<float>, dim3(grid), dim3(BN_THREADS), 0, ST, (const float*)da, (const float*)y, P, C, gamma, beta, mean, rstd, sums);
   return check_launch("vsx_bn_bwd_stats");
 }
 
@@ -648,9 +674,9 @@ extern "C" int vsx_bn_bwd_apply(const void* da, const void* y, int dtype, long P
   VSX_REQUIRE(C % 4 == 0 && C <= BN_MAXC, "vsx_bn_bwd_apply: C must be a multiple of 4 and <= 32 (got %d)", C);
   const int grid = grid_for(P * C / 4);
   if (dtype == VSX_BF16)
-    bn_bwd_apply_kernel<bf16><<<grid, 256, 0, ST>>>((const bf16*)da, (const bf16*)y, P, C, gamma, beta, mean, rstd, sums, (bf16*)dy, dgamma, dbeta);
+    launch_pdl(bn_bwd_apply_kernel<bf16>, dim3(grid), dim3(256), 0, ST, (const bf16*)da, (const bf16*)y, P, C, gamma, beta, mean, rstd, sums, (bf16*)dy, dgamma, dbeta);
   else
-    bn_bwd_apply_kernel<float><<<grid, 256, 0, ST>>>((const float*)da, (const float*)y, P, C, gamma, beta, mean, rstd, sums, (float*)dy, dgamma, dbeta);
+    launch_pdl(bn_bwd_apply_kernel<float>, dim3(grid), dim3(256), 0, ST, (const float*)da, (const float*)y, P, C, gamma, beta, mean, rstd, sums, (float*)dy, dgamma, dbeta);
   return check_launch("vsx_bn_bwd_apply");
 }
 
@@ -659,7 +685,7 @@ extern "C" int vsx_embed_assemble(const float* patches, const float* tokens, con
   VSX_REQUIRE(C % 4 == 0 && keep >= 0 && keep <= C, "vsx_embed_assemble: bad C/keep");
   VSX_REQUIRE(num_tokens >= 1 && num_tokens < tokens_per_sample, "vsx_embed_assemble: bad num_tokens %d", num_tokens);
   if (batch == 0) return VSX_OK;
-  embed_assemble_kernel<<<grid_for((long)batch * tokens_per_sample * C / 4), 256, 0, ST>>>(patches, tokens, pos, x0, batch, tokens_per_sample, C, keep,
+  launch_pdl(embed_assemble_kernel, dim3(grid_for((long)batch * tokens_per_sample * C / 4)), dim3(256), 0, ST, patches, tokens, pos, x0, batch, tokens_per_sample, C, keep,
                                                                                             num_tokens);
   return check_launch("vsx_embed_assemble");
 }
@@ -673,8 +699,8 @@ extern "C" int vsx_embed_assemble_bwd(const float* g, void* dpatches, int dtype,
   int gyy = (4 * num_sms() + gx - 1) / gx;
   gyy = gyy > batch ? batch : (gyy < 1 ? 1 : gyy);
   const dim3 grid(gx, gyy);
-  if (dtype == VSX_BF16) embed_assemble_bwd_kernel<bf16><<<grid, 256, 0, ST>>>(g, (bf16*)dpatches, dpos, dtokens, batch, tokens_per_sample, C, keep, num_tokens);
-  else embed_assemble_bwd_kernel<float><<<grid, 256, 0, ST>>>(g, (float*)dpatches, dpos, dtokens, batch, tokens_per_sample, C, keep, num_tokens);
+  if (dtype == VSX_BF16) launch_pdl(embed_assemble_bwd_kernel<bf16>, dim3(grid), dim3(256), 0, ST, g, (bf16*)dpatches, dpos, dtokens, batch, tokens_per_sample, C, keep, num_tokens);
+  else launch_pdl(embed_assemble_bwd_kernel<float>, dim3(grid), dim3(256), 0, ST, g, (float*)dpatches, dpos, dtokens, batch, tokens_per_sample, C, keep, num_tokens);
   return check_launch("vsx_embed_assemble_bwd");
 }
 
@@ -683,7 +709,7 @@ extern "C" int vsx_sr_combine(const float* conv, const float* tok, const float* 
   VSX_REQUIRE(C1 % 4 == 0 && C2 % 4 == 0 && C2 >= C1 && grid_in % 2 == 0 && keep2 >= 0 && keep2 <= C2, "vsx_sr_combine: bad shape");
   if (batch == 0) return VSX_OK;
   const int N2 = 1 + (grid_in / 2) * (grid_in / 2);
-  sr_combine_kernel<<<grid_for((long)batch * N2 * C2 / 4), 256, 0, ST>>>(conv, tok, pos, x, y, batch, grid_in, C1, C2, keep2);
+  launch_pdl(sr_combine_kernel, dim3(grid_for((long)batch * N2 * C2 / 4)), dim3(256), 0, ST, conv, tok, pos, x, y, batch, grid_in, C1, C2, keep2);
   return check_launch("vsx_sr_combine");
 }
 
@@ -697,7 +723,7 @@ extern "C" int vsx_sr_combine_bwd(const float* gy, void* dconv, void* dtok, int 
   if (gy_ > batch) gy_ = batch;
   if (gy_ < 1) gy_ = 1;
   const dim3 grid(gx, gy_);
-  if (dtype == VSX_BF16) sr_combine_bwd_kernel<bf16><<<grid, 256, 0, ST>>>(gy, (bf16*)dconv, (bf16*)dtok, dpos, gres, batch, grid_in, C1, C2, keep2);
-  else sr_combine_bwd_kernel<float><<<grid, 256, 0, ST>>>(gy, (float*)dconv, (float*)dtok, dpos, gres, batch, grid_in, C1, C2, keep2);
+  if (dtype == VSX_BF16) launch_pdl(sr_combine_bwd_kernel<bf16>, dim3(grid), dim3(256), 0, ST, gy, (bf16*)dconv, (bf16*)dtok, dpos, gres, batch, grid_in, C1, C2, keep2);
+  else launch_pdl(sr_combine_bwd_kernel<float>, dim3(grid), dim3(256), 0, ST, gy, (float*)dconv, (float*)dtok, dpos, gres, batch, grid_in, C1, C2, keep2);
   return check_launch("vsx_sr_combine_bwd");
 }

@@ -14,6 +14,8 @@ namespace {
 __global__ void __launch_bounds__(256) token_mix_samples_kernel(const float* __restrict__ in, float* __restrict__ out, const int* __restrict__ perm1,
                                                                  const int* __restrict__ perm2, int B, int n1, int CHW, int HW, int W, int py0, int py1,
                                                                  int px0, int px1, float lam2, float one_minus_lam2) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long total4 = (long)B * CHW / 4;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long)gridDim.x * blockDim.x) {
     const long e = i * 4;
@@ -46,6 +48,8 @@ __global__ void __launch_bounds__(256) token_mix_targets_kernel(const long* __re
                                                                  float* __restrict__ targets, float* __restrict__ ptargets, int B, int n1, int K, int PL,
                                                                  int by0, int by1, int bx0, int bx1, float on, float off, float lam1,
                                                                  float one_minus_lam1, float lam2, float one_minus_lam2) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long total = (long)B * K;
   const int P = PL * PL;
   for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
@@ -87,12 +91,12 @@ extern "C" int vsx_token_mix(const float* samples, float* out, const long* label
   const float lam1f = (float)lam_patch, lam2f = (float)lam_image;
   long blocks = ((long)batch * CHW / 4 + 255) / 256;
   const long cap = (long)num_sms() * 16;
-  token_mix_samples_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(samples, out, perm_patch, perm_image, batch, n1, (int)CHW, height * width,
+  launch_pdl(token_mix_samples_kernel, dim3((int)(blocks < cap ? blocks : cap)), dim3(256), 0, st, samples, out, perm_patch, perm_image, batch, n1, (int)CHW, height * width,
                                                                                width, box_y0 * ph, box_y1 * ph, box_x0 * pw, box_x1 * pw, lam2f, oml2);
   int rc = check_launch("vsx_token_mix");
   if (rc) return rc;
   blocks = ((long)batch * num_classes + 255) / 256;
-  token_mix_targets_kernel<<<(int)(blocks < cap ? blocks : cap), 256, 0, st>>>(labels, perm_patch, perm_image, targets, patch_targets, batch, n1,
+  launch_pdl(token_mix_targets_kernel, dim3((int)(blocks < cap ? blocks : cap)), dim3(256), 0, st, labels, perm_patch, perm_image, targets, patch_targets, batch, n1,
                                                                                num_classes, patch_len, box_y0, box_y1, box_x0, box_x1, on_value, off_value,
                                                                                lam1f, oml1, lam2f, oml2);
   return check_launch("vsx_token_mix");

@@ -96,3 +96,30 @@ class CandidateEvaluator:
             return evaluate(data_loader, m, self.device, self.meters)
         finally:
             m.set_active_subnet(None)
+
+
+def sample_candidate(nd, ks, rng):
+    """A random dense sub-network definition of the search space (uniform choice per entry; a removed block removes the removable
+    blocks that follow it in the stage, like search_utils/gen_utils.update_depth)."""
+    out, width, removing = [], None, False
+    for d, k in zip(nd, ks):
+        if d[0] in (0, 4, 5):
+            width = int(rng.choice(list(k)))
+            out.append((d[0], width) + tuple(d[2:]))
+        elif d[0] == 1:
+            hd = d[1][2]
+            heads = int(rng.choice(list(k['attn']))) // hd
+            feat = int(rng.choice(list(k['mlp'])))
+            exists = 1
+            if k.get('layer') is None:
+                removing = False
+            elif removing or int(rng.choice(list(k['layer']))) == 0:
+                exists, removing = 0, True
+            out.append((1, (width, heads, hd), (width, feat), exists))
+        elif d[0] == 3:
+            nxt = int(rng.choice(list(k)))
+            out.append((3, width, nxt))
+            width, removing = nxt, False
+        else:
+            out.append((2, width, d[2]))
+    return tuple(out)

@@ -76,3 +76,12 @@ def network_def(space, num_classes=1000):
 VIT_RES_TINY = ((4, 192),) + ((1, (192, 3, 64), (192, 768), 1),) * 4 + ((3, 192, 384),) + \
     ((1, (384, 6, 64), (384, 1536), 1),) * 4 + ((3, 384, 768),) + \
     ((1, (768, 12, 64), (768, 3072), 1),) * 4 + ((2, 768, 1000),)   # scripts/vit-sr-nas/reference_net/tiny.sh:18
+
+# BASELINE configs[3]: the searched ViT-ResNAS-Medium network, 4.6 G MACs (scripts/vit-sr-nas/searched_net/medium_mac@4.6G.sh:18)
+VIT_RESNAS_MEDIUM = (
+    (4, 240), (1, (240, 7, 32), (240, 960), 1), (1, (240, 6, 32), (240, 960), 1), (1, (240, 7, 32), (240, 800), 1),
+    (1, (240, 8, 32), (240, 960), 1), (1, (240, 7, 32), (240, 880), 1), (1, (240, 8, 32), (240, 880), 1), (1, (240, 6, 32), (240, 800), 1),
+    (3, 240, 640), (1, (640, 10, 48), (640, 1120), 1), (1, (640, 14, 48), (640, 1760), 1), (1, (640, 14, 48), (640, 1920), 1),
+    (1, (640, 16, 48), (640, 1760), 1), (1, (640, 14, 48), (640, 1440), 1), (1, (640, 16, 48), (640, 1760), 1), (1, (640, 16, 48), (640, 1920), 1),
+    (3, 640, 880), (1, (880, 16, 64), (880, 3200), 1), (1, (880, 10, 64), (880, 3840), 1), (1, (880, 16, 64), (880, 3840), 1),
+    (1, (880, 12, 64), (880, 3200), 1), (1, (880, 16, 64), (880, 3520), 1), (1, (880, 14, 64), (880, 3520), 1), (2, 880, 1000))
