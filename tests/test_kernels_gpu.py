@@ -249,9 +249,11 @@ def test_gemm_grouped(ops, tile_rows):
 
 # ---------------------------------------------------------------------------------------------- attention core
 @pytest.mark.parametrize('N,H,D,Hk', [(257, 3, 64, 3), (257, 6, 32, 5), (65, 4, 48, 2), (17, 4, 64, 3), (50, 2, 32, 2), (197, 2, 64, 1)])
-@pytest.mark.parametrize('mode', ['bf16_auto', 'bf16_mma', 'bf16_fp32math', 'fp32'])
+@pytest.mark.parametrize('mode', ['bf16_tcgen05', 'bf16_auto', 'bf16_mma', 'bf16_fp32math', 'fp32'])
 def test_attention_core(ops, N, H, D, Hk, mode):
-    """bf16_auto = the tcgen05 kernel for head_dim 64 (csrc/attn_tc.cu), mma.sync otherwise; bf16_mma forces the mma.sync kernel."""
+    """bf16_tcgen05 forces the tcgen05 / TMEM kernel (csrc/attn_tc.cu: head_dim 64, and 32 / 48 through zero-padded 4-D TMA boxes) and
+    fails if a shape is not served by it; bf16_auto = what the model gets (the same kernel for every shape here); bf16_mma forces the
+    legacy mma.sync kernel."""
     B = 3
     g = torch.Generator().manual_seed(N + H + D)
     dt_ = torch.float32 if mode == 'fp32' else torch.bfloat16
@@ -268,7 +270,7 @@ def test_attention_core(ops, N, H, D, Hk, mode):
     o_ref = o_ref.detach() * keep.view(1, 1, H, 1)
     lse_ref = torch.logsumexp(s.detach(), -1)                                 # [B,H,N]
 
-    impl = {'bf16_fp32math': ops.ATTN_FP32, 'bf16_mma': ops.ATTN_MMA_SYNC}.get(mode, ops.ATTN_AUTO)
+    impl = {'bf16_fp32math': ops.ATTN_FP32, 'bf16_mma': ops.ATTN_MMA_SYNC, 'bf16_tcgen05': ops.ATTN_TCGEN05}.get(mode, ops.ATTN_AUTO)
     qd = qkv.cuda().view(B * N, 3 * H * D)
     o = torch.full((B * N, H * D), float('nan'), device='cuda', dtype=dt_)
     lse = torch.zeros(B, H, N, device='cuda')
@@ -284,12 +286,12 @@ def test_attention_core(ops, N, H, D, Hk, mode):
         assert rel(dq[:, :, i], dqkv_ref[:, :, i]) < (2e-5 if mode == 'fp32' else 1.5e-2), nm
 
 
-@pytest.mark.parametrize('B,N,H,Hk', [(70, 257, 4, 3), (200, 65, 8, 5), (256, 17, 12, 12), (40, 288, 2, 2), (33, 128, 3, 3), (5, 97, 2, 1)])
-def test_attention_tcgen05_persistent(ops, B, N, H, Hk):
+@pytest.mark.parametrize('B,N,H,Hk,D', [(70, 257, 4, 3, 64), (200, 65, 8, 5, 64), (256, 17, 12, 12, 64), (40, 288, 2, 2, 64), (33, 128, 3, 3, 64), (5, 97, 2, 1, 64),
+                                        (48, 257, 8, 7, 32), (64, 65, 12, 10, 48), (40, 257, 6, 6, 32), (100, 17, 12, 6, 48), (9, 198, 2, 2, 32)])
+def test_attention_tcgen05_persistent(ops, B, N, H, Hk, D):
     """The tcgen05 attention kernels with more (sample, head) pairs than SMs, so every CTA walks several pairs through its
     TMA / TMEM / mbarrier pipelines, against the fp32-math CUDA-core kernel on the same bf16 inputs (outputs, lse, dqkv and
-    the fused qkv-bias gradient)."""
-    D = 64
+    the fused qkv-bias gradient).  head_dim 32 / 48 are the shapes of sr_tiny_mh, sr_small and the searched Medium network."""
     g = torch.Generator().manual_seed(B + N + H)
     qkv = (torch.randn(B * N, 3 * H * D, generator=g) * 1.2).to(torch.bfloat16).cuda()
     do = torch.randn(B * N, H * D, generator=g).to(torch.bfloat16).cuda()

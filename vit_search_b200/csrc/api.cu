@@ -117,6 +117,35 @@ int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows,
   return VSX_OK;
 }
 
+// 4-D bf16 map over a [B][rows][heads][head_dim] tensor (the qkv / attention-output layout with heads as their own dimension);
+// box = 64 x 1 x box_rows x 1, 128B swizzle.  A box is 64 columns wide whatever head_dim is: columns >= head_dim are out of bounds in
+// dimension 0 and therefore zero-filled, as are rows >= `rows` -- a head of width 32 or 48 lands in shared memory as the zero-padded
+// 128-byte-row tile the head_dim-64 kernels expect.
+int make_tmap_heads(CUtensorMap* m, const void* base, uint64_t head_dim, uint64_t heads, uint64_t rows, uint64_t batch, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return VSX_ERR_CUDA;
+  }
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (head_dim * 2) % 16 != 0 || head_dim == 0 || head_dim > 64 || heads == 0 || rows == 0 || batch == 0) {
+    set_error("make_tmap_heads: need a 16-byte aligned base and a head_dim that is a multiple of 8, <= 64 (base=%p head_dim=%llu)", base,
+              (unsigned long long)head_dim);
+    return VSX_ERR_ARG;
+  }
+  cuuint64_t dims[4] = {head_dim, heads, rows, batch};
+  cuuint64_t strides[3] = {head_dim * 2, heads * head_dim * 2, rows * heads * head_dim * 2};
+  cuuint32_t box[4] = {64, 1, box_rows, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (heads) failed with CUresult %d (head_dim=%llu heads=%llu rows=%llu batch=%llu box_rows=%u)", (int)r,
+              (unsigned long long)head_dim, (unsigned long long)heads, (unsigned long long)rows, (unsigned long long)batch, box_rows);
+    return VSX_ERR_CUDA;
+  }
+  return VSX_OK;
+}
+
 // 4-D channels-last bf16 map [B][H][W][C]; box = C x box_w x box_h x 1, no swizzle (dense [box_h][box_w][C] in shared memory).
 // Out-of-range coordinates (negative included) are zero-filled on loads and clipped on stores: the halo of a convolution tile.
 int make_tmap_nhwc(CUtensorMap* m, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint32_t box_w, uint32_t box_h) {

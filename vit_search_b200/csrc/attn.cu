@@ -11,8 +11,8 @@ int attn_fwd_mma(const void* qkv, void* o, float* lse, int B, int N, int H, int 
 int attn_bwd_mma(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int N, int H, int D, int Hk,
                  float scale, float* dbias, cudaStream_t st);
 bool attn_mma_supported(int N, int D);
-int attn_fwd_tc(const void* qkv, void* o, float* lse, int B, int N, int H, int Hk, float scale, cudaStream_t st);
-int attn_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int N, int H, int Hk, float scale,
+int attn_fwd_tc(const void* qkv, void* o, float* lse, int B, int N, int H, int D, int Hk, float scale, cudaStream_t st);
+int attn_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int N, int H, int D, int Hk, float scale,
                 float* dbias, cudaStream_t st);
 bool attn_tc_supported(int N, int D);
 void attn_set_debug(long long* p);
@@ -35,8 +35,8 @@ extern "C" int vsx_attn_fwd(const void* qkv, void* o, float* lse, int dtype, int
   if (dtype == VSX_F32) return attn_fwd_ref<float>(qkv, o, lse, batch, tokens, heads, head_dim, heads_keep, scale, st);
   if (dtype == VSX_BF16) {
     if ((impl == VSX_ATTN_IMPL_AUTO || impl == VSX_ATTN_IMPL_TCGEN05) && attn_tc_supported(tokens, head_dim))
-      return attn_fwd_tc(qkv, o, lse, batch, tokens, heads, heads_keep, scale, st);
-    VSX_REQUIRE(impl != VSX_ATTN_IMPL_TCGEN05, "vsx_attn_fwd: the tcgen05 kernel needs head_dim 64 and tokens <= 288 (got %d, %d)", head_dim, tokens);
+      return attn_fwd_tc(qkv, o, lse, batch, tokens, heads, head_dim, heads_keep, scale, st);
+    VSX_REQUIRE(impl != VSX_ATTN_IMPL_TCGEN05, "vsx_attn_fwd: the tcgen05 kernel needs head_dim 32 / 48 / 64 and tokens <= 288 (got %d, %d)", head_dim, tokens);
     if (impl != VSX_ATTN_IMPL_FP32 && attn_mma_supported(tokens, head_dim))
       return attn_fwd_mma(qkv, o, lse, batch, tokens, heads, head_dim, heads_keep, scale, st);
     return attn_fwd_ref<bf16>(qkv, o, lse, batch, tokens, heads, head_dim, heads_keep, scale, st);
@@ -61,8 +61,8 @@ extern "C" int vsx_attn_bwd(const void* qkv, const void* o, const void* d_o, con
   }
   if (dtype == VSX_BF16) {
     if ((impl == VSX_ATTN_IMPL_AUTO || impl == VSX_ATTN_IMPL_TCGEN05) && attn_tc_supported(tokens, head_dim))
-      return attn_bwd_tc(qkv, o, d_o, lse, dqkv, batch, tokens, heads, heads_keep, scale, dbias, st);
-    VSX_REQUIRE(impl != VSX_ATTN_IMPL_TCGEN05, "vsx_attn_bwd: the tcgen05 kernel needs head_dim 64 and tokens <= 288 (got %d, %d)", head_dim, tokens);
+      return attn_bwd_tc(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, heads_keep, scale, dbias, st);
+    VSX_REQUIRE(impl != VSX_ATTN_IMPL_TCGEN05, "vsx_attn_bwd: the tcgen05 kernel needs head_dim 32 / 48 / 64 and tokens <= 288 (got %d, %d)", head_dim, tokens);
     if (impl != VSX_ATTN_IMPL_FP32 && attn_mma_supported(tokens, head_dim))
       return attn_bwd_mma(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, heads_keep, scale, dbias, st);
     rc = attn_bwd_ref<bf16>(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, heads_keep, scale, st);

@@ -1,4 +1,7 @@
-// tcgen05 / TMEM / TMA attention for the ViT-Res shapes (head_dim 64, N = 257 / 65 / 17 tokens, N <= 288), bf16 in / fp32 softmax.
+// tcgen05 / TMEM / TMA attention for the ViT-Res shapes (head_dim 64, 48 or 32; N = 257 / 65 / 17 tokens, N <= 288), bf16 in / fp32 softmax.
+// Head dims below 64 (sr_tiny_mh, sr_small, the searched Medium network) run the SAME kernels: the 4-D tensor maps [B][N][heads][D] load
+// 64-column boxes whose columns >= D are out of bounds and therefore hardware zero-filled, so every shared-memory tile keeps the
+// 128-byte swizzled row of the D = 64 layout; the reductions over the head dim stop after D / 16 k steps and results are written D wide.
 //
 // Replaces q@k^T*scale -> softmax -> attn@v and their autograd (nets/supernet_blocks.py:103-112).  Nothing of size N x N
 // touches HBM (the reference materialises [B,H,N,N] three times); masked heads are never computed.
@@ -24,12 +27,11 @@
 
 namespace vsx {
 
-int make_tmap_3d(CUtensorMap* m, const void* base, uint64_t cols, uint64_t rows, uint64_t batch, uint64_t ld_elems,
-                 uint64_t batch_stride_elems, uint32_t box_cols, uint32_t box_rows);
+int make_tmap_heads(CUtensorMap* m, const void* base, uint64_t head_dim, uint64_t heads, uint64_t rows, uint64_t batch, uint32_t box_rows);
 
 namespace {
 
-constexpr int HD_ = 64;                    // head dim: one 128-byte swizzle row
+constexpr int HD_ = 64;                    // tile width in shared memory: one 128-byte swizzle row (head dims < 64 are zero padded)
 constexpr int KV_BOX = 96;                 // rows per K / V TMA box (= backward key block)
 constexpr int ATT_MAX_N = 288;             // 3 boxes of keys, 3 query tiles
 constexpr int TILE16K = 128 * 128;         // [128 rows][64 bf16] tile = one swizzle atom column
@@ -41,13 +43,13 @@ constexpr float LOG2E_F = 1.4426950408889634f;
 constexpr float LN2_F = 0.6931471805599453f;
 
 struct AttnMaps {
-  CUtensorMap q;    // qkv [B][N][3*H*64], box 64 x 128 x 1
-  CUtensorMap kv;   // qkv, box 64 x 96 x 1
-  CUtensorMap d_o;  // d_o [B][N][H*64], box 64 x 128 x 1 (backward only)
+  CUtensorMap q;    // qkv as [B][N][3*H heads][D], box 64 x 1 x 128 x 1 (columns >= D zero-filled)
+  CUtensorMap kv;   // qkv, box 64 x 1 x 96 (forward) / 64 (backward) x 1
+  CUtensorMap d_o;  // d_o as [B][N][H][D], box 64 x 1 x 128 x 1 (backward only)
 };
 
 struct AttnArgs {
-  int B, N, H, Hk;
+  int B, N, H, Hk, D;
   float scale;
   bf16* o;             // fwd: output; bwd: forward output (for delta)
   const bf16* d_o;     // bwd
@@ -57,11 +59,26 @@ struct AttnArgs {
   long long* dbg;      // optional timeline buffer (tools/attn_timeline.py); null in production
 };
 
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2) {
+// one [rows][64] tile of head `head` (index into the 3*H or H head slots), rows row0.. of sample b
+__device__ __forceinline__ void tma_load_head(uint32_t dst, const CUtensorMap* m, uint32_t bar, int head, int row0, int b) {
   asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
-      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(0), "r"(head), "r"(row0), "r"(b)
       : "memory");
+}
+// `ncols` (a multiple of 8, <= 32) of 32 fp32 values -> bf16 -> global
+__device__ __forceinline__ void store_bf16_n(bf16* dst, const float (&v)[32], int ncols) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (8 * i < ncols) {
+      uint4 r;
+      r.x = pack_bf16(v[8 * i], v[8 * i + 1]);
+      r.y = pack_bf16(v[8 * i + 2], v[8 * i + 3]);
+      r.z = pack_bf16(v[8 * i + 4], v[8 * i + 5]);
+      r.w = pack_bf16(v[8 * i + 6], v[8 * i + 7]);
+      *reinterpret_cast<uint4*>(dst + 8 * i) = r;
+    }
+  }
 }
 
 // Shared-memory matrix descriptors (128B swizzle, 8-row groups 1024 B apart).
@@ -218,7 +235,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_tc_kernel(const __gri
   float* xl = xm + 256;                                       // [2][128] partial row sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int N = a.N, HD = a.H * HD_;
+  const int N = a.N, D = a.D, HD = a.H * D, KS = D >> 4;      // KS: 16-wide k steps over the head dim
   const int QT = (N + 127) / 128, NKP = round16(N), nkb = (N + KV_BOX - 1) / KV_BOX;
   const int total = a.B * a.Hk;
 
@@ -247,16 +264,16 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_tc_kernel(const __gri
         const int b = w / a.Hk, h = w % a.Hk;
         mbar_wait_relaxed(bar(1), ((uint32_t)nw & 1u) ^ 1u);
         mbar_expect_tx(bar(0), (uint32_t)nkb * BOX12K);
-        for (int c = 0; c < nkb; ++c) tma_load_3d(base + F_K + c * BOX12K, &maps.kv, bar(0), HD + h * HD_, c * KV_BOX, b);
+        for (int c = 0; c < nkb; ++c) tma_load_head(base + F_K + c * BOX12K, &maps.kv, bar(0), a.H + h, c * KV_BOX, b);
         for (int i = 0; i < QT; ++i, ++qit) {
           const int s = qit & 1;
           mbar_wait_relaxed(bar(6 + s), (((uint32_t)qit >> 1) & 1u) ^ 1u);
           mbar_expect_tx(bar(4 + s), TILE16K);
-          tma_load_3d(base + F_Q + s * TILE16K, &maps.q, bar(4 + s), h * HD_, i * 128, b);
+          tma_load_head(base + F_Q + s * TILE16K, &maps.q, bar(4 + s), h, i * 128, b);
           if (i == 0) {
             mbar_wait_relaxed(bar(3), ((uint32_t)nw & 1u) ^ 1u);
             mbar_expect_tx(bar(2), (uint32_t)nkb * BOX12K);
-            for (int c = 0; c < nkb; ++c) tma_load_3d(base + F_V + c * BOX12K, &maps.kv, bar(2), 2 * HD + h * HD_, c * KV_BOX, b);
+            for (int c = 0; c < nkb; ++c) tma_load_head(base + F_V + c * BOX12K, &maps.kv, bar(2), 2 * a.H + h, c * KV_BOX, b);
           }
         }
       }
@@ -278,7 +295,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_tc_kernel(const __gri
           const uint64_t dq = desc_k(qa), dk = desc_k(base + F_K + c * BOX12K);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            if (leader) umma_bf16(tmem + c * KV_BOX, dq + 2 * k, dk + 2 * k, id_s, k > 0 ? 1u : 0u);
+            if (leader && k < KS) umma_bf16(tmem + c * KV_BOX, dq + 2 * k, dk + 2 * k, id_s, k > 0 ? 1u : 0u);
         }
         if (leader) {
           umma_commit(bar(6 + s));
@@ -312,7 +329,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_tc_kernel(const __gri
     const int nch = (NKP + 31) / 32;
     uint8_t* Ps = smem + F_P;
     int blk = 0;
-    zero_masked(a.o, HD, (long)a.B * N, a.Hk * HD_, (a.H - a.Hk) * HD_, 1, 0, threadIdx.x - SM_WARP0 * 32, SM_THREADS);
+    zero_masked(a.o, HD, (long)a.B * N, a.Hk * D, (a.H - a.Hk) * D, 1, 0, threadIdx.x - SM_WARP0 * 32, SM_THREADS);
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
       const int b = w / a.Hk, h = w % a.Hk;
       for (int i = 0; i < QT; ++i, ++blk) {
@@ -380,7 +397,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_tc_kernel(const __gri
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= inv;
             const long r = (long)b * N + i * 128 + row;
-            store_bf16_32(a.o + r * HD + h * HD_ + hf * 32, v);
+            store_bf16_n(a.o + r * HD + h * D + hf * 32, v, D - hf * 32);
             if (hf == 0) a.lse[((long)b * a.H + h) * N + i * 128 + row] = (mc + log2f(l)) * LN2_F;
           }
         }
@@ -454,7 +471,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
   float2* stats = reinterpret_cast<float2*>(smem + B_END + 256 + 768);   // [2 buffers][3 tiles][128 rows] (lse * log2e, delta)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int N = a.N, HD = a.H * HD_;
+  const int N = a.N, D = a.D, HD = a.H * D, KS = D >> 4;
   const int QT = (N + 127) / 128, KB = (N + BKW - 1) / BKW;
   // accumulator buffers (see dvk_col / dq_col).  Double buffering for N <= 128 is wired up but measured 10 % SLOWER on the N = 17
   // launches (profiles/: r1l vs r1k; the epilogue warps then compete with the softmax warps for tcgen05.ld bandwidth instead of
@@ -491,15 +508,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
           const int ks = kvit & 1;
           mbar_wait_relaxed(bar(2 + ks), (((uint32_t)kvit >> 1) & 1u) ^ 1u);
           mbar_expect_tx(bar(ks), 2 * BOX8K);
-          tma_load_3d(base + B_KV + ks * 2 * BOX8K, &maps.kv, bar(ks), HD + h * HD_, j * BKW, b);
-          tma_load_3d(base + B_KV + ks * 2 * BOX8K + BOX8K, &maps.kv, bar(ks), 2 * HD + h * HD_, j * BKW, b);
+          tma_load_head(base + B_KV + ks * 2 * BOX8K, &maps.kv, bar(ks), a.H + h, j * BKW, b);
+          tma_load_head(base + B_KV + ks * 2 * BOX8K + BOX8K, &maps.kv, bar(ks), 2 * a.H + h, j * BKW, b);
           if (j == 0) {
             for (int i = 0; i < QT; ++i, ++qit) {
               const int qs = qit % 3;
               mbar_wait_relaxed(bar(7 + qs), (((uint32_t)qit / 3) & 1u) ^ 1u);
               mbar_expect_tx(bar(4 + qs), 2 * TILE16K);
-              tma_load_3d(base + B_QDO + qs * 2 * TILE16K, &maps.q, bar(4 + qs), h * HD_, i * 128, b);
-              tma_load_3d(base + B_QDO + qs * 2 * TILE16K + TILE16K, &maps.d_o, bar(4 + qs), h * HD_, i * 128, b);
+              tma_load_head(base + B_QDO + qs * 2 * TILE16K, &maps.q, bar(4 + qs), h, i * 128, b);
+              tma_load_head(base + B_QDO + qs * 2 * TILE16K + TILE16K, &maps.d_o, bar(4 + qs), h, i * 128, b);
             }
           }
         }
@@ -521,10 +538,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
       const uint64_t dq = desc_k(qa), dk = desc_k(ka), ddo = desc_k(qa + TILE16K), dv = desc_k(ka + BOX8K);
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (leader) umma_bf16(tmem + C_S, dq + 2 * k, dk + 2 * k, id_s, k > 0 ? 1u : 0u);
+        if (leader && k < KS) umma_bf16(tmem + C_S, dq + 2 * k, dk + 2 * k, id_s, k > 0 ? 1u : 0u);
 #pragma unroll
       for (int k = 0; k < 4; ++k)
-        if (leader) umma_bf16(tmem + C_DP, ddo + 2 * k, dv + 2 * k, id_s, k > 0 ? 1u : 0u);
+        if (leader && k < KS) umma_bf16(tmem + C_DP, ddo + 2 * k, dv + 2 * k, id_s, k > 0 ? 1u : 0u);
       if (leader) umma_commit(bar(BAR_SDP));
       __syncwarp();
     };
@@ -658,7 +675,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
     const int q = warp & 3, row = q * 32 + lane, et = threadIdx.x - EP_WARP0 * 32;   // et = 0..127
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
     const long ldq = 3L * HD;
-    zero_masked(a.dqkv, ldq, (long)a.B * N, a.Hk * HD_, (a.H - a.Hk) * HD_, 3, HD, et, 128);
+    zero_masked(a.dqkv, ldq, (long)a.B * N, a.Hk * D, (a.H - a.Hk) * D, 3, HD, et, 128);
     // lse (log2 units) and delta = dO . O of sample b's query rows -> stats buffer; rows >= N get lse = +inf, so P = exp2(S*c - inf) = 0
     // and dS = 0 there (S and dP are exact zeros on those rows: TMA zero fill)
     auto make_stats = [&](int b, int buf) {
@@ -669,11 +686,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
         const int r = i * 128 + et;
         if (i < QT && r < N) {
           v.x = a.lse[((long)b * a.H + h) * N + r] * LOG2E_F;
-          const bf16* op = a.o + ((long)b * N + r) * HD + h * HD_;
-          const bf16* dp = a.d_o + ((long)b * N + r) * HD + h * HD_;
+          const bf16* op = a.o + ((long)b * N + r) * HD + h * D;
+          const bf16* dp = a.d_o + ((long)b * N + r) * HD + h * D;
           float acc = 0.f;
 #pragma unroll
-          for (int cc = 0; cc < HD_; cc += 8) {
+          for (int cc = 0; cc < D; cc += 8) {
             const uint4 ov = *reinterpret_cast<const uint4*>(op + cc);
             const uint4 dv = *reinterpret_cast<const uint4*>(dp + cc);
             const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
@@ -708,7 +725,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
         const int keys_valid = min(BKW, N - j * BKW);
         if ((q & 1) * 32 < keys_valid) {
           const bool kvalid = krow < keys_valid;
-          bf16* dst = a.dqkv + ((long)b * N + j * BKW + krow) * ldq + (is_v ? 2 * HD : HD) + h * HD_;
+          bf16* dst = a.dqkv + ((long)b * N + j * BKW + krow) * ldq + (is_v ? 2 * HD : HD) + h * D;
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             float v[32];
@@ -720,7 +737,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
                 v[t] *= kv_mul;
                 csum[half][t] += v[t];
               }
-              store_bf16_32(dst + half * 32, v);
+              store_bf16_n(dst + half * 32, v, D - half * 32);
             }
           }
         }
@@ -753,7 +770,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
                   v[t] *= a.scale;
                   csum[half][t] += v[t];
                 }
-                store_bf16_32(a.dqkv + ((long)b * N + i * 128 + row) * ldq + h * HD_ + half * 32, v);
+                store_bf16_n(a.dqkv + ((long)b * N + i * 128 + row) * ldq + h * D + half * 32, v, D - half * 32);
               }
             }
           }
@@ -769,7 +786,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
     }
     if (a.dbias != nullptr) {
       named_bar_sync(1, 128);
-      for (int t = et; t < 192; t += 128) atomicAdd(a.dbias + (long)(t >> 6) * HD + h * HD_ + (t & 63), cs[t]);
+      for (int t = et; t < 192; t += 128)
+        if ((t & 63) < D) atomicAdd(a.dbias + (long)(t >> 6) * HD + h * D + (t & 63), cs[t]);
     }
   }
   tc_fence_before();
@@ -802,45 +820,45 @@ int zero_cols(void* base, long ld_elems, long rows, long col0, long ncols, cudaS
 static long long* g_attn_dbg = nullptr;
 void attn_set_debug(long long* p) { g_attn_dbg = p; }
 
-bool attn_tc_supported(int N, int D) { return D == HD_ && N >= 1 && N <= ATT_MAX_N; }
+bool attn_tc_supported(int N, int D) { return (D == 64 || D == 48 || D == 32) && N >= 1 && N <= ATT_MAX_N; }
 
-int attn_fwd_tc(const void* qkv, void* o, float* lse, int B, int N, int H, int Hk, float scale, cudaStream_t st) {
-  const long HD = (long)H * HD_;
+int attn_fwd_tc(const void* qkv, void* o, float* lse, int B, int N, int H, int D, int Hk, float scale, cudaStream_t st) {
+  const long HD = (long)H * D;
   int rc = VSX_OK;
   if (Hk == 0) return zero_cols(o, HD, (long)B * N, 0, HD, st, "vsx_attn_fwd");
   AttnMaps maps;
   memset(&maps, 0, sizeof(maps));
-  if ((rc = make_tmap_3d(&maps.q, qkv, 3 * HD, N, B, 3 * HD, (uint64_t)N * 3 * HD, 64, 128))) return rc;
-  if ((rc = make_tmap_3d(&maps.kv, qkv, 3 * HD, N, B, 3 * HD, (uint64_t)N * 3 * HD, 64, KV_BOX))) return rc;
+  if ((rc = make_tmap_heads(&maps.q, qkv, D, 3 * H, N, B, 128))) return rc;
+  if ((rc = make_tmap_heads(&maps.kv, qkv, D, 3 * H, N, B, KV_BOX))) return rc;
   static bool configured = false;
   if (!configured) {
     if ((rc = set_smem((const void*)attn_fwd_tc_kernel, F_SMEM, "vsx_attn_fwd"))) return rc;
     configured = true;
   }
   AttnArgs a;
-  a.B = B, a.N = N, a.H = H, a.Hk = Hk, a.scale = scale, a.o = (bf16*)o, a.d_o = nullptr, a.lse = lse, a.dqkv = nullptr, a.dbias = nullptr, a.dbg = nullptr;
+  a.B = B, a.N = N, a.H = H, a.Hk = Hk, a.D = D, a.scale = scale, a.o = (bf16*)o, a.d_o = nullptr, a.lse = lse, a.dqkv = nullptr, a.dbias = nullptr, a.dbg = nullptr;
   const int total = B * Hk;
   const int grid = total < num_sms() ? total : num_sms();
   launch_pdl(attn_fwd_tc_kernel, dim3(grid), dim3(ATT_THREADS), F_SMEM, st, maps, a);
   return check_launch("vsx_attn_fwd");
 }
 
-int attn_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int N, int H, int Hk, float scale,
+int attn_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int N, int H, int D, int Hk, float scale,
                 float* dbias, cudaStream_t st) {
-  const long HD = (long)H * HD_;
+  const long HD = (long)H * D;
   int rc = VSX_OK;
   if (Hk == 0) return zero_cols(dqkv, 3 * HD, (long)B * N, 0, 3 * HD, st, "vsx_attn_bwd");
   AttnMaps maps;
-  if ((rc = make_tmap_3d(&maps.q, qkv, 3 * HD, N, B, 3 * HD, (uint64_t)N * 3 * HD, 64, 128))) return rc;
-  if ((rc = make_tmap_3d(&maps.kv, qkv, 3 * HD, N, B, 3 * HD, (uint64_t)N * 3 * HD, 64, BKW))) return rc;
-  if ((rc = make_tmap_3d(&maps.d_o, d_o, HD, N, B, HD, (uint64_t)N * HD, 64, 128))) return rc;
+  if ((rc = make_tmap_heads(&maps.q, qkv, D, 3 * H, N, B, 128))) return rc;
+  if ((rc = make_tmap_heads(&maps.kv, qkv, D, 3 * H, N, B, BKW))) return rc;
+  if ((rc = make_tmap_heads(&maps.d_o, d_o, D, H, N, B, 128))) return rc;
   static bool configured = false;
   if (!configured) {
     if ((rc = set_smem((const void*)attn_bwd_tc_kernel, B_SMEM, "vsx_attn_bwd"))) return rc;
     configured = true;
   }
   AttnArgs a;
-  a.B = B, a.N = N, a.H = H, a.Hk = Hk, a.scale = scale, a.o = (bf16*)const_cast<void*>(o), a.d_o = (const bf16*)d_o,
+  a.B = B, a.N = N, a.H = H, a.Hk = Hk, a.D = D, a.scale = scale, a.o = (bf16*)const_cast<void*>(o), a.d_o = (const bf16*)d_o,
   a.lse = const_cast<float*>(lse), a.dqkv = (bf16*)dqkv, a.dbias = dbias, a.dbg = g_attn_dbg;
   int per_head = num_sms() / Hk;
   if (per_head < 1) per_head = 1;
