@@ -212,6 +212,11 @@ typedef struct vsx_half_block_grad {
 } vsx_half_block_grad;
 int vsx_half_block_fwd(const vsx_half_block* d, void* stream);
 int vsx_half_block_bwd(const vsx_half_block_grad* d, void* stream);
+/* All half blocks of a stage (consecutive transformer blocks between two spatial reductions: the loop at nets/vit_sr_supernet.py:
+ * 431-441) in one call per direction.  `halves` is in forward order for both; vsx_stage_bwd walks it from the last entry to the
+ * first (g_out of entry i must be g_in of entry i + 1). */
+int vsx_stage_fwd(const vsx_half_block* halves, int count, void* stream);
+int vsx_stage_bwd(const vsx_half_block_grad* halves, int count, void* stream);
 /* Kernels launched by this thread through the library so far (bench.py's gpu_launches). */
 long vsx_launch_count(void);
 
@@ -321,6 +326,29 @@ int vsx_token_mix(const float* samples, float* out, const long* labels, const in
  * -------------------------------------------------------------------------------------------------- */
 int vsx_eval_metrics(const float* logits, long ld, const long* labels, int rows, int cols, float* row_loss, int* row_rank, double* totals,
                      void* stream);
+
+/* ----------------------------------------------------------------------------------------------------
+ * Several extents in ONE launch: a batch that carries several sub-architectures (the multi-architectural sampling of
+ * nets/channel_drop.py:93-111: sample i uses mask row perm[i % G]) is a sequence of row ranges ("segments": consecutive samples that
+ * share one set of keep counts).  The *_segs entry points process the whole batch in one launch and look each row's extents up in the
+ * table, instead of one launch per segment.  keep[i] == 0: the rows of segment i are skipped (dropped layer).  When a shape does not
+ * qualify for the single-launch kernels they fall back to one launch per segment with identical results.
+ * -------------------------------------------------------------------------------------------------- */
+#define VSX_MAX_SEGMENTS 8
+typedef struct vsx_row_segments {
+  int count;                        /* 1 .. VSX_MAX_SEGMENTS */
+  int row_end[VSX_MAX_SEGMENTS];    /* exclusive end row of segment i, relative to the first row of the launch; the last one = rows */
+  int keep[VSX_MAX_SEGMENTS];       /* kept channels (LayerNorm: kept embedding width; cast: kept output width) */
+  int keep2[VSX_MAX_SEGMENTS];      /* vsx_masked_ln_bwd_segs: kept width of the fused cast output (ignored without cast_out) */
+} vsx_row_segments;
+int vsx_masked_ln_fwd_segs(const float* x, long ldx, const float* gamma, const float* beta, void* y, int dtype, long ldy, float* mean,
+                           float* rstd, int rows, int C, const vsx_row_segments* segs, float eps, void* stream);
+int vsx_masked_ln_bwd_segs(const void* dy, int dtype, long lddy, const float* x, long ldx, const float* mean, const float* rstd,
+                           const float* gamma, const float* g_in, float* g_out, long ldg, float* dgamma, float* dbeta, int rows, int C,
+                           const vsx_row_segments* segs, void* cast_out, long ld_cast, const float* cast_scale, int cast_rows_per_sample,
+                           float* cast_colsum, void* stream);
+int vsx_scale_mask_cast_segs(const float* g, long ldg, const float* row_scale, int rows_per_sample, void* out, int dtype, long ldo,
+                             int rows, int cols, const vsx_row_segments* segs, float* colsum, void* stream);
 
 /* ----------------------------------------------------------------------------------------------------
  * Loss and optimizer ends of the step (engine.py:152-157, :175-177).

@@ -33,6 +33,9 @@ SIGNATURES = {
     'vsx_masked_ln_fwd': [_p, _l, _p, _p, _p, _p, _i, _l, _p, _p, _i, _i, _i, _f, _i, _i, _p],
     'vsx_masked_ln_bwd_cast': [_p, _i, _l, _p, _l, _p, _p, _p, _p, _p, _l, _p, _p, _i, _i, _i, _p, _l, _p, _i, _i, _p, _p],
     'vsx_masked_ln_bwd': [_p, _p, _i, _l, _p, _l, _p, _p, _p, _p, _p, _l, _p, _p, _i, _i, _i, _i, _i, _p],
+    'vsx_masked_ln_fwd_segs': [_p, _l, _p, _p, _p, _i, _l, _p, _p, _i, _i, _p, _f, _p],
+    'vsx_masked_ln_bwd_segs': [_p, _i, _l, _p, _l, _p, _p, _p, _p, _p, _l, _p, _p, _i, _i, _p, _p, _l, _p, _i, _p, _p],
+    'vsx_scale_mask_cast_segs': [_p, _l, _p, _i, _p, _i, _l, _i, _i, _p, _p, _p],
     'vsx_gemm': [C.POINTER(GemmDesc), _p],
     'vsx_attn_fwd': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p],
     'vsx_attn_bwd': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p],
@@ -42,6 +45,8 @@ SIGNATURES = {
     'vsx_gemm_grouped': [_p, _i, _p],
     'vsx_half_block_fwd': [_p, _p],
     'vsx_half_block_bwd': [_p, _p],
+    'vsx_stage_fwd': [_p, _i, _p],
+    'vsx_stage_bwd': [_p, _i, _p],
     'vsx_launch_count': [],
     'vsx_token_mix': [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _f, C.c_double, C.c_double, _p],
     'vsx_conv3x3_force_impl': [_i],
@@ -76,6 +81,10 @@ _RESTYPES = {'vsx_last_error': C.c_char_p, 'vsx_launch_count': C.c_long}
 class AdamWTensor(C.Structure):
     _fields_ = [('param', _p), ('grad', _p), ('exp_avg', _p), ('exp_avg_sq', _p), ('shadow_hi', _p), ('shadow_lo', _p),
                 ('numel', _l), ('weight_decay', _f), ('ema_decay', _f), ('ema', _p)]
+
+
+class RowSegments(C.Structure):
+    _fields_ = [('count', _i), ('row_end', _i * 8), ('keep', _i * 8), ('keep2', _i * 8)]
 
 
 class Segment(C.Structure):

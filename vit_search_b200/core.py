@@ -180,7 +180,14 @@ class _GradPool:
         self.flat, self.off = None, 0
 
     def begin(self, numel, device):
-        self.flat, self.off = torch.zeros(numel, device=device, dtype=torch.float32), 0
+        # one PERSISTENT buffer, cleared with a memset: gradient addresses are then the same in every step (the optimizer's pointer table
+        # stays valid, the all-reduce always works on the same registered memory) and the caching allocator is not asked for 280 MB per step
+        buf = getattr(self, 'buf', None)
+        if buf is None or buf.numel() != numel or buf.device != torch.device(device):
+            self.buf = buf = torch.zeros(numel, device=device, dtype=torch.float32)
+        else:
+            buf.zero_()
+        self.flat, self.off = buf, 0
 
     def end(self):
         self.flat, self.off = None, 0
@@ -621,3 +628,105 @@ class HalfBlockFn(torch.autograd.Function):
             g_in, pg = bwd(ctx.meta, g, ctx.saved, x, *params)
         ctx.saved = ctx.prev = None
         return (None, g_in) + tuple(pg)
+
+
+# ------------------------------------------------------------------------------------------------ stage-level native path
+# All half blocks of a stage (the transformer blocks between two spatial reductions) as ONE autograd node: one workspace allocation,
+# one descriptor array and one C-ABI call per direction (vsx_stage_fwd / vsx_stage_bwd) instead of one of each per half block.
+USE_NATIVE_STAGE = True
+
+
+def stage_native_ok(metas, params):
+    return (USE_NATIVE_STAGE and USE_NATIVE_HALF and _precision == 'bf16' and ops.PROFILE is None and len(metas) > 0
+            and all(p is not None for p in params))
+
+
+def _half_sizes(meta, M, C):
+    attn = meta.kind == 'attn'
+    inner = 3 * meta.H * meta.D if attn else meta.F
+    a2 = meta.H * meta.D if attn else meta.F
+    return attn, inner, a2
+
+
+class StageFn(torch.autograd.Function):
+    """x -> half block 0 -> ... -> half block n-1 (each x_out = x + mask * drop_path(branch(LN(x))), nets/supernet_blocks.py:213-253)."""
+
+    @staticmethod
+    def forward(ctx, metas, x, *params):
+        require_cuda(x, 'Block')
+        if not x.is_contiguous():
+            x = x.contiguous()
+        n = len(metas)
+        B, N, C = x.shape
+        M = B * N
+        dev = x.device
+        outs = torch.empty((n, B, N, C), device=dev, dtype=torch.float32)
+        n16 = n32 = 0
+        sizes = []
+        for meta in metas:
+            attn, inner, a2 = _half_sizes(meta, M, C)
+            sizes.append((attn, inner, a2, n16, n32))
+            n16 += M * (C + inner + a2)
+            n32 += 2 * M + (B * meta.H * N if attn else 0)
+        ws16 = torch.empty(n16, device=dev, dtype=torch.bfloat16)
+        ws32 = torch.empty(n32, device=dev, dtype=torch.float32)
+        p16, p32, po, px = ws16.data_ptr(), ws32.data_ptr(), outs.data_ptr(), x.data_ptr()
+        ostride = 4 * M * C
+        descs = (_lib.HalfBlock * n)()
+        keep_alive = []
+        for i, meta in enumerate(metas):
+            attn, inner, a2, o16, o32 = sizes[i]
+            ln_w, ln_b, w1, b1, w2, b2 = params[6 * i:6 * i + 6]
+            wa, wb = weights.get(w1), weights.get(w2)
+            keep_alive.append((wa, wb))
+            rs = meta.row_scale
+            q16, q32 = p16 + 2 * o16, p32 + 4 * o32
+            descs[i] = _lib.HalfBlock(0 if attn else 1, B, N, C, meta.H, meta.D, meta.F, 1 if meta.pre_norm else 0, 1 if meta.residual else 0,
+                                      meta.eps, len(meta.segs), _C.cast(_segments_c(meta), _C.c_void_p),
+                                      px if i == 0 else po + (i - 1) * ostride, po + i * ostride, ln_w.data_ptr(), ln_b.data_ptr(), wa.data_ptr(), wb.data_ptr(),
+                                      None if b1 is None else b1.data_ptr(), None if b2 is None else b2.data_ptr(),
+                                      None if rs is None else rs.data_ptr(), meta.scale_off,
+                                      q16, q32, q32 + 4 * M, q16 + 2 * M * C, q16 + 2 * M * (C + inner), (q32 + 8 * M) if attn else None)
+        ops._ck(_lib.lib().vsx_stage_fwd(descs, n, ops._stream()))
+        ctx.metas, ctx.descs, ctx.sizes = metas, descs, sizes
+        ctx.keep = (outs, ws16, ws32, keep_alive)
+        ctx.save_for_backward(x, *params)
+        return outs[n - 1]
+
+    @staticmethod
+    def backward(ctx, g):
+        x, *params = ctx.saved_tensors
+        metas, fdescs, sizes = ctx.metas, ctx.descs, ctx.sizes
+        n = len(metas)
+        B, N, C = x.shape
+        M = B * N
+        dev = x.device
+        g = g if g.is_contiguous() else g.contiguous()
+        gbuf = torch.empty((2, B, N, C), device=dev, dtype=torch.float32)       # g_in of half block i = g_out of half block i - 1: ping-pong
+        sc_elems = max(M * (2 * C + inner + (a2 if attn else 0)) for attn, inner, a2, _, _ in sizes)
+        sc = torch.empty(2 * sc_elems, device=dev, dtype=torch.bfloat16)        # [df | dxn | d_act1 | d_act2] of half block i in buffer i & 1
+        grads = zeros_like_many(*params)
+        pg, pgb, psc = g.data_ptr(), gbuf.data_ptr(), sc.data_ptr()
+        gstride = 4 * M * C
+        descs = (_lib.HalfBlockGrad * n)()
+        fuse = [False] * n          # fuse[i]: half block i's df is written by the LayerNorm backward of half block i + 1
+        if FUSE_CAST:
+            for i in range(n - 1):
+                fuse[i] = _fusable(metas[i]) and _fusable(metas[i + 1])
+        for i, meta in enumerate(metas):
+            attn, inner, a2, _, _ = sizes[i]
+            ps = psc + 2 * sc_elems * (i & 1)
+            g_out = pg if i == n - 1 else pgb + gstride * ((i + 1) & 1)
+            g_in = pgb + gstride * (i & 1)
+            nxt = (None, None, 0, 0, None)
+            if i > 0 and fuse[i - 1]:
+                pm = metas[i - 1]
+                rs = pm.row_scale
+                nxt = (psc + 2 * sc_elems * ((i - 1) & 1), None if rs is None else rs.data_ptr(), pm.scale_off if rs is not None else 0, pm.segs[0].ck,
+                       grads[6 * (i - 1) + 5].data_ptr())
+            gi = grads[6 * i:6 * i + 6]
+            descs[i] = _lib.HalfBlockGrad(fdescs[i], g_out, g_in, ps, ps + 2 * M * C, ps + 4 * M * C, (ps + 2 * M * (2 * C + inner)) if attn else None,
+                                          *[t.data_ptr() for t in gi], 1 if fuse[i] else 0, *nxt)
+        ops._ck(_lib.lib().vsx_stage_bwd(descs, n, ops._stream()))
+        ctx.keep = None
+        return (None, gbuf[0]) + tuple(grads)

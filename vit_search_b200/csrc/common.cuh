@@ -48,6 +48,24 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 }
 #endif
 
+// ---------------------------------------------------------------- per-segment extents inside ONE launch (multi-architecture batches)
+// A batch that carries several sub-architectures is a sequence of row ranges ("segments": consecutive samples that share one set of
+// extents).  Row kernels take the whole batch in one launch and look their row's extents up here instead of being launched once per
+// segment.  Same layout as vsx_row_segments in include/vsx.h.  count == 0: uniform extents (the scalar kernel arguments apply).
+struct RowSegs {
+  int count;
+  int row_end[VSX_MAX_SEGMENTS];   // exclusive end row of segment i (relative to the first row of the launch)
+  int keep[VSX_MAX_SEGMENTS];      // kept channels of segment i; 0: its rows are skipped
+  int keep2[VSX_MAX_SEGMENTS];     // second extent where the operation has one
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ int seg_of_row(const RowSegs& s, long r) {
+  int i = 0;
+  while (i < s.count - 1 && r >= s.row_end[i]) ++i;
+  return i;
+}
+#endif
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long ceil_div_l(long a, long b) { return (a + b - 1) / b; }
 int num_sms();

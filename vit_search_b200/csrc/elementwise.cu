@@ -1,5 +1,7 @@
 // Small HBM-bound helper kernels around the GEMMs: operand casts / bf16 hi-lo splits, the masked + drop-path-scaled
 // gradient cast that opens each branch's backward, and bias-gradient column sums.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace vsx {
@@ -85,10 +87,10 @@ __global__ void __launch_bounds__(SMC_WARPS * 32) scale_mask_cast_kernel(const f
 template <int NV, typename T>
 __global__ void __launch_bounds__(SMC_WARPS * 32) scale_mask_cast_bulk_kernel(const float* __restrict__ g, long ldg, const float* __restrict__ row_scale,
                                                                              int rps, int n_keep, T* __restrict__ out, long ldo, int rows, int cols,
-                                                                             float* __restrict__ colsum) {
+                                                                             float* __restrict__ colsum, const RowSegs segs) {
   pdl_launch_dependents();
   pdl_wait();
-  extern __shared__ __align__(128) uint8_t smc_smem[];
+  extern __shared__ __align__(128) uint8_t smc_smem[];      // n_keep = the largest kept width of the launch when there are segments
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t gb = (uint32_t)n_keep * 4;
   const uint32_t slot = (gb + 127u) & ~127u;
@@ -104,8 +106,9 @@ __global__ void __launch_bounds__(SMC_WARPS * 32) scale_mask_cast_bulk_kernel(co
   const long stride = (long)gridDim.x * SMC_WARPS;
   auto issue = [&](long r, int sl) {
     const uint32_t bar = sl ? bar1 : bar0;
-    mbar_expect_tx(bar, gb);
-    bulk_g2s(smem_u32(my + (size_t)sl * slot), g + r * ldg, gb, bar);
+    const uint32_t gr = (uint32_t)(segs.count ? segs.keep[seg_of_row(segs, r)] : n_keep) * 4;
+    mbar_expect_tx(bar, gr);             // 0 bytes for a skipped row: the phase completes at once
+    if (gr) bulk_g2s(smem_u32(my + (size_t)sl * slot), g + r * ldg, gr, bar);
   };
   float4 acc[NV];
 #pragma unroll
@@ -117,14 +120,19 @@ __global__ void __launch_bounds__(SMC_WARPS * 32) scale_mask_cast_bulk_kernel(co
     const int sl = it & 1;
     if (r + stride < rows && lane == 0) issue(r + stride, sl ^ 1);
     const float s = row_scale != nullptr ? __ldg(row_scale + r / rps) : 1.0f;
+    const int keep_r = segs.count ? segs.keep[seg_of_row(segs, r)] : n_keep;
     mbar_wait(sl ? bar1 : bar0, (uint32_t)(it >> 1) & 1u);
+    if (keep_r == 0) {
+      __syncwarp();
+      continue;
+    }
     const float* gs = reinterpret_cast<const float*>(my + (size_t)sl * slot);
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
       if (c < cols) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < n_keep) {
+        if (c < keep_r) {
           v = ld4(gs + c);
           v.x *= s, v.y *= s, v.z *= s, v.w *= s;
         }
@@ -204,11 +212,16 @@ extern "C" int vsx_split_bf16(const float* src, long lds, void* hi, void* lo, vo
 
 template <typename T>
 static int smc_dispatch(const float* g, long ldg, const float* row_scale, int rps, int n_keep, void* out, long ldo, int rows, int cols,
-                        float* colsum, cudaStream_t st) {
+                        float* colsum, cudaStream_t st, const RowSegs* segs = nullptr) {
   const int nv = ceil_div(cols, 128);
+  bool seg_ok = true;
+  if (segs != nullptr) {        // several extents in one launch: bulk variant only; returns 1 ("not handled") when it does not apply
+    n_keep = 0;
+    for (int i = 0; i < segs->count; ++i) seg_ok = seg_ok && segs->keep[i] % 4 == 0, n_keep = segs->keep[i] > n_keep ? segs->keep[i] : n_keep;
+  }
   const int need = ceil_div(rows, SMC_WARPS), cap = num_sms() * (colsum != nullptr ? 4 : 8);
   const int grid = need < cap ? need : cap;
-  if (n_keep > 0 && n_keep % 4 == 0 && ldg % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 && nv <= 10) {
+  if (seg_ok && n_keep > 0 && n_keep % 4 == 0 && ldg % 4 == 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0 && nv <= 10) {
     const size_t smem = (((size_t)n_keep * 4 + 127) & ~(size_t)127) * 2 * SMC_WARPS;
     const int cap4 = num_sms() * 4, gridb = need < cap4 ? need : cap4;
 #define VSX_SMCB(NV)                                                                                                                       \
@@ -218,7 +231,7 @@ static int smc_dispatch(const float* g, long ldg, const float* row_scale, int rp
       cudaFuncSetAttribute(scale_mask_cast_bulk_kernel<NV, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                    \
       cfg = true;                                                                                                                          \
     }                                                                                                                                      \
-    launch_pdl(scale_mask_cast_bulk_kernel<NV, T>, dim3(gridb), dim3(SMC_WARPS * 32), smem, st, g, ldg, row_scale, rps, n_keep, (T*)out, ldo, rows, cols, colsum); \
+    launch_pdl(scale_mask_cast_bulk_kernel<NV, T>, dim3(gridb), dim3(SMC_WARPS * 32), smem, st, g, ldg, row_scale, rps, n_keep, (T*)out, ldo, rows, cols, colsum, segs ? *segs : RowSegs{}); \
     return check_launch("vsx_scale_mask_cast");                                                                                            \
   }
     switch (nv) {
@@ -227,6 +240,7 @@ static int smc_dispatch(const float* g, long ldg, const float* row_scale, int rp
     }
 #undef VSX_SMCB
   }
+  if (segs != nullptr) return 1;
 #define VSX_SMC(NV)                                                                                                                 \
   case NV:                                                                                                                          \
     launch_pdl(scale_mask_cast_kernel<NV, T>, dim3(grid), dim3(SMC_WARPS * 32), 0, st, g, ldg, row_scale, rps, n_keep, (T*)out, ldo, rows, cols, colsum); \
@@ -268,4 +282,30 @@ extern "C" int vsx_colsum(const void* x, int dtype, long ldx, int rows, int cols
     return VSX_ERR_ARG;
   }
   return check_launch("vsx_colsum");
+}
+
+// Several extents in one launch (multi-architecture batches): rows of segment i keep segs->keep[i] channels; keep 0 = rows untouched.
+extern "C" int vsx_scale_mask_cast_segs(const float* g, long ldg, const float* row_scale, int rows_per_sample, void* out, int dtype, long ldo,
+                                        int rows, int cols, const vsx_row_segments* segs, float* colsum, void* stream) {
+  VSX_REQUIRE(cols % 4 == 0 && ldg % 4 == 0 && ldo % 4 == 0, "vsx_scale_mask_cast_segs: cols and pitches must be multiples of 4");
+  VSX_REQUIRE(segs != nullptr && segs->count >= 1 && segs->count <= VSX_MAX_SEGMENTS && segs->row_end[segs->count - 1] == rows,
+              "vsx_scale_mask_cast_segs: 1..%d segments covering the %d rows", VSX_MAX_SEGMENTS, rows);
+  VSX_REQUIRE(dtype == VSX_BF16 || dtype == VSX_F32, "vsx_scale_mask_cast_segs: bad dtype %d", dtype);
+  if (rows <= 0 || cols <= 0) return VSX_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int rps = rows_per_sample > 0 ? rows_per_sample : 1;
+  RowSegs sg;
+  static_assert(sizeof(RowSegs) == sizeof(vsx_row_segments), "RowSegs mirrors vsx_row_segments");
+  memcpy(&sg, segs, sizeof(sg));
+  int rc = dtype == VSX_BF16 ? smc_dispatch<bf16>(g, ldg, row_scale, rps, 0, out, ldo, rows, cols, colsum, st, &sg)
+                             : smc_dispatch<float>(g, ldg, row_scale, rps, 0, out, ldo, rows, cols, colsum, st, &sg);
+  if (rc != 1) return rc;
+  const size_t es = dtype == VSX_BF16 ? 2 : 4;
+  for (int i = 0, r0 = 0; i < segs->count; r0 = segs->row_end[i], ++i) {
+    if (segs->keep[i] == 0 || segs->row_end[i] == r0) continue;
+    rc = vsx_scale_mask_cast(g + (long)r0 * ldg, ldg, row_scale != nullptr ? row_scale + r0 / rps : nullptr, rps, segs->keep[i],
+                             static_cast<uint8_t*>(out) + (size_t)r0 * ldo * es, dtype, ldo, segs->row_end[i] - r0, cols, colsum, stream);
+    if (rc) return rc;
+  }
+  return VSX_OK;
 }

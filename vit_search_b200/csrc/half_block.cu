@@ -63,6 +63,23 @@ int passthrough(const float* src, float* dst, long elems, bool copy, void* strea
   return VSX_OK;
 }
 
+// Row-segment table of a half block for the single-launch row kernels: `which` selects the extent (0 embed, 2 out), dropped segments get 0.
+// Returns false when the batch has too many segments for one table (the callers then launch per segment).
+bool row_segments(const vsx_half_block* h, int which, vsx_row_segments* t) {
+  if (h->num_segments < 2 || h->num_segments > VSX_MAX_SEGMENTS) return false;
+  memset(t, 0, sizeof(*t));
+  t->count = h->num_segments;
+  int active = 0;
+  for (int i = 0; i < h->num_segments; ++i) {
+    const vsx_segment& s = h->segments[i];
+    t->row_end[i] = s.b1 * h->tokens;
+    const int ext = which == 0 ? s.embed_keep : (h->residual ? s.out_keep : h->width);
+    t->keep[i] = (s.active && s.b1 > s.b0) ? ext : 0;
+    active += t->keep[i] > 0;
+  }
+  return active >= 2 && h->segments[0].b0 == 0 && h->segments[h->num_segments - 1].b1 == h->batch;
+}
+
 int check_desc(const vsx_half_block* h, const char* what) {
   VSX_REQUIRE(h != nullptr && (h->kind == VSX_HALF_ATTN || h->kind == VSX_HALF_MLP), "%s: bad descriptor", what);
   VSX_REQUIRE(h->batch > 0 && h->tokens > 0 && h->width > 0 && h->width % 8 == 0, "%s: bad shape batch=%d tokens=%d width=%d", what, h->batch, h->tokens, h->width);
@@ -103,7 +120,17 @@ extern "C" int vsx_half_block_fwd(const vsx_half_block* h, void* stream) {
   HB_CHECK(check_desc(h, "vsx_half_block_fwd"));
   const int N = h->tokens, C = h->width, H = h->heads, D = h->head_dim, HD = H * D, F = h->hidden;
   const float scale = h->kind == VSX_HALF_ATTN ? 1.0f / sqrtf((float)D) : 0.f;
-  // phase 1: dropped layers pass through; LayerNorm (or the bare input mask) of every active segment
+  // phase 1: dropped layers pass through; LayerNorm (or the bare input mask) of every active segment -- ONE launch over the whole batch
+  // with per-row extents when the batch carries several sub-architectures
+  vsx_row_segments tab;
+  const bool one_launch = row_segments(h, 0, &tab);
+  if (one_launch) {
+    const int rows_all = h->batch * N;
+    if (h->pre_norm)
+      HB_CHECK(vsx_masked_ln_fwd_segs(h->x, C, h->ln_w, h->ln_b, h->xn, VSX_BF16, C, h->mean, h->rstd, rows_all, C, &tab, h->eps, stream));
+    else
+      HB_CHECK(vsx_scale_mask_cast_segs(h->x, C, nullptr, 1, h->xn, VSX_BF16, C, rows_all, C, &tab, nullptr, stream));
+  }
   for (int si = 0; si < h->num_segments; ++si) {
     const vsx_segment& s = h->segments[si];
     const long r0 = (long)s.b0 * N;
@@ -113,7 +140,7 @@ extern "C" int vsx_half_block_fwd(const vsx_half_block* h, void* stream) {
       HB_CHECK(passthrough(h->x + r0 * C, h->out + r0 * C, (long)rows * C, h->residual != 0, stream));
       continue;
     }
-    HB_CHECK(pre_norm_or_cast(h, s, r0, rows, stream));
+    if (!one_launch) HB_CHECK(pre_norm_or_cast(h, s, r0, rows, stream));
   }
   auto for_active = [&](auto&& fn) -> int {
     for (int si = 0; si < h->num_segments; ++si) {
@@ -188,6 +215,12 @@ extern "C" int vsx_half_block_bwd(const vsx_half_block_grad* b, void* stream) {
               "vsx_half_block_bwd: df_ready / next_df need a single active segment covering the batch, pre_norm and residual");
   // phase 1: dropped layers pass the gradient through; gradient of the branch output of every active segment: drop-path scale,
   // output mask, cast -- its column sums are the bias gradient of proj / fc2
+  vsx_row_segments tab_out, tab_in;
+  const bool one_cast = !b->df_ready && row_segments(h, 2, &tab_out);
+  const bool one_ln = h->pre_norm && row_segments(h, 0, &tab_in);
+  if (one_cast)
+    HB_CHECK(vsx_scale_mask_cast_segs(b->g_out, C, (h->residual && h->row_scale != nullptr) ? h->row_scale + h->scale_off : nullptr, N, b->df, VSX_BF16, C,
+                                      h->batch * N, C, &tab_out, b->d_b2, stream));
   for (int si = 0; si < h->num_segments; ++si) {
     const vsx_segment& s = h->segments[si];
     const long r0 = (long)s.b0 * N;
@@ -198,7 +231,7 @@ extern "C" int vsx_half_block_bwd(const vsx_half_block_grad* b, void* stream) {
       continue;
     }
     const int ck = h->residual ? s.out_keep : C;
-    if (b->df_ready) continue;               // written by the LayerNorm backward of the call that produced g_out
+    if (b->df_ready || one_cast) continue;   // written by the LayerNorm backward of the call that produced g_out / by the launch above
     HB_CHECK(vsx_scale_mask_cast(b->g_out + r0 * C, C, (h->residual && h->row_scale != nullptr) ? h->row_scale + h->scale_off + s.b0 : nullptr, N, ck,
                                  B16(b->df) + r0 * C, VSX_BF16, C, rows, C, b->d_b2, stream));
   }
@@ -286,7 +319,10 @@ extern "C" int vsx_half_block_bwd(const vsx_half_block_grad* b, void* stream) {
     HB_CHECK(for_active([&](const SegView& v) -> int { return dxn_gemm(v, B16(b->d_act1) + v.r0 * F, F, v.s->inner_keep, -1); }));
     HB_CHECK(batch.flush());
   }
-  if (h->pre_norm) {
+  if (one_ln) {
+    HB_CHECK(vsx_masked_ln_bwd_segs(b->dxn, VSX_BF16, C, h->x, C, h->mean, h->rstd, h->ln_w, h->residual ? b->g_out : nullptr, b->g_in, C, b->d_ln_w, b->d_ln_b,
+                                    h->batch * N, C, &tab_in, nullptr, C, nullptr, 0, nullptr, stream));
+  } else if (h->pre_norm) {
     HB_CHECK(for_active([&](const SegView& v) -> int {
       if (b->next_df != nullptr)
         return vsx_masked_ln_bwd_cast(B16(b->dxn) + v.r0 * C, VSX_BF16, C, h->x + v.r0 * C, C, h->mean + v.r0, h->rstd + v.r0, h->ln_w,
@@ -299,5 +335,22 @@ extern "C" int vsx_half_block_bwd(const vsx_half_block_grad* b, void* stream) {
                                stream);
     }));
   }
+  return VSX_OK;
+}
+
+// A run of consecutive half blocks (all transformer blocks of a stage) in ONE C-ABI call per direction: the launching thread pays one
+// foreign call, one workspace allocation and one autograd node per stage instead of one per half block (the Python side of a train step
+// was 12.9 ms against 14.0 ms of GPU work; tools/host_vs_gpu.py).  Descriptors are in forward order for both directions; the
+// backward walks them from the last to the first, and the LayerNorm backward of half block i writes the bf16 gradient copy half block
+// i - 1 starts from (next_df / df_ready links prepared by the caller).
+extern "C" int vsx_stage_fwd(const vsx_half_block* halves, int count, void* stream) {
+  VSX_REQUIRE(halves != nullptr && count >= 1, "vsx_stage_fwd: need at least one half block");
+  for (int i = 0; i < count; ++i) HB_CHECK(vsx_half_block_fwd(&halves[i], stream));
+  return VSX_OK;
+}
+
+extern "C" int vsx_stage_bwd(const vsx_half_block_grad* halves, int count, void* stream) {
+  VSX_REQUIRE(halves != nullptr && count >= 1, "vsx_stage_bwd: need at least one half block");
+  for (int i = count - 1; i >= 0; --i) HB_CHECK(vsx_half_block_bwd(&halves[i], stream));
   return VSX_OK;
 }

@@ -8,6 +8,8 @@
 //   backward: read dy (2 B) + x (4 B) + g_in (4 B), write g_out (4 B); dgamma/dbeta via per-CTA partials + atomics
 #include <algorithm>
 
+#include <string.h>
+
 #include "common.cuh"
 
 namespace vsx {
@@ -197,11 +199,12 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 2 ? 4 : 1) ln_bwd_bulk_ke
                                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
                                                                      const float* __restrict__ gamma, const float* __restrict__ g_in,
                                                                      float* __restrict__ g_out, long ldg, float* __restrict__ dgamma,
-                                                                     float* __restrict__ dbeta, int rows, int C, int keep, const LnCast cast) {
+                                                                     float* __restrict__ dbeta, int rows, int C, int keep, const LnCast cast, const RowSegs segs) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // `keep` is the LARGEST kept width of the launch (slot size, width of the column reductions); with segments every row uses its own
   const uint32_t xb = (uint32_t)keep * 4, gb = g_in != nullptr ? (uint32_t)C * 4 : 0u, db = (uint32_t)keep * (uint32_t)sizeof(T);
   const uint32_t slot = ((xb + gb + db) + 127u) & ~127u;
   uint8_t* my = ln_smem + (size_t)warp * 2 * slot;
@@ -216,12 +219,17 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 2 ? 4 : 1) ln_bwd_bulk_ke
   const long stride = (long)gridDim.x * LN_WARPS;
   auto issue = [&](long r, int sl) {     // lane 0 only
     const uint32_t dst = smem_u32(my + (size_t)sl * slot), bar = sl ? bar1 : bar0;
-    mbar_expect_tx(bar, xb + gb + db);
-    bulk_g2s(dst, x + r * ldx, xb, bar);
+    const int kr = segs.count ? segs.keep[seg_of_row(segs, r)] : keep;
+    if (kr == 0) {                       // skipped row (dropped layer): complete the phase so that the slot parities stay in step
+      mbar_expect_tx(bar, 0);
+      return;
+    }
+    const uint32_t xr = (uint32_t)kr * 4, dr = (uint32_t)kr * (uint32_t)sizeof(T);
+    mbar_expect_tx(bar, xr + gb + dr);
+    bulk_g2s(dst, x + r * ldx, xr, bar);
     if (gb) bulk_g2s(dst + xb, g_in + r * ldg, gb, bar);
-    bulk_g2s(dst + xb + gb, dy + r * lddy, db, bar);
+    bulk_g2s(dst + xb + gb, dy + r * lddy, dr, bar);
   };
-  const float inv_keep = 1.0f / (float)keep;
   float4 ag[NV], ab[NV], ac[CAST ? NV : 1];
 #pragma unroll
   for (int i = 0; i < NV; ++i) ag[i] = make_float4(0.f, 0.f, 0.f, 0.f), ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -235,7 +243,17 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 2 ? 4 : 1) ln_bwd_bulk_ke
     if (r + stride < rows && lane == 0) issue(r + stride, sl ^ 1);      // the other slot was fully consumed one iteration ago
     float cs = 1.0f;
     if (CAST && cast.scale != nullptr) cs = __ldg(cast.scale + r / cast.rps);
+    int keep_r = keep, cast_keep = cast.keep;
+    if (segs.count) {
+      const int si = seg_of_row(segs, r);
+      keep_r = segs.keep[si], cast_keep = segs.keep2[si];
+    }
     mbar_wait(sl ? bar1 : bar0, (uint32_t)(it >> 1) & 1u);
+    if (keep_r == 0) {
+      __syncwarp();
+      continue;
+    }
+    const float inv_keep = 1.0f / (float)keep_r;
     const float* xs = reinterpret_cast<const float*>(my + (size_t)sl * slot);
     const float* gs = reinterpret_cast<const float*>(my + (size_t)sl * slot + xb);
     const T* ds = reinterpret_cast<const T*>(my + (size_t)sl * slot + xb + gb);
@@ -244,7 +262,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 2 ? 4 : 1) ln_bwd_bulk_ke
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
-      if (c < keep) {
+      if (c < keep_r) {
         float4 d = ld4(ds + c);
         const float4 xv = ld4(xs + c), gm = ld4(gamma + c);
         const float4 z = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
@@ -263,7 +281,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 2 ? 4 : 1) ln_bwd_bulk_ke
       const int c = (i * 32 + lane) * 4;
       if (c < C) {
         float4 o = gb ? ld4(gs + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < keep) {
+        if (c < keep_r) {
           const float4 d0 = ld4(ds + c), xv = ld4(xs + c), gm = ld4(gamma + c);
           o.x += (d0.x * gm.x - s1 - (xv.x - mu) * rs * s2) * rs;
           o.y += (d0.y * gm.y - s1 - (xv.y - mu) * rs * s2) * rs;
@@ -273,7 +291,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32, NV <= 2 ? 4 : 1) ln_bwd_bulk_ke
         st4(go + c, o);
         if (CAST) {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (c < cast.keep) v = make_float4(o.x * cs, o.y * cs, o.z * cs, o.w * cs);
+          if (c < cast_keep) v = make_float4(o.x * cs, o.y * cs, o.z * cs, o.w * cs);
           st4(static_cast<T*>(cast.out) + r * cast.ld + c, v);
           ac[i].x += v.x, ac[i].y += v.y, ac[i].z += v.z, ac[i].w += v.w;
         }
@@ -307,12 +325,12 @@ template <int NV, typename T>
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_bulk_kernel(const float* __restrict__ x, long ldx, const float* __restrict__ gamma,
                                                                      const float* __restrict__ beta, T* __restrict__ y, long ldy,
                                                                      float* __restrict__ mean, float* __restrict__ rstd, int rows, int C,
-                                                                     int keep, float eps) {
+                                                                     int keep, float eps, const RowSegs segs) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t xb = (uint32_t)keep * 4;
+  const uint32_t xb = (uint32_t)keep * 4;       // largest kept width of the launch
   const uint32_t slot = (xb + 127u) & ~127u;
   uint8_t* my = ln_smem + (size_t)warp * 2 * slot;
   __shared__ __align__(8) unsigned long long bars[LN_WARPS][2];
@@ -326,24 +344,30 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_bulk_kernel(const float*
   const long stride = (long)gridDim.x * LN_WARPS;
   auto issue = [&](long r, int sl) {
     const uint32_t bar = sl ? bar1 : bar0;
-    mbar_expect_tx(bar, xb);
-    bulk_g2s(smem_u32(my + (size_t)sl * slot), x + r * ldx, xb, bar);
+    const uint32_t xr = (uint32_t)(segs.count ? segs.keep[seg_of_row(segs, r)] : keep) * 4;
+    mbar_expect_tx(bar, xr);             // 0 bytes for a skipped row: the phase completes at once, slot parities stay in step
+    if (xr) bulk_g2s(smem_u32(my + (size_t)sl * slot), x + r * ldx, xr, bar);
   };
-  const float inv_keep = 1.0f / (float)keep;
   long r = (long)blockIdx.x * LN_WARPS + warp;
   if (r < rows && lane == 0) issue(r, 0);
   int it = 0;
   for (; r < rows; r += stride, ++it) {
     const int sl = it & 1;
     if (r + stride < rows && lane == 0) issue(r + stride, sl ^ 1);
+    const int keep_r = segs.count ? segs.keep[seg_of_row(segs, r)] : keep;
     mbar_wait(sl ? bar1 : bar0, (uint32_t)(it >> 1) & 1u);
+    if (keep_r == 0) {
+      __syncwarp();
+      continue;
+    }
+    const float inv_keep = 1.0f / (float)keep_r;
     const float* xs = reinterpret_cast<const float*>(my + (size_t)sl * slot);
     float4 v[NV];
     float s = 0.f, ss = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (i * 32 + lane) * 4;
-      v[i] = c < keep ? ld4(xs + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[i] = c < keep_r ? ld4(xs + c) : make_float4(0.f, 0.f, 0.f, 0.f);
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
       ss += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
     }
@@ -362,7 +386,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_bulk_kernel(const float*
       const int c = (i * 32 + lane) * 4;
       if (c < C) {
         float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c < keep) {
+        if (c < keep_r) {
           const float4 gm = ld4(gamma + c), bt = ld4(beta + c);
           o.x = gm.x * ((v[i].x - mu) * rs) + bt.x;
           o.y = gm.y * ((v[i].y - mu) * rs) + bt.y;
@@ -384,10 +408,17 @@ int ln_grid(int rows, int per_sm) {
 
 template <typename T>
 int ln_fwd_dispatch(const float* x, long ldx, const float* gamma, const float* beta, void* y, void* y2, long ldy, float* mean,
-                    float* rstd, int rows, int C, int keep, float eps, int rps, int split, cudaStream_t st) {
+                    float* rstd, int rows, int C, int keep, float eps, int rps, int split, cudaStream_t st, const RowSegs* segs = nullptr) {
   const int nv = ceil_div(C, 128);
+  // segments (several extents in one launch) exist in the bulk variant only: returns 1 ("not handled") when it does not apply
+  bool seg_ok = true;
+  if (segs != nullptr) {
+    keep = 0;
+    for (int i = 0; i < segs->count; ++i) seg_ok = seg_ok && segs->keep[i] % 4 == 0, keep = segs->keep[i] > keep ? segs->keep[i] : keep;
+    if (keep == 0) return VSX_OK;
+  }
   // bulk-copy prefetch variant: kept prefix in whole float4s (the masked tail of a row is then exactly c >= keep), no row remap
-  if (rps <= 0 && keep % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+  if (seg_ok && rps <= 0 && keep % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
     const size_t slot = ((size_t)keep * 4 + 127) & ~(size_t)127;
     const size_t smem = slot * 2 * LN_WARPS;
     const int gridb = ln_grid(rows, 4);
@@ -398,7 +429,7 @@ int ln_fwd_dispatch(const float* x, long ldx, const float* gamma, const float* b
       cudaFuncSetAttribute(ln_fwd_bulk_kernel<NV, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);                   \
       cfg = true;                                                                                                                \
     }                                                                                                                            \
-    launch_pdl(ln_fwd_bulk_kernel<NV, T>, dim3(gridb), dim3(LN_WARPS * 32), smem, st, x, ldx, gamma, beta, (T*)y, ldy, mean, rstd, rows, C, keep, eps); \
+    launch_pdl(ln_fwd_bulk_kernel<NV, T>, dim3(gridb), dim3(LN_WARPS * 32), smem, st, x, ldx, gamma, beta, (T*)y, ldy, mean, rstd, rows, C, keep, eps, segs ? *segs : RowSegs{}); \
     return check_launch("vsx_masked_ln_fwd");                                                                                    \
   }
     switch (nv) {
@@ -407,6 +438,7 @@ int ln_fwd_dispatch(const float* x, long ldx, const float* gamma, const float* b
     }
 #undef VSX_LN_FB
   }
+  if (segs != nullptr) return 1;
   const int grid = ln_grid(rows, 8);
 #define VSX_LN_F(NV)                                                                                                        \
   case NV:                                                                                                                  \
@@ -426,11 +458,18 @@ int ln_fwd_dispatch(const float* x, long ldx, const float* gamma, const float* b
 template <typename T>
 int ln_bwd_dispatch(const void* dy, const void* dy2, long lddy, const float* x, long ldx, const float* mean, const float* rstd,
                     const float* gamma, const float* g_in, float* g_out, long ldg, float* dgamma, float* dbeta, int rows, int C,
-                    int keep, int rps, int split, cudaStream_t st, const LnCast* cast = nullptr, bool* cast_done = nullptr) {
+                    int keep, int rps, int split, cudaStream_t st, const LnCast* cast = nullptr, bool* cast_done = nullptr,
+                    const RowSegs* segs = nullptr) {
   const int nv = ceil_div(C, 128);
+  bool seg_ok = true;
+  if (segs != nullptr) {        // several extents in one launch: bulk variant only; returns 1 ("not handled") when it does not apply
+    keep = 0;
+    for (int i = 0; i < segs->count; ++i) seg_ok = seg_ok && segs->keep[i] % 8 == 0, keep = segs->keep[i] > keep ? segs->keep[i] : keep;
+    if (keep == 0) return VSX_OK;
+  }
   // bulk-copy prefetch variant: whole kept prefix in 16-byte units, no final-norm row remap, 16-byte aligned rows
   const size_t esz = sizeof(T);
-  const bool bulk = rps <= 0 && keep % 8 == 0 && C % 4 == 0 && lddy % 8 == 0 && ldx % 4 == 0 && ldg % 4 == 0 &&
+  const bool bulk = seg_ok && rps <= 0 && keep % 8 == 0 && C % 4 == 0 && lddy % 8 == 0 && ldx % 4 == 0 && ldg % 4 == 0 &&
                     ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g_in)) & 15) == 0;
   if (bulk && (((size_t)keep * 4 + (g_in != nullptr ? (size_t)C * 4 : 0) + (size_t)keep * esz + 127) & ~(size_t)127) * 2 * LN_WARPS + 4096 * (size_t)nv + 512 <= 227 * 1024) {
     const size_t slot = (((size_t)keep * 4 + (g_in != nullptr ? (size_t)C * 4 : 0) + (size_t)keep * esz) + 127) & ~(size_t)127;
@@ -451,12 +490,12 @@ int ln_bwd_dispatch(const void* dy, const void* dy2, long lddy, const float* x, 
         cfg2 = true;                                                                                                                \
       }                                                                                                                             \
       launch_pdl(ln_bwd_bulk_kernel<NV, T, true>, dim3(gridb), dim3(LN_WARPS * 32), smem, st, (const T*)dy, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, \
-                                                                           dgamma, dbeta, rows, C, keep, *cast);                    \
+                                                                           dgamma, dbeta, rows, C, keep, *cast, segs ? *segs : RowSegs{});                    \
       if (cast_done != nullptr) *cast_done = true;                                                                                  \
       return check_launch("vsx_masked_ln_bwd");                                                                                     \
     }                                                                                                                               \
     launch_pdl(ln_bwd_bulk_kernel<NV, T, false>, dim3(gridb), dim3(LN_WARPS * 32), smem, st, (const T*)dy, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, \
-                                                                          dgamma, dbeta, rows, C, keep, LnCast{});                  \
+                                                                          dgamma, dbeta, rows, C, keep, LnCast{}, segs ? *segs : RowSegs{});                  \
     return check_launch("vsx_masked_ln_bwd");                                                                                       \
   }
     switch (nv) {
@@ -465,6 +504,7 @@ int ln_bwd_dispatch(const void* dy, const void* dy2, long lddy, const float* x, 
     }
 #undef VSX_LN_BB
   }
+  if (segs != nullptr) return 1;
   const int grid = ln_grid(rows, 4);
 #define VSX_LN_B(NV)                                                                                                      \
   case NV:                                                                                                                \
@@ -544,4 +584,88 @@ extern "C" int vsx_masked_ln_bwd_cast(const void* dy, int dtype, long lddy, cons
     rc = ln_bwd_dispatch<float>(dy, nullptr, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, dgamma, dbeta, rows, C, keep, 0, 0, st, &cast, &done);
   if (rc != VSX_OK || done) return rc;
   return vsx_scale_mask_cast(g_out, ldg, cast_scale, rps, cast_keep, cast_out, dtype, ld_cast, rows, C, cast_colsum, stream);
+}
+
+// ---------------------------------------------------------------- several extents in one launch (multi-architecture batches)
+namespace {
+int check_segs(const vsx_row_segments* sg, int rows, int C, const char* what) {
+  VSX_REQUIRE(sg != nullptr && sg->count >= 1 && sg->count <= VSX_MAX_SEGMENTS, "%s: 1..%d segments", what, VSX_MAX_SEGMENTS);
+  int prev = 0;
+  for (int i = 0; i < sg->count; ++i) {
+    VSX_REQUIRE(sg->row_end[i] >= prev && sg->keep[i] >= 0 && sg->keep[i] <= C && sg->keep2[i] >= 0 && sg->keep2[i] <= C,
+                "%s: segment %d is not ordered or its extents exceed C=%d (row_end=%d keep=%d keep2=%d)", what, i, C, sg->row_end[i], sg->keep[i], sg->keep2[i]);
+    prev = sg->row_end[i];
+  }
+  VSX_REQUIRE(prev == rows, "%s: the segments must cover the %d rows of the launch (last row_end = %d)", what, rows, prev);
+  return VSX_OK;
+}
+inline RowSegs to_segs(const vsx_row_segments* sg) {
+  RowSegs r;
+  static_assert(sizeof(RowSegs) == sizeof(vsx_row_segments), "RowSegs mirrors vsx_row_segments");
+  memcpy(&r, sg, sizeof(r));
+  return r;
+}
+}  // namespace
+
+extern "C" int vsx_masked_ln_fwd_segs(const float* x, long ldx, const float* gamma, const float* beta, void* y, int dtype, long ldy, float* mean,
+                                      float* rstd, int rows, int C, const vsx_row_segments* segs, float eps, void* stream) {
+  int rc = check_segs(segs, rows, C, "vsx_masked_ln_fwd_segs");
+  if (rc) return rc;
+  VSX_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && ldy % 4 == 0, "vsx_masked_ln_fwd_segs: C and pitches must be multiples of 4");
+  VSX_REQUIRE(dtype == VSX_BF16 || dtype == VSX_F32, "vsx_masked_ln_fwd_segs: bad dtype %d", dtype);
+  if (rows == 0) return VSX_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const RowSegs sg = to_segs(segs);
+  rc = dtype == VSX_BF16 ? ln_fwd_dispatch<bf16>(x, ldx, gamma, beta, y, nullptr, ldy, mean, rstd, rows, C, 0, eps, 0, 0, st, &sg)
+                         : ln_fwd_dispatch<float>(x, ldx, gamma, beta, y, nullptr, ldy, mean, rstd, rows, C, 0, eps, 0, 0, st, &sg);
+  if (rc != 1) return rc;
+  const size_t es = dtype == VSX_BF16 ? 2 : 4;      // not handled in one launch: one launch per segment
+  for (int i = 0, r0 = 0; i < segs->count; r0 = segs->row_end[i], ++i) {
+    if (segs->keep[i] == 0 || segs->row_end[i] == r0) continue;
+    rc = vsx_masked_ln_fwd(x + (long)r0 * ldx, ldx, gamma, beta, static_cast<uint8_t*>(y) + (size_t)r0 * ldy * es, nullptr, dtype, ldy, mean + r0, rstd + r0,
+                           segs->row_end[i] - r0, C, segs->keep[i], eps, 0, 0, stream);
+    if (rc) return rc;
+  }
+  return VSX_OK;
+}
+
+// keep2 of a segment = the cast extent when cast_out != NULL (see vsx_masked_ln_bwd_cast)
+extern "C" int vsx_masked_ln_bwd_segs(const void* dy, int dtype, long lddy, const float* x, long ldx, const float* mean, const float* rstd,
+                                      const float* gamma, const float* g_in, float* g_out, long ldg, float* dgamma, float* dbeta, int rows, int C,
+                                      const vsx_row_segments* segs, void* cast_out, long ld_cast, const float* cast_scale, int cast_rows_per_sample,
+                                      float* cast_colsum, void* stream) {
+  int rc = check_segs(segs, rows, C, "vsx_masked_ln_bwd_segs");
+  if (rc) return rc;
+  VSX_REQUIRE(C % 4 == 0 && ldx % 4 == 0 && lddy % 4 == 0 && ldg % 4 == 0 && ld_cast % 4 == 0, "vsx_masked_ln_bwd_segs: C and pitches must be multiples of 4");
+  VSX_REQUIRE(dtype == VSX_BF16 || dtype == VSX_F32, "vsx_masked_ln_bwd_segs: bad dtype %d", dtype);
+  if (rows == 0) return VSX_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const RowSegs sg = to_segs(segs);
+  const int rps = cast_rows_per_sample > 0 ? cast_rows_per_sample : 1;
+  const LnCast cast{cast_out, ld_cast, cast_scale, rps, 0, cast_colsum};
+  bool done = false;
+  rc = dtype == VSX_BF16 ? ln_bwd_dispatch<bf16>(dy, nullptr, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, dgamma, dbeta, rows, C, 0, 0, 0, st,
+                                                 cast_out != nullptr ? &cast : nullptr, &done, &sg)
+                         : ln_bwd_dispatch<float>(dy, nullptr, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, dgamma, dbeta, rows, C, 0, 0, 0, st,
+                                                  cast_out != nullptr ? &cast : nullptr, &done, &sg);
+  if (rc < 0) return rc;
+  const size_t es = dtype == VSX_BF16 ? 2 : 4;
+  if (rc == 1) {                                      // not handled in one launch: one launch per segment
+    for (int i = 0, r0 = 0; i < segs->count; r0 = segs->row_end[i], ++i) {
+      if (segs->keep[i] == 0 || segs->row_end[i] == r0) continue;
+      rc = vsx_masked_ln_bwd(static_cast<const uint8_t*>(dy) + (size_t)r0 * lddy * es, nullptr, dtype, lddy, x + (long)r0 * ldx, ldx, mean + r0, rstd + r0, gamma,
+                             g_in != nullptr ? g_in + (long)r0 * ldg : nullptr, g_out + (long)r0 * ldg, ldg, dgamma, dbeta, segs->row_end[i] - r0, C,
+                             segs->keep[i], 0, 0, stream);
+      if (rc) return rc;
+    }
+  }
+  if (cast_out != nullptr && !done) {                 // the cast did not ride on the LayerNorm backward: separate pass per segment
+    for (int i = 0, r0 = 0; i < segs->count; r0 = segs->row_end[i], ++i) {
+      if (segs->keep[i] == 0 || segs->row_end[i] == r0) continue;
+      rc = vsx_scale_mask_cast(g_out + (long)r0 * ldg, ldg, cast_scale != nullptr ? cast_scale + r0 / rps : nullptr, rps, segs->keep2[i],
+                               static_cast<uint8_t*>(cast_out) + (size_t)r0 * ld_cast * es, dtype, ld_cast, segs->row_end[i] - r0, C, cast_colsum, stream);
+      if (rc) return rc;
+    }
+  }
+  return VSX_OK;
 }

@@ -127,7 +127,8 @@ class FusedAdamW:
             p.grad = None
 
     def _build_table(self):
-        """Pointer table of the fused kernel: one 64-byte record per tensor (struct vsx_adamw_tensor), packed with numpy."""
+        """Pointer table of the fused kernel: one 64-byte record per tensor (struct vsx_adamw_tensor), packed with numpy.  Everything
+        but the gradient pointers is static between `rewiring` calls; step() refreshes the gradient column only."""
         import numpy as np
         dev = self.entries[0][1].device
         n = len(self.entries)
@@ -136,10 +137,6 @@ class FusedAdamW:
         assert rec.itemsize == C.sizeof(_lib.AdamWTensor)
         chunks = []
         for i, (name, p, wd) in enumerate(self.entries):
-            if p.grad is None:
-                p.grad = torch.zeros_like(p)
-            elif not p.grad.is_contiguous():
-                p.grad = p.grad.contiguous()
             st = self.state.get(name)
             if st is None or st[0].shape != p.shape:
                 st = (torch.zeros_like(p), torch.zeros_like(p))
@@ -156,7 +153,7 @@ class FusedAdamW:
             ema_ptr, ema_decay = 0, 0.0
             if self.ema is not None:
                 ema_ptr, ema_decay = self.ema.param_of(name).data_ptr(), self.ema.decay
-            rec[i] = (p.data_ptr(), p.grad.data_ptr(), st[0].data_ptr(), st[1].data_ptr(), hi, 0, p.numel(), wd, ema_decay, ema_ptr)
+            rec[i] = (p.data_ptr(), 0, st[0].data_ptr(), st[1].data_ptr(), hi, 0, p.numel(), wd, ema_decay, ema_ptr)
             chunks.append(math.ceil(p.numel() / self.chunk))
         if getattr(self, '_chunks', None) != chunks:
             self._chunks = chunks
@@ -165,19 +162,33 @@ class FusedAdamW:
             self._ct = core.h2d(torch.from_numpy(ct), dev)
             self._ci = core.h2d(torch.from_numpy(ci), dev)
             self._nchunks = int(ct.shape[0])
-        # asynchronous upload through pinned memory: a blocking copy here would drain the GPU once per step
-        self._tab = core.h2d(torch.from_numpy(rec.view(np.uint8)), dev)
+        self._rec = rec
+        self._grad_ptrs = None
         self._tab_has_shadow = bool((rec['hi'] != 0).any())
 
     def step(self, grad_scale=None):
         """grad_scale: optional fp32 device scalar multiplied into every gradient inside the kernel (1 / world_size after a SUM
         all-reduce; a loss-scaler's inverse scale)."""
-        # gradient tensors are re-allocated by every backward, parameters by `rewiring`: re-derive the pointer table when
-        # any pointer changed (a host-side comparison of ~250 integers)
-        key = (core.get_precision(), id(self.ema)) + tuple((p.data_ptr(), 0 if p.grad is None else p.grad.data_ptr()) for _, p, _ in self.entries)
+        # parameters are re-allocated by `rewiring` (and moments by load_state_dict): re-derive the static part of the table when a
+        # parameter pointer changed (a host-side comparison of ~250 integers)
+        key = (core.get_precision(), id(self.ema)) + tuple(p.data_ptr() for _, p, _ in self.entries)
         if key != self._table_key:
             self._build_table()
-            self._table_key = (core.get_precision(), id(self.ema)) + tuple((p.data_ptr(), p.grad.data_ptr()) for _, p, _ in self.entries)
+            self._table_key = key
+        # gradient pointers: stable from step to step when they live in the persistent gradient pool (core.grad_pool); the table is
+        # uploaded again (asynchronously, through pinned memory: a blocking copy would drain the GPU once per step) only when one moved
+        ptrs = []
+        for _, p, _ in self.entries:
+            g = p.grad
+            if g is None:
+                g = p.grad = torch.zeros_like(p)
+            elif not g.is_contiguous():
+                g = p.grad = g.contiguous()
+            ptrs.append(g.data_ptr())
+        if ptrs != self._grad_ptrs:
+            self._rec['grad'] = ptrs
+            self._tab = core.h2d(torch.from_numpy(self._rec.view('uint8').copy()), self.entries[0][1].device)
+            self._grad_ptrs = ptrs
         self.step_count += 1
         lrs = set(float(g['lr']) for g in self.param_groups)
         if len(lrs) != 1:

@@ -26,6 +26,16 @@ def _cd(num_channels_to_keep, num_warmup_epochs, example_per_arch, single_arch):
                        example_per_arch=example_per_arch, single_arch=single_arch)
 
 
+def run_half_blocks(x, metas, params):
+    """x through a run of half blocks (`params`: six tensors per half block).  bf16 training path: ONE autograd node and one C-ABI call
+    per direction for the whole run (core.StageFn); parity / instrumented modes: one node per half block (core.HalfBlockFn)."""
+    if core.stage_native_ok(metas, params):
+        return core.StageFn.apply(metas, x, *params)
+    for i, meta in enumerate(metas):
+        x = core.HalfBlockFn.apply(meta, x, *params[6 * i:6 * i + 6])
+    return x
+
+
 class Mlp(nn.Module):
     def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.,
                  num_channels_to_keep=None, num_warmup_epochs=_NUM_WARMUP_EPOCHS_CHANNEL,
@@ -137,10 +147,8 @@ class Block(nn.Module):
         k['mlp'] = self.mlp.draw(batch, like)
         return k
 
-    def forward_keeps(self, x, embed_keep, layer_keep_in, keeps, dp_scale=None, dp_off=0):
-        """x [B,N,C] fp32.  keeps = self.draw(B).  dp_scale: optional fp32 device table whose rows dp_off and dp_off+1
-        hold the per-sample drop-path scales of the attention and MLP branches.  Returns (x, current_layer_keep)."""
-        B, N, C = x.shape
+    def half_metas(self, B, N, C, embed_keep, layer_keep_in, keeps, dp_scale=None, dp_off=0):
+        """Static descriptions of the two half blocks for one batch (host integers only).  -> (attention meta, MLP meta, current layer keep)."""
         cur = attn_ck = None
         if keeps.get('layer') is not None:                      # reference :220-223: layer_drop(f_x) masks the attention branch with
             attn_ck = list(keeps['layer'])                      # this block's OWN layer mask; the incoming one only joins `cur`
@@ -151,14 +159,24 @@ class Block(nn.Module):
         a, m = self.attn, self.mlp
         hd = a.num_heads * a.head_dim
         segs = core.make_segments(B, C, embed_keep, keeps.get('attn'), hd, attn_ck)
-        meta = core.HalfMeta('attn', segs, N, C, heads=a.num_heads, head_dim=a.head_dim, row_scale=dp_scale, scale_off=dp_off * B,
-                             eps=self.norm1.eps)
-        x = core.HalfBlockFn.apply(meta, x, self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias)
+        meta_a = core.HalfMeta('attn', segs, N, C, heads=a.num_heads, head_dim=a.head_dim, row_scale=dp_scale, scale_off=dp_off * B,
+                               eps=self.norm1.eps)
         segs = core.make_segments(B, C, embed_keep, keeps.get('mlp'), m.fc1.out_features, cur)
-        meta = core.HalfMeta('mlp', segs, N, C, hidden=m.fc1.out_features, row_scale=dp_scale, scale_off=(dp_off + 1) * B,
-                             eps=self.norm2.eps)
-        x = core.HalfBlockFn.apply(meta, x, self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias)
-        return x, cur
+        meta_m = core.HalfMeta('mlp', segs, N, C, hidden=m.fc1.out_features, row_scale=dp_scale, scale_off=(dp_off + 1) * B,
+                               eps=self.norm2.eps)
+        return meta_a, meta_m, cur
+
+    def half_params(self):
+        a, m = self.attn, self.mlp
+        return (self.norm1.weight, self.norm1.bias, a.qkv.weight, a.qkv.bias, a.proj.weight, a.proj.bias,
+                self.norm2.weight, self.norm2.bias, m.fc1.weight, m.fc1.bias, m.fc2.weight, m.fc2.bias)
+
+    def forward_keeps(self, x, embed_keep, layer_keep_in, keeps, dp_scale=None, dp_off=0):
+        """x [B,N,C] fp32.  keeps = self.draw(B).  dp_scale: optional fp32 device table whose rows dp_off and dp_off+1
+        hold the per-sample drop-path scales of the attention and MLP branches.  Returns (x, current_layer_keep)."""
+        B, N, C = x.shape
+        meta_a, meta_m, cur = self.half_metas(B, N, C, embed_keep, layer_keep_in, keeps, dp_scale, dp_off)
+        return run_half_blocks(x, [meta_a, meta_m], self.half_params()), cur
 
     def forward(self, x, embed_mask=None, layer_mask=None):
         """Reference signature (:209-255): masks are [B,1,C] bool prefix masks; returns (x, embed_mask, current_layer_mask)."""

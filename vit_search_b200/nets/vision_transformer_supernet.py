@@ -16,7 +16,7 @@ from .channel_drop import ChannelDrop
 from .masked_layer_norm import MaskedLayerNorm
 from .patch_conv import PatchEmbed
 from .registry import register_model
-from .supernet_blocks import Block
+from .supernet_blocks import Block, run_half_blocks
 from .vit_sr_supernet import BypassBlock, FlexibleDistillVisionTransformerSR, _EmbedAssembleFn, _cfg, _runs, trunc_normal_
 
 _BLOCK_EMBED_INDEX, _EMBED_CHANNEL = 0, 1
@@ -194,11 +194,17 @@ class FlexibleDistillVisionTransformer(nn.Module):
         embed_keep = keeps[0].get('embed')
         h = _EmbedAssembleFn.apply(h, self.tokens, self.pos_embed, embed_keep)
         layer_keep = None
+        run_metas, run_params = [], []          # all transformer blocks run as ONE autograd node (core.StageFn)
         for t, blk in enumerate(self.blocks):
             if isinstance(blk, Block):
-                h, layer_keep = blk.forward_keeps(h, embed_keep, layer_keep, keeps[t + 1], dp if rates[t] > 0 else None, 2 * t)
+                meta_a, meta_m, layer_keep = blk.half_metas(B, h.shape[1], h.shape[2], embed_keep, layer_keep, keeps[t + 1],
+                                                            dp if rates[t] > 0 else None, 2 * t)
+                run_metas.extend((meta_a, meta_m))
+                run_params.extend(blk.half_params())
             else:
                 layer_keep = None
+        if run_metas:
+            h = run_half_blocks(h, run_metas, tuple(run_params))
         heads = [self.cls_head.weight, self.cls_head.bias]
         if self.num_tokens == 2:
             heads += [self.dst_head.weight, self.dst_head.bias]

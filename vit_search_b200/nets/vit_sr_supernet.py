@@ -22,7 +22,7 @@ from .drop import draw_scale
 from .masked_layer_norm import MaskedLayerNorm
 from .patch_conv import PatchConvEmbed, PatchEmbed, to_2tuple
 from .registry import register_model
-from .supernet_blocks import Block
+from .supernet_blocks import Block, run_half_blocks
 from ._masks import keep_of, make_mask
 
 _BLOCK_EMBED_INDEX, _EMBED_CHANNEL, _EMBED_CONV_MID_CHANNELS = 0, 1, 2
@@ -553,21 +553,33 @@ class FlexibleDistillVisionTransformerSR(nn.Module):
             h.register_hook(core.trunk_grads_ready_hook)
         layer_keep = None
         j = t = 0
+        run_metas, run_params = [], []          # consecutive transformer blocks of a stage run as ONE autograd node (core.StageFn)
+
+        def flush(h):
+            if run_metas:
+                h = run_half_blocks(h, list(run_metas), tuple(run_params))
+                run_metas.clear()
+                run_params.clear()
+            return h
         for i, d in enumerate(self.network_def):
             if d[_BLOCK_TYPE] == _TYPE_IS_TRANS:
                 blk = self.blocks[j]
                 if isinstance(blk, Block) and not keeps[i].get('skip'):
                     use_dp = dp if rates[t] > 0 else None
-                    h, layer_keep = blk.forward_keeps(h, embed_keep, layer_keep, keeps[i], use_dp, 2 * t)
+                    meta_a, meta_m, layer_keep = blk.half_metas(B, h.shape[1], h.shape[2], embed_keep, layer_keep, keeps[i], use_dp, 2 * t)
+                    run_metas.extend((meta_a, meta_m))
+                    run_params.extend(blk.half_params())
                 else:
                     layer_keep = None
                 j += 1
                 t += 1
             elif d[_BLOCK_TYPE] == _TYPE_IS_SR:
+                h = flush(h)
                 new_keep = keeps[i].get('embed')
                 h = self.blocks[j].forward_keeps(h, embed_keep, new_keep)
                 embed_keep, layer_keep = new_keep, None
                 j += 1
+        h = flush(h)
         return h, embed_keep, perm
 
     def forward(self, x, patch_output_type=None):
