@@ -121,8 +121,9 @@ typedef struct vsx_gemm_desc {
 } vsx_gemm_desc;
 
 int vsx_gemm(const vsx_gemm_desc* d, void* stream);
-/* Up to 4 independent problems with the same epilogue and output dtype in ONE launch (the q / k / v row blocks of a head-masked
- * qkv projection; all weight gradients of a half block): their tiles form one work list for the persistent CTAs. */
+/* Up to 16 independent problems with the same epilogue and output dtype in ONE launch (the q / k / v row blocks of a head-masked
+ * qkv projection for every segment of a multi-architecture batch; all weight gradients of a half block): their tiles form one work
+ * list for the persistent CTAs.  More than 4 problems per launch: single-term (plain bf16) problems only. */
 int vsx_gemm_grouped(const vsx_gemm_desc* descs, int count, void* stream);
 /* CTA tile rows: 0 = heuristic (256-row tiles sharing one B box per k block when they fill the machine), 128 / 256 = forced (tests). */
 int vsx_gemm_force_tile_rows(int rows);

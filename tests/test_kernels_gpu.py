@@ -529,3 +529,57 @@ def test_conv1_direct(ops, B, H, W):
     ops.call('conv1_wgrad', x.cuda(), dy.cuda(), dw, 28, B, H, W)
     assert rel(dw[:, :27].reshape(24, 3, 3, 3).permute(0, 3, 1, 2), wref.grad) < 2e-3
     assert torch.all(dw[:, 27] == 0)
+
+
+def test_gemm_grouped_wide(ops, tile_rows):
+    """Up to 16 single-term problems in one launch: the q / k / v row blocks of FOUR segments with different kept heads / embedding widths
+    (a multi-architecture batch), and the GELU' data gradients of four segments adding their bias-gradient column sums into one vector."""
+    g = torch.Generator().manual_seed(11)
+    C, H, D = 160, 4, 64
+    HD = H * D
+    segs = [(300, 3, 144), (257, 4, 160), (514, 2, 128), (130, 1, 96)]          # rows, kept heads, kept embedding width
+    M = sum(r for r, _, _ in segs)
+    x = torch.randn(M, C, generator=g).to(torch.bfloat16)
+    w = (torch.randn(3 * HD, C, generator=g) * 0.1).to(torch.bfloat16)
+    b = torch.randn(3 * HD, generator=g)
+    qkv = torch.full((M, 3 * HD), float('nan'), device='cuda', dtype=torch.bfloat16)
+    xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+    probs, r0 = [], 0
+    for rows, hk, ek in segs:
+        for j in range(3):
+            probs.append(((xd, wd, C, C, rows, hk * D, ek, ops.EPI_STORE, qkv, 3 * HD),
+                          dict(a_off=r0 * C, b_off=j * HD * C, out_off=r0 * 3 * HD + j * HD, bias=bd, bias_off=j * HD)))
+        r0 += rows
+    assert len(probs) == 12
+    ops.gemm_grouped(probs)
+    r0 = 0
+    for rows, hk, ek in segs:
+        ref = (x[r0:r0 + rows, :ek].double() @ w[:, :ek].double().t() + b.double()).view(rows, 3, H, D)[:, :, :hk]
+        got = qkv[r0:r0 + rows].view(rows, 3, H, D)[:, :, :hk].double().cpu()
+        assert rel(got, ref) < 6e-3, (rows, hk, ek)
+        assert torch.isnan(qkv[r0:r0 + rows].view(rows, 3, H, D)[:, :, hk:].float()).all()
+        r0 += rows
+    # GELU' data gradients of four segments: du = (df W2) * gelu'(u), column sums of all segments into ONE bias-gradient vector
+    F = 384
+    df = torch.randn(M, C, generator=g).to(torch.bfloat16)
+    w2 = (torch.randn(C, F, generator=g) * 0.1).to(torch.bfloat16)
+    u = torch.randn(M, F, generator=g).to(torch.bfloat16)
+    du = torch.zeros(M, F, device='cuda', dtype=torch.bfloat16)
+    db = torch.zeros(F, device='cuda')
+    dfd, w2d, ud = df.cuda(), w2.cuda(), u.cuda()
+    probs, r0, keeps = [], 0, [(160, 384), (144, 256), (128, 320), (96, 192)]
+    for (rows, _, _), (ck, ik) in zip(segs, keeps):
+        probs.append(((dfd, w2d, C, F, rows, ik, ck, ops.EPI_GELUGRAD, du, F),
+                      dict(a_off=r0 * C, out_off=r0 * F, n_out=ik, aux=ud, ld_aux=F, aux_off=r0 * F, b_layout=ops.MNMAJOR, colsum=db)))
+        r0 += rows
+    ops.gemm_grouped(probs)
+    ref_db = torch.zeros(F, dtype=torch.float64)
+    r0 = 0
+    for (rows, _, _), (ck, ik) in zip(segs, keeps):
+        ud64 = u[r0:r0 + rows, :ik].double().requires_grad_(True)
+        torch.nn.functional.gelu(ud64).sum().backward()
+        ref = (df[r0:r0 + rows, :ck].double() @ w2[:ck, :ik].double()) * ud64.grad
+        assert rel(du[r0:r0 + rows, :ik], ref) < 8e-3
+        ref_db[:ik] += ref.sum(0)
+        r0 += rows
+    assert rel(db, ref_db) < 5e-3

@@ -56,11 +56,14 @@ constexpr int SMEM_MISC_BASE = 1024 /*align*/ + 256 /*barriers, tmem slot*/;    
 
 constexpr int COLACC_MAX = 3072;      // widest output whose bias-gradient column sums are accumulated in shared memory
 constexpr int MAX_TERMS = 6;
-struct TmapPack {
-  CUtensorMap a[MAX_TERMS];
-  CUtensorMap b[MAX_TERMS];
+template <int TERMS> struct TmapPackT {
+  CUtensorMap a[TERMS];
+  CUtensorMap b[TERMS];
   CUtensorMap out, out2, aux;   // epilogue tiles (128B-swizzled boxes of 128 rows x 128 bytes)
 };
+// Launches of up to 4 problems carry six operand-map pairs per problem (the split-bf16 parity mode contracts six terms); launches of up to
+// 16 problems (all segments of a multi-architecture half block at once) carry one pair: single-term bf16 problems only.
+template <int G> struct GroupPack { using type = TmapPackT<(G > 4 ? 1 : MAX_TERMS)>; };
 
 static long long* g_gemm_dbg = nullptr;   // development aid: clock stamps of CTA 0 (tools/gemm_timeline.py)
 static int g_force_mt = 0;   // 0 = heuristic, 1 / 2 = force the 128- / 256-row CTA tile (tests)
@@ -82,10 +85,11 @@ struct GemmArgs {
 // the q / k / v row blocks of a head-masked qkv projection, or all weight gradients of a half block.  Tiles of all problems form
 // one list that the persistent CTAs walk, so small problems fill the machine together instead of paying one launch each.
 template <int G> struct Group {
-  TmapPack maps[G];
+  typename GroupPack<G>::type maps[G];
   GemmArgs args[G];
   int tile_end[G];     // exclusive prefix sums of the problems' tile counts
   int count, total;
+  int colacc_n;        // > 0: every problem accumulates its fused column sums into ONE target of this width (per-CTA shared-memory partials)
 };
 
 // Shared-memory matrix descriptor (tcgen05), 128B swizzle.  K-major: rows of 128 B, 8-row groups 1024 B apart (SBO).
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (2 * MAX_STAGES + 8));
   float* bias_s = reinterpret_cast<float*>(misc + 256);   // [2][TILE_N]
   float* colacc = reinterpret_cast<float*>(misc + P::SMEM_MISC - 1024);   // [COLACC_MAX] when P::COLACC != 0 (after the 1 KB alignment slack)
-  const bool use_colacc = G == 1 && P::COLACC != 0 && grp.args[0].colsum != nullptr && grp.args[0].n_out <= COLACC_MAX;
+  const bool use_colacc = P::COLACC != 0 && grp.colacc_n > 0;
   long long* const dbg = grp.args[0].dbg;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -314,7 +318,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         int pi, m0, n0, kb0, nkb;
         tile_info(t, pi, m0, n0, kb0, nkb);
         const GemmArgs& g = grp.args[pi];
-        const TmapPack& maps = grp.maps[pi];
+        const auto& maps = grp.maps[pi];
         const int nb0 = n0 + cta_rank * BN;          // this CTA's B columns
         for (int i = 0; i < nkb * g.terms; ++i, ++it) {
           const int s = it % STAGES;
@@ -400,7 +404,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         int pi, m0, n0, kb0, nkb;
         tile_info(t, pi, m0, n0, kb0, nkb);
         const GemmArgs& g = grp.args[pi];
-        const TmapPack& maps = grp.maps[pi];
+        const auto& maps = grp.maps[pi];
         const int nu = n0 + (sub % NT) * BN;
         const int ncols = max(0, min(BN, g.n_out - nu));
         const int nbox = (ncols + BOXC - 1) / BOXC;
@@ -425,7 +429,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
         int pi, m0, n0, kb0, nkb;
         tile_info(t, pi, m0, n0, kb0, nkb);
         const GemmArgs& g = grp.args[pi];
-        const TmapPack& maps = grp.maps[pi];
+        const auto& maps = grp.maps[pi];
         const int ms = m0 + (sub / NT) * BM, nu = n0 + (sub % NT) * BN;
         const int ncols = max(0, min(BN, g.n_out - nu));
         const int nbox = (ncols + BOXC - 1) / BOXC;
@@ -463,7 +467,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
       chalf = ew >> 2;
     }
     if (use_colacc) {
-      for (int i = et; i < grp.args[0].n_out; i += EPI_WARPS * 32) colacc[i] = 0.f;
+      for (int i = et; i < ((grp.colacc_n + 3) & ~3); i += EPI_WARPS * 32) colacc[i] = 0.f;
       named_bar_sync(1, EPI_WARPS * 32);
     }
     const uint32_t acc_empty_leader = CG == 2 ? mapa_cluster(acc_empty(0), 0) : 0u;      // + 8 * ab
@@ -607,9 +611,9 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
     }
     if (use_colacc) {
       named_bar_sync(1, EPI_WARPS * 32);
-      for (int i = et * 4; i < grp.args[0].N; i += EPI_WARPS * 32 * 4) {
+      for (int i = et * 4; i < grp.colacc_n; i += EPI_WARPS * 32 * 4) {
         const float4 t4 = *reinterpret_cast<const float4*>(colacc + i);
-        red_add4(grp.args[0].colsum + i, t4, i, grp.args[0].N);
+        red_add4(grp.args[0].colsum + i, t4, i, grp.colacc_n);
       }
     }
   }
@@ -623,7 +627,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   }
 }
 
-constexpr int MAX_GROUP = 4;
+constexpr int MAX_GROUP = 4, MAX_GROUP_WIDE = 16;
 
 template <int EPI, typename OutT, int MT, int G, int CG>
 int launch_g(const Group<G>& grp, cudaStream_t st) {
@@ -726,8 +730,9 @@ int launch(Group<G>& grp, cudaStream_t st) {
 }
 
 // One problem descriptor -> kernel arguments + tensor maps.  Returns VSX_OK, an error, or 1 when there is nothing to do.
-int build_problem(const vsx_gemm_desc* d, TmapPack& maps, GemmArgs& g) {
-  VSX_REQUIRE(d->terms >= 1 && d->terms <= MAX_TERMS, "vsx_gemm: terms must be 1..6 (got %d)", d->terms);
+template <int TERMS>
+int build_problem(const vsx_gemm_desc* d, TmapPackT<TERMS>& maps, GemmArgs& g) {
+  VSX_REQUIRE(d->terms >= 1 && d->terms <= TERMS, "vsx_gemm: this launch takes 1..%d product terms per problem (got %d)", TERMS, d->terms);
   VSX_REQUIRE(d->M > 0 && d->N >= 0 && d->K >= 0, "vsx_gemm: bad extents M=%d N=%d K=%d", d->M, d->N, d->K);
   VSX_REQUIRE(d->lda % 8 == 0 && d->ldb % 8 == 0, "vsx_gemm: operand pitches must be multiples of 8 elements (lda=%ld ldb=%ld)", d->lda, d->ldb);
   VSX_REQUIRE(d->out != nullptr && d->n_out >= d->N && d->n_out <= d->ldo, "vsx_gemm: need N <= n_out <= ldo (N=%d n_out=%d ldo=%ld)", d->N, d->n_out, d->ldo);
@@ -815,6 +820,14 @@ int run_group(const vsx_gemm_desc* descs, int count, cudaStream_t st) {
     if (rc == 0) ++gr.count;
   }
   if (gr.count == 0) return VSX_OK;
+  // fused column sums (bias gradients): per-CTA shared-memory partials when every problem of the launch adds into the same vector
+  gr.colacc_n = 0;
+  if (gr.args[0].colsum != nullptr) {
+    int nmax = 0;
+    bool same = true;
+    for (int q = 0; q < gr.count; ++q) same = same && gr.args[q].colsum == gr.args[0].colsum, nmax = gr.args[q].N > nmax ? gr.args[q].N : nmax;
+    if (same && nmax <= COLACC_MAX) gr.colacc_n = nmax;
+  }
   const bool f32 = descs[0].out_dtype == VSX_F32;
   switch (descs[0].epilogue) {
     case VSX_EPI_STORE: return f32 ? launch<VSX_EPI_STORE, float, G>(gr, st) : launch<VSX_EPI_STORE, bf16, G>(gr, st);
@@ -855,7 +868,8 @@ extern "C" int vsx_gemm(const vsx_gemm_desc* d, void* stream) {
 }
 
 extern "C" int vsx_gemm_grouped(const vsx_gemm_desc* descs, int count, void* stream) {
-  VSX_REQUIRE(descs != nullptr && count >= 1 && count <= MAX_GROUP, "vsx_gemm_grouped: 1..%d problems per launch (got %d)", MAX_GROUP, count);
+  VSX_REQUIRE(descs != nullptr && count >= 1 && count <= MAX_GROUP_WIDE, "vsx_gemm_grouped: 1..%d problems per launch (got %d)", MAX_GROUP_WIDE, count);
   if (count == 1) return run_group<1>(descs, 1, reinterpret_cast<cudaStream_t>(stream));
-  return run_group<MAX_GROUP>(descs, count, reinterpret_cast<cudaStream_t>(stream));
+  if (count <= MAX_GROUP) return run_group<MAX_GROUP>(descs, count, reinterpret_cast<cudaStream_t>(stream));
+  return run_group<MAX_GROUP_WIDE>(descs, count, reinterpret_cast<cudaStream_t>(stream));
 }

@@ -89,10 +89,13 @@ int check_desc(const vsx_half_block* h, const char* what) {
   return VSX_OK;
 }
 
-// Problems of the same epilogue collected over the segments of a half block and launched in groups of up to four: a step with
-// several sub-architectures (multi / hybrid sampling) then costs about as many GEMM launches as a single-architecture step.
+// Problems of the same epilogue collected over the segments of a half block and launched together (up to 16 single-term problems per
+// launch: four segments x {q, k, v} row blocks, or all weight gradients of a half block): a step with several sub-architectures
+// (multi / hybrid sampling) then costs the same number of GEMM launches as a single-architecture step, and the persistent CTAs walk
+// ONE tile list.
 struct GemmBatch {
-  vsx_gemm_desc d[4];
+  static constexpr int CAP = 16;
+  vsx_gemm_desc d[CAP];
   int n = 0;
   void* stream;
   explicit GemmBatch(void* st) : stream(st) {}
@@ -104,7 +107,7 @@ struct GemmBatch {
   }
   int add(const vsx_gemm_desc& g) {
     d[n++] = g;
-    return n == 4 ? flush() : VSX_OK;
+    return n == CAP ? flush() : VSX_OK;
   }
 };
 
@@ -291,15 +294,16 @@ extern "C" int vsx_half_block_bwd(const vsx_half_block_grad* b, void* stream) {
     HB_CHECK(for_active([&](const SegView& v) -> int { return dxn_gemm(v, B16(b->d_act1) + v.r0 * 3 * HD, 3 * HD, 3 * HD, v.s->inner_keep / D); }));
     HB_CHECK(batch.flush());
   } else {
-    // phase 2: du[rows, ik] = (df[rows, ck] W2[ck, ik]) * gelu'(u); its column sums are the fc1 bias gradient.  One launch per
-    // segment: the per-CTA shared-memory accumulation of those sums only exists for single-problem launches
+    // phase 2: du[rows, ik] = (df[rows, ck] W2[ck, ik]) * gelu'(u); its column sums are the fc1 bias gradient (all segments add into
+    // the same vector: per-CTA shared-memory partials also for the grouped launch)
     HB_CHECK(for_active([&](const SegView& v) -> int {
       const vsx_segment& s = *v.s;
       const int ck = h->residual ? s.out_keep : C;
       Gemm g(B16(b->df) + v.r0 * C, C, VSX_KMAJOR, h->w2, F, VSX_MNMAJOR, v.rows, s.inner_keep, ck, VSX_EPI_GELUGRAD, VSX_BF16, B16(b->d_act1) + v.r0 * F, F);
       g.d.n_out = up8(s.inner_keep), g.d.aux = B16(h->act1) + v.r0 * F, g.d.ld_aux = F, g.d.colsum = b->d_b1;
-      return vsx_gemm(&g.d, stream);
+      return batch.add(g.d);
     }));
+    HB_CHECK(batch.flush());
     // phase 3: weight gradients: dW2[ck, ik] += df^T h and dW1[ik, ek] += du^T xn
     HB_CHECK(for_active([&](const SegView& v) -> int {
       const vsx_segment& s = *v.s;
