@@ -351,6 +351,17 @@ int vsx_masked_ln_bwd_segs(const void* dy, int dtype, long lddy, const float* x,
 int vsx_scale_mask_cast_segs(const float* g, long ldg, const float* row_scale, int rows_per_sample, void* out, int dtype, long ldo,
                              int rows, int cols, const vsx_row_segments* segs, float* colsum, void* stream);
 
+/* Attention core over a batch whose consecutive sample ranges keep different numbers of heads (heads_keep[i] == 0: samples skipped). */
+typedef struct vsx_sample_segments {
+  int count;                           /* 1 .. VSX_MAX_SEGMENTS */
+  int sample_end[VSX_MAX_SEGMENTS];    /* exclusive end sample of segment i; the last one = batch */
+  int heads_keep[VSX_MAX_SEGMENTS];
+} vsx_sample_segments;
+int vsx_attn_fwd_segs(const void* qkv, void* o, float* lse, int dtype, int batch, int tokens, int heads, int head_dim,
+                      const vsx_sample_segments* segs, float scale, int impl, void* stream);
+int vsx_attn_bwd_segs(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int dtype, int batch, int tokens,
+                      int heads, int head_dim, const vsx_sample_segments* segs, float scale, int impl, float* dbias, void* stream);
+
 /* ----------------------------------------------------------------------------------------------------
  * Loss and optimizer ends of the step (engine.py:152-157, :175-177).
  * vsx_soft_ce: *loss_sum += loss_scale * sum_rows(-sum_c t*log_softmax(x)); dlogits = grad_scale*(softmax*sum(t) - t)

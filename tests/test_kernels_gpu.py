@@ -583,3 +583,49 @@ def test_gemm_grouped_wide(ops, tile_rows):
         ref_db[:ik] += ref.sum(0)
         r0 += rows
     assert rel(db, ref_db) < 5e-3
+
+
+@pytest.mark.parametrize('N,H,D', [(257, 4, 64), (65, 12, 48), (17, 6, 32)])
+def test_attention_segments_one_launch(ops, N, H, D):
+    """vsx_attn_fwd_segs / vsx_attn_bwd_segs: a batch whose consecutive sample ranges keep different numbers of heads (one range dropped
+    entirely) in ONE launch of the tcgen05 kernels, against per-segment launches of the fp32-math kernel."""
+    import ctypes as C
+    from vit_search_b200 import _lib
+    ranges = [(20, H), (13, max(1, H // 2)), (7, 0), (30, H - 1)]
+    B = sum(n for n, _ in ranges)
+    g = torch.Generator().manual_seed(N + H)
+    qkv = (torch.randn(B * N, 3 * H * D, generator=g) * 1.2).to(torch.bfloat16).cuda()
+    do = torch.randn(B * N, H * D, generator=g).to(torch.bfloat16).cuda()
+    sg = _lib.SampleSegments()
+    sg.count = len(ranges)
+    e = 0
+    for i, (n, hk) in enumerate(ranges):
+        e += n
+        sg.sample_end[i], sg.heads_keep[i] = e, hk
+    o = torch.full((B * N, H * D), float('nan'), device='cuda', dtype=torch.bfloat16)
+    lse = torch.zeros(B, H, N, device='cuda')
+    dq = torch.full((B * N, 3 * H * D), float('nan'), device='cuda', dtype=torch.bfloat16)
+    db = torch.zeros(3 * H * D, device='cuda')
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(_lib.lib().vsx_attn_fwd_segs(qkv.data_ptr(), o.data_ptr(), lse.data_ptr(), _lib.BF16, B, N, H, D, C.byref(sg), D ** -0.5, ops.ATTN_TCGEN05, st))
+    _lib.check(_lib.lib().vsx_attn_bwd_segs(qkv.data_ptr(), o.data_ptr(), do.data_ptr(), lse.data_ptr(), dq.data_ptr(), _lib.BF16, B, N, H, D, C.byref(sg),
+                                            D ** -0.5, ops.ATTN_TCGEN05, db.data_ptr(), st))
+    torch.cuda.synchronize()
+    db_ref = torch.zeros(3 * H * D, device='cuda')
+    b0 = 0
+    for n, hk in ranges:
+        rows = slice(b0 * N, (b0 + n) * N)
+        if hk == 0:
+            assert torch.isnan(o[rows].float()).all() and torch.isnan(dq[rows].float()).all()       # dropped samples are not touched
+            b0 += n
+            continue
+        o_r = torch.full((n * N, H * D), float('nan'), device='cuda', dtype=torch.bfloat16)
+        lse_r = torch.zeros(n, H, N, device='cuda')
+        dq_r = torch.full((n * N, 3 * H * D), float('nan'), device='cuda', dtype=torch.bfloat16)
+        ops.attn_fwd(qkv[rows], o_r, lse_r, n, N, H, D, hk, D ** -0.5, impl=ops.ATTN_FP32)
+        ops.attn_bwd(qkv[rows], o_r, do[rows], lse_r, dq_r, n, N, H, D, hk, D ** -0.5, impl=ops.ATTN_FP32, dbias=db_ref)
+        assert rel(o[rows], o_r) < 8e-3 and rel(lse[b0:b0 + n, :hk], lse_r[:, :hk]) < 1e-5
+        assert torch.all(o[rows].view(n * N, H, D)[:, hk:] == 0) and torch.all(dq[rows].view(n * N, 3, H, D)[:, :, hk:] == 0)
+        assert rel(dq[rows], dq_r) < 1.5e-2
+        b0 += n
+    assert rel(db, db_ref) < 8e-3

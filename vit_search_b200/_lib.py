@@ -39,6 +39,8 @@ SIGNATURES = {
     'vsx_gemm': [C.POINTER(GemmDesc), _p],
     'vsx_attn_fwd': [_p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p],
     'vsx_attn_bwd': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p],
+    'vsx_attn_fwd_segs': [_p, _p, _p, _i, _i, _i, _i, _i, _p, _f, _i, _p],
+    'vsx_attn_bwd_segs': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _f, _i, _p, _p],
     'vsx_attn_debug_buffer': [_p],
     'vsx_gemm_force_tile_rows': [_i],
     'vsx_gemm_force_cta_group': [_i],
@@ -85,6 +87,10 @@ class AdamWTensor(C.Structure):
 
 class RowSegments(C.Structure):
     _fields_ = [('count', _i), ('row_end', _i * 8), ('keep', _i * 8), ('keep2', _i * 8)]
+
+
+class SampleSegments(C.Structure):
+    _fields_ = [('count', _i), ('sample_end', _i * 8), ('heads_keep', _i * 8)]
 
 
 class Segment(C.Structure):

@@ -11,9 +11,10 @@ int attn_fwd_mma(const void* qkv, void* o, float* lse, int B, int N, int H, int 
 int attn_bwd_mma(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int N, int H, int D, int Hk,
                  float scale, float* dbias, cudaStream_t st);
 bool attn_mma_supported(int N, int D);
-int attn_fwd_tc(const void* qkv, void* o, float* lse, int B, int N, int H, int D, int Hk, float scale, cudaStream_t st);
+int attn_fwd_tc(const void* qkv, void* o, float* lse, int B, int N, int H, int D, int Hk, float scale, cudaStream_t st,
+                const vsx_sample_segments* sg = nullptr);
 int attn_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int N, int H, int D, int Hk, float scale,
-                float* dbias, cudaStream_t st);
+                float* dbias, cudaStream_t st, const vsx_sample_segments* sg = nullptr);
 bool attn_tc_supported(int N, int D);
 void attn_set_debug(long long* p);
 }  // namespace vsx
@@ -71,6 +72,64 @@ extern "C" int vsx_attn_bwd(const void* qkv, const void* o, const void* d_o, con
   }
   set_error("vsx_attn_bwd: bad dtype %d", dtype);
   return VSX_ERR_ARG;
+}
+
+// ---------------------------------------------------------------- several head extents in one launch (multi-architecture batches)
+static int check_sample_segs(const vsx_sample_segments* sg, int batch, int heads, int* hmax, const char* what) {
+  VSX_REQUIRE(sg != nullptr && sg->count >= 1 && sg->count <= VSX_MAX_SEGMENTS, "%s: 1..%d segments", what, VSX_MAX_SEGMENTS);
+  int prev = 0;
+  *hmax = 0;
+  for (int i = 0; i < sg->count; ++i) {
+    VSX_REQUIRE(sg->sample_end[i] >= prev && sg->heads_keep[i] >= 0 && sg->heads_keep[i] <= heads, "%s: segment %d is not ordered or keeps more than %d heads", what, i, heads);
+    prev = sg->sample_end[i];
+    *hmax = sg->heads_keep[i] > *hmax ? sg->heads_keep[i] : *hmax;
+  }
+  VSX_REQUIRE(prev == batch, "%s: the segments must cover the %d samples (last sample_end = %d)", what, batch, prev);
+  return VSX_OK;
+}
+
+extern "C" int vsx_attn_fwd_segs(const void* qkv, void* o, float* lse, int dtype, int batch, int tokens, int heads, int head_dim,
+                                 const vsx_sample_segments* segs, float scale, int impl, void* stream) {
+  int hmax = 0;
+  int rc = check_sample_segs(segs, batch, heads, &hmax, "vsx_attn_fwd_segs");
+  if (rc) return rc;
+  if ((rc = check_shape("vsx_attn_fwd_segs", batch, tokens, heads, head_dim, hmax))) return rc;
+  if (batch == 0 || hmax == 0) return VSX_OK;
+  if (dtype == VSX_BF16 && (impl == VSX_ATTN_IMPL_AUTO || impl == VSX_ATTN_IMPL_TCGEN05) && attn_tc_supported(tokens, head_dim))
+    return attn_fwd_tc(qkv, o, lse, batch, tokens, heads, head_dim, hmax, scale, reinterpret_cast<cudaStream_t>(stream), segs);
+  const size_t es = dtype == VSX_F32 ? 4 : 2;       // other implementations: one launch per segment
+  const long HD = (long)heads * head_dim;
+  for (int i = 0, b0 = 0; i < segs->count; b0 = segs->sample_end[i], ++i) {
+    const int nb = segs->sample_end[i] - b0;
+    if (nb == 0 || segs->heads_keep[i] == 0) continue;
+    rc = vsx_attn_fwd(static_cast<const uint8_t*>(qkv) + (size_t)b0 * tokens * 3 * HD * es, static_cast<uint8_t*>(o) + (size_t)b0 * tokens * HD * es,
+                      lse + (long)b0 * heads * tokens, dtype, nb, tokens, heads, head_dim, segs->heads_keep[i], scale, impl, stream);
+    if (rc) return rc;
+  }
+  return VSX_OK;
+}
+
+extern "C" int vsx_attn_bwd_segs(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int dtype, int batch, int tokens,
+                                 int heads, int head_dim, const vsx_sample_segments* segs, float scale, int impl, float* dbias, void* stream) {
+  int hmax = 0;
+  int rc = check_sample_segs(segs, batch, heads, &hmax, "vsx_attn_bwd_segs");
+  if (rc) return rc;
+  if ((rc = check_shape("vsx_attn_bwd_segs", batch, tokens, heads, head_dim, hmax))) return rc;
+  if (batch == 0 || hmax == 0) return VSX_OK;
+  if (dtype == VSX_BF16 && (impl == VSX_ATTN_IMPL_AUTO || impl == VSX_ATTN_IMPL_TCGEN05) && attn_tc_supported(tokens, head_dim))
+    return attn_bwd_tc(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, hmax, scale, dbias, reinterpret_cast<cudaStream_t>(stream), segs);
+  const size_t es = dtype == VSX_F32 ? 4 : 2;
+  const long HD = (long)heads * head_dim;
+  for (int i = 0, b0 = 0; i < segs->count; b0 = segs->sample_end[i], ++i) {
+    const int nb = segs->sample_end[i] - b0;
+    if (nb == 0 || segs->heads_keep[i] == 0) continue;
+    const size_t ro = (size_t)b0 * tokens;
+    rc = vsx_attn_bwd(static_cast<const uint8_t*>(qkv) + ro * 3 * HD * es, static_cast<const uint8_t*>(o) + ro * HD * es,
+                      static_cast<const uint8_t*>(d_o) + ro * HD * es, lse + (long)b0 * heads * tokens, static_cast<uint8_t*>(dqkv) + ro * 3 * HD * es, dtype, nb,
+                      tokens, heads, head_dim, segs->heads_keep[i], scale, impl, dbias, stream);
+    if (rc) return rc;
+  }
+  return VSX_OK;
 }
 
 /* Development aid (tools/attn_timeline.py): device buffer of 64 x 8 clock64 stamps written by CTA 0 of the tcgen05 backward kernel. */

@@ -48,7 +48,17 @@ struct AttnMaps {
   CUtensorMap d_o;  // d_o as [B][N][H][D], box 64 x 1 x 128 x 1 (backward only)
 };
 
+// Several head extents in one launch (multi-architecture batches): consecutive sample ranges with their own number of kept heads.
+// count == 0: every sample keeps Hk heads.  With segments, Hk is the LARGEST kept-head count.
+struct AttnSegs {
+  int count;
+  int b_end[VSX_MAX_SEGMENTS];      // exclusive end sample of segment i
+  int hk[VSX_MAX_SEGMENTS];         // kept heads of segment i (0: its samples are skipped)
+  int w_end[VSX_MAX_SEGMENTS];      // exclusive end of segment i in the flattened (sample, head) work list of the forward kernel
+};
+
 struct AttnArgs {
+  AttnSegs segs;
   int B, N, H, Hk, D;
   float scale;
   bf16* o;             // fwd: output; bwd: forward output (for delta)
@@ -66,6 +76,41 @@ __device__ __forceinline__ void tma_load_head(uint32_t dst, const CUtensorMap* m
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(0), "r"(head), "r"(row0), "r"(b)
       : "memory");
 }
+// forward work item w -> (sample, head)
+__device__ __forceinline__ void pair_of(const AttnSegs& sg, int Hk, int w, int& b, int& h) {
+  if (sg.count == 0) {
+    b = w / Hk, h = w % Hk;
+    return;
+  }
+  int i = 0, w0 = 0, b0 = 0;
+  while (i < sg.count - 1 && w >= sg.w_end[i]) w0 = sg.w_end[i], b0 = sg.b_end[i], ++i;
+  const int l = w - w0;
+  b = b0 + l / sg.hk[i], h = l % sg.hk[i];
+}
+// backward: the v-th sample (in batch order) that keeps head h, and how many there are
+__device__ __forceinline__ int sample_of(const AttnSegs& sg, int h, int v) {
+  if (sg.count == 0) return v;
+  int acc = 0, b0 = 0;
+  for (int i = 0; i < sg.count; ++i) {
+    if (sg.hk[i] > h) {
+      const int nb = sg.b_end[i] - b0;
+      if (v < acc + nb) return b0 + (v - acc);
+      acc += nb;
+    }
+    b0 = sg.b_end[i];
+  }
+  return b0;      // not reached for v < samples_with(sg, h, B)
+}
+__device__ __forceinline__ int samples_with(const AttnSegs& sg, int h, int B) {
+  if (sg.count == 0) return B;
+  int acc = 0, b0 = 0;
+  for (int i = 0; i < sg.count; ++i) {
+    if (sg.hk[i] > h) acc += sg.b_end[i] - b0;
+    b0 = sg.b_end[i];
+  }
+  return acc;
+}
+
 // `ncols` (a multiple of 8, <= 32) of 32 fp32 values -> bf16 -> global
 __device__ __forceinline__ void store_bf16_n(bf16* dst, const float (&v)[32], int ncols) {
 #pragma unroll
@@ -237,7 +282,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_tc_kernel(const __gri
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int N = a.N, D = a.D, HD = a.H * D, KS = D >> 4;      // KS: 16-wide k steps over the head dim
   const int QT = (N + 127) / 128, NKP = round16(N), nkb = (N + KV_BOX - 1) / KV_BOX;
-  const int total = a.B * a.Hk;
+  const int total = a.segs.count ? a.segs.w_end[a.segs.count - 1] : a.B * a.Hk;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.q);
@@ -261,7 +306,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_tc_kernel(const __gri
     if (lane == 0) {
       int nw = 0, qit = 0;
       for (int w = blockIdx.x; w < total; w += gridDim.x, ++nw) {
-        const int b = w / a.Hk, h = w % a.Hk;
+        int b, h;
+        pair_of(a.segs, a.Hk, w, b, h);
         mbar_wait_relaxed(bar(1), ((uint32_t)nw & 1u) ^ 1u);
         mbar_expect_tx(bar(0), (uint32_t)nkb * BOX12K);
         for (int c = 0; c < nkb; ++c) tma_load_head(base + F_K + c * BOX12K, &maps.kv, bar(0), a.H + h, c * KV_BOX, b);
@@ -329,9 +375,17 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_fwd_tc_kernel(const __gri
     const int nch = (NKP + 31) / 32;
     uint8_t* Ps = smem + F_P;
     int blk = 0;
-    zero_masked(a.o, HD, (long)a.B * N, a.Hk * D, (a.H - a.Hk) * D, 1, 0, threadIdx.x - SM_WARP0 * 32, SM_THREADS);
+    if (a.segs.count == 0) {
+      zero_masked(a.o, HD, (long)a.B * N, a.Hk * D, (a.H - a.Hk) * D, 1, 0, threadIdx.x - SM_WARP0 * 32, SM_THREADS);
+    } else {
+      for (int i = 0, b0 = 0; i < a.segs.count; b0 = a.segs.b_end[i], ++i)
+        if (a.segs.hk[i] > 0)
+          zero_masked(a.o + (long)b0 * N * HD, HD, (long)(a.segs.b_end[i] - b0) * N, a.segs.hk[i] * D, (a.H - a.segs.hk[i]) * D, 1, 0,
+                      threadIdx.x - SM_WARP0 * 32, SM_THREADS);
+    }
     for (int w = blockIdx.x; w < total; w += gridDim.x) {
-      const int b = w / a.Hk, h = w % a.Hk;
+      int b, h;
+      pair_of(a.segs, a.Hk, w, b, h);
       for (int i = 0; i < QT; ++i, ++blk) {
         const int rows_valid = min(128, N - i * 128);
         const bool active = q * 32 < rows_valid;
@@ -479,6 +533,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
   const int nbuf = 1;
   // this CTA's head and its samples: gridDim.x is a multiple of Hk
   const int h = blockIdx.x % a.Hk, slot = blockIdx.x / a.Hk, nslots = gridDim.x / a.Hk;
+  // samples that keep this CTA's head, in batch order: the loops below count v = slot, slot + nslots, ... < NB and map v to a sample
+  const int NB = samples_with(a.segs, h, a.B);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&maps.q);
@@ -503,7 +559,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
   if (warp == 0) {
     if (lane == 0) {
       int kvit = 0, qit = 0;
-      for (int b = slot; b < a.B; b += nslots) {
+      for (int v = slot; v < NB; v += nslots) {
+        const int b = sample_of(a.segs, h, v);
         for (int j = 0; j < KB; ++j, ++kvit) {
           const int ks = kvit & 1;
           mbar_wait_relaxed(bar(2 + ks), (((uint32_t)kvit >> 1) & 1u) ^ 1u);
@@ -546,14 +603,14 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
       __syncwarp();
     };
     BwdCursor c = {slot, 0, 0, 0, 0, 0, 0};
-    if (c.b < a.B) issue_sdp(c);
+    if (c.b < NB) issue_sdp(c);
     BwdCursor nx = c;
     nx.advance(QT, KB, nslots);
-    while (c.b < a.B) {
+    while (c.b < NB) {
       mbar_wait(bar(BAR_PDS), (uint32_t)c.n & 1u);      // P / dS of block c staged; S / dP columns free again
       tc_fence_after();
       if (a.dbg != nullptr && blockIdx.x == 0 && leader && c.n < 64) a.dbg[c.n * 8 + 0] = clock64();
-      if (nx.b < a.B) issue_sdp(nx);
+      if (nx.b < NB) issue_sdp(nx);
       if (a.dbg != nullptr && blockIdx.x == 0 && leader && c.n < 64) a.dbg[c.n * 8 + 1] = clock64();
       // accumulators about to be overwritten (first block of a key block / of a pair) must have been drained by the epilogue warps
       if (c.i == 0) mbar_wait(bar(BAR_DKV_EMPTY + c.kvit % nbuf), ((uint32_t)(c.kvit / nbuf) & 1u) ^ 1u);
@@ -592,7 +649,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
     const float c_exp = a.scale * LOG2E_F;
     BwdCursor c = {slot, 0, 0, 0, 0, 0, 0};
     float lse2[3] = {INFINITY, INFINITY, INFINITY}, delta[3] = {0.f, 0.f, 0.f};
-    while (c.b < a.B) {
+    while (c.b < NB) {
       if (c.j == 0 && c.i == 0) {
         // statistics of this pair, produced by the epilogue warps one pair ahead
         named_bar_sync(2 + (c.pair & 1), SM_THREADS + 128);
@@ -675,7 +732,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
     const int q = warp & 3, row = q * 32 + lane, et = threadIdx.x - EP_WARP0 * 32;   // et = 0..127
     const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16);
     const long ldq = 3L * HD;
-    zero_masked(a.dqkv, ldq, (long)a.B * N, a.Hk * D, (a.H - a.Hk) * D, 3, HD, et, 128);
+    if (a.segs.count == 0) {
+      zero_masked(a.dqkv, ldq, (long)a.B * N, a.Hk * D, (a.H - a.Hk) * D, 3, HD, et, 128);
+    } else {
+      for (int i = 0, b0 = 0; i < a.segs.count; b0 = a.segs.b_end[i], ++i)
+        if (a.segs.hk[i] > 0)
+          zero_masked(a.dqkv + (long)b0 * N * ldq, ldq, (long)(a.segs.b_end[i] - b0) * N, a.segs.hk[i] * D, (a.H - a.segs.hk[i]) * D, 3, HD, et, 128);
+    }
     // lse (log2 units) and delta = dO . O of sample b's query rows -> stats buffer; rows >= N get lse = +inf, so P = exp2(S*c - inf) = 0
     // and dS = 0 there (S and dP are exact zeros on those rows: TMA zero fill)
     auto make_stats = [&](int b, int buf) {
@@ -713,9 +776,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
     const bool is_v = q < 2;          // lanes 0..63 hold dV (columns 64..127), lanes 64..127 hold dK (columns 0..63)
     const int krow = row & 63;
     const float kv_mul = is_v ? 1.0f : a.scale;
-    if (slot < a.B) make_stats(slot, 0);
-    for (int b = slot; b < a.B; b += nslots, ++pair) {
-      if (b + nslots < a.B) make_stats(b + nslots, (pair + 1) & 1);
+    if (slot < NB) make_stats(sample_of(a.segs, h, slot), 0);
+    for (int v = slot; v < NB; v += nslots, ++pair) {
+      const int b = sample_of(a.segs, h, v);
+      if (v + nslots < NB) make_stats(sample_of(a.segs, h, v + nslots), (pair + 1) & 1);
       float csum[2][32];              // this thread's rows, summed over the key blocks of the pair: the butterfly runs once per pair
 #pragma unroll
       for (int t = 0; t < 32; ++t) csum[0][t] = 0.f, csum[1][t] = 0.f;
@@ -817,12 +881,26 @@ int zero_cols(void* base, long ld_elems, long rows, long col0, long ncols, cudaS
 
 }  // namespace
 
+// kernel-side copy of a segment list (plus the forward work-list prefix sums); sg == nullptr: uniform
+static void fill_segs(AttnSegs& t, const vsx_sample_segments* sg) {
+  memset(&t, 0, sizeof(t));
+  if (sg == nullptr) return;
+  t.count = sg->count;
+  int w = 0, b0 = 0;
+  for (int i = 0; i < sg->count; ++i) {
+    t.b_end[i] = sg->sample_end[i], t.hk[i] = sg->heads_keep[i];
+    w += (sg->sample_end[i] - b0) * sg->heads_keep[i];
+    t.w_end[i] = w;
+    b0 = sg->sample_end[i];
+  }
+}
+
 static long long* g_attn_dbg = nullptr;
 void attn_set_debug(long long* p) { g_attn_dbg = p; }
 
 bool attn_tc_supported(int N, int D) { return (D == 64 || D == 48 || D == 32) && N >= 1 && N <= ATT_MAX_N; }
 
-int attn_fwd_tc(const void* qkv, void* o, float* lse, int B, int N, int H, int D, int Hk, float scale, cudaStream_t st) {
+int attn_fwd_tc(const void* qkv, void* o, float* lse, int B, int N, int H, int D, int Hk, float scale, cudaStream_t st, const vsx_sample_segments* sg) {
   const long HD = (long)H * D;
   int rc = VSX_OK;
   if (Hk == 0) return zero_cols(o, HD, (long)B * N, 0, HD, st, "vsx_attn_fwd");
@@ -837,14 +915,16 @@ int attn_fwd_tc(const void* qkv, void* o, float* lse, int B, int N, int H, int D
   }
   AttnArgs a;
   a.B = B, a.N = N, a.H = H, a.Hk = Hk, a.D = D, a.scale = scale, a.o = (bf16*)o, a.d_o = nullptr, a.lse = lse, a.dqkv = nullptr, a.dbias = nullptr, a.dbg = nullptr;
-  const int total = B * Hk;
+  fill_segs(a.segs, sg);
+  const int total = sg != nullptr ? a.segs.w_end[a.segs.count - 1] : B * Hk;
+  if (total == 0) return VSX_OK;
   const int grid = total < num_sms() ? total : num_sms();
   launch_pdl(attn_fwd_tc_kernel, dim3(grid), dim3(ATT_THREADS), F_SMEM, st, maps, a);
   return check_launch("vsx_attn_fwd");
 }
 
 int attn_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int B, int N, int H, int D, int Hk, float scale,
-                float* dbias, cudaStream_t st) {
+                float* dbias, cudaStream_t st, const vsx_sample_segments* sg) {
   const long HD = (long)H * D;
   int rc = VSX_OK;
   if (Hk == 0) return zero_cols(dqkv, 3 * HD, (long)B * N, 0, 3 * HD, st, "vsx_attn_bwd");
@@ -860,6 +940,7 @@ int attn_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* ls
   AttnArgs a;
   a.B = B, a.N = N, a.H = H, a.Hk = Hk, a.D = D, a.scale = scale, a.o = (bf16*)const_cast<void*>(o), a.d_o = (const bf16*)d_o,
   a.lse = const_cast<float*>(lse), a.dqkv = (bf16*)dqkv, a.dbias = dbias, a.dbg = g_attn_dbg;
+  fill_segs(a.segs, sg);
   int per_head = num_sms() / Hk;
   if (per_head < 1) per_head = 1;
   if (per_head > B) per_head = B;

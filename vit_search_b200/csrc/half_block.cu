@@ -80,6 +80,21 @@ bool row_segments(const vsx_half_block* h, int which, vsx_row_segments* t) {
   return active >= 2 && h->segments[0].b0 == 0 && h->segments[h->num_segments - 1].b1 == h->batch;
 }
 
+// Sample-segment table (kept heads per segment) for the single-launch attention core; false: launch per segment.
+bool sample_segments(const vsx_half_block* h, vsx_sample_segments* t) {
+  if (h->num_segments < 2 || h->num_segments > VSX_MAX_SEGMENTS) return false;
+  memset(t, 0, sizeof(*t));
+  t->count = h->num_segments;
+  int active = 0;
+  for (int i = 0; i < h->num_segments; ++i) {
+    const vsx_segment& s = h->segments[i];
+    t->sample_end[i] = s.b1;
+    t->heads_keep[i] = (s.active && s.b1 > s.b0) ? s.inner_keep / h->head_dim : 0;
+    active += t->heads_keep[i] > 0;
+  }
+  return active >= 2 && h->segments[0].b0 == 0 && h->segments[h->num_segments - 1].b1 == h->batch;
+}
+
 int check_desc(const vsx_half_block* h, const char* what) {
   VSX_REQUIRE(h != nullptr && (h->kind == VSX_HALF_ATTN || h->kind == VSX_HALF_MLP), "%s: bad descriptor", what);
   VSX_REQUIRE(h->batch > 0 && h->tokens > 0 && h->width > 0 && h->width % 8 == 0, "%s: bad shape batch=%d tokens=%d width=%d", what, h->batch, h->tokens, h->width);
@@ -184,7 +199,11 @@ extern "C" int vsx_half_block_fwd(const vsx_half_block* h, void* stream) {
       return VSX_OK;
     }));
     HB_CHECK(batch.flush());
-    // phase 3: attention core per segment (heads_keep differs)
+    // phase 3: attention core: one launch over the batch with per-segment kept heads, or one per segment
+    vsx_sample_segments stab;
+    if (sample_segments(h, &stab)) {
+      HB_CHECK(vsx_attn_fwd_segs(h->act1, h->act2, h->lse, VSX_BF16, h->batch, N, H, D, &stab, scale, VSX_ATTN_IMPL_AUTO, stream));
+    } else
     HB_CHECK(for_active([&](const SegView& v) -> int {
       return vsx_attn_fwd(B16(h->act1) + v.r0 * 3 * HD, B16(h->act2) + v.r0 * HD, h->lse + (long)v.s->b0 * H * N, VSX_BF16, v.nb, N, H, D,
                           v.s->inner_keep / D, scale, VSX_ATTN_IMPL_AUTO, stream);
@@ -266,7 +285,11 @@ extern "C" int vsx_half_block_bwd(const vsx_half_block_grad* b, void* stream) {
       return batch.add(g.d);
     }));
     HB_CHECK(batch.flush());
-    // phase 3: attention backward per segment (also accumulates the qkv bias gradient)
+    // phase 3: attention backward (also accumulates the qkv bias gradient): one launch over the batch, or one per segment
+    vsx_sample_segments stab;
+    if (sample_segments(h, &stab)) {
+      HB_CHECK(vsx_attn_bwd_segs(h->act1, h->act2, b->d_act2, h->lse, b->d_act1, VSX_BF16, h->batch, N, H, D, &stab, scale, VSX_ATTN_IMPL_AUTO, b->d_b1, stream));
+    } else
     HB_CHECK(for_active([&](const SegView& v) -> int {
       return vsx_attn_bwd(B16(h->act1) + v.r0 * 3 * HD, B16(h->act2) + v.r0 * HD, B16(b->d_act2) + v.r0 * HD, h->lse + (long)v.s->b0 * H * N,
                           B16(b->d_act1) + v.r0 * 3 * HD, VSX_BF16, v.nb, N, H, D, v.s->inner_keep / D, scale, VSX_ATTN_IMPL_AUTO, b->d_b1, stream);
