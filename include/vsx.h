@@ -200,16 +200,19 @@ typedef struct vsx_half_block_grad {
   void* d_act1;              /* bf16 scratch: dqkv [.., 3*H*D] | du [.., hidden] */
   void* d_act2;              /* bf16 scratch: d_o [.., H*D] (attention only) */
   float *d_ln_w, *d_ln_b, *d_w1, *d_b1, *d_w2, *d_b2;   /* fp32 parameter gradients, ACCUMULATED into (zero them once per step) */
-  /* Optional fusion across consecutive half blocks (single-segment, pre-norm, residual calls; all zero / NULL = off).
+  /* Optional fusion across consecutive half blocks (pre-norm, residual calls whose segments are all active; all zero / NULL = off).
    * df_ready != 0: `df` already holds the scaled / masked gradient of the branch output and d_b2 its column sums -- they were written by
    * the call that produced g_out (its next_* fields) -- so the cast pass over g_out is skipped.
    * next_df != NULL: the LayerNorm backward of THIS call also writes next_df = bf16(next_row_scale[next_scale_off + sample] * g_in) masked
-   * to next_keep channels and accumulates its column sums into next_d_b2: the `df` / `d_b2` of the half block that consumes g_in. */
+   * to next_keep channels and accumulates its column sums into next_d_b2: the `df` / `d_b2` of the half block that consumes g_in.
+   * Several segments: next_segments points to the consuming half block's segment list (same count and sample ranges as this call's);
+   * segment i is then masked to next_segments[i].out_keep channels and next_keep is ignored. */
   int df_ready;
   void* next_df;
   const float* next_row_scale;
   int next_scale_off, next_keep;
   float* next_d_b2;
+  const vsx_segment* next_segments;
 } vsx_half_block_grad;
 int vsx_half_block_fwd(const vsx_half_block* d, void* stream);
 int vsx_half_block_bwd(const vsx_half_block_grad* d, void* stream);

@@ -107,7 +107,7 @@ class HalfBlock(C.Structure):
 class HalfBlockGrad(C.Structure):
     _fields_ = [('fwd', HalfBlock), ('g_out', _p), ('g_in', _p), ('df', _p), ('dxn', _p), ('d_act1', _p), ('d_act2', _p),
                 ('d_ln_w', _p), ('d_ln_b', _p), ('d_w1', _p), ('d_b1', _p), ('d_w2', _p), ('d_b2', _p),
-                ('df_ready', _i), ('next_df', _p), ('next_row_scale', _p), ('next_scale_off', _i), ('next_keep', _i), ('next_d_b2', _p)]
+                ('df_ready', _i), ('next_df', _p), ('next_row_scale', _p), ('next_scale_off', _i), ('next_keep', _i), ('next_d_b2', _p), ('next_segments', _p)]
 
 
 _lib = None

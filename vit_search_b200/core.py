@@ -236,15 +236,26 @@ class Seg:
         return (self.ek, self.ik, self.ck, self.active)
 
 
-def make_segments(batch, width, embed_keep, inner_keep, inner_full, cur_keep):
-    """Per-sample keep lists (or None) -> list of Seg with maximal runs of identical keeps."""
+def make_segments(batch, width, embed_keep, inner_keep, inner_full, cur_keep, bounds=None, grouped=False):
+    """Per-sample keep lists (or None) -> list of Seg with maximal runs of identical keeps.  `bounds`: sample indices at which a new
+    segment starts even if the extents do not change (the architecture-group boundaries of the batch: every half block of a step then
+    has the SAME sample ranges, so consecutive half blocks can hand gradients over segment by segment).  grouped=True: the caller
+    guarantees that the keeps only change at `bounds` (None: one architecture), so only the first sample of every group is inspected."""
     segs = []
+    if grouped:
+        starts = [0] + (sorted(bounds) if bounds else [])
+        for i, b in enumerate(starts):
+            ek = width if embed_keep is None else int(embed_keep[b])
+            ik = inner_full if inner_keep is None else int(inner_keep[b])
+            ck = width if cur_keep is None else int(cur_keep[b])
+            segs.append(Seg(b, starts[i + 1] if i + 1 < len(starts) else batch, ek, ik, ck, ck > 0 and ik > 0 and ek > 0))
+        return segs
     for b in range(batch):
         ek = width if embed_keep is None else int(embed_keep[b])
         ik = inner_full if inner_keep is None else int(inner_keep[b])
         ck = width if cur_keep is None else int(cur_keep[b])
         act = ck > 0 and ik > 0 and ek > 0
-        if segs and segs[-1].key() == (ek, ik, ck, act):
+        if segs and segs[-1].key() == (ek, ik, ck, act) and not (bounds is not None and b in bounds):
             segs[-1].b1 = b + 1
         else:
             segs.append(Seg(b, b + 1, ek, ik, ck, act))
@@ -531,6 +542,15 @@ def _fusable(meta):
     return bool(meta.segs[0].active) and meta.residual and meta.pre_norm
 
 
+def _fusable_pair(consumer, producer):
+    """The LayerNorm backward of `producer` (the later half block) may write the bf16 gradient copy `consumer` (the earlier one) starts
+    from: both pre-norm + residual, every segment active, and identical sample ranges."""
+    for m in (consumer, producer):
+        if not (m.residual and m.pre_norm and 1 <= len(m.segs) <= 8 and all(s.active for s in m.segs)):
+            return False
+    return [(s.b0, s.b1) for s in consumer.segs] == [(s.b0, s.b1) for s in producer.segs]
+
+
 def _half_backward_buffers(meta, x, params):
     B, N, C = x.shape
     M = B * N
@@ -562,7 +582,7 @@ def native_half_backward(meta, g_out, saved, x, params, ctx=None):
         sc, grads = _half_backward_buffers(meta, x, params)
     fd, _ = _half_desc(meta, x, None, params, ws16, ws32)
     ps = sc.data_ptr()
-    nxt = (None, None, 0, 0, None)
+    nxt = (None, None, 0, 0, None, None)
     prev = getattr(ctx, 'prev', None) if ctx is not None else None
     if FUSE_CAST and prev is not None and _fusable(meta) and _fusable(prev.meta) and prev.saved is not None:
         px, *pparams = prev.saved_tensors
@@ -571,7 +591,7 @@ def native_half_backward(meta, g_out, saved, x, params, ctx=None):
             pm = prev.meta
             rs = pm.row_scale
             nxt = (psc.data_ptr(), None if rs is None else rs.data_ptr(), pm.scale_off if rs is not None else 0, pm.segs[0].ck,
-                   pgrads[5].data_ptr())
+                   pgrads[5].data_ptr(), None)
             prev.prefetched = (psc, pgrads, g_in, None)
     d = _lib.HalfBlockGrad(fd, g_out.data_ptr(), g_in.data_ptr(), ps, ps + 2 * M * C, ps + 4 * M * C, (ps + 2 * M * (2 * C + inner)) if attn else None,
                            *[t.data_ptr() for t in grads], df_ready, *nxt)
@@ -712,18 +732,18 @@ class StageFn(torch.autograd.Function):
         fuse = [False] * n          # fuse[i]: half block i's df is written by the LayerNorm backward of half block i + 1
         if FUSE_CAST:
             for i in range(n - 1):
-                fuse[i] = _fusable(metas[i]) and _fusable(metas[i + 1])
+                fuse[i] = _fusable_pair(metas[i], metas[i + 1])
         for i, meta in enumerate(metas):
             attn, inner, a2, _, _ = sizes[i]
             ps = psc + 2 * sc_elems * (i & 1)
             g_out = pg if i == n - 1 else pgb + gstride * ((i + 1) & 1)
             g_in = pgb + gstride * (i & 1)
-            nxt = (None, None, 0, 0, None)
+            nxt = (None, None, 0, 0, None, None)
             if i > 0 and fuse[i - 1]:
                 pm = metas[i - 1]
                 rs = pm.row_scale
                 nxt = (psc + 2 * sc_elems * ((i - 1) & 1), None if rs is None else rs.data_ptr(), pm.scale_off if rs is not None else 0, pm.segs[0].ck,
-                       grads[6 * (i - 1) + 5].data_ptr())
+                       grads[6 * (i - 1) + 5].data_ptr(), _C.cast(_segments_c(pm), _C.c_void_p))
             gi = grads[6 * i:6 * i + 6]
             descs[i] = _lib.HalfBlockGrad(fdescs[i], g_out, g_in, ps, ps + 2 * M * C, ps + 4 * M * C, (ps + 2 * M * (2 * C + inner)) if attn else None,
                                           *[t.data_ptr() for t in gi], 1 if fuse[i] else 0, *nxt)

@@ -55,6 +55,7 @@ struct AttnSegs {
   int b_end[VSX_MAX_SEGMENTS];      // exclusive end sample of segment i
   int hk[VSX_MAX_SEGMENTS];         // kept heads of segment i (0: its samples are skipped)
   int w_end[VSX_MAX_SEGMENTS];      // exclusive end of segment i in the flattened (sample, head) work list of the forward kernel
+  int cta_end[16];                  // backward: exclusive end of the CTA range that works on head h (CTAs in proportion to the samples keeping h)
 };
 
 struct AttnArgs {
@@ -532,7 +533,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
   // running in the shadow of the MMA wait), so every shape runs single buffered.
   const int nbuf = 1;
   // this CTA's head and its samples: gridDim.x is a multiple of Hk
-  const int h = blockIdx.x % a.Hk, slot = blockIdx.x / a.Hk, nslots = gridDim.x / a.Hk;
+  int h, slot, nslots;
+  if (a.segs.count == 0) {
+    h = blockIdx.x % a.Hk, slot = blockIdx.x / a.Hk, nslots = gridDim.x / a.Hk;
+  } else {            // heads kept by fewer samples get fewer CTAs
+    h = 0;
+    while (h < a.Hk - 1 && (int)blockIdx.x >= a.segs.cta_end[h]) ++h;
+    const int c0 = h == 0 ? 0 : a.segs.cta_end[h - 1];
+    slot = blockIdx.x - c0, nslots = a.segs.cta_end[h] - c0;
+  }
   // samples that keep this CTA's head, in batch order: the loops below count v = slot, slot + nslots, ... < NB and map v to a sample
   const int NB = samples_with(a.segs, h, a.B);
 
@@ -944,7 +953,28 @@ int attn_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* ls
   int per_head = num_sms() / Hk;
   if (per_head < 1) per_head = 1;
   if (per_head > B) per_head = B;
-  launch_pdl(attn_bwd_tc_kernel, dim3(per_head * Hk), dim3(BWD_THREADS), B_SMEM, st, maps, a);
+  int grid = per_head * Hk;
+  if (sg != nullptr) {
+    // CTAs per head in proportion to the number of samples that keep it (at least one, at most one per sample)
+    VSX_REQUIRE(Hk <= 16, "vsx_attn_bwd_segs: at most 16 heads (got %d)", Hk);
+    int cnt[16], total = 0;
+    for (int hh = 0; hh < Hk; ++hh) {
+      cnt[hh] = 0;
+      for (int i = 0, b0 = 0; i < sg->count; b0 = sg->sample_end[i], ++i)
+        if (sg->heads_keep[i] > hh) cnt[hh] += sg->sample_end[i] - b0;
+      total += cnt[hh];
+    }
+    const int sms = num_sms() > Hk ? num_sms() : Hk;
+    int end = 0;
+    for (int hh = 0; hh < Hk; ++hh) {
+      int c = total > 0 ? (int)((long)sms * cnt[hh] / total) : 1;
+      c = c < 1 ? 1 : (c > cnt[hh] && cnt[hh] > 0 ? cnt[hh] : c);
+      end += c;
+      a.segs.cta_end[hh] = end;
+    }
+    grid = end;
+  }
+  launch_pdl(attn_bwd_tc_kernel, dim3(grid), dim3(BWD_THREADS), B_SMEM, st, maps, a);
   return check_launch("vsx_attn_bwd");
 }
 

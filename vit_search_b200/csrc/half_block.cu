@@ -232,9 +232,12 @@ extern "C" int vsx_half_block_bwd(const vsx_half_block_grad* b, void* stream) {
   HB_CHECK(check_desc(h, "vsx_half_block_bwd"));
   const int N = h->tokens, C = h->width, H = h->heads, D = h->head_dim, HD = H * D, F = h->hidden;
   const float scale = h->kind == VSX_HALF_ATTN ? 1.0f / sqrtf((float)D) : 0.f;
-  VSX_REQUIRE((!b->df_ready && b->next_df == nullptr) || (h->num_segments == 1 && h->segments[0].active && h->segments[0].b0 == 0 &&
-                                                           h->segments[0].b1 == h->batch && h->pre_norm && h->residual),
-              "vsx_half_block_bwd: df_ready / next_df need a single active segment covering the batch, pre_norm and residual");
+  if (b->df_ready || b->next_df != nullptr) {
+    bool ok = h->pre_norm && h->residual && h->num_segments >= 1 && h->num_segments <= VSX_MAX_SEGMENTS && h->segments[0].b0 == 0 &&
+              h->segments[h->num_segments - 1].b1 == h->batch && (h->num_segments == 1 || b->next_df == nullptr || b->next_segments != nullptr);
+    for (int i = 0; ok && i < h->num_segments; ++i) ok = h->segments[i].active && h->segments[i].b1 > h->segments[i].b0;
+    VSX_REQUIRE(ok, "vsx_half_block_bwd: df_ready / next_df need pre_norm, residual and active segments covering the batch (next_segments for several)");
+  }
   // phase 1: dropped layers pass the gradient through; gradient of the branch output of every active segment: drop-path scale,
   // output mask, cast -- its column sums are the bias gradient of proj / fc2
   vsx_row_segments tab_out, tab_in;
@@ -347,6 +350,12 @@ extern "C" int vsx_half_block_bwd(const vsx_half_block_grad* b, void* stream) {
     HB_CHECK(batch.flush());
   }
   if (one_ln) {
+    if (b->next_df != nullptr) {        // the cast of the consuming half block rides on this LayerNorm backward, segment by segment
+      for (int i = 0; i < h->num_segments; ++i) tab_in.keep2[i] = b->next_segments[i].out_keep;
+      HB_CHECK(vsx_masked_ln_bwd_segs(b->dxn, VSX_BF16, C, h->x, C, h->mean, h->rstd, h->ln_w, h->residual ? b->g_out : nullptr, b->g_in, C, b->d_ln_w,
+                                      b->d_ln_b, h->batch * N, C, &tab_in, b->next_df, C,
+                                      b->next_row_scale != nullptr ? b->next_row_scale + b->next_scale_off : nullptr, N, b->next_d_b2, stream));
+    } else
     HB_CHECK(vsx_masked_ln_bwd_segs(b->dxn, VSX_BF16, C, h->x, C, h->mean, h->rstd, h->ln_w, h->residual ? b->g_out : nullptr, b->g_in, C, b->d_ln_w, b->d_ln_b,
                                     h->batch * N, C, &tab_in, nullptr, C, nullptr, 0, nullptr, stream));
   } else if (h->pre_norm) {

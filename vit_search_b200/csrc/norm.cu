@@ -642,7 +642,9 @@ extern "C" int vsx_masked_ln_bwd_segs(const void* dy, int dtype, long lddy, cons
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const RowSegs sg = to_segs(segs);
   const int rps = cast_rows_per_sample > 0 ? cast_rows_per_sample : 1;
-  const LnCast cast{cast_out, ld_cast, cast_scale, rps, 0, cast_colsum};
+  int keep2_max = 0;        // width of the cast's column sums: the largest cast extent of the launch
+  for (int i = 0; i < segs->count; ++i) keep2_max = segs->keep2[i] > keep2_max ? segs->keep2[i] : keep2_max;
+  const LnCast cast{cast_out, ld_cast, cast_scale, rps, keep2_max, cast_colsum};
   bool done = false;
   rc = dtype == VSX_BF16 ? ln_bwd_dispatch<bf16>(dy, nullptr, lddy, x, ldx, mean, rstd, gamma, g_in, g_out, ldg, dgamma, dbeta, rows, C, 0, 0, 0, st,
                                                  cast_out != nullptr ? &cast : nullptr, &done, &sg)

@@ -147,7 +147,7 @@ class Block(nn.Module):
         k['mlp'] = self.mlp.draw(batch, like)
         return k
 
-    def half_metas(self, B, N, C, embed_keep, layer_keep_in, keeps, dp_scale=None, dp_off=0):
+    def half_metas(self, B, N, C, embed_keep, layer_keep_in, keeps, dp_scale=None, dp_off=0, bounds=None, grouped=False):
         """Static descriptions of the two half blocks for one batch (host integers only).  -> (attention meta, MLP meta, current layer keep)."""
         cur = attn_ck = None
         if keeps.get('layer') is not None:                      # reference :220-223: layer_drop(f_x) masks the attention branch with
@@ -158,10 +158,10 @@ class Block(nn.Module):
             attn_ck = cur
         a, m = self.attn, self.mlp
         hd = a.num_heads * a.head_dim
-        segs = core.make_segments(B, C, embed_keep, keeps.get('attn'), hd, attn_ck)
+        segs = core.make_segments(B, C, embed_keep, keeps.get('attn'), hd, attn_ck, bounds, grouped)
         meta_a = core.HalfMeta('attn', segs, N, C, heads=a.num_heads, head_dim=a.head_dim, row_scale=dp_scale, scale_off=dp_off * B,
                                eps=self.norm1.eps)
-        segs = core.make_segments(B, C, embed_keep, keeps.get('mlp'), m.fc1.out_features, cur)
+        segs = core.make_segments(B, C, embed_keep, keeps.get('mlp'), m.fc1.out_features, cur, bounds, grouped)
         meta_m = core.HalfMeta('mlp', segs, N, C, hidden=m.fc1.out_features, row_scale=dp_scale, scale_off=(dp_off + 1) * B,
                                eps=self.norm2.eps)
         return meta_a, meta_m, cur

@@ -171,6 +171,7 @@ class FlexibleDistillVisionTransformer(nn.Module):
         return out
 
     _group_permutation = staticmethod(FlexibleDistillVisionTransformerSR._group_permutation)
+    _group_layout = staticmethod(FlexibleDistillVisionTransformerSR._group_layout)
 
     def forward(self, x):
         core.require_cuda(x, 'FlexibleDistillVisionTransformer')
@@ -179,7 +180,7 @@ class FlexibleDistillVisionTransformer(nn.Module):
         B = x.shape[0]
         keeps = self.sample_keeps(B) if self.is_supernet else [{} for _ in range(len(self.blocks) + 1)]
         self.last_keeps = keeps
-        perm = self._group_permutation(keeps, B)
+        perm, bounds = self._group_layout(keeps, B)
         if perm is not None:       # make architecture groups contiguous; undone on the logits
             x = x.index_select(0, core.h2d(perm, x.device))
             keeps = [{k: [v[p] for p in perm] for k, v in kd.items()} for kd in keeps]
@@ -198,7 +199,7 @@ class FlexibleDistillVisionTransformer(nn.Module):
         for t, blk in enumerate(self.blocks):
             if isinstance(blk, Block):
                 meta_a, meta_m, layer_keep = blk.half_metas(B, h.shape[1], h.shape[2], embed_keep, layer_keep, keeps[t + 1],
-                                                            dp if rates[t] > 0 else None, 2 * t)
+                                                            dp if rates[t] > 0 else None, 2 * t, bounds, True)
                 run_metas.extend((meta_a, meta_m))
                 run_params.extend(blk.half_params())
             else:

@@ -460,16 +460,27 @@ class FlexibleDistillVisionTransformerSR(nn.Module):
         return out
 
     @staticmethod
-    def _group_permutation(keeps, batch):
-        """Order that makes samples with identical keep tuples contiguous (stable).  Identity when there is one group."""
-        sig = [tuple(v[b] for k in keeps for v in k.values()) for b in range(batch)]
+    def _group_layout(keeps, batch):
+        """-> (order, bounds): the order that makes samples with identical keep tuples contiguous (stable; None = already so) and the
+        sample indices (in the new order) at which the sub-architecture changes (None = one architecture).  Signatures are built with
+        zip (C speed): this runs once per step on ~50 keep lists of `batch` integers."""
+        cols = [v for k in keeps for v in k.values()]
+        if not cols:
+            return None, None
+        sig = list(zip(*cols))
         if len(set(sig)) <= 1:
-            return None
+            return None, None
         first = {}
         for b, s in enumerate(sig):
             first.setdefault(s, b)
         order = sorted(range(batch), key=lambda b: (first[sig[b]], b))
-        return None if order == list(range(batch)) else order
+        bounds = {i for i in range(1, batch) if sig[order[i]] != sig[order[i - 1]]}
+        return (None if order == list(range(batch)) else order), bounds
+
+    @staticmethod
+    def _group_permutation(keeps, batch):
+        """Order that makes samples with identical keep tuples contiguous (stable).  Identity when there is one group."""
+        return FlexibleDistillVisionTransformerSR._group_layout(keeps, batch)[0]
 
     # ------------------------------------------------------------------ candidate evaluation on resident weights
     def subnet_extents(self, sub_network_def):
@@ -531,7 +542,7 @@ class FlexibleDistillVisionTransformerSR(nn.Module):
         if self.training or not self.weights_resident:
             core.weights.generation += 1      # weights may have been updated since the last forward: re-derive operand copies
         self.last_keeps = keeps
-        perm = None if self.active_subnet is not None else self._group_permutation(keeps, B)
+        perm, bounds = (None, None) if self.active_subnet is not None else self._group_layout(keeps, B)
         if perm is not None:       # make architecture groups contiguous; undone on the logits
             idx = core.h2d(perm, x.device)
             x = x.index_select(0, idx)
@@ -566,7 +577,7 @@ class FlexibleDistillVisionTransformerSR(nn.Module):
                 blk = self.blocks[j]
                 if isinstance(blk, Block) and not keeps[i].get('skip'):
                     use_dp = dp if rates[t] > 0 else None
-                    meta_a, meta_m, layer_keep = blk.half_metas(B, h.shape[1], h.shape[2], embed_keep, layer_keep, keeps[i], use_dp, 2 * t)
+                    meta_a, meta_m, layer_keep = blk.half_metas(B, h.shape[1], h.shape[2], embed_keep, layer_keep, keeps[i], use_dp, 2 * t, bounds, True)
                     run_metas.extend((meta_a, meta_m))
                     run_params.extend(blk.half_params())
                 else:
