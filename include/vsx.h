@@ -88,9 +88,9 @@ int vsx_masked_ln_bwd_cast(const void* dy, int dtype, long lddy, const float* x,
 #define VSX_MNMAJOR 1
 
 #define VSX_EPI_STORE 0     /* out = acc + bias                                   (out: bf16|f32)            */
-#define VSX_EPI_GELU 1      /* out = acc + bias (pre-activation), out2 = gelu(out) (bf16|f32)                */
+#define VSX_EPI_GELU 1      /* u = acc + bias; out = gelu'(u), out2 = gelu(u)     (bf16|f32; u itself is not stored) */
 #define VSX_EPI_RESIDUAL 2  /* out = aux + [n < n_keep] * row_scale[sample] * (acc + bias)   (f32, aux f32)  */
-#define VSX_EPI_GELUGRAD 3  /* out = acc * gelu'(aux)                             (out, aux: bf16|f32)       */
+#define VSX_EPI_GELUGRAD 3  /* out = acc * aux, aux = the gelu'(u) VSX_EPI_GELU stored (out, aux: bf16|f32)  */
 #define VSX_EPI_ATOMIC 4    /* out += acc (fp32 atomics; weight gradients, split-K over the reduction)      */
 
 typedef struct vsx_gemm_desc {

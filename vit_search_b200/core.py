@@ -458,7 +458,8 @@ def mlp_half_backward(meta, g_out, saved, x, ln_w, ln_b, fc1_w, fc1_b, fc2_w, fc
         # dW2[ck, ik] += df^T h : launched together with dW1 below
         wgrads = [((a_df, a_h, C, F, ck, s.ik, rows, ops.EPI_ATOMIC, d_w2, F),
                    dict(a_off=r0 * C, b_off=r0 * F, a_layout=ops.MNMAJOR, b_layout=ops.MNMAJOR, split_k=split_k_for(ck, s.ik, rows)))]
-        # du[rows, ik] = (df[rows, ck] W2[ck, ik]) * gelu'(u)
+        # du[rows, ik] = (df[rows, ck] W2[ck, ik]) * gelu'(pre-activation): `u` holds that derivative (the fc1 epilogue stores it
+        # instead of the pre-activation)
         ops.gemm(a_df, w2, C, F, rows, s.ik, ck, ops.EPI_GELUGRAD, du, F, a_off=r0 * C, out_off=r0 * F, n_out=up8(s.ik), aux=u,
                  ld_aux=F, aux_off=r0 * F, b_layout=ops.MNMAJOR, colsum=d_b1)
         a_du = acts.get(du, F, r0, rows, s.ik)

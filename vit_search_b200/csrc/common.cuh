@@ -255,6 +255,28 @@ __device__ __forceinline__ f32x2 poly_gelu_grad2(float x0, float x1) {
   p = fma2(p, s, pk2(1.594292470e-01f, 1.594292470e-01f));
   return fma2(xc, p, pk2(0.5f, 0.5f));
 }
+// in place on 32 values: d = gelu'(v), v = gelu(v): both polynomials share the clamp and s, and their two Horner chains interleave
+__device__ __forceinline__ void gelu_and_grad32(float (&v)[32], float (&d)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const f32x2 xc = pk2(fminf(fmaxf(v[j], -4.5f), 4.5f), fminf(fmaxf(v[j + 1], -4.5f), 4.5f));
+    const f32x2 s = fma2(mul2(xc, xc), pk2(0.0987654321f, 0.0987654321f), pk2(-1.0f, -1.0f));
+    f32x2 p = pk2(1.074221019e-03f, 1.074221019e-03f), q = pk2(-6.985080961e-03f, -6.985080961e-03f);
+    q = fma2(q, s, pk2(1.433847597e-02f, 1.433847597e-02f));
+    p = fma2(p, s, pk2(-2.304612824e-03f, -2.304612824e-03f)), q = fma2(q, s, pk2(-1.157771896e-02f, -1.157771896e-02f));
+    p = fma2(p, s, pk2(2.497475973e-03f, 2.497475973e-03f)), q = fma2(q, s, pk2(2.306988463e-02f, 2.306988463e-02f));
+    p = fma2(p, s, pk2(-5.324486247e-03f, -5.324486247e-03f)), q = fma2(q, s, pk2(-5.256838405e-02f, -5.256838405e-02f));
+    p = fma2(p, s, pk2(1.161688181e-02f, 1.161688181e-02f)), q = fma2(q, s, pk2(7.393936118e-02f, 7.393936118e-02f));
+    p = fma2(p, s, pk2(-1.897149445e-02f, -1.897149445e-02f)), q = fma2(q, s, pk2(-8.730810965e-02f, -8.730810965e-02f));
+    p = fma2(p, s, pk2(2.822568407e-02f, 2.822568407e-02f)), q = fma2(q, s, pk2(9.659937234e-02f, 9.659937234e-02f));
+    p = fma2(p, s, pk2(-4.012141573e-02f, -4.012141573e-02f)), q = fma2(q, s, pk2(-9.497554799e-02f, -9.497554799e-02f));
+    p = fma2(p, s, pk2(5.470778012e-02f, 5.470778012e-02f)), q = fma2(q, s, pk2(8.712603100e-02f, 8.712603100e-02f));
+    p = fma2(p, s, pk2(-7.719306673e-02f, -7.719306673e-02f)), q = fma2(q, s, pk2(-8.996616928e-02f, -8.996616928e-02f));
+    p = fma2(p, s, pk2(1.569048135e-01f, 1.569048135e-01f)), q = fma2(q, s, pk2(1.594292470e-01f, 1.594292470e-01f));
+    unpk2(fma2(xc, q, pk2(0.5f, 0.5f)), d[j], d[j + 1]);
+    unpk2(mul2(pk2(v[j], v[j + 1]), fma2(xc, p, pk2(0.5f, 0.5f))), v[j], v[j + 1]);
+  }
+}
 // in place on 32 values: v = gelu(v)   /   v = v * gelu'(u)
 __device__ __forceinline__ void gelu_fast32(float (&v)[32]) {
 #pragma unroll

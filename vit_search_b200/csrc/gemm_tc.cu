@@ -538,14 +538,21 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 #pragma unroll
               for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] + bs[c + jj] : 0.f;
             }
-            stage_write32<OutT>(tile, row, c, v);
+            // out = gelu'(pre-activation), out2 = gelu(pre-activation): both from the fp32 accumulator, so the backward's data gradient
+            // only multiplies by the stored derivative (no transcendental math, no bf16-rounded pre-activation in the backward)
+            float d[32];
             if (sizeof(OutT) == 2) {
-              gelu_fast32(v);                                                 // bf16 training path: packed fp32x2 math
+              gelu_and_grad32(v, d);                                          // bf16 training path: packed fp32x2 polynomials
             } else {
 #pragma unroll
-              for (int jj = 0; jj < 32; ++jj) v[jj] = gelu_sel<OutT>(v[jj]);   // gelu(0) = 0 keeps the zero fill
+              for (int jj = 0; jj < 32; ++jj) d[jj] = gelu_grad_sel<OutT>(v[jj]), v[jj] = gelu_sel<OutT>(v[jj]);
             }
-            stage_write32<OutT>(tile2, row, c, v);
+            if (!full) {                                                      // gelu'(0) = 0.5: the zero fill beyond N is explicit
+#pragma unroll
+              for (int jj = 0; jj < 32; ++jj) d[jj] = (n + jj < g.N) ? d[jj] : 0.f;
+            }
+            stage_write32<OutT>(tile, row, c, d);
+            stage_write32<OutT>(tile2, row, c, v);                            // gelu(0) = 0 keeps the zero fill
           } else if (EPI == VSX_EPI_RESIDUAL) {
             float r[32];
             stage_read32<float>(tile, row, c, r);
@@ -558,14 +565,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
             }
             stage_write32<float>(tile, row, c, r);
           } else if (EPI == VSX_EPI_GELUGRAD) {
-            float u[32];
+            float u[32];                                                       // aux = gelu'(pre-activation), stored by the forward
             stage_read32<OutT>(tile, row, c, u);
-            if (sizeof(OutT) == 2) {
-              gelu_grad_fast32(v, u);                                                // computed for every column, masked below
-            } else {
 #pragma unroll
-              for (int jj = 0; jj < 32; ++jj) v[jj] *= gelu_grad_sel<OutT>(u[jj]);
-            }
+            for (int jj = 0; jj < 32; ++jj) v[jj] *= u[jj];
             if (!full) {
 #pragma unroll
               for (int jj = 0; jj < 32; ++jj) v[jj] = (n + jj < g.N) ? v[jj] : 0.f;
