@@ -170,18 +170,24 @@ class ClockSampler:
         return out
 
 
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
 def _synthetic_batch(B, rank, dev):
-    """ImageNet-shaped synthetic batch: pinned host tensors (images fp32 [B,3,224,224], soft targets [B,1000], per-patch soft targets
-    [B,16,1000] as SwitchTokenMix produces them) and device-resident copies."""
+    """ImageNet-shaped synthetic batch: pinned host tensors (images uint8 [B,3,224,224] as a decoder produces them AND the fp32 batch
+    ToTensor + Normalize makes of them, soft targets [B,1000], per-patch soft targets [B,16,1000] as SwitchTokenMix produces them) and
+    device-resident copies of the fp32 images and the targets."""
     import torch
     g = torch.Generator().manual_seed(1234 + rank)
-    hx = torch.randn(B, 3, 224, 224, generator=g).pin_memory()
+    hu8 = torch.randint(0, 256, (B, 3, 224, 224), generator=g, dtype=torch.uint8).pin_memory()
+    mean, std = torch.tensor(IMAGENET_MEAN).view(1, 3, 1, 1), torch.tensor(IMAGENET_STD).view(1, 3, 1, 1)
+    hx = ((hu8.float() / 255.0 - mean) / std).pin_memory()
     y = torch.randint(0, 1000, (B,), generator=g)
     ht = torch.full((B, 1000), 0.1 / 1000)
     ht[torch.arange(B), y] += 0.9
     hpt = ht.unsqueeze(1).repeat(1, 16, 1).contiguous().pin_memory()
     ht = ht.pin_memory()
-    return (hx, ht, hpt), (hx.to(dev), ht.to(dev), hpt.to(dev))
+    return (hx, ht, hpt, hu8), (hx.to(dev), ht.to(dev), hpt.to(dev))
 
 
 def _timed_steps(fn, n, world, dev):
@@ -339,7 +345,7 @@ def run_ours(args):
         broadcast_parameters(model)
     opt = FusedAdamW(model, lr=LR * B * world / 512.0, weight_decay=WD)
     step = TrainStep(model, opt, arch_sample='single', world_size=world, ddp_model=net if (world > 1 and use_ddp) else None)
-    (hx, ht, hpt), (x, t, pt) = _synthetic_batch(B, rank, dev)
+    (hx, ht, hpt, hu8), (x, t, pt) = _synthetic_batch(B, rank, dev)
     step_macs = []
 
     def dev_step():
@@ -349,16 +355,22 @@ def run_ours(args):
     h_loss = torch.empty((), dtype=torch.float32).pin_memory()
 
     # end to end through the public API: every step uploads its own batch from pinned host memory (engine.DeviceFeeder: side
-    # stream, two device slots, so batch i+1 travels while batch i computes) and reads the loss back
+    # stream, two device slots, so batch i+1 travels while batch i computes) and reads the loss back.  Images travel as uint8 (what a
+    # decoder produces: 1 byte per pixel) and ToTensor + Normalize runs on the device (vsx_image_normalize_u8); the fp32-image variant
+    # (the reference's engine.py:104-105 uploads 4 bytes per pixel) is timed as well.
     from vit_search_b200.engine import DeviceFeeder
-    feeder = DeviceFeeder(dev)
+    feeder = DeviceFeeder(dev, normalize=(IMAGENET_MEAN, IMAGENET_STD))
+    feeder32 = DeviceFeeder(dev)
 
-    def e2e_step():
-        feeder.submit(hx, ht, hpt)             # batch i+1 (the first call of a window primes the pipeline with an extra submit)
-        xs, ts, pts = feeder.next()
-        loss = step(xs, ts, pts, epoch=0)
-        feeder.release()
-        h_loss.copy_(loss, non_blocking=True)
+    def make_e2e(fd, himg):
+        def e2e_step():
+            fd.submit(himg, ht, hpt)               # batch i+1 (the first call of a window primes the pipeline with an extra submit)
+            xs, ts, pts = fd.next()
+            loss = step(xs, ts, pts, epoch=0)
+            fd.release()
+            h_loss.copy_(loss, non_blocking=True)
+        return e2e_step
+    e2e_step, e2e_step32 = make_e2e(feeder, hu8), make_e2e(feeder32, hx)
 
     n_warm = max(args.warmup, 3)                          # exactly the driver's W (the contract asks for W >= 3)
     clocks = ClockSampler(local) if rank == 0 else None   # started before the warm-up: nvidia-smi needs ~0.2 s to deliver its first sample
@@ -376,6 +388,10 @@ def run_ours(args):
     e2e_step()
     ms_e2e, per_step_e2e = _timed_steps(e2e_step, args.steps, world, dev)       # K steps = K uploads + K train steps + K loss read-backs
     feeder.next(), feeder.release()            # drain the batch left in flight
+    feeder32.submit(hx, ht, hpt)
+    e2e_step32()
+    ms_e2e32, _ = _timed_steps(e2e_step32, args.steps, world, dev)
+    feeder32.next(), feeder32.release()
     torch.cuda.synchronize()
     gc.enable()
     loss_val = float(h_loss)
@@ -412,8 +428,11 @@ def run_ours(args):
                        l2='inputs larger than L2: every step streams >10 GB of activations, no tensor survives in the 126 MB L2',
                        timing='one CUDA event per step boundary; ms_per_step = window / K (the value), ms_per_step_p50 = median of the K step times of rank 0'),
             'e2e': {'value': world * B * args.steps / (ms_e2e * 1e-3), 'unit': 'images/sec',
-                    'h2d_bytes_per_step': hx.numel() * 4 + ht.numel() * 4 + hpt.numel() * 4, 'd2h_bytes_per_step': 4,
-                    'ms_per_step': ms_e2e / args.steps, 'ms_per_step_p50': _p50(per_step_e2e)},
+                    'h2d_bytes_per_step': hu8.numel() + ht.numel() * 4 + hpt.numel() * 4, 'd2h_bytes_per_step': 4,
+                    'ms_per_step': ms_e2e / args.steps, 'ms_per_step_p50': _p50(per_step_e2e),
+                    'input': 'uint8 images [B,3,224,224] + fp32 soft targets from pinned host memory; ToTensor + Normalize on the device',
+                    'fp32_image_input': {'value': world * B * args.steps / (ms_e2e32 * 1e-3), 'ms_per_step': ms_e2e32 / args.steps,
+                                         'h2d_bytes_per_step': hx.numel() * 4 + ht.numel() * 4 + hpt.numel() * 4}},
             'gpu_launches': launches,
             'roofline': {'bound': 'tensor', 'kernel': 'gemm_tc_kernel (tcgen05 GEMM, all epilogues: fwd, dgrad, wgrad; single-CTA and cta_group::2 tiles)',
                          'achieved': achieved, 'peak': pk['tflops'], 'unit': 'TFLOP/s', 'frac': achieved / pk['tflops'],

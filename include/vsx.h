@@ -331,6 +331,12 @@ int vsx_token_mix(const float* samples, float* out, const long* labels, const in
 int vsx_eval_metrics(const float* logits, long ld, const long* labels, int rows, int cols, float* row_loss, int* row_rank, double* totals,
                      void* stream);
 
+/* Input side of the step (engine.py:104-105 uploads fp32 images: 4 bytes per pixel).  vsx_image_normalize_u8 does torchvision's
+ * ToTensor + Normalize on the device: out[i, c, p] = (in[i, c, p] / 255 - mean[c]) / std[c] for a uint8 batch [images, channels, pixels]
+ * (mean / std: HOST arrays of `channels` floats), so that the per-step upload is 1 byte per pixel (engine.DeviceFeeder(normalize=...)). */
+int vsx_image_normalize_u8(const void* in_u8, float* out, int images, int channels, long pixels, const float* mean, const float* stdv,
+                           void* stream);
+
 /* ----------------------------------------------------------------------------------------------------
  * Several extents in ONE launch: a batch that carries several sub-architectures (the multi-architectural sampling of
  * nets/channel_drop.py:93-111: sample i uses mask row perm[i % G]) is a sequence of row ranges ("segments": consecutive samples that

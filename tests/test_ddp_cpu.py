@@ -42,6 +42,28 @@ def _worker(rank, world, port, q):
     exchange_pool_gradients(flat, off, first, ps)
     ok = ok and all(torch.allclose(p.grad, torch.full_like(p, 3.0 * (i + 1))) for i, p in enumerate(ps))
     ok = ok and all(p.grad.data_ptr() >= flat.data_ptr() and p.grad.data_ptr() < flat.data_ptr() + 4 * off for p in ps[:3])
+    # the gradient that lived outside the pool was moved behind it (one collective, stable addresses) ...
+    ok = ok and flat.data_ptr() + 4 * off <= ps[3].grad.data_ptr() < flat.data_ptr() + 4 * flat.numel()
+    # ... and the staged exchange driven by the stage-backward hooks: prefixes of the pool are reduced as they become final
+    from vit_search_b200 import core
+    from vit_search_b200.engine import StagedExchange
+    flat2 = torch.zeros(4096)
+    core.grad_pool.flat, core.grad_pool.off = flat2, 0
+    ex = StagedExchange(flat2, None, min_elems=256)
+    a = core.grad_pool.take(1000, flat2.device)
+    a.fill_(float(rank + 1))
+    ex.prefix_ready()                       # 1000 elements final -> exchanged
+    b = core.grad_pool.take(100, flat2.device)
+    b.fill_(10.0 * (rank + 1))
+    ex.prefix_ready()                       # too small: rides along with the next range
+    c = core.grad_pool.take(600, flat2.device)
+    c.fill_(100.0 * (rank + 1))
+    ex.tensor_hook(None)                    # the trunk hook
+    used = core.grad_pool.off
+    ok = ok and ex.calls == 2 and ex.done == used == 1700
+    exchange_pool_gradients(flat2, used, ex.done, [])
+    ok = ok and bool((a == 3.0).all() and (b == 30.0).all() and (c == 300.0).all()) and bool((flat2[1700:] == 0).all())
+    core.grad_pool.end()
     q.put((rank, ok))
     dist.destroy_process_group()
 

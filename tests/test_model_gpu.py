@@ -428,3 +428,22 @@ def test_finite_loss_guard_skips_the_update_on_the_device():
             assert torch.equal(v[0], m1[k]), k
         with pytest.raises(FloatingPointError, match='not finite'):
             step.check_finite()
+
+
+def test_device_feeder_uint8_normalize():
+    """DeviceFeeder(normalize=(mean, std)): a uint8 image batch uploaded as 1 byte per pixel comes out as the fp32 batch torchvision's
+    ToTensor + Normalize would have produced on the host; the other tensors of the batch pass through unchanged."""
+    from vit_search_b200.engine import DeviceFeeder
+    mean, std = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+    dev = torch.device('cuda', 0)
+    feeder = DeviceFeeder(dev, normalize=(mean, std))
+    g = torch.Generator().manual_seed(0)
+    for it in range(3):
+        u8 = torch.randint(0, 256, (5, 3, 224, 224), generator=g, dtype=torch.uint8).pin_memory()
+        tgt = torch.randn(5, 10, generator=g).pin_memory()
+        feeder.submit(u8, tgt)
+        x, t = feeder.next()
+        ref = (u8.float() / 255.0 - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+        assert x.dtype == torch.float32 and (x.cpu() - ref).abs().max().item() < 1e-6
+        assert torch.equal(t.cpu(), tgt)
+        feeder.release()

@@ -59,6 +59,7 @@ SIGNATURES = {
     'vsx_split_bf16': [_p, _l, _p, _p, _p, _l, _i, _i, _p],
     'vsx_scale_mask_cast': [_p, _l, _p, _i, _i, _p, _i, _l, _i, _i, _p, _p],
     'vsx_colsum': [_p, _i, _l, _i, _i, _p, _p],
+    'vsx_image_normalize_u8': [_p, _p, _i, _i, _l, _p, _p, _p],
     'vsx_im2col': [_p, _p, _p, _p, _p, _p, _i, _i, _l, _l, _i, _i, _i, _i, _i, _i, _i, _p, _i, _l, _p],
     'vsx_col2im': [_p, _l, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _l, _l, _p],
     'vsx_bn_stats': [_p, _i, _l, _i, _p, _p],

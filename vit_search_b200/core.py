@@ -203,6 +203,8 @@ class _GradPool:
 
 grad_pool = _GradPool()
 trunk_grads_ready_hook = None    # set by engine.TrainStep for data-parallel runs (see nets/vit_sr_supernet.py forward_features)
+pool_prefix_ready_hook = None    # set by engine.TrainStep for data-parallel runs: called (no arguments) whenever a stage's backward has been
+                                 # queued, i.e. grad_pool.flat[:grad_pool.off] is final -- the staged gradient exchange starts there
 
 
 def zeros_like_many(*tensors):
@@ -750,4 +752,6 @@ class StageFn(torch.autograd.Function):
                                           *[t.data_ptr() for t in gi], 1 if fuse[i] else 0, *nxt)
         ops._ck(_lib.lib().vsx_stage_bwd(descs, n, ops._stream()))
         ctx.keep = None
+        if pool_prefix_ready_hook is not None:
+            pool_prefix_ready_hook()        # every gradient carved from the pool so far is final: the data-parallel exchange of that prefix may start
         return (None, gbuf[0]) + tuple(grads)

@@ -263,7 +263,7 @@ class TrainStep:
         self._native_dp = world_size > 1 and ddp_model is None
         self._comm_stream = None
         self._inv_world = None
-        self._hook_off = 0
+        self._exchange = None
 
     def __call__(self, samples, targets, patch_targets, epoch=0):
         """samples [B,3,224,224], targets [B,K], patch_targets [B,16,K] on the GPU.  Returns the loss as a device scalar
@@ -295,6 +295,7 @@ class TrainStep:
         finally:
             core.grad_pool.end()
             core.trunk_grads_ready_hook = None
+            core.pool_prefix_ready_hook = None
         if self.nonfinite is None:
             self.nonfinite = torch.zeros(1, dtype=torch.int32, device=samples.device)
         if hasattr(self.optimizer, 'guard'):
@@ -323,42 +324,78 @@ class TrainStep:
 
     # ------------------------------------------------------------------ native data parallelism
     def _arm_overlap(self, flat):
-        import torch.distributed as dist
-        if self._comm_stream is None:
+        if self._comm_stream is None and flat.is_cuda:
             self._comm_stream = torch.cuda.Stream(device=flat.device)
+        if self._inv_world is None:
             self._inv_world = torch.full((1,), 1.0 / self.world_size, device=flat.device)
-        self._hook_off = 0
-
-        def hook(grad):
-            # gradients of every block are complete in flat[:off]; the stem backward that follows only appends behind `off`
-            off = core.grad_pool.off
-            if off > 0:
-                ready = torch.cuda.Event()
-                ready.record()
-                with torch.cuda.stream(self._comm_stream):
-                    self._comm_stream.wait_event(ready)
-                    dist.all_reduce(flat[:off])
-                self._hook_off = off
-            return grad
-        core.trunk_grads_ready_hook = hook
+        ex = StagedExchange(flat, self._comm_stream)
+        self._exchange = ex
+        core.pool_prefix_ready_hook = ex.prefix_ready       # after every stage's backward (stage 3 holds 60 % of the gradient bytes
+        core.trunk_grads_ready_hook = ex.tensor_hook        # and is final a fifth of the way into the backward) and before the stem
 
     def _finish_allreduce(self, flat, used):
-        exchange_pool_gradients(flat, used, self._hook_off, self.model.parameters(), self._comm_stream)
+        core.pool_prefix_ready_hook = None
+        exchange_pool_gradients(flat, used, self._exchange.done, self.model.parameters(), self._comm_stream)
+
+
+class StagedExchange:
+    """Gradient all-reduce (SUM) of the per-step gradient pool in stages (the reference's DDP overlaps bucket all-reduces with the
+    backward, main.py:366-368): every gradient of a step is a view of ONE flat buffer that fills from the front in backward order
+    (heads, stage 3, SR, stage 2, SR, stage 1, stem), so whenever a stage's backward has been queued the prefix flat[:off] is final
+    and its not-yet-exchanged part goes to NCCL on a side stream while the earlier stages' backward keeps the SMs busy."""
+
+    def __init__(self, flat, comm_stream=None, min_elems=1 << 20):
+        self.flat, self.comm, self.done, self.min_elems = flat, comm_stream, 0, min_elems
+        self.calls = 0
+
+    def prefix_ready(self):
+        import torch.distributed as dist
+        off = core.grad_pool.off
+        if off - self.done < self.min_elems:          # tiny ranges ride along with the next one
+            return
+        if self.comm is not None:
+            ready = torch.cuda.Event()
+            ready.record()
+            with torch.cuda.stream(self.comm):
+                self.comm.wait_event(ready)
+                dist.all_reduce(self.flat[self.done:off])
+        else:
+            dist.all_reduce(self.flat[self.done:off])
+        self.done = off
+        self.calls += 1
+
+    def tensor_hook(self, grad):
+        self.prefix_ready()
+        return grad
 
 
 def exchange_pool_gradients(flat, used, reduced_upto, params, comm_stream=None):
     """SUM all-reduce of one step's gradients: flat[reduced_upto:used] in place (flat[:reduced_upto] was already put on
-    `comm_stream` by the backward hook), plus one small flattened bucket for gradients that do not live in the pool (re-laid-out conv
-    weights, BN affine parameters).  The 1/world factor is applied by the optimizer kernel (FusedAdamW.step(grad_scale=...))."""
+    `comm_stream` by the backward hooks).  Gradients that do not live in the pool (re-laid-out conv weights, BN affine parameters:
+    a few hundred KB) are first moved behind `used` -- one multi-tensor copy, p.grad re-pointed at the pool views -- so that ONE
+    collective finishes the step and every gradient address is the same in every step.  The 1/world factor is applied by the
+    optimizer kernel (FusedAdamW.step(grad_scale=...))."""
     import torch.distributed as dist
+    lo, hi = flat.data_ptr(), flat.data_ptr() + used * flat.element_size()
+    rest = [p for p in params if p.grad is not None and not (lo <= p.grad.data_ptr() < hi)]
+    if rest:
+        need = sum((p.grad.numel() + 3) // 4 * 4 for p in rest)
+        if used + need <= flat.numel() and all(p.grad.dtype == flat.dtype for p in rest):
+            views, off = [], used
+            for p in rest:
+                views.append(flat[off:off + p.grad.numel()].view(p.grad.shape))
+                off += (p.grad.numel() + 3) // 4 * 4
+            torch._foreach_copy_(views, [p.grad for p in rest])
+            for p, v in zip(rest, views):
+                p.grad = v
+            used, rest = off, []
     if used > reduced_upto:
         dist.all_reduce(flat[reduced_upto:used])
-    lo, hi = flat.data_ptr(), flat.data_ptr() + used * flat.element_size()
-    rest = [p.grad for p in params if p.grad is not None and not (lo <= p.grad.data_ptr() < hi)]
-    if rest:
-        bucket = torch._utils._flatten_dense_tensors(rest)
+    if rest:                                  # no room behind the pool (foreign tensors): one flattened bucket
+        grads = [p.grad for p in rest]
+        bucket = torch._utils._flatten_dense_tensors(grads)
         dist.all_reduce(bucket)
-        for g, f in zip(rest, torch._utils._unflatten_dense_tensors(bucket, rest)):
+        for g, f in zip(grads, torch._utils._unflatten_dense_tensors(bucket, grads)):
             g.copy_(f)
     if comm_stream is not None and flat.is_cuda:
         torch.cuda.current_stream(flat.device).wait_stream(comm_stream)   # the overlapped part must have landed before the optimizer
@@ -382,25 +419,44 @@ class DeviceFeeder:
         x, t, pt = feeder.next()                              # device tensors of batch i (waits only for its copy)
     """
 
-    def __init__(self, device):
+    def __init__(self, device, normalize=None):
+        """normalize=(mean, std) (per-channel sequences): uint8 image batches [B, C, H, W] submitted as the FIRST tensor are converted on
+        the device, on the upload stream, to the fp32 batch torchvision's ToTensor + Normalize would have produced on the host
+        (vsx_image_normalize_u8) -- the step then uploads 1 byte per pixel instead of 4."""
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(device=self.device)
         self.slots = [None, None]
+        self.staging = [None, None]                              # uint8 device copies of the image batch (normalize mode)
         self.events = [torch.cuda.Event(), torch.cuda.Event()]
         self.free = [torch.cuda.Event(), torch.cuda.Event()]     # recorded on the compute stream when a slot's step has been queued
         self.used = [False, False]
         self.head = self.tail = 0
+        self.normalize = None
+        if normalize is not None:
+            mean, std = normalize
+            self.normalize = ((C.c_float * len(mean))(*[float(v) for v in mean]), (C.c_float * len(std))(*[float(v) for v in std]))
 
     def submit(self, *host_tensors):
         i = self.head & 1
         assert self.head - self.tail < 2, 'DeviceFeeder: two batches are already in flight'
+        u8 = self.normalize is not None and host_tensors[0].dtype == torch.uint8
         with torch.cuda.stream(self.stream):
             if self.used[i]:
                 self.stream.wait_event(self.free[i])        # the step that read this slot has finished
-            if self.slots[i] is None or any(d.shape != h.shape or d.dtype != h.dtype for d, h in zip(self.slots[i], host_tensors)):
-                self.slots[i] = tuple(torch.empty(h.shape, dtype=h.dtype, device=self.device) for h in host_tensors)
-            for d, h in zip(self.slots[i], host_tensors):
-                d.copy_(h, non_blocking=True)
+            want = [(h.shape, torch.float32 if (u8 and j == 0) else h.dtype) for j, h in enumerate(host_tensors)]
+            if self.slots[i] is None or [(d.shape, d.dtype) for d in self.slots[i]] != want:
+                self.slots[i] = tuple(torch.empty(sh, dtype=dt, device=self.device) for sh, dt in want)
+            for j, (d, h) in enumerate(zip(self.slots[i], host_tensors)):
+                if u8 and j == 0:
+                    st = self.staging[i]
+                    if st is None or st.shape != h.shape:
+                        st = self.staging[i] = torch.empty(h.shape, dtype=torch.uint8, device=self.device)
+                    st.copy_(h, non_blocking=True)
+                    B_, C_ = h.shape[0], h.shape[1]
+                    _lib.check(_lib.lib().vsx_image_normalize_u8(st.data_ptr(), d.data_ptr(), B_, C_, h[0, 0].numel(), self.normalize[0], self.normalize[1],
+                                                                 self.stream.cuda_stream))
+                else:
+                    d.copy_(h, non_blocking=True)
             self.events[i].record(self.stream)
         self.head += 1
 
