@@ -760,12 +760,20 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
           v.x = a.lse[((long)b * a.H + h) * N + r] * LOG2E_F;
           const bf16* op = a.o + ((long)b * N + r) * HD + h * D;
           const bf16* dp = a.d_o + ((long)b * N + r) * HD + h * D;
+          // all (up to) 16 row loads are issued before the first use: a loop over the runtime head dim would serialise their latencies
+          uint4 ov[8], dv[8];
+#pragma unroll
+          for (int c8 = 0; c8 < 8; ++c8) {
+            ov[c8] = make_uint4(0u, 0u, 0u, 0u), dv[c8] = make_uint4(0u, 0u, 0u, 0u);
+            if (c8 * 8 < D) {
+              ov[c8] = *reinterpret_cast<const uint4*>(op + c8 * 8);
+              dv[c8] = *reinterpret_cast<const uint4*>(dp + c8 * 8);
+            }
+          }
           float acc = 0.f;
 #pragma unroll
-          for (int cc = 0; cc < D; cc += 8) {
-            const uint4 ov = *reinterpret_cast<const uint4*>(op + cc);
-            const uint4 dv = *reinterpret_cast<const uint4*>(dp + cc);
-            const uint32_t ow[4] = {ov.x, ov.y, ov.z, ov.w}, dw[4] = {dv.x, dv.y, dv.z, dv.w};
+          for (int c8 = 0; c8 < 8; ++c8) {
+            const uint32_t ow[4] = {ov[c8].x, ov[c8].y, ov[c8].z, ov[c8].w}, dw[4] = {dv[c8].x, dv[c8].y, dv[c8].z, dv[c8].w};
 #pragma unroll
             for (int t = 0; t < 4; ++t) {
               const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&ow[t]));
@@ -788,7 +796,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
     if (slot < NB) make_stats(sample_of(a.segs, h, slot), 0);
     for (int v = slot; v < NB; v += nslots, ++pair) {
       const int b = sample_of(a.segs, h, v);
-      if (v + nslots < NB) make_stats(sample_of(a.segs, h, v + nslots), (pair + 1) & 1);
       float csum[2][32];              // this thread's rows, summed over the key blocks of the pair: the butterfly runs once per pair
 #pragma unroll
       for (int t = 0; t < 32; ++t) csum[0][t] = 0.f, csum[1][t] = 0.f;
@@ -817,6 +824,10 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(BAR_DKV_EMPTY + nkv % nbuf));
+        // statistics of the NEXT pair: ~3 x 128 rows x (lse + 128 B of O + 128 B of dO) of latency-bound global loads.  Issued after the first
+        // accumulator drain of this pair -- at the top of the loop they delayed that drain, on which the MMA thread waits before it may
+        // overwrite dV / dK (tools/attn_timeline.py: 4000 - 9500 clocks of stall per pair)
+        if (j == 0 && v + nslots < NB) make_stats(sample_of(a.segs, h, v + nslots), (pair + 1) & 1);
       }
       if (a.dbias != nullptr) {
 #pragma unroll
