@@ -21,6 +21,16 @@ void attn_set_debug(long long* p);
 
 using namespace vsx;
 
+// Which bf16 kernel serves a shape.  The tcgen05 kernels work on 128-query tiles: at N = 17 (stage 3) a (sample, head) pair fills 13 % of
+// a tile and every pair still pays the full TMA -> MMA -> softmax -> MMA -> drain chain, so the register-resident mma.sync kernel is
+// faster there (B = 256, H = 12, D = 64, tools/attn_bench.py: forward 13.4 vs 32.8 us, backward 61 vs 104 us); from N = 65 up the
+// tensor-memory kernels win (backward 94 vs 201 us at N = 65, 184 vs 389 us at N = 257).
+static bool prefer_tc(int impl, int tokens, int head_dim) {
+  if (!attn_tc_supported(tokens, head_dim)) return false;
+  if (impl == VSX_ATTN_IMPL_TCGEN05) return true;
+  return impl == VSX_ATTN_IMPL_AUTO && !(tokens <= 32 && attn_mma_supported(tokens, head_dim));
+}
+
 static int check_shape(const char* what, int B, int N, int H, int D, int Hk) {
   VSX_REQUIRE(B >= 0 && N > 0 && H > 0 && Hk >= 0 && Hk <= H, "%s: bad shape batch=%d tokens=%d heads=%d heads_keep=%d", what, B, N, H, Hk);
   VSX_REQUIRE(D % 4 == 0 && D > 0 && D <= 64, "%s: head_dim must be a multiple of 4 and <= 64 (got %d)", what, D);
@@ -35,8 +45,7 @@ extern "C" int vsx_attn_fwd(const void* qkv, void* o, float* lse, int dtype, int
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (dtype == VSX_F32) return attn_fwd_ref<float>(qkv, o, lse, batch, tokens, heads, head_dim, heads_keep, scale, st);
   if (dtype == VSX_BF16) {
-    if ((impl == VSX_ATTN_IMPL_AUTO || impl == VSX_ATTN_IMPL_TCGEN05) && attn_tc_supported(tokens, head_dim))
-      return attn_fwd_tc(qkv, o, lse, batch, tokens, heads, head_dim, heads_keep, scale, st);
+    if (prefer_tc(impl, tokens, head_dim)) return attn_fwd_tc(qkv, o, lse, batch, tokens, heads, head_dim, heads_keep, scale, st);
     VSX_REQUIRE(impl != VSX_ATTN_IMPL_TCGEN05, "vsx_attn_fwd: the tcgen05 kernel needs head_dim 32 / 48 / 64 and tokens <= 288 (got %d, %d)", head_dim, tokens);
     if (impl != VSX_ATTN_IMPL_FP32 && attn_mma_supported(tokens, head_dim))
       return attn_fwd_mma(qkv, o, lse, batch, tokens, heads, head_dim, heads_keep, scale, st);
@@ -61,8 +70,7 @@ extern "C" int vsx_attn_bwd(const void* qkv, const void* o, const void* d_o, con
     return rc;
   }
   if (dtype == VSX_BF16) {
-    if ((impl == VSX_ATTN_IMPL_AUTO || impl == VSX_ATTN_IMPL_TCGEN05) && attn_tc_supported(tokens, head_dim))
-      return attn_bwd_tc(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, heads_keep, scale, dbias, st);
+    if (prefer_tc(impl, tokens, head_dim)) return attn_bwd_tc(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, heads_keep, scale, dbias, st);
     VSX_REQUIRE(impl != VSX_ATTN_IMPL_TCGEN05, "vsx_attn_bwd: the tcgen05 kernel needs head_dim 32 / 48 / 64 and tokens <= 288 (got %d, %d)", head_dim, tokens);
     if (impl != VSX_ATTN_IMPL_FP32 && attn_mma_supported(tokens, head_dim))
       return attn_bwd_mma(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, heads_keep, scale, dbias, st);
@@ -95,7 +103,7 @@ extern "C" int vsx_attn_fwd_segs(const void* qkv, void* o, float* lse, int dtype
   if (rc) return rc;
   if ((rc = check_shape("vsx_attn_fwd_segs", batch, tokens, heads, head_dim, hmax))) return rc;
   if (batch == 0 || hmax == 0) return VSX_OK;
-  if (dtype == VSX_BF16 && (impl == VSX_ATTN_IMPL_AUTO || impl == VSX_ATTN_IMPL_TCGEN05) && attn_tc_supported(tokens, head_dim))
+  if (dtype == VSX_BF16 && prefer_tc(impl, tokens, head_dim))
     return attn_fwd_tc(qkv, o, lse, batch, tokens, heads, head_dim, hmax, scale, reinterpret_cast<cudaStream_t>(stream), segs);
   const size_t es = dtype == VSX_F32 ? 4 : 2;       // other implementations: one launch per segment
   const long HD = (long)heads * head_dim;
@@ -116,7 +124,7 @@ extern "C" int vsx_attn_bwd_segs(const void* qkv, const void* o, const void* d_o
   if (rc) return rc;
   if ((rc = check_shape("vsx_attn_bwd_segs", batch, tokens, heads, head_dim, hmax))) return rc;
   if (batch == 0 || hmax == 0) return VSX_OK;
-  if (dtype == VSX_BF16 && (impl == VSX_ATTN_IMPL_AUTO || impl == VSX_ATTN_IMPL_TCGEN05) && attn_tc_supported(tokens, head_dim))
+  if (dtype == VSX_BF16 && prefer_tc(impl, tokens, head_dim))
     return attn_bwd_tc(qkv, o, d_o, lse, dqkv, batch, tokens, heads, head_dim, hmax, scale, dbias, reinterpret_cast<cudaStream_t>(stream), segs);
   const size_t es = dtype == VSX_F32 ? 4 : 2;
   const long HD = (long)heads * head_dim;

@@ -796,6 +796,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
     if (slot < NB) make_stats(sample_of(a.segs, h, slot), 0);
     for (int v = slot; v < NB; v += nslots, ++pair) {
       const int b = sample_of(a.segs, h, v);
+      // statistics of the NEXT pair while the MMAs of this one run (moving this behind the first accumulator drain was measured: 4-15 %
+      // slower per launch -- with one key block per pair it delays the dQ drain the next pair's MMAs wait for)
+      if (v + nslots < NB) make_stats(sample_of(a.segs, h, v + nslots), (pair + 1) & 1);
       float csum[2][32];              // this thread's rows, summed over the key blocks of the pair: the butterfly runs once per pair
 #pragma unroll
       for (int t = 0; t < 32; ++t) csum[0][t] = 0.f, csum[1][t] = 0.f;
@@ -824,10 +827,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) attn_bwd_tc_kernel(const __gri
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(bar(BAR_DKV_EMPTY + nkv % nbuf));
-        // statistics of the NEXT pair: ~3 x 128 rows x (lse + 128 B of O + 128 B of dO) of latency-bound global loads.  Issued after the first
-        // accumulator drain of this pair -- at the top of the loop they delayed that drain, on which the MMA thread waits before it may
-        // overwrite dV / dK (tools/attn_timeline.py: 4000 - 9500 clocks of stall per pair)
-        if (j == 0 && v + nslots < NB) make_stats(sample_of(a.segs, h, v + nslots), (pair + 1) & 1);
       }
       if (a.dbias != nullptr) {
 #pragma unroll
