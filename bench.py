@@ -29,6 +29,13 @@ SPACE = 'sr_tiny'
 BATCH = 256
 DROP_PATH = 0.2
 LR, WD = 5e-4, 0.05
+
+
+def bench_lr(batch, world):
+    """The reference scales lr = 5e-4 * global_batch / 512 and reaches it after warm-up epochs (main.py: --lr, --warmup-epochs); a bench of a
+    few dozen steps from random init has no warm-up, so the rate is capped at 5e-4 (at 8 x 256 the uncapped 2e-3 diverges to a non-finite
+    loss within ~10 steps, which TrainStep.check_finite() reports).  The arithmetic per step does not depend on the value."""
+    return min(LR * batch * world / 512.0, LR)
 METRIC = 'images/sec ViT-ResNAS-Tiny supernet train step'
 WORKLOAD = 'ViT-ResNAS-Tiny supernet (supernet_config/sr_tiny) train, 1 arch/step, bs=256/GPU'
 
@@ -238,7 +245,7 @@ def _extra_configs(args, world, rank, dev):
         model.train()
         if world > 1:
             broadcast_parameters(model)
-        opt = FusedAdamW(model, lr=LR * B * world / 512.0, weight_decay=WD)
+        opt = FusedAdamW(model, lr=bench_lr(B, world), weight_decay=WD)
         step = TrainStep(model, opt, arch_sample=mode, world_size=world, model_ema=ema)
         for _ in range(W):
             step(x, t, pt, epoch=0)
@@ -343,7 +350,7 @@ def run_ours(args):
     elif world > 1:
         from vit_search_b200.engine import broadcast_parameters
         broadcast_parameters(model)
-    opt = FusedAdamW(model, lr=LR * B * world / 512.0, weight_decay=WD)
+    opt = FusedAdamW(model, lr=bench_lr(B, world), weight_decay=WD)
     step = TrainStep(model, opt, arch_sample='single', world_size=world, ddp_model=net if (world > 1 and use_ddp) else None)
     (hx, ht, hpt, hu8), (x, t, pt) = _synthetic_batch(B, rank, dev)
     step_macs = []
