@@ -64,6 +64,14 @@ def _worker(rank, world, port, q):
     exchange_pool_gradients(flat2, used, ex.done, [])
     ok = ok and bool((a == 3.0).all() and (b == 30.0).all() and (c == 300.0).all()) and bool((flat2[1700:] == 0).all())
     core.grad_pool.end()
+    # DDP's broadcast_buffers (main.py:366-368): rank 0's BatchNorm running statistics on every rank, float and integer buffers alike
+    from vit_search_b200.engine import broadcast_buffers
+    bn = torch.nn.Sequential(torch.nn.BatchNorm2d(6), torch.nn.BatchNorm2d(3))
+    for i, t in enumerate(bn.buffers()):
+        t.fill_(7 * (rank + 1) + i)
+    broadcast_buffers(bn)
+    ok = ok and all(bool((t == 7 + i).all()) for i, t in enumerate(bn.buffers()))
+    ok = ok and bn[0].num_batches_tracked.dtype == torch.int64
     q.put((rank, ok))
     dist.destroy_process_group()
 

@@ -18,8 +18,17 @@ bias = torch.zeros(768, device='cuda')
 cs = torch.zeros(768, device='cuda')
 
 
+xr = torch.randn(M, 256, device='cuda')
+xo = torch.empty(M, 256, device='cuda')
+Wp = (torch.randn(256, 256, device='cuda') * 0.05).to(torch.bfloat16)
+rs = torch.ones(256, device='cuda')
+
+
 def run():
-    if kind == 'gelugrad':
+    if kind == 'resid':      # proj / fc2 of stage 1: x_new = x + row_scale * mask * (a W^T + b), fp32 residual stream in and out
+        ops.gemm(A, Wp, 256, 256, M, 224, 256, ops.EPI_RESIDUAL, xo, 256, n_out=256, aux=xr, ld_aux=256, bias=bias, row_scale=rs,
+                 rows_per_sample=257, n_keep=224)
+    elif kind == 'gelugrad':
         ops.gemm(A, W, 256, 256, M, N, K, ops.EPI_GELUGRAD, out, 768, n_out=768, aux=u, ld_aux=768, colsum=cs)
     elif kind == 'gelu':
         ops.gemm(A, W, 256, 256, M, N, K, ops.EPI_GELU, out, 768, n_out=768, out2=out2, ldo2=768, bias=bias)

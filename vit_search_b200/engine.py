@@ -243,8 +243,10 @@ class ModelEma:
 class TrainStep:
     """One data-parallel training step, the drop-in for the body of engine.train_one_epoch."""
 
-    def __init__(self, model, optimizer=None, criterion=None, arch_sample='multi', world_size=1, ddp_model=None, model_ema=None):
+    def __init__(self, model, optimizer=None, criterion=None, arch_sample='multi', world_size=1, ddp_model=None, model_ema=None,
+                 broadcast_buffers=True):
         self.model = model
+        self.broadcast_buffers = broadcast_buffers    # native data parallelism only (a DDP wrapper broadcasts its buffers itself)
         self.net = ddp_model if ddp_model is not None else model
         self.optimizer = optimizer if optimizer is not None else FusedAdamW(model)
         self.criterion = criterion if criterion is not None else SoftTargetCrossEntropy()
@@ -270,6 +272,7 @@ class TrainStep:
         (no host sync)."""
         if epoch != self._epoch:                                 # engine.py:100: `train_iter = 0` at the top of every epoch, so the
             self._epoch, self.train_iter = epoch, 0              # sampling seed is epoch * 10000 + iteration-in-epoch
+            self.sync_buffers()
         rng = None
         if self.arch_sample is not None:                         # engine.py:119-131
             rng = torch.random.get_rng_state()
@@ -308,6 +311,12 @@ class TrainStep:
         if self.model_ema is not None:
             self.model_ema.update(self.model)                    # engine.py:179-180
         return loss.detach()
+
+    def sync_buffers(self, src=0):
+        """Rank `src`'s BatchNorm running statistics on every rank (see broadcast_buffers).  Called at the start of every epoch; call it
+        before evaluating or checkpointing on a rank other than `src` in the middle of one."""
+        if self._native_dp and self.broadcast_buffers:
+            broadcast_buffers(self.model, src)
 
     def reset_epoch(self, epoch=None):
         """Start of an epoch (engine.py:100): the sampling seed counts iterations from 0 again."""
@@ -407,6 +416,26 @@ def broadcast_parameters(model, src=0):
     import torch.distributed as dist
     for t in list(model.parameters()) + list(model.buffers()):
         dist.broadcast(t.data, src)
+
+
+def broadcast_buffers(model, src=0):
+    """DistributedDataParallel(broadcast_buffers=True), the reference's setting (main.py:366-368): every rank's buffers -- the BatchNorm
+    running statistics of the conv stem -- are overwritten with rank `src`'s.  DDP does it before every forward; the buffers never enter
+    the training arithmetic (train-mode BatchNorm normalises with batch statistics), and rank `src`'s own copy only ever sees its own
+    batches either way, so doing it lazily -- at the start of every epoch and before evaluation / checkpoints (`TrainStep.sync_buffers`)
+    -- leaves every observable state identical.  One collective per dtype: the buffers travel as one flat tensor."""
+    import torch.distributed as dist
+    by_dtype = {}
+    for t in model.buffers():
+        by_dtype.setdefault(t.dtype, []).append(t)
+    for dtype, ts in by_dtype.items():
+        flat = torch.cat([t.detach().reshape(-1) for t in ts])
+        dist.broadcast(flat, src)
+        off = 0
+        with torch.no_grad():
+            for t in ts:
+                t.copy_(flat[off:off + t.numel()].view_as(t))
+                off += t.numel()
 
 
 class DeviceFeeder:
