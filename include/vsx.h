@@ -152,8 +152,14 @@ int vsx_attn_fwd(const void* qkv, void* o, float* lse, int dtype, int batch, int
 int vsx_attn_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, void* dqkv, int dtype, int batch,
                  int tokens, int heads, int head_dim, int heads_keep, float scale, int impl,
                  float* dbias /* NULL, or [3*heads*head_dim]: += column sums of dqkv (the qkv bias gradient) */, void* stream);
-/* Development aid: device buffer of 64 x 8 int64 clock stamps written by CTA 0 of the tcgen05 backward kernel (NULL = off). */
+/* Development aid: device buffer of (64 x 16 + 3 x 160) int64 stamps written by the tcgen05 backward kernel (NULL = off): clock64 stamps of
+ * every warp role of one CTA (VSX_ATTN_DBG_CTA, default 0) and globaltimer start / end / SM id of every CTA (tools/attn_timeline.py). */
 int vsx_attn_debug_buffer(void* buffer);
+/* Development aid (tests, A-B measurements): which tcgen05 launches run the LAST token (the class token of N = 2^k + 1 tokens) on the
+ * CUDA-core side warps instead of a query tile / key block of its own (csrc/attn_tc.cu, "the odd token").  forward: 0 / 1 (N = 128 k + 1 > 128);
+ * backward_large / backward_small (N = 64 k + 1 above / up to 128 tokens): bit 0 = as a query, bit 1 = as a key.  A negative value restores
+ * the built-in choice (1, 3, 0).  Every combination computes the same result. */
+int vsx_attn_odd_token_modes(int forward, int backward_large, int backward_small);
 
 /* ----------------------------------------------------------------------------------------------------
  * One half of a transformer Block in one call (bf16 training path) -- replaces Block.forward's

@@ -322,6 +322,50 @@ def test_attention_tcgen05_persistent(ops, B, N, H, Hk, D):
     assert rel(db_t, db_r) < 5e-3
 
 
+@pytest.fixture
+def odd_modes():
+    from vit_search_b200 import _lib
+
+    def force(f, b, s):
+        _lib.check(_lib.lib().vsx_attn_odd_token_modes(f, b, s))
+    yield force
+    force(-1, -1, -1)
+
+
+@pytest.mark.parametrize('modes', [(0, 0, 0), (1, 1, 1), (1, 2, 2), (1, 3, 3)])
+@pytest.mark.parametrize('B,N,H,Hk,D', [(70, 257, 4, 3, 64), (150, 65, 8, 5, 64), (40, 257, 6, 6, 32), (64, 65, 12, 10, 48), (20, 129, 2, 2, 64)])
+def test_attention_odd_token_modes(ops, odd_modes, modes, B, N, H, Hk, D):
+    """The class token (the LAST of N = 2^k + 1 tokens) on the CUDA-core side warps of the tcgen05 kernels (csrc/attn_tc.cu, "the odd
+    token"): every combination -- off, as a query, as a key, both -- against the fp32-math kernel, with more (sample, head) pairs than
+    SMs so that the side warps run through their double-buffered side data and barrier phases several times.  The model uses (1, 3, 0)."""
+    odd_modes(*modes)
+    g = torch.Generator().manual_seed(B + N + H)
+    qkv = (torch.randn(B * N, 3 * H * D, generator=g) * 1.2).to(torch.bfloat16).cuda()
+    do = torch.randn(B * N, H * D, generator=g).to(torch.bfloat16).cuda()
+    res = {}
+    for name, impl in (('ref', ops.ATTN_FP32), ('tc', ops.ATTN_TCGEN05)):
+        o = torch.full((B * N, H * D), float('nan'), device='cuda', dtype=torch.bfloat16)
+        lse = torch.zeros(B, H, N, device='cuda')
+        ops.attn_fwd(qkv, o, lse, B, N, H, D, Hk, D ** -0.5, impl=impl)
+        dq = torch.full((B * N, 3 * H * D), float('nan'), device='cuda', dtype=torch.bfloat16)
+        db = torch.zeros(3 * H * D, device='cuda')
+        ops.attn_bwd(qkv, res['ref'][0] if name == 'tc' else o, do, res['ref'][1] if name == 'tc' else lse, dq, B, N, H, D, Hk, D ** -0.5,
+                     impl=impl, dbias=db)
+        res[name] = (o, lse, dq, db)
+    torch.cuda.synchronize()
+    (o_r, lse_r, dq_r, db_r), (o_t, lse_t, dq_t, db_t) = res['ref'], res['tc']
+    assert torch.all(o_t.view(B, N, H, D)[:, :, Hk:] == 0) and torch.all(dq_t.view(B, N, 3, H, D)[:, :, :, Hk:] == 0)
+    assert rel(o_t, o_r) < 8e-3 and rel(lse_t[:, :Hk], lse_r[:, :Hk]) < 1e-5
+    # the odd token's own rows separately: they are a 1 / N share of the tensors above
+    assert rel(o_t.view(B, N, H * D)[:, -1], o_r.view(B, N, H * D)[:, -1]) < 8e-3
+    assert rel(lse_t[:, :Hk, -1], lse_r[:, :Hk, -1]) < 1e-5
+    for i, nm in enumerate('qkv'):
+        a, b = dq_t.view(B, N, 3, H, D)[:, :, i], dq_r.view(B, N, 3, H, D)[:, :, i]
+        assert rel(a, b) < 1.5e-2, nm
+        assert rel(a[:, -1], b[:, -1]) < 1.5e-2, nm + ' (odd token)'
+    assert rel(db_t, db_r) < 5e-3
+
+
 # ---------------------------------------------------------------------------------------------- direct 3x3 conv (stem)
 @pytest.fixture
 def conv_impl():

@@ -42,6 +42,7 @@ SIGNATURES = {
     'vsx_attn_fwd_segs': [_p, _p, _p, _i, _i, _i, _i, _i, _p, _f, _i, _p],
     'vsx_attn_bwd_segs': [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _f, _i, _p, _p],
     'vsx_attn_debug_buffer': [_p],
+    'vsx_attn_odd_token_modes': [_i, _i, _i],
     'vsx_gemm_force_tile_rows': [_i],
     'vsx_gemm_force_cta_group': [_i],
     'vsx_gemm_grouped': [_p, _i, _p],

@@ -17,6 +17,7 @@ int attn_bwd_tc(const void* qkv, const void* o, const void* d_o, const float* ls
                 float* dbias, cudaStream_t st, const vsx_sample_segments* sg = nullptr);
 bool attn_tc_supported(int N, int D);
 void attn_set_debug(long long* p);
+void attn_set_odd_modes(int f, int b, int s);
 }  // namespace vsx
 
 using namespace vsx;
@@ -141,6 +142,11 @@ extern "C" int vsx_attn_bwd_segs(const void* qkv, const void* o, const void* d_o
 }
 
 /* Development aid (tools/attn_timeline.py): device buffer of 64 x 8 clock64 stamps written by CTA 0 of the tcgen05 backward kernel. */
+extern "C" int vsx_attn_odd_token_modes(int forward, int backward_large, int backward_small) {
+  attn_set_odd_modes(forward, backward_large, backward_small);
+  return VSX_OK;
+}
+
 extern "C" int vsx_attn_debug_buffer(void* p) {
   attn_set_debug(static_cast<long long*>(p));
   return VSX_OK;

@@ -1217,21 +1217,26 @@ static void fill_segs(AttnSegs& t, const vsx_sample_segments* sg) {
 
 static long long* g_attn_dbg = nullptr;
 void attn_set_debug(long long* p) { g_attn_dbg = p; }
+void attn_set_odd_modes(int f, int b, int s);
 
 // Which launches run the last token on the side paths.  Forward: as a query when that saves a query tile (N = 128 k + 1 > 128: 97 -> 75 us
 // at N = 257, B = 256, 4 heads).  Backward, N = 64 k + 1 > 128: both sides (8 instead of 15 blocks per pair: 189 -> 162 us; the query side
 // alone, 10 blocks: 176 us).  Backward at N = 65: off (measured: 105 us without, 108 .. 131 us with either side -- one block per pair leaves
 // the side warps no time to hide in).  VSX_ATTN_ODD = "f,b,s" overrides (development / A-B measurements): f = forward 0 / 1; b, s =
 // backward mode for N > 128 / N <= 128 (bit 0 query side, bit 1 key side).  Numbers: tools/attn_bench.py, profiles/r2_attention.md.
+static int g_odd_force[3] = {-1, -1, -1};      // vsx_attn_odd_token_modes
 static int odd_mode(int which, int dflt) {
   static int m[3] = {-1, -1, -1};
-  if (m[0] < 0) {
+  if (m[0] == -1) {
     m[0] = -2, m[1] = -2, m[2] = -2;
     const char* e = getenv("VSX_ATTN_ODD");
     if (e != nullptr) sscanf(e, "%d,%d,%d", &m[0], &m[1], &m[2]);
   }
+  if (g_odd_force[which] >= 0) return g_odd_force[which] & 3;
   return m[which] >= 0 ? m[which] & 3 : dflt;
 }
+
+void attn_set_odd_modes(int f, int b, int s) { g_odd_force[0] = f, g_odd_force[1] = b, g_odd_force[2] = s; }
 
 bool attn_tc_supported(int N, int D) { return (D == 64 || D == 48 || D == 32) && N >= 1 && N <= ATT_MAX_N; }
 
