@@ -10,6 +10,8 @@
 
 #include <string.h>
 
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace vsx {
@@ -421,7 +423,9 @@ int ln_fwd_dispatch(const float* x, long ldx, const float* gamma, const float* b
   if (seg_ok && rps <= 0 && keep % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
     const size_t slot = ((size_t)keep * 4 + 127) & ~(size_t)127;
     const size_t smem = slot * 2 * LN_WARPS;
-    const int gridb = ln_grid(rows, 4);
+    // CTAs per SM: 4 -> 8 (register-limited to ~6 resident) measured 32.9 -> 24.2 us at stage 1 (tools/ln_bench.py), 13.30 -> 13.18 ms per train step
+    static const int fwd_per_sm = getenv("VSX_LN_FWD_PER_SM") ? atoi(getenv("VSX_LN_FWD_PER_SM")) : 8;
+    const int gridb = ln_grid(rows, fwd_per_sm);
 #define VSX_LN_FB(NV)                                                                                                            \
   case NV: {                                                                                                                     \
     static bool cfg = false;                                                                                                     \
@@ -474,7 +478,8 @@ int ln_bwd_dispatch(const void* dy, const void* dy2, long lddy, const float* x, 
   if (bulk && (((size_t)keep * 4 + (g_in != nullptr ? (size_t)C * 4 : 0) + (size_t)keep * esz + 127) & ~(size_t)127) * 2 * LN_WARPS + 4096 * (size_t)nv + 512 <= 227 * 1024) {
     const size_t slot = (((size_t)keep * 4 + (g_in != nullptr ? (size_t)C * 4 : 0) + (size_t)keep * esz) + 127) & ~(size_t)127;
     const size_t smem = slot * 2 * LN_WARPS, stat = 4096 * (size_t)nv + 512;     // dynamic row slots + the static reduction buffer
-    const int per_sm = (int)std::min<size_t>(4, (227 * 1024) / (smem + stat + 1024));
+    static const int bwd_per_sm = getenv("VSX_LN_BWD_PER_SM") ? atoi(getenv("VSX_LN_BWD_PER_SM")) : 4;
+    const int per_sm = (int)std::min<size_t>(bwd_per_sm, (227 * 1024) / (smem + stat + 1024));
     const int gridb = ln_grid(rows, per_sm < 1 ? 1 : per_sm);
 #define VSX_LN_BB(NV)                                                                                                               \
   case NV: {                                                                                                                        \
