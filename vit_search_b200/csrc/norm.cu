@@ -423,8 +423,9 @@ int ln_fwd_dispatch(const float* x, long ldx, const float* gamma, const float* b
   if (seg_ok && rps <= 0 && keep % 4 == 0 && ldx % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
     const size_t slot = ((size_t)keep * 4 + 127) & ~(size_t)127;
     const size_t smem = slot * 2 * LN_WARPS;
-    // CTAs per SM: 4 -> 8 (register-limited to ~6 resident) measured 32.9 -> 24.2 us at stage 1 (tools/ln_bench.py), 13.30 -> 13.18 ms per train step
-    static const int fwd_per_sm = getenv("VSX_LN_FWD_PER_SM") ? atoi(getenv("VSX_LN_FWD_PER_SM")) : 8;
+    // CTAs per SM: 4 -> 6 (what 40 registers per thread allow to be resident) measured 32.9 -> 24.7 us at stage 1, 14.3 -> 13.9 us at stage 2
+    // (tools/ln_bench.py), 13.30 -> 13.19 ms per train step; 8 requested CTAs are no faster and add a second wave at the small stages
+    static const int fwd_per_sm = getenv("VSX_LN_FWD_PER_SM") ? atoi(getenv("VSX_LN_FWD_PER_SM")) : 6;
     const int gridb = ln_grid(rows, fwd_per_sm);
 #define VSX_LN_FB(NV)                                                                                                            \
   case NV: {                                                                                                                     \
