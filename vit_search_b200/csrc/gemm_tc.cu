@@ -718,6 +718,10 @@ int launch(Group<G>& grp, cudaStream_t st) {
     const bool fills = 2 * tpair >= pairs;      // at least half of the SM pairs get a tile (a 256 x 128 tiling of such a problem does not fill 148 SMs either)
     cg2 = force_cg == 2 || (force_cg == 0 && g_force_mt == 0 && fills && (no_extra_padding || (max_kb >= 24 && 4 * tpair * 4 <= 2 * t256 * 5)));
     mt2 = !cg2 && g_force_mt != 1 && (g_force_mt == 2 || t256 >= num_sms());
+    // RESIDUAL with a short reduction (proj forward: K = kept heads x head dim) is bound by the latency of its fp32 residual tiles, not by
+    // operand fill: 128 x 128 single-CTA tiles (twice the CTAs per row block, 6.95 instead of 3.47 -> 4 waves at stage 1) measured 30.8 vs
+    // 43.6 us at K <= 192, 35.5 vs 46.6 us at K = 256, 42.1 vs 48.7 us at K = 384, equal at K = 512 (tools/gemm_tiles_resid.py)
+    if (EPI == VSX_EPI_RESIDUAL && force_cg == 0 && g_force_mt == 0 && max_kb <= 6) cg2 = false, mt2 = false;
   }
   int total = 0;
   for (int q = 0; q < grp.count; ++q) {
