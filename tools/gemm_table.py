@@ -25,6 +25,12 @@ t = torch.softmax(torch.randn(B, 1000, device='cuda'), -1)
 pt = t.unsqueeze(1).repeat(1, 16, 1).contiguous()
 for _ in range(3):
     step(x, t, pt)
+# VSX_GEMM_TILE=128 / 256 forces the single-CTA tile rows (with VSX_GEMM_CTA_GROUP=1), for per-shape comparisons of the three tile shapes
+if os.environ.get('VSX_GEMM_TILE'):
+    from vit_search_b200 import _lib
+    _lib.lib().vsx_gemm_force_tile_rows(int(os.environ['VSX_GEMM_TILE']))
+    for _ in range(2):
+        step(x, t, pt)
 ops.PROFILE = []
 step(x, t, pt)
 torch.cuda.synchronize()
@@ -36,11 +42,11 @@ for e0, e1, fl, key, _nbytes in ops.PROFILE:
     a[2] += fl
 EPI = ['STORE', 'GELU', 'RESID', 'GELUGRAD', 'ATOMIC']
 rows = sorted(agg.items(), key=lambda kv: -kv[1][1])
-out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out', 'gemm_table.txt')
+out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out', os.environ.get('VSX_GEMM_TABLE_OUT', 'gemm_table.txt'))
 with open(out, 'w') as f:
     tot = sum(v[1] for v in agg.values())
     f.write('total GEMM ms/step %.3f over %d launches, %.1f TFLOP/s\n' % (tot, sum(v[0] for v in agg.values()), sum(v[2] for v in agg.values()) / tot / 1e9))
     f.write('%8s %6s %8s %-8s %2s %2s %5s %4s | %4s %9s %9s %9s\n' % ('M', 'N', 'K', 'epi', 'aL', 'bL', 'n_out', 'splt', 'cnt', 'ms_total', 'us_each', 'TFLOP/s'))
     for (M, N, K, epi, al, bl, n_out, sk, terms), (cnt, ms, fl) in rows:
         f.write('%8d %6d %8d %-8s %2d %2d %5d %4d | %4d %9.3f %9.1f %9.1f\n' % (M, N, K, EPI[epi], al, bl, n_out, sk, cnt, ms, ms / cnt * 1e3, fl / ms / 1e9))
-print(open(out).read())
+print(open(out).read()[:300])
