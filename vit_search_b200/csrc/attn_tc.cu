@@ -7,20 +7,25 @@
 // touches HBM (the reference materialises [B,H,N,N] three times); masked heads are never computed.
 //
 // Both kernels are persistent (one CTA per SM walking a list of (sample, head) pairs) and warp specialised:
-//   warp 0      TMA producer: 3-D tensor maps over [B, N, features] so that rows >= N are hardware zero-filled
+//   warp 0      TMA producer: 4-D tensor maps [B][N][heads][D] so that rows >= N and columns >= D are hardware zero-filled
 //   warp 1      MMA issuer  : one thread issues every tcgen05.mma; tcgen05.commit publishes results / frees operand buffers
-//   warps 2..9  softmax + epilogue: thread = TMEM lane = one query (or key) row; two warps share a lane quarter and split the
-//               columns; exp2 on the SFU, P / dS written as bf16 into 128B-swizzled shared-memory atoms that the next MMA reads
+//   warps 2..9  softmax: thread = TMEM lane = one query row; two warps share a lane quarter and split the columns; exp2 on the SFU,
+//               P / dS written as bf16 into 128B-swizzled shared-memory atoms that the next MMA reads
+//   backward only: warps 10..13 epilogue (row statistics of the next pair, accumulator drains, bias-gradient column sums)
+//   odd token (below): forward warps 10..13, backward warps 14..15 = side warps on the CUDA cores
 //
 // forward, per 128-query tile:  S[128 x N] = Q K^T (TMEM) -> row max / exp2 / row sum -> P (smem) -> O[128 x 64] = P V (TMEM)
 //                               -> O / l -> global, lse = max*scale + ln(l)
-// backward, key blocks j of 96 keys (outer) x query tiles i of 128 (inner), everything accumulated in tensor memory:
-//     S = Q_i K_j^T, dP = dO_i V_j^T            (TMEM columns   0.. 95,  96..191)
-//     P = exp2(S*c - lse), dS = P o (dP - delta) (registers -> smem, bf16)
-//     dV_j += P^T dO_i,  dK_j += dS^T Q_i        (TMEM columns 192..255, 256..319; MN-major A and B operands: no transposes)
-//     dQ_i += dS K_j                             (TMEM columns 320 + 64 i .. : all query tiles stay resident, 512 columns in total)
+// backward, key blocks j of 64 keys (outer) x query tiles i of 128 (inner), everything accumulated in tensor memory:
+//     S = Q_i K_j^T, dP = dO_i V_j^T            (TMEM columns 0..63, 64..127)
+//     P = exp2(S*c - lse), dS = P o (dP - delta) (registers -> smem, bf16, double buffered)
+//     [dV_j | dK_j] += [P^T ; dS^T] [Q_i | dO_i] (ONE chain, TMEM columns 128..255: MN-major A and B operands, no transposes)
+//     dQ_i += dS K_j                             (TMEM columns 256 + 64 i: all query tiles stay resident)
 //   the qkv-bias gradient (column sums of dQ, dK, dV) is reduced with a shuffle butterfly into shared memory and flushed once per CTA
 //   (every CTA works on ONE head).
+// The odd token: N = 2^k + 1 tokens (257, 65) leave one token over after tiles of 128 queries x 64 keys; it can run on side warps instead of
+// costing a query tile and a key block of its own (section "the odd token" below; then [dV|dK] is double buffered at TMEM columns 128..383
+// and the two dQ tiles sit at 384..511).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
