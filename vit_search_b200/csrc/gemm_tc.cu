@@ -52,7 +52,10 @@ constexpr int EPI0 = 3;                 // warp 0 TMA producer, warp 1 MMA issue
 constexpr int GEMM_THREADS = (EPI0 + EPI_WARPS) * 32;
 constexpr int MAX_STAGES = 5;
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int SMEM_MISC_BASE = 1024 /*align*/ + 256 /*barriers, tmem slot*/;      // + two bias tiles (Plan::SMEM_MISC)
+// No alignment slack: the kernel has no static shared memory, so its dynamic shared memory starts right behind the 1 KB the system reserves
+// per block, i.e. 1024-byte aligned (declared __align__(1024) and checked at run time).  The 1 KB this frees is what a third operand stage of
+// the GELU pair launches and a fifth of the RESIDUAL pair launches were short of.
+constexpr int SMEM_MISC_BASE = 256 /*barriers, tmem slot*/;      // + two bias tiles (Plan::SMEM_MISC)
 
 constexpr int COLACC_MAX = 3072;      // widest output whose bias-gradient column sums are accumulated in shared memory
 constexpr int MAX_TERMS = 6;
@@ -220,10 +223,13 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   constexpr int BOXC = 128 / (int)sizeof(OutT);     // columns per 128-byte box row
   constexpr int NBOX = BN / BOXC;                   // boxes per output tile
   pdl_launch_dependents();
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw = smem_u32(smem_raw);
-  const uint32_t base = (raw + 1023u) & ~1023u;     // 128B-swizzle atoms need 1024-byte alignment
-  uint8_t* smem = smem_raw + (base - raw);
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw);         // 128B-swizzle atoms need 1024-byte alignment
+  if ((base & 1023u) != 0u) {
+    if (threadIdx.x == 0) printf("vsx: gemm_tc_kernel: dynamic shared memory is not 1024-byte aligned (0x%x)\n", base);
+    __trap();
+  }
+  uint8_t* smem = smem_raw;
   const uint32_t ring = base, stg = base + STAGES * STAGE_BYTES;
   uint8_t* stg_g = smem + STAGES * STAGE_BYTES;
   const uint32_t bar0 = stg + NBUF * P::TILE_BYTES;
@@ -237,7 +243,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
   auto staged_bar = [&](int b) { return bar0 + 8u * (2 * MAX_STAGES + 6 + b); };
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(misc + 8 * (2 * MAX_STAGES + 8));
   float* bias_s = reinterpret_cast<float*>(misc + 256);   // [2][TILE_N]
-  float* colacc = reinterpret_cast<float*>(misc + P::SMEM_MISC - 1024);   // [COLACC_MAX] when P::COLACC != 0 (after the 1 KB alignment slack)
+  float* colacc = reinterpret_cast<float*>(misc + P::SMEM_MISC);          // [COLACC_MAX] when P::COLACC != 0
   const bool use_colacc = P::COLACC != 0 && grp.colacc_n > 0;
   long long* const dbg = grp.args[0].dbg;
 
@@ -718,10 +724,11 @@ int launch(Group<G>& grp, cudaStream_t st) {
     const bool fills = 2 * tpair >= pairs;      // at least half of the SM pairs get a tile (a 256 x 128 tiling of such a problem does not fill 148 SMs either)
     cg2 = force_cg == 2 || (force_cg == 0 && g_force_mt == 0 && fills && (no_extra_padding || (max_kb >= 24 && 4 * tpair * 4 <= 2 * t256 * 5)));
     mt2 = !cg2 && g_force_mt != 1 && (g_force_mt == 2 || t256 >= num_sms());
-    // RESIDUAL with a short reduction (proj forward: K = kept heads x head dim) is bound by the latency of its fp32 residual tiles, not by
-    // operand fill: 128 x 128 single-CTA tiles (twice the CTAs per row block, 6.95 instead of 3.47 -> 4 waves at stage 1) measured 30.8 vs
-    // 43.6 us at K <= 192, 35.5 vs 46.6 us at K = 256, 42.1 vs 48.7 us at K = 384, equal at K = 512 (tools/gemm_tiles_resid.py)
-    if (EPI == VSX_EPI_RESIDUAL && force_cg == 0 && g_force_mt == 0 && max_kb <= 6) cg2 = false, mt2 = false;
+    // RESIDUAL with a very short reduction at stage 1 (proj forward with few kept heads: K <= 192) is bound by the latency of its fp32
+    // residual tiles: 128 x 128 single-CTA tiles (6.95 instead of 3.47 -> 4 waves) measured 30.3 / 29.8 / 30.8 us against 31.0 / 31.8 / 33.2 us
+    // on pairs at K = 64 / 128 / 192; from K = 256 on (and at the smaller stages) the pairs win since they double buffer their staging tile
+    // (34.9 vs 35.5 us at K = 256, 37.9 vs 42.2 us at K = 384: tools/gemm_tiles_resid.py)
+    if (EPI == VSX_EPI_RESIDUAL && force_cg == 0 && g_force_mt == 0 && max_kb <= 3 && m_sum >= 32768) cg2 = false, mt2 = false;
   }
   int total = 0;
   for (int q = 0; q < grp.count; ++q) {
