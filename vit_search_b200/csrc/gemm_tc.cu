@@ -186,13 +186,15 @@ __device__ __forceinline__ float warp_colsum32(const float (&in)[32], int lane) 
 }
 
 // Per-instantiation shared-memory plan: NBUF staging tiles (epilogue output / aux input), the rest is the operand ring.
-template <int EPI, typename OutT, int MT, int CG> struct Plan {
+template <int EPI, typename OutT, int MT, int CG, bool CA> struct Plan {
   static constexpr int STAGE_BYTES = Shape<MT, CG>::STAGE_BYTES;
   static constexpr int SMEM_MISC = SMEM_MISC_BASE + 2 * Shape<MT, CG>::TILE_N * 4;
   static constexpr int TILE_BYTES = BM * BN * (int)sizeof(OutT) * (EPI == VSX_EPI_GELU ? 2 : 1);
   // per-CTA accumulator of the fused bias-gradient column sums (flushed once at the end of the persistent loop: thousands of
   // per-tile global atomics on a few hundred addresses serialise in L2 and used to dominate the GELU' dgrad GEMMs)
-  static constexpr int COLACC = (EPI == VSX_EPI_GELUGRAD || EPI == VSX_EPI_STORE) ? COLACC_MAX * 4 : 0;
+  // (CA: only the instantiations launched WITH fused column sums reserve it -- 12 KB are the difference between four and five operand
+  // stages for the bf16 STORE pair launches, which are bound by operand latency at K <= 256)
+  static constexpr int COLACC = (CA && (EPI == VSX_EPI_GELUGRAD || EPI == VSX_EPI_STORE)) ? COLACC_MAX * 4 : 0;
   // two staging tiles when at least three operand stages still fit (the ring has to cover the L2 latency: ~100 KB in flight)
   // GELU (two output tiles per unit) and RESIDUAL (fp32 tile in, fp32 tile out): double buffering the 64 KB staging tile matters
   // more than ring depth (measured: GELU 88 -> 76 us at 65792 x 768 x 224 with two stages + two staging tiles)
@@ -212,9 +214,9 @@ template <int EPI, typename OutT, int MT, int CG> struct Plan {
 //                       later TMA-stores / reduce-adds the staged result; staging is double buffered
 //   warps 3+ epilogue : TMEM -> registers -> fused math -> swizzled staging tile
 // so the loads of tile i+1, the MMAs of tile i+1 and the stores of tile i-1 overlap the epilogue of tile i.
-template <int EPI, typename OutT, int MT, int G, int CG>
+template <int EPI, typename OutT, int MT, int G, int CG, bool CA>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ Group<G> grp) {
-  using P = Plan<EPI, OutT, MT, CG>;
+  using P = Plan<EPI, OutT, MT, CG, CA>;
   using S = Shape<MT, CG>;
   constexpr int STAGES = P::STAGES, NBUF = P::NBUF;
   constexpr int STAGE_BYTES = P::STAGE_BYTES, STAGE_A = S::STAGE_A, TMEM_COLS = S::TMEM_COLS;
@@ -638,10 +640,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const __grid_c
 
 constexpr int MAX_GROUP = 4, MAX_GROUP_WIDE = 16;
 
-template <int EPI, typename OutT, int MT, int G, int CG>
-int launch_g(const Group<G>& grp, cudaStream_t st) {
-  using P = Plan<EPI, OutT, MT, CG>;
-  auto kern = gemm_tc_kernel<EPI, OutT, MT, G, CG>;
+template <int EPI, typename OutT, int MT, int G, int CG, bool CA>
+int launch_ca(const Group<G>& grp, cudaStream_t st) {
+  using P = Plan<EPI, OutT, MT, CG, CA>;
+  auto kern = gemm_tc_kernel<EPI, OutT, MT, G, CG, CA>;
   static bool configured = false;   // benign race: attribute set is idempotent
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, P::SMEM);
@@ -675,6 +677,13 @@ int launch_g(const Group<G>& grp, cudaStream_t st) {
     return VSX_ERR_CUDA;
   }
   return check_launch("vsx_gemm");
+}
+
+// with / without the shared-memory accumulator of the fused column sums (only STORE and GELUGRAD launches can have one)
+template <int EPI, typename OutT, int MT, int G, int CG>
+int launch_g(const Group<G>& grp, cudaStream_t st) {
+  if ((EPI == VSX_EPI_GELUGRAD || EPI == VSX_EPI_STORE) && grp.colacc_n > 0) return launch_ca<EPI, OutT, MT, G, CG, true>(grp, st);
+  return launch_ca<EPI, OutT, MT, G, CG, false>(grp, st);
 }
 
 // Tile shape and reduction splits for a list of problems that run in one launch.
