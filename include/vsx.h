@@ -206,7 +206,9 @@ typedef struct vsx_half_block_grad {
   void* d_act1;              /* bf16 scratch: dqkv [.., 3*H*D] | du [.., hidden] */
   void* d_act2;              /* bf16 scratch: d_o [.., H*D] (attention only) */
   float *d_ln_w, *d_ln_b, *d_w1, *d_b1, *d_w2, *d_b2;   /* fp32 parameter gradients, ACCUMULATED into (zero them once per step) */
-  /* Optional fusion across consecutive half blocks (pre-norm, residual calls whose segments are all active; all zero / NULL = off).
+  /* Optional fusion across consecutive half blocks (pre-norm, residual calls; all zero / NULL = off).  Segments that drop the layer
+   * (active == 0) take part: a dropped segment of THIS call gets its rows of next_df from a cast of the passed-through gradient, a
+   * dropped segment of the consuming call is left untouched.
    * df_ready != 0: `df` already holds the scaled / masked gradient of the branch output and d_b2 its column sums -- they were written by
    * the call that produced g_out (its next_* fields) -- so the cast pass over g_out is skipped.
    * next_df != NULL: the LayerNorm backward of THIS call also writes next_df = bf16(next_row_scale[next_scale_off + sample] * g_in) masked

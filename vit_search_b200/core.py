@@ -546,11 +546,17 @@ def _fusable(meta):
 
 
 def _fusable_pair(consumer, producer):
-    """The LayerNorm backward of `producer` (the later half block) may write the bf16 gradient copy `consumer` (the earlier one) starts
-    from: both pre-norm + residual, every segment active, and identical sample ranges."""
+    """The backward of `producer` (the later half block) may write the bf16 gradient copy `consumer` (the earlier one) starts from:
+    both pre-norm + residual with identical sample ranges.  Segments that drop the layer take part (vsx_half_block_bwd: a dropped
+    producer segment casts the passed-through gradient, a dropped consumer segment is left alone); with several segments the producer
+    needs at least two active ones (its one-launch LayerNorm backward carries the per-segment extents of the cast)."""
     for m in (consumer, producer):
-        if not (m.residual and m.pre_norm and 1 <= len(m.segs) <= 8 and all(s.active for s in m.segs)):
+        if not (m.residual and m.pre_norm and 1 <= len(m.segs) <= 8 and all(s.b1 > s.b0 for s in m.segs)):
             return False
+    if not any(s.active for s in consumer.segs):
+        return False
+    if len(producer.segs) == 1 and not (producer.segs[0].active and consumer.segs[0].active):
+        return False
     return [(s.b0, s.b1) for s in consumer.segs] == [(s.b0, s.b1) for s in producer.segs]
 
 

@@ -235,9 +235,14 @@ extern "C" int vsx_half_block_bwd(const vsx_half_block_grad* b, void* stream) {
   if (b->df_ready || b->next_df != nullptr) {
     bool ok = h->pre_norm && h->residual && h->num_segments >= 1 && h->num_segments <= VSX_MAX_SEGMENTS && h->segments[0].b0 == 0 &&
               h->segments[h->num_segments - 1].b1 == h->batch && (h->num_segments == 1 || b->next_df == nullptr || b->next_segments != nullptr);
-    for (int i = 0; ok && i < h->num_segments; ++i) ok = h->segments[i].active && h->segments[i].b1 > h->segments[i].b0;
-    VSX_REQUIRE(ok, "vsx_half_block_bwd: df_ready / next_df need pre_norm, residual and active segments covering the batch (next_segments for several)");
+    for (int i = 0; ok && i < h->num_segments; ++i) ok = h->segments[i].b1 > h->segments[i].b0;
+    VSX_REQUIRE(ok, "vsx_half_block_bwd: df_ready / next_df need pre_norm, residual and non-empty segments covering the batch (next_segments for several)");
   }
+  // extent of the CONSUMING half block's cast for this call's segment si (0: the consumer drops its layer for these samples)
+  auto next_keep_of = [&](int si) -> int {
+    if (b->next_segments == nullptr) return b->next_keep;
+    return b->next_segments[si].active ? b->next_segments[si].out_keep : 0;
+  };
   // phase 1: dropped layers pass the gradient through; gradient of the branch output of every active segment: drop-path scale,
   // output mask, cast -- its column sums are the bias gradient of proj / fc2
   vsx_row_segments tab_out, tab_in;
@@ -253,6 +258,10 @@ extern "C" int vsx_half_block_bwd(const vsx_half_block_grad* b, void* stream) {
     if (rows <= 0) continue;
     if (!s.active) {
       HB_CHECK(passthrough(b->g_out + r0 * C, b->g_in + r0 * C, (long)rows * C, h->residual != 0, stream));
+      // no LayerNorm backward runs on these rows: the cast the consuming half block starts from is made here, from the passed-through rows
+      if (b->next_df != nullptr && next_keep_of(si) > 0)
+        HB_CHECK(vsx_scale_mask_cast(b->g_out + r0 * C, C, b->next_row_scale != nullptr ? b->next_row_scale + b->next_scale_off + s.b0 : nullptr, N,
+                                     next_keep_of(si), B16(b->next_df) + r0 * C, VSX_BF16, C, rows, C, b->next_d_b2, stream));
       continue;
     }
     const int ck = h->residual ? s.out_keep : C;
@@ -351,7 +360,7 @@ extern "C" int vsx_half_block_bwd(const vsx_half_block_grad* b, void* stream) {
   }
   if (one_ln) {
     if (b->next_df != nullptr) {        // the cast of the consuming half block rides on this LayerNorm backward, segment by segment
-      for (int i = 0; i < h->num_segments; ++i) tab_in.keep2[i] = b->next_segments[i].out_keep;
+      for (int i = 0; i < h->num_segments; ++i) tab_in.keep2[i] = next_keep_of(i);
       HB_CHECK(vsx_masked_ln_bwd_segs(b->dxn, VSX_BF16, C, h->x, C, h->mean, h->rstd, h->ln_w, h->residual ? b->g_out : nullptr, b->g_in, C, b->d_ln_w,
                                       b->d_ln_b, h->batch * N, C, &tab_in, b->next_df, C,
                                       b->next_row_scale != nullptr ? b->next_row_scale + b->next_scale_off : nullptr, N, b->next_d_b2, stream));
@@ -360,12 +369,12 @@ extern "C" int vsx_half_block_bwd(const vsx_half_block_grad* b, void* stream) {
                                     h->batch * N, C, &tab_in, nullptr, C, nullptr, 0, nullptr, stream));
   } else if (h->pre_norm) {
     HB_CHECK(for_active([&](const SegView& v) -> int {
-      if (b->next_df != nullptr)
+      if (b->next_df != nullptr && next_keep_of((int)(v.s - h->segments)) > 0)
         return vsx_masked_ln_bwd_cast(B16(b->dxn) + v.r0 * C, VSX_BF16, C, h->x + v.r0 * C, C, h->mean + v.r0, h->rstd + v.r0, h->ln_w,
                                       h->residual ? b->g_out + v.r0 * C : nullptr, b->g_in + v.r0 * C, C, b->d_ln_w, b->d_ln_b, v.rows, C,
                                       v.s->embed_keep, B16(b->next_df) + v.r0 * C, C,
-                                      b->next_row_scale != nullptr ? b->next_row_scale + b->next_scale_off + v.s->b0 : nullptr, N, b->next_keep,
-                                      b->next_d_b2, stream);
+                                      b->next_row_scale != nullptr ? b->next_row_scale + b->next_scale_off + v.s->b0 : nullptr, N,
+                                      next_keep_of((int)(v.s - h->segments)), b->next_d_b2, stream);
       return vsx_masked_ln_bwd(B16(b->dxn) + v.r0 * C, nullptr, VSX_BF16, C, h->x + v.r0 * C, C, h->mean + v.r0, h->rstd + v.r0, h->ln_w,
                                h->residual ? b->g_out + v.r0 * C : nullptr, b->g_in + v.r0 * C, C, b->d_ln_w, b->d_ln_b, v.rows, C, v.s->embed_keep, 0, 0,
                                stream);

@@ -669,7 +669,7 @@ extern "C" int vsx_masked_ln_bwd_segs(const void* dy, int dtype, long lddy, cons
   }
   if (cast_out != nullptr && !done) {                 // the cast did not ride on the LayerNorm backward: separate pass per segment
     for (int i = 0, r0 = 0; i < segs->count; r0 = segs->row_end[i], ++i) {
-      if (segs->keep[i] == 0 || segs->row_end[i] == r0) continue;
+      if (segs->keep[i] == 0 || segs->keep2[i] == 0 || segs->row_end[i] == r0) continue;      // keep2 == 0: the consumer drops the layer there
       rc = vsx_scale_mask_cast(g_out + (long)r0 * ldg, ldg, cast_scale != nullptr ? cast_scale + r0 / rps : nullptr, rps, segs->keep2[i],
                                static_cast<uint8_t*>(cast_out) + (size_t)r0 * ld_cast * es, dtype, ld_cast, segs->row_end[i] - r0, C, cast_colsum, stream);
       if (rc) return rc;
